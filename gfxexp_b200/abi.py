@@ -1,0 +1,234 @@
+"""ctypes mirror of include/gfxb200.h (the C ABI) — PODs, enums and the library loader.
+
+The Python host side plays the role the reference's C++ hosts play (restir_di_main.cpp etc.):
+it owns scene arrays, fills the per-frame parameter block and calls the launch entry points.
+There is no Python fallback: if libgfxb200.so is missing, loading raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgfxb200.so")
+
+c_f = C.c_float
+c_u32 = C.c_uint32
+
+
+class GfxMeshDesc(C.Structure):
+    _fields_ = [("positions", C.POINTER(c_f)), ("normals", C.POINTER(c_f)), ("tangents", C.POINTER(c_f)),
+                ("texcoords", C.POINTER(c_f)), ("triangles", C.POINTER(c_u32)),
+                ("numVertices", c_u32), ("numTriangles", c_u32), ("materialSlot", c_u32), ("reserved", c_u32)]
+
+
+class GfxMaterialDesc(C.Structure):
+    _fields_ = [("p0", c_f * 3), ("p2", c_f), ("p1", c_f * 3), ("bsdfType", c_u32),
+                ("emittance", c_f * 3), ("hasEmittance", c_u32)]
+
+
+class GfxInstanceDesc(C.Structure):
+    _fields_ = [("transform", c_f * 12), ("curToPrevTransform", c_f * 12), ("normalMatrix", c_f * 9),
+                ("uniformScale", c_f), ("firstMeshSlot", c_u32), ("numMeshSlots", c_u32)]
+
+
+class GfxSceneDesc(C.Structure):
+    _fields_ = [("meshes", C.POINTER(GfxMeshDesc)), ("materials", C.POINTER(GfxMaterialDesc)),
+                ("instances", C.POINTER(GfxInstanceDesc)), ("instanceMeshSlots", C.POINTER(c_u32)),
+                ("numMeshes", c_u32), ("numMaterials", c_u32), ("numInstances", c_u32),
+                ("numInstanceMeshSlots", c_u32)]
+
+
+class GfxBvhInfo(C.Structure):
+    _fields_ = [("numNodes", c_u32), ("numPrimRefs", c_u32), ("numTriangles", c_u32), ("numGeoms", c_u32),
+                ("sceneMin", c_f * 3), ("sceneMax", c_f * 3)]
+
+
+class GfxCamera(C.Structure):
+    _fields_ = [("aspect", c_f), ("fovY", c_f), ("position", c_f * 3), ("orientation", c_f * 9)]
+
+
+class GfxFrameParams(C.Structure):
+    _fields_ = [("camera", GfxCamera), ("prevCamera", GfxCamera),
+                ("numAccumFrames", c_u32), ("frameIndex", c_u32), ("bufferIndex", c_u32),
+                ("spatialNeighborRadius", c_f),
+                ("log2NumCandidateSamples", c_u32), ("numSpatialNeighbors", c_u32),
+                ("useLowDiscrepancyNeighbors", c_u32), ("reuseVisibility", c_u32),
+                ("enableTemporalReuse", c_u32), ("enableSpatialReuse", c_u32),
+                ("useUnbiasedEstimator", c_u32), ("resetFlowBuffer", c_u32), ("enableJittering", c_u32),
+                ("currentReservoirIndex", c_u32), ("spatialNeighborBaseIndex", c_u32),
+                ("tileOriginY", c_u32), ("tileRows", c_u32)]
+
+
+NODE_DTYPE = np.dtype([("quantBoxOrigin", np.float32, 3), ("quantBoxExpScale", np.uint8, 3),
+                       ("internalMask", np.uint8), ("intNodeChildBaseIndex", np.uint32),
+                       ("leafBaseIndex", np.uint32), ("childMetas", np.uint8, 8),
+                       ("childQMin", np.uint8, (3, 8)), ("childQMax", np.uint8, (3, 8))])
+TRI_DTYPE = np.dtype([("pA", np.float32, 3), ("pB", np.float32, 3), ("pC", np.float32, 3),
+                      ("geomIndex", np.uint32), ("primIndex", np.uint32), ("padding", np.uint32)])
+HIT_DTYPE = np.dtype([("dist", np.float32), ("instIndex", np.uint32), ("instUserData", np.uint32),
+                      ("geomIndex", np.uint32), ("primIndex", np.uint32),
+                      ("bcA", np.float32), ("bcB", np.float32), ("bcC", np.float32)])
+RAY_DTYPE = np.dtype([("org", np.float32, 3), ("tmin", np.float32), ("dir", np.float32, 3), ("tmax", np.float32)])
+assert NODE_DTYPE.itemsize == 80 and TRI_DTYPE.itemsize == 48 and HIT_DTYPE.itemsize == 32 and RAY_DTYPE.itemsize == 32
+
+# enums
+TRACE_CLOSEST, TRACE_ANY = 0, 1
+(RESTIR_INITIAL_RIS, RESTIR_INITIAL_AND_TEMPORAL_BIASED, RESTIR_INITIAL_AND_TEMPORAL_UNBIASED,
+ RESTIR_SPATIAL_BIASED, RESTIR_SPATIAL_UNBIASED, RESTIR_SHADING) = range(6)
+(SVGF_TEMPORAL_ACCUMULATE, SVGF_ESTIMATE_VARIANCE, SVGF_ATROUS, SVGF_MODULATE_TAA) = range(4)
+(BUF_GBUFFER0, BUF_GBUFFER1, BUF_GBUFFER2, BUF_GBUFFER3, BUF_RNG, BUF_RESERVOIR, BUF_RESERVOIR_INFO,
+ BUF_BEAUTY_ACCUM, BUF_ALBEDO_ACCUM, BUF_NORMAL_ACCUM, BUF_SVGF_LIGHTING_VARIANCE, BUF_SVGF_FINAL) = range(12)
+
+# logical per-pixel layout of each downloadable buffer: (numpy dtype, elements per pixel, planes)
+BUFFER_LAYOUT = {
+    BUF_GBUFFER0: (np.uint32, 4, 1), BUF_GBUFFER1: (np.float32, 2, 1), BUF_GBUFFER2: (np.uint32, 4, 1),
+    BUF_GBUFFER3: (np.uint32, 4, 1), BUF_RNG: (np.uint64, 1, 1), BUF_RESERVOIR: (np.uint32, 4, 3),
+    BUF_RESERVOIR_INFO: (np.float32, 2, 1), BUF_BEAUTY_ACCUM: (np.float32, 4, 1),
+    BUF_ALBEDO_ACCUM: (np.float32, 4, 1), BUF_NORMAL_ACCUM: (np.float32, 4, 1),
+    BUF_SVGF_LIGHTING_VARIANCE: (np.float32, 4, 1), BUF_SVGF_FINAL: (np.float32, 4, 1),
+}
+
+
+def _fp(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(c_f))
+
+
+def _up(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(c_u32))
+
+
+class SceneArrays:
+    """Keeps the numpy arrays of a scenes.Scene alive and exposes them as a GfxSceneDesc."""
+
+    def __init__(self, scene):
+        self.scene = scene
+        self._keep: List[np.ndarray] = []
+        meshes = (GfxMeshDesc * len(scene.meshes))()
+        for i, m in enumerate(scene.meshes):
+            arrs = [np.ascontiguousarray(a) for a in (m.positions, m.normals, m.tangents, m.texcoords, m.triangles)]
+            self._keep.extend(arrs)
+            meshes[i].positions = _fp(arrs[0])
+            meshes[i].normals = _fp(arrs[1])
+            meshes[i].tangents = _fp(arrs[2])
+            meshes[i].texcoords = _fp(arrs[3])
+            meshes[i].triangles = _up(arrs[4])
+            meshes[i].numVertices = arrs[0].shape[0]
+            meshes[i].numTriangles = arrs[4].shape[0]
+            meshes[i].materialSlot = m.material
+        self.meshes = meshes
+        mats = np.ascontiguousarray(scene.materials)
+        assert mats.dtype.itemsize == C.sizeof(GfxMaterialDesc)
+        self._keep.append(mats)
+        self.materials = mats
+        insts = (GfxInstanceDesc * len(scene.instances))()
+        slots: List[int] = []
+        for i, inst in enumerate(scene.instances):
+            insts[i].transform = (c_f * 12)(*np.asarray(inst.transform, dtype=np.float32).reshape(-1))
+            insts[i].curToPrevTransform = (c_f * 12)(*np.asarray(inst.cur_to_prev, dtype=np.float32).reshape(-1))
+            insts[i].normalMatrix = (c_f * 9)(*np.asarray(inst.normal_matrix, dtype=np.float32).reshape(-1))
+            insts[i].uniformScale = inst.uniform_scale
+            insts[i].firstMeshSlot = len(slots)
+            insts[i].numMeshSlots = len(inst.mesh_slots)
+            slots.extend(inst.mesh_slots)
+        self.instances = insts
+        self.slots = np.asarray(slots, dtype=np.uint32)
+        self.desc = GfxSceneDesc()
+        self.desc.meshes = C.cast(meshes, C.POINTER(GfxMeshDesc))
+        self.desc.materials = mats.ctypes.data_as(C.POINTER(GfxMaterialDesc))
+        self.desc.instances = C.cast(insts, C.POINTER(GfxInstanceDesc))
+        self.desc.instanceMeshSlots = _up(self.slots)
+        self.desc.numMeshes = len(scene.meshes)
+        self.desc.numMaterials = mats.shape[0]
+        self.desc.numInstances = len(scene.instances)
+        self.desc.numInstanceMeshSlots = self.slots.shape[0]
+
+
+def make_camera(scene, width: int, height: int) -> GfxCamera:
+    cam = GfxCamera()
+    cam.aspect = float(np.float32(width) / np.float32(height))
+    cam.fovY = float(np.float32(scene.fov_y))
+    cam.position = (c_f * 3)(*np.asarray(scene.camera_position, dtype=np.float32))
+    cam.orientation = (c_f * 9)(*np.asarray(scene.camera_orientation, dtype=np.float32).reshape(-1))
+    return cam
+
+
+def default_frame_params(scene, width: int, height: int) -> GfxFrameParams:
+    """restir_di defaults: ReSTIRConfigs(5, passes, neighbours), radius 20, low-discrepancy neighbours,
+    reuseVisibility (restir_di_main.cpp:1938-1966), config 2 uses 1 spatial pass x 4 neighbours."""
+    p = GfxFrameParams()
+    p.camera = make_camera(scene, width, height)
+    p.prevCamera = make_camera(scene, width, height)
+    p.numAccumFrames = 0
+    p.frameIndex = 0
+    p.bufferIndex = 0
+    p.spatialNeighborRadius = 20.0
+    p.log2NumCandidateSamples = 5
+    p.numSpatialNeighbors = 4
+    p.useLowDiscrepancyNeighbors = 1
+    p.reuseVisibility = 1
+    p.enableTemporalReuse = 1
+    p.enableSpatialReuse = 1
+    p.useUnbiasedEstimator = 0
+    p.resetFlowBuffer = 1
+    p.enableJittering = 0
+    p.currentReservoirIndex = 0
+    p.spatialNeighborBaseIndex = 0
+    p.tileOriginY = 0
+    p.tileRows = 0
+    return p
+
+
+_DECLS = {
+    "gfx_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "gfx_ctx_destroy": (None, [C.c_void_p]),
+    "gfx_last_error_string": (C.c_char_p, [C.c_void_p]),
+    "gfx_synchronize": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "gfx_kernel_launch_count": (C.c_uint64, [C.c_void_p]),
+    "gfx_scene_upload": (C.c_int, [C.c_void_p, C.POINTER(GfxSceneDesc)]),
+    "gfx_scene_update_instances": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxInstanceDesc), c_u32]),
+    "gfx_bvh_build": (C.c_int, [C.c_void_p, C.c_void_p, c_u32]),
+    "gfx_bvh_info": (C.c_int, [C.c_void_p, C.POINTER(GfxBvhInfo)]),
+    "gfx_bvh_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gfx_bvh_import": (C.c_int, [C.c_void_p, C.c_void_p, c_u32, C.c_void_p, c_u32, C.c_void_p, c_u32]),
+    "gfx_trace_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, c_u32, C.c_void_p, C.c_int]),
+    "gfx_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, c_u32, C.c_void_p, C.c_int]),
+    "gfx_light_dist_build": (C.c_int, [C.c_void_p, C.c_void_p, c_u32]),
+    "gfx_light_dist_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(c_f)]),
+    "gfx_frame_create": (C.c_int, [C.c_void_p, c_u32, c_u32]),
+    "gfx_rng_seed": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "gfx_restir_setup_neighbor_table": (C.c_int, [C.c_void_p]),
+    "gfx_buffer_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, c_u32, C.c_void_p, C.c_size_t]),
+    "gfx_buffer_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, c_u32, C.c_void_p, C.c_size_t]),
+    "gfx_buffer_device_ptr": (C.c_void_p, [C.c_void_p, C.c_int, c_u32, C.POINTER(C.c_size_t)]),
+    "gfx_gbuffer_launch": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxFrameParams)]),
+    "gfx_restir_launch": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxFrameParams), C.c_int]),
+    "gfx_svgf_launch": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxFrameParams), C.c_int, c_u32]),
+    "gfx_nrc_create": (C.c_int, [C.c_void_p, c_u32, c_f, C.POINTER(C.c_void_p)]),
+    "gfx_nrc_destroy": (None, [C.c_void_p]),
+    "gfx_nrc_infer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_u32]),
+    "gfx_nrc_train": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_u32, C.POINTER(c_f)]),
+    "gfx_nrc_get_params": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "gfx_nrc_set_params": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "gfx_nrc_num_params": (c_u32, [C.c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_DECLS.keys())
+
+
+def load_library(path: str | None = None) -> C.CDLL:
+    """Load libgfxb200.so and attach prototypes.  Raises OSError if the CUDA extension has not been
+    built (python -c 'import __graft_entry__ as g; g.build()') — there is no fallback path."""
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise OSError(f"{path} not found: build the CUDA extension first (__graft_entry__.build()); "
+                      "gfxexp_b200 has no CPU fallback")
+    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    for name, (res, args) in _DECLS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib

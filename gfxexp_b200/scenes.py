@@ -1,0 +1,415 @@
+"""Deterministic synthetic scenes for the hot path (SURVEY.md §8d "Synthetic inputs").
+
+The reference ships no Bistro/Zero-Day assets (restir_di/restir_di_main.cpp:1-26 asks the user
+to download them), so configs 2-5 use a procedural "city block" with the same gross statistics
+as Bistro exterior: ~2.8 M triangles in ~1 000 instances of ~50 meshes, 100 materials with 1x1
+textures, ~20 000 emissive triangles in ~200 light instances.  Everything is generated with
+numpy from a fixed seed; the same arrays feed the CUDA library and the CPU oracle.
+
+Conventions mirrored from the reference host code:
+  * materials are DiffuseAndSpecular with constant (1x1 texture) parameters; colour texels are
+    UNORM8 + sRGB-decoded, scalar texels UNORM8 (common/common_host.cpp:1045-1088,1566-1585);
+  * instance transforms are T * R * S(uniform) (common/common_host.cpp:2582-2656), normalMatrix =
+    transpose(inverse(upper-left 3x3)) (:2635), curToPrevTransform = identity for static scenes
+    (:2634).
+"""
+from __future__ import annotations
+
+import dataclasses
+import math
+from typing import List
+
+import numpy as np
+
+F32 = np.float32
+
+
+@dataclasses.dataclass
+class Mesh:
+    positions: np.ndarray  # [V,3] f32
+    normals: np.ndarray    # [V,3] f32
+    tangents: np.ndarray   # [V,3] f32
+    texcoords: np.ndarray  # [V,2] f32
+    triangles: np.ndarray  # [T,3] u32
+    material: int
+
+
+@dataclasses.dataclass
+class Instance:
+    transform: np.ndarray        # [3,4] f32
+    cur_to_prev: np.ndarray      # [3,4] f32
+    normal_matrix: np.ndarray    # [3,3] f32
+    uniform_scale: float
+    mesh_slots: List[int]
+
+
+@dataclasses.dataclass
+class Scene:
+    meshes: List[Mesh]
+    materials: np.ndarray        # structured array, see MATERIAL_DTYPE
+    instances: List[Instance]
+    camera_position: np.ndarray  # [3]
+    camera_orientation: np.ndarray  # [3,3] row-major
+    fov_y: float
+    name: str = "scene"
+
+    @property
+    def num_triangles(self) -> int:
+        return sum(self.meshes[m].triangles.shape[0] for inst in self.instances for m in inst.mesh_slots)
+
+    @property
+    def num_emissive_triangles(self) -> int:
+        n = 0
+        for inst in self.instances:
+            for m in inst.mesh_slots:
+                if self.materials[self.meshes[m].material]["hasEmittance"]:
+                    n += self.meshes[m].triangles.shape[0]
+        return n
+
+
+MATERIAL_DTYPE = np.dtype([
+    ("p0", F32, 3), ("p2", F32), ("p1", F32, 3), ("bsdfType", np.uint32),
+    ("emittance", F32, 3), ("hasEmittance", np.uint32)])
+
+BSDF_LAMBERT, BSDF_DIFFUSE_AND_SPECULAR, BSDF_SIMPLE_PBR = 0, 1, 2
+
+
+def srgb_unorm8_to_linear(q: np.ndarray) -> np.ndarray:
+    """Texture-unit decode of an sRGB UNORM8 texel (IEC 61966-2-1 EOTF), float32 result."""
+    c = q.astype(np.float64) / 255.0
+    lin = np.where(c <= 0.04045, c / 12.92, ((c + 0.055) / 1.055) ** 2.4)
+    return lin.astype(F32)
+
+
+# --------------------------------------------------------------------------------------
+# mesh primitives
+# --------------------------------------------------------------------------------------
+def _grid_face(n: int, origin, du, dv, normal, rng: np.random.Generator | None, bump: float):
+    """(n+1)^2 vertices spanning origin + s*du + t*dv, s,t in [0,1]; 2 n^2 triangles (CCW about `normal`)."""
+    s, t = np.meshgrid(np.linspace(0.0, 1.0, n + 1), np.linspace(0.0, 1.0, n + 1), indexing="xy")
+    s = s.reshape(-1, 1)
+    t = t.reshape(-1, 1)
+    origin = np.asarray(origin, dtype=np.float64)
+    du = np.asarray(du, dtype=np.float64)
+    dv = np.asarray(dv, dtype=np.float64)
+    normal = np.asarray(normal, dtype=np.float64)
+    pos = origin + s * du + t * dv
+    if rng is not None and bump > 0.0:
+        # displace interior vertices along the normal so faces are not exactly planar
+        h = rng.uniform(-bump, bump, size=(pos.shape[0], 1))
+        interior = ((s > 0) & (s < 1) & (t > 0) & (t < 1)).astype(np.float64)
+        pos = pos + h * interior * normal
+    nrm = np.broadcast_to(normal, pos.shape).copy()
+    tan = np.broadcast_to(du / np.linalg.norm(du), pos.shape).copy()
+    uv = np.concatenate([s, t], axis=1)
+    idx = np.arange((n + 1) * (n + 1)).reshape(n + 1, n + 1)
+    a = idx[:-1, :-1].reshape(-1)
+    b = idx[:-1, 1:].reshape(-1)
+    c = idx[1:, 1:].reshape(-1)
+    d = idx[1:, :-1].reshape(-1)
+    tris = np.concatenate([np.stack([a, b, c], 1), np.stack([a, c, d], 1)], 0)
+    return pos, nrm, tan, uv, tris
+
+
+def _merge(parts, material: int) -> Mesh:
+    pos, nrm, tan, uv, tris = [], [], [], [], []
+    base = 0
+    for p, n_, t_, u, tr in parts:
+        pos.append(p)
+        nrm.append(n_)
+        tan.append(t_)
+        uv.append(u)
+        tris.append(tr + base)
+        base += p.shape[0]
+    return Mesh(np.ascontiguousarray(np.concatenate(pos), dtype=F32),
+                np.ascontiguousarray(np.concatenate(nrm), dtype=F32),
+                np.ascontiguousarray(np.concatenate(tan), dtype=F32),
+                np.ascontiguousarray(np.concatenate(uv), dtype=F32),
+                np.ascontiguousarray(np.concatenate(tris), dtype=np.uint32), material)
+
+
+def make_box(n: int, size, material: int, rng=None, bump: float = 0.0) -> Mesh:
+    """Axis-aligned box centred at the origin in x/z, sitting on y=0; each face n x n quads (12 n^2 triangles)."""
+    sx, sy, sz = size
+    hx, hz = sx * 0.5, sz * 0.5
+    faces = [
+        ((-hx, 0, hz), (sx, 0, 0), (0, sy, 0), (0, 0, 1)),     # +z
+        ((hx, 0, -hz), (-sx, 0, 0), (0, sy, 0), (0, 0, -1)),   # -z
+        ((hx, 0, hz), (0, 0, -sz), (0, sy, 0), (1, 0, 0)),     # +x
+        ((-hx, 0, -hz), (0, 0, sz), (0, sy, 0), (-1, 0, 0)),   # -x
+        ((-hx, sy, hz), (sx, 0, 0), (0, 0, -sz), (0, 1, 0)),   # +y
+        ((-hx, 0, -hz), (sx, 0, 0), (0, 0, sz), (0, -1, 0)),   # -y
+    ]
+    return _merge([_grid_face(n, o, du, dv, nn, rng, bump) for o, du, dv, nn in faces], material)
+
+
+def make_plane(n: int, size: float, material: int, rng=None, bump: float = 0.0) -> Mesh:
+    h = size * 0.5
+    return _merge([_grid_face(n, (-h, 0, h), (size, 0, 0), (0, 0, -size), (0, 1, 0), rng, bump)], material)
+
+
+def make_quad_light(size: float, material: int) -> Mesh:
+    """createRectangleLight (common/common_host.cpp:2431-2476): a quad in the xz-plane facing -y."""
+    h = size * 0.5
+    return _merge([_grid_face(1, (-h, 0, -h), (size, 0, 0), (0, 0, size), (0, -1, 0), None, 0.0)], material)
+
+
+def make_sphere(nu: int, nv: int, radius: float, material: int) -> Mesh:
+    """UV sphere, 2*nu*(nv-1) triangles."""
+    pos, nrm, tan, uv = [], [], [], []
+    for j in range(nv + 1):
+        theta = math.pi * j / nv
+        for i in range(nu + 1):
+            phi = 2.0 * math.pi * i / nu
+            d = np.array([math.sin(theta) * math.cos(phi), math.cos(theta), math.sin(theta) * math.sin(phi)])
+            pos.append(radius * d)
+            nrm.append(d)
+            tan.append(np.array([-math.sin(phi), 0.0, math.cos(phi)]))
+            uv.append((i / nu, j / nv))
+    tris = []
+    for j in range(nv):
+        for i in range(nu):
+            a = j * (nu + 1) + i
+            b = a + 1
+            c = a + nu + 1
+            d = c + 1
+            if j != 0:
+                tris.append((a, b, c))
+            if j != nv - 1:
+                tris.append((b, d, c))
+    return Mesh(np.asarray(pos, dtype=F32), np.asarray(nrm, dtype=F32), np.asarray(tan, dtype=F32),
+                np.asarray(uv, dtype=F32), np.asarray(tris, dtype=np.uint32), material)
+
+
+# --------------------------------------------------------------------------------------
+# transforms
+# --------------------------------------------------------------------------------------
+def rot_y(deg: float) -> np.ndarray:
+    a = math.radians(deg)
+    c, s = math.cos(a), math.sin(a)
+    return np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]], dtype=np.float64)
+
+
+def rot_x(deg: float) -> np.ndarray:
+    a = math.radians(deg)
+    c, s = math.cos(a), math.sin(a)
+    return np.array([[1, 0, 0], [0, c, -s], [0, s, c]], dtype=np.float64)
+
+
+def make_instance(mesh_slots, translate=(0, 0, 0), yaw_deg=0.0, scale=1.0, pitch_deg=0.0) -> Instance:
+    r = rot_y(yaw_deg) @ rot_x(pitch_deg)
+    m = np.zeros((3, 4), dtype=np.float64)
+    m[:, :3] = r * scale
+    m[:, 3] = translate
+    m32 = m.astype(F32)
+    # normalMatrix = transpose(inverse(upper-left)), evaluated in float like the reference host
+    upper = m32[:, :3].astype(np.float64)
+    nm = np.linalg.inv(upper).T.astype(F32)
+    ident = np.zeros((3, 4), dtype=F32)
+    ident[0, 0] = ident[1, 1] = ident[2, 2] = 1.0
+    return Instance(m32, ident, nm, float(F32(scale)), list(mesh_slots))
+
+
+def _random_materials(rng: np.random.Generator, count: int) -> np.ndarray:
+    mats = np.zeros(count, dtype=MATERIAL_DTYPE)
+    q_diffuse = rng.integers(30, 230, size=(count, 3), dtype=np.int64)
+    q_spec = rng.integers(5, 60, size=(count, 1), dtype=np.int64).repeat(3, axis=1)
+    q_smooth = rng.integers(20, 200, size=count, dtype=np.int64)
+    mats["p0"] = srgb_unorm8_to_linear(q_diffuse)
+    mats["p1"] = srgb_unorm8_to_linear(q_spec)
+    mats["p2"] = (q_smooth.astype(np.float64) / 255.0).astype(F32)
+    mats["bsdfType"] = BSDF_DIFFUSE_AND_SPECULAR
+    return mats
+
+
+def look_at_orientation(eye, target) -> np.ndarray:
+    """Row-major 3x3 whose columns are (right, up, forward); rays are orientation * (vw(.5-x), vh(.5-y), 1)
+    (optix_gbuffer_kernels.cu:21-27)."""
+    eye = np.asarray(eye, dtype=np.float64)
+    fwd = np.asarray(target, dtype=np.float64) - eye
+    fwd /= np.linalg.norm(fwd)
+    up = np.array([0.0, 1.0, 0.0])
+    right = np.cross(up, fwd)
+    right /= np.linalg.norm(right)
+    up2 = np.cross(fwd, right)
+    return np.stack([right, up2, fwd], axis=1).astype(F32)
+
+
+# --------------------------------------------------------------------------------------
+# scenes
+# --------------------------------------------------------------------------------------
+def city_scene(num_buildings: int = 700, building_tess=(12, 20), ground_tess: int = 256, num_lamps: int = 200,
+               num_props: int = 100, lamp_tess=(8, 6), num_building_meshes: int = 30, num_materials: int = 100,
+               seed: int = 0xB157, name: str = "city") -> Scene:
+    """Procedural city block ("Bistro-exterior-class")."""
+    rng = np.random.default_rng(seed)
+    materials = _random_materials(rng, num_materials)
+    # the last 8 materials are emitters: warm/cool street lights and coloured signs
+    num_emitters = 8
+    for k in range(num_emitters):
+        m = materials[num_materials - 1 - k]
+        m["hasEmittance"] = 1
+        tint = np.array([[1.0, 0.85, 0.6], [0.7, 0.85, 1.0], [1.0, 0.3, 0.2], [0.2, 1.0, 0.4],
+                         [0.3, 0.4, 1.0], [1.0, 1.0, 1.0], [1.0, 0.6, 0.1], [0.8, 0.2, 1.0]][k], dtype=F32)
+        m["emittance"] = tint * F32(40.0 + 10.0 * k)
+        m["p0"] = F32(0.0)
+        m["p1"] = F32(0.0)
+        m["p2"] = F32(0.3)
+    meshes: List[Mesh] = []
+    instances: List[Instance] = []
+
+    extent = 24.0 * math.sqrt(max(num_buildings, 1) / 64.0)  # half-size of the block
+    # ground
+    meshes.append(make_plane(ground_tess, 2.2 * extent, int(rng.integers(0, num_materials - num_emitters)), rng, 0.01))
+    instances.append(make_instance([0]))
+
+    # building meshes: unit-ish boxes with bumpy facades
+    building_slots = []
+    for _ in range(num_building_meshes):
+        n = int(rng.integers(building_tess[0], building_tess[1] + 1))
+        size = (float(rng.uniform(3.0, 6.0)), float(rng.uniform(4.0, 14.0)), float(rng.uniform(3.0, 6.0)))
+        mat = int(rng.integers(0, num_materials - num_emitters))
+        building_slots.append(len(meshes))
+        meshes.append(make_box(n, size, mat, rng, 0.03))
+    # street grid: buildings on a jittered lattice, leaving an avenue along z through x = 0
+    side = int(math.ceil(math.sqrt(num_buildings)))
+    pitch = 2.0 * extent / side
+    placed = 0
+    for iz in range(side):
+        for ix in range(side):
+            if placed >= num_buildings:
+                break
+            cx = -extent + (ix + 0.5) * pitch + float(rng.uniform(-0.15, 0.15)) * pitch
+            cz = -extent + (iz + 0.5) * pitch + float(rng.uniform(-0.15, 0.15)) * pitch
+            if abs(cx) < 3.5:  # the avenue
+                cx = math.copysign(3.5 + abs(cx), cx if cx != 0 else 1.0)
+            slot = building_slots[int(rng.integers(0, len(building_slots)))]
+            instances.append(make_instance([slot], (cx, 0.0, cz), float(rng.uniform(0.0, 360.0)),
+                                           float(rng.uniform(0.7, 1.3))))
+            placed += 1
+
+    # lamps: pole (box) + emissive head (sphere) share one instance -> 2 mesh slots per instance
+    lamp_variants = []
+    for k in range(4):
+        pole = len(meshes)
+        meshes.append(make_box(1, (0.12, 3.0, 0.12), int(rng.integers(0, num_materials - num_emitters))))
+        head = len(meshes)
+        hm = make_sphere(lamp_tess[0], lamp_tess[1], 0.22, num_materials - 1 - (k % 2))
+        hm.positions[:, 1] += F32(3.15)
+        meshes.append(hm)
+        lamp_variants.append([pole, head])
+    for k in range(num_lamps):
+        side_sign = -1.0 if (k % 2) else 1.0
+        z = -extent + 2.0 * extent * (k + 0.5) / max(num_lamps, 1)
+        x = side_sign * (2.6 + float(rng.uniform(0.0, 0.4)))
+        if k % 5 == 4:  # every fifth lamp sits in a side street
+            x = float(rng.uniform(-extent, extent))
+        instances.append(make_instance(lamp_variants[k % 4], (x, 0.0, z), float(rng.uniform(0, 360)), 1.0))
+
+    # emissive signs: small quads hung over the avenue, coloured emitters
+    sign_slots = []
+    for k in range(6):
+        sign_slots.append(len(meshes))
+        meshes.append(make_quad_light(0.8, num_materials - 3 - k))
+    for k in range(max(num_lamps // 8, 1)):
+        z = -extent + 2.0 * extent * (k + 0.5) / max(num_lamps // 8, 1)
+        instances.append(make_instance([sign_slots[k % 6]], (float(rng.uniform(-2.0, 2.0)), 4.5, z),
+                                       float(rng.uniform(0, 360)), float(rng.uniform(0.8, 1.5))))
+
+    # props: spheres and crates on the pavement
+    prop_slots = []
+    for k in range(6):
+        prop_slots.append(len(meshes))
+        if k % 2 == 0:
+            meshes.append(make_sphere(32, 16, 0.5, int(rng.integers(0, num_materials - num_emitters))))
+        else:
+            meshes.append(make_box(6, (0.9, 0.9, 0.9), int(rng.integers(0, num_materials - num_emitters)), rng, 0.02))
+    for k in range(num_props):
+        x = float(rng.uniform(-3.2, 3.2))
+        z = float(rng.uniform(-extent, extent))
+        slot = prop_slots[int(rng.integers(0, 6))]
+        y = 0.5 if slot in prop_slots[0::2] else 0.0
+        instances.append(make_instance([slot], (x, y, z), float(rng.uniform(0, 360)), float(rng.uniform(0.5, 1.2))))
+
+    eye = np.array([0.4, 1.7, -extent * 0.85])
+    target = np.array([0.0, 2.2, 0.0])
+    return Scene(meshes, materials, instances, eye.astype(F32), look_at_orientation(eye, target),
+                 math.radians(50.0), name)
+
+
+def bistro_class_scene() -> Scene:
+    """Config 2/4/5 scene: ~2.8 M triangles, ~1 000 instances, ~50 meshes, ~20 k emissive triangles."""
+    return city_scene(num_buildings=760, building_tess=(14, 20), ground_tess=300, num_lamps=200, num_props=120,
+                      lamp_tess=(10, 6), num_building_meshes=30, name="bistro_class")
+
+
+def small_city_scene() -> Scene:
+    """~60 k triangles: full-resolution GPU-vs-oracle parity in seconds."""
+    return city_scene(num_buildings=36, building_tess=(5, 8), ground_tess=32, num_lamps=24, num_props=12,
+                      lamp_tess=(8, 6), num_building_meshes=8, name="small_city")
+
+
+def tiny_city_scene() -> Scene:
+    """~4 k triangles: brute-force-checkable on the CPU."""
+    return city_scene(num_buildings=9, building_tess=(2, 3), ground_tess=8, num_lamps=6, num_props=4,
+                      lamp_tess=(6, 4), num_building_meshes=4, name="tiny_city")
+
+
+def load_obj(path: str):
+    """Minimal OBJ reader (v / f only, fan triangulation) for data/teapot.obj-style files."""
+    verts, faces = [], []
+    with open(path, "r") as fh:
+        for line in fh:
+            if line.startswith("v "):
+                verts.append([float(v) for v in line.split()[1:4]])
+            elif line.startswith("f "):
+                idx = [int(tok.split("/")[0]) for tok in line.split()[1:]]
+                idx = [i - 1 if i > 0 else len(verts) + i for i in idx]
+                for k in range(1, len(idx) - 1):
+                    faces.append((idx[0], idx[k], idx[k + 1]))
+    return np.asarray(verts, dtype=F32), np.asarray(faces, dtype=np.uint32)
+
+
+def mesh_from_triangles(verts: np.ndarray, faces: np.ndarray, material: int) -> Mesh:
+    """Area-weighted vertex normals (assimp GenNormals-like) and makeCoordinateSystem-style tangents."""
+    v = verts.astype(np.float64)
+    fn = np.cross(v[faces[:, 1]] - v[faces[:, 0]], v[faces[:, 2]] - v[faces[:, 0]])
+    n = np.zeros_like(v)
+    for k in range(3):
+        np.add.at(n, faces[:, k], fn)
+    ln = np.linalg.norm(n, axis=1, keepdims=True)
+    n = np.where(ln > 0, n / np.maximum(ln, 1e-30), np.array([0.0, 1.0, 0.0]))
+    sign = np.where(n[:, 2] >= 0, 1.0, -1.0)
+    a = -1.0 / (sign + n[:, 2])
+    b = n[:, 0] * n[:, 1] * a
+    t = np.stack([1 + sign * n[:, 0] * n[:, 0] * a, sign * b, -sign * n[:, 0]], axis=1)
+    uv = np.zeros((v.shape[0], 2))
+    return Mesh(np.ascontiguousarray(v, dtype=F32), np.ascontiguousarray(n, dtype=F32),
+                np.ascontiguousarray(t, dtype=F32), np.ascontiguousarray(uv, dtype=F32),
+                np.ascontiguousarray(faces, dtype=np.uint32), material)
+
+
+def teapot_like_scene(obj_path: str | None = None) -> Scene:
+    """Config 1 (path_tracing on data/teapot.obj + one rectangle light).  When the OBJ is not
+    available (the GPU box has no /root/reference) a sphere of similar size stands in."""
+    mats = np.zeros(2, dtype=MATERIAL_DTYPE)
+    mats[0]["p0"] = F32(1.0)                       # Kd 1
+    mats[0]["p1"] = F32(0.2)                       # Ks .2
+    mats[0]["p2"] = F32(math.sqrt(10.0) / 11.0)    # smoothness = sqrt(Ns)/11 (common_host.cpp:2271-2274)
+    mats[0]["bsdfType"] = BSDF_DIFFUSE_AND_SPECULAR
+    mats[1]["bsdfType"] = BSDF_DIFFUSE_AND_SPECULAR
+    mats[1]["hasEmittance"] = 1
+    mats[1]["emittance"] = F32(50.0)
+    mats[1]["p2"] = F32(0.3)
+    if obj_path is not None:
+        verts, faces = load_obj(obj_path)
+        body = mesh_from_triangles(verts, faces, 0)
+    else:
+        body = make_sphere(96, 48, 60.0, 0)
+        body.positions[:, 1] += F32(60.0)
+    light = make_quad_light(100.0, 1)
+    meshes = [body, light]
+    instances = [make_instance([0]), make_instance([1], (0.0, 200.0, 0.0))]
+    # camera: translate(0,133.3,200) * rotY(180) * rotX(25)  (nrtdsm/nrtdsm_sandbox.cpp:3137-3146)
+    ori = (rot_y(180.0) @ rot_x(25.0)).astype(F32)
+    return Scene(meshes, mats, instances, np.array([0.0, 133.3, 200.0], dtype=F32), ori, math.radians(50.0), "teapot")

@@ -1,0 +1,295 @@
+/* gfxb200.h — C ABI of the B200-native per-frame hot path (BVH build/traverse, G-buffer,
+ * ReSTIR DI, SVGF, NRC).  This is the drop-in boundary that stands where the reference's
+ * OptiX wrapper and per-app launch sites stand today:
+ *
+ *   optixu::Pipeline::launch(stream, plp, W, H, 1)        utils/optix_util.h:2149-2151
+ *   optixu::Pipeline::setRayGenerationProgram(entry)      utils/optix_util.h:2116
+ *   Scene::updateASs() -> GAS/IAS rebuild                 common/common_host.h:1027-1100
+ *   Scene::setupLightGeomDistributions / setupLightInstDistribution
+ *                                                          common/common_host.h:1102-1359
+ *   cudau::Kernel::operator() / launchWithThreadDim        utils/cuda_util.h:421-436
+ *   NeuralRadianceCache::{initialize,finalize,infer,train} neural_radiance_caching/network_interface.h:22-27
+ *
+ * Conventions: every entry point is extern "C", returns 0 on success or a negative GfxStatus,
+ * never throws; gfx_last_error_string() gives the message (the reference throws
+ * std::runtime_error from CUDADRV_CHECK/OPTIX_CHECK, utils/optix_util_private.h:66-100).
+ * `stream` is a cudaStream_t passed as void* (NULL = default stream).  Pointers marked
+ * "host" are read/written with cudaMemcpy inside the call; everything else lives in HBM
+ * owned by the context.  There is no CPU fallback: every call fails with GFX_ERR_NO_DEVICE
+ * when no sm_100 device is present.
+ */
+#ifndef GFXB200_H
+#define GFXB200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gfx_ctx gfx_ctx;
+
+typedef enum GfxStatus {
+    GFX_OK = 0,
+    GFX_ERR_INVALID_ARGUMENT = -1,
+    GFX_ERR_NO_DEVICE = -2,
+    GFX_ERR_CUDA = -3,
+    GFX_ERR_NOT_READY = -4,     /* e.g. launch before scene upload / BVH build */
+    GFX_ERR_OUT_OF_MEMORY = -5,
+    GFX_ERR_UNSUPPORTED = -6
+} GfxStatus;
+
+/* ---- scene description (host side, SoA per mesh) ------------------------------------- */
+
+/* One GeometryInstance: vertex/triangle buffers + material slot
+ * (shared::GeometryInstanceData, common/common_shared.h:1172-1186; shared::Vertex :1109-1114). */
+typedef struct GfxMeshDesc {
+    const float* positions;   /* host, 3 * numVertices */
+    const float* normals;     /* host, 3 * numVertices */
+    const float* tangents;    /* host, 3 * numVertices (Vertex::texCoord0Dir) */
+    const float* texcoords;   /* host, 2 * numVertices */
+    const uint32_t* triangles;/* host, 3 * numTriangles */
+    uint32_t numVertices;
+    uint32_t numTriangles;
+    uint32_t materialSlot;
+    uint32_t reserved;
+} GfxMeshDesc;
+
+typedef enum GfxBsdfType {
+    GFX_BSDF_LAMBERT = 0,              /* common_device.cuh:335-385   p0 = reflectance */
+    GFX_BSDF_DIFFUSE_AND_SPECULAR = 1, /* common_device.cuh:443-765   p0 = diffuse, p1 = specular F0, p2 = smoothness */
+    GFX_BSDF_SIMPLE_PBR = 2            /* common_device.cuh:767-826   p0 = baseColor, p1 = (occlusion, roughness, metallic) */
+} GfxBsdfType;
+
+/* shared::MaterialData (common/common_shared.h:1131-1170) with every texture a 1x1 texel:
+ * the fields are the texel values *after* the texture unit's UNORM8/sRGB decode. */
+typedef struct GfxMaterialDesc {
+    float p0[3];
+    float p2;
+    float p1[3];
+    uint32_t bsdfType;     /* GfxBsdfType */
+    float emittance[3];
+    uint32_t hasEmittance; /* mat.emittance != 0 */
+} GfxMaterialDesc;
+
+/* shared::InstanceData (common/common_shared.h:1241-1249). Matrices are row-major. */
+typedef struct GfxInstanceDesc {
+    float transform[12];          /* object -> world, 3x4 */
+    float curToPrevTransform[12]; /* world(cur) -> world(prev), 3x4 */
+    float normalMatrix[9];        /* transpose(inverse(upper-left 3x3)), common_host.cpp:2635 */
+    float uniformScale;
+    uint32_t firstMeshSlot;       /* range into GfxSceneDesc::instanceMeshSlots (InstanceData::geomInstSlots) */
+    uint32_t numMeshSlots;
+} GfxInstanceDesc;
+
+typedef struct GfxSceneDesc {
+    const GfxMeshDesc* meshes;
+    const GfxMaterialDesc* materials;
+    const GfxInstanceDesc* instances;
+    const uint32_t* instanceMeshSlots;
+    uint32_t numMeshes;
+    uint32_t numMaterials;
+    uint32_t numInstances;
+    uint32_t numInstanceMeshSlots;
+} GfxSceneDesc;
+
+/* ---- BVH formats (bit-identical to the reference structs) ---------------------------- */
+
+/* shared::CompressedInternalNode_T<8>, 80 B (common/common_shared.h:757-917) */
+typedef struct GfxBvhNode8 {
+    float quantBoxOrigin[3];
+    uint8_t quantBoxExpScale[3];
+    uint8_t internalMask;
+    uint32_t intNodeChildBaseIndex;
+    uint32_t leafBaseIndex;
+    uint8_t childMetas[8];
+    uint8_t childQMin[3][8]; /* Xs, Ys, Zs */
+    uint8_t childQMax[3][8];
+} GfxBvhNode8;
+
+/* shared::TriangleStorage, 48 B (common/common_shared.h:1017-1025). geomIndex enumerates
+ * (instance, mesh-slot-in-instance) pairs in instance order, as Scene flattening does. */
+typedef struct GfxTriangleStorage {
+    float pA[3], pB[3], pC[3];
+    uint32_t geomIndex;
+    uint32_t primIndex;
+    uint32_t padding;
+} GfxTriangleStorage;
+
+/* shared::HitObject, 32 B (common/common_shared.h:1065-1078) */
+typedef struct GfxHitObject {
+    float dist;
+    uint32_t instIndex;
+    uint32_t instUserData;
+    uint32_t geomIndex;
+    uint32_t primIndex;
+    float bcA, bcB, bcC;
+} GfxHitObject;
+
+/* ray record of the wavefront trace entry point: 32 B */
+typedef struct GfxRay {
+    float org[3];
+    float tmin;
+    float dir[3];
+    float tmax;
+} GfxRay;
+
+typedef struct GfxBvhInfo {
+    uint32_t numNodes;
+    uint32_t numPrimRefs;
+    uint32_t numTriangles;
+    uint32_t numGeoms;
+    float sceneMin[3];
+    float sceneMax[3];
+} GfxBvhInfo;
+
+typedef enum GfxTraceMode {
+    GFX_TRACE_CLOSEST = 0, /* bvh::traverse semantics, tie -> smaller storage index */
+    GFX_TRACE_ANY = 1      /* visibility ray: dist = 0 if anything is hit in (tmin,tmax), else tmax */
+} GfxTraceMode;
+
+/* ---- per-frame parameters ------------------------------------------------------------ */
+
+/* shared::PerspectiveCamera (restir_di/restir_di_shared.h:45-60) */
+typedef struct GfxCamera {
+    float aspect;
+    float fovY;
+    float position[3];
+    float orientation[9]; /* row-major 3x3 */
+} GfxCamera;
+
+/* shared::PerFramePipelineLaunchParameters + the per-launch bitfields of
+ * PipelineLaunchParameters (restir_di/restir_di_shared.h:243-288). */
+typedef struct GfxFrameParams {
+    GfxCamera camera;
+    GfxCamera prevCamera;
+    uint32_t numAccumFrames;
+    uint32_t frameIndex;
+    uint32_t bufferIndex;              /* G-buffer double-buffer slot (frameIndex % 2) */
+    float spatialNeighborRadius;
+    uint32_t log2NumCandidateSamples;
+    uint32_t numSpatialNeighbors;
+    uint32_t useLowDiscrepancyNeighbors;
+    uint32_t reuseVisibility;
+    uint32_t enableTemporalReuse;
+    uint32_t enableSpatialReuse;
+    uint32_t useUnbiasedEstimator;
+    uint32_t resetFlowBuffer;
+    uint32_t enableJittering;
+    uint32_t currentReservoirIndex;    /* plp.currentReservoirIndex */
+    uint32_t spatialNeighborBaseIndex; /* plp.spatialNeighborBaseIndex */
+    uint32_t tileOriginY;              /* multi-GPU: first row owned by this rank (0 on 1 GPU) */
+    uint32_t tileRows;                 /* multi-GPU: rows owned by this rank (0 = all) */
+} GfxFrameParams;
+
+/* ReSTIR DI entry points (restir_di/restir_di_main.cpp:63-74 ReSTIREntryPoint) */
+typedef enum GfxReSTIRPass {
+    GFX_RESTIR_INITIAL_RIS = 0,                 /* performInitialRIS */
+    GFX_RESTIR_INITIAL_AND_TEMPORAL_BIASED = 1, /* performInitialAndTemporalRISBiased */
+    GFX_RESTIR_INITIAL_AND_TEMPORAL_UNBIASED = 2,
+    GFX_RESTIR_SPATIAL_BIASED = 3,              /* performSpatialRISBiased */
+    GFX_RESTIR_SPATIAL_UNBIASED = 4,
+    GFX_RESTIR_SHADING = 5                      /* shading */
+} GfxReSTIRPass;
+
+/* SVGF entry points (svgf/svgf_main.cpp:2127-2172) */
+typedef enum GfxSVGFPass {
+    GFX_SVGF_TEMPORAL_ACCUMULATE = 0,
+    GFX_SVGF_ESTIMATE_VARIANCE = 1,
+    GFX_SVGF_ATROUS = 2,
+    GFX_SVGF_MODULATE_TAA = 3
+} GfxSVGFPass;
+
+/* buffers that can be read back for parity checks (logical row-major (x,y) order) */
+typedef enum GfxBufferId {
+    GFX_BUF_GBUFFER0 = 0,   /* uint32 x4 : instSlot, geomInstSlot, primIndex, qbcB | qbcC<<16 */
+    GFX_BUF_GBUFFER1 = 1,   /* float  x2 : motion vector */
+    GFX_BUF_GBUFFER2 = 2,   /* float3 position + uint32 qGeometricNormal */
+    GFX_BUF_GBUFFER3 = 3,   /* uint32 x4 : qShadingNormal, qShadingTangent, qTexCoord, matSlot */
+    GFX_BUF_RNG = 4,        /* uint64    : PCG32 state */
+    GFX_BUF_RESERVOIR = 5,  /* 12 floats : emittance3, position3, normal3, sumWeights, streamLength(u32) | atInfinity<<31, pad */
+    GFX_BUF_RESERVOIR_INFO = 6, /* float x2 : recPDFEstimate, targetDensity */
+    GFX_BUF_BEAUTY_ACCUM = 7,   /* float x4 */
+    GFX_BUF_ALBEDO_ACCUM = 8,   /* float x4 */
+    GFX_BUF_NORMAL_ACCUM = 9,   /* float x4 */
+    GFX_BUF_SVGF_LIGHTING_VARIANCE = 10, /* float x4 : noisy/filtered lighting rgb + variance */
+    GFX_BUF_SVGF_FINAL = 11     /* float x4 */
+} GfxBufferId;
+
+/* ---- context ------------------------------------------------------------------------- */
+int gfx_ctx_create(int device, gfx_ctx** out);
+void gfx_ctx_destroy(gfx_ctx* ctx);
+const char* gfx_last_error_string(gfx_ctx* ctx);
+int gfx_synchronize(gfx_ctx* ctx, void* stream);
+/* number of kernels this library has launched since the context was created */
+uint64_t gfx_kernel_launch_count(gfx_ctx* ctx);
+
+/* ---- scene, acceleration structure, light distributions ------------------------------ */
+/* replaces Scene::initialize + createTriangleMeshes/createInstance uploads
+ * (common/common_host.h:912-969, common/common_host.cpp:2178-2429,2582-2656) */
+int gfx_scene_upload(gfx_ctx* ctx, const GfxSceneDesc* scene);
+/* per-frame instance update (InstanceController::update, common/common_host.h:798-856) */
+int gfx_scene_update_instances(gfx_ctx* ctx, void* stream, const GfxInstanceDesc* instances, uint32_t numInstances);
+
+/* replaces Scene::updateASs (common/common_host.h:1027-1100): Morton-sorted LBVH over the
+ * world-space triangles of all instances, collapsed to CompressedInternalNode_T<8>. */
+int gfx_bvh_build(gfx_ctx* ctx, void* stream, uint32_t flags);
+int gfx_bvh_info(gfx_ctx* ctx, GfxBvhInfo* info);
+/* read the built BVH back in the reference layout (host buffers sized from gfx_bvh_info) */
+int gfx_bvh_export(gfx_ctx* ctx, GfxBvhNode8* nodes, uint32_t* primRefs, GfxTriangleStorage* tris);
+/* adopt a BVH built elsewhere in the reference layout (e.g. by bvh::buildGeometryBVH<8>) */
+int gfx_bvh_import(gfx_ctx* ctx, const GfxBvhNode8* nodes, uint32_t numNodes,
+                   const uint32_t* primRefs, uint32_t numPrimRefs,
+                   const GfxTriangleStorage* tris, uint32_t numTris);
+
+/* wavefront trace: bvh::traverse<8> (common/bvh_builder.cpp:1653-1663) for a batch of rays.
+ * rays/hits are DEVICE pointers in the _device variant and HOST pointers otherwise. */
+int gfx_trace_device(gfx_ctx* ctx, void* stream, const GfxRay* rays, uint32_t numRays,
+                     GfxHitObject* hits, int mode);
+int gfx_trace(gfx_ctx* ctx, void* stream, const GfxRay* rays, uint32_t numRays,
+              GfxHitObject* hits, int mode);
+
+/* replaces Scene::setupLightGeomDistributions (static part, once) and
+ * Scene::setupLightInstDistribution (per frame) + ext/cubd ExclusiveSum */
+int gfx_light_dist_build(gfx_ctx* ctx, void* stream, uint32_t bufferIndex);
+/* host read-back of the instance-level distribution for parity: weights/cdf sized numInstances */
+int gfx_light_dist_export(gfx_ctx* ctx, float* instWeights, float* instCdf, float* integral);
+
+/* ---- frame state ---------------------------------------------------------------------- */
+/* allocates G-buffers x2, reservoirs x2, rng, accumulation buffers (restir_di_main.cpp:1225-1330) */
+int gfx_frame_create(gfx_ctx* ctx, uint32_t width, uint32_t height);
+/* seeds one PCG32 per pixel, row-major, from std::mt19937_64(seed) (restir_di_main.cpp:1309-1321) */
+int gfx_rng_seed(gfx_ctx* ctx, uint64_t seed);
+/* Halton(2,3) concentric-disk neighbour table of 1024 entries (restir_di_main.cpp:1489-1542) */
+int gfx_restir_setup_neighbor_table(gfx_ctx* ctx);
+int gfx_buffer_download(gfx_ctx* ctx, void* stream, int bufferId, uint32_t index, void* host, size_t bytes);
+int gfx_buffer_upload(gfx_ctx* ctx, void* stream, int bufferId, uint32_t index, const void* host, size_t bytes);
+/* device pointer of a frame buffer (for NCCL collectives / torch views) */
+void* gfx_buffer_device_ptr(gfx_ctx* ctx, int bufferId, uint32_t index, size_t* bytes);
+
+/* ---- launches -------------------------------------------------------------------------- */
+/* replaces gBuffer.optixPipeline.launch (restir_di_main.cpp:2366; RG/CH/MS setupGBuffers) */
+int gfx_gbuffer_launch(gfx_ctx* ctx, void* stream, const GfxFrameParams* params);
+/* replaces restir.setEntryPoint(pass) + restir.optixPipeline.launch (restir_di_main.cpp:2378-2421) */
+int gfx_restir_launch(gfx_ctx* ctx, void* stream, const GfxFrameParams* params, int pass);
+/* replaces the svgf.cu kernels (svgf_main.cpp:2127-2172) */
+int gfx_svgf_launch(gfx_ctx* ctx, void* stream, const GfxFrameParams* params, int pass, uint32_t stage);
+
+/* ---- NRC network (network_interface.h:14-28) ------------------------------------------ */
+typedef struct gfx_nrc gfx_nrc;
+int gfx_nrc_create(gfx_ctx* ctx, uint32_t numHiddenLayers, float learningRate, gfx_nrc** out);
+void gfx_nrc_destroy(gfx_nrc* nrc);
+/* inputData: device float[14, numData] (column per query), predictionData: device float[3, numData];
+ * numData % 128 == 0 (network_interface.cu:141-147) */
+int gfx_nrc_infer(gfx_nrc* nrc, void* stream, const float* inputData, float* predictionData, uint32_t numData);
+int gfx_nrc_train(gfx_nrc* nrc, void* stream, const float* inputData, const float* targetData,
+                  uint32_t numData, float* lossOnHost);
+int gfx_nrc_get_params(gfx_nrc* nrc, void* hostHalfParams, size_t bytes);
+int gfx_nrc_set_params(gfx_nrc* nrc, const void* hostHalfParams, size_t bytes);
+uint32_t gfx_nrc_num_params(gfx_nrc* nrc);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GFXB200_H */

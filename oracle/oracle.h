@@ -1,0 +1,73 @@
+/* oracle/oracle.h — C API of the CPU oracle.  TEST INFRASTRUCTURE: only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
+ * liboracle.so.  The product library (libgfxb200.so) never links or calls it.
+ *
+ * The scene/parameter PODs are the ones of include/gfxb200.h (the interface spec), so one
+ * set of host arrays feeds both sides of a parity test.
+ *
+ * Parity status (also in DESIGN.md): the reference has no golden vectors for this path and
+ * cannot be built here, so this oracle is "parity unpinned" against the reference binary;
+ * it is pinned against (a) the reference's struct-size static_asserts, (b) brute-force
+ * closest-hit, (c) libm for detmath, (d) the analytic RIS expectation of
+ * restir_di/RIS_Test/ris_test.ipynb (tests/test_oracle_*.py).
+ */
+#ifndef ORACLE_H
+#define ORACLE_H
+#include "../include/gfxb200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct orc_scene orc_scene;
+typedef struct orc_frame orc_frame;
+
+typedef struct OrcBuildConfig { /* bvh::GeometryBVHBuildConfig, common/bvh_builder.h:38-44 */
+    float splittingBudget;
+    float intNodeTravCost;
+    float primIntersectCost;
+    uint32_t minNumPrimsPerLeaf;
+    uint32_t maxNumPrimsPerLeaf;
+} OrcBuildConfig;
+
+typedef struct OrcTraversalStats { /* bvh::TraversalStatistics (bvh_builder.h:79-86), summed over rays */
+    uint64_t numAabbTests;
+    uint64_t numTriTests;
+    uint64_t numIntNodes;
+    int32_t maxStackDepth;
+    uint32_t numHits;
+} OrcTraversalStats;
+
+enum { ORC_TRACE_FIRST_FOUND = 0, ORC_TRACE_CANONICAL = 1, ORC_TRACE_BRUTE_FORCE = 2, ORC_TRACE_ANY = 3 };
+
+/* scene = flattened geometries + SBVH (bvh::buildGeometryBVH<8>) + light distributions */
+orc_scene* orc_scene_create(const GfxSceneDesc* scene, const OrcBuildConfig* cfg, int numThreads);
+void orc_scene_destroy(orc_scene* s);
+double orc_scene_build_seconds(orc_scene* s);
+void orc_bvh_info(orc_scene* s, GfxBvhInfo* info);
+void orc_bvh_export(orc_scene* s, GfxBvhNode8* nodes, uint32_t* primRefs, GfxTriangleStorage* tris);
+/* replace the BVH by one given in the reference layout (e.g. exported from the GPU builder) */
+void orc_bvh_import(orc_scene* s, const GfxBvhNode8* nodes, uint32_t numNodes,
+                    const uint32_t* primRefs, uint32_t numPrimRefs,
+                    const GfxTriangleStorage* tris, uint32_t numTris);
+/* structural validation of a BVH in the reference layout: every triangle referenced at least
+ * once, every child box contains its subtree, leaf chains terminated. returns 0 if valid. */
+int orc_bvh_validate(orc_scene* s, char* msg, size_t msgLen);
+void orc_trace(orc_scene* s, const GfxRay* rays, uint32_t numRays, GfxHitObject* hits, int mode,
+               OrcTraversalStats* stats, int numThreads);
+void orc_light_dist_export(orc_scene* s, float* instWeights, float* instCdf, float* integral);
+
+orc_frame* orc_frame_create(orc_scene* s, uint32_t width, uint32_t height);
+void orc_frame_destroy(orc_frame* f);
+void orc_rng_seed(orc_frame* f, uint64_t seed);
+void orc_restir_setup_neighbor_table(orc_frame* f);
+void* orc_buffer_ptr(orc_frame* f, int bufferId, uint32_t index, size_t* bytes);
+void orc_gbuffer(orc_frame* f, const GfxFrameParams* p, int numThreads);
+void orc_restir(orc_frame* f, const GfxFrameParams* p, int pass, int numThreads);
+/* primary rays of the G-buffer pass (for the trace-only benchmarks) */
+void orc_generate_primary_rays(const GfxFrameParams* p, uint32_t width, uint32_t height, GfxRay* rays);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,178 @@
+"""ctypes binding of oracle/liboracle.so — TEST INFRASTRUCTURE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import
+this module.  The product package (gfxexp_b200) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from gfxexp_b200 import abi
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(_ROOT, "oracle")
+ORACLE_LIB = os.path.join(ORACLE_DIR, "liboracle.so")
+
+
+class OrcBuildConfig(C.Structure):
+    _fields_ = [("splittingBudget", C.c_float), ("intNodeTravCost", C.c_float), ("primIntersectCost", C.c_float),
+                ("minNumPrimsPerLeaf", C.c_uint32), ("maxNumPrimsPerLeaf", C.c_uint32)]
+
+
+class OrcTraversalStats(C.Structure):
+    _fields_ = [("numAabbTests", C.c_uint64), ("numTriTests", C.c_uint64), ("numIntNodes", C.c_uint64),
+                ("maxStackDepth", C.c_int32), ("numHits", C.c_uint32)]
+
+
+TRACE_FIRST_FOUND, TRACE_CANONICAL, TRACE_BRUTE_FORCE, TRACE_ANY = range(4)
+
+
+def reference_build_config() -> OrcBuildConfig:
+    """nrtdsm/nrtdsm_sandbox.cpp:3177-3184: budget .3, trav 1.2, isect 1.0, leaf 1..128."""
+    return OrcBuildConfig(0.3, 1.2, 1.0, 1, 128)
+
+
+def build_oracle(force: bool = False) -> str:
+    if force or not os.path.exists(ORACLE_LIB):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "-j8"], stdout=subprocess.DEVNULL)
+    return ORACLE_LIB
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build_oracle()
+        L = C.CDLL(ORACLE_LIB)
+        vp = C.c_void_p
+        L.orc_scene_create.restype = vp
+        L.orc_scene_create.argtypes = [C.POINTER(abi.GfxSceneDesc), C.POINTER(OrcBuildConfig), C.c_int]
+        L.orc_scene_destroy.argtypes = [vp]
+        L.orc_scene_build_seconds.restype = C.c_double
+        L.orc_scene_build_seconds.argtypes = [vp]
+        L.orc_bvh_info.argtypes = [vp, C.POINTER(abi.GfxBvhInfo)]
+        L.orc_bvh_export.argtypes = [vp, vp, vp, vp]
+        L.orc_bvh_import.argtypes = [vp, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32]
+        L.orc_bvh_validate.restype = C.c_int
+        L.orc_bvh_validate.argtypes = [vp, C.c_char_p, C.c_size_t]
+        L.orc_trace.argtypes = [vp, vp, C.c_uint32, vp, C.c_int, C.POINTER(OrcTraversalStats), C.c_int]
+        L.orc_light_dist_export.argtypes = [vp, vp, vp, C.POINTER(C.c_float)]
+        L.orc_frame_create.restype = vp
+        L.orc_frame_create.argtypes = [vp, C.c_uint32, C.c_uint32]
+        L.orc_frame_destroy.argtypes = [vp]
+        L.orc_rng_seed.argtypes = [vp, C.c_uint64]
+        L.orc_restir_setup_neighbor_table.argtypes = [vp]
+        L.orc_buffer_ptr.restype = vp
+        L.orc_buffer_ptr.argtypes = [vp, C.c_int, C.c_uint32, C.POINTER(C.c_size_t)]
+        L.orc_gbuffer.argtypes = [vp, C.POINTER(abi.GfxFrameParams), C.c_int]
+        L.orc_restir.argtypes = [vp, C.POINTER(abi.GfxFrameParams), C.c_int, C.c_int]
+        L.orc_generate_primary_rays.argtypes = [C.POINTER(abi.GfxFrameParams), C.c_uint32, C.c_uint32, vp]
+        _lib = L
+    return _lib
+
+
+class OracleScene:
+    def __init__(self, scene, cfg: OrcBuildConfig | None = None):
+        self.arrays = abi.SceneArrays(scene)
+        self.cfg = cfg or reference_build_config()
+        self.h = lib().orc_scene_create(C.byref(self.arrays.desc), C.byref(self.cfg), 0)
+        assert self.h
+
+    def close(self):
+        if self.h:
+            lib().orc_scene_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    @property
+    def build_seconds(self) -> float:
+        return lib().orc_scene_build_seconds(self.h)
+
+    def info(self) -> abi.GfxBvhInfo:
+        info = abi.GfxBvhInfo()
+        lib().orc_bvh_info(self.h, C.byref(info))
+        return info
+
+    def export_bvh(self):
+        info = self.info()
+        nodes = np.zeros(info.numNodes, dtype=abi.NODE_DTYPE)
+        refs = np.zeros(info.numPrimRefs, dtype=np.uint32)
+        tris = np.zeros(info.numTriangles, dtype=abi.TRI_DTYPE)
+        lib().orc_bvh_export(self.h, nodes.ctypes.data, refs.ctypes.data, tris.ctypes.data)
+        return nodes, refs, tris
+
+    def import_bvh(self, nodes, refs, tris):
+        nodes = np.ascontiguousarray(nodes)
+        refs = np.ascontiguousarray(refs)
+        tris = np.ascontiguousarray(tris)
+        lib().orc_bvh_import(self.h, nodes.ctypes.data, nodes.shape[0], refs.ctypes.data, refs.shape[0],
+                             tris.ctypes.data, tris.shape[0])
+
+    def validate(self) -> str:
+        buf = C.create_string_buffer(512)
+        rc = lib().orc_bvh_validate(self.h, buf, 512)
+        return "" if rc == 0 else f"[{rc}] {buf.value.decode()}"
+
+    def trace(self, rays: np.ndarray, mode: int = TRACE_CANONICAL, want_stats: bool = False, threads: int = 0):
+        rays = np.ascontiguousarray(rays)
+        assert rays.dtype == abi.RAY_DTYPE
+        hits = np.zeros(rays.shape[0], dtype=abi.HIT_DTYPE)
+        stats = OrcTraversalStats()
+        lib().orc_trace(self.h, rays.ctypes.data, rays.shape[0], hits.ctypes.data, mode,
+                        C.byref(stats) if want_stats else None, threads)
+        return (hits, stats) if want_stats else hits
+
+    def light_dist(self):
+        n = len(self.arrays.scene.instances)
+        w = np.zeros(n, dtype=np.float32)
+        cdf = np.zeros(n, dtype=np.float32)
+        integ = C.c_float()
+        lib().orc_light_dist_export(self.h, w.ctypes.data, cdf.ctypes.data, C.byref(integ))
+        return w, cdf, integ.value
+
+
+class OracleFrame:
+    def __init__(self, oscene: OracleScene, width: int, height: int, seed: int = 591842031321323413):
+        self.oscene = oscene
+        self.W, self.H = width, height
+        self.h = lib().orc_frame_create(oscene.h, width, height)
+        lib().orc_rng_seed(self.h, seed)
+        lib().orc_restir_setup_neighbor_table(self.h)
+
+    def close(self):
+        if self.h:
+            lib().orc_frame_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def buffer(self, buffer_id: int, index: int = 0) -> np.ndarray:
+        nbytes = C.c_size_t()
+        ptr = lib().orc_buffer_ptr(self.h, buffer_id, index, C.byref(nbytes))
+        dtype, comps, planes = abi.BUFFER_LAYOUT[buffer_id]
+        raw = (C.c_uint8 * nbytes.value).from_address(ptr)
+        arr = np.frombuffer(raw, dtype=dtype).copy()
+        if planes > 1:
+            return arr.reshape(planes, self.H, self.W, comps)
+        return arr.reshape(self.H, self.W, comps) if comps > 1 else arr.reshape(self.H, self.W)
+
+    def gbuffer(self, params, threads: int = 0):
+        lib().orc_gbuffer(self.h, C.byref(params), threads)
+
+    def restir(self, params, pass_id: int, threads: int = 0):
+        lib().orc_restir(self.h, C.byref(params), pass_id, threads)
+
+
+def primary_rays(params, width: int, height: int) -> np.ndarray:
+    rays = np.zeros(width * height, dtype=abi.RAY_DTYPE)
+    lib().orc_generate_primary_rays(C.byref(params), width, height, rays.ctypes.data)
+    return rays
