@@ -1,0 +1,635 @@
+// api.cu — the extern "C" entry points of include/gfxb200.h: context, scene upload, BVH
+// import/export, frame buffers.  Kernels live in bvh_build.cu / trace.cu / lights.cu /
+// gbuffer.cu / restir.cu / svgf.cu / nrc.cu.
+#include "context.h"
+#include <random>
+#include <cmath>
+
+using namespace gfx;
+
+namespace gfx {
+
+void SceneState::release() {
+    cudaFree(vertices); cudaFree(triangles); cudaFree(meshes); cudaFree(materials); cudaFree(instances);
+    cudaFree(instanceMeshSlots); cudaFree(geomToInstMesh); cudaFree(geomTriOffsets);
+    cudaFree(primWeights); cudaFree(primCdf); cudaFree(geomWeights); cudaFree(geomCdf);
+    cudaFree(instWeights); cudaFree(instCdf); cudaFree(instIntegral);
+    *this = SceneState();
+}
+void BvhState::release() {
+    cudaFree(nodes); cudaFree(primRefs); cudaFree(tris); cudaFree(sceneBounds);
+    uint32_t* keepFlag = overflowFlag;
+    *this = BvhState();
+    overflowFlag = keepFlag;
+}
+void FrameState::release() {
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(gb0[i]); cudaFree(gb1[i]); cudaFree(gb2[i]); cudaFree(gb3[i]);
+        cudaFree(reservoir[i]); cudaFree(reservoirInfo[i]);
+        cudaFree(svgfLighting[i]); cudaFree(svgfMoments[i]); cudaFree(svgfFinal[i]); cudaFree(svgfDepth[i]);
+    }
+    cudaFree(rng); cudaFree(beauty); cudaFree(albedo); cudaFree(normal); cudaFree(neighborDeltas);
+    cudaFree(svgfPrevLighting);
+    *this = FrameState();
+}
+
+DevFrameParams makeDevParams(const gfx_ctx* ctx, const GfxFrameParams* p) {
+    auto cam = [](const GfxCamera &c) {
+        DevCamera d;
+        d.aspect = c.aspect;
+        d.fovY = c.fovY;
+        d.position = f3(c.position[0], c.position[1], c.position[2]);
+        memcpy(d.orientation, c.orientation, 36);
+        // Matrix3x3::invert (common/basic_types.h:4150-4158): adjugate * (1/det), on the host
+        const float* m = c.orientation;
+        const float m00 = m[0], m01 = m[1], m02 = m[2], m10 = m[3], m11 = m[4], m12 = m[5], m20 = m[6], m21 = m[7], m22 = m[8];
+        const float det = m00 * m11 * m22 + m01 * m12 * m20 + m02 * m10 * m21
+            - m02 * m11 * m20 - m01 * m10 * m22 - m00 * m12 * m21;
+        const float rdet = 1 / det;
+        d.invOrientation[0] = (m11 * m22 - m12 * m21) * rdet;
+        d.invOrientation[1] = -(m01 * m22 - m02 * m21) * rdet;
+        d.invOrientation[2] = (m01 * m12 - m02 * m11) * rdet;
+        d.invOrientation[3] = -(m10 * m22 - m12 * m20) * rdet;
+        d.invOrientation[4] = (m00 * m22 - m02 * m20) * rdet;
+        d.invOrientation[5] = -(m00 * m12 - m02 * m10) * rdet;
+        d.invOrientation[6] = (m10 * m21 - m11 * m20) * rdet;
+        d.invOrientation[7] = -(m00 * m21 - m01 * m20) * rdet;
+        d.invOrientation[8] = (m00 * m11 - m01 * m10) * rdet;
+        // vh = 2 tan(fovY/2) is evaluated once on the host (optix_gbuffer_kernels.cu:23-24 does it per pixel)
+        d.vh = 2 * std::tan(c.fovY * 0.5f);
+        d.vw = c.aspect * d.vh;
+        return d;
+    };
+    DevFrameParams d;
+    d.camera = cam(p->camera);
+    d.prevCamera = cam(p->prevCamera);
+    d.numAccumFrames = p->numAccumFrames;
+    d.frameIndex = p->frameIndex;
+    d.bufferIndex = p->bufferIndex & 1;
+    d.spatialNeighborRadius = p->spatialNeighborRadius;
+    d.log2NumCandidateSamples = p->log2NumCandidateSamples;
+    d.numSpatialNeighbors = p->numSpatialNeighbors;
+    d.useLowDiscrepancyNeighbors = p->useLowDiscrepancyNeighbors;
+    d.reuseVisibility = p->reuseVisibility;
+    d.enableTemporalReuse = p->enableTemporalReuse;
+    d.enableSpatialReuse = p->enableSpatialReuse;
+    d.useUnbiasedEstimator = p->useUnbiasedEstimator;
+    d.resetFlowBuffer = p->resetFlowBuffer;
+    d.enableJittering = p->enableJittering;
+    d.currentReservoirIndex = p->currentReservoirIndex & 1;
+    d.spatialNeighborBaseIndex = p->spatialNeighborBaseIndex;
+    d.y0 = p->tileOriginY;
+    d.y1 = p->tileRows ? min(ctx->frame.H, p->tileOriginY + p->tileRows) : ctx->frame.H;
+    return d;
+}
+
+} // namespace gfx
+
+DevScene gfx_ctx::devScene() const {
+    DevScene d;
+    d.vertices = scene.vertices;
+    d.triangles = scene.triangles;
+    d.meshes = scene.meshes;
+    d.materials = scene.materials;
+    d.instances = scene.instances;
+    d.instanceMeshSlots = scene.instanceMeshSlots;
+    d.geomToInstMesh = scene.geomToInstMesh;
+    d.primWeights = scene.primWeights;
+    d.primCdf = scene.primCdf;
+    d.geomWeights = scene.geomWeights;
+    d.geomCdf = scene.geomCdf;
+    d.instWeights = scene.instWeights;
+    d.instCdf = scene.instCdf;
+    d.instIntegral = scene.instIntegral;
+    d.numInstances = scene.numInstances;
+    d.bvh.nodes = reinterpret_cast<const uint4*>(bvh.nodes);
+    d.bvh.primRefs = bvh.primRefs;
+    d.bvh.tris = bvh.tris;
+    d.bvh.numNodes = bvh.numNodes;
+    d.bvh.overflowFlag = bvh.overflowFlag;
+    return d;
+}
+DevFrame gfx_ctx::devFrame() const {
+    DevFrame d;
+    d.W = frame.W;
+    d.H = frame.H;
+    for (int i = 0; i < 2; ++i) {
+        d.gb0[i] = frame.gb0[i];
+        d.gb1[i] = frame.gb1[i];
+        d.gb2[i] = frame.gb2[i];
+        d.gb3[i] = frame.gb3[i];
+        d.reservoir[i] = frame.reservoir[i];
+        d.reservoirInfo[i] = frame.reservoirInfo[i];
+    }
+    d.rng = frame.rng;
+    d.beauty = frame.beauty;
+    d.albedo = frame.albedo;
+    d.normal = frame.normal;
+    d.neighborDeltas = frame.neighborDeltas;
+    return d;
+}
+
+#define CHECK_CTX(ctx) do { if (!(ctx)) return GFX_ERR_INVALID_ARGUMENT; } while (0)
+
+extern "C" {
+
+int gfx_ctx_create(int device, gfx_ctx** out) {
+    if (!out)
+        return GFX_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count)
+        return GFX_ERR_NO_DEVICE; // no CPU fallback by design
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess)
+        return GFX_ERR_NO_DEVICE;
+    if (prop.major < 10)
+        return GFX_ERR_NO_DEVICE; // the fat binary only carries sm_100a code
+    if (cudaSetDevice(device) != cudaSuccess)
+        return GFX_ERR_CUDA;
+    gfx_ctx* ctx = new gfx_ctx();
+    ctx->device = device;
+    if (cudaMalloc(&ctx->bvh.overflowFlag, 4) != cudaSuccess) {
+        delete ctx;
+        return GFX_ERR_OUT_OF_MEMORY;
+    }
+    cudaMemset(ctx->bvh.overflowFlag, 0, 4);
+    *out = ctx;
+    return GFX_OK;
+}
+
+void gfx_ctx_destroy(gfx_ctx* ctx) {
+    if (!ctx)
+        return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    ctx->frame.release();
+    ctx->bvh.release();
+    cudaFree(ctx->bvh.overflowFlag);
+    ctx->scene.release();
+    delete ctx;
+}
+
+const char* gfx_last_error_string(gfx_ctx* ctx) { return ctx ? ctx->lastError.c_str() : "null context"; }
+
+int gfx_synchronize(gfx_ctx* ctx, void* stream) {
+    CHECK_CTX(ctx);
+    GFX_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+    uint32_t flag = 0;
+    GFX_CUDA(ctx, cudaMemcpy(&flag, ctx->bvh.overflowFlag, 4, cudaMemcpyDeviceToHost));
+    if (flag) {
+        ctx->setError("traversal stack overflow (kStackSize too small for this BVH)");
+        return GFX_ERR_CUDA;
+    }
+    return GFX_OK;
+}
+
+uint64_t gfx_kernel_launch_count(gfx_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int gfx_scene_upload(gfx_ctx* ctx, const GfxSceneDesc* sd) {
+    CHECK_CTX(ctx);
+    if (!sd || (sd->numMeshes && !sd->meshes) || (sd->numInstances && !sd->instances))
+        return GFX_ERR_INVALID_ARGUMENT;
+    GFX_CUDA(ctx, cudaSetDevice(ctx->device));
+    SceneState &S = ctx->scene;
+    S.release();
+    ctx->bvh.release();
+
+    // meshes: concatenate vertex / triangle tables
+    std::vector<DevMesh> meshes(sd->numMeshes);
+    size_t numVerts = 0, numTris = 0;
+    for (uint32_t i = 0; i < sd->numMeshes; ++i) {
+        const GfxMeshDesc &m = sd->meshes[i];
+        if (m.materialSlot >= sd->numMaterials) {
+            ctx->setError("gfx_scene_upload: material slot out of range");
+            return GFX_ERR_INVALID_ARGUMENT;
+        }
+        meshes[i].vertexBase = (uint32_t)numVerts;
+        meshes[i].triBase = (uint32_t)numTris;
+        meshes[i].numTriangles = m.numTriangles;
+        meshes[i].materialSlot = m.materialSlot;
+        meshes[i].primIntegral = 0.0f;
+        numVerts += m.numVertices;
+        numTris += m.numTriangles;
+    }
+    std::vector<float4> verts(3 * numVerts);
+    std::vector<uint4> tris(numTris);
+    for (uint32_t i = 0; i < sd->numMeshes; ++i) {
+        const GfxMeshDesc &m = sd->meshes[i];
+        for (uint32_t v = 0; v < m.numVertices; ++v) {
+            float4* o = &verts[3 * (size_t)(meshes[i].vertexBase + v)];
+            o[0] = make_float4(m.positions[3 * v], m.positions[3 * v + 1], m.positions[3 * v + 2], m.texcoords[2 * v]);
+            o[1] = make_float4(m.normals[3 * v], m.normals[3 * v + 1], m.normals[3 * v + 2], m.texcoords[2 * v + 1]);
+            o[2] = make_float4(m.tangents[3 * v], m.tangents[3 * v + 1], m.tangents[3 * v + 2], 0.0f);
+        }
+        for (uint32_t t = 0; t < m.numTriangles; ++t) {
+            const uint32_t* idx = m.triangles + 3 * (size_t)t;
+            if (idx[0] >= m.numVertices || idx[1] >= m.numVertices || idx[2] >= m.numVertices) {
+                ctx->setError("gfx_scene_upload: vertex index out of range");
+                return GFX_ERR_INVALID_ARGUMENT;
+            }
+            tris[meshes[i].triBase + t] = make_uint4(idx[0], idx[1], idx[2], 0u);
+        }
+    }
+    // instances + flattened geometry table (instance order, then mesh slot order)
+    std::vector<DevInstance> insts(sd->numInstances);
+    std::vector<uint2> geomToInstMesh;
+    std::vector<uint32_t> geomTriOffsets;
+    uint32_t flatTris = 0;
+    for (uint32_t i = 0; i < sd->numInstances; ++i) {
+        const GfxInstanceDesc &in = sd->instances[i];
+        if ((size_t)in.firstMeshSlot + in.numMeshSlots > sd->numInstanceMeshSlots) {
+            ctx->setError("gfx_scene_upload: instance mesh-slot range out of bounds");
+            return GFX_ERR_INVALID_ARGUMENT;
+        }
+        DevInstance &d = insts[i];
+        memset(&d, 0, sizeof(d));
+        memcpy(d.transform, in.transform, 48);
+        memcpy(d.curToPrevTransform, in.curToPrevTransform, 48);
+        memcpy(d.normalMatrix, in.normalMatrix, 36);
+        d.uniformScale = in.uniformScale;
+        d.firstMeshSlot = in.firstMeshSlot;
+        d.numMeshSlots = in.numMeshSlots;
+        for (uint32_t k = 0; k < in.numMeshSlots; ++k) {
+            const uint32_t slot = sd->instanceMeshSlots[in.firstMeshSlot + k];
+            if (slot >= sd->numMeshes) {
+                ctx->setError("gfx_scene_upload: mesh slot out of range");
+                return GFX_ERR_INVALID_ARGUMENT;
+            }
+            geomToInstMesh.push_back(make_uint2(i, slot));
+            geomTriOffsets.push_back(flatTris);
+            flatTris += meshes[slot].numTriangles;
+        }
+    }
+    geomTriOffsets.push_back(flatTris);
+
+    auto upload = [&](auto** dst, const void* src, size_t bytes) -> cudaError_t {
+        cudaError_t e = cudaMalloc((void**)dst, bytes ? bytes : 16);
+        if (e != cudaSuccess) return e;
+        return bytes ? cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) : cudaSuccess;
+    };
+    GFX_CUDA(ctx, upload(&S.vertices, verts.data(), verts.size() * 16));
+    GFX_CUDA(ctx, upload(&S.triangles, tris.data(), tris.size() * 16));
+    GFX_CUDA(ctx, upload(&S.meshes, meshes.data(), meshes.size() * sizeof(DevMesh)));
+    GFX_CUDA(ctx, upload(&S.materials, sd->materials, sd->numMaterials * sizeof(GfxMaterialDesc)));
+    GFX_CUDA(ctx, upload(&S.instances, insts.data(), insts.size() * sizeof(DevInstance)));
+    GFX_CUDA(ctx, upload(&S.instanceMeshSlots, sd->instanceMeshSlots, sd->numInstanceMeshSlots * 4));
+    GFX_CUDA(ctx, upload(&S.geomToInstMesh, geomToInstMesh.data(), geomToInstMesh.size() * 8));
+    GFX_CUDA(ctx, upload(&S.geomTriOffsets, geomTriOffsets.data(), geomTriOffsets.size() * 4));
+    GFX_CUDA(ctx, cudaMalloc(&S.primWeights, (numTris ? numTris : 4) * 4));
+    GFX_CUDA(ctx, cudaMalloc(&S.primCdf, (numTris ? numTris : 4) * 4));
+    GFX_CUDA(ctx, cudaMalloc(&S.geomWeights, (sd->numInstanceMeshSlots ? sd->numInstanceMeshSlots : 4) * 4));
+    GFX_CUDA(ctx, cudaMalloc(&S.geomCdf, (sd->numInstanceMeshSlots ? sd->numInstanceMeshSlots : 4) * 4));
+    GFX_CUDA(ctx, cudaMalloc(&S.instWeights, (sd->numInstances ? sd->numInstances : 4) * 4));
+    GFX_CUDA(ctx, cudaMalloc(&S.instCdf, (sd->numInstances ? sd->numInstances : 4) * 4));
+    GFX_CUDA(ctx, cudaMalloc(&S.instIntegral, 16));
+    GFX_CUDA(ctx, cudaMemset(S.instIntegral, 0, 16));
+    S.numMeshes = sd->numMeshes;
+    S.numMaterials = sd->numMaterials;
+    S.numInstances = sd->numInstances;
+    S.numInstanceMeshSlots = sd->numInstanceMeshSlots;
+    S.numGeoms = (uint32_t)geomToInstMesh.size();
+    S.numFlatTris = flatTris;
+    S.numMeshTris = (uint32_t)numTris;
+    S.numVertices = (uint32_t)numVerts;
+    S.hostMeshes = meshes;
+    S.hostInstances = insts;
+    S.uploaded = true;
+    return GFX_OK;
+}
+
+int gfx_scene_update_instances(gfx_ctx* ctx, void* stream, const GfxInstanceDesc* instances, uint32_t numInstances) {
+    CHECK_CTX(ctx);
+    SceneState &S = ctx->scene;
+    if (!S.uploaded)
+        return GFX_ERR_NOT_READY;
+    if (!instances || numInstances != S.numInstances)
+        return GFX_ERR_INVALID_ARGUMENT;
+    for (uint32_t i = 0; i < numInstances; ++i) {
+        DevInstance &d = S.hostInstances[i];
+        memcpy(d.transform, instances[i].transform, 48);
+        memcpy(d.curToPrevTransform, instances[i].curToPrevTransform, 48);
+        memcpy(d.normalMatrix, instances[i].normalMatrix, 36);
+        d.uniformScale = instances[i].uniformScale;
+    }
+    // geomIntegral lives on the device copy only: patch the transform part of each record
+    for (uint32_t i = 0; i < numInstances; ++i)
+        GFX_CUDA(ctx, cudaMemcpyAsync(S.instances + i, &S.hostInstances[i], offsetof(DevInstance, firstMeshSlot),
+                                      cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return GFX_OK;
+}
+
+int gfx_bvh_build(gfx_ctx* ctx, void* stream, uint32_t flags) {
+    CHECK_CTX(ctx);
+    if (!ctx->scene.uploaded) {
+        ctx->setError("gfx_bvh_build: no scene uploaded");
+        return GFX_ERR_NOT_READY;
+    }
+    GFX_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int rc = buildBvh(ctx, (cudaStream_t)stream, flags);
+    if (rc == GFX_OK)
+        ctx->bvh.ready = true;
+    return rc;
+}
+
+int gfx_bvh_info(gfx_ctx* ctx, GfxBvhInfo* info) {
+    CHECK_CTX(ctx);
+    if (!info)
+        return GFX_ERR_INVALID_ARGUMENT;
+    if (!ctx->bvh.ready)
+        return GFX_ERR_NOT_READY;
+    info->numNodes = ctx->bvh.numNodes;
+    info->numPrimRefs = ctx->bvh.numPrimRefs;
+    info->numTriangles = ctx->bvh.numTris;
+    info->numGeoms = ctx->scene.numGeoms;
+    for (int i = 0; i < 3; ++i) {
+        info->sceneMin[i] = ctx->bvh.sceneMin[i];
+        info->sceneMax[i] = ctx->bvh.sceneMax[i];
+    }
+    return GFX_OK;
+}
+
+int gfx_bvh_export(gfx_ctx* ctx, GfxBvhNode8* nodes, uint32_t* primRefs, GfxTriangleStorage* tris) {
+    CHECK_CTX(ctx);
+    if (!ctx->bvh.ready)
+        return GFX_ERR_NOT_READY;
+    static_assert(sizeof(GfxBvhNode8) == 80 && sizeof(GfxTriangleStorage) == 48 && sizeof(GfxHitObject) == 32, "reference layouts");
+    if (nodes) GFX_CUDA(ctx, cudaMemcpy(nodes, ctx->bvh.nodes, (size_t)ctx->bvh.numNodes * 80, cudaMemcpyDeviceToHost));
+    if (primRefs) GFX_CUDA(ctx, cudaMemcpy(primRefs, ctx->bvh.primRefs, (size_t)ctx->bvh.numPrimRefs * 4, cudaMemcpyDeviceToHost));
+    if (tris) GFX_CUDA(ctx, cudaMemcpy(tris, ctx->bvh.tris, (size_t)ctx->bvh.numTris * 48, cudaMemcpyDeviceToHost));
+    return GFX_OK;
+}
+
+int gfx_bvh_import(gfx_ctx* ctx, const GfxBvhNode8* nodes, uint32_t numNodes, const uint32_t* primRefs,
+                   uint32_t numPrimRefs, const GfxTriangleStorage* tris, uint32_t numTris) {
+    CHECK_CTX(ctx);
+    if (!nodes || !primRefs || !tris)
+        return GFX_ERR_INVALID_ARGUMENT;
+    GFX_CUDA(ctx, cudaSetDevice(ctx->device));
+    BvhState &B = ctx->bvh;
+    B.release();
+    GFX_CUDA(ctx, cudaMalloc(&B.nodes, (size_t)max(numNodes, 1u) * 80));
+    GFX_CUDA(ctx, cudaMalloc(&B.primRefs, (size_t)max(numPrimRefs, 1u) * 4));
+    GFX_CUDA(ctx, cudaMalloc(&B.tris, (size_t)max(numTris, 1u) * 48));
+    GFX_CUDA(ctx, cudaMemcpy(B.nodes, nodes, (size_t)numNodes * 80, cudaMemcpyHostToDevice));
+    GFX_CUDA(ctx, cudaMemcpy(B.primRefs, primRefs, (size_t)numPrimRefs * 4, cudaMemcpyHostToDevice));
+    GFX_CUDA(ctx, cudaMemcpy(B.tris, tris, (size_t)numTris * 48, cudaMemcpyHostToDevice));
+    B.numNodes = numNodes;
+    B.numPrimRefs = numPrimRefs;
+    B.numTris = numTris;
+    B.ready = true;
+    return GFX_OK;
+}
+
+int gfx_trace_device(gfx_ctx* ctx, void* stream, const GfxRay* rays, uint32_t numRays, GfxHitObject* hits, int mode) {
+    CHECK_CTX(ctx);
+    if (!ctx->bvh.ready) {
+        ctx->setError("gfx_trace: BVH not built");
+        return GFX_ERR_NOT_READY;
+    }
+    if ((!rays || !hits) && numRays)
+        return GFX_ERR_INVALID_ARGUMENT;
+    return traceRays(ctx, (cudaStream_t)stream, rays, numRays, hits, mode);
+}
+
+int gfx_trace(gfx_ctx* ctx, void* stream, const GfxRay* rays, uint32_t numRays, GfxHitObject* hits, int mode) {
+    CHECK_CTX(ctx);
+    if (!ctx->bvh.ready) {
+        ctx->setError("gfx_trace: BVH not built");
+        return GFX_ERR_NOT_READY;
+    }
+    if (numRays == 0)
+        return GFX_OK;
+    if (!rays || !hits)
+        return GFX_ERR_INVALID_ARGUMENT;
+    GfxRay* dRays = nullptr;
+    GfxHitObject* dHits = nullptr;
+    GFX_CUDA(ctx, cudaMalloc(&dRays, (size_t)numRays * sizeof(GfxRay)));
+    GFX_CUDA(ctx, cudaMalloc(&dHits, (size_t)numRays * sizeof(GfxHitObject)));
+    GFX_CUDA(ctx, cudaMemcpyAsync(dRays, rays, (size_t)numRays * sizeof(GfxRay), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    const int rc = traceRays(ctx, (cudaStream_t)stream, dRays, numRays, dHits, mode);
+    if (rc == GFX_OK) {
+        GFX_CUDA(ctx, cudaMemcpyAsync(hits, dHits, (size_t)numRays * sizeof(GfxHitObject), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+        GFX_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+    }
+    cudaFree(dRays);
+    cudaFree(dHits);
+    return rc;
+}
+
+int gfx_light_dist_build(gfx_ctx* ctx, void* stream, uint32_t bufferIndex) {
+    CHECK_CTX(ctx);
+    if (!ctx->scene.uploaded)
+        return GFX_ERR_NOT_READY;
+    return buildLightDistributions(ctx, (cudaStream_t)stream, bufferIndex);
+}
+
+int gfx_light_dist_export(gfx_ctx* ctx, float* instWeights, float* instCdf, float* integral) {
+    CHECK_CTX(ctx);
+    const SceneState &S = ctx->scene;
+    if (!S.uploaded)
+        return GFX_ERR_NOT_READY;
+    GFX_CUDA(ctx, cudaDeviceSynchronize());
+    if (instWeights) GFX_CUDA(ctx, cudaMemcpy(instWeights, S.instWeights, (size_t)S.numInstances * 4, cudaMemcpyDeviceToHost));
+    if (instCdf) GFX_CUDA(ctx, cudaMemcpy(instCdf, S.instCdf, (size_t)S.numInstances * 4, cudaMemcpyDeviceToHost));
+    if (integral) GFX_CUDA(ctx, cudaMemcpy(integral, S.instIntegral, 4, cudaMemcpyDeviceToHost));
+    return GFX_OK;
+}
+
+int gfx_frame_create(gfx_ctx* ctx, uint32_t W, uint32_t H) {
+    CHECK_CTX(ctx);
+    if (W == 0 || H == 0)
+        return GFX_ERR_INVALID_ARGUMENT;
+    GFX_CUDA(ctx, cudaSetDevice(ctx->device));
+    FrameState &F = ctx->frame;
+    F.release();
+    const size_t n = (size_t)W * H;
+    for (int i = 0; i < 2; ++i) {
+        GFX_CUDA(ctx, cudaMalloc(&F.gb0[i], n * 16));
+        GFX_CUDA(ctx, cudaMalloc(&F.gb1[i], n * 8));
+        GFX_CUDA(ctx, cudaMalloc(&F.gb2[i], n * 16));
+        GFX_CUDA(ctx, cudaMalloc(&F.gb3[i], n * 16));
+        GFX_CUDA(ctx, cudaMalloc(&F.reservoir[i], n * 48));
+        GFX_CUDA(ctx, cudaMalloc(&F.reservoirInfo[i], n * 8));
+        GFX_CUDA(ctx, cudaMemset(F.gb0[i], 0xFF, n * 16));
+        GFX_CUDA(ctx, cudaMemset(F.gb1[i], 0, n * 8));
+        GFX_CUDA(ctx, cudaMemset(F.gb2[i], 0, n * 16));
+        GFX_CUDA(ctx, cudaMemset(F.gb3[i], 0, n * 16));
+        GFX_CUDA(ctx, cudaMemset(F.reservoir[i], 0, n * 48));
+        GFX_CUDA(ctx, cudaMemset(F.reservoirInfo[i], 0, n * 8));
+        GFX_CUDA(ctx, cudaMalloc(&F.svgfLighting[i], n * 16));
+        GFX_CUDA(ctx, cudaMalloc(&F.svgfMoments[i], n * 16));
+        GFX_CUDA(ctx, cudaMalloc(&F.svgfFinal[i], n * 16));
+        GFX_CUDA(ctx, cudaMalloc(&F.svgfDepth[i], n * 4));
+        GFX_CUDA(ctx, cudaMemset(F.svgfLighting[i], 0, n * 16));
+        GFX_CUDA(ctx, cudaMemset(F.svgfMoments[i], 0, n * 16));
+        GFX_CUDA(ctx, cudaMemset(F.svgfFinal[i], 0, n * 16));
+        GFX_CUDA(ctx, cudaMemset(F.svgfDepth[i], 0, n * 4));
+    }
+    GFX_CUDA(ctx, cudaMalloc(&F.svgfPrevLighting, n * 16));
+    GFX_CUDA(ctx, cudaMemset(F.svgfPrevLighting, 0, n * 16));
+    GFX_CUDA(ctx, cudaMalloc(&F.rng, n * 8));
+    GFX_CUDA(ctx, cudaMalloc(&F.beauty, n * 16));
+    GFX_CUDA(ctx, cudaMalloc(&F.albedo, n * 16));
+    GFX_CUDA(ctx, cudaMalloc(&F.normal, n * 16));
+    GFX_CUDA(ctx, cudaMalloc(&F.neighborDeltas, 1024 * 8));
+    GFX_CUDA(ctx, cudaMemset(F.rng, 0, n * 8));
+    GFX_CUDA(ctx, cudaMemset(F.beauty, 0, n * 16));
+    GFX_CUDA(ctx, cudaMemset(F.albedo, 0, n * 16));
+    GFX_CUDA(ctx, cudaMemset(F.normal, 0, n * 16));
+    GFX_CUDA(ctx, cudaMemset(F.neighborDeltas, 0, 1024 * 8));
+    F.W = W;
+    F.H = H;
+    F.created = true;
+    return GFX_OK;
+}
+
+int gfx_rng_seed(gfx_ctx* ctx, uint64_t seed) {
+    CHECK_CTX(ctx);
+    FrameState &F = ctx->frame;
+    if (!F.created)
+        return GFX_ERR_NOT_READY;
+    // restir_di_main.cpp:1309-1321: one std::mt19937_64 draw per pixel, row-major
+    std::vector<unsigned long long> states((size_t)F.W * F.H);
+    std::mt19937_64 rngSeed(seed);
+    for (size_t i = 0; i < states.size(); ++i)
+        states[i] = rngSeed();
+    GFX_CUDA(ctx, cudaMemcpy(F.rng, states.data(), states.size() * 8, cudaMemcpyHostToDevice));
+    return GFX_OK;
+}
+
+int gfx_restir_setup_neighbor_table(gfx_ctx* ctx) {
+    CHECK_CTX(ctx);
+    FrameState &F = ctx->frame;
+    if (!F.created)
+        return GFX_ERR_NOT_READY;
+    // restir_di_main.cpp:1489-1542: Halton(2,3) mapped through the concentric disk map
+    auto halton = [](uint32_t base, uint32_t idx) {
+        const float recBase = 1.0f / base;
+        float ret = 0.0f;
+        float scale = 1.0f;
+        while (idx) {
+            scale *= recBase;
+            ret += (idx % base) * scale;
+            idx /= base;
+        }
+        return ret;
+    };
+    std::vector<float2> deltas(1024);
+    const float pi = 3.14159265358979323846f;
+    for (uint32_t i = 0; i < 1024; ++i) {
+        const float u0 = halton(2, i), u1 = halton(3, i);
+        const float sx = 2 * u0 - 1;
+        const float sy = 2 * u1 - 1;
+        float2 d = make_float2(0.0f, 0.0f);
+        if (!(sx == 0 && sy == 0)) {
+            float r, theta;
+            if (sx >= -sy) {
+                if (sx > sy) { r = sx; theta = sy / sx; }
+                else { r = sy; theta = 2 - sx / sy; }
+            }
+            else {
+                if (sx > sy) { r = -sy; theta = 6 + sx / sy; }
+                else { r = -sx; theta = 4 + sy / sx; }
+            }
+            theta *= pi / 4;
+            d.x = (float)(r * std::cos((double)theta));
+            d.y = (float)(r * std::sin((double)theta));
+        }
+        deltas[i] = d;
+    }
+    GFX_CUDA(ctx, cudaMemcpy(F.neighborDeltas, deltas.data(), 1024 * 8, cudaMemcpyHostToDevice));
+    return GFX_OK;
+}
+
+static void* bufferPtr(gfx_ctx* ctx, int id, uint32_t index, size_t* bytes) {
+    FrameState &F = ctx->frame;
+    const size_t n = (size_t)F.W * F.H;
+    const uint32_t i = index & 1;
+    void* p = nullptr;
+    size_t b = 0;
+    switch (id) {
+    case GFX_BUF_GBUFFER0: p = F.gb0[i]; b = n * 16; break;
+    case GFX_BUF_GBUFFER1: p = F.gb1[i]; b = n * 8; break;
+    case GFX_BUF_GBUFFER2: p = F.gb2[i]; b = n * 16; break;
+    case GFX_BUF_GBUFFER3: p = F.gb3[i]; b = n * 16; break;
+    case GFX_BUF_RNG: p = F.rng; b = n * 8; break;
+    case GFX_BUF_RESERVOIR: p = F.reservoir[i]; b = n * 48; break;
+    case GFX_BUF_RESERVOIR_INFO: p = F.reservoirInfo[i]; b = n * 8; break;
+    case GFX_BUF_BEAUTY_ACCUM: p = F.beauty; b = n * 16; break;
+    case GFX_BUF_ALBEDO_ACCUM: p = F.albedo; b = n * 16; break;
+    case GFX_BUF_NORMAL_ACCUM: p = F.normal; b = n * 16; break;
+    case GFX_BUF_SVGF_LIGHTING_VARIANCE: p = F.svgfLighting[i]; b = n * 16; break;
+    case GFX_BUF_SVGF_FINAL: p = F.svgfFinal[i]; b = n * 16; break;
+    default: break;
+    }
+    if (bytes) *bytes = b;
+    return p;
+}
+
+void* gfx_buffer_device_ptr(gfx_ctx* ctx, int bufferId, uint32_t index, size_t* bytes) {
+    if (!ctx || !ctx->frame.created) {
+        if (bytes) *bytes = 0;
+        return nullptr;
+    }
+    return bufferPtr(ctx, bufferId, index, bytes);
+}
+
+int gfx_buffer_download(gfx_ctx* ctx, void* stream, int bufferId, uint32_t index, void* host, size_t bytes) {
+    CHECK_CTX(ctx);
+    if (!ctx->frame.created)
+        return GFX_ERR_NOT_READY;
+    size_t have = 0;
+    void* p = bufferPtr(ctx, bufferId, index, &have);
+    if (!p || !host || bytes > have)
+        return GFX_ERR_INVALID_ARGUMENT;
+    GFX_CUDA(ctx, cudaMemcpyAsync(host, p, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    GFX_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+    return GFX_OK;
+}
+
+int gfx_buffer_upload(gfx_ctx* ctx, void* stream, int bufferId, uint32_t index, const void* host, size_t bytes) {
+    CHECK_CTX(ctx);
+    if (!ctx->frame.created)
+        return GFX_ERR_NOT_READY;
+    size_t have = 0;
+    void* p = bufferPtr(ctx, bufferId, index, &have);
+    if (!p || !host || bytes > have)
+        return GFX_ERR_INVALID_ARGUMENT;
+    GFX_CUDA(ctx, cudaMemcpyAsync(p, host, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    GFX_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+    return GFX_OK;
+}
+
+int gfx_gbuffer_launch(gfx_ctx* ctx, void* stream, const GfxFrameParams* params) {
+    CHECK_CTX(ctx);
+    if (!params)
+        return GFX_ERR_INVALID_ARGUMENT;
+    if (!ctx->bvh.ready || !ctx->frame.created) {
+        ctx->setError("gfx_gbuffer_launch: BVH or frame buffers missing");
+        return GFX_ERR_NOT_READY;
+    }
+    return launchGBuffer(ctx, (cudaStream_t)stream, params);
+}
+
+int gfx_restir_launch(gfx_ctx* ctx, void* stream, const GfxFrameParams* params, int pass) {
+    CHECK_CTX(ctx);
+    if (!params)
+        return GFX_ERR_INVALID_ARGUMENT;
+    if (!ctx->bvh.ready || !ctx->frame.created) {
+        ctx->setError("gfx_restir_launch: BVH or frame buffers missing");
+        return GFX_ERR_NOT_READY;
+    }
+    return launchReSTIR(ctx, (cudaStream_t)stream, params, pass);
+}
+
+int gfx_svgf_launch(gfx_ctx* ctx, void* stream, const GfxFrameParams* params, int pass, uint32_t stage) {
+    CHECK_CTX(ctx);
+    if (!params)
+        return GFX_ERR_INVALID_ARGUMENT;
+    if (!ctx->frame.created)
+        return GFX_ERR_NOT_READY;
+    return launchSVGF(ctx, (cudaStream_t)stream, params, pass, stage);
+}
+
+} // extern "C"

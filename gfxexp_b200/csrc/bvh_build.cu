@@ -1,0 +1,473 @@
+// bvh_build.cu — GPU LBVH builder emitting the reference's wide-BVH format.
+//
+// Stands where Scene::updateASs -> optixAccelBuild stands (common/common_host.h:1027-1100,
+// utils/optix_util.cpp:1776,2799) and where the CPU bvh::buildGeometryBVH<8>
+// (common/bvh_builder.cpp:656-1125) stands for the software path.  Output is bit-compatible with
+// shared::CompressedInternalNode_T<8> / TriangleStorage / PrimitiveReference
+// (common/common_shared.h:757-917,1012-1025), so the reference traverser can walk it.
+//
+// Pipeline (all on the device, one stream):
+//   1 flatten      : world-space TriangleStorage per (instance, mesh, prim) + AABB + scene bounds
+//   2 morton       : 63-bit Morton key of the AABB centre
+//   3 sort         : cub::DeviceRadixSort (key, triangle id)
+//   4 hierarchy    : Karras 2012 binary radix tree over the sorted keys
+//   5 refit        : bottom-up AABBs with per-node arrival counters
+//   6 collapse     : level-synchronous top-down collapse of the binary tree into 8-wide nodes
+//                    (largest-surface-area child is opened first, like the reference's task loop
+//                    :777-800), leaves of <= maxLeaf triangles, conservative 8-bit quantisation.
+#include "scene.cuh"
+#include "context.h"
+#include <cub/cub.cuh>
+
+namespace gfx {
+
+__device__ __forceinline__ uint32_t orderedFromFloat(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return u ^ (u < 0x80000000u ? 0x80000000u : 0xFFFFFFFFu);
+}
+__device__ __forceinline__ float floatFromOrdered(uint32_t u) {
+    return __uint_as_float(u ^ (u >= 0x80000000u ? 0x80000000u : 0xFFFFFFFFu));
+}
+
+// ---- 1. flatten -----------------------------------------------------------------------------
+__global__ void k_flatten(DevScene scene, const uint32_t* __restrict__ geomTriOffsets, uint32_t numGeoms,
+                          uint32_t numTris, float4* __restrict__ tris, float4* __restrict__ triLo,
+                          float4* __restrict__ triHi, uint32_t* __restrict__ sceneBounds /*6 ordered uints*/) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    f3 lo(INFINITY), hi(-INFINITY);
+    if (t < numTris) {
+        // geometry of this triangle: largest g with geomTriOffsets[g] <= t  (extractGeomAndPrimIndex,
+        // common/bvh_builder.cpp:680-692)
+        uint32_t g = 0;
+        for (uint32_t d = 1u << (31 - __clz(max(numGeoms, 1u))); d >= 1; d >>= 1) {
+            if (g + d < numGeoms && __ldg(geomTriOffsets + g + d) <= t)
+                g += d;
+        }
+        const uint32_t prim = t - __ldg(geomTriOffsets + g);
+        const uint2 im = __ldg(scene.geomToInstMesh + g);
+        const DevInstance* inst = scene.instances + im.x;
+        const DevMesh mesh = scene.meshes[im.y];
+        const uint4 tri = __ldg(scene.triangles + mesh.triBase + prim);
+        const float4 a = __ldg(scene.vertices + 3 * (size_t)(mesh.vertexBase + tri.x));
+        const float4 b = __ldg(scene.vertices + 3 * (size_t)(mesh.vertexBase + tri.y));
+        const float4 c = __ldg(scene.vertices + 3 * (size_t)(mesh.vertexBase + tri.z));
+        // calcTriangleVertices: preTransform * p (common/bvh_builder.cpp:176-209)
+        const f3 pA = xfmPoint(inst->transform, f3(a.x, a.y, a.z));
+        const f3 pB = xfmPoint(inst->transform, f3(b.x, b.y, b.z));
+        const f3 pC = xfmPoint(inst->transform, f3(c.x, c.y, c.z));
+        tris[3 * (size_t)t + 0] = make_float4(pA.x, pA.y, pA.z, pB.x);
+        tris[3 * (size_t)t + 1] = make_float4(pB.y, pB.z, pC.x, pC.y);
+        tris[3 * (size_t)t + 2] = make_float4(pC.z, __uint_as_float(g), __uint_as_float(prim), 0.0f);
+        lo = min3(min3(pA, pB), pC);
+        hi = max3(max3(pA, pB), pC);
+        triLo[t] = make_float4(lo.x, lo.y, lo.z, 0.0f);
+        triHi[t] = make_float4(hi.x, hi.y, hi.z, 0.0f);
+    }
+    // block reduction of the scene bounds, then 6 atomics per block
+    typedef cub::BlockReduce<float, 256> BR;
+    __shared__ typename BR::TempStorage tmp;
+    float v;
+    v = BR(tmp).Reduce(lo.x, cub::Min()); __syncthreads(); if (threadIdx.x == 0) atomicMin(sceneBounds + 0, orderedFromFloat(v));
+    v = BR(tmp).Reduce(lo.y, cub::Min()); __syncthreads(); if (threadIdx.x == 0) atomicMin(sceneBounds + 1, orderedFromFloat(v));
+    v = BR(tmp).Reduce(lo.z, cub::Min()); __syncthreads(); if (threadIdx.x == 0) atomicMin(sceneBounds + 2, orderedFromFloat(v));
+    v = BR(tmp).Reduce(hi.x, cub::Max()); __syncthreads(); if (threadIdx.x == 0) atomicMax(sceneBounds + 3, orderedFromFloat(v));
+    v = BR(tmp).Reduce(hi.y, cub::Max()); __syncthreads(); if (threadIdx.x == 0) atomicMax(sceneBounds + 4, orderedFromFloat(v));
+    v = BR(tmp).Reduce(hi.z, cub::Max()); __syncthreads(); if (threadIdx.x == 0) atomicMax(sceneBounds + 5, orderedFromFloat(v));
+}
+
+// ---- 2. morton ------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t expandBits21(uint64_t v) {
+    v &= 0x1FFFFFull;
+    v = (v | v << 32) & 0x1F00000000FFFFull;
+    v = (v | v << 16) & 0x1F0000FF0000FFull;
+    v = (v | v << 8) & 0x100F00F00F00F00Full;
+    v = (v | v << 4) & 0x10C30C30C30C30C3ull;
+    v = (v | v << 2) & 0x1249249249249249ull;
+    return v;
+}
+__global__ void k_morton(uint32_t numTris, const float4* __restrict__ triLo, const float4* __restrict__ triHi,
+                         const uint32_t* __restrict__ sceneBounds, uint64_t* __restrict__ keys, uint32_t* __restrict__ ids) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= numTris)
+        return;
+    const f3 smin(floatFromOrdered(sceneBounds[0]), floatFromOrdered(sceneBounds[1]), floatFromOrdered(sceneBounds[2]));
+    const f3 smax(floatFromOrdered(sceneBounds[3]), floatFromOrdered(sceneBounds[4]), floatFromOrdered(sceneBounds[5]));
+    const float4 lo = triLo[t], hi = triHi[t];
+    const f3 c(0.5f * (lo.x + hi.x), 0.5f * (lo.y + hi.y), 0.5f * (lo.z + hi.z));
+    const f3 ext = smax - smin;
+    const float sx = ext.x > 0 ? 2097151.0f / ext.x : 0.0f;
+    const float sy = ext.y > 0 ? 2097151.0f / ext.y : 0.0f;
+    const float sz = ext.z > 0 ? 2097151.0f / ext.z : 0.0f;
+    const uint64_t qx = (uint64_t)fminf(fmaxf((c.x - smin.x) * sx, 0.0f), 2097151.0f);
+    const uint64_t qy = (uint64_t)fminf(fmaxf((c.y - smin.y) * sy, 0.0f), 2097151.0f);
+    const uint64_t qz = (uint64_t)fminf(fmaxf((c.z - smin.z) * sz, 0.0f), 2097151.0f);
+    keys[t] = (expandBits21(qx) << 2) | (expandBits21(qy) << 1) | expandBits21(qz);
+    ids[t] = t;
+}
+
+// ---- 4. Karras hierarchy --------------------------------------------------------------------
+__device__ __forceinline__ int deltaKey(const uint64_t* __restrict__ keys, int n, int i, int j) {
+    if (j < 0 || j >= n)
+        return -1;
+    const uint64_t a = keys[i], b = keys[j];
+    if (a == b)
+        return 64 + __clz((uint32_t)i ^ (uint32_t)j);
+    return __clzll((long long)(a ^ b));
+}
+// children are encoded as index | 0x80000000 for leaves
+__global__ void k_hierarchy(int n, const uint64_t* __restrict__ keys, uint32_t* __restrict__ childL,
+                            uint32_t* __restrict__ childR, uint32_t* __restrict__ rangeFirst,
+                            uint32_t* __restrict__ rangeLast, uint32_t* __restrict__ parentOfInternal,
+                            uint32_t* __restrict__ parentOfLeaf) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1)
+        return;
+    const int d = (deltaKey(keys, n, i, i + 1) - deltaKey(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    const int deltaMin = deltaKey(keys, n, i, i - d);
+    int lmax = 2;
+    while (deltaKey(keys, n, i, i + lmax * d) > deltaMin)
+        lmax *= 2;
+    int l = 0;
+    for (int t = lmax / 2; t >= 1; t /= 2)
+        if (deltaKey(keys, n, i, i + (l + t) * d) > deltaMin)
+            l += t;
+    const int j = i + l * d;
+    const int deltaNode = deltaKey(keys, n, i, j);
+    int s = 0;
+    for (int t = (l + 1) / 2;; t = (t + 1) / 2) {
+        if (deltaKey(keys, n, i, i + (s + t) * d) > deltaNode)
+            s += t;
+        if (t == 1)
+            break;
+    }
+    const int gamma = i + s * d + min(d, 0);
+    const int first = min(i, j), last = max(i, j);
+    const uint32_t left = (first == gamma) ? ((uint32_t)gamma | 0x80000000u) : (uint32_t)gamma;
+    const uint32_t right = (last == gamma + 1) ? ((uint32_t)(gamma + 1) | 0x80000000u) : (uint32_t)(gamma + 1);
+    childL[i] = left;
+    childR[i] = right;
+    rangeFirst[i] = (uint32_t)first;
+    rangeLast[i] = (uint32_t)last;
+    if (left & 0x80000000u) parentOfLeaf[gamma] = (uint32_t)i; else parentOfInternal[gamma] = (uint32_t)i;
+    if (right & 0x80000000u) parentOfLeaf[gamma + 1] = (uint32_t)i; else parentOfInternal[gamma + 1] = (uint32_t)i;
+    if (i == 0)
+        parentOfInternal[0] = 0xFFFFFFFFu;
+}
+
+// ---- 5. refit -------------------------------------------------------------------------------
+// binary node boxes: internal i -> boxLo/Hi[i], leaf j -> boxLo/Hi[(n-1)+j]
+__global__ void k_refit(int n, const uint32_t* __restrict__ sortedIds, const float4* __restrict__ triLo,
+                        const float4* __restrict__ triHi, const uint32_t* __restrict__ childL,
+                        const uint32_t* __restrict__ childR, const uint32_t* __restrict__ parentOfInternal,
+                        const uint32_t* __restrict__ parentOfLeaf, uint32_t* __restrict__ counters,
+                        float4* boxLo, float4* boxHi) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n)
+        return;
+    const uint32_t tid = sortedIds[j];
+    boxLo[(n - 1) + j] = triLo[tid];
+    boxHi[(n - 1) + j] = triHi[tid];
+    if (n == 1)
+        return;
+    __threadfence();
+    uint32_t p = parentOfLeaf[j];
+    while (p != 0xFFFFFFFFu) {
+        if (atomicAdd(counters + p, 1u) == 0u)
+            return; // the sibling subtree is not done yet
+        __threadfence();
+        const uint32_t l = childL[p], r = childR[p];
+        const uint32_t li = (l & 0x80000000u) ? (uint32_t)(n - 1) + (l & 0x7FFFFFFFu) : l;
+        const uint32_t ri = (r & 0x80000000u) ? (uint32_t)(n - 1) + (r & 0x7FFFFFFFu) : r;
+        const volatile float4* vlo = boxLo;
+        const volatile float4* vhi = boxHi;
+        const float4 a = make_float4(vlo[li].x, vlo[li].y, vlo[li].z, 0), b = make_float4(vlo[ri].x, vlo[ri].y, vlo[ri].z, 0);
+        const float4 c = make_float4(vhi[li].x, vhi[li].y, vhi[li].z, 0), d = make_float4(vhi[ri].x, vhi[ri].y, vhi[ri].z, 0);
+        boxLo[p] = make_float4(fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z), 0.0f);
+        boxHi[p] = make_float4(fmaxf(c.x, d.x), fmaxf(c.y, d.y), fmaxf(c.z, d.z), 0.0f);
+        __threadfence();
+        p = parentOfInternal[p];
+    }
+}
+
+// ---- 6. collapse ----------------------------------------------------------------------------
+struct CollapseArgs {
+    int n;                   // triangles
+    uint32_t maxLeaf;
+    const uint32_t* childL;
+    const uint32_t* childR;
+    const uint32_t* rangeFirst;
+    const uint32_t* rangeLast;
+    const float4* boxLo;
+    const float4* boxHi;
+    const uint32_t* sortedIds;
+    uint4* nodes;            // output, 5 x uint4 per node
+    uint32_t* primRefs;      // output
+    uint32_t* counters;      // [0] nodes allocated, [1] primRefs allocated, [2] next-queue size
+    const uint2* queueIn;    // (wide node index, binary node ref)
+    uint2* queueOut;
+    uint32_t queueInSize;
+};
+
+__device__ __forceinline__ uint32_t refCount(const CollapseArgs &a, uint32_t ref) {
+    return (ref & 0x80000000u) ? 1u : (a.rangeLast[ref] - a.rangeFirst[ref] + 1u);
+}
+__device__ __forceinline__ uint32_t refBoxIndex(const CollapseArgs &a, uint32_t ref) {
+    return (ref & 0x80000000u) ? (uint32_t)(a.n - 1) + (ref & 0x7FFFFFFFu) : ref;
+}
+
+__global__ void k_collapse(CollapseArgs a) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.queueInSize)
+        return;
+    const uint2 item = a.queueIn[i];
+    const uint32_t wide = item.x;
+    const uint32_t root = item.y;
+
+    uint32_t ch[8];
+    float area[8]; // < 0: not expandable (leaf-sized)
+    int nc = 0;
+    auto pushChild = [&](uint32_t ref) {
+        const uint32_t bi = refBoxIndex(a, ref);
+        const float4 lo = a.boxLo[bi], hi = a.boxHi[bi];
+        const float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+        const bool leafSized = refCount(a, ref) <= a.maxLeaf;
+        ch[nc] = ref;
+        area[nc] = leafSized ? -1.0f : (dx * dy + dy * dz + dz * dx);
+        ++nc;
+    };
+    if (refCount(a, root) <= a.maxLeaf) {
+        pushChild(root);
+    }
+    else {
+        pushChild(a.childL[root]);
+        pushChild(a.childR[root]);
+        while (nc < 8) {
+            int best = -1;
+            float bestArea = -1.0f;
+            for (int k = 0; k < nc; ++k)
+                if (area[k] >= 0.0f && area[k] > bestArea) {
+                    bestArea = area[k];
+                    best = k;
+                }
+            if (best < 0)
+                break;
+            const uint32_t ref = ch[best];
+            // replace in place by the left child, append the right child
+            const int saved = nc;
+            nc = best;
+            pushChild(a.childL[ref]);
+            nc = saved;
+            pushChild(a.childR[ref]);
+        }
+    }
+
+    // classify + allocate
+    uint32_t numInt = 0, numLeafPrims = 0;
+    for (int k = 0; k < nc; ++k) {
+        if (area[k] >= 0.0f) ++numInt;
+        else numLeafPrims += refCount(a, ch[k]);
+    }
+    const uint32_t nodeBase = numInt ? atomicAdd(a.counters + 0, numInt) : 0xFFFFFFFFu;
+    const uint32_t primBase = numLeafPrims ? atomicAdd(a.counters + 1, numLeafPrims) : 0xFFFFFFFFu;
+    const uint32_t queueBase = numInt ? atomicAdd(a.counters + 2, numInt) : 0u;
+
+    // quantisation frame (setQuantizationAabb, common_shared.h:814-830) from the exact node box,
+    // with the exponent bumped until origin + 255 * scale covers the box in float arithmetic.
+    const uint32_t rbi = refBoxIndex(a, root);
+    const float4 nlo = a.boxLo[rbi], nhi = a.boxHi[rbi];
+    const float org[3] = { nlo.x, nlo.y, nlo.z };
+    const float mx[3] = { nhi.x, nhi.y, nhi.z };
+    uint32_t expo[3];
+    float scale[3], recScale[3];
+    for (int d = 0; d < 3; ++d) {
+        const float dd = (mx[d] - org[d]) * (1.0f / 255.0f);
+        const uint32_t us = __float_as_uint(dd);
+        uint32_t e = (us >> 23) + ((us & 0x7FFFFFu) ? 1u : 0u);
+        while (e < 254u && org[d] + 255.0f * __uint_as_float(e << 23) < mx[d])
+            ++e;
+        expo[d] = e;
+        scale[d] = __uint_as_float(e << 23);
+        recScale[d] = scale[d] != 0.0f ? 1.0f / scale[d] : 0.0f;
+    }
+
+    uint32_t qmin[3][2] = { { 0, 0 }, { 0, 0 }, { 0, 0 } }; // [axis][word]: 8 bytes as two uint32
+    uint32_t qmax[3][2] = { { 0, 0 }, { 0, 0 }, { 0, 0 } };
+    uint32_t metas[2] = { 0, 0 };
+    uint32_t internalMask = 0;
+    uint32_t nthInt = 0, leafOffset = 0;
+    for (int k = 0; k < 8; ++k) {
+        const int w = k >> 2, sh = 8 * (k & 3);
+        if (k >= nc) { // setInvalidChildBox (common_shared.h:852-860)
+            for (int d = 0; d < 3; ++d) {
+                qmin[d][w] |= 255u << sh;
+            }
+            continue;
+        }
+        const uint32_t ref = ch[k];
+        const uint32_t bi = refBoxIndex(a, ref);
+        const float4 lo4 = a.boxLo[bi], hi4 = a.boxHi[bi];
+        const float lo[3] = { lo4.x, lo4.y, lo4.z }, hi[3] = { hi4.x, hi4.y, hi4.z };
+        for (int d = 0; d < 3; ++d) {
+            // setChildAabb (common_shared.h:839-851) + a fix-up so that the *decoded* box
+            // (origin + q * scale, rounded) always contains the child box
+            int q0 = (int)dm_f2uint((lo[d] - org[d]) * recScale[d]);
+            q0 = min(q0, 255);
+            while (q0 > 0 && org[d] + (float)q0 * scale[d] > lo[d])
+                --q0;
+            int q1 = (int)min(dm_f2uint((hi[d] - org[d]) * recScale[d]) + 1u, 255u);
+            while (q1 < 255 && org[d] + (float)q1 * scale[d] < hi[d])
+                ++q1;
+            qmin[d][w] |= (uint32_t)q0 << sh;
+            qmax[d][w] |= (uint32_t)q1 << sh;
+        }
+        if (area[k] >= 0.0f) {
+            internalMask |= 1u << k;
+            a.queueOut[queueBase + nthInt] = make_uint2(nodeBase + nthInt, ref);
+            ++nthInt;
+        }
+        else {
+            metas[w] |= leafOffset << sh;
+            uint32_t first, last;
+            if (ref & 0x80000000u) {
+                first = last = ref & 0x7FFFFFFFu;
+            }
+            else {
+                first = a.rangeFirst[ref];
+                last = a.rangeLast[ref];
+            }
+            for (uint32_t s = first; s <= last; ++s)
+                a.primRefs[primBase + leafOffset + (s - first)] = a.sortedIds[s] | (s == last ? 0x80000000u : 0u);
+            leafOffset += last - first + 1;
+        }
+    }
+
+    uint4* np = a.nodes + 5 * (size_t)wide;
+    np[0] = make_uint4(__float_as_uint(org[0]), __float_as_uint(org[1]), __float_as_uint(org[2]),
+                       expo[0] | (expo[1] << 8) | (expo[2] << 16) | (internalMask << 24));
+    np[1] = make_uint4(nodeBase, primBase, metas[0], metas[1]);
+    np[2] = make_uint4(qmin[0][0], qmin[0][1], qmin[1][0], qmin[1][1]);
+    np[3] = make_uint4(qmin[2][0], qmin[2][1], qmax[0][0], qmax[0][1]);
+    np[4] = make_uint4(qmax[1][0], qmax[1][1], qmax[2][0], qmax[2][1]);
+}
+
+__global__ void k_initBounds(uint32_t* sceneBounds) {
+    if (threadIdx.x < 3) sceneBounds[threadIdx.x] = 0xFFFFFFFFu;
+    else if (threadIdx.x < 6) sceneBounds[threadIdx.x] = 0u;
+}
+
+// ---------------------------------------------------------------------------------------------
+int buildBvh(gfx_ctx* ctx, cudaStream_t stream, uint32_t flags) {
+    SceneState &S = ctx->scene;
+    const uint32_t n = S.numFlatTris;
+    uint32_t maxLeaf = flags & 0xFFu;
+    if (maxLeaf == 0) maxLeaf = 4;
+    if (maxLeaf > 31) maxLeaf = 31;
+
+    BvhState &B = ctx->bvh;
+    B.release();
+    B.numTris = n;
+    if (n == 0) {
+        B.numNodes = 0;
+        B.numPrimRefs = 0;
+        return GFX_OK;
+    }
+    GFX_CUDA(ctx, cudaMalloc(&B.tris, (size_t)n * 48));
+    GFX_CUDA(ctx, cudaMalloc(&B.primRefs, (size_t)n * 4));
+    // every wide node has >= 2 children except a degenerate root, so #nodes <= n
+    GFX_CUDA(ctx, cudaMalloc(&B.nodes, (size_t)max(n, 1u) * 80));
+    GFX_CUDA(ctx, cudaMalloc(&B.sceneBounds, 6 * 4));
+
+    // scratch
+    float4 *triLo, *triHi, *boxLo, *boxHi;
+    uint64_t *keys, *keysSorted;
+    uint32_t *ids, *idsSorted, *childL, *childR, *rangeFirst, *rangeLast, *parentI, *parentL, *arrive, *counters;
+    uint2 *queueA, *queueB;
+    GFX_CUDA(ctx, cudaMalloc(&triLo, (size_t)n * 16));
+    GFX_CUDA(ctx, cudaMalloc(&triHi, (size_t)n * 16));
+    GFX_CUDA(ctx, cudaMalloc(&boxLo, (size_t)(2 * n) * 16));
+    GFX_CUDA(ctx, cudaMalloc(&boxHi, (size_t)(2 * n) * 16));
+    GFX_CUDA(ctx, cudaMalloc(&keys, (size_t)n * 8));
+    GFX_CUDA(ctx, cudaMalloc(&keysSorted, (size_t)n * 8));
+    GFX_CUDA(ctx, cudaMalloc(&ids, (size_t)n * 4));
+    GFX_CUDA(ctx, cudaMalloc(&idsSorted, (size_t)n * 4));
+    GFX_CUDA(ctx, cudaMalloc(&childL, (size_t)n * 4));
+    GFX_CUDA(ctx, cudaMalloc(&childR, (size_t)n * 4));
+    GFX_CUDA(ctx, cudaMalloc(&rangeFirst, (size_t)n * 4));
+    GFX_CUDA(ctx, cudaMalloc(&rangeLast, (size_t)n * 4));
+    GFX_CUDA(ctx, cudaMalloc(&parentI, (size_t)n * 4));
+    GFX_CUDA(ctx, cudaMalloc(&parentL, (size_t)n * 4));
+    GFX_CUDA(ctx, cudaMalloc(&arrive, (size_t)n * 4));
+    GFX_CUDA(ctx, cudaMalloc(&counters, 4 * 4));
+    GFX_CUDA(ctx, cudaMalloc(&queueA, (size_t)n * 8));
+    GFX_CUDA(ctx, cudaMalloc(&queueB, (size_t)n * 8));
+
+    const DevScene dev = ctx->devScene();
+    const uint32_t blocks = (n + 255) / 256;
+    k_initBounds<<<1, 32, 0, stream>>>(B.sceneBounds); ctx->launches++;
+    k_flatten<<<blocks, 256, 0, stream>>>(dev, S.geomTriOffsets, S.numGeoms, n, B.tris, triLo, triHi, B.sceneBounds); ctx->launches++;
+    k_morton<<<blocks, 256, 0, stream>>>(n, triLo, triHi, B.sceneBounds, keys, ids); ctx->launches++;
+
+    size_t tmpBytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, keys, keysSorted, ids, idsSorted, (int)n, 0, 63, stream);
+    void* tmp = nullptr;
+    GFX_CUDA(ctx, cudaMalloc(&tmp, tmpBytes));
+    cub::DeviceRadixSort::SortPairs(tmp, tmpBytes, keys, keysSorted, ids, idsSorted, (int)n, 0, 63, stream); ctx->launches += 8;
+
+    GFX_CUDA(ctx, cudaMemsetAsync(arrive, 0, (size_t)n * 4, stream));
+    if (n > 1) {
+        k_hierarchy<<<(n - 1 + 255) / 256, 256, 0, stream>>>((int)n, keysSorted, childL, childR, rangeFirst, rangeLast, parentI, parentL); ctx->launches++;
+    }
+    k_refit<<<blocks, 256, 0, stream>>>((int)n, idsSorted, triLo, triHi, childL, childR, parentI, parentL, arrive, boxLo, boxHi); ctx->launches++;
+
+    // collapse, level by level
+    uint32_t hostCounters[4] = { 1u, 0u, 0u, 0u }; // node 0 = root is pre-allocated
+    GFX_CUDA(ctx, cudaMemcpyAsync(counters, hostCounters, 16, cudaMemcpyHostToDevice, stream));
+    const uint2 rootItem = make_uint2(0u, n == 1 ? 0x80000000u : 0u);
+    GFX_CUDA(ctx, cudaMemcpyAsync(queueA, &rootItem, 8, cudaMemcpyHostToDevice, stream));
+    CollapseArgs a;
+    a.n = (int)n;
+    a.maxLeaf = maxLeaf;
+    a.childL = childL; a.childR = childR; a.rangeFirst = rangeFirst; a.rangeLast = rangeLast;
+    a.boxLo = boxLo; a.boxHi = boxHi; a.sortedIds = idsSorted;
+    a.nodes = reinterpret_cast<uint4*>(B.nodes);
+    a.primRefs = B.primRefs;
+    a.counters = counters;
+    uint32_t queueSize = 1;
+    uint2 *qin = queueA, *qout = queueB;
+    uint32_t levels = 0;
+    while (queueSize > 0) {
+        a.queueIn = qin;
+        a.queueOut = qout;
+        a.queueInSize = queueSize;
+        k_collapse<<<(queueSize + 127) / 128, 128, 0, stream>>>(a); ctx->launches++;
+        GFX_CUDA(ctx, cudaMemcpyAsync(hostCounters, counters, 16, cudaMemcpyDeviceToHost, stream));
+        GFX_CUDA(ctx, cudaStreamSynchronize(stream));
+        queueSize = hostCounters[2];
+        const uint32_t zero = 0;
+        GFX_CUDA(ctx, cudaMemcpyAsync(counters + 2, &zero, 4, cudaMemcpyHostToDevice, stream));
+        std::swap(qin, qout);
+        if (++levels > 4096) {
+            ctx->setError("gfx_bvh_build: collapse did not converge");
+            return GFX_ERR_CUDA;
+        }
+    }
+    B.numNodes = hostCounters[0];
+    B.numPrimRefs = hostCounters[1];
+    B.levels = levels;
+    uint32_t ob[6];
+    GFX_CUDA(ctx, cudaMemcpy(ob, B.sceneBounds, 24, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 6; ++i) {
+        const uint32_t u = ob[i] ^ (ob[i] >= 0x80000000u ? 0x80000000u : 0xFFFFFFFFu);
+        float f;
+        memcpy(&f, &u, 4);
+        (i < 3 ? B.sceneMin[i] : B.sceneMax[i - 3]) = f;
+    }
+
+    cudaFree(tmp);
+    cudaFree(triLo); cudaFree(triHi); cudaFree(boxLo); cudaFree(boxHi); cudaFree(keys); cudaFree(keysSorted);
+    cudaFree(ids); cudaFree(idsSorted); cudaFree(childL); cudaFree(childR); cudaFree(rangeFirst); cudaFree(rangeLast);
+    cudaFree(parentI); cudaFree(parentL); cudaFree(arrive); cudaFree(counters); cudaFree(queueA); cudaFree(queueB);
+    return GFX_OK;
+}
+
+} // namespace gfx

@@ -1,0 +1,105 @@
+// context.h — host-side state behind the opaque gfx_ctx of include/gfxb200.h.
+#pragma once
+#include "scene.cuh"
+#include <string>
+#include <vector>
+#include <cstdio>
+#include <cstring>
+
+namespace gfx {
+
+struct SceneState {
+    float4* vertices = nullptr;
+    uint4* triangles = nullptr;
+    DevMesh* meshes = nullptr;
+    GfxMaterialDesc* materials = nullptr;
+    DevInstance* instances = nullptr;
+    uint32_t* instanceMeshSlots = nullptr;
+    uint2* geomToInstMesh = nullptr;
+    uint32_t* geomTriOffsets = nullptr; // numGeoms + 1
+    float* primWeights = nullptr;
+    float* primCdf = nullptr;
+    float* geomWeights = nullptr;
+    float* geomCdf = nullptr;
+    float* instWeights = nullptr;
+    float* instCdf = nullptr;
+    float* instIntegral = nullptr;
+    uint32_t numMeshes = 0, numMaterials = 0, numInstances = 0, numInstanceMeshSlots = 0;
+    uint32_t numGeoms = 0, numFlatTris = 0, numMeshTris = 0, numVertices = 0;
+    bool uploaded = false;
+    bool staticLightDistsBuilt = false;
+    std::vector<DevMesh> hostMeshes;
+    std::vector<DevInstance> hostInstances;
+    void release();
+};
+
+struct BvhState {
+    void* nodes = nullptr;       // GfxBvhNode8[numNodes]
+    uint32_t* primRefs = nullptr;
+    float4* tris = nullptr;      // GfxTriangleStorage[numTris]
+    uint32_t* sceneBounds = nullptr;
+    uint32_t* overflowFlag = nullptr;
+    uint32_t numNodes = 0, numPrimRefs = 0, numTris = 0, levels = 0;
+    float sceneMin[3] = { 0, 0, 0 }, sceneMax[3] = { 0, 0, 0 };
+    bool ready = false;
+    void release();
+};
+
+struct FrameState {
+    uint32_t W = 0, H = 0;
+    uint4* gb0[2] = { nullptr, nullptr };
+    float2* gb1[2] = { nullptr, nullptr };
+    float4* gb2[2] = { nullptr, nullptr };
+    uint4* gb3[2] = { nullptr, nullptr };
+    unsigned long long* rng = nullptr;
+    float4* reservoir[2] = { nullptr, nullptr };
+    float2* reservoirInfo[2] = { nullptr, nullptr };
+    float4* beauty = nullptr;
+    float4* albedo = nullptr;
+    float4* normal = nullptr;
+    float2* neighborDeltas = nullptr;
+    // SVGF state
+    float4* svgfLighting[2] = { nullptr, nullptr };  // lighting rgb + variance, ping-pong
+    float4* svgfMoments[2] = { nullptr, nullptr };   // first/second luminance moments + history length
+    float4* svgfPrevLighting = nullptr;
+    float4* svgfFinal[2] = { nullptr, nullptr };
+    float* svgfDepth[2] = { nullptr, nullptr };
+    bool created = false;
+    void release();
+};
+
+} // namespace gfx
+
+struct gfx_ctx {
+    int device = 0;
+    std::string lastError;
+    uint64_t launches = 0;
+    gfx::SceneState scene;
+    gfx::BvhState bvh;
+    gfx::FrameState frame;
+
+    void setError(const std::string &msg) { lastError = msg; }
+    gfx::DevScene devScene() const;
+    gfx::DevFrame devFrame() const;
+};
+
+#define GFX_CUDA(ctx, call) \
+    do { \
+        const cudaError_t err_ = (call); \
+        if (err_ != cudaSuccess) { \
+            char buf_[512]; \
+            snprintf(buf_, sizeof(buf_), "%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(err_)); \
+            (ctx)->setError(buf_); \
+            return err_ == cudaErrorMemoryAllocation ? GFX_ERR_OUT_OF_MEMORY : GFX_ERR_CUDA; \
+        } \
+    } while (0)
+
+namespace gfx {
+int buildBvh(gfx_ctx* ctx, cudaStream_t stream, uint32_t flags);
+int traceRays(gfx_ctx* ctx, cudaStream_t stream, const GfxRay* dRays, uint32_t numRays, GfxHitObject* dHits, int mode);
+int buildLightDistributions(gfx_ctx* ctx, cudaStream_t stream, uint32_t bufferIndex);
+int launchGBuffer(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* p);
+int launchReSTIR(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* p, int pass);
+int launchSVGF(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* p, int pass, uint32_t stage);
+DevFrameParams makeDevParams(const gfx_ctx* ctx, const GfxFrameParams* p);
+} // namespace gfx

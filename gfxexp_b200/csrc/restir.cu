@@ -1,0 +1,625 @@
+// restir.cu — ReSTIR DI passes as sm_100a kernels.
+//
+// Replaces restir.optixPipeline.launch(W, H, 1) with the ray-generation entry points
+// performInitialRIS / performInitialAndTemporalRIS{Biased,Unbiased} / performSpatialRIS{Biased,
+// Unbiased} / shading (restir_di/gpu_kernels/optix_restir_di_kernels.cu:14-287, 303-547, 559-637;
+// launch sites restir_di/restir_di_main.cpp:2378-2421) and the helpers they share
+// (sampleLight<false> restir_di_shared.h:320-516, performDirectLighting :518-557,
+// evaluateVisibility :559-582, testNeighbor :747-771).  Visibility rays run through the inline
+// any-hit traversal of traverse.cuh instead of optixTrace + the AH program.
+//
+// Per-pixel state is SoA: reservoirs are three float4 planes (Le|sumW, pos|M, n|-) so a pixel's own
+// reservoir is three coalesced 16-byte loads; neighbour gathers hit the same planes through L2.
+// RNG draw order per pixel is the reference's.
+#include "traverse.cuh"
+#include "shading.cuh"
+#include "context.h"
+
+namespace gfx {
+
+struct LightSample { // restir_di_shared.h:89-96
+    f3 emittance, position, normal;
+    uint32_t atInfinity;
+};
+GFX_D LightSample emptyLightSample() {
+    LightSample s;
+    s.emittance = f3(0.0f);
+    s.position = f3(0.0f);
+    s.normal = f3(0.0f);
+    s.atInfinity = 0;
+    return s;
+}
+struct Reservoir { // restir_di_shared.h:106-139
+    LightSample sample;
+    float sumWeights;
+    uint32_t streamLength;
+    GFX_D void initialize(const LightSample &s) { sample = s; sumWeights = 0; streamLength = 0; }
+    GFX_D bool update(const LightSample &newSample, float weight, float u) {
+        sumWeights += weight;
+        const bool accepted = u < weight / sumWeights;
+        if (accepted)
+            sample = newSample;
+        ++streamLength;
+        return accepted;
+    }
+};
+
+GFX_D float convertToWeight(const f3 &c) { return (c.x + c.y + c.z) / 3; } // restir_di_shared.h:82-85
+
+GFX_D void sampleLight(const DevScene &s, float ul, float u0, float u1, LightSample* lightSample, float* areaPDensity) {
+    // restir_di_shared.h:320-516 with sampleEnvLight = false, useSolidAngleSampling = false
+    f3 emittance(0.0f);
+    float lightProb = 1.0f;
+
+    DiscreteDistribution1D lightInstDist;
+    lightInstDist.weights = s.instWeights;
+    lightInstDist.cdf = s.instCdf;
+    lightInstDist.integral = *s.instIntegral;
+    lightInstDist.numValues = s.numInstances;
+    float instProb, uGeomInst;
+    const uint32_t instSlot = lightInstDist.sample(ul, &instProb, &uGeomInst);
+    lightProb *= instProb;
+    const DevInstance* inst = s.instances + instSlot;
+    if (instProb == 0.0f) {
+        *areaPDensity = 0.0f;
+        return;
+    }
+
+    DiscreteDistribution1D lightGeomInstDist;
+    lightGeomInstDist.weights = s.geomWeights + inst->firstMeshSlot;
+    lightGeomInstDist.cdf = s.geomCdf + inst->firstMeshSlot;
+    lightGeomInstDist.integral = inst->geomIntegral;
+    lightGeomInstDist.numValues = inst->numMeshSlots;
+    float geomInstProb, uPrim;
+    const uint32_t geomInstIndexInInst = lightGeomInstDist.sample(uGeomInst, &geomInstProb, &uPrim);
+    const uint32_t geomInstSlot = s.instanceMeshSlots[inst->firstMeshSlot + geomInstIndexInInst];
+    lightProb *= geomInstProb;
+    const DevMesh mesh = s.meshes[geomInstSlot];
+    if (geomInstProb == 0.0f) {
+        *areaPDensity = 0.0f;
+        return;
+    }
+
+    DiscreteDistribution1D emitterPrimDist;
+    emitterPrimDist.weights = s.primWeights + mesh.triBase;
+    emitterPrimDist.cdf = s.primCdf + mesh.triBase;
+    emitterPrimDist.integral = mesh.primIntegral;
+    emitterPrimDist.numValues = mesh.numTriangles;
+    float primProb;
+    const uint32_t primIndex = emitterPrimDist.sample(uPrim, &primProb);
+    lightProb *= primProb;
+
+    const GfxMaterialDesc* mat = s.materials + mesh.materialSlot;
+    const uint4 tri = __ldg(s.triangles + mesh.triBase + primIndex);
+    const float4* vA = s.vertices + 3 * (size_t)(mesh.vertexBase + tri.x);
+    const float4* vB = s.vertices + 3 * (size_t)(mesh.vertexBase + tri.y);
+    const float4* vC = s.vertices + 3 * (size_t)(mesh.vertexBase + tri.z);
+    const float4 a0 = __ldg(vA), a1 = __ldg(vA + 1);
+    const float4 b0 = __ldg(vB), b1 = __ldg(vB + 1);
+    const float4 c0 = __ldg(vC), c1 = __ldg(vC + 1);
+    const f3 pA = xfmPoint(inst->transform, f3(a0.x, a0.y, a0.z));
+    const f3 pB = xfmPoint(inst->transform, f3(b0.x, b0.y, b0.z));
+    const f3 pC = xfmPoint(inst->transform, f3(c0.x, c0.y, c0.z));
+    const f3 geomNormal = cross(pB - pA, pC - pA);
+
+    // A Low-Distortion Map Between Triangle and Square (:485-498)
+    float bcA = 0.5f * u0;
+    float bcB = 0.5f * u1;
+    const float offset = bcB - bcA;
+    if (offset > 0)
+        bcB += offset;
+    else
+        bcA -= offset;
+    const float bcC = 1 - (bcA + bcB);
+
+    const float recArea = 2.0f / length(geomNormal);
+    *areaPDensity = lightProb * recArea;
+
+    lightSample->position = bcA * pA + bcB * pB + bcC * pC;
+    lightSample->atInfinity = 0;
+    lightSample->normal = bcA * f3(a1.x, a1.y, a1.z) + bcB * f3(b1.x, b1.y, b1.z) + bcC * f3(c1.x, c1.y, c1.z);
+    lightSample->normal = normalize(mul3x3(inst->normalMatrix, lightSample->normal));
+
+    if (mat->hasEmittance) {
+        emittance = f3(1.0f, 1.0f, 1.0f);
+        emittance *= f3(mat->emittance[0], mat->emittance[1], mat->emittance[2]);
+    }
+    lightSample->emittance = emittance;
+}
+
+GFX_D bool traceVisibility(const DevScene &s, const f3 &org, const f3 &dir, float tmax) {
+    const Hit h = traverseBvh<true>(s.bvh, org, dir, 0.0f, tmax);
+    return h.storageIndex == 0xFFFFFFFFu;
+}
+
+GFX_D bool evaluateVisibility(const DevScene &s, const f3 &shadingPoint, const LightSample &ls) { // :559-582
+    f3 shadowRayDir = ls.atInfinity ? ls.position : (ls.position - shadingPoint);
+    const float dist2 = sqLength(shadowRayDir);
+    float dist = sqrtf(dist2);
+    shadowRayDir /= dist;
+    if (ls.atInfinity)
+        dist = 1e+10f;
+    return traceVisibility(s, shadingPoint, shadowRayDir, dist * 0.9999f);
+}
+
+template <bool withVisibility>
+GFX_D f3 performDirectLighting(const DevScene &s, const f3 &shadingPoint, const f3 &vOutLocal,
+                               const ReferenceFrame &shadingFrame, const BSDF &bsdf, const LightSample &ls) { // :518-557
+    f3 shadowRayDir = ls.atInfinity ? ls.position : (ls.position - shadingPoint);
+    const float dist2 = sqLength(shadowRayDir);
+    float dist = sqrtf(dist2);
+    shadowRayDir /= dist;
+    const f3 shadowRayDirLocal = shadingFrame.toLocal(shadowRayDir);
+
+    const float lpCos = dot(-shadowRayDir, ls.normal);
+    const float spCos = shadowRayDirLocal.z;
+
+    float visibility = 1.0f;
+    if (withVisibility) {
+        if (ls.atInfinity)
+            dist = 1e+10f;
+        if (!traceVisibility(s, shadingPoint, shadowRayDir, dist * 0.9999f))
+            visibility = 0.0f;
+    }
+
+    if (visibility > 0 && lpCos > 0) {
+        const f3 Le = ls.emittance / kPi;
+        const f3 fsValue = bsdf.evaluate(vOutLocal, shadowRayDirLocal);
+        const float G = lpCos * fabsf(spCos) / dist2;
+        return fsValue * Le * G;
+    }
+    return f3(0.0f);
+}
+
+GFX_D Reservoir loadReservoir(const DevFrame &f, uint32_t idx, size_t pix) {
+    const size_t n = (size_t)f.W * f.H;
+    const float4 a = f.reservoir[idx][pix], b = f.reservoir[idx][n + pix], c = f.reservoir[idx][2 * n + pix];
+    Reservoir r;
+    r.sample.emittance = f3(a.x, a.y, a.z);
+    r.sumWeights = a.w;
+    r.sample.position = f3(b.x, b.y, b.z);
+    const uint32_t m = __float_as_uint(b.w);
+    r.streamLength = m & 0x7FFFFFFFu;
+    r.sample.atInfinity = m >> 31;
+    r.sample.normal = f3(c.x, c.y, c.z);
+    return r;
+}
+GFX_D void storeReservoir(const DevFrame &f, uint32_t idx, size_t pix, const Reservoir &r) {
+    const size_t n = (size_t)f.W * f.H;
+    f.reservoir[idx][pix] = make_float4(r.sample.emittance.x, r.sample.emittance.y, r.sample.emittance.z, r.sumWeights);
+    f.reservoir[idx][n + pix] = make_float4(r.sample.position.x, r.sample.position.y, r.sample.position.z,
+                                            __uint_as_float((r.streamLength & 0x7FFFFFFFu) | (r.sample.atInfinity << 31)));
+    f.reservoir[idx][2 * n + pix] = make_float4(r.sample.normal.x, r.sample.normal.y, r.sample.normal.z, 0.0f);
+}
+
+template <bool testGeometry>
+GFX_D bool testNeighbor(const DevFrame &f, const DevCamera &camera, uint32_t nbBufIdx, int nbx, int nby, float dist,
+                        const f3 &normalInWorld) { // restir_di_shared.h:747-771
+    if (nbx < 0 || nbx >= (int)f.W || nby < 0 || nby >= (int)f.H)
+        return false;
+    const size_t nbPix = (size_t)nby * f.W + nbx;
+    if (f.gb0[nbBufIdx][nbPix].x == 0xFFFFFFFFu)
+        return false;
+    if (testGeometry) {
+        const float4 g2 = f.gb2[nbBufIdx][nbPix];
+        const uint4 g3 = f.gb3[nbBufIdx][nbPix];
+        const f3 nbPositionInWorld(g2.x, g2.y, g2.z);
+        const f3 nbNormalInWorld = decodeVector(g3.x);
+        const float nbDist = length(camera.position - nbPositionInWorld);
+        if (fabsf(nbDist - dist) / dist > 0.1f || dot(normalInWorld, nbNormalInWorld) < 0.9f)
+            return false;
+    }
+    return true;
+}
+
+GFX_D BSDF setupBsdf(const DevScene &s, uint32_t matSlot) {
+    const GfxMaterialDesc* m = s.materials + matSlot;
+    BSDF b;
+    b.setup(m->bsdfType, m->p0, m->p1, m->p2);
+    return b;
+}
+
+// ---------------------------------------------------------------------------------------------
+template <bool withTemporalRIS, bool useUnbiasedEstimator>
+__global__ void __launch_bounds__(64) k_initialAndTemporalRIS(DevScene s, DevFrame f, DevFrameParams p) {
+    // optix_restir_di_kernels.cu:14-287
+    const uint32_t x = blockIdx.x * 8 + threadIdx.x;
+    const uint32_t y = p.y0 + blockIdx.y * 8 + threadIdx.y;
+    if (x >= f.W || y >= p.y1)
+        return;
+    const size_t pix = (size_t)y * f.W + x;
+    const uint32_t curBufIdx = p.bufferIndex;
+
+    const uint4 gb0 = f.gb0[curBufIdx][pix];
+    if (gb0.x == 0xFFFFFFFFu)
+        return;
+    const float4 gb2 = f.gb2[curBufIdx][pix];
+    const uint4 gb3 = f.gb3[curBufIdx][pix];
+
+    f3 positionInWorld(gb2.x, gb2.y, gb2.z);
+    const f3 geometricNormalInWorld = decodeVector(__float_as_uint(gb2.w));
+
+    PCG32RNG rng{ f.rng[pix] };
+
+    f3 vOut = p.camera.position - positionInWorld;
+    const float frontHit = dot(vOut, geometricNormalInWorld) >= 0.0f ? 1.0f : -1.0f;
+    positionInWorld = offsetRayOrigin(positionInWorld, frontHit * geometricNormalInWorld);
+    const float dist = length(vOut);
+    vOut /= dist;
+
+    const f3 shadingNormalInWorld = decodeVector(gb3.x);
+    const f3 shadingTangentInWorld = decodeVector(gb3.y);
+    const ReferenceFrame shadingFrame(shadingNormalInWorld, shadingTangentInWorld);
+    const f3 vOutLocal = shadingFrame.toLocal(vOut);
+    const BSDF bsdf = setupBsdf(s, gb3.w);
+
+    const uint32_t curResIndex = p.currentReservoirIndex;
+    Reservoir reservoir;
+    reservoir.initialize(emptyLightSample());
+
+    float selectedTargetDensity = 0.0f;
+    const uint32_t numCandidates = 1u << p.log2NumCandidateSamples;
+    for (uint32_t i = 0; i < numCandidates; ++i) {
+        const float ul = rng.getFloat0cTo1o();
+        const float probToSampleCurLightType = 1.0f;
+        LightSample lightSample = emptyLightSample();
+        float probDensity;
+        const float u0 = rng.getFloat0cTo1o();
+        const float u1 = rng.getFloat0cTo1o();
+        sampleLight(s, ul, u0, u1, &lightSample, &probDensity);
+        const f3 cont = performDirectLighting<false>(s, positionInWorld, vOutLocal, shadingFrame, bsdf, lightSample);
+        probDensity *= probToSampleCurLightType;
+        const float targetDensity = convertToWeight(cont);
+        const float weight = targetDensity / probDensity;
+        if (reservoir.update(lightSample, weight, rng.getFloat0cTo1o()))
+            selectedTargetDensity = targetDensity;
+    }
+
+    float recPDFEstimate = reservoir.sumWeights / (selectedTargetDensity * reservoir.streamLength);
+    if (!isfinite(recPDFEstimate)) {
+        recPDFEstimate = 0.0f;
+        selectedTargetDensity = 0.0f;
+    }
+
+    if (p.reuseVisibility && selectedTargetDensity > 0.0f) {
+        if (!evaluateVisibility(s, positionInWorld, reservoir.sample)) {
+            recPDFEstimate = 0.0f;
+            selectedTargetDensity = 0.0f;
+        }
+    }
+
+    if (withTemporalRIS) {
+        const uint32_t prevBufIdx = (curBufIdx + 1) % 2;
+        const uint32_t prevResIndex = (curResIndex + 1) % 2;
+
+        bool neighborIsSelected = false;
+        const uint32_t selfStreamLength = reservoir.streamLength;
+        if (recPDFEstimate == 0.0f)
+            reservoir.initialize(emptyLightSample());
+        uint32_t combinedStreamLength = selfStreamLength;
+        const uint32_t maxPrevStreamLength = 20 * selfStreamLength;
+
+        const float2 gb1 = f.gb1[curBufIdx][pix];
+        const int nbx = dm_f2int(x + 0.5f - gb1.x);
+        const int nby = dm_f2int(y + 0.5f - gb1.y);
+
+        const bool acceptedNeighbor = testNeighbor<!useUnbiasedEstimator>(f, p.camera, prevBufIdx, nbx, nby, dist, shadingNormalInWorld);
+        if (acceptedNeighbor) {
+            const size_t nbPix = (size_t)nby * f.W + nbx;
+            const Reservoir neighbor = loadReservoir(f, prevResIndex, nbPix);
+            const float2 neighborInfo = f.reservoirInfo[prevResIndex][nbPix];
+            const LightSample nbLightSample = neighbor.sample;
+            const f3 cont = performDirectLighting<false>(s, positionInWorld, vOutLocal, shadingFrame, bsdf, nbLightSample);
+            const float targetDensity = convertToWeight(cont);
+            const uint32_t nbStreamLength = min(neighbor.streamLength, maxPrevStreamLength);
+            const float weight = targetDensity * neighborInfo.x * nbStreamLength;
+            if (reservoir.update(nbLightSample, weight, rng.getFloat0cTo1o())) {
+                selectedTargetDensity = targetDensity;
+                if (useUnbiasedEstimator)
+                    neighborIsSelected = true;
+            }
+            combinedStreamLength += nbStreamLength;
+        }
+        reservoir.streamLength = combinedStreamLength;
+
+        float weightForEstimate;
+        if (useUnbiasedEstimator) { // :192-266, useMIS_RIS = true
+            const LightSample selectedLightSample = reservoir.sample;
+            float numWeight, denomWeight;
+            {
+                const f3 cont = performDirectLighting<false>(s, positionInWorld, vOutLocal, shadingFrame, bsdf, selectedLightSample);
+                const float targetDensityForSelf = convertToWeight(cont);
+                numWeight = targetDensityForSelf;
+                denomWeight = targetDensityForSelf * selfStreamLength;
+            }
+            if (acceptedNeighbor) {
+                const size_t nbPix = (size_t)nby * f.W + nbx;
+                const float4 nbGb2 = f.gb2[prevBufIdx][nbPix];
+                const uint4 nbGb3 = f.gb3[prevBufIdx][nbPix];
+                f3 nbPositionInWorld(nbGb2.x, nbGb2.y, nbGb2.z);
+                const f3 nbGeometricNormalInWorld = decodeVector(__float_as_uint(nbGb2.w));
+                const f3 nbVOut = normalize(p.prevCamera.position - nbPositionInWorld);
+                const float nbFrontHit = dot(nbVOut, nbGeometricNormalInWorld) >= 0.0f ? 1.0f : -1.0f;
+                nbPositionInWorld = offsetRayOrigin(nbPositionInWorld, nbFrontHit * nbGeometricNormalInWorld);
+                const BSDF nbBsdf = setupBsdf(s, nbGb3.w);
+                const ReferenceFrame nbShadingFrame(decodeVector(nbGb3.x), decodeVector(nbGb3.y));
+                const f3 nbVOutLocal = nbShadingFrame.toLocal(nbVOut);
+                const Reservoir neighbor = loadReservoir(f, prevResIndex, nbPix);
+                const f3 cont = performDirectLighting<false>(s, nbPositionInWorld, nbVOutLocal, nbShadingFrame, nbBsdf, selectedLightSample);
+                const float nbTargetDensity = convertToWeight(cont);
+                const uint32_t nbStreamLength = min(neighbor.streamLength, maxPrevStreamLength);
+                denomWeight += nbTargetDensity * nbStreamLength;
+                if (neighborIsSelected)
+                    numWeight = nbTargetDensity;
+            }
+            weightForEstimate = numWeight / denomWeight;
+        }
+        else {
+            weightForEstimate = 1.0f / reservoir.streamLength;
+        }
+
+        recPDFEstimate = weightForEstimate * reservoir.sumWeights / selectedTargetDensity;
+        if (!isfinite(recPDFEstimate)) {
+            recPDFEstimate = 0.0f;
+            selectedTargetDensity = 0.0f;
+        }
+    }
+
+    f.rng[pix] = rng.state;
+    storeReservoir(f, curResIndex, pix, reservoir);
+    f.reservoirInfo[curResIndex][pix] = make_float2(recPDFEstimate, selectedTargetDensity);
+}
+
+// ---------------------------------------------------------------------------------------------
+GFX_D void neighborCoord(const DevFrame &f, const DevFrameParams &p, uint32_t x, uint32_t y, int nIdx, PCG32RNG &rng,
+                         int* nbx, int* nby) { // optix_restir_di_kernels.cu:356-371
+    float radius = p.spatialNeighborRadius;
+    float deltaX, deltaY;
+    if (p.useLowDiscrepancyNeighbors) {
+        const float2 delta = __ldg(f.neighborDeltas + ((p.spatialNeighborBaseIndex + nIdx) % 1024));
+        deltaX = radius * delta.x;
+        deltaY = radius * delta.y;
+    }
+    else {
+        radius *= sqrtf(rng.getFloat0cTo1o());
+        const float angle = 2 * kPi * rng.getFloat0cTo1o();
+        float sa, ca;
+        dm_sincos(angle, &sa, &ca);
+        deltaX = radius * ca;
+        deltaY = radius * sa;
+    }
+    *nbx = dm_f2int(x + 0.5f + deltaX);
+    *nby = dm_f2int(y + 0.5f + deltaY);
+}
+
+template <bool useUnbiasedEstimator>
+__global__ void __launch_bounds__(64) k_spatialRIS(DevScene s, DevFrame f, DevFrameParams p) {
+    // optix_restir_di_kernels.cu:303-547
+    const uint32_t x = blockIdx.x * 8 + threadIdx.x;
+    const uint32_t y = p.y0 + blockIdx.y * 8 + threadIdx.y;
+    if (x >= f.W || y >= p.y1)
+        return;
+    const size_t pix = (size_t)y * f.W + x;
+    const uint32_t bufIdx = p.bufferIndex;
+
+    const uint4 gb0 = f.gb0[bufIdx][pix];
+    if (gb0.x == 0xFFFFFFFFu)
+        return;
+    const float4 gb2 = f.gb2[bufIdx][pix];
+    const uint4 gb3 = f.gb3[bufIdx][pix];
+
+    f3 positionInWorld(gb2.x, gb2.y, gb2.z);
+    const f3 geometricNormalInWorld = decodeVector(__float_as_uint(gb2.w));
+    PCG32RNG rng{ f.rng[pix] };
+
+    f3 vOut = p.camera.position - positionInWorld;
+    const float frontHit = dot(vOut, geometricNormalInWorld) >= 0.0f ? 1.0f : -1.0f;
+    positionInWorld = offsetRayOrigin(positionInWorld, frontHit * geometricNormalInWorld);
+    const float dist = length(vOut);
+    vOut /= dist;
+
+    const ReferenceFrame shadingFrame(decodeVector(gb3.x), decodeVector(gb3.y));
+    const f3 vOutLocal = shadingFrame.toLocal(vOut);
+    const BSDF bsdf = setupBsdf(s, gb3.w);
+
+    const uint32_t srcResIndex = p.currentReservoirIndex;
+    const uint32_t dstResIndex = (srcResIndex + 1) % 2;
+
+    Reservoir combinedReservoir;
+    combinedReservoir.initialize(emptyLightSample());
+    float selectedTargetDensity = 0.0f;
+    int32_t selectedNeighborIndex = -1;
+
+    const Reservoir self = loadReservoir(f, srcResIndex, pix);
+    const float2 selfResInfo = f.reservoirInfo[srcResIndex][pix];
+    if (selfResInfo.x > 0.0f) {
+        combinedReservoir = self;
+        selectedTargetDensity = selfResInfo.y;
+    }
+    uint32_t combinedStreamLength = self.streamLength;
+
+    for (int nIdx = 0; nIdx < (int)p.numSpatialNeighbors; ++nIdx) {
+        int nbx, nby;
+        neighborCoord(f, p, x, y, nIdx, rng, &nbx, &nby);
+        const bool acceptedNeighbor =
+            testNeighbor<!useUnbiasedEstimator>(f, p.camera, bufIdx, nbx, nby, dist, shadingFrame.normal)
+            && (nbx != (int)x || nby != (int)y);
+        if (acceptedNeighbor) {
+            const size_t nbPix = (size_t)nby * f.W + nbx;
+            const Reservoir neighbor = loadReservoir(f, srcResIndex, nbPix);
+            const float2 neighborInfo = f.reservoirInfo[srcResIndex][nbPix];
+            const LightSample nbLightSample = neighbor.sample;
+            const f3 cont = performDirectLighting<false>(s, positionInWorld, vOutLocal, shadingFrame, bsdf, nbLightSample);
+            const float targetDensity = convertToWeight(cont);
+            const uint32_t nbStreamLength = neighbor.streamLength;
+            const float weight = targetDensity * neighborInfo.x * nbStreamLength;
+            if (combinedReservoir.update(nbLightSample, weight, rng.getFloat0cTo1o())) {
+                selectedTargetDensity = targetDensity;
+                if (useUnbiasedEstimator)
+                    selectedNeighborIndex = nIdx;
+            }
+            combinedStreamLength += nbStreamLength;
+        }
+    }
+    combinedReservoir.streamLength = combinedStreamLength;
+
+    float weightForEstimate = 0.0f;
+    if (useUnbiasedEstimator) { // :414-529
+        if (selectedTargetDensity > 0.0f) {
+            const LightSample selectedLightSample = combinedReservoir.sample;
+            float numWeight, denomWeight;
+            bool visibility = true;
+            {
+                f3 cont;
+                if (p.reuseVisibility)
+                    cont = performDirectLighting<true>(s, positionInWorld, vOutLocal, shadingFrame, bsdf, selectedLightSample);
+                else
+                    cont = performDirectLighting<false>(s, positionInWorld, vOutLocal, shadingFrame, bsdf, selectedLightSample);
+                const float targetDensityForSelf = convertToWeight(cont);
+                if (p.reuseVisibility)
+                    visibility = targetDensityForSelf > 0.0f;
+                numWeight = targetDensityForSelf;
+                denomWeight = targetDensityForSelf * self.streamLength;
+            }
+            for (int nIdx = 0; nIdx < (int)p.numSpatialNeighbors; ++nIdx) {
+                int nbx, nby;
+                neighborCoord(f, p, x, y, nIdx, rng, &nbx, &nby);
+                const bool acceptedNeighbor =
+                    (nbx >= 0 && nbx < (int)f.W && nby >= 0 && nby < (int)f.H) && (nbx != (int)x || nby != (int)y);
+                if (acceptedNeighbor) {
+                    const size_t nbPix = (size_t)nby * f.W + nbx;
+                    if (f.gb0[bufIdx][nbPix].x == 0xFFFFFFFFu)
+                        continue;
+                    const float4 nbGb2 = f.gb2[bufIdx][nbPix];
+                    const uint4 nbGb3 = f.gb3[bufIdx][nbPix];
+                    f3 nbPositionInWorld(nbGb2.x, nbGb2.y, nbGb2.z);
+                    const f3 nbGeometricNormalInWorld = decodeVector(__float_as_uint(nbGb2.w));
+                    const f3 nbVOut = normalize(p.prevCamera.position - nbPositionInWorld);
+                    const float nbFrontHit = dot(nbVOut, nbGeometricNormalInWorld) >= 0.0f ? 1.0f : -1.0f;
+                    nbPositionInWorld = offsetRayOrigin(nbPositionInWorld, nbFrontHit * nbGeometricNormalInWorld);
+                    const BSDF nbBsdf = setupBsdf(s, nbGb3.w);
+                    const ReferenceFrame nbShadingFrame(decodeVector(nbGb3.x), decodeVector(nbGb3.y));
+                    const f3 nbVOutLocal = nbShadingFrame.toLocal(nbVOut);
+                    const Reservoir neighbor = loadReservoir(f, srcResIndex, nbPix);
+                    f3 cont;
+                    if (p.reuseVisibility)
+                        cont = performDirectLighting<true>(s, nbPositionInWorld, nbVOutLocal, nbShadingFrame, nbBsdf, selectedLightSample);
+                    else
+                        cont = performDirectLighting<false>(s, nbPositionInWorld, nbVOutLocal, nbShadingFrame, nbBsdf, selectedLightSample);
+                    const float nbTargetDensity = convertToWeight(cont);
+                    const uint32_t nbStreamLength = neighbor.streamLength;
+                    denomWeight += nbTargetDensity * nbStreamLength;
+                    if (nIdx == selectedNeighborIndex)
+                        numWeight = nbTargetDensity;
+                }
+            }
+            weightForEstimate = numWeight / denomWeight;
+            if (p.reuseVisibility && !visibility)
+                weightForEstimate = 0.0f;
+        }
+    }
+    else {
+        weightForEstimate = 1.0f / combinedReservoir.streamLength;
+    }
+
+    float recPDFEstimate = weightForEstimate * combinedReservoir.sumWeights / selectedTargetDensity;
+    float targetDensityOut = selectedTargetDensity;
+    if (!isfinite(recPDFEstimate)) {
+        recPDFEstimate = 0.0f;
+        targetDensityOut = 0.0f;
+    }
+
+    f.rng[pix] = rng.state;
+    storeReservoir(f, dstResIndex, pix, combinedReservoir);
+    f.reservoirInfo[dstResIndex][pix] = make_float2(recPDFEstimate, targetDensityOut);
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) k_shading(DevScene s, DevFrame f, DevFrameParams p) {
+    // optix_restir_di_kernels.cu:559-637
+    const uint32_t x = blockIdx.x * 8 + threadIdx.x;
+    const uint32_t y = p.y0 + blockIdx.y * 8 + threadIdx.y;
+    if (x >= f.W || y >= p.y1)
+        return;
+    const size_t pix = (size_t)y * f.W + x;
+    const uint32_t bufIdx = p.bufferIndex;
+    const uint4 gb0 = f.gb0[bufIdx][pix];
+    const uint4 gb3 = f.gb3[bufIdx][pix];
+
+    f3 contribution(0.01f, 0.01f, 0.01f);
+    if (gb0.x != 0xFFFFFFFFu) {
+        const float4 gb2 = f.gb2[bufIdx][pix];
+        f3 positionInWorld(gb2.x, gb2.y, gb2.z);
+        const f3 geometricNormalInWorld = decodeVector(__float_as_uint(gb2.w));
+        const f3 vOut = normalize(p.camera.position - positionInWorld);
+        const float frontHit = dot(vOut, geometricNormalInWorld) >= 0.0f ? 1.0f : -1.0f;
+        positionInWorld = offsetRayOrigin(positionInWorld, frontHit * geometricNormalInWorld);
+
+        const ReferenceFrame shadingFrame(decodeVector(gb3.x), decodeVector(gb3.y));
+        const f3 vOutLocal = shadingFrame.toLocal(vOut);
+        const GfxMaterialDesc* mat = s.materials + gb3.w;
+        const BSDF bsdf = setupBsdf(s, gb3.w);
+
+        const uint32_t curResIndex = p.currentReservoirIndex;
+        const Reservoir reservoir = loadReservoir(f, curResIndex, pix);
+        const float2 reservoirInfo = f.reservoirInfo[curResIndex][pix];
+
+        contribution = f3(0.0f);
+        if (vOutLocal.z > 0) {
+            f3 emittance(0.0f);
+            if (mat->hasEmittance)
+                emittance = f3(mat->emittance[0], mat->emittance[1], mat->emittance[2]);
+            contribution += emittance / kPi;
+        }
+
+        const LightSample lightSample = reservoir.sample;
+        f3 directCont(0.0f);
+        const float recPDFEstimate = reservoirInfo.x;
+        if (recPDFEstimate > 0 && isfinite(recPDFEstimate)) {
+            const bool visDone = p.reuseVisibility &&
+                (!p.enableTemporalReuse || (p.enableSpatialReuse && p.useUnbiasedEstimator));
+            if (visDone)
+                directCont = performDirectLighting<false>(s, positionInWorld, vOutLocal, shadingFrame, bsdf, lightSample);
+            else
+                directCont = performDirectLighting<true>(s, positionInWorld, vOutLocal, shadingFrame, bsdf, lightSample);
+        }
+        contribution += recPDFEstimate * directCont;
+    }
+
+    f3 prevColorResult(0.0f);
+    if (p.numAccumFrames > 0) {
+        const float4 pb = f.beauty[pix];
+        prevColorResult = f3(pb.x, pb.y, pb.z);
+    }
+    const float curWeight = 1.0f / (1 + p.numAccumFrames);
+    const f3 colorResult = (1 - curWeight) * prevColorResult + curWeight * contribution;
+    f.beauty[pix] = make_float4(colorResult.x, colorResult.y, colorResult.z, 1.0f);
+}
+
+int launchReSTIR(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* params, int pass) {
+    const DevFrameParams p = makeDevParams(ctx, params);
+    if (p.y1 <= p.y0)
+        return GFX_OK;
+    if (p.log2NumCandidateSamples > 15 || p.numSpatialNeighbors > 15)
+        return GFX_ERR_INVALID_ARGUMENT; // 4-bit fields in the reference (restir_di_shared.h:258-259)
+    const dim3 block(8, 8);
+    const dim3 grid((ctx->frame.W + 7) / 8, (p.y1 - p.y0 + 7) / 8);
+    const DevScene s = ctx->devScene();
+    const DevFrame f = ctx->devFrame();
+    switch (pass) {
+    case GFX_RESTIR_INITIAL_RIS: k_initialAndTemporalRIS<false, false><<<grid, block, 0, stream>>>(s, f, p); break;
+    case GFX_RESTIR_INITIAL_AND_TEMPORAL_BIASED: k_initialAndTemporalRIS<true, false><<<grid, block, 0, stream>>>(s, f, p); break;
+    case GFX_RESTIR_INITIAL_AND_TEMPORAL_UNBIASED: k_initialAndTemporalRIS<true, true><<<grid, block, 0, stream>>>(s, f, p); break;
+    case GFX_RESTIR_SPATIAL_BIASED: k_spatialRIS<false><<<grid, block, 0, stream>>>(s, f, p); break;
+    case GFX_RESTIR_SPATIAL_UNBIASED: k_spatialRIS<true><<<grid, block, 0, stream>>>(s, f, p); break;
+    case GFX_RESTIR_SHADING: k_shading<<<grid, block, 0, stream>>>(s, f, p); break;
+    default:
+        ctx->setError("gfx_restir_launch: unknown pass");
+        return GFX_ERR_INVALID_ARGUMENT;
+    }
+    ctx->launches++;
+    GFX_CUDA(ctx, cudaGetLastError());
+    return GFX_OK;
+}
+
+} // namespace gfx

@@ -1,0 +1,102 @@
+// scene.cuh — device-side scene tables, BVH views and frame buffers (all plain pointers into HBM).
+//
+// Layout decisions (B200-first, see DESIGN.md "Data layout in HBM"):
+//  * vertices: AoS of three float4 per vertex (pos+u | normal+v | tangent) = 48 B, so a gather of one
+//    vertex is three aligned 16-byte loads from two 32-byte sectors (the reference's shared::Vertex
+//    is 44 B and straddles sectors; common_shared.h:1109-1114);
+//  * triangles: uint4 {i0,i1,i2,-} per mesh triangle (aligned 16-byte load);
+//  * BVH: the reference's own formats (CompressedInternalNode_T<8> 80 B = five 16-byte loads,
+//    TriangleStorage 48 B = three 16-byte loads, PrimitiveReference 4 B), world-space triangles of
+//    ALL instances flattened into one single-level BVH (180 GB HBM makes the IAS/GAS split of the
+//    reference unnecessary and saves the per-instance ray transform);
+//  * per-pixel frame state: SoA planes of float4/uint4 (one 16-byte load per thread, fully coalesced
+//    along x), reservoirs as three float4 planes.
+#pragma once
+#include "vec.cuh"
+#include "../../include/gfxb200.h"
+
+namespace gfx {
+
+struct DevMesh {
+    uint32_t vertexBase;   // into vertices (units of vertices)
+    uint32_t triBase;      // into triangles / primWeights / primCdf
+    uint32_t numTriangles;
+    uint32_t materialSlot;
+    float primIntegral;    // emitterPrimDist.integral()
+    uint32_t pad[3];
+};
+
+struct DevInstance {
+    float transform[12];
+    float curToPrevTransform[12];
+    float normalMatrix[9];
+    float uniformScale;
+    uint32_t firstMeshSlot;
+    uint32_t numMeshSlots;
+    float geomIntegral;    // lightGeomInstDist.integral()
+    uint32_t pad[3];
+};
+static_assert(sizeof(DevInstance) % 16 == 0, "DevInstance must stay 16-byte aligned");
+
+struct DevBvh {
+    const uint4* nodes;     // 5 x uint4 per node
+    const uint32_t* primRefs;
+    const float4* tris;     // 3 x float4 per triangle
+    uint32_t numNodes;
+    uint32_t* overflowFlag; // set to 1 if a traversal stack overflowed (checked by the host)
+};
+
+struct DevScene {
+    const float4* vertices;          // 3 per vertex
+    const uint4* triangles;
+    const DevMesh* meshes;
+    const GfxMaterialDesc* materials;
+    const DevInstance* instances;
+    const uint32_t* instanceMeshSlots;
+    const uint2* geomToInstMesh;     // flattened geometry -> (instance, mesh slot)
+    const float* primWeights;        // per mesh triangle
+    const float* primCdf;
+    const float* geomWeights;        // per (instance, mesh slot)
+    const float* geomCdf;
+    const float* instWeights;        // per instance
+    const float* instCdf;
+    const float* instIntegral;       // device scalar (rebuilt every frame on the GPU)
+    uint32_t numInstances;
+    DevBvh bvh;
+};
+
+struct DevFrame {
+    uint32_t W, H;
+    uint4* gb0[2];
+    float2* gb1[2];
+    float4* gb2[2];
+    uint4* gb3[2];
+    unsigned long long* rng;
+    float4* reservoir[2];       // 3 planes of W*H float4
+    float2* reservoirInfo[2];
+    float4* beauty;
+    float4* albedo;
+    float4* normal;
+    const float2* neighborDeltas; // 1024 entries
+};
+
+struct DevCamera {
+    float aspect, fovY;
+    f3 position;
+    float orientation[9];
+    float invOrientation[9];
+    float vh, vw;
+};
+
+struct DevFrameParams {
+    DevCamera camera, prevCamera;
+    uint32_t numAccumFrames, frameIndex, bufferIndex;
+    float spatialNeighborRadius;
+    uint32_t log2NumCandidateSamples, numSpatialNeighbors;
+    uint32_t useLowDiscrepancyNeighbors, reuseVisibility, enableTemporalReuse, enableSpatialReuse;
+    uint32_t useUnbiasedEstimator, resetFlowBuffer, enableJittering;
+    uint32_t currentReservoirIndex, spatialNeighborBaseIndex;
+    uint32_t y0, y1; // rows owned by this rank
+};
+
+} // namespace gfx

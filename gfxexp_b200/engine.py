@@ -1,0 +1,205 @@
+"""Host-side mirror of the reference's per-app frame loops, on top of the C ABI.
+
+`Context` is a thin, loud wrapper over libgfxb200.so (every non-zero status raises GfxError with
+gfx_last_error_string).  `ReSTIRRenderer.render_frame` issues the launch sequence of
+restir_di/restir_di_main.cpp:2245-2421 (updateASs once, setupLightInstDistribution, gBuffer launch,
+performInitialAndTemporalRIS, numSpatialReusePasses x performSpatialRIS with ping-pong reservoirs,
+shading).  There is no CPU path here: without the CUDA library nothing runs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import abi
+
+
+class GfxError(RuntimeError):
+    pass
+
+
+class Context:
+    def __init__(self, device: int = 0, lib: Optional[C.CDLL] = None):
+        self.lib = lib or abi.load_library()
+        h = C.c_void_p()
+        rc = self.lib.gfx_ctx_create(device, C.byref(h))
+        if rc != 0:
+            raise GfxError(f"gfx_ctx_create(device={device}) failed with status {rc} "
+                           "(-2 = no sm_100 device; this library has no CPU fallback)")
+        self.h = h
+        self.device = device
+        self.width = self.height = 0
+        self._scene_arrays = None
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            msg = self.lib.gfx_last_error_string(self.h)
+            raise GfxError(f"{what} failed with status {rc}: {msg.decode() if msg else ''}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.gfx_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self, stream=None):
+        self._check(self.lib.gfx_synchronize(self.h, stream), "gfx_synchronize")
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self.lib.gfx_kernel_launch_count(self.h))
+
+    # -- scene / BVH ------------------------------------------------------------------------
+    def upload_scene(self, scene):
+        self._scene_arrays = abi.SceneArrays(scene)
+        self._check(self.lib.gfx_scene_upload(self.h, C.byref(self._scene_arrays.desc)), "gfx_scene_upload")
+
+    def build_bvh(self, flags: int = 0, stream=None):
+        self._check(self.lib.gfx_bvh_build(self.h, stream, flags), "gfx_bvh_build")
+
+    def bvh_info(self) -> abi.GfxBvhInfo:
+        info = abi.GfxBvhInfo()
+        self._check(self.lib.gfx_bvh_info(self.h, C.byref(info)), "gfx_bvh_info")
+        return info
+
+    def export_bvh(self):
+        info = self.bvh_info()
+        nodes = np.zeros(info.numNodes, dtype=abi.NODE_DTYPE)
+        refs = np.zeros(info.numPrimRefs, dtype=np.uint32)
+        tris = np.zeros(info.numTriangles, dtype=abi.TRI_DTYPE)
+        self._check(self.lib.gfx_bvh_export(self.h, nodes.ctypes.data, refs.ctypes.data, tris.ctypes.data),
+                    "gfx_bvh_export")
+        return nodes, refs, tris
+
+    def import_bvh(self, nodes, refs, tris):
+        nodes = np.ascontiguousarray(nodes)
+        refs = np.ascontiguousarray(refs)
+        tris = np.ascontiguousarray(tris)
+        self._check(self.lib.gfx_bvh_import(self.h, nodes.ctypes.data, nodes.shape[0], refs.ctypes.data,
+                                            refs.shape[0], tris.ctypes.data, tris.shape[0]), "gfx_bvh_import")
+
+    def trace(self, rays: np.ndarray, mode: int = abi.TRACE_CLOSEST, stream=None) -> np.ndarray:
+        rays = np.ascontiguousarray(rays)
+        assert rays.dtype == abi.RAY_DTYPE
+        hits = np.zeros(rays.shape[0], dtype=abi.HIT_DTYPE)
+        self._check(self.lib.gfx_trace(self.h, stream, rays.ctypes.data, rays.shape[0], hits.ctypes.data, mode),
+                    "gfx_trace")
+        self.synchronize(stream)
+        return hits
+
+    def trace_device(self, d_rays: int, num_rays: int, d_hits: int, mode: int = abi.TRACE_CLOSEST, stream=None):
+        self._check(self.lib.gfx_trace_device(self.h, stream, d_rays, num_rays, d_hits, mode), "gfx_trace_device")
+
+    def build_light_distributions(self, buffer_index: int = 0, stream=None):
+        self._check(self.lib.gfx_light_dist_build(self.h, stream, buffer_index), "gfx_light_dist_build")
+
+    def light_dist(self):
+        n = len(self._scene_arrays.scene.instances)
+        w = np.zeros(n, dtype=np.float32)
+        cdf = np.zeros(n, dtype=np.float32)
+        integ = C.c_float()
+        self._check(self.lib.gfx_light_dist_export(self.h, w.ctypes.data, cdf.ctypes.data, C.byref(integ)),
+                    "gfx_light_dist_export")
+        return w, cdf, integ.value
+
+    # -- frame state --------------------------------------------------------------------------
+    def create_frame(self, width: int, height: int, seed: int = 591842031321323413):
+        self._check(self.lib.gfx_frame_create(self.h, width, height), "gfx_frame_create")
+        self.width, self.height = width, height
+        self._check(self.lib.gfx_rng_seed(self.h, seed), "gfx_rng_seed")
+        self._check(self.lib.gfx_restir_setup_neighbor_table(self.h), "gfx_restir_setup_neighbor_table")
+
+    def download(self, buffer_id: int, index: int = 0, out: Optional[np.ndarray] = None, stream=None) -> np.ndarray:
+        dtype, comps, planes = abi.BUFFER_LAYOUT[buffer_id]
+        count = planes * self.height * self.width * comps
+        arr = out if out is not None else np.empty(count, dtype=dtype)
+        self._check(self.lib.gfx_buffer_download(self.h, stream, buffer_id, index, arr.ctypes.data, arr.nbytes),
+                    "gfx_buffer_download")
+        if out is not None:
+            return out
+        if planes > 1:
+            return arr.reshape(planes, self.height, self.width, comps)
+        return arr.reshape(self.height, self.width, comps) if comps > 1 else arr.reshape(self.height, self.width)
+
+    def upload(self, buffer_id: int, index: int, data: np.ndarray, stream=None):
+        data = np.ascontiguousarray(data)
+        self._check(self.lib.gfx_buffer_upload(self.h, stream, buffer_id, index, data.ctypes.data, data.nbytes),
+                    "gfx_buffer_upload")
+
+    def device_ptr(self, buffer_id: int, index: int = 0):
+        nbytes = C.c_size_t()
+        p = self.lib.gfx_buffer_device_ptr(self.h, buffer_id, index, C.byref(nbytes))
+        return p, nbytes.value
+
+    # -- launches -------------------------------------------------------------------------------
+    def gbuffer(self, params, stream=None):
+        self._check(self.lib.gfx_gbuffer_launch(self.h, stream, C.byref(params)), "gfx_gbuffer_launch")
+
+    def restir(self, params, pass_id: int, stream=None):
+        self._check(self.lib.gfx_restir_launch(self.h, stream, C.byref(params), pass_id), "gfx_restir_launch")
+
+    def svgf(self, params, pass_id: int, stage: int = 0, stream=None):
+        self._check(self.lib.gfx_svgf_launch(self.h, stream, C.byref(params), pass_id, stage), "gfx_svgf_launch")
+
+
+def restir_frame_passes(params, frame_index: int, num_spatial_passes: int = 1, temporal: bool = True,
+                        unbiased: bool = False):
+    """The launch list of one ReSTIR DI frame (restir_di_main.cpp:2321-2421).  Yields
+    (kind, pass_id) with `params` mutated in place exactly as the host mutates plp between launches."""
+    params.frameIndex = frame_index
+    params.bufferIndex = frame_index % 2
+    params.useUnbiasedEstimator = 1 if unbiased else 0
+    # enableTemporalReuse is the renderer *config* flag; the first frame of a sequence only selects the
+    # performInitialRIS entry point (restir_di_main.cpp:2378-2383) and resets the flow buffer (:2340)
+    params.enableTemporalReuse = 1 if temporal else 0
+    params.enableSpatialReuse = 1 if num_spatial_passes > 0 else 0
+    new_sequence = frame_index == 0
+    params.resetFlowBuffer = 1 if new_sequence else 0
+    yield ("gbuffer", -1)
+    # curReservoirIndex = (lastReservoirIndex + 1) % 2, starts so that frame 0 writes reservoir 0
+    base = (frame_index * (1 + num_spatial_passes)) % 2
+    params.currentReservoirIndex = base
+    if params.enableTemporalReuse and not new_sequence:
+        yield ("restir", abi.RESTIR_INITIAL_AND_TEMPORAL_UNBIASED if unbiased else abi.RESTIR_INITIAL_AND_TEMPORAL_BIASED)
+    else:
+        yield ("restir", abi.RESTIR_INITIAL_RIS)
+    cur = base
+    for s in range(num_spatial_passes):
+        params.currentReservoirIndex = cur
+        params.spatialNeighborBaseIndex = (frame_index * num_spatial_passes * max(params.numSpatialNeighbors, 1)
+                                           + s * params.numSpatialNeighbors) % 1024
+        yield ("restir", abi.RESTIR_SPATIAL_UNBIASED if unbiased else abi.RESTIR_SPATIAL_BIASED)
+        cur = (cur + 1) % 2
+    params.currentReservoirIndex = cur
+    yield ("restir", abi.RESTIR_SHADING)
+
+
+class ReSTIRRenderer:
+    """Config-2 style frame driver (OriginalReSTIRBiased by default)."""
+
+    def __init__(self, ctx: Context, scene, width: int, height: int, num_spatial_passes: int = 1,
+                 unbiased: bool = False):
+        self.ctx = ctx
+        self.scene = scene
+        self.params = abi.default_frame_params(scene, width, height)
+        self.num_spatial_passes = num_spatial_passes
+        self.unbiased = unbiased
+        self.frame_index = 0
+
+    def render_frame(self, stream=None):
+        self.ctx.build_light_distributions(self.frame_index % 2, stream)
+        for kind, pass_id in restir_frame_passes(self.params, self.frame_index, self.num_spatial_passes,
+                                                 True, self.unbiased):
+            if kind == "gbuffer":
+                self.ctx.gbuffer(self.params, stream)
+            else:
+                self.ctx.restir(self.params, pass_id, stream)
+        self.frame_index += 1
