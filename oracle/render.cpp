@@ -384,10 +384,10 @@ extern "C" orc_frame* orc_frame_create(orc_scene* s, uint32_t W, uint32_t H) {
     f->H = H;
     const size_t n = (size_t)W * H;
     for (int i = 0; i < 2; ++i) {
-        f->gb0[i].assign(n, GB0{ 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0 });
+        f->gb0[i].assign(n, GB0{ 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu });
         f->gb1[i].assign(n, GB1{ 0, 0 });
         f->gb2[i].assign(n, GB2{ 0, 0, 0, 0 });
-        f->gb3[i].assign(n, GB3{ 0, 0, 0, 0xFFFFFFFFu });
+        f->gb3[i].assign(n, GB3{ 0, 0, 0, 0 });
         f->reservoir[i].assign(3 * n, F4{ 0, 0, 0, 0 });
         f->reservoirInfo[i].assign(n, GB1{ 0, 0 });
     }
