@@ -1,0 +1,443 @@
+#!/usr/bin/env python
+"""bench.py — the hot path's headline benchmark (BASELINE.json: Mrays/s and fps at 1920x1080, 1 spp).
+
+A "step" is one ReSTIR DI frame of config 2 (BASELINE.json configs[1]): Bistro-exterior-class
+synthetic scene (~2.87 M triangles, 1 106 instances, 20 050 emissive triangles), 1920x1080, 1 spp,
+32 initial candidates, temporal reuse, 1 spatial pass x 4 neighbours, shading
+= setupLightInstDistribution + setupGBuffers + performInitialAndTemporalRISBiased +
+  performSpatialRISBiased + shading (restir_di/restir_di_main.cpp:2303-2421).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (C ABI)
+  python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU
+                                                           # (oracle port; oracle/_ref is unbuildable)
+
+One JSON line on stdout (rank 0).  `value` = rays traced by the whole job per second with
+everything resident in HBM; `e2e` = the same through the C ABI with per-frame host->device uploads
+(instance table + parameter blocks from pinned memory) and the device->host read of the beauty
+framebuffer inside the timed region; `roofline` = the dominant kernel against the measured HBM
+peak; `cpu_baseline` = the oracle on the host cores on a bounded sample of the same frame.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WIDTH, HEIGHT = 1920, 1080
+METRIC = "Mrays/s at 1920x1080 1spp (ReSTIR DI frame: 32 candidates, temporal + 1x4 spatial reuse)"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, device: int):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smmax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smmax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smmax) if smmax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def frame_launches(ctx, params, frame_index, num_spatial_passes, timers=None):
+    """Issue one frame; with `timers` (dict name -> list of (start, end) events) bracket every launch."""
+    from gfxexp_b200 import engine
+    import torch
+
+    def timed(name, fn):
+        if timers is None:
+            fn()
+            return
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        timers.setdefault(name, []).append((a, b))
+
+    timed("light_dist", lambda: ctx.build_light_distributions(frame_index % 2))
+    names = {0: "initial_ris", 1: "initial_temporal_ris", 2: "initial_temporal_ris_unbiased", 3: "spatial_ris",
+             4: "spatial_ris_unbiased", 5: "shading"}
+    for kind, pass_id in engine.restir_frame_passes(params, frame_index, num_spatial_passes):
+        if kind == "gbuffer":
+            timed("gbuffer", lambda: ctx.gbuffer(params))
+        else:
+            timed(names[pass_id], lambda pid=pass_id: ctx.restir(params, pid))
+
+
+def traversal_stats(ctx, rays, mode):
+    """mean (internal nodes, triangles tested) per ray from the stats variant of the trace kernel."""
+    from gfxexp_b200 import abi
+    hits = ctx.trace(rays, mode | abi.TRACE_STATS)
+    packed = hits["instUserData"]
+    return float((packed & 0xFFFF).mean()), float((packed >> 16).mean())
+
+
+def cpu_reference_step(O, oframe, params, rows, halo, num_spatial_passes, threads):
+    """The reference algorithm (oracle port) on a bounded sample: a full-width strip of `rows` rows
+    (+halo rows for the per-pixel passes feeding the spatial gather).  Returns seconds per pass kind."""
+    from gfxexp_b200 import abi, engine
+    H = oframe.H
+    y0 = (H - rows) // 2
+    t = {}
+    for kind, pass_id in engine.restir_frame_passes(params, 0, num_spatial_passes):
+        needs_halo = kind == "gbuffer" or pass_id in (abi.RESTIR_INITIAL_RIS, abi.RESTIR_INITIAL_AND_TEMPORAL_BIASED)
+        lo = max(0, y0 - (halo if needs_halo else 0))
+        hi = min(H, y0 + rows + (halo if needs_halo else 0))
+        params.tileOriginY, params.tileRows = lo, hi - lo
+        t0 = time.perf_counter()
+        if kind == "gbuffer":
+            oframe.gbuffer(params, threads)
+        else:
+            oframe.restir(params, pass_id, threads)
+        dt = time.perf_counter() - t0
+        name = "gbuffer" if kind == "gbuffer" else str(pass_id)
+        # scale this pass to a full frame by the rows it actually processed
+        t[name] = t.get(name, 0.0) + dt * (H / (hi - lo))
+    params.tileOriginY, params.tileRows = 0, 0
+    return t
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from gfxexp_b200 import abi, scenes
+    from tests import oracle_lib as O
+    threads = os.cpu_count() or 1
+    scene = scenes.bistro_class_scene()
+    oscene = O.OracleScene(scene)
+    oframe = O.OracleFrame(oscene, WIDTH, HEIGHT)
+    params = abi.default_frame_params(scene, WIDTH, HEIGHT)
+    rows, halo = args.cpu_rows, 24
+    rays_per_px = args.rays_per_px
+    times = []
+    for it in range(args.warmup + args.steps):
+        t = cpu_reference_step(O, oframe, params, rows, halo, 1, threads)
+        if it >= args.warmup:
+            times.append(sum(t.values()))
+    frame_s = float(np.mean(times))
+    rays_per_frame = rays_per_px * WIDTH * HEIGHT
+    value = rays_per_frame / frame_s / 1e6
+    sample = (f"{rows}-row full-width strip (+{halo}-row halo for per-pixel passes) of the 1920x1080 frame per pass, "
+              f"scaled to the full frame by rows; rays/frame = {rays_per_px:.3f} rays/px (GPU-counted) x px")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": frame_s * 1e3, "fps": 1.0 / frame_s,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "restir_di config 2: bistro_class synthetic scene 1920x1080 1spp, 32 candidates, "
+                               "temporal + 1x4 spatial reuse", "triangles": scene.num_triangles,
+                   "bvh": "bvh::buildGeometryBVH<8> restatement (SBVH, budget .3), build %.1f s single-thread" % oscene.build_seconds},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from gfxexp_b200 import abi, engine, scenes
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+
+    scene = scenes.bistro_class_scene()
+    ctx = engine.Context(local_rank)
+    t0 = time.perf_counter()
+    ctx.upload_scene(scene)
+    ctx.synchronize()
+    upload_s = time.perf_counter() - t0
+    # BVH build: once untimed (allocations), then timed
+    ctx.build_bvh()
+    ctx.synchronize()
+    t0 = time.perf_counter()
+    ctx.build_bvh()
+    ctx.synchronize()
+    bvh_build_ms = (time.perf_counter() - t0) * 1e3
+    info = ctx.bvh_info()
+    ctx.create_frame(WIDTH, HEIGHT)
+    params = abi.default_frame_params(scene, WIDTH, HEIGHT)
+    nsp = 1
+
+    if world > 1:
+        from gfxexp_b200 import multigpu
+        driver = multigpu.StripDriver(ctx, params, WIDTH, HEIGHT, rank, world)
+    else:
+        driver = None
+
+    def one_frame(fi, timers=None):
+        if driver is not None:
+            driver.render_frame(fi, nsp)
+        else:
+            frame_launches(ctx, params, fi, nsp, timers)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    frame = 0
+    for _ in range(max(args.warmup, 3)):
+        one_frame(frame)
+        frame += 1
+    barrier()
+    ctx.read_stats(reset=True)
+    launches0 = ctx.kernel_launches
+
+    # ---- timed region 1: everything resident in HBM -------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        one_frame(frame)
+        frame += 1
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = ev0.elapsed_time(ev1)
+    rays = ctx.read_stats(reset=True)[0]
+    launches = ctx.kernel_launches - launches0
+    if world > 1:
+        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        r = torch.tensor([rays], device="cuda", dtype=torch.float64)
+        dist.all_reduce(r, op=dist.ReduceOp.SUM)
+        rays = float(r.item())
+    ms_per_step = ms_total / args.steps
+    value = rays / (ms_total * 1e-3) / 1e6
+    rays_per_px = rays / args.steps / (WIDTH * HEIGHT)
+
+    # ---- timed region 2: end to end through the C ABI with host buffers ---------------------------
+    pinned_out = torch.empty((HEIGHT, WIDTH, 4), dtype=torch.float32, pin_memory=True)
+    out_np = pinned_out.numpy()
+    sa = ctx._scene_arrays
+    inst_bytes = C.sizeof(abi.GfxInstanceDesc) * len(scene.instances)
+    param_bytes = C.sizeof(abi.GfxFrameParams) * (3 + nsp)
+    rows_lo, rows_hi = (driver.y0, driver.y1) if driver is not None else (0, HEIGHT)
+
+    def one_frame_e2e(fi):
+        # host -> device: the instance table (InstanceController::update re-uploads it every frame,
+        # common/common_host.h:798-856) + the per-launch parameter blocks; device -> host: the beauty
+        # framebuffer rows this rank owns.
+        ctx._check(ctx.lib.gfx_scene_update_instances(ctx.h, None, sa.instances, len(scene.instances)),
+                   "gfx_scene_update_instances")
+        one_frame(fi)
+        view = out_np[rows_lo:rows_hi]
+        p, nbytes = ctx.device_ptr(abi.BUF_BEAUTY_ACCUM, 0)
+        off = rows_lo * WIDTH * 16
+        rc = cudart.cudaMemcpyAsync(C.c_void_p(view.ctypes.data), C.c_void_p(p + off), C.c_size_t(view.nbytes), 2, None)
+        assert rc == 0
+        cudart.cudaStreamSynchronize(None)
+
+    cudart = C.CDLL("libcudart.so.12") if os.path.exists("/usr/local/cuda/lib64/libcudart.so.12") else C.CDLL("libcudart.so")
+    cudart.cudaMemcpyAsync.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
+    cudart.cudaStreamSynchronize.argtypes = [C.c_void_p]
+    one_frame_e2e(frame)
+    frame += 1
+    barrier()
+    ctx.read_stats(reset=True)
+    t0 = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        one_frame_e2e(frame)
+        frame += 1
+    ev1.record()
+    barrier()
+    e2e_ms = ev0.elapsed_time(ev1)
+    e2e_rays = ctx.read_stats(reset=True)[0]
+    if world > 1:
+        t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+        r = torch.tensor([e2e_rays], device="cuda", dtype=torch.float64)
+        dist.all_reduce(r, op=dist.ReduceOp.SUM)
+        e2e_rays = float(r.item())
+    e2e_value = e2e_rays / (e2e_ms * 1e-3) / 1e6
+    d2h_bytes = (rows_hi - rows_lo) * WIDTH * 16
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel breakdown + roofline of the dominant kernel (rank 0, single-GPU launches) ------
+    roofline = None
+    breakdown = {}
+    if driver is None:
+        timers = {}
+        for _ in range(args.steps):
+            frame_launches(ctx, params, frame, nsp, timers)
+            frame += 1
+        torch.cuda.synchronize()
+        breakdown = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in timers.items()}
+        dominant = max(breakdown, key=breakdown.get)
+        # traversal statistics of this BVH for the rays the dominant kernel traces
+        from tests import oracle_lib as O  # only for the primary-ray generator (host arithmetic)
+        prim = O.primary_rays(params, WIDTH, HEIGHT)[:: 7]
+        n_int_p, n_tri_p = traversal_stats(ctx, prim, abi.TRACE_CLOSEST)
+        gb2 = ctx.download(abi.BUF_GBUFFER2, params.bufferIndex).view(np.float32)
+        gb0 = ctx.download(abi.BUF_GBUFFER0, params.bufferIndex)
+        res = ctx.download(abi.BUF_RESERVOIR, params.currentReservoirIndex).view(np.float32)
+        hit = gb0[..., 0] != 0xFFFFFFFF
+        org = gb2[..., :3][hit][::7]
+        tgt = res[1][..., :3][hit][::7]
+        d = tgt - org
+        dist_ = np.linalg.norm(d, axis=1)
+        ok = dist_ > 1e-3
+        sh = np.zeros(int(ok.sum()), dtype=abi.RAY_DTYPE)
+        sh["org"] = org[ok] + 1e-3 * (d[ok] / dist_[ok, None])
+        sh["dir"] = d[ok] / dist_[ok, None]
+        sh["tmax"] = dist_[ok] * 0.9999
+        n_int_s, n_tri_s = traversal_stats(ctx, sh, abi.TRACE_ANY)
+        px = WIDTH * HEIGHT
+        trav_primary = 80 * n_int_p + 52 * n_tri_p + 64
+        trav_shadow = 80 * n_int_s + 52 * n_tri_s + 64
+        # algorithmic bytes per pixel, SURVEY.md §8(d): struct sizes of the reference + traversal counters
+        alg = {
+            "gbuffer": 56 + 32 + trav_primary + 3 * 48 + 16,
+            "initial_ris": 120 + trav_shadow,
+            "initial_temporal_ris": 120 + 112 + trav_shadow,
+            "spatial_ris": 592,
+            "shading": 120 + trav_shadow,
+            "light_dist": 0,
+        }
+        hbm_peak, peak_src = measured_peaks()
+        bytes_per_launch = alg.get(dominant, 0) * px
+        achieved = bytes_per_launch / (breakdown[dominant] * 1e-3) / 1e9
+        roofline = {"kernel": dominant, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": bytes_per_launch, "ms_per_launch": breakdown[dominant],
+                    "traversal": {"primary_nodes_per_ray": n_int_p, "primary_tris_per_ray": n_tri_p,
+                                  "shadow_nodes_per_ray": n_int_s, "shadow_tris_per_ray": n_tri_s},
+                    "per_kernel": {k: {"ms": breakdown[k], "GBps": alg.get(k, 0) * px / (breakdown[k] * 1e-3) / 1e9}
+                                   for k in breakdown}}
+
+    # ---- CPU baseline: the oracle on the host cores, bounded sample (rank 0, N=1 only) -------------
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        from tests import oracle_lib as O
+        threads = os.cpu_count() or 1
+        oscene = O.OracleScene(scene)
+        oframe = O.OracleFrame(oscene, WIDTH, HEIGHT)
+        cparams = abi.default_frame_params(scene, WIDTH, HEIGHT)
+        t = cpu_reference_step(O, oframe, cparams, args.cpu_rows, 24, nsp, threads)
+        frame_s = sum(t.values())
+        cpu_baseline = {"value": rays_per_px * WIDTH * HEIGHT / frame_s / 1e6, "unit": "Mrays/s", "cores": threads,
+                        "kind": "port", "fps": 1.0 / frame_s, "bvh_build_s_single_thread": oscene.build_seconds,
+                        "sample": f"{args.cpu_rows}-row full-width strip (+24-row halo for the per-pixel passes) of the "
+                                  f"1920x1080 frame per pass, scaled to the full frame by rows; rays counted as the "
+                                  f"GPU's {rays_per_px:.3f} rays/px"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "fps": 1e3 / ms_per_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "restir_di config 2: bistro_class synthetic scene 1920x1080 1spp, 32 candidates, "
+                               "temporal + 1x4 spatial reuse",
+                   "triangles": info.numTriangles, "bvh_nodes": info.numNodes, "instances": len(scene.instances),
+                   "emissive_triangles": scene.num_emissive_triangles, "rays_per_pixel": rays_per_px,
+                   "l2": "inputs larger than L2 (BVH %.0f MB + %.0f MB of per-pixel state per frame)" % (
+                       (info.numTriangles * 52 + info.numNodes * 80) / 1e6, WIDTH * HEIGHT * 400 / 1e6),
+                   "parallelism": "screen strips x%d" % world if world > 1 else "1 GPU",
+                   "bvh_build_ms": bvh_build_ms, "scene_upload_s": upload_s},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": e2e_ms / args.steps, "fps": 1e3 * args.steps / e2e_ms,
+                "h2d_bytes_per_step": inst_bytes + param_bytes, "d2h_bytes_per_step": d2h_bytes},
+        "gpu_launches": launches,
+    }
+    if roofline is not None:
+        line["roofline"] = roofline
+    if cpu_baseline is not None:
+        line["cpu_baseline"] = cpu_baseline
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="gfxb200", choices=["gfxb200", "reference"])
+    ap.add_argument("--cpu-rows", type=int, default=48, help="rows of the CPU-baseline strip sample")
+    ap.add_argument("--rays-per-px", type=float, default=2.62, help="--impl reference: rays per pixel (GPU-counted)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -76,7 +76,7 @@ RAY_DTYPE = np.dtype([("org", np.float32, 3), ("tmin", np.float32), ("dir", np.f
 assert NODE_DTYPE.itemsize == 80 and TRI_DTYPE.itemsize == 48 and HIT_DTYPE.itemsize == 32 and RAY_DTYPE.itemsize == 32
 
 # enums
-TRACE_CLOSEST, TRACE_ANY = 0, 1
+TRACE_CLOSEST, TRACE_ANY, TRACE_STATS = 0, 1, 2
 (RESTIR_INITIAL_RIS, RESTIR_INITIAL_AND_TEMPORAL_BIASED, RESTIR_INITIAL_AND_TEMPORAL_UNBIASED,
  RESTIR_SPATIAL_BIASED, RESTIR_SPATIAL_UNBIASED, RESTIR_SHADING) = range(6)
 (SVGF_TEMPORAL_ACCUMULATE, SVGF_ESTIMATE_VARIANCE, SVGF_ATROUS, SVGF_MODULATE_TAA) = range(4)
@@ -204,6 +204,7 @@ _DECLS = {
     "gfx_buffer_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, c_u32, C.c_void_p, C.c_size_t]),
     "gfx_buffer_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, c_u32, C.c_void_p, C.c_size_t]),
     "gfx_buffer_device_ptr": (C.c_void_p, [C.c_void_p, C.c_int, c_u32, C.POINTER(C.c_size_t)]),
+    "gfx_stats_read": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_int]),
     "gfx_gbuffer_launch": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxFrameParams)]),
     "gfx_restir_launch": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxFrameParams), C.c_int]),
     "gfx_svgf_launch": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxFrameParams), C.c_int, c_u32]),

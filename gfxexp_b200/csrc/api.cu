@@ -28,7 +28,7 @@ void FrameState::release() {
         cudaFree(reservoir[i]); cudaFree(reservoirInfo[i]);
         cudaFree(svgfLighting[i]); cudaFree(svgfMoments[i]); cudaFree(svgfFinal[i]); cudaFree(svgfDepth[i]);
     }
-    cudaFree(rng); cudaFree(beauty); cudaFree(albedo); cudaFree(normal); cudaFree(neighborDeltas);
+    cudaFree(stats); cudaFree(rng); cudaFree(beauty); cudaFree(albedo); cudaFree(normal); cudaFree(neighborDeltas);
     cudaFree(svgfPrevLighting);
     *this = FrameState();
 }
@@ -102,6 +102,7 @@ DevScene gfx_ctx::devScene() const {
     d.instCdf = scene.instCdf;
     d.instIntegral = scene.instIntegral;
     d.numInstances = scene.numInstances;
+    d.rayCounter = frame.stats;
     d.bvh.nodes = reinterpret_cast<const uint4*>(bvh.nodes);
     d.bvh.primRefs = bvh.primRefs;
     d.bvh.tris = bvh.tris;
@@ -126,6 +127,7 @@ DevFrame gfx_ctx::devFrame() const {
     d.albedo = frame.albedo;
     d.normal = frame.normal;
     d.neighborDeltas = frame.neighborDeltas;
+    d.stats = frame.stats;
     return d;
 }
 
@@ -473,6 +475,8 @@ int gfx_frame_create(gfx_ctx* ctx, uint32_t W, uint32_t H) {
     GFX_CUDA(ctx, cudaMalloc(&F.albedo, n * 16));
     GFX_CUDA(ctx, cudaMalloc(&F.normal, n * 16));
     GFX_CUDA(ctx, cudaMalloc(&F.neighborDeltas, 1024 * 8));
+    GFX_CUDA(ctx, cudaMalloc(&F.stats, 4 * 8));
+    GFX_CUDA(ctx, cudaMemset(F.stats, 0, 4 * 8));
     GFX_CUDA(ctx, cudaMemset(F.rng, 0, n * 8));
     GFX_CUDA(ctx, cudaMemset(F.beauty, 0, n * 16));
     GFX_CUDA(ctx, cudaMemset(F.albedo, 0, n * 16));
@@ -539,6 +543,19 @@ int gfx_restir_setup_neighbor_table(gfx_ctx* ctx) {
         deltas[i] = d;
     }
     GFX_CUDA(ctx, cudaMemcpy(F.neighborDeltas, deltas.data(), 1024 * 8, cudaMemcpyHostToDevice));
+    return GFX_OK;
+}
+
+int gfx_stats_read(gfx_ctx* ctx, void* stream, uint64_t* out4, int reset) {
+    CHECK_CTX(ctx);
+    if (!ctx->frame.created)
+        return GFX_ERR_NOT_READY;
+    if (!out4)
+        return GFX_ERR_INVALID_ARGUMENT;
+    GFX_CUDA(ctx, cudaMemcpyAsync(out4, ctx->frame.stats, 32, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    GFX_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+    if (reset)
+        GFX_CUDA(ctx, cudaMemsetAsync(ctx->frame.stats, 0, 32, (cudaStream_t)stream));
     return GFX_OK;
 }
 

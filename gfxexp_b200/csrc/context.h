@@ -58,6 +58,7 @@ struct FrameState {
     float4* albedo = nullptr;
     float4* normal = nullptr;
     float2* neighborDeltas = nullptr;
+    unsigned long long* stats = nullptr; // 4 counters
     // SVGF state
     float4* svgfLighting[2] = { nullptr, nullptr };  // lighting rgb + variance, ping-pong
     float4* svgfMoments[2] = { nullptr, nullptr };   // first/second luminance moments + history length

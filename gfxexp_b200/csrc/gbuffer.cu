@@ -23,11 +23,18 @@ GFX_D f2 calcScreenPosition(const DevCamera &cam, const f3 &posInWorld) { // res
     return f2(1 - (posAtZ1.x + 0.5f * w) / w, 1 - (posAtZ1.y + 0.5f * h) / h);
 }
 
-__global__ void __launch_bounds__(64) k_gbuffer(DevScene scene, DevFrame frame, DevFrameParams p) {
+GFX_D void countRays(const DevFrame &frame, uint32_t n) {
+    // one atomic per warp; every lane of the warp reaches this point (no early kernel exits)
+    const uint32_t total = __reduce_add_sync(0xFFFFFFFFu, n);
+    if ((threadIdx.x + threadIdx.y * blockDim.x) % 32 == 0 && total)
+        atomicAdd(frame.stats, (unsigned long long)total);
+}
+
+GFX_D uint32_t gbufferPixel(const DevScene &scene, const DevFrame &frame, const DevFrameParams &p) {
     const uint32_t x = blockIdx.x * 8 + threadIdx.x;
     const uint32_t y = p.y0 + blockIdx.y * 8 + threadIdx.y;
     if (x >= frame.W || y >= p.y1)
-        return;
+        return 0;
     const size_t pix = (size_t)y * frame.W + x;
     const uint32_t bufIdx = p.bufferIndex;
 
@@ -151,6 +158,11 @@ __global__ void __launch_bounds__(64) k_gbuffer(DevScene scene, DevFrame frame, 
     const f3 normalResult = (1 - curWeight) * prevNormalResult + curWeight * shadingNormalInWorld;
     frame.albedo[pix] = make_float4(albedoResult.x, albedoResult.y, albedoResult.z, 1.0f);
     frame.normal[pix] = make_float4(normalResult.x, normalResult.y, normalResult.z, 1.0f);
+    return 1;
+}
+
+__global__ void __launch_bounds__(64) k_gbuffer(DevScene scene, DevFrame frame, DevFrameParams p) {
+    countRays(frame, gbufferPixel(scene, frame, p));
 }
 
 int launchGBuffer(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* params) {

@@ -128,6 +128,10 @@ GFX_D void sampleLight(const DevScene &s, float ul, float u0, float u1, LightSam
 }
 
 GFX_D bool traceVisibility(const DevScene &s, const f3 &org, const f3 &dir, float tmax) {
+    // ray statistics: one atomic per warp per call site (lanes currently active here)
+    const uint32_t active = __activemask();
+    if ((threadIdx.x + threadIdx.y * blockDim.x) % 32 == (uint32_t)(__ffs(active) - 1))
+        atomicAdd(s.rayCounter, (unsigned long long)__popc(active));
     const Hit h = traverseBvh<true>(s.bvh, org, dir, 0.0f, tmax);
     return h.storageIndex == 0xFFFFFFFFu;
 }

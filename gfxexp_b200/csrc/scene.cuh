@@ -62,6 +62,7 @@ struct DevScene {
     const float* instCdf;
     const float* instIntegral;       // device scalar (rebuilt every frame on the GPU)
     uint32_t numInstances;
+    unsigned long long* rayCounter;  // frame statistics: rays traced (primary + visibility)
     DevBvh bvh;
 };
 
@@ -78,6 +79,7 @@ struct DevFrame {
     float4* albedo;
     float4* normal;
     const float2* neighborDeltas; // 1024 entries
+    unsigned long long* stats;    // [0] rays traced (primary + visibility)
 };
 
 struct DevCamera {

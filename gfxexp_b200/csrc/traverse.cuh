@@ -25,6 +25,7 @@ struct Hit {
     uint32_t geomIndex;
     uint32_t primIndex;
     float bcB, bcC;
+    uint32_t statNodes, statTris; // only maintained by the STATS instantiation
 };
 
 GFX_D bool testRayVsTriangle( // common/bvh_builder.cpp:1251-1270
@@ -47,7 +48,7 @@ GFX_D bool testRayVsTriangle( // common/bvh_builder.cpp:1251-1270
 
 constexpr int kStackSize = 64;
 
-template <bool ANY_HIT>
+template <bool ANY_HIT, bool STATS = false>
 GFX_D Hit traverseBvh(const DevBvh &bvh, const f3 &org, const f3 &dir, const float tmin, const float tmax) {
     Hit best;
     best.dist = tmax;
@@ -56,6 +57,8 @@ GFX_D Hit traverseBvh(const DevBvh &bvh, const f3 &org, const f3 &dir, const flo
     best.primIndex = 0xFFFFFFFFu;
     best.bcB = 0.0f;
     best.bcC = 0.0f;
+    best.statNodes = 0;
+    best.statTris = 0;
     if (bvh.numNodes == 0)
         return best;
 
@@ -77,6 +80,8 @@ GFX_D Hit traverseBvh(const DevBvh &bvh, const f3 &org, const f3 &dir, const flo
         const uint4 n2 = __ldg(np + 2);
         const uint4 n3 = __ldg(np + 3);
         const uint4 n4 = __ldg(np + 4);
+        if (STATS)
+            ++best.statNodes;
 
         const uint32_t internalMask = n0.w >> 24;
         const float ax = __uint_as_float((n0.w & 0xFFu) << 23) * idir.x;
@@ -136,6 +141,8 @@ GFX_D Hit traverseBvh(const DevBvh &bvh, const f3 &org, const f3 &dir, const flo
                 const float4 t1 = __ldg(tp + 1);
                 const float4 t2 = __ldg(tp + 2);
                 float hitDist, bcB, bcC;
+                if (STATS)
+                    ++best.statTris;
                 const bool hit = testRayVsTriangle(org, dir, tmin, tmax,
                                                    f3(t0.x, t0.y, t0.z), f3(t0.w, t1.x, t1.y), f3(t1.z, t1.w, t2.x),
                                                    &hitDist, &bcB, &bcC);

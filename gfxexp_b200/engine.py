@@ -139,6 +139,11 @@ class Context:
         p = self.lib.gfx_buffer_device_ptr(self.h, buffer_id, index, C.byref(nbytes))
         return p, nbytes.value
 
+    def read_stats(self, reset: bool = True, stream=None):
+        out = (C.c_uint64 * 4)()
+        self._check(self.lib.gfx_stats_read(self.h, stream, out, 1 if reset else 0), "gfx_stats_read")
+        return [int(v) for v in out]
+
     # -- launches -------------------------------------------------------------------------------
     def gbuffer(self, params, stream=None):
         self._check(self.lib.gfx_gbuffer_launch(self.h, stream, C.byref(params)), "gfx_gbuffer_launch")

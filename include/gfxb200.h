@@ -146,7 +146,9 @@ typedef struct GfxBvhInfo {
 
 typedef enum GfxTraceMode {
     GFX_TRACE_CLOSEST = 0, /* bvh::traverse semantics, tie -> smaller storage index */
-    GFX_TRACE_ANY = 1      /* visibility ray: dist = 0 if anything is hit in (tmin,tmax), else tmax */
+    GFX_TRACE_ANY = 1,     /* visibility ray: dist = 0 if anything is hit in (tmin,tmax), else tmax */
+    GFX_TRACE_STATS = 2    /* flag: also return bvh::TraversalStatistics per ray in instUserData
+                              (internal nodes visited | triangles tested << 16) */
 } GfxTraceMode;
 
 /* ---- per-frame parameters ------------------------------------------------------------ */
@@ -267,6 +269,9 @@ int gfx_buffer_download(gfx_ctx* ctx, void* stream, int bufferId, uint32_t index
 int gfx_buffer_upload(gfx_ctx* ctx, void* stream, int bufferId, uint32_t index, const void* host, size_t bytes);
 /* device pointer of a frame buffer (for NCCL collectives / torch views) */
 void* gfx_buffer_device_ptr(gfx_ctx* ctx, int bufferId, uint32_t index, size_t* bytes);
+
+/* counters accumulated by the frame kernels: out4[0] = rays traced (primary + visibility), others reserved */
+int gfx_stats_read(gfx_ctx* ctx, void* stream, uint64_t* out4, int reset);
 
 /* ---- launches -------------------------------------------------------------------------- */
 /* replaces gBuffer.optixPipeline.launch (restir_di_main.cpp:2366; RG/CH/MS setupGBuffers) */
