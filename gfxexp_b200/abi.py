@@ -60,7 +60,7 @@ class GfxFrameParams(C.Structure):
                 ("enableTemporalReuse", c_u32), ("enableSpatialReuse", c_u32),
                 ("useUnbiasedEstimator", c_u32), ("resetFlowBuffer", c_u32), ("enableJittering", c_u32),
                 ("currentReservoirIndex", c_u32), ("spatialNeighborBaseIndex", c_u32),
-                ("tileOriginY", c_u32), ("tileRows", c_u32)]
+                ("tileOriginY", c_u32), ("tileRows", c_u32), ("svgfFlags", c_u32), ("taaHistoryLength", c_u32)]
 
 
 NODE_DTYPE = np.dtype([("quantBoxOrigin", np.float32, 3), ("quantBoxExpScale", np.uint8, 3),
@@ -79,9 +79,11 @@ assert NODE_DTYPE.itemsize == 80 and TRI_DTYPE.itemsize == 48 and HIT_DTYPE.item
 TRACE_CLOSEST, TRACE_ANY, TRACE_STATS = 0, 1, 2
 (RESTIR_INITIAL_RIS, RESTIR_INITIAL_AND_TEMPORAL_BIASED, RESTIR_INITIAL_AND_TEMPORAL_UNBIASED,
  RESTIR_SPATIAL_BIASED, RESTIR_SPATIAL_UNBIASED, RESTIR_SHADING) = range(6)
-(SVGF_TEMPORAL_ACCUMULATE, SVGF_ESTIMATE_VARIANCE, SVGF_ATROUS, SVGF_MODULATE_TAA) = range(4)
+(SVGF_TEMPORAL_ACCUMULATE, SVGF_ESTIMATE_VARIANCE, SVGF_ATROUS, SVGF_FILL_BACKGROUND, SVGF_MODULATE_TAA) = range(5)
+SVGF_IS_FIRST_FRAME, SVGF_ENABLE_TEMPORAL_ACCUMULATION, SVGF_FEEDBACK_1ST, SVGF_ENABLE_TAA, SVGF_MODULATE_ALBEDO = 1, 2, 4, 8, 16
 (BUF_GBUFFER0, BUF_GBUFFER1, BUF_GBUFFER2, BUF_GBUFFER3, BUF_RNG, BUF_RESERVOIR, BUF_RESERVOIR_INFO,
- BUF_BEAUTY_ACCUM, BUF_ALBEDO_ACCUM, BUF_NORMAL_ACCUM, BUF_SVGF_LIGHTING_VARIANCE, BUF_SVGF_FINAL) = range(12)
+ BUF_BEAUTY_ACCUM, BUF_ALBEDO_ACCUM, BUF_NORMAL_ACCUM, BUF_SVGF_LIGHTING_VARIANCE, BUF_SVGF_FINAL,
+ BUF_SVGF_MOMENTS, BUF_SVGF_PREV_LIGHTING, BUF_SVGF_ALBEDO, BUF_SVGF_DEPTH) = range(16)
 
 # logical per-pixel layout of each downloadable buffer: (numpy dtype, elements per pixel, planes)
 BUFFER_LAYOUT = {
@@ -90,6 +92,8 @@ BUFFER_LAYOUT = {
     BUF_RESERVOIR_INFO: (np.float32, 2, 1), BUF_BEAUTY_ACCUM: (np.float32, 4, 1),
     BUF_ALBEDO_ACCUM: (np.float32, 4, 1), BUF_NORMAL_ACCUM: (np.float32, 4, 1),
     BUF_SVGF_LIGHTING_VARIANCE: (np.float32, 4, 1), BUF_SVGF_FINAL: (np.float32, 4, 1),
+    BUF_SVGF_MOMENTS: (np.uint32, 4, 1), BUF_SVGF_PREV_LIGHTING: (np.float32, 4, 1),
+    BUF_SVGF_ALBEDO: (np.float32, 4, 1), BUF_SVGF_DEPTH: (np.float32, 1, 1),
 }
 
 
@@ -179,6 +183,8 @@ def default_frame_params(scene, width: int, height: int) -> GfxFrameParams:
     p.spatialNeighborBaseIndex = 0
     p.tileOriginY = 0
     p.tileRows = 0
+    p.svgfFlags = SVGF_ENABLE_TEMPORAL_ACCUMULATION | SVGF_FEEDBACK_1ST | SVGF_ENABLE_TAA | SVGF_MODULATE_ALBEDO
+    p.taaHistoryLength = 16
     return p
 
 

@@ -14,6 +14,7 @@ void SceneState::release() {
     cudaFree(instanceMeshSlots); cudaFree(geomToInstMesh); cudaFree(geomTriOffsets);
     cudaFree(primWeights); cudaFree(primCdf); cudaFree(geomWeights); cudaFree(geomCdf);
     cudaFree(instWeights); cudaFree(instCdf); cudaFree(instIntegral);
+    cudaFree(primProb); cudaFree(geomProb); cudaFree(instProb); cudaFree(lightTris); cudaFree(lightTriBase); cudaFree(emissiveGeoms);
     *this = SceneState();
 }
 void BvhState::release() {
@@ -29,7 +30,7 @@ void FrameState::release() {
         cudaFree(svgfLighting[i]); cudaFree(svgfMoments[i]); cudaFree(svgfFinal[i]); cudaFree(svgfDepth[i]);
     }
     cudaFree(stats); cudaFree(rng); cudaFree(beauty); cudaFree(albedo); cudaFree(normal); cudaFree(neighborDeltas);
-    cudaFree(svgfPrevLighting);
+    cudaFree(svgfPrevLighting); cudaFree(svgfAlbedo); cudaFree(svgfPrevScreenPos);
     *this = FrameState();
 }
 
@@ -101,6 +102,11 @@ DevScene gfx_ctx::devScene() const {
     d.instWeights = scene.instWeights;
     d.instCdf = scene.instCdf;
     d.instIntegral = scene.instIntegral;
+    d.primProb = scene.primProb;
+    d.geomProb = scene.geomProb;
+    d.instProb = scene.instProb;
+    d.lightTris = scene.lightTris;
+    d.lightTriBase = scene.lightTriBase;
     d.numInstances = scene.numInstances;
     d.rayCounter = frame.stats;
     d.bvh.nodes = reinterpret_cast<const uint4*>(bvh.nodes);
@@ -252,6 +258,7 @@ int gfx_scene_upload(gfx_ctx* ctx, const GfxSceneDesc* sd) {
         d.uniformScale = in.uniformScale;
         d.firstMeshSlot = in.firstMeshSlot;
         d.numMeshSlots = in.numMeshSlots;
+        d.geomBase = (uint32_t)geomToInstMesh.size();
         for (uint32_t k = 0; k < in.numMeshSlots; ++k) {
             const uint32_t slot = sd->instanceMeshSlots[in.firstMeshSlot + k];
             if (slot >= sd->numMeshes) {
@@ -264,6 +271,17 @@ int gfx_scene_upload(gfx_ctx* ctx, const GfxSceneDesc* sd) {
         }
     }
     geomTriOffsets.push_back(flatTris);
+    // light-triangle table layout: every triangle of every geometry whose material is an emitter
+    std::vector<uint32_t> lightTriBase(geomToInstMesh.size(), 0xFFFFFFFFu), emissiveGeoms;
+    uint32_t numLightTris = 0;
+    for (size_t g = 0; g < geomToInstMesh.size(); ++g) {
+        const DevMesh &m = meshes[geomToInstMesh[g].y];
+        if (sd->materials[m.materialSlot].hasEmittance) {
+            lightTriBase[g] = numLightTris;
+            emissiveGeoms.push_back((uint32_t)g);
+            numLightTris += m.numTriangles;
+        }
+    }
 
     auto upload = [&](auto** dst, const void* src, size_t bytes) -> cudaError_t {
         cudaError_t e = cudaMalloc((void**)dst, bytes ? bytes : 16);
@@ -285,6 +303,14 @@ int gfx_scene_upload(gfx_ctx* ctx, const GfxSceneDesc* sd) {
     GFX_CUDA(ctx, cudaMalloc(&S.instWeights, (sd->numInstances ? sd->numInstances : 4) * 4));
     GFX_CUDA(ctx, cudaMalloc(&S.instCdf, (sd->numInstances ? sd->numInstances : 4) * 4));
     GFX_CUDA(ctx, cudaMalloc(&S.instIntegral, 16));
+    GFX_CUDA(ctx, cudaMalloc(&S.primProb, (numTris ? numTris : 4) * 4));
+    GFX_CUDA(ctx, cudaMalloc(&S.geomProb, (sd->numInstanceMeshSlots ? sd->numInstanceMeshSlots : 4) * 4));
+    GFX_CUDA(ctx, cudaMalloc(&S.instProb, (sd->numInstances ? sd->numInstances : 4) * 4));
+    GFX_CUDA(ctx, cudaMalloc(&S.lightTris, (size_t)(numLightTris ? numLightTris : 1) * 96));
+    GFX_CUDA(ctx, upload(&S.lightTriBase, lightTriBase.data(), lightTriBase.size() * 4));
+    GFX_CUDA(ctx, upload(&S.emissiveGeoms, emissiveGeoms.data(), emissiveGeoms.size() * 4));
+    S.numEmissiveGeoms = (uint32_t)emissiveGeoms.size();
+    S.numLightTris = numLightTris;
     GFX_CUDA(ctx, cudaMemset(S.instIntegral, 0, 16));
     S.numMeshes = sd->numMeshes;
     S.numMaterials = sd->numMaterials;
@@ -314,6 +340,7 @@ int gfx_scene_update_instances(gfx_ctx* ctx, void* stream, const GfxInstanceDesc
         memcpy(d.normalMatrix, instances[i].normalMatrix, 36);
         d.uniformScale = instances[i].uniformScale;
     }
+    S.lightTrisDirty = true;
     // geomIntegral lives on the device copy only: patch the transform part of each record
     for (uint32_t i = 0; i < numInstances; ++i)
         GFX_CUDA(ctx, cudaMemcpyAsync(S.instances + i, &S.hostInstances[i], offsetof(DevInstance, firstMeshSlot),
@@ -470,6 +497,10 @@ int gfx_frame_create(gfx_ctx* ctx, uint32_t W, uint32_t H) {
     }
     GFX_CUDA(ctx, cudaMalloc(&F.svgfPrevLighting, n * 16));
     GFX_CUDA(ctx, cudaMemset(F.svgfPrevLighting, 0, n * 16));
+    GFX_CUDA(ctx, cudaMalloc(&F.svgfAlbedo, n * 16));
+    GFX_CUDA(ctx, cudaMemset(F.svgfAlbedo, 0, n * 16));
+    GFX_CUDA(ctx, cudaMalloc(&F.svgfPrevScreenPos, n * 8));
+    GFX_CUDA(ctx, cudaMemset(F.svgfPrevScreenPos, 0, n * 8));
     GFX_CUDA(ctx, cudaMalloc(&F.rng, n * 8));
     GFX_CUDA(ctx, cudaMalloc(&F.beauty, n * 16));
     GFX_CUDA(ctx, cudaMalloc(&F.albedo, n * 16));
@@ -578,6 +609,10 @@ static void* bufferPtr(gfx_ctx* ctx, int id, uint32_t index, size_t* bytes) {
     case GFX_BUF_NORMAL_ACCUM: p = F.normal; b = n * 16; break;
     case GFX_BUF_SVGF_LIGHTING_VARIANCE: p = F.svgfLighting[i]; b = n * 16; break;
     case GFX_BUF_SVGF_FINAL: p = F.svgfFinal[i]; b = n * 16; break;
+    case GFX_BUF_SVGF_MOMENTS: p = F.svgfMoments[i]; b = n * 16; break;
+    case GFX_BUF_SVGF_PREV_LIGHTING: p = F.svgfPrevLighting; b = n * 16; break;
+    case GFX_BUF_SVGF_ALBEDO: p = F.svgfAlbedo; b = n * 16; break;
+    case GFX_BUF_SVGF_DEPTH: p = F.svgfDepth[i]; b = n * 4; break;
     default: break;
     }
     if (bytes) *bytes = b;

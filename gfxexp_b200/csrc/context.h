@@ -24,10 +24,18 @@ struct SceneState {
     float* instWeights = nullptr;
     float* instCdf = nullptr;
     float* instIntegral = nullptr;
+    float* primProb = nullptr;
+    float* geomProb = nullptr;
+    float* instProb = nullptr;
+    float4* lightTris = nullptr;
+    uint32_t* lightTriBase = nullptr;      // per flattened geometry
+    uint32_t* emissiveGeoms = nullptr;     // list of flattened geometry indices with an emissive material
+    uint32_t numEmissiveGeoms = 0, numLightTris = 0;
     uint32_t numMeshes = 0, numMaterials = 0, numInstances = 0, numInstanceMeshSlots = 0;
     uint32_t numGeoms = 0, numFlatTris = 0, numMeshTris = 0, numVertices = 0;
     bool uploaded = false;
     bool staticLightDistsBuilt = false;
+    bool lightTrisDirty = true;
     std::vector<DevMesh> hostMeshes;
     std::vector<DevInstance> hostInstances;
     void release();
@@ -63,6 +71,8 @@ struct FrameState {
     float4* svgfLighting[2] = { nullptr, nullptr };  // lighting rgb + variance, ping-pong
     float4* svgfMoments[2] = { nullptr, nullptr };   // first/second luminance moments + history length
     float4* svgfPrevLighting = nullptr;
+    float4* svgfAlbedo = nullptr;
+    float2* svgfPrevScreenPos = nullptr;
     float4* svgfFinal[2] = { nullptr, nullptr };
     float* svgfDepth[2] = { nullptr, nullptr };
     bool created = false;

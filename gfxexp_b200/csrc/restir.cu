@@ -46,18 +46,40 @@ struct Reservoir { // restir_di_shared.h:106-139
 
 GFX_D float convertToWeight(const f3 &c) { return (c.x + c.y + c.z) / 3; } // restir_di_shared.h:82-85
 
+// last index with cdf[idx] <= u: the power-of-two stepping search of
+// DiscreteDistribution1DTemplate::sample (common_shared.h:226-232)
+GFX_D uint32_t searchCdf(const float* __restrict__ cdf, uint32_t numValues, float u) {
+    int idx = 0;
+    for (int d = (int)(nextPowerOf2(numValues) >> 1); d >= 1; d >>= 1) {
+        if (idx + d >= (int)numValues)
+            continue;
+        if (__ldg(cdf + idx + d) <= u)
+            idx += d;
+    }
+    return (uint32_t)idx;
+}
+GFX_D float remapCdf(const float* __restrict__ cdf, uint32_t numValues, float integral, uint32_t idx, float u) {
+    // common_shared.h:235-241
+    const float lCDF = __ldg(cdf + idx);
+    float rCDF = integral;
+    if (idx < numValues - 1)
+        rCDF = __ldg(cdf + idx + 1);
+    return (u - lCDF) / (rCDF - lCDF);
+}
+
 GFX_D void sampleLight(const DevScene &s, float ul, float u0, float u1, LightSample* lightSample, float* areaPDensity) {
-    // restir_di_shared.h:320-516 with sampleEnvLight = false, useSolidAngleSampling = false
-    f3 emittance(0.0f);
+    // restir_di_shared.h:320-516 with sampleEnvLight = false, useSolidAngleSampling = false.
+    // The three DiscreteDistribution1D::sample calls are spelled out; weights[idx] / integral comes
+    // from the pre-divided prob tables and the triangle operands from the lightTris table (lights.cu),
+    // both produced by the reference's own expressions, so the result is bit-identical.
     float lightProb = 1.0f;
 
-    DiscreteDistribution1D lightInstDist;
-    lightInstDist.weights = s.instWeights;
-    lightInstDist.cdf = s.instCdf;
-    lightInstDist.integral = *s.instIntegral;
-    lightInstDist.numValues = s.numInstances;
-    float instProb, uGeomInst;
-    const uint32_t instSlot = lightInstDist.sample(ul, &instProb, &uGeomInst);
+    // instance
+    const float instIntegral = __ldg(s.instIntegral);
+    float u = ul * instIntegral;
+    const uint32_t instSlot = searchCdf(s.instCdf, s.numInstances, u);
+    const float uGeomInst = remapCdf(s.instCdf, s.numInstances, instIntegral, instSlot, u);
+    const float instProb = __ldg(s.instProb + instSlot);
     lightProb *= instProb;
     const DevInstance* inst = s.instances + instSlot;
     if (instProb == 0.0f) {
@@ -65,42 +87,33 @@ GFX_D void sampleLight(const DevScene &s, float ul, float u0, float u1, LightSam
         return;
     }
 
-    DiscreteDistribution1D lightGeomInstDist;
-    lightGeomInstDist.weights = s.geomWeights + inst->firstMeshSlot;
-    lightGeomInstDist.cdf = s.geomCdf + inst->firstMeshSlot;
-    lightGeomInstDist.integral = inst->geomIntegral;
-    lightGeomInstDist.numValues = inst->numMeshSlots;
-    float geomInstProb, uPrim;
-    const uint32_t geomInstIndexInInst = lightGeomInstDist.sample(uGeomInst, &geomInstProb, &uPrim);
-    const uint32_t geomInstSlot = s.instanceMeshSlots[inst->firstMeshSlot + geomInstIndexInInst];
+    // geometry instance
+    const uint32_t firstMeshSlot = inst->firstMeshSlot, numMeshSlots = inst->numMeshSlots;
+    const float geomIntegral = inst->geomIntegral;
+    u = uGeomInst * geomIntegral;
+    const uint32_t geomInstIndexInInst = searchCdf(s.geomCdf + firstMeshSlot, numMeshSlots, u);
+    const float uPrim = remapCdf(s.geomCdf + firstMeshSlot, numMeshSlots, geomIntegral, geomInstIndexInInst, u);
+    const float geomInstProb = __ldg(s.geomProb + firstMeshSlot + geomInstIndexInInst);
+    const uint32_t geomInstSlot = __ldg(s.instanceMeshSlots + firstMeshSlot + geomInstIndexInInst);
     lightProb *= geomInstProb;
-    const DevMesh mesh = s.meshes[geomInstSlot];
     if (geomInstProb == 0.0f) {
         *areaPDensity = 0.0f;
         return;
     }
 
-    DiscreteDistribution1D emitterPrimDist;
-    emitterPrimDist.weights = s.primWeights + mesh.triBase;
-    emitterPrimDist.cdf = s.primCdf + mesh.triBase;
-    emitterPrimDist.integral = mesh.primIntegral;
-    emitterPrimDist.numValues = mesh.numTriangles;
-    float primProb;
-    const uint32_t primIndex = emitterPrimDist.sample(uPrim, &primProb);
+    // primitive
+    const DevMesh* mesh = s.meshes + geomInstSlot;
+    const uint32_t triBase = mesh->triBase, numTriangles = mesh->numTriangles;
+    u = uPrim * mesh->primIntegral;
+    const uint32_t primIndex = searchCdf(s.primCdf + triBase, numTriangles, u);
+    const float primProb = __ldg(s.primProb + triBase + primIndex);
     lightProb *= primProb;
 
-    const GfxMaterialDesc* mat = s.materials + mesh.materialSlot;
-    const uint4 tri = __ldg(s.triangles + mesh.triBase + primIndex);
-    const float4* vA = s.vertices + 3 * (size_t)(mesh.vertexBase + tri.x);
-    const float4* vB = s.vertices + 3 * (size_t)(mesh.vertexBase + tri.y);
-    const float4* vC = s.vertices + 3 * (size_t)(mesh.vertexBase + tri.z);
-    const float4 a0 = __ldg(vA), a1 = __ldg(vA + 1);
-    const float4 b0 = __ldg(vB), b1 = __ldg(vB + 1);
-    const float4 c0 = __ldg(vC), c1 = __ldg(vC + 1);
-    const f3 pA = xfmPoint(inst->transform, f3(a0.x, a0.y, a0.z));
-    const f3 pB = xfmPoint(inst->transform, f3(b0.x, b0.y, b0.z));
-    const f3 pC = xfmPoint(inst->transform, f3(c0.x, c0.y, c0.z));
-    const f3 geomNormal = cross(pB - pA, pC - pA);
+    const uint32_t lt = __ldg(s.lightTriBase + inst->geomBase + geomInstIndexInInst) + primIndex;
+    const float4* e = s.lightTris + 6 * (size_t)lt;
+    const float4 e0 = __ldg(e + 0), e1 = __ldg(e + 1), e2 = __ldg(e + 2), e3 = __ldg(e + 3), e4 = __ldg(e + 4), e5 = __ldg(e + 5);
+    const f3 pA(e0.x, e0.y, e0.z), pB(e1.x, e1.y, e1.z), pC(e2.x, e2.y, e2.z);
+    const f3 nA(e1.w, e2.w, e3.x), nB(e3.y, e3.z, e3.w), nC(e4.x, e4.y, e4.z);
 
     // A Low-Distortion Map Between Triangle and Square (:485-498)
     float bcA = 0.5f * u0;
@@ -112,19 +125,14 @@ GFX_D void sampleLight(const DevScene &s, float ul, float u0, float u1, LightSam
         bcA -= offset;
     const float bcC = 1 - (bcA + bcB);
 
-    const float recArea = 2.0f / length(geomNormal);
+    const float recArea = e0.w;
     *areaPDensity = lightProb * recArea;
 
     lightSample->position = bcA * pA + bcB * pB + bcC * pC;
     lightSample->atInfinity = 0;
-    lightSample->normal = bcA * f3(a1.x, a1.y, a1.z) + bcB * f3(b1.x, b1.y, b1.z) + bcC * f3(c1.x, c1.y, c1.z);
+    lightSample->normal = bcA * nA + bcB * nB + bcC * nC;
     lightSample->normal = normalize(mul3x3(inst->normalMatrix, lightSample->normal));
-
-    if (mat->hasEmittance) {
-        emittance = f3(1.0f, 1.0f, 1.0f);
-        emittance *= f3(mat->emittance[0], mat->emittance[1], mat->emittance[2]);
-    }
-    lightSample->emittance = emittance;
+    lightSample->emittance = f3(e5.x, e5.y, e5.z);
 }
 
 GFX_D bool traceVisibility(const DevScene &s, const f3 &org, const f3 &dir, float tmax) {

@@ -34,7 +34,8 @@ struct DevInstance {
     uint32_t firstMeshSlot;
     uint32_t numMeshSlots;
     float geomIntegral;    // lightGeomInstDist.integral()
-    uint32_t pad[3];
+    uint32_t geomBase;     // index of this instance's first flattened geometry (instance order)
+    uint32_t pad[2];
 };
 static_assert(sizeof(DevInstance) % 16 == 0, "DevInstance must stay 16-byte aligned");
 
@@ -61,6 +62,16 @@ struct DevScene {
     const float* instWeights;        // per instance
     const float* instCdf;
     const float* instIntegral;       // device scalar (rebuilt every frame on the GPU)
+    // pre-divided selection probabilities weights[i] / integral (same IEEE division the sampler did)
+    const float* primProb;
+    const float* geomProb;
+    const float* instProb;
+    // world-space table of the triangles of every emissive geometry, 6 float4 each:
+    // (pA, recArea) (pB, nA.x) (pC, nA.y) (nA.z, nB) (nC, -) (emittance, -); lightTriBase[g] = first entry
+    // of flattened geometry g or 0xFFFFFFFF.  Values are produced by the very expressions of
+    // sampleLight (restir_di_shared.h:417-425,485-511), so reading them is bit-identical to recomputing.
+    const float4* lightTris;
+    const uint32_t* lightTriBase;
     uint32_t numInstances;
     unsigned long long* rayCounter;  // frame statistics: rays traced (primary + visibility)
     DevBvh bvh;

@@ -187,6 +187,22 @@ def restir_frame_passes(params, frame_index: int, num_spatial_passes: int = 1, t
     yield ("restir", abi.RESTIR_SHADING)
 
 
+def svgf_frame_passes(params, frame_index: int, num_filtering_stages: int = 5):
+    """The launch list of the SVGF part of a frame (svgf/svgf_main.cpp:2118-2172): temporal accumulation of
+    the demodulated lighting, variance estimate, 5 a-trous stages, background fill, albedo modulation + TAA.
+    Yields (pass_id, stage); sets the first-frame flag exactly like the host (`isFirstFrame`)."""
+    if frame_index == 0:
+        params.svgfFlags |= abi.SVGF_IS_FIRST_FRAME
+    else:
+        params.svgfFlags &= ~abi.SVGF_IS_FIRST_FRAME
+    yield (abi.SVGF_TEMPORAL_ACCUMULATE, 0)
+    yield (abi.SVGF_ESTIMATE_VARIANCE, 0)
+    for stage in range(num_filtering_stages):
+        yield (abi.SVGF_ATROUS, stage)
+    yield (abi.SVGF_FILL_BACKGROUND, num_filtering_stages)
+    yield (abi.SVGF_MODULATE_TAA, num_filtering_stages)
+
+
 class ReSTIRRenderer:
     """Config-2 style frame driver (OriginalReSTIRBiased by default)."""
 

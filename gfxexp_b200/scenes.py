@@ -252,8 +252,8 @@ def city_scene(num_buildings: int = 700, building_tess=(12, 20), ground_tess: in
         tint = np.array([[1.0, 0.85, 0.6], [0.7, 0.85, 1.0], [1.0, 0.3, 0.2], [0.2, 1.0, 0.4],
                          [0.3, 0.4, 1.0], [1.0, 1.0, 1.0], [1.0, 0.6, 0.1], [0.8, 0.2, 1.0]][k], dtype=F32)
         m["emittance"] = tint * F32(40.0 + 10.0 * k)
-        m["p0"] = F32(0.0)
-        m["p1"] = F32(0.0)
+        m["p0"] = F32(0.8)   # lamp glass: bright diffuse body so demodulated lighting stays finite (SVGF)
+        m["p1"] = F32(0.04)
         m["p2"] = F32(0.3)
     meshes: List[Mesh] = []
     instances: List[Instance] = []

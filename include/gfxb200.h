@@ -183,7 +183,19 @@ typedef struct GfxFrameParams {
     uint32_t spatialNeighborBaseIndex; /* plp.spatialNeighborBaseIndex */
     uint32_t tileOriginY;              /* multi-GPU: first row owned by this rank (0 on 1 GPU) */
     uint32_t tileRows;                 /* multi-GPU: rows owned by this rank (0 = all) */
+    /* SVGF (svgf_shared.h PerFramePipelineLaunchParameters: isFirstFrame, enableTemporalAccumulation,
+     * feedback1stFilteredResult, enableTemporalAA, modulateAlbedo, taaHistoryLength; svgf_main.cpp:1730-1736) */
+    uint32_t svgfFlags;                /* GfxSVGFFlags */
+    uint32_t taaHistoryLength;         /* 16 by default */
 } GfxFrameParams;
+
+typedef enum GfxSVGFFlags {
+    GFX_SVGF_IS_FIRST_FRAME = 1,
+    GFX_SVGF_ENABLE_TEMPORAL_ACCUMULATION = 2,
+    GFX_SVGF_FEEDBACK_1ST_FILTERED_RESULT = 4,
+    GFX_SVGF_ENABLE_TEMPORAL_AA = 8,
+    GFX_SVGF_MODULATE_ALBEDO = 16
+} GfxSVGFFlags;
 
 /* ReSTIR DI entry points (restir_di/restir_di_main.cpp:63-74 ReSTIREntryPoint) */
 typedef enum GfxReSTIRPass {
@@ -197,10 +209,11 @@ typedef enum GfxReSTIRPass {
 
 /* SVGF entry points (svgf/svgf_main.cpp:2127-2172) */
 typedef enum GfxSVGFPass {
-    GFX_SVGF_TEMPORAL_ACCUMULATE = 0,
-    GFX_SVGF_ESTIMATE_VARIANCE = 1,
-    GFX_SVGF_ATROUS = 2,
-    GFX_SVGF_MODULATE_TAA = 3
+    GFX_SVGF_TEMPORAL_ACCUMULATE = 0, /* demodulate + reprojectPreviousAccumulation + EMA (svgf/gpu_kernels/optix_pathtracing_kernels.cu:55-128,325-378) */
+    GFX_SVGF_ESTIMATE_VARIANCE = 1,   /* estimateVariance (svgf.cu:30-134) */
+    GFX_SVGF_ATROUS = 2,              /* applyATrousFilter_box3x3(stage) (svgf.cu:221-354) */
+    GFX_SVGF_FILL_BACKGROUND = 3,     /* fillBackground (svgf.cu:378-461) */
+    GFX_SVGF_MODULATE_TAA = 4         /* applyAlbedoModulationAndTemporalAntiAliasing (svgf.cu:533-611) */
 } GfxSVGFPass;
 
 /* buffers that can be read back for parity checks (logical row-major (x,y) order) */
@@ -216,7 +229,11 @@ typedef enum GfxBufferId {
     GFX_BUF_ALBEDO_ACCUM = 8,   /* float x4 */
     GFX_BUF_NORMAL_ACCUM = 9,   /* float x4 */
     GFX_BUF_SVGF_LIGHTING_VARIANCE = 10, /* float x4 : noisy/filtered lighting rgb + variance */
-    GFX_BUF_SVGF_FINAL = 11     /* float x4 */
+    GFX_BUF_SVGF_FINAL = 11,    /* float x4 */
+    GFX_BUF_SVGF_MOMENTS = 12,  /* float x4 : firstMoment, secondMoment, sampleInfo(u32), 0 */
+    GFX_BUF_SVGF_PREV_LIGHTING = 13, /* float x4 : prevNoisyLightingBuffer */
+    GFX_BUF_SVGF_ALBEDO = 14,   /* float x4 : dhReflectance */
+    GFX_BUF_SVGF_DEPTH = 15     /* float : GL-style depth, background 1.0 */
 } GfxBufferId;
 
 /* ---- context ------------------------------------------------------------------------- */

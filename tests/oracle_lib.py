@@ -73,6 +73,12 @@ def lib() -> C.CDLL:
         L.orc_gbuffer.argtypes = [vp, C.POINTER(abi.GfxFrameParams), C.c_int]
         L.orc_restir.argtypes = [vp, C.POINTER(abi.GfxFrameParams), C.c_int, C.c_int]
         L.orc_generate_primary_rays.argtypes = [C.POINTER(abi.GfxFrameParams), C.c_uint32, C.c_uint32, vp]
+        L.orc_svgf_create.restype = vp
+        L.orc_svgf_create.argtypes = [vp, C.c_uint32, C.c_uint32]
+        L.orc_svgf_destroy.argtypes = [vp]
+        L.orc_svgf_buffer_ptr.restype = vp
+        L.orc_svgf_buffer_ptr.argtypes = [vp, C.c_int, C.c_uint32, C.POINTER(C.c_size_t)]
+        L.orc_svgf_pass.argtypes = [vp, C.POINTER(abi.GfxFrameParams), C.c_int, C.c_uint32, C.c_int]
         _lib = L
     return _lib
 
@@ -170,6 +176,32 @@ class OracleFrame:
 
     def restir(self, params, pass_id: int, threads: int = 0):
         lib().orc_restir(self.h, C.byref(params), pass_id, threads)
+
+
+class OracleSvgf:
+    def __init__(self, oframe: OracleFrame):
+        self.oframe = oframe
+        self.W, self.H = oframe.W, oframe.H
+        self.h = lib().orc_svgf_create(oframe.h, oframe.W, oframe.H)
+
+    def close(self):
+        if self.h:
+            lib().orc_svgf_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def run(self, params, pass_id: int, stage: int = 0, threads: int = 0):
+        lib().orc_svgf_pass(self.h, C.byref(params), pass_id, stage, threads)
+
+    def buffer(self, buffer_id: int, index: int = 0) -> np.ndarray:
+        nbytes = C.c_size_t()
+        ptr = lib().orc_svgf_buffer_ptr(self.h, buffer_id, index, C.byref(nbytes))
+        dtype, comps, planes = abi.BUFFER_LAYOUT[buffer_id]
+        raw = (C.c_uint8 * nbytes.value).from_address(ptr)
+        arr = np.frombuffer(raw, dtype=dtype).copy()
+        return arr.reshape(self.H, self.W, comps) if comps > 1 else arr.reshape(self.H, self.W)
 
 
 def primary_rays(params, width: int, height: int) -> np.ndarray:
