@@ -1,12 +1,750 @@
-// nrc.cu — NRC network (placeholder until the tcgen05 MLP lands; see DESIGN.md build order).
+// nrc.cu — the Neural Radiance Cache network on sm_100a.
+//
+// Replaces NeuralRadianceCache::{initialize,infer,train} (neural_radiance_caching/network_interface.cu:
+// 48-157) and the tiny-cuda-nn kernels behind it (ext/tiny-cuda-nn: kernel_grid<half,3,2>
+// encodings/grid.h:132-304, kernel_one_blob encodings/oneblob.h:83-108, kernel_mlp_fused<64,...>
+// src/fully_fused_mlp.cu:47-129 — nvcuda::wmma 16x16x16 half —, relative_l2_luminance_loss,
+// adam_step, ema_step_half_precision).
+//
+// Inference (2.2 M queries per 1080p frame) is ONE fused kernel: each 128-thread CTA encodes 128
+// queries (hash grid + one-blob + identity -> 64 fp16 features) straight into shared memory in the
+// tcgen05 K-major core-matrix layout, then runs the 64->64->...->16 MLP on the 5th-generation tensor
+// cores: tcgen05.mma (M=128, N=64|16, K=16, fp16 in, fp32 accumulate) issued by one thread with the
+// accumulator in TMEM, tcgen05.ld back to registers for ReLU + fp16 rounding, activations written
+// back to the same shared-memory tile for the next layer.  Weights (18 KB) stay resident in shared
+// memory, pre-arranged in the UMMA layout by k_nrcPrepWeights.  No activation ever touches HBM: the
+// compulsory traffic is 56 B in + 12 B out per query.
+//
+// Training (4 x 16 384 samples per frame) is latency-bound and runs on CUDA cores: one block = 128
+// samples, weights and activations in shared memory, dW reduced per block then atomically added.
 #include "context.h"
-struct gfx_nrc { gfx_ctx* ctx; };
-extern "C" {
-int gfx_nrc_create(gfx_ctx* ctx, uint32_t, float, gfx_nrc** out) { if (out) *out = nullptr; if (ctx) ctx->setError("gfx_nrc_create: not implemented yet"); return GFX_ERR_UNSUPPORTED; }
-void gfx_nrc_destroy(gfx_nrc* nrc) { delete nrc; }
-int gfx_nrc_infer(gfx_nrc*, void*, const float*, float*, uint32_t) { return GFX_ERR_UNSUPPORTED; }
-int gfx_nrc_train(gfx_nrc*, void*, const float*, const float*, uint32_t, float*) { return GFX_ERR_UNSUPPORTED; }
-int gfx_nrc_get_params(gfx_nrc*, void*, size_t) { return GFX_ERR_UNSUPPORTED; }
-int gfx_nrc_set_params(gfx_nrc*, const void*, size_t) { return GFX_ERR_UNSUPPORTED; }
-uint32_t gfx_nrc_num_params(gfx_nrc*) { return 0; }
+#include <cuda_fp16.h>
+
+namespace gfx {
+
+constexpr uint32_t kInputDims = 14, kOutputDims = 3, kWidth = 64, kPaddedOutput = 16;
+constexpr uint32_t kLevels = 16, kLog2HashmapSize = 15, kBaseResolution = 16;
+constexpr float kLossScale = 128.0f;
+
+struct NrcLevel {
+    uint32_t offset;      // grid entries
+    uint32_t hashmapSize;
+    float scale;
+    uint32_t resolution;
+};
+struct NrcLevels { NrcLevel l[kLevels]; };
+
+} // namespace gfx
+
+struct gfx_nrc {
+    gfx_ctx* ctx = nullptr;
+    uint32_t numHiddenLayers = 2;
+    float learningRate = 1e-2f;
+    uint32_t numMatrixWeights = 0, numParams = 0;
+    gfx::NrcLevels levels;
+    __half* params = nullptr;     // current fp16 weights
+    __half* paramsEma = nullptr;  // inference weights
+    float* master = nullptr;
+    float* m1 = nullptr;
+    float* m2 = nullptr;
+    uint32_t* steps = nullptr;
+    float* grads = nullptr;       // fp32, loss-scaled
+    float* loss = nullptr;        // device scalar
+    uint4* ummaWeights = nullptr; // EMA MLP weights in the tcgen05 shared-memory layout
+    uint32_t globalStep = 0;
+    bool ummaDirty = true;
+};
+
+namespace gfx {
+
+GFX_D float quarticCdf(float x, float invRadius) { // tiny-cuda-nn common_device.h:478-483
+    const float u = x * invRadius;
+    const float u2 = u * u;
+    const float u4 = u2 * u2;
+    return fmaxf(0.0f, fminf(1.0f, (15.0f / 16.0f) * u * (1 - (2.0f / 3.0f) * u2 + (1.0f / 5.0f) * u4) + 0.5f));
 }
+
+GFX_D uint32_t nrcGridIndex(const NrcLevel &lv, const uint32_t pos[3]) { // grid.h:76-111
+    uint32_t stride = 1;
+    uint32_t index = 0;
+#pragma unroll
+    for (uint32_t dim = 0; dim < 3; ++dim) {
+        if (stride <= lv.hashmapSize) {
+            index += pos[dim] * stride;
+            stride *= lv.resolution;
+        }
+    }
+    if (lv.hashmapSize < stride)
+        index = (pos[0] * 1u) ^ (pos[1] * 2654435761u) ^ (pos[2] * 805459861u);
+    return (index % lv.hashmapSize) * 2u;
+}
+
+// Encodes one query into 64 halves, delivered 8 at a time (chunk c = features 8c..8c+7) through `emit`.
+// Arithmetic mirrors oracle/nrc.cpp::encode (half accumulation of the trilinear blend like kernel_grid).
+template <typename Emit>
+GFX_D void nrcEncode(const NrcLevels &levels, const __half* __restrict__ table, const float* __restrict__ in, Emit emit) {
+    float q[kInputDims];
+#pragma unroll
+    for (uint32_t d = 0; d < kInputDims; ++d)
+        q[d] = in[d];
+    __half feat[8];
+#pragma unroll 1
+    for (uint32_t l = 0; l < kLevels; ++l) {
+        const NrcLevel lv = levels.l[l];
+        const __half2* grid = reinterpret_cast<const __half2*>(table + (size_t)lv.offset * 2);
+        float pos[3];
+        uint32_t posGrid[3];
+#pragma unroll
+        for (uint32_t d = 0; d < 3; ++d) {
+            pos[d] = q[d] * lv.scale + 0.5f;
+            const int tmp = (int)floorf(pos[d]);
+            posGrid[d] = (uint32_t)tmp;
+            pos[d] -= (float)tmp;
+        }
+        __half r0 = __float2half(0.0f), r1 = __float2half(0.0f);
+#pragma unroll
+        for (uint32_t idx = 0; idx < 8; ++idx) {
+            float weight = 1;
+            uint32_t local[3];
+#pragma unroll
+            for (uint32_t d = 0; d < 3; ++d) {
+                if ((idx & (1u << d)) == 0) {
+                    weight *= 1 - pos[d];
+                    local[d] = posGrid[d];
+                }
+                else {
+                    weight *= pos[d];
+                    local[d] = posGrid[d] + 1;
+                }
+            }
+            const __half2 v = __ldg(grid + (nrcGridIndex(lv, local) >> 1));
+            r0 = __float2half(__half2float(r0) + __half2float(__float2half(weight * __low2float(v))));
+            r1 = __float2half(__half2float(r1) + __half2float(__float2half(weight * __high2float(v))));
+        }
+        feat[(l & 3) * 2 + 0] = r0;
+        feat[(l & 3) * 2 + 1] = r1;
+        if ((l & 3) == 3)
+            emit(l >> 2, feat);
+    }
+    // OneBlob: 5 dims x 4 bins -> features 32..51, identity 52..57, ones 58..63
+    __half tail[32];
+#pragma unroll
+    for (uint32_t d = 0; d < 5; ++d) {
+        const float x = q[3 + d];
+        float leftCdf[4];
+#pragma unroll
+        for (uint32_t b = 0; b < 4; ++b) {
+            const float lb = 0.25f * (float)b; // scalbnf(b, -2)
+            leftCdf[b] = quarticCdf(lb - x, 4.0f) + quarticCdf(lb - x - 1.0f, 4.0f) + quarticCdf(lb - x + 1.0f, 4.0f);
+        }
+#pragma unroll
+        for (uint32_t b = 0; b < 4; ++b) {
+            float rightCdf = leftCdf[(b + 1) & 3];
+            if (b == 3)
+                rightCdf += 1;
+            tail[d * 4 + b] = __float2half(rightCdf - leftCdf[b]);
+        }
+    }
+#pragma unroll
+    for (uint32_t d = 0; d < 6; ++d)
+        tail[20 + d] = __float2half(q[8 + d]);
+#pragma unroll
+    for (uint32_t k = 26; k < 32; ++k)
+        tail[k] = __float2half(1.0f);
+#pragma unroll
+    for (uint32_t c = 0; c < 4; ++c)
+        emit(4 + c, tail + 8 * c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// tcgen05 helpers (PTX for sm_100a)
+// ---------------------------------------------------------------------------------------------
+GFX_D uint32_t smemU32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor): core matrices are
+// 8 rows x 16 B stored contiguously; LBO = byte distance between the two K-halves of one MMA (K = 16),
+// SBO = byte distance between consecutive 8-row groups.
+GFX_D uint64_t makeSmemDesc(uint32_t addr, uint32_t lboBytes, uint32_t sboBytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((lboBytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sboBytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46; // descriptor version for sm_100
+    return d;               // base_offset 0, lbo_mode 0, layout_type 0 (SWIZZLE_NONE)
+}
+// instruction descriptor for kind::f16 (cute::UMMA::InstrDescriptor): D = F32, A = B = F16, K-major both
+__host__ __device__ constexpr uint32_t makeInstrDesc(uint32_t M, uint32_t N) {
+    return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+GFX_D void umma(uint32_t tmemD, uint64_t aDesc, uint64_t bDesc, uint32_t iDesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n"
+        :: "r"(tmemD), "l"(aDesc), "l"(bDesc), "r"(iDesc), "r"(accumulate) : "memory");
+}
+GFX_D void ummaCommit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smemU32(bar)) : "memory");
+}
+GFX_D void mbarInit(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smemU32(bar)), "r"(count) : "memory");
+}
+GFX_D void mbarWait(uint64_t* bar, uint32_t phase) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}\n"
+        :: "r"(smemU32(bar)), "r"(phase) : "memory");
+}
+GFX_D void tmemLoad32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+GFX_D void tmemLoad4(uint32_t taddr, uint32_t (&r)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
+GFX_D void tmemWaitLd() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+GFX_D void tcFenceBefore() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+GFX_D void tcFenceAfter() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+GFX_D void fenceProxyAsync() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
+// k_nrcPrepWeights: EMA MLP weights [out][in] -> per-layer K-major core-matrix blobs:
+//   byte offset(layer, n, k) = layerBase + (k / 8) * (N * 16) + n * 16 + (k % 8) * 2
+// ---------------------------------------------------------------------------------------------
+__global__ void k_nrcPrepWeights(const __half* __restrict__ w, uint32_t numHiddenLayers, __half* __restrict__ blob) {
+    const uint32_t total = numHiddenLayers * kWidth * kWidth + kPaddedOutput * kWidth;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        uint32_t layer = i / (kWidth * kWidth), rem = i % (kWidth * kWidth), N = kWidth;
+        if (layer >= numHiddenLayers) {
+            layer = numHiddenLayers;
+            rem = i - numHiddenLayers * kWidth * kWidth;
+            N = kPaddedOutput;
+        }
+        const uint32_t n = rem / kWidth, k = rem % kWidth;
+        const uint32_t dst = layer * kWidth * kWidth + (k / 8) * (N * 8) + n * 8 + (k % 8);
+        blob[dst] = w[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_nrcInfer: fused encode + MLP on tcgen05. 128 threads, persistent over 128-query tiles.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kTileRows = 128;
+constexpr uint32_t kATileBytes = kTileRows * kWidth * 2; // 16 KB: 8 K-chunks x 128 rows x 16 B
+
+__global__ void __launch_bounds__(128) k_nrcInfer(NrcLevels levels, const __half* __restrict__ table,
+                                                  const uint4* __restrict__ ummaWeights, uint32_t numHiddenLayers,
+                                                  const float* __restrict__ input, float* __restrict__ output,
+                                                  uint32_t numData) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sA = smem;                                    // activation tile (A operand)
+    uint8_t* sW = smem + kATileBytes;                      // all weight blobs (B operands)
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmemBaseShared;
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t warp = tid >> 5;
+    const uint32_t weightBytes = (numHiddenLayers * kWidth * kWidth + kPaddedOutput * kWidth) * 2;
+
+    // resident weights: straight 16-byte copies of the pre-arranged blob
+    for (uint32_t i = tid; i < weightBytes / 16; i += blockDim.x)
+        reinterpret_cast<uint4*>(sW)[i] = __ldg(ummaWeights + i);
+    if (tid == 0) {
+        mbarInit(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) { // TMEM: 64 fp32 accumulator columns x 128 lanes
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smemU32(&tmemBaseShared)), "r"(64u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fenceProxyAsync();
+    tcFenceBefore();
+    __syncthreads();
+    tcFenceAfter();
+    const uint32_t tmemBase = tmemBaseShared;
+    const uint32_t tmemRow = tmemBase + ((warp * 32u) << 16); // this warp's 32 lanes
+
+    const uint32_t aAddr = smemU32(sA);
+    const uint32_t wAddr = smemU32(sW);
+    const uint32_t idescHidden = makeInstrDesc(128, kWidth);
+    const uint32_t idescOut = makeInstrDesc(128, kPaddedOutput);
+    uint32_t phase = 0;
+
+    const uint32_t numTiles = (numData + kTileRows - 1) / kTileRows;
+    for (uint32_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
+        const uint32_t row = tile * kTileRows + tid;
+        // ---- encode this thread's query into the A tile: chunk c at c * 2048 + row * 16
+        if (row < numData) {
+            nrcEncode(levels, table, input + (size_t)row * kInputDims, [&](uint32_t c, const __half* f) {
+                uint4 v;
+                v.x = (uint32_t)__half_as_ushort(f[0]) | ((uint32_t)__half_as_ushort(f[1]) << 16);
+                v.y = (uint32_t)__half_as_ushort(f[2]) | ((uint32_t)__half_as_ushort(f[3]) << 16);
+                v.z = (uint32_t)__half_as_ushort(f[4]) | ((uint32_t)__half_as_ushort(f[5]) << 16);
+                v.w = (uint32_t)__half_as_ushort(f[6]) | ((uint32_t)__half_as_ushort(f[7]) << 16);
+                *reinterpret_cast<uint4*>(sA + c * (kTileRows * 16) + tid * 16) = v;
+            });
+        }
+        else {
+#pragma unroll
+            for (uint32_t c = 0; c < 8; ++c)
+                *reinterpret_cast<uint4*>(sA + c * (kTileRows * 16) + tid * 16) = make_uint4(0, 0, 0, 0);
+        }
+
+        for (uint32_t layer = 0; layer <= numHiddenLayers; ++layer) {
+            const bool last = layer == numHiddenLayers;
+            const uint32_t N = last ? kPaddedOutput : kWidth;
+            // make the generic-proxy writes of sA visible to the tensor core, order against previous tcgen05.ld
+            fenceProxyAsync();
+            tcFenceBefore();
+            __syncthreads();
+            if (tid == 0) {
+                tcFenceAfter();
+                const uint32_t wLayer = wAddr + layer * kWidth * kWidth * 2;
+#pragma unroll
+                for (uint32_t k = 0; k < kWidth / 16; ++k) {
+                    // K step k covers chunks 2k, 2k+1: A chunk stride 2048 B, B chunk stride N*16 B
+                    const uint64_t aDesc = makeSmemDesc(aAddr + 2 * k * (kTileRows * 16), kTileRows * 16, 128);
+                    const uint64_t bDesc = makeSmemDesc(wLayer + 2 * k * (N * 16), N * 16, 128);
+                    umma(tmemBase, aDesc, bDesc, last ? idescOut : idescHidden, k > 0 ? 1u : 0u);
+                }
+                ummaCommit(&bar);
+            }
+            mbarWait(&bar, phase);
+            phase ^= 1;
+            tcFenceAfter();
+            if (!last) {
+                // epilogue: accumulator row -> ReLU -> fp16 -> back into the A tile
+#pragma unroll
+                for (uint32_t half_ = 0; half_ < 2; ++half_) {
+                    uint32_t r[32];
+                    tmemLoad32(tmemRow + half_ * 32, r);
+                    tmemWaitLd();
+#pragma unroll
+                    for (uint32_t c = 0; c < 4; ++c) {
+                        uint32_t packed[4];
+#pragma unroll
+                        for (uint32_t e = 0; e < 4; ++e) {
+                            const float a = fmaxf(__uint_as_float(r[c * 8 + 2 * e]), 0.0f);
+                            const float b = fmaxf(__uint_as_float(r[c * 8 + 2 * e + 1]), 0.0f);
+                            packed[e] = (uint32_t)__half_as_ushort(__float2half(a)) | ((uint32_t)__half_as_ushort(__float2half(b)) << 16);
+                        }
+                        *reinterpret_cast<uint4*>(sA + (half_ * 4 + c) * (kTileRows * 16) + tid * 16) =
+                            make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                    }
+                }
+            }
+            else {
+                uint32_t r[4];
+                tmemLoad4(tmemRow, r);
+                tmemWaitLd();
+                if (row < numData) {
+                    // trim_and_cast_from: half output -> float
+                    output[(size_t)row * kOutputDims + 0] = __half2float(__float2half(__uint_as_float(r[0])));
+                    output[(size_t)row * kOutputDims + 1] = __half2float(__float2half(__uint_as_float(r[1])));
+                    output[(size_t)row * kOutputDims + 2] = __half2float(__float2half(__uint_as_float(r[2])));
+                }
+            }
+        }
+        // all warps are done reading TMEM / the A tile before the next tile overwrites them
+        tcFenceBefore();
+        __syncthreads();
+        tcFenceAfter();
+    }
+
+    tcFenceBefore();
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmemBase), "r"(64u) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// training step on CUDA cores: block = 128 samples
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kRowStride = 66; // halves per activation row in shared memory (conflict-free rows)
+
+__global__ void __launch_bounds__(128) k_nrcTrain(NrcLevels levels, const __half* __restrict__ params, uint32_t numMatrixWeights,
+                                                  uint32_t numHiddenLayers, const float* __restrict__ input,
+                                                  const float* __restrict__ target, uint32_t numData,
+                                                  float* __restrict__ grads, float* __restrict__ lossOut) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t H = numHiddenLayers;
+    __half* sW = reinterpret_cast<__half*>(smem);                              // numMatrixWeights
+    __half* sAct = sW + numMatrixWeights;                                      // (H + 1) x 128 x kRowStride
+    __half* sD = sAct + (size_t)(H + 1) * 128 * kRowStride;                    // 128 x kRowStride
+    __shared__ float sLoss[4];
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t q = blockIdx.x * 128 + tid;
+    const bool valid = q < numData;
+    for (uint32_t i = tid; i < numMatrixWeights; i += 128)
+        sW[i] = params[i];
+    const __half* table = params + numMatrixWeights;
+
+    __half* x = sAct + (size_t)tid * kRowStride;
+    if (valid) {
+        nrcEncode(levels, table, input + (size_t)q * kInputDims, [&](uint32_t c, const __half* f) {
+#pragma unroll
+            for (uint32_t e = 0; e < 8; ++e)
+                x[c * 8 + e] = f[e];
+        });
+    }
+    else {
+        for (uint32_t e = 0; e < 64; ++e)
+            x[e] = __float2half(0.0f);
+    }
+    __syncthreads();
+
+    // forward
+    for (uint32_t layer = 0; layer < H; ++layer) {
+        const __half* W = sW + (size_t)layer * kWidth * kWidth;
+        const __half* in = sAct + ((size_t)layer * 128 + tid) * kRowStride;
+        __half* out = sAct + ((size_t)(layer + 1) * 128 + tid) * kRowStride;
+        for (uint32_t j = 0; j < kWidth; ++j) {
+            float acc = 0.0f;
+#pragma unroll 8
+            for (uint32_t i = 0; i < kWidth; ++i)
+                acc += __half2float(W[j * kWidth + i]) * __half2float(in[i]);
+            out[j] = __float2half(fmaxf(acc, 0.0f));
+        }
+    }
+    __half o[kPaddedOutput];
+    {
+        const __half* W = sW + (size_t)H * kWidth * kWidth;
+        const __half* in = sAct + ((size_t)H * 128 + tid) * kRowStride;
+        for (uint32_t j = 0; j < kPaddedOutput; ++j) {
+            float acc = 0.0f;
+#pragma unroll 8
+            for (uint32_t i = 0; i < kWidth; ++i)
+                acc += __half2float(W[j * kWidth + i]) * __half2float(in[i]);
+            o[j] = __float2half(acc);
+        }
+    }
+    // loss + dL/dy (relative_l2_luminance.h:41-88)
+    float localLoss = 0.0f;
+    __half* d = sD + (size_t)tid * kRowStride;
+    {
+        const uint32_t nTotal = numData * kOutputDims;
+        const float r = __half2float(o[0]), g = __half2float(o[1]), b = __half2float(o[2]);
+        const float luminance = 0.299f * r + 0.587f * g + 0.114f * b;
+        const float denom = luminance * luminance + 0.01f;
+        for (uint32_t k = 0; k < kPaddedOutput; ++k) {
+            float gr = 0.0f;
+            if (k < kOutputDims && valid) {
+                const float difference = __half2float(o[k]) - target[(size_t)q * kOutputDims + k];
+                localLoss += difference * difference / denom / nTotal;
+                gr = kLossScale * (2 * difference / denom) / nTotal;
+            }
+            d[k] = __float2half(gr);
+        }
+    }
+    __syncthreads();
+
+    // output layer: dW, then dL/d(hidden)
+    {
+        const uint32_t base = H * kWidth * kWidth;
+        const __half* hin = sAct + (size_t)H * 128 * kRowStride;
+        for (uint32_t p = tid; p < kPaddedOutput * kWidth; p += 128) {
+            const uint32_t j = p / kWidth, i = p % kWidth;
+            float acc = 0.0f;
+            for (uint32_t s = 0; s < 128; ++s)
+                acc += __half2float(sD[s * kRowStride + j]) * __half2float(hin[s * kRowStride + i]);
+            if (acc != 0.0f)
+                atomicAdd(grads + base + p, acc);
+        }
+        const __half* W = sW + (size_t)H * kWidth * kWidth;
+        const __half* myIn = hin + (size_t)tid * kRowStride;
+        __half dNext[64];
+        for (uint32_t i = 0; i < kWidth; ++i) {
+            float acc = 0.0f;
+#pragma unroll
+            for (uint32_t j = 0; j < kPaddedOutput; ++j)
+                acc += __half2float(W[j * kWidth + i]) * __half2float(d[j]);
+            dNext[i] = (H > 0 && !(__half2float(myIn[i]) > 0.0f)) ? __float2half(0.0f) : __float2half(acc);
+        }
+        __syncthreads();
+        for (uint32_t i = 0; i < kWidth; ++i)
+            d[i] = dNext[i];
+        __syncthreads();
+    }
+    for (int layer = (int)H - 1; layer >= 0; --layer) {
+        const uint32_t base = (uint32_t)layer * kWidth * kWidth;
+        const __half* hin = sAct + (size_t)layer * 128 * kRowStride;
+        for (uint32_t p = tid; p < kWidth * kWidth; p += 128) {
+            const uint32_t j = p / kWidth, i = p % kWidth;
+            float acc = 0.0f;
+            for (uint32_t s = 0; s < 128; ++s)
+                acc += __half2float(sD[s * kRowStride + j]) * __half2float(hin[s * kRowStride + i]);
+            if (acc != 0.0f)
+                atomicAdd(grads + base + p, acc);
+        }
+        const __half* W = sW + (size_t)layer * kWidth * kWidth;
+        const __half* myIn = hin + (size_t)tid * kRowStride;
+        __half dNext[64];
+        for (uint32_t i = 0; i < kWidth; ++i) {
+            float acc = 0.0f;
+            for (uint32_t j = 0; j < kWidth; ++j)
+                acc += __half2float(W[j * kWidth + i]) * __half2float(d[j]);
+            dNext[i] = (layer > 0 && !(__half2float(myIn[i]) > 0.0f)) ? __float2half(0.0f) : __float2half(acc);
+        }
+        __syncthreads();
+        for (uint32_t i = 0; i < kWidth; ++i)
+            d[i] = dNext[i];
+        __syncthreads();
+    }
+
+    // hash-grid backward (kernel_grid_backward, grid.h:306-429): scatter the first 32 input gradients
+    if (valid) {
+        float* gGrid = grads + numMatrixWeights;
+        const float* in = input + (size_t)q * kInputDims;
+        for (uint32_t l = 0; l < kLevels; ++l) {
+            const NrcLevel lv = levels.l[l];
+            const float g0 = __half2float(d[l * 2 + 0]), g1 = __half2float(d[l * 2 + 1]);
+            if (g0 == 0.0f && g1 == 0.0f)
+                continue;
+            float pos[3];
+            uint32_t posGrid[3];
+            for (uint32_t dd = 0; dd < 3; ++dd) {
+                pos[dd] = in[dd] * lv.scale + 0.5f;
+                const int tmp = (int)floorf(pos[dd]);
+                posGrid[dd] = (uint32_t)tmp;
+                pos[dd] -= (float)tmp;
+            }
+            for (uint32_t idx = 0; idx < 8; ++idx) {
+                float weight = 1;
+                uint32_t local[3];
+                for (uint32_t dd = 0; dd < 3; ++dd) {
+                    if ((idx & (1u << dd)) == 0) {
+                        weight *= 1 - pos[dd];
+                        local[dd] = posGrid[dd];
+                    }
+                    else {
+                        weight *= pos[dd];
+                        local[dd] = posGrid[dd] + 1;
+                    }
+                }
+                const uint32_t gi = lv.offset * 2 + nrcGridIndex(lv, local);
+                atomicAdd(gGrid + gi, weight * g0);
+                atomicAdd(gGrid + gi + 1, weight * g1);
+            }
+        }
+    }
+    // block loss
+    for (int off = 16; off > 0; off >>= 1)
+        localLoss += __shfl_xor_sync(0xFFFFFFFFu, localLoss, off);
+    if ((tid & 31) == 0)
+        sLoss[tid >> 5] = localLoss;
+    __syncthreads();
+    if (tid == 0)
+        atomicAdd(lossOut, sLoss[0] + sLoss[1] + sLoss[2] + sLoss[3]);
+}
+
+// adam_step (adam.h:49-115) + ema_step_half_precision (ema.h:61-77); clears the gradient for the next step
+__global__ void k_nrcAdamEma(uint32_t numParams, uint32_t numMatrixWeights, float learningRate, float emaDebiasOld,
+                             float emaDebiasNew, float* __restrict__ grads, float* __restrict__ master,
+                             __half* __restrict__ params, __half* __restrict__ paramsEma, float* __restrict__ m1,
+                             float* __restrict__ m2, uint32_t* __restrict__ steps) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= numParams)
+        return;
+    const float beta1 = 0.9f, beta2 = 0.99f, epsilon = 1e-15f, l2Reg = 1e-6f, emaDecay = 0.99f;
+    float gradient = __half2float(__float2half(grads[i])) / kLossScale;
+    grads[i] = 0.0f;
+    const bool matrix = i < numMatrixWeights;
+    if (matrix || gradient != 0) {
+        const float weightFp = master[i];
+        if (matrix)
+            gradient += l2Reg * weightFp;
+        const float gradientSq = gradient * gradient;
+        const float firstMoment = m1[i] = beta1 * m1[i] + (1 - beta1) * gradient;
+        const float secondMoment = m2[i] = beta2 * m2[i] + (1 - beta2) * gradientSq;
+        float lr = learningRate;
+        const uint32_t currentStep = ++steps[i];
+        lr *= sqrtf(1 - powf(beta2, (float)currentStep)) / (1 - powf(beta1, (float)currentStep));
+        const float effectiveLr = fminf(fmaxf(lr / (sqrtf(secondMoment) + epsilon), 0.0f), 3.402823466e+38f);
+        const float newWeight = weightFp - effectiveLr * firstMoment;
+        master[i] = newWeight;
+        params[i] = __float2half(newWeight);
+    }
+    const float filtered = (__half2float(paramsEma[i]) * emaDecay * emaDebiasOld + __half2float(params[i]) * (1 - emaDecay)) * emaDebiasNew;
+    paramsEma[i] = __float2half(filtered);
+}
+
+__global__ void k_nrcHalfToFloat(uint32_t n, const __half* __restrict__ src, float* __restrict__ dst) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        dst[i] = __half2float(src[i]);
+}
+
+static void setupLevels(gfx_nrc* n) { // grid.h:885-922
+    uint32_t offset = 0;
+    for (uint32_t l = 0; l < kLevels; ++l) {
+        const float scale = exp2f(l * log2f(2.0f)) * kBaseResolution - 1.0f;
+        const uint32_t resolution = (uint32_t)ceilf(scale) + 1;
+        const double dense = pow((double)resolution, 3.0);
+        uint32_t paramsInLevel = dense > (double)(0xFFFFFFFFu / 2) ? 0xFFFFFFFFu / 2 : resolution * resolution * resolution;
+        paramsInLevel = (paramsInLevel + 7u) / 8u * 8u;
+        paramsInLevel = paramsInLevel < (1u << kLog2HashmapSize) ? paramsInLevel : (1u << kLog2HashmapSize);
+        n->levels.l[l] = NrcLevel{ offset, paramsInLevel, scale, resolution };
+        offset += paramsInLevel;
+    }
+    n->numMatrixWeights = kWidth * kWidth * n->numHiddenLayers + kPaddedOutput * kWidth;
+    n->numParams = n->numMatrixWeights + offset * 2;
+}
+
+} // namespace gfx
+
+using namespace gfx;
+
+#define NRC_CUDA(nrc, call) GFX_CUDA((nrc)->ctx, call)
+
+extern "C" {
+
+int gfx_nrc_create(gfx_ctx* ctx, uint32_t numHiddenLayers, float learningRate, gfx_nrc** out) {
+    if (!ctx || !out)
+        return GFX_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (numHiddenLayers < 1 || numHiddenLayers > 8) {
+        ctx->setError("gfx_nrc_create: numHiddenLayers must be in 1..8");
+        return GFX_ERR_INVALID_ARGUMENT;
+    }
+    GFX_CUDA(ctx, cudaSetDevice(ctx->device));
+    gfx_nrc* n = new gfx_nrc();
+    n->ctx = ctx;
+    n->numHiddenLayers = numHiddenLayers;
+    n->learningRate = learningRate;
+    setupLevels(n);
+    const size_t P = n->numParams;
+    GFX_CUDA(ctx, cudaMalloc(&n->params, P * 2));
+    GFX_CUDA(ctx, cudaMalloc(&n->paramsEma, P * 2));
+    GFX_CUDA(ctx, cudaMalloc(&n->master, P * 4));
+    GFX_CUDA(ctx, cudaMalloc(&n->m1, P * 4));
+    GFX_CUDA(ctx, cudaMalloc(&n->m2, P * 4));
+    GFX_CUDA(ctx, cudaMalloc(&n->steps, P * 4));
+    GFX_CUDA(ctx, cudaMalloc(&n->grads, P * 4));
+    GFX_CUDA(ctx, cudaMalloc(&n->loss, 16));
+    GFX_CUDA(ctx, cudaMalloc(&n->ummaWeights, (size_t)n->numMatrixWeights * 2));
+    GFX_CUDA(ctx, cudaMemset(n->params, 0, P * 2));
+    GFX_CUDA(ctx, cudaMemset(n->paramsEma, 0, P * 2));
+    GFX_CUDA(ctx, cudaMemset(n->master, 0, P * 4));
+    GFX_CUDA(ctx, cudaMemset(n->m1, 0, P * 4));
+    GFX_CUDA(ctx, cudaMemset(n->m2, 0, P * 4));
+    GFX_CUDA(ctx, cudaMemset(n->steps, 0, P * 4));
+    GFX_CUDA(ctx, cudaMemset(n->grads, 0, P * 4));
+    *out = n;
+    return GFX_OK;
+}
+
+void gfx_nrc_destroy(gfx_nrc* n) {
+    if (!n)
+        return;
+    cudaFree(n->params); cudaFree(n->paramsEma); cudaFree(n->master); cudaFree(n->m1); cudaFree(n->m2);
+    cudaFree(n->steps); cudaFree(n->grads); cudaFree(n->loss); cudaFree(n->ummaWeights);
+    delete n;
+}
+
+uint32_t gfx_nrc_num_params(gfx_nrc* n) { return n ? n->numParams : 0; }
+
+int gfx_nrc_set_params(gfx_nrc* n, const void* hostHalfParams, size_t bytes) {
+    if (!n || !hostHalfParams || bytes != (size_t)n->numParams * 2)
+        return GFX_ERR_INVALID_ARGUMENT;
+    const size_t P = n->numParams;
+    NRC_CUDA(n, cudaMemcpy(n->params, hostHalfParams, bytes, cudaMemcpyHostToDevice));
+    NRC_CUDA(n, cudaMemcpy(n->paramsEma, n->params, bytes, cudaMemcpyDeviceToDevice));
+    k_nrcHalfToFloat<<<(n->numParams + 255) / 256, 256>>>(n->numParams, n->params, n->master);
+    n->ctx->launches++;
+    NRC_CUDA(n, cudaMemset(n->m1, 0, P * 4));
+    NRC_CUDA(n, cudaMemset(n->m2, 0, P * 4));
+    NRC_CUDA(n, cudaMemset(n->steps, 0, P * 4));
+    NRC_CUDA(n, cudaMemset(n->grads, 0, P * 4));
+    n->globalStep = 0;
+    n->ummaDirty = true;
+    NRC_CUDA(n, cudaDeviceSynchronize());
+    return GFX_OK;
+}
+
+int gfx_nrc_get_params(gfx_nrc* n, void* hostHalfParams, size_t bytes) {
+    if (!n || !hostHalfParams || bytes != (size_t)n->numParams * 2)
+        return GFX_ERR_INVALID_ARGUMENT;
+    NRC_CUDA(n, cudaMemcpy(hostHalfParams, n->paramsEma, bytes, cudaMemcpyDeviceToHost));
+    return GFX_OK;
+}
+
+int gfx_nrc_infer(gfx_nrc* n, void* stream, const float* inputData, float* predictionData, uint32_t numData) {
+    if (!n || (!inputData && numData) || (!predictionData && numData))
+        return GFX_ERR_INVALID_ARGUMENT;
+    if (numData & 0x7F) { // network_interface.cu:143 Assert((numData & 0x7F) == 0)
+        n->ctx->setError("gfx_nrc_infer: numData must be a multiple of 128");
+        return GFX_ERR_INVALID_ARGUMENT;
+    }
+    if (numData == 0)
+        return GFX_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n->ummaDirty) {
+        k_nrcPrepWeights<<<32, 256, 0, s>>>(n->paramsEma, n->numHiddenLayers, reinterpret_cast<__half*>(n->ummaWeights));
+        n->ctx->launches++;
+        n->ummaDirty = false;
+    }
+    const size_t smem = kATileBytes + (size_t)n->numMatrixWeights * 2;
+    NRC_CUDA(n, cudaFuncSetAttribute(k_nrcInfer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const uint32_t numTiles = numData / kTileRows;
+    const uint32_t grid = numTiles < (uint32_t)sms * 6 ? numTiles : (uint32_t)sms * 6;
+    k_nrcInfer<<<grid, 128, smem, s>>>(n->levels, n->paramsEma + n->numMatrixWeights, n->ummaWeights, n->numHiddenLayers,
+                                       inputData, predictionData, numData);
+    n->ctx->launches++;
+    NRC_CUDA(n, cudaGetLastError());
+    return GFX_OK;
+}
+
+int gfx_nrc_train(gfx_nrc* n, void* stream, const float* inputData, const float* targetData, uint32_t numData, float* lossOnHost) {
+    if (!n || !inputData || !targetData)
+        return GFX_ERR_INVALID_ARGUMENT;
+    if (numData & 0x7F) {
+        n->ctx->setError("gfx_nrc_train: numData must be a multiple of 128");
+        return GFX_ERR_INVALID_ARGUMENT;
+    }
+    if (numData == 0)
+        return GFX_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    NRC_CUDA(n, cudaMemsetAsync(n->loss, 0, 4, s));
+    const size_t smem = ((size_t)n->numMatrixWeights + (size_t)(n->numHiddenLayers + 2) * 128 * kRowStride) * 2;
+    NRC_CUDA(n, cudaFuncSetAttribute(k_nrcTrain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_nrcTrain<<<numData / 128, 128, smem, s>>>(n->levels, n->params, n->numMatrixWeights, n->numHiddenLayers, inputData,
+                                                targetData, numData, n->grads, n->loss);
+    n->ctx->launches++;
+    ++n->globalStep;
+    const float emaDecay = 0.99f;
+    const float emaDebiasOld = 1 - (float)pow((double)emaDecay, (double)(n->globalStep - 1));
+    const float emaDebiasNew = 1.0f / (1 - (float)pow((double)emaDecay, (double)n->globalStep));
+    k_nrcAdamEma<<<(n->numParams + 255) / 256, 256, 0, s>>>(n->numParams, n->numMatrixWeights, n->learningRate, emaDebiasOld,
+                                                            emaDebiasNew, n->grads, n->master, n->params, n->paramsEma,
+                                                            n->m1, n->m2, n->steps);
+    n->ctx->launches++;
+    n->ummaDirty = true;
+    NRC_CUDA(n, cudaGetLastError());
+    if (lossOnHost) { // network_interface.cu:155-156: optional blocking read-back
+        NRC_CUDA(n, cudaMemcpyAsync(lossOnHost, n->loss, 4, cudaMemcpyDeviceToHost, s));
+        NRC_CUDA(n, cudaStreamSynchronize(s));
+    }
+    return GFX_OK;
+}
+
+} // extern "C"

@@ -155,6 +155,58 @@ class Context:
         self._check(self.lib.gfx_svgf_launch(self.h, stream, C.byref(params), pass_id, stage), "gfx_svgf_launch")
 
 
+class NeuralRadianceCache:
+    """Mirror of the reference's NeuralRadianceCache facade (neural_radiance_caching/network_interface.h:14-28):
+    initialize -> __init__, infer, train, finalize -> close.  Device buffers are torch CUDA tensors or raw
+    device pointers (queries: float[numData, 14] row per query; predictions/targets: float[numData, 3])."""
+
+    def __init__(self, ctx: "Context", num_hidden_layers: int = 2, learning_rate: float = 1e-2):
+        self.ctx = ctx
+        h = C.c_void_p()
+        ctx._check(ctx.lib.gfx_nrc_create(ctx.h, num_hidden_layers, learning_rate, C.byref(h)), "gfx_nrc_create")
+        self.h = h
+        self.num_params = int(ctx.lib.gfx_nrc_num_params(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.gfx_nrc_destroy(self.h)
+            self.h = None
+
+    def set_params(self, params_f16: np.ndarray):
+        p = np.ascontiguousarray(params_f16, dtype=np.float16)
+        self.ctx._check(self.ctx.lib.gfx_nrc_set_params(self.h, p.ctypes.data, p.nbytes), "gfx_nrc_set_params")
+
+    def get_params(self) -> np.ndarray:
+        out = np.empty(self.num_params, dtype=np.float16)
+        self.ctx._check(self.ctx.lib.gfx_nrc_get_params(self.h, out.ctypes.data, out.nbytes), "gfx_nrc_get_params")
+        return out
+
+    @staticmethod
+    def _ptr(t):
+        return t if isinstance(t, int) else t.data_ptr()
+
+    def infer(self, queries, predictions, num_data: int, stream=None):
+        self.ctx._check(self.ctx.lib.gfx_nrc_infer(self.h, stream, self._ptr(queries), self._ptr(predictions), num_data),
+                        "gfx_nrc_infer")
+
+    def train(self, queries, targets, num_data: int, want_loss: bool = False, stream=None):
+        loss = C.c_float()
+        self.ctx._check(self.ctx.lib.gfx_nrc_train(self.h, stream, self._ptr(queries), self._ptr(targets), num_data,
+                                                   C.byref(loss) if want_loss else None), "gfx_nrc_train")
+        return loss.value if want_loss else None
+
+
+def random_nrc_params(num_params: int, num_matrix_weights: int, seed: int = 1337, grid_amplitude: float = 1e-4) -> np.ndarray:
+    """Xavier-uniform MLP matrices and U(-a, a) hash-grid entries (tcnn: gpu_matrix.h initialize_xavier_uniform,
+    grid.h:1267-1272), from a numpy stream (the reference's pcg32 stream is not reproduced)."""
+    rng = np.random.default_rng(seed)
+    p = np.empty(num_params, dtype=np.float32)
+    bound = np.sqrt(6.0 / (64 + 64))
+    p[:num_matrix_weights] = rng.uniform(-bound, bound, num_matrix_weights)
+    p[num_matrix_weights:] = rng.uniform(-grid_amplitude, grid_amplitude, num_params - num_matrix_weights)
+    return p.astype(np.float16)
+
+
 def restir_frame_passes(params, frame_index: int, num_spatial_passes: int = 1, temporal: bool = True,
                         unbiased: bool = False):
     """The launch list of one ReSTIR DI frame (restir_di_main.cpp:2321-2421).  Yields

@@ -79,6 +79,19 @@ def lib() -> C.CDLL:
         L.orc_svgf_buffer_ptr.restype = vp
         L.orc_svgf_buffer_ptr.argtypes = [vp, C.c_int, C.c_uint32, C.POINTER(C.c_size_t)]
         L.orc_svgf_pass.argtypes = [vp, C.POINTER(abi.GfxFrameParams), C.c_int, C.c_uint32, C.c_int]
+        L.orc_nrc_create.restype = vp
+        L.orc_nrc_create.argtypes = [C.c_uint32, C.c_float]
+        L.orc_nrc_destroy.argtypes = [vp]
+        L.orc_nrc_num_params.restype = C.c_uint32
+        L.orc_nrc_num_params.argtypes = [vp]
+        L.orc_nrc_num_matrix_weights.restype = C.c_uint32
+        L.orc_nrc_num_matrix_weights.argtypes = [vp]
+        L.orc_nrc_set_params.argtypes = [vp, vp]
+        L.orc_nrc_get_params.argtypes = [vp, vp, C.c_int]
+        L.orc_nrc_encode.argtypes = [vp, vp, C.c_uint32, vp, C.c_int]
+        L.orc_nrc_infer.argtypes = [vp, vp, vp, C.c_uint32]
+        L.orc_nrc_train.restype = C.c_float
+        L.orc_nrc_train.argtypes = [vp, vp, vp, C.c_uint32]
         _lib = L
     return _lib
 
@@ -202,6 +215,50 @@ class OracleSvgf:
         raw = (C.c_uint8 * nbytes.value).from_address(ptr)
         arr = np.frombuffer(raw, dtype=dtype).copy()
         return arr.reshape(self.H, self.W, comps) if comps > 1 else arr.reshape(self.H, self.W)
+
+
+class OracleNrc:
+    """CPU restatement of NeuralRadianceCache (network_interface.cu) — see oracle/nrc.cpp."""
+
+    def __init__(self, num_hidden_layers: int = 2, learning_rate: float = 1e-2):
+        self.h = lib().orc_nrc_create(num_hidden_layers, learning_rate)
+        self.num_params = lib().orc_nrc_num_params(self.h)
+        self.num_matrix_weights = lib().orc_nrc_num_matrix_weights(self.h)
+
+    def close(self):
+        if self.h:
+            lib().orc_nrc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def set_params(self, params_f16: np.ndarray):
+        p = np.ascontiguousarray(params_f16, dtype=np.float16)
+        assert p.shape[0] == self.num_params
+        lib().orc_nrc_set_params(self.h, p.ctypes.data)
+
+    def get_params(self, ema: bool = True) -> np.ndarray:
+        out = np.empty(self.num_params, dtype=np.float16)
+        lib().orc_nrc_get_params(self.h, out.ctypes.data, 1 if ema else 0)
+        return out
+
+    def encode(self, queries: np.ndarray, ema: bool = True) -> np.ndarray:
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        out = np.empty((q.shape[0], 64), dtype=np.float16)
+        lib().orc_nrc_encode(self.h, q.ctypes.data, q.shape[0], out.ctypes.data, 1 if ema else 0)
+        return out
+
+    def infer(self, queries: np.ndarray) -> np.ndarray:
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        out = np.empty((q.shape[0], 3), dtype=np.float32)
+        lib().orc_nrc_infer(self.h, q.ctypes.data, out.ctypes.data, q.shape[0])
+        return out
+
+    def train(self, queries: np.ndarray, targets: np.ndarray) -> float:
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        t = np.ascontiguousarray(targets, dtype=np.float32)
+        return float(lib().orc_nrc_train(self.h, q.ctypes.data, t.ctypes.data, q.shape[0]))
 
 
 def primary_rays(params, width: int, height: int) -> np.ndarray:
