@@ -88,7 +88,7 @@ GFX_D void nrcEncode(const NrcLevels &levels, const __half* __restrict__ table, 
     for (uint32_t d = 0; d < kInputDims; ++d)
         q[d] = in[d];
     __half feat[8];
-#pragma unroll 1
+#pragma unroll 1 // measured on B200: unrolling (more gathers in flight, 62 regs) is 6 % slower than 1 level at a time
     for (uint32_t l = 0; l < kLevels; ++l) {
         const NrcLevel lv = levels.l[l];
         const __half2* grid = reinterpret_cast<const __half2*>(table + (size_t)lv.offset * 2);

@@ -1,0 +1,151 @@
+"""Screen-strip sharding of a ReSTIR DI frame across the GPUs of one box.
+
+Rank r owns the contiguous rows [r*H/N, (r+1)*H/N).  Scene, BVH and light tables are replicated; every
+rank allocates full-frame buffers and addresses rows globally, so exchanged rows land at their own
+offsets.  Per frame:
+
+  1. G-buffer for the owned rows plus `halo` rows on each side (stateless, recomputed instead of sent)
+  2. initial(+temporal) RIS on the owned rows                                    - no communication
+  3. send/recv of the reservoir + reservoir-info halo rows with the neighbour ranks (the spatial pass
+     gathers within `spatialNeighborRadius` pixels, restir_di_main.cpp:2069; default 20)
+  4. spatial RIS pass(es) on the owned rows (halo exchange again after every pass that feeds another)
+  5. shading on the owned rows, exchange of the final reservoir halo (next frame's temporal reuse)
+  6. all-gather of the composited beauty strips: the one mandatory collective
+
+The driver is backend-agnostic: `GpuBackend` drives libgfxb200 with NCCL on the device pointers,
+`tests/test_multigpu_cpu.py` drives the CPU oracle through the same code with gloo, which is how the
+host-side sharding logic is verified bit-for-bit against a single-process render.
+"""
+from __future__ import annotations
+
+from typing import List
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import abi, engine
+
+
+class _DevicePtr:
+    """Zero-copy torch view of a raw device pointer through __cuda_array_interface__."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+class GpuBackend:
+    def __init__(self, ctx: engine.Context):
+        self.ctx = ctx
+        self._views = {}
+
+    def light_dist(self, frame_index: int):
+        self.ctx.build_light_distributions(frame_index % 2)
+
+    def gbuffer(self, params):
+        self.ctx.gbuffer(params)
+
+    def restir(self, params, pass_id: int):
+        self.ctx.restir(params, pass_id)
+
+    def tensor(self, buffer_id: int, index: int = 0) -> torch.Tensor:
+        key = (buffer_id, index)
+        if key not in self._views:
+            ptr, nbytes = self.ctx.device_ptr(buffer_id, index)
+            self._views[key] = torch.as_tensor(_DevicePtr(ptr, nbytes), device=f"cuda:{self.ctx.device}")
+        return self._views[key]
+
+    def new_tensor(self, numel: int) -> torch.Tensor:
+        return torch.empty(numel, dtype=torch.float32, device=f"cuda:{self.ctx.device}")
+
+
+class StripDriver:
+    def __init__(self, backend_or_ctx, params, width: int, height: int, rank: int, world: int, halo: int = 24):
+        self.backend = GpuBackend(backend_or_ctx) if isinstance(backend_or_ctx, engine.Context) else backend_or_ctx
+        self.params = params
+        self.W, self.H = width, height
+        self.rank, self.world = rank, world
+        self.halo = halo
+        rows = (height + world - 1) // world
+        self.y0 = min(height, rank * rows)
+        self.y1 = min(height, self.y0 + rows)
+        self.rows = rows
+        if rows * world != height:
+            raise ValueError(f"height {height} must be divisible by the number of ranks {world} (equal all-gather chunks)")
+        if params.enableJittering:
+            raise ValueError("strip sharding recomputes G-buffer halo rows; sub-pixel jitter would double-advance their RNG")
+        self.composited = self.backend.new_tensor(width * height * 4)
+
+    # -- helpers --------------------------------------------------------------------------------------
+    def _tile(self, lo: int, hi: int):
+        self.params.tileOriginY, self.params.tileRows = lo, hi - lo
+
+    def _row_slices(self, buffer_id: int, index: int, lo: int, hi: int) -> List[torch.Tensor]:
+        """Views of rows [lo, hi) of every plane of a frame buffer."""
+        _, comps, planes = abi.BUFFER_LAYOUT[buffer_id]
+        words = comps * (2 if buffer_id == abi.BUF_RNG else 1)
+        t = self.backend.tensor(buffer_id, index)
+        plane = self.W * self.H * words
+        return [t[p * plane + lo * self.W * words: p * plane + hi * self.W * words] for p in range(planes)]
+
+    def exchange_halo(self, buffers):
+        """Neighbour exchange of `halo` seam rows for the given [(buffer_id, index)] list."""
+        if self.world == 1:
+            return
+        ops = []
+        for buffer_id, index in buffers:
+            if self.rank > 0:  # my top rows go up, their bottom rows come down
+                up = self.rank - 1
+                for s in self._row_slices(buffer_id, index, self.y0, min(self.y0 + self.halo, self.y1)):
+                    ops.append(dist.P2POp(dist.isend, s, up))
+                for s in self._row_slices(buffer_id, index, max(self.y0 - self.halo, 0), self.y0):
+                    ops.append(dist.P2POp(dist.irecv, s, up))
+            if self.rank < self.world - 1:
+                down = self.rank + 1
+                for s in self._row_slices(buffer_id, index, max(self.y1 - self.halo, self.y0), self.y1):
+                    ops.append(dist.P2POp(dist.isend, s, down))
+                for s in self._row_slices(buffer_id, index, self.y1, min(self.y1 + self.halo, self.H)):
+                    ops.append(dist.P2POp(dist.irecv, s, down))
+        if ops:
+            for work in dist.batch_isend_irecv(ops):
+                work.wait()
+
+    # -- one frame ------------------------------------------------------------------------------------
+    def render_frame(self, frame_index: int, num_spatial_passes: int = 1, unbiased: bool = False):
+        p = self.params
+        b = self.backend
+        b.light_dist(frame_index)
+        lo_h, hi_h = max(0, self.y0 - self.halo), min(self.H, self.y1 + self.halo)
+        spatial_seen = 0
+        # the generator mutates `p` between launches exactly like the reference host mutates plp
+        for kind, pass_id in engine.restir_frame_passes(p, frame_index, num_spatial_passes, True, unbiased):
+            if kind == "gbuffer":
+                self._tile(lo_h, hi_h)
+                b.gbuffer(p)
+            elif pass_id in (abi.RESTIR_INITIAL_RIS, abi.RESTIR_INITIAL_AND_TEMPORAL_BIASED,
+                             abi.RESTIR_INITIAL_AND_TEMPORAL_UNBIASED):
+                self._tile(self.y0, self.y1)
+                b.restir(p, pass_id)
+                if num_spatial_passes > 0:
+                    cur = p.currentReservoirIndex
+                    self.exchange_halo([(abi.BUF_RESERVOIR, cur), (abi.BUF_RESERVOIR_INFO, cur)])
+            elif pass_id in (abi.RESTIR_SPATIAL_BIASED, abi.RESTIR_SPATIAL_UNBIASED):
+                self._tile(self.y0, self.y1)
+                b.restir(p, pass_id)
+                spatial_seen += 1
+                dst = (p.currentReservoirIndex + 1) % 2
+                if spatial_seen < num_spatial_passes:
+                    self.exchange_halo([(abi.BUF_RESERVOIR, dst), (abi.BUF_RESERVOIR_INFO, dst)])
+            else:  # shading
+                self._tile(self.y0, self.y1)
+                b.restir(p, pass_id)
+                # final reservoirs of the seam rows: next frame's temporal reuse may look across the seam
+                cur = p.currentReservoirIndex
+                self.exchange_halo([(abi.BUF_RESERVOIR, cur), (abi.BUF_RESERVOIR_INFO, cur)])
+        self._tile(0, 0)
+        if self.world > 1:
+            strip = self._row_slices(abi.BUF_BEAUTY_ACCUM, 0, self.y0, self.y1)[0]
+            dist.all_gather_into_tensor(self.composited, strip.contiguous())
+        else:
+            self.composited.copy_(self.backend.tensor(abi.BUF_BEAUTY_ACCUM, 0))
+        p.tileOriginY, p.tileRows = 0, 0
