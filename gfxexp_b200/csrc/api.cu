@@ -14,7 +14,7 @@ void SceneState::release() {
     cudaFree(instanceMeshSlots); cudaFree(geomToInstMesh); cudaFree(geomTriOffsets);
     cudaFree(primWeights); cudaFree(primCdf); cudaFree(geomWeights); cudaFree(geomCdf);
     cudaFree(instWeights); cudaFree(instCdf); cudaFree(instIntegral);
-    cudaFree(primProb); cudaFree(geomProb); cudaFree(instProb); cudaFree(lightTris); cudaFree(lightTriBase); cudaFree(emissiveGeoms);
+    cudaFree(primProb); cudaFree(geomProb); cudaFree(instProb); cudaFree(lightTris); cudaFree(lightTriBase); cudaFree(emissiveGeoms); cudaFree(instGuide); cudaFree(primGuide);
     *this = SceneState();
 }
 void BvhState::release() {
@@ -107,6 +107,8 @@ DevScene gfx_ctx::devScene() const {
     d.instProb = scene.instProb;
     d.lightTris = scene.lightTris;
     d.lightTriBase = scene.lightTriBase;
+    d.instGuide = scene.instGuide;
+    d.primGuide = scene.primGuide;
     d.numInstances = scene.numInstances;
     d.rayCounter = frame.stats;
     d.bvh.nodes = reinterpret_cast<const uint4*>(bvh.nodes);
@@ -309,6 +311,9 @@ int gfx_scene_upload(gfx_ctx* ctx, const GfxSceneDesc* sd) {
     GFX_CUDA(ctx, cudaMalloc(&S.lightTris, (size_t)(numLightTris ? numLightTris : 1) * 96));
     GFX_CUDA(ctx, upload(&S.lightTriBase, lightTriBase.data(), lightTriBase.size() * 4));
     GFX_CUDA(ctx, upload(&S.emissiveGeoms, emissiveGeoms.data(), emissiveGeoms.size() * 4));
+    GFX_CUDA(ctx, cudaMalloc(&S.instGuide, (kInstGuideSize + 1) * 4));
+    GFX_CUDA(ctx, cudaMemset(S.instGuide, 0, (kInstGuideSize + 1) * 4));
+    GFX_CUDA(ctx, cudaMalloc(&S.primGuide, (size_t)(sd->numMeshes ? sd->numMeshes : 1) * (kPrimGuideSize + 1) * 4));
     S.numEmissiveGeoms = (uint32_t)emissiveGeoms.size();
     S.numLightTris = numLightTris;
     GFX_CUDA(ctx, cudaMemset(S.instIntegral, 0, 16));

@@ -224,47 +224,66 @@ __global__ void k_collapse(CollapseArgs a) {
     const uint32_t root = item.y;
 
     uint32_t ch[8];
-    float area[8]; // < 0: not expandable (leaf-sized)
+    float area[8];
+    bool leafSized[8]; // child becomes a leaf of this wide node (<= maxLeaf triangles)
     int nc = 0;
     auto pushChild = [&](uint32_t ref) {
         const uint32_t bi = refBoxIndex(a, ref);
         const float4 lo = a.boxLo[bi], hi = a.boxHi[bi];
         const float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
-        const bool leafSized = refCount(a, ref) <= a.maxLeaf;
         ch[nc] = ref;
-        area[nc] = leafSized ? -1.0f : (dx * dy + dy * dz + dz * dx);
+        leafSized[nc] = refCount(a, ref) <= a.maxLeaf;
+        area[nc] = dx * dy + dy * dz + dz * dx;
         ++nc;
     };
-    if (refCount(a, root) <= a.maxLeaf) {
+    auto openChild = [&](int k) { // replace child k in place by its left half, append the right half
+        const uint32_t ref = ch[k];
+        const int saved = nc;
+        nc = k;
+        pushChild(a.childL[ref]);
+        nc = saved;
+        pushChild(a.childR[ref]);
+    };
+    if (refCount(a, root) <= a.maxLeaf && (root & 0x80000000u)) {
         pushChild(root);
     }
     else {
         pushChild(a.childL[root]);
         pushChild(a.childR[root]);
+        // phase 1: open the largest-area subtree that is too big for a leaf (the reference's task loop
+        // picks the largest-surface-area splittable child the same way, bvh_builder.cpp:785-800)
         while (nc < 8) {
             int best = -1;
             float bestArea = -1.0f;
             for (int k = 0; k < nc; ++k)
-                if (area[k] >= 0.0f && area[k] > bestArea) {
+                if (!leafSized[k] && area[k] > bestArea) {
                     bestArea = area[k];
                     best = k;
                 }
             if (best < 0)
                 break;
-            const uint32_t ref = ch[best];
-            // replace in place by the left child, append the right child
-            const int saved = nc;
-            nc = best;
-            pushChild(a.childL[ref]);
-            nc = saved;
-            pushChild(a.childR[ref]);
+            openChild(best);
+        }
+        // phase 2: spare slots are used to split multi-triangle leaves (tighter boxes, fewer triangle
+        // tests per ray, fuller nodes)
+        while (nc < 8) {
+            int best = -1;
+            float bestArea = -1.0f;
+            for (int k = 0; k < nc; ++k)
+                if (leafSized[k] && !(ch[k] & 0x80000000u) && area[k] > bestArea) {
+                    bestArea = area[k];
+                    best = k;
+                }
+            if (best < 0)
+                break;
+            openChild(best);
         }
     }
 
     // classify + allocate
     uint32_t numInt = 0, numLeafPrims = 0;
     for (int k = 0; k < nc; ++k) {
-        if (area[k] >= 0.0f) ++numInt;
+        if (!leafSized[k]) ++numInt;
         else numLeafPrims += refCount(a, ch[k]);
     }
     const uint32_t nodeBase = numInt ? atomicAdd(a.counters + 0, numInt) : 0xFFFFFFFFu;
@@ -320,7 +339,7 @@ __global__ void k_collapse(CollapseArgs a) {
             qmin[d][w] |= (uint32_t)q0 << sh;
             qmax[d][w] |= (uint32_t)q1 << sh;
         }
-        if (area[k] >= 0.0f) {
+        if (!leafSized[k]) {
             internalMask |= 1u << k;
             a.queueOut[queueBase + nthInt] = make_uint2(nodeBase + nthInt, ref);
             ++nthInt;

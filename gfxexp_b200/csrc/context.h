@@ -28,6 +28,8 @@ struct SceneState {
     float* geomProb = nullptr;
     float* instProb = nullptr;
     float4* lightTris = nullptr;
+    uint32_t* instGuide = nullptr;
+    uint32_t* primGuide = nullptr;
     uint32_t* lightTriBase = nullptr;      // per flattened geometry
     uint32_t* emissiveGeoms = nullptr;     // list of flattened geometry indices with an emissive material
     uint32_t numEmissiveGeoms = 0, numLightTris = 0;

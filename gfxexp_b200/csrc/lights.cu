@@ -24,6 +24,32 @@
 
 namespace gfx {
 
+// DiscreteDistribution1DTemplate::sample's stepping search (common_shared.h:226-232): last index with cdf <= u
+GFX_D uint32_t steppingSearch(const float* cdf, uint32_t numValues, float u) {
+    int idx = 0;
+    uint32_t p2 = numValues <= 1 ? numValues : 1u << (32 - __clz(numValues - 1));
+    for (int d = (int)(p2 >> 1); d >= 1; d >>= 1) {
+        if (idx + d >= (int)numValues)
+            continue;
+        if (cdf[idx + d] <= u)
+            idx += d;
+    }
+    return (uint32_t)idx;
+}
+
+// per-mesh guide table for the primitive-level search
+__global__ void k_primGuide(DevScene scene, uint32_t numMeshes) {
+    const uint32_t mesh = blockIdx.x;
+    if (mesh >= numMeshes)
+        return;
+    const DevMesh m = scene.meshes[mesh];
+    uint32_t* guide = const_cast<uint32_t*>(scene.primGuide) + (size_t)mesh * (kPrimGuideSize + 1);
+    for (uint32_t b = threadIdx.x; b <= kPrimGuideSize; b += blockDim.x) {
+        const float u = ((float)b / (float)kPrimGuideSize) * m.primIntegral;
+        guide[b] = m.numTriangles ? steppingSearch(scene.primCdf + m.triBase, m.numTriangles, u) : 0u;
+    }
+}
+
 // computeTriangleImportance (compute_light_probs.cu:22-46)
 __global__ void k_triangleImportance(DevScene scene, uint32_t numMeshes) {
     const uint32_t mesh = blockIdx.y;
@@ -170,6 +196,10 @@ __global__ void __launch_bounds__(1024) k_instanceDist(DevScene scene, uint32_t 
         const_cast<float*>(scene.instCdf)[i] = sc[i];
         const_cast<float*>(scene.instProb)[i] = sw[i] / integral;
     }
+    for (uint32_t b = threadIdx.x; b <= kInstGuideSize; b += blockDim.x) {
+        const float u = ((float)b / (float)kInstGuideSize) * integral;
+        const_cast<uint32_t*>(scene.instGuide)[b] = steppingSearch(sc, numInstances, u);
+    }
 }
 
 int buildLightDistributions(gfx_ctx* ctx, cudaStream_t stream, uint32_t /*bufferIndex*/) {
@@ -180,6 +210,7 @@ int buildLightDistributions(gfx_ctx* ctx, cudaStream_t stream, uint32_t /*buffer
             k_triangleImportance<<<dim3(64, S.numMeshes), 128, 0, stream>>>(dev, S.numMeshes); ctx->launches++;
             k_scanMeshes<<<(S.numMeshes + 31) / 32, 32, 0, stream>>>(dev, S.numMeshes); ctx->launches++;
             k_primProb<<<dim3(64, S.numMeshes), 128, 0, stream>>>(dev, S.numMeshes); ctx->launches++;
+            k_primGuide<<<S.numMeshes, 128, 0, stream>>>(dev, S.numMeshes); ctx->launches++;
         }
         if (S.numInstances) {
             k_scanInstanceGeoms<<<(S.numInstances + 63) / 64, 64, 0, stream>>>(dev, S.numInstances); ctx->launches++;

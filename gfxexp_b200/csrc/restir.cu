@@ -58,6 +58,16 @@ GFX_D uint32_t searchCdf(const float* __restrict__ cdf, uint32_t numValues, floa
     }
     return (uint32_t)idx;
 }
+// the same search seeded by a guide table (scene.cuh): exact, 1-3 loads instead of log2(n)
+GFX_D uint32_t guidedSearchCdf(const float* __restrict__ cdf, const uint32_t* __restrict__ guide, uint32_t guideSize,
+                               float u01, float u) {
+    const uint32_t b = min(dm_f2uint(u01 * (float)guideSize), guideSize - 1);
+    uint32_t idx = __ldg(guide + b);
+    const uint32_t hi = __ldg(guide + b + 1);
+    while (idx < hi && __ldg(cdf + idx + 1) <= u)
+        ++idx;
+    return idx;
+}
 GFX_D float remapCdf(const float* __restrict__ cdf, uint32_t numValues, float integral, uint32_t idx, float u) {
     // common_shared.h:235-241
     const float lCDF = __ldg(cdf + idx);
@@ -77,7 +87,7 @@ GFX_D void sampleLight(const DevScene &s, float ul, float u0, float u1, LightSam
     // instance
     const float instIntegral = __ldg(s.instIntegral);
     float u = ul * instIntegral;
-    const uint32_t instSlot = searchCdf(s.instCdf, s.numInstances, u);
+    const uint32_t instSlot = guidedSearchCdf(s.instCdf, s.instGuide, kInstGuideSize, ul, u);
     const float uGeomInst = remapCdf(s.instCdf, s.numInstances, instIntegral, instSlot, u);
     const float instProb = __ldg(s.instProb + instSlot);
     lightProb *= instProb;
@@ -105,7 +115,8 @@ GFX_D void sampleLight(const DevScene &s, float ul, float u0, float u1, LightSam
     const DevMesh* mesh = s.meshes + geomInstSlot;
     const uint32_t triBase = mesh->triBase, numTriangles = mesh->numTriangles;
     u = uPrim * mesh->primIntegral;
-    const uint32_t primIndex = searchCdf(s.primCdf + triBase, numTriangles, u);
+    const uint32_t primIndex = guidedSearchCdf(s.primCdf + triBase, s.primGuide + (size_t)geomInstSlot * (kPrimGuideSize + 1),
+                                               kPrimGuideSize, uPrim, u);
     const float primProb = __ldg(s.primProb + triBase + primIndex);
     lightProb *= primProb;
 
@@ -271,6 +282,13 @@ __global__ void __launch_bounds__(64) k_initialAndTemporalRIS(DevScene s, DevFra
 
     float selectedTargetDensity = 0.0f;
     const uint32_t numCandidates = 1u << p.log2NumCandidateSamples;
+    // Streaming RIS (:66-123).  Reservoir::update (restir_di_shared.h:118-125) is spelled out: instead of
+    // copying the 10-float LightSample on every acceptance, the three primary sample values that
+    // generated it are kept and the winner is re-generated once after the loop (sampleLight is a pure
+    // function of (ul, u0, u1)), which is bit-identical and frees registers in the hot loop.
+    float selUl = 0.0f, selU0 = 0.0f, selU1 = 0.0f;
+    bool hasSelection = false;
+    float sumWeights = 0.0f;
     for (uint32_t i = 0; i < numCandidates; ++i) {
         const float ul = rng.getFloat0cTo1o();
         const float probToSampleCurLightType = 1.0f;
@@ -283,9 +301,22 @@ __global__ void __launch_bounds__(64) k_initialAndTemporalRIS(DevScene s, DevFra
         probDensity *= probToSampleCurLightType;
         const float targetDensity = convertToWeight(cont);
         const float weight = targetDensity / probDensity;
-        if (reservoir.update(lightSample, weight, rng.getFloat0cTo1o()))
+        const float u = rng.getFloat0cTo1o();
+        sumWeights += weight;
+        if (u < weight / sumWeights) {
+            selUl = ul;
+            selU0 = u0;
+            selU1 = u1;
+            hasSelection = true;
             selectedTargetDensity = targetDensity;
+        }
     }
+    if (hasSelection) {
+        float unusedDensity;
+        sampleLight(s, selUl, selU0, selU1, &reservoir.sample, &unusedDensity);
+    }
+    reservoir.sumWeights = sumWeights;
+    reservoir.streamLength = numCandidates;
 
     float recPDFEstimate = reservoir.sumWeights / (selectedTargetDensity * reservoir.streamLength);
     if (!isfinite(recPDFEstimate)) {

@@ -17,6 +17,9 @@
 
 namespace gfx {
 
+constexpr uint32_t kInstGuideSize = 2048;
+constexpr uint32_t kPrimGuideSize = 128;
+
 struct DevMesh {
     uint32_t vertexBase;   // into vertices (units of vertices)
     uint32_t triBase;      // into triangles / primWeights / primCdf
@@ -72,6 +75,11 @@ struct DevScene {
     // sampleLight (restir_di_shared.h:417-425,485-511), so reading them is bit-identical to recomputing.
     const float4* lightTris;
     const uint32_t* lightTriBase;
+    // guide tables for the CDF searches: guide[b] = search(cdf, fl(b / G * integral)), b = 0..G, so the
+    // answer for u = fl(ul * integral) with ul in [b/G, (b+1)/G) lies in [guide[b], guide[b+1]]
+    // (rounding is monotone) and a short scan finishes the exact search.
+    const uint32_t* instGuide;       // kInstGuideSize + 1 entries
+    const uint32_t* primGuide;       // per mesh: kPrimGuideSize + 1 entries
     uint32_t numInstances;
     unsigned long long* rayCounter;  // frame statistics: rays traced (primary + visibility)
     DevBvh bvh;

@@ -7,7 +7,11 @@
 //   normalize(v) = v * (1 / sqrt(dot(v,v)))  (operator/=(F) multiplies by the reciprocal,
 //                  basic_types.h:2564-2570, 2590-2593)
 //   Matrix * v   = row-dot products                     (basic_types.h:4264-4271, 4760-4768)
-// Build with -ffp-contract=off (no FMA contraction) — see oracle/Makefile.
+// dot / cross / length / matrix-vector products are spelled with EXPLICIT fused multiply-adds in a fixed
+// association order (z-term outermost); csrc/vec.cuh spells them identically with fmaf, so host and device
+// round the same way.  (The reference itself is built with nvcc's default FMA contraction + fast-math, so
+// no particular contraction pattern is canonical.)  Everything else is built with -ffp-contract=off
+// (no implicit contraction) — see oracle/Makefile.
 #pragma once
 #include <cstdint>
 #include <cmath>
@@ -49,11 +53,11 @@ inline float2 operator-(const float2 &a, const float2 &b) { return float2(a.x - 
 inline float2 operator*(float s, const float2 &a) { return float2(s * a.x, s * a.y); }
 inline float2 operator*(const float2 &a, const float2 &b) { return float2(a.x * b.x, a.y * b.y); }
 
-inline float dot(const float3 &a, const float3 &b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline float dot(const float3 &a, const float3 &b) { return std::fmaf(a.z, b.z, std::fmaf(a.y, b.y, a.x * b.x)); }
 inline float3 cross(const float3 &a, const float3 &b) {
-    return float3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+    return float3(std::fmaf(a.y, b.z, -(a.z * b.y)), std::fmaf(a.z, b.x, -(a.x * b.z)), std::fmaf(a.x, b.y, -(a.y * b.x)));
 }
-inline float sqLength(const float3 &v) { return v.x * v.x + v.y * v.y + v.z * v.z; }
+inline float sqLength(const float3 &v) { return std::fmaf(v.z, v.z, std::fmaf(v.y, v.y, v.x * v.x)); }
 inline float length(const float3 &v) { return std::sqrt(sqLength(v)); }
 inline float3 normalize(const float3 &v) { const float l = length(v); return v / l; }
 inline float3 min3(const float3 &a, const float3 &b) {
@@ -82,24 +86,24 @@ struct Affine {
     float m[12];
     float3 point(const float3 &p) const {
         return float3(
-            m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3] * 1.0f,
-            m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7] * 1.0f,
-            m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11] * 1.0f);
+            std::fmaf(m[2], p.z, std::fmaf(m[1], p.y, m[0] * p.x)) + m[3],
+            std::fmaf(m[6], p.z, std::fmaf(m[5], p.y, m[4] * p.x)) + m[7],
+            std::fmaf(m[10], p.z, std::fmaf(m[9], p.y, m[8] * p.x)) + m[11]);
     }
     float3 vector(const float3 &v) const {
         return float3(
-            m[0] * v.x + m[1] * v.y + m[2] * v.z,
-            m[4] * v.x + m[5] * v.y + m[6] * v.z,
-            m[8] * v.x + m[9] * v.y + m[10] * v.z);
+            std::fmaf(m[2], v.z, std::fmaf(m[1], v.y, m[0] * v.x)),
+            std::fmaf(m[6], v.z, std::fmaf(m[5], v.y, m[4] * v.x)),
+            std::fmaf(m[10], v.z, std::fmaf(m[9], v.y, m[8] * v.x)));
     }
 };
 struct Mat3 { // row-major
     float m[9];
     float3 mul(const float3 &v) const {
         return float3(
-            m[0] * v.x + m[1] * v.y + m[2] * v.z,
-            m[3] * v.x + m[4] * v.y + m[5] * v.z,
-            m[6] * v.x + m[7] * v.y + m[8] * v.z);
+            std::fmaf(m[2], v.z, std::fmaf(m[1], v.y, m[0] * v.x)),
+            std::fmaf(m[5], v.z, std::fmaf(m[4], v.y, m[3] * v.x)),
+            std::fmaf(m[8], v.z, std::fmaf(m[7], v.y, m[6] * v.x)));
     }
 };
 
