@@ -29,6 +29,7 @@ void FrameState::release() {
         cudaFree(reservoir[i]); cudaFree(reservoirInfo[i]);
         cudaFree(svgfLighting[i]); cudaFree(svgfMoments[i]); cudaFree(svgfFinal[i]); cudaFree(svgfDepth[i]);
     }
+    cudaFree(rayQueue); cudaFree(rayPixel); cudaFree(rayCounters); cudaFree(visibility);
     cudaFree(stats); cudaFree(rng); cudaFree(beauty); cudaFree(albedo); cudaFree(normal); cudaFree(neighborDeltas);
     cudaFree(svgfPrevLighting); cudaFree(svgfAlbedo); cudaFree(svgfPrevScreenPos);
     *this = FrameState();
@@ -136,6 +137,10 @@ DevFrame gfx_ctx::devFrame() const {
     d.normal = frame.normal;
     d.neighborDeltas = frame.neighborDeltas;
     d.stats = frame.stats;
+    d.rayQueue = frame.rayQueue;
+    d.rayPixel = frame.rayPixel;
+    d.rayCounters = frame.rayCounters;
+    d.visibility = frame.visibility;
     return d;
 }
 
@@ -164,6 +169,10 @@ int gfx_ctx_create(int device, gfx_ctx** out) {
         return GFX_ERR_OUT_OF_MEMORY;
     }
     cudaMemset(ctx->bvh.overflowFlag, 0, 4);
+    if (cudaMalloc(&ctx->traceFetchCounter, 4) != cudaSuccess) {
+        delete ctx;
+        return GFX_ERR_OUT_OF_MEMORY;
+    }
     *out = ctx;
     return GFX_OK;
 }
@@ -176,6 +185,7 @@ void gfx_ctx_destroy(gfx_ctx* ctx) {
     ctx->frame.release();
     ctx->bvh.release();
     cudaFree(ctx->bvh.overflowFlag);
+    cudaFree(ctx->traceFetchCounter);
     ctx->scene.release();
     delete ctx;
 }
@@ -512,6 +522,12 @@ int gfx_frame_create(gfx_ctx* ctx, uint32_t W, uint32_t H) {
     GFX_CUDA(ctx, cudaMalloc(&F.normal, n * 16));
     GFX_CUDA(ctx, cudaMalloc(&F.neighborDeltas, 1024 * 8));
     GFX_CUDA(ctx, cudaMalloc(&F.stats, 4 * 8));
+    GFX_CUDA(ctx, cudaMalloc(&F.rayQueue, n * 32));
+    GFX_CUDA(ctx, cudaMalloc(&F.rayPixel, n * 4));
+    GFX_CUDA(ctx, cudaMalloc(&F.rayCounters, 16));
+    GFX_CUDA(ctx, cudaMemset(F.rayCounters, 0, 16));
+    GFX_CUDA(ctx, cudaMalloc(&F.visibility, n));
+    GFX_CUDA(ctx, cudaMemset(F.visibility, 0, n));
     GFX_CUDA(ctx, cudaMemset(F.stats, 0, 4 * 8));
     GFX_CUDA(ctx, cudaMemset(F.rng, 0, n * 8));
     GFX_CUDA(ctx, cudaMemset(F.beauty, 0, n * 16));

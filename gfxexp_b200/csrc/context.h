@@ -69,6 +69,11 @@ struct FrameState {
     float4* normal = nullptr;
     float2* neighborDeltas = nullptr;
     unsigned long long* stats = nullptr; // 4 counters
+    // wavefront visibility queue (SoA ray records compacted with warp ballots, traced by persistent threads)
+    float4* rayQueue = nullptr;      // 2 x float4 per ray: (org, tmin) (dir, tmax)
+    uint32_t* rayPixel = nullptr;    // pixel that asked for the ray
+    uint32_t* rayCounters = nullptr; // [0] rays queued, [1] rays fetched
+    uint8_t* visibility = nullptr;   // per pixel: 1 = unoccluded
     // SVGF state
     float4* svgfLighting[2] = { nullptr, nullptr };  // lighting rgb + variance, ping-pong
     float4* svgfMoments[2] = { nullptr, nullptr };   // first/second luminance moments + history length
@@ -87,6 +92,7 @@ struct gfx_ctx {
     int device = 0;
     std::string lastError;
     uint64_t launches = 0;
+    uint32_t* traceFetchCounter = nullptr; // device counter of the wavefront trace kernel
     gfx::SceneState scene;
     gfx::BvhState bvh;
     gfx::FrameState frame;
@@ -110,6 +116,8 @@ struct gfx_ctx {
 namespace gfx {
 int buildBvh(gfx_ctx* ctx, cudaStream_t stream, uint32_t flags);
 int traceRays(gfx_ctx* ctx, cudaStream_t stream, const GfxRay* dRays, uint32_t numRays, GfxHitObject* dHits, int mode);
+int resetVisibilityQueue(gfx_ctx* ctx, cudaStream_t stream);
+int traceVisibilityQueue(gfx_ctx* ctx, cudaStream_t stream);
 int buildLightDistributions(gfx_ctx* ctx, cudaStream_t stream, uint32_t bufferIndex);
 int launchGBuffer(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* p);
 int launchReSTIR(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* p, int pass);

@@ -243,19 +243,62 @@ GFX_D BSDF setupBsdf(const DevScene &s, uint32_t matSlot) {
 }
 
 // ---------------------------------------------------------------------------------------------
-template <bool withTemporalRIS, bool useUnbiasedEstimator>
-__global__ void __launch_bounds__(64) k_initialAndTemporalRIS(DevScene s, DevFrame f, DevFrameParams p) {
+// A visibility ray requested by a pixel (wavefront mode): appended to the frame's queue with one atomic per
+// warp (ballot compaction), traced by trace.cu's persistent kernel, answered in f.visibility[pixel].
+struct RayRequest {
+    f3 org, dir;
+    float tmax;
+    uint32_t pixel;
+};
+GFX_D void enqueueRay(const DevFrame &f, unsigned long long* rayCounter, bool want, const RayRequest &r) {
+    const uint32_t lane = (threadIdx.x + threadIdx.y * blockDim.x) & 31u;
+    const uint32_t mask = __ballot_sync(0xFFFFFFFFu, want);
+    if (mask == 0)
+        return;
+    const int leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if ((int)lane == leader) {
+        base = atomicAdd(f.rayCounters, (uint32_t)__popc(mask));
+        atomicAdd(rayCounter, (unsigned long long)__popc(mask));
+    }
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    if (want) {
+        const uint32_t slot = base + __popc(mask & ((1u << lane) - 1u));
+        f.rayQueue[2 * (size_t)slot] = make_float4(r.org.x, r.org.y, r.org.z, 0.0f);
+        f.rayQueue[2 * (size_t)slot + 1] = make_float4(r.dir.x, r.dir.y, r.dir.z, r.tmax);
+        f.rayPixel[slot] = r.pixel;
+    }
+}
+GFX_D void visibilityRay(const f3 &shadingPoint, const LightSample &ls, uint32_t pixel, RayRequest* r) {
+    // the ray of evaluateVisibility / performDirectLighting<..., true> (restir_di_shared.h:518-582)
+    f3 shadowRayDir = ls.atInfinity ? ls.position : (ls.position - shadingPoint);
+    const float dist2 = sqLength(shadowRayDir);
+    float dist = sqrtf(dist2);
+    shadowRayDir /= dist;
+    if (ls.atInfinity)
+        dist = 1e+10f;
+    r->org = shadingPoint;
+    r->dir = shadowRayDir;
+    r->tmax = dist * 0.9999f;
+    r->pixel = pixel;
+}
+
+// PHASE 0: the whole program in one kernel, visibility traced inline (megakernel form of the reference).
+// PHASE 1: candidates + recPDF, the visibility ray is only *requested* (wavefront form).
+// PHASE 2: applies the answered visibility, then the temporal merge.
+template <bool withTemporalRIS, bool useUnbiasedEstimator, int PHASE>
+GFX_D bool risPixel(const DevScene &s, const DevFrame &f, const DevFrameParams &p, RayRequest* request) {
     // optix_restir_di_kernels.cu:14-287
     const uint32_t x = blockIdx.x * 8 + threadIdx.x;
     const uint32_t y = p.y0 + blockIdx.y * 8 + threadIdx.y;
     if (x >= f.W || y >= p.y1)
-        return;
+        return false;
     const size_t pix = (size_t)y * f.W + x;
     const uint32_t curBufIdx = p.bufferIndex;
 
     const uint4 gb0 = f.gb0[curBufIdx][pix];
     if (gb0.x == 0xFFFFFFFFu)
-        return;
+        return false;
     const float4 gb2 = f.gb2[curBufIdx][pix];
     const uint4 gb3 = f.gb3[curBufIdx][pix];
 
@@ -281,6 +324,8 @@ __global__ void __launch_bounds__(64) k_initialAndTemporalRIS(DevScene s, DevFra
     reservoir.initialize(emptyLightSample());
 
     float selectedTargetDensity = 0.0f;
+    float recPDFEstimate = 0.0f;
+    if (PHASE != 2) {
     const uint32_t numCandidates = 1u << p.log2NumCandidateSamples;
     // Streaming RIS (:66-123).  Reservoir::update (restir_di_shared.h:118-125) is spelled out: instead of
     // copying the 10-float LightSample on every acceptance, the three primary sample values that
@@ -318,17 +363,38 @@ __global__ void __launch_bounds__(64) k_initialAndTemporalRIS(DevScene s, DevFra
     reservoir.sumWeights = sumWeights;
     reservoir.streamLength = numCandidates;
 
-    float recPDFEstimate = reservoir.sumWeights / (selectedTargetDensity * reservoir.streamLength);
+    recPDFEstimate = reservoir.sumWeights / (selectedTargetDensity * reservoir.streamLength);
     if (!isfinite(recPDFEstimate)) {
         recPDFEstimate = 0.0f;
         selectedTargetDensity = 0.0f;
     }
+    }
+    else { // PHASE 2: pick up where phase 1 stopped
+        reservoir = loadReservoir(f, curResIndex, pix);
+        const float2 info = f.reservoirInfo[curResIndex][pix];
+        recPDFEstimate = info.x;
+        selectedTargetDensity = info.y;
+    }
 
     if (p.reuseVisibility && selectedTargetDensity > 0.0f) {
-        if (!evaluateVisibility(s, positionInWorld, reservoir.sample)) {
+        if (PHASE == 1) {
+            visibilityRay(positionInWorld, reservoir.sample, (uint32_t)pix, request);
+            f.rng[pix] = rng.state;
+            storeReservoir(f, curResIndex, pix, reservoir);
+            f.reservoirInfo[curResIndex][pix] = make_float2(recPDFEstimate, selectedTargetDensity);
+            return true;
+        }
+        const bool visible = PHASE == 2 ? (f.visibility[pix] != 0) : evaluateVisibility(s, positionInWorld, reservoir.sample);
+        if (!visible) {
             recPDFEstimate = 0.0f;
             selectedTargetDensity = 0.0f;
         }
+    }
+    if (PHASE == 1) {
+        f.rng[pix] = rng.state;
+        storeReservoir(f, curResIndex, pix, reservoir);
+        f.reservoirInfo[curResIndex][pix] = make_float2(recPDFEstimate, selectedTargetDensity);
+        return false;
     }
 
     if (withTemporalRIS) {
@@ -411,6 +477,15 @@ __global__ void __launch_bounds__(64) k_initialAndTemporalRIS(DevScene s, DevFra
     f.rng[pix] = rng.state;
     storeReservoir(f, curResIndex, pix, reservoir);
     f.reservoirInfo[curResIndex][pix] = make_float2(recPDFEstimate, selectedTargetDensity);
+    return false;
+}
+
+template <bool withTemporalRIS, bool useUnbiasedEstimator, int PHASE>
+__global__ void __launch_bounds__(64) k_initialAndTemporalRIS(DevScene s, DevFrame f, DevFrameParams p) {
+    RayRequest request;
+    const bool want = risPixel<withTemporalRIS, useUnbiasedEstimator, PHASE>(s, f, p, &request);
+    if (PHASE == 1)
+        enqueueRay(f, s.rayCounter, want, request);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -578,6 +653,35 @@ __global__ void __launch_bounds__(64) k_spatialRIS(DevScene s, DevFrame f, DevFr
 }
 
 // ---------------------------------------------------------------------------------------------
+// wavefront form of `shading`: phase 1 only requests the shadow ray of the surviving sample
+__global__ void __launch_bounds__(64) k_shadingRays(DevScene s, DevFrame f, DevFrameParams p) {
+    RayRequest request;
+    bool want = false;
+    const uint32_t x = blockIdx.x * 8 + threadIdx.x;
+    const uint32_t y = p.y0 + blockIdx.y * 8 + threadIdx.y;
+    if (x < f.W && y < p.y1) {
+        const size_t pix = (size_t)y * f.W + x;
+        const uint32_t bufIdx = p.bufferIndex;
+        if (f.gb0[bufIdx][pix].x != 0xFFFFFFFFu) {
+            const float2 reservoirInfo = f.reservoirInfo[p.currentReservoirIndex][pix];
+            const float recPDFEstimate = reservoirInfo.x;
+            if (recPDFEstimate > 0 && isfinite(recPDFEstimate)) {
+                const float4 gb2 = f.gb2[bufIdx][pix];
+                f3 positionInWorld(gb2.x, gb2.y, gb2.z);
+                const f3 geometricNormalInWorld = decodeVector(__float_as_uint(gb2.w));
+                const f3 vOut = normalize(p.camera.position - positionInWorld);
+                const float frontHit = dot(vOut, geometricNormalInWorld) >= 0.0f ? 1.0f : -1.0f;
+                positionInWorld = offsetRayOrigin(positionInWorld, frontHit * geometricNormalInWorld);
+                const Reservoir reservoir = loadReservoir(f, p.currentReservoirIndex, pix);
+                visibilityRay(positionInWorld, reservoir.sample, (uint32_t)pix, &request);
+                want = true;
+            }
+        }
+    }
+    enqueueRay(f, s.rayCounter, want, request);
+}
+
+template <bool QUEUED_VISIBILITY>
 __global__ void __launch_bounds__(64) k_shading(DevScene s, DevFrame f, DevFrameParams p) {
     // optix_restir_di_kernels.cu:559-637
     const uint32_t x = blockIdx.x * 8 + threadIdx.x;
@@ -623,6 +727,9 @@ __global__ void __launch_bounds__(64) k_shading(DevScene s, DevFrame f, DevFrame
                 (!p.enableTemporalReuse || (p.enableSpatialReuse && p.useUnbiasedEstimator));
             if (visDone)
                 directCont = performDirectLighting<false>(s, positionInWorld, vOutLocal, shadingFrame, bsdf, lightSample);
+            else if (QUEUED_VISIBILITY) // performDirectLighting<true> with the answer of the wavefront trace
+                directCont = f.visibility[pix] ? performDirectLighting<false>(s, positionInWorld, vOutLocal, shadingFrame, bsdf, lightSample)
+                                               : f3(0.0f);
             else
                 directCont = performDirectLighting<true>(s, positionInWorld, vOutLocal, shadingFrame, bsdf, lightSample);
         }
@@ -649,17 +756,43 @@ int launchReSTIR(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* params
     const dim3 grid((ctx->frame.W + 7) / 8, (p.y1 - p.y0 + 7) / 8);
     const DevScene s = ctx->devScene();
     const DevFrame f = ctx->devFrame();
+    // wavefront form (default): request rays -> persistent-thread trace -> resolve.  GFX_MEGAKERNEL=1 selects
+    // the single-kernel form with inline traversal (same results; kept for A/B measurements).
+    static const bool megakernel = getenv("GFX_MEGAKERNEL") != nullptr;
+    const bool wave = !megakernel;
+#define RIS_LAUNCH(T, U) \
+    if (wave && p.reuseVisibility) { \
+        int rc_ = resetVisibilityQueue(ctx, stream); if (rc_) return rc_; \
+        k_initialAndTemporalRIS<T, U, 1><<<grid, block, 0, stream>>>(s, f, p); ctx->launches++; \
+        rc_ = traceVisibilityQueue(ctx, stream); if (rc_) return rc_; \
+        k_initialAndTemporalRIS<T, U, 2><<<grid, block, 0, stream>>>(s, f, p); \
+    } else { \
+        k_initialAndTemporalRIS<T, U, 0><<<grid, block, 0, stream>>>(s, f, p); \
+    }
     switch (pass) {
-    case GFX_RESTIR_INITIAL_RIS: k_initialAndTemporalRIS<false, false><<<grid, block, 0, stream>>>(s, f, p); break;
-    case GFX_RESTIR_INITIAL_AND_TEMPORAL_BIASED: k_initialAndTemporalRIS<true, false><<<grid, block, 0, stream>>>(s, f, p); break;
-    case GFX_RESTIR_INITIAL_AND_TEMPORAL_UNBIASED: k_initialAndTemporalRIS<true, true><<<grid, block, 0, stream>>>(s, f, p); break;
+    case GFX_RESTIR_INITIAL_RIS: RIS_LAUNCH(false, false); break;
+    case GFX_RESTIR_INITIAL_AND_TEMPORAL_BIASED: RIS_LAUNCH(true, false); break;
+    case GFX_RESTIR_INITIAL_AND_TEMPORAL_UNBIASED: RIS_LAUNCH(true, true); break;
     case GFX_RESTIR_SPATIAL_BIASED: k_spatialRIS<false><<<grid, block, 0, stream>>>(s, f, p); break;
     case GFX_RESTIR_SPATIAL_UNBIASED: k_spatialRIS<true><<<grid, block, 0, stream>>>(s, f, p); break;
-    case GFX_RESTIR_SHADING: k_shading<<<grid, block, 0, stream>>>(s, f, p); break;
+    case GFX_RESTIR_SHADING: {
+        const bool visDone = p.reuseVisibility && (!p.enableTemporalReuse || (p.enableSpatialReuse && p.useUnbiasedEstimator));
+        if (wave && !visDone) {
+            int rc_ = resetVisibilityQueue(ctx, stream); if (rc_) return rc_;
+            k_shadingRays<<<grid, block, 0, stream>>>(s, f, p); ctx->launches++;
+            rc_ = traceVisibilityQueue(ctx, stream); if (rc_) return rc_;
+            k_shading<true><<<grid, block, 0, stream>>>(s, f, p);
+        }
+        else {
+            k_shading<false><<<grid, block, 0, stream>>>(s, f, p);
+        }
+        break;
+    }
     default:
         ctx->setError("gfx_restir_launch: unknown pass");
         return GFX_ERR_INVALID_ARGUMENT;
     }
+#undef RIS_LAUNCH
     ctx->launches++;
     GFX_CUDA(ctx, cudaGetLastError());
     return GFX_OK;

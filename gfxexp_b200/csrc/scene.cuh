@@ -99,6 +99,10 @@ struct DevFrame {
     float4* normal;
     const float2* neighborDeltas; // 1024 entries
     unsigned long long* stats;    // [0] rays traced (primary + visibility)
+    float4* rayQueue;             // wavefront visibility queue, see context.h
+    uint32_t* rayPixel;
+    uint32_t* rayCounters;
+    uint8_t* visibility;
 };
 
 struct DevCamera {

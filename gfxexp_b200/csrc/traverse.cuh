@@ -4,8 +4,8 @@
 // semantics of the only BVH traverser in the reference tree, bvh::traverse<8>
 // (common/bvh_builder.cpp:1272-1649): children are visited leaf-groups-first, near to far, by the
 // same key (entry distance, isInternal<<31); the ray/triangle test is bit-for-bit
-// testRayVsTriangle (common/bvh_builder.cpp:1251-1270) — this TU must be compiled with
-// -fmad=false so that it rounds like the IEEE oracle.
+// testRayVsTriangle (common/bvh_builder.cpp:1251-1270) on the explicit-FMA vector kernels of
+// vec.cuh / oracle/vecmath.h.
 //
 // Differences by design (documented in DESIGN.md):
 //  * ties in hit distance resolve to the smaller TriangleStorage index instead of "first found"
@@ -14,6 +14,10 @@
 //  * the slab test works on t = q * (scale/dir) + (origin-org)/dir with explicit FMAs and a 1e-5
 //    relative slack, i.e. it is conservative w.r.t. AABB::intersect (common/basic_types.h:3450-3465);
 //    it only decides which nodes are visited, never the hit itself.
+//
+// The traversal is exposed as a resumable state machine (TraversalState + traverseStep = one internal
+// node incl. its leaf children) so that the wavefront kernel of trace.cu can refill finished lanes
+// with new rays (persistent threads) while the fused kernels simply loop traverseStep to completion.
 #pragma once
 #include "scene.cuh"
 
@@ -48,158 +52,174 @@ GFX_D bool testRayVsTriangle( // common/bvh_builder.cpp:1251-1270
 
 constexpr int kStackSize = 64;
 
-template <bool ANY_HIT, bool STATS = false>
-GFX_D Hit traverseBvh(const DevBvh &bvh, const f3 &org, const f3 &dir, const float tmin, const float tmax) {
+struct TraversalState {
+    f3 org, dir, idir;
+    float tmin, tmax;
     Hit best;
-    best.dist = tmax;
-    best.storageIndex = 0xFFFFFFFFu;
-    best.geomIndex = 0xFFFFFFFFu;
-    best.primIndex = 0xFFFFFFFFu;
-    best.bcB = 0.0f;
-    best.bcC = 0.0f;
-    best.statNodes = 0;
-    best.statTris = 0;
-    if (bvh.numNodes == 0)
-        return best;
+    uint32_t nodeIdx;
+    int sp;
+    uint2 stack[kStackSize]; // (node index, truncated entry distance bits)
+};
 
+GFX_D void traverseInit(TraversalState &st, const f3 &org, const f3 &dir, float tmin, float tmax) {
+    st.org = org;
+    st.dir = dir;
+    st.tmin = tmin;
+    st.tmax = tmax;
+    st.best.dist = tmax;
+    st.best.storageIndex = 0xFFFFFFFFu;
+    st.best.geomIndex = 0xFFFFFFFFu;
+    st.best.primIndex = 0xFFFFFFFFu;
+    st.best.bcB = 0.0f;
+    st.best.bcC = 0.0f;
+    st.best.statNodes = 0;
+    st.best.statTris = 0;
     // guarded reciprocal direction for the slab test only
     const float ooeps = 8.271806e-25f; // 2^-80
     const f3 sd(fabsf(dir.x) > ooeps ? dir.x : copysignf(ooeps, dir.x),
                 fabsf(dir.y) > ooeps ? dir.y : copysignf(ooeps, dir.y),
                 fabsf(dir.z) > ooeps ? dir.z : copysignf(ooeps, dir.z));
-    const f3 idir(1.0f / sd.x, 1.0f / sd.y, 1.0f / sd.z);
+    st.idir = f3(1.0f / sd.x, 1.0f / sd.y, 1.0f / sd.z);
+    st.nodeIdx = 0;
+    st.sp = 0;
+}
 
-    uint2 stack[kStackSize]; // (node index, entry distance bits)
-    int sp = 0;
-    uint32_t nodeIdx = 0;
+// Processes node st.nodeIdx: slab-tests its children, intersects the triangle chains of the leaf
+// children that are hit, selects the next internal node.  Returns false when the traversal is finished.
+template <bool ANY_HIT, bool STATS>
+GFX_D bool traverseStep(const DevBvh &bvh, TraversalState &st) {
+    const uint4* np = bvh.nodes + 5 * (size_t)st.nodeIdx;
+    const uint4 n0 = __ldg(np + 0);
+    const uint4 n1 = __ldg(np + 1);
+    const uint4 n2 = __ldg(np + 2);
+    const uint4 n3 = __ldg(np + 3);
+    const uint4 n4 = __ldg(np + 4);
+    if (STATS)
+        ++st.best.statNodes;
 
-    while (true) {
-        const uint4* np = bvh.nodes + 5 * (size_t)nodeIdx;
-        const uint4 n0 = __ldg(np + 0);
-        const uint4 n1 = __ldg(np + 1);
-        const uint4 n2 = __ldg(np + 2);
-        const uint4 n3 = __ldg(np + 3);
-        const uint4 n4 = __ldg(np + 4);
-        if (STATS)
-            ++best.statNodes;
+    const uint32_t internalMask = n0.w >> 24;
+    const float ax = __uint_as_float((n0.w & 0xFFu) << 23) * st.idir.x;
+    const float ay = __uint_as_float(((n0.w >> 8) & 0xFFu) << 23) * st.idir.y;
+    const float az = __uint_as_float(((n0.w >> 16) & 0xFFu) << 23) * st.idir.z;
+    const float bx = (__uint_as_float(n0.x) - st.org.x) * st.idir.x;
+    const float by = (__uint_as_float(n0.y) - st.org.y) * st.idir.y;
+    const float bz = (__uint_as_float(n0.z) - st.org.z) * st.idir.z;
 
-        const uint32_t internalMask = n0.w >> 24;
-        const float ax = __uint_as_float((n0.w & 0xFFu) << 23) * idir.x;
-        const float ay = __uint_as_float(((n0.w >> 8) & 0xFFu) << 23) * idir.y;
-        const float az = __uint_as_float(((n0.w >> 16) & 0xFFu) << 23) * idir.z;
-        const float bx = (__uint_as_float(n0.x) - org.x) * idir.x;
-        const float by = (__uint_as_float(n0.y) - org.y) * idir.y;
-        const float bz = (__uint_as_float(n0.z) - org.z) * idir.z;
-
-        uint32_t keys[8];
+    uint32_t keys[8];
 #pragma unroll
-        for (int slot = 0; slot < 8; ++slot) {
-            const int sh = 8 * (slot & 3);
-            const uint32_t qminx = ((slot < 4 ? n2.x : n2.y) >> sh) & 0xFFu;
-            const uint32_t qminy = ((slot < 4 ? n2.z : n2.w) >> sh) & 0xFFu;
-            const uint32_t qminz = ((slot < 4 ? n3.x : n3.y) >> sh) & 0xFFu;
-            const uint32_t qmaxx = ((slot < 4 ? n3.z : n3.w) >> sh) & 0xFFu;
-            const uint32_t qmaxy = ((slot < 4 ? n4.x : n4.y) >> sh) & 0xFFu;
-            const uint32_t qmaxz = ((slot < 4 ? n4.z : n4.w) >> sh) & 0xFFu;
-            const bool valid = (qminx != 255u) || (qmaxx != 0u);
-            const float tlx = __fmaf_rn((float)qminx, ax, bx), thx = __fmaf_rn((float)qmaxx, ax, bx);
-            const float tly = __fmaf_rn((float)qminy, ay, by), thy = __fmaf_rn((float)qmaxy, ay, by);
-            const float tlz = __fmaf_rn((float)qminz, az, bz), thz = __fmaf_rn((float)qmaxz, az, bz);
-            const float tn = fmaxf(fmaxf(fminf(tlx, thx), fminf(tly, thy)), fmaxf(fminf(tlz, thz), tmin));
-            const float tf = fminf(fminf(fmaxf(tlx, thx), fmaxf(tly, thy)), fminf(fmaxf(tlz, thz), best.dist));
-            const bool hit = valid && (tn <= tf * 1.00001f);
-            const uint32_t isInternal = (internalMask >> slot) & 1u;
-            keys[slot] = hit ? ((isInternal << 31) | ((__float_as_uint(tn) >> 1) & 0x7FFFFFF8u) | (uint32_t)slot)
-                             : 0xFFFFFFFFu;
-        }
-        // 19-comparator network, ascending: leaf hits (near..far), internal hits (near..far), misses
-        GFX_CSWAP(keys[0], keys[2]); GFX_CSWAP(keys[1], keys[3]); GFX_CSWAP(keys[4], keys[6]); GFX_CSWAP(keys[5], keys[7]);
-        GFX_CSWAP(keys[0], keys[4]); GFX_CSWAP(keys[1], keys[5]); GFX_CSWAP(keys[2], keys[6]); GFX_CSWAP(keys[3], keys[7]);
-        GFX_CSWAP(keys[0], keys[1]); GFX_CSWAP(keys[2], keys[3]); GFX_CSWAP(keys[4], keys[5]); GFX_CSWAP(keys[6], keys[7]);
-        GFX_CSWAP(keys[2], keys[4]); GFX_CSWAP(keys[3], keys[5]);
-        GFX_CSWAP(keys[1], keys[4]); GFX_CSWAP(keys[3], keys[6]);
-        GFX_CSWAP(keys[1], keys[2]); GFX_CSWAP(keys[3], keys[4]); GFX_CSWAP(keys[5], keys[6]);
-
-        // ---- leaf children: intersect their triangle chains now (shrinks best.dist before descending)
-        const uint32_t leafBase = n1.y;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const uint32_t key = keys[k];
-            if (key >= 0x80000000u)
-                break;
-            const uint32_t slot = key & 7u;
-            const float tn = __uint_as_float((key & 0x7FFFFFF8u) << 1);
-            if (tn > best.dist)
-                continue;
-            const uint32_t metas = slot < 4 ? n1.z : n1.w;
-            uint32_t idx = leafBase + ((metas >> (8 * (slot & 3))) & 0xFFu);
-            while (true) {
-                const uint32_t pr = __ldg(bvh.primRefs + idx);
-                const uint32_t si = pr & 0x7FFFFFFFu;
-                const float4* tp = bvh.tris + 3 * (size_t)si;
-                const float4 t0 = __ldg(tp + 0);
-                const float4 t1 = __ldg(tp + 1);
-                const float4 t2 = __ldg(tp + 2);
-                float hitDist, bcB, bcC;
-                if (STATS)
-                    ++best.statTris;
-                const bool hit = testRayVsTriangle(org, dir, tmin, tmax,
-                                                   f3(t0.x, t0.y, t0.z), f3(t0.w, t1.x, t1.y), f3(t1.z, t1.w, t2.x),
-                                                   &hitDist, &bcB, &bcC);
-                if (hit && (hitDist < best.dist || (hitDist == best.dist && si < best.storageIndex))) {
-                    best.dist = hitDist;
-                    best.storageIndex = si;
-                    best.geomIndex = __float_as_uint(t2.y);
-                    best.primIndex = __float_as_uint(t2.z);
-                    best.bcB = bcB;
-                    best.bcC = bcC;
-                    if (ANY_HIT)
-                        return best;
-                }
-                if (pr >> 31)
-                    break;
-                ++idx;
-            }
-        }
-
-        // ---- internal children: nearest becomes the next node, the others are pushed far -> near
-        const uint32_t childBase = n1.x;
-        uint32_t next = 0xFFFFFFFFu, nextT = 0u;
-#pragma unroll
-        for (int k = 7; k >= 0; --k) {
-            const uint32_t key = keys[k];
-            if (key == 0xFFFFFFFFu || key < 0x80000000u)
-                continue;
-            const uint32_t slot = key & 7u;
-            const uint32_t tnBits = (key & 0x7FFFFFF8u) << 1; // truncated entry distance (<= true tn)
-            if (__uint_as_float(tnBits) > best.dist)
-                continue;
-            if (next != 0xFFFFFFFFu) {
-                if (sp < kStackSize)
-                    stack[sp++] = make_uint2(next, nextT);
-                else if (bvh.overflowFlag)
-                    *bvh.overflowFlag = 1u;
-            }
-            next = childBase + __popc(internalMask & ((1u << slot) - 1u));
-            nextT = tnBits;
-        }
-        if (next != 0xFFFFFFFFu) {
-            nodeIdx = next;
-            continue;
-        }
-        bool found = false;
-        while (sp > 0) {
-            const uint2 e = stack[--sp];
-            if (__uint_as_float(e.y) <= best.dist) {
-                nodeIdx = e.x;
-                found = true;
-                break;
-            }
-        }
-        if (!found)
-            break;
+    for (int slot = 0; slot < 8; ++slot) {
+        const int sh = 8 * (slot & 3);
+        const uint32_t qminx = ((slot < 4 ? n2.x : n2.y) >> sh) & 0xFFu;
+        const uint32_t qminy = ((slot < 4 ? n2.z : n2.w) >> sh) & 0xFFu;
+        const uint32_t qminz = ((slot < 4 ? n3.x : n3.y) >> sh) & 0xFFu;
+        const uint32_t qmaxx = ((slot < 4 ? n3.z : n3.w) >> sh) & 0xFFu;
+        const uint32_t qmaxy = ((slot < 4 ? n4.x : n4.y) >> sh) & 0xFFu;
+        const uint32_t qmaxz = ((slot < 4 ? n4.z : n4.w) >> sh) & 0xFFu;
+        const bool valid = (qminx != 255u) || (qmaxx != 0u);
+        const float tlx = __fmaf_rn((float)qminx, ax, bx), thx = __fmaf_rn((float)qmaxx, ax, bx);
+        const float tly = __fmaf_rn((float)qminy, ay, by), thy = __fmaf_rn((float)qmaxy, ay, by);
+        const float tlz = __fmaf_rn((float)qminz, az, bz), thz = __fmaf_rn((float)qmaxz, az, bz);
+        const float tn = fmaxf(fmaxf(fminf(tlx, thx), fminf(tly, thy)), fmaxf(fminf(tlz, thz), st.tmin));
+        const float tf = fminf(fminf(fmaxf(tlx, thx), fmaxf(tly, thy)), fminf(fmaxf(tlz, thz), st.best.dist));
+        const bool hit = valid && (tn <= tf * 1.00001f);
+        const uint32_t isInternal = (internalMask >> slot) & 1u;
+        keys[slot] = hit ? ((isInternal << 31) | ((__float_as_uint(tn) >> 1) & 0x7FFFFFF8u) | (uint32_t)slot)
+                         : 0xFFFFFFFFu;
     }
-    return best;
+    // 19-comparator network, ascending: leaf hits (near..far), internal hits (near..far), misses
+    GFX_CSWAP(keys[0], keys[2]); GFX_CSWAP(keys[1], keys[3]); GFX_CSWAP(keys[4], keys[6]); GFX_CSWAP(keys[5], keys[7]);
+    GFX_CSWAP(keys[0], keys[4]); GFX_CSWAP(keys[1], keys[5]); GFX_CSWAP(keys[2], keys[6]); GFX_CSWAP(keys[3], keys[7]);
+    GFX_CSWAP(keys[0], keys[1]); GFX_CSWAP(keys[2], keys[3]); GFX_CSWAP(keys[4], keys[5]); GFX_CSWAP(keys[6], keys[7]);
+    GFX_CSWAP(keys[2], keys[4]); GFX_CSWAP(keys[3], keys[5]);
+    GFX_CSWAP(keys[1], keys[4]); GFX_CSWAP(keys[3], keys[6]);
+    GFX_CSWAP(keys[1], keys[2]); GFX_CSWAP(keys[3], keys[4]); GFX_CSWAP(keys[5], keys[6]);
+
+    // ---- leaf children: intersect their triangle chains now (shrinks best.dist before descending)
+    const uint32_t leafBase = n1.y;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t key = keys[k];
+        if (key >= 0x80000000u)
+            break;
+        const uint32_t slot = key & 7u;
+        const float tn = __uint_as_float((key & 0x7FFFFFF8u) << 1);
+        if (tn > st.best.dist)
+            continue;
+        const uint32_t metas = slot < 4 ? n1.z : n1.w;
+        uint32_t idx = leafBase + ((metas >> (8 * (slot & 3))) & 0xFFu);
+        while (true) {
+            const uint32_t pr = __ldg(bvh.primRefs + idx);
+            const uint32_t si = pr & 0x7FFFFFFFu;
+            const float4* tp = bvh.tris + 3 * (size_t)si;
+            const float4 t0 = __ldg(tp + 0);
+            const float4 t1 = __ldg(tp + 1);
+            const float4 t2 = __ldg(tp + 2);
+            float hitDist, bcB, bcC;
+            if (STATS)
+                ++st.best.statTris;
+            const bool hit = testRayVsTriangle(st.org, st.dir, st.tmin, st.tmax,
+                                               f3(t0.x, t0.y, t0.z), f3(t0.w, t1.x, t1.y), f3(t1.z, t1.w, t2.x),
+                                               &hitDist, &bcB, &bcC);
+            if (hit && (hitDist < st.best.dist || (hitDist == st.best.dist && si < st.best.storageIndex))) {
+                st.best.dist = hitDist;
+                st.best.storageIndex = si;
+                st.best.geomIndex = __float_as_uint(t2.y);
+                st.best.primIndex = __float_as_uint(t2.z);
+                st.best.bcB = bcB;
+                st.best.bcC = bcC;
+                if (ANY_HIT)
+                    return false;
+            }
+            if (pr >> 31)
+                break;
+            ++idx;
+        }
+    }
+
+    // ---- internal children: nearest becomes the next node, the others are pushed far -> near
+    const uint32_t childBase = n1.x;
+    uint32_t next = 0xFFFFFFFFu, nextT = 0u;
+#pragma unroll
+    for (int k = 7; k >= 0; --k) {
+        const uint32_t key = keys[k];
+        if (key == 0xFFFFFFFFu || key < 0x80000000u)
+            continue;
+        const uint32_t slot = key & 7u;
+        const uint32_t tnBits = (key & 0x7FFFFFF8u) << 1; // truncated entry distance (<= true tn)
+        if (__uint_as_float(tnBits) > st.best.dist)
+            continue;
+        if (next != 0xFFFFFFFFu) {
+            if (st.sp < kStackSize)
+                st.stack[st.sp++] = make_uint2(next, nextT);
+            else if (bvh.overflowFlag)
+                *bvh.overflowFlag = 1u;
+        }
+        next = childBase + __popc(internalMask & ((1u << slot) - 1u));
+        nextT = tnBits;
+    }
+    if (next != 0xFFFFFFFFu) {
+        st.nodeIdx = next;
+        return true;
+    }
+    while (st.sp > 0) {
+        const uint2 e = st.stack[--st.sp];
+        if (__uint_as_float(e.y) <= st.best.dist) {
+            st.nodeIdx = e.x;
+            return true;
+        }
+    }
+    return false;
+}
+
+template <bool ANY_HIT, bool STATS = false>
+GFX_D Hit traverseBvh(const DevBvh &bvh, const f3 &org, const f3 &dir, const float tmin, const float tmax) {
+    TraversalState st;
+    traverseInit(st, org, dir, tmin, tmax);
+    if (bvh.numNodes == 0)
+        return st.best;
+    while (traverseStep<ANY_HIT, STATS>(bvh, st)) {
+    }
+    return st.best;
 }
 
 } // namespace gfx
