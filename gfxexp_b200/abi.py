@@ -60,7 +60,8 @@ class GfxFrameParams(C.Structure):
                 ("enableTemporalReuse", c_u32), ("enableSpatialReuse", c_u32),
                 ("useUnbiasedEstimator", c_u32), ("resetFlowBuffer", c_u32), ("enableJittering", c_u32),
                 ("currentReservoirIndex", c_u32), ("spatialNeighborBaseIndex", c_u32),
-                ("tileOriginY", c_u32), ("tileRows", c_u32), ("svgfFlags", c_u32), ("taaHistoryLength", c_u32)]
+                ("tileOriginY", c_u32), ("tileRows", c_u32), ("svgfFlags", c_u32), ("taaHistoryLength", c_u32),
+                ("maxPathLength", c_u32)]
 
 
 NODE_DTYPE = np.dtype([("quantBoxOrigin", np.float32, 3), ("quantBoxExpScale", np.uint8, 3),
@@ -77,6 +78,7 @@ assert NODE_DTYPE.itemsize == 80 and TRI_DTYPE.itemsize == 48 and HIT_DTYPE.item
 
 # enums
 TRACE_CLOSEST, TRACE_ANY, TRACE_STATS = 0, 1, 2
+PT_BASELINE = 0  # GfxPathTraceVariant
 (RESTIR_INITIAL_RIS, RESTIR_INITIAL_AND_TEMPORAL_BIASED, RESTIR_INITIAL_AND_TEMPORAL_UNBIASED,
  RESTIR_SPATIAL_BIASED, RESTIR_SPATIAL_UNBIASED, RESTIR_SHADING) = range(6)
 (SVGF_TEMPORAL_ACCUMULATE, SVGF_ESTIMATE_VARIANCE, SVGF_ATROUS, SVGF_FILL_BACKGROUND, SVGF_MODULATE_TAA) = range(5)
@@ -185,6 +187,7 @@ def default_frame_params(scene, width: int, height: int) -> GfxFrameParams:
     p.tileRows = 0
     p.svgfFlags = SVGF_ENABLE_TEMPORAL_ACCUMULATION | SVGF_FEEDBACK_1ST | SVGF_ENABLE_TAA | SVGF_MODULATE_ALBEDO
     p.taaHistoryLength = 16
+    p.maxPathLength = 5
     return p
 
 
@@ -214,6 +217,7 @@ _DECLS = {
     "gfx_gbuffer_launch": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxFrameParams)]),
     "gfx_restir_launch": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxFrameParams), C.c_int]),
     "gfx_svgf_launch": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxFrameParams), C.c_int, c_u32]),
+    "gfx_pathtrace_launch": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxFrameParams), C.c_int]),
     "gfx_nrc_create": (C.c_int, [C.c_void_p, c_u32, c_f, C.POINTER(C.c_void_p)]),
     "gfx_nrc_destroy": (None, [C.c_void_p]),
     "gfx_nrc_infer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_u32]),

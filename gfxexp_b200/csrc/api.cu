@@ -28,10 +28,12 @@ void FrameState::release() {
         cudaFree(gb0[i]); cudaFree(gb1[i]); cudaFree(gb2[i]); cudaFree(gb3[i]);
         cudaFree(reservoir[i]); cudaFree(reservoirInfo[i]);
         cudaFree(svgfLighting[i]); cudaFree(svgfMoments[i]); cudaFree(svgfFinal[i]); cudaFree(svgfDepth[i]);
+        cudaFree(ptExtRays[i]); cudaFree(ptExtPixel[i]);
     }
     cudaFree(rayQueue); cudaFree(rayPixel); cudaFree(rayCounters); cudaFree(visibility);
     cudaFree(stats); cudaFree(rng); cudaFree(beauty); cudaFree(albedo); cudaFree(normal); cudaFree(neighborDeltas);
     cudaFree(svgfPrevLighting); cudaFree(svgfAlbedo); cudaFree(svgfPrevScreenPos);
+    cudaFree(ptAlphaPdf); cudaFree(ptRadiance); cudaFree(ptExtHits); cudaFree(ptShadowPending); cudaFree(ptCounters);
     *this = FrameState();
 }
 
@@ -703,6 +705,15 @@ int gfx_svgf_launch(gfx_ctx* ctx, void* stream, const GfxFrameParams* params, in
     if (!ctx->frame.created)
         return GFX_ERR_NOT_READY;
     return launchSVGF(ctx, (cudaStream_t)stream, params, pass, stage);
+}
+
+int gfx_pathtrace_launch(gfx_ctx* ctx, void* stream, const GfxFrameParams* params, int variant) {
+    CHECK_CTX(ctx);
+    if (!params)
+        return GFX_ERR_INVALID_ARGUMENT;
+    if (!ctx->frame.created || !ctx->bvh.ready)
+        return GFX_ERR_NOT_READY;
+    return launchPathTrace(ctx, (cudaStream_t)stream, params, variant);
 }
 
 } // extern "C"

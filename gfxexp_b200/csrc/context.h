@@ -74,6 +74,14 @@ struct FrameState {
     uint32_t* rayPixel = nullptr;    // pixel that asked for the ray
     uint32_t* rayCounters = nullptr; // [0] rays queued, [1] rays fetched
     uint8_t* visibility = nullptr;   // per pixel: 1 = unoccluded
+    // wavefront path tracer (pathtrace.cu), allocated on first use
+    float4* ptAlphaPdf = nullptr;
+    float4* ptRadiance = nullptr;
+    float4* ptExtRays[2] = { nullptr, nullptr };
+    uint32_t* ptExtPixel[2] = { nullptr, nullptr };
+    uint4* ptExtHits = nullptr;
+    float4* ptShadowPending = nullptr;
+    uint32_t* ptCounters = nullptr;
     // SVGF state
     float4* svgfLighting[2] = { nullptr, nullptr };  // lighting rgb + variance, ping-pong
     float4* svgfMoments[2] = { nullptr, nullptr };   // first/second luminance moments + history length
@@ -122,5 +130,6 @@ int buildLightDistributions(gfx_ctx* ctx, cudaStream_t stream, uint32_t bufferIn
 int launchGBuffer(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* p);
 int launchReSTIR(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* p, int pass);
 int launchSVGF(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* p, int pass, uint32_t stage);
+int launchPathTrace(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* p, int variant);
 DevFrameParams makeDevParams(const gfx_ctx* ctx, const GfxFrameParams* p);
 } // namespace gfx

@@ -1,0 +1,183 @@
+// lighting.cuh — light sampling and direct-lighting helpers shared by the ReSTIR, ReGIR and path-tracing kernels.
+//
+// sampleLight<false> (restir_di/restir_di_shared.h:320-516; identical copies live in path_tracing_shared.h:220-482,
+// regir_shared.h, neural_radiance_caching_shared.h, svgf_shared.h), performDirectLighting (:518-557),
+// evaluateVisibility (:559-582).  Visibility rays run through the inline any-hit traversal of traverse.cuh
+// (fused kernels) or are queued for trace.cu's persistent kernel (wavefront kernels).
+#pragma once
+#include "traverse.cuh"
+#include "shading.cuh"
+
+namespace gfx {
+
+struct LightSample { // restir_di_shared.h:89-96
+    f3 emittance, position, normal;
+    uint32_t atInfinity;
+};
+GFX_D LightSample emptyLightSample() {
+    LightSample s;
+    s.emittance = f3(0.0f);
+    s.position = f3(0.0f);
+    s.normal = f3(0.0f);
+    s.atInfinity = 0;
+    return s;
+}
+
+GFX_D float convertToWeight(const f3 &c) { return (c.x + c.y + c.z) / 3; } // restir_di_shared.h:82-85
+
+// last index with cdf[idx] <= u: the power-of-two stepping search of
+// DiscreteDistribution1DTemplate::sample (common_shared.h:226-232)
+GFX_D uint32_t searchCdf(const float* __restrict__ cdf, uint32_t numValues, float u) {
+    int idx = 0;
+    for (int d = (int)(nextPowerOf2(numValues) >> 1); d >= 1; d >>= 1) {
+        if (idx + d >= (int)numValues)
+            continue;
+        if (__ldg(cdf + idx + d) <= u)
+            idx += d;
+    }
+    return (uint32_t)idx;
+}
+// the same search seeded by a guide table (scene.cuh): exact, 1-3 loads instead of log2(n)
+GFX_D uint32_t guidedSearchCdf(const float* __restrict__ cdf, const uint32_t* __restrict__ guide, uint32_t guideSize,
+                               float u01, float u) {
+    const uint32_t b = min(dm_f2uint(u01 * (float)guideSize), guideSize - 1);
+    uint32_t idx = __ldg(guide + b);
+    const uint32_t hi = __ldg(guide + b + 1);
+    while (idx < hi && __ldg(cdf + idx + 1) <= u)
+        ++idx;
+    return idx;
+}
+GFX_D float remapCdf(const float* __restrict__ cdf, uint32_t numValues, float integral, uint32_t idx, float u) {
+    // common_shared.h:235-241
+    const float lCDF = __ldg(cdf + idx);
+    float rCDF = integral;
+    if (idx < numValues - 1)
+        rCDF = __ldg(cdf + idx + 1);
+    return (u - lCDF) / (rCDF - lCDF);
+}
+
+GFX_D void sampleLight(const DevScene &s, float ul, float u0, float u1, LightSample* lightSample, float* areaPDensity) {
+    // restir_di_shared.h:320-516 with sampleEnvLight = false, useSolidAngleSampling = false.
+    // The three DiscreteDistribution1D::sample calls are spelled out; weights[idx] / integral comes
+    // from the pre-divided prob tables and the triangle operands from the lightTris table (lights.cu),
+    // both produced by the reference's own expressions, so the result is bit-identical.
+    float lightProb = 1.0f;
+
+    // instance
+    const float instIntegral = __ldg(s.instIntegral);
+    float u = ul * instIntegral;
+    const uint32_t instSlot = guidedSearchCdf(s.instCdf, s.instGuide, kInstGuideSize, ul, u);
+    const float uGeomInst = remapCdf(s.instCdf, s.numInstances, instIntegral, instSlot, u);
+    const float instProb = __ldg(s.instProb + instSlot);
+    lightProb *= instProb;
+    const DevInstance* inst = s.instances + instSlot;
+    if (instProb == 0.0f) {
+        *areaPDensity = 0.0f;
+        return;
+    }
+
+    // geometry instance
+    const uint32_t firstMeshSlot = inst->firstMeshSlot, numMeshSlots = inst->numMeshSlots;
+    const float geomIntegral = inst->geomIntegral;
+    u = uGeomInst * geomIntegral;
+    const uint32_t geomInstIndexInInst = searchCdf(s.geomCdf + firstMeshSlot, numMeshSlots, u);
+    const float uPrim = remapCdf(s.geomCdf + firstMeshSlot, numMeshSlots, geomIntegral, geomInstIndexInInst, u);
+    const float geomInstProb = __ldg(s.geomProb + firstMeshSlot + geomInstIndexInInst);
+    const uint32_t geomInstSlot = __ldg(s.instanceMeshSlots + firstMeshSlot + geomInstIndexInInst);
+    lightProb *= geomInstProb;
+    if (geomInstProb == 0.0f) {
+        *areaPDensity = 0.0f;
+        return;
+    }
+
+    // primitive
+    const DevMesh* mesh = s.meshes + geomInstSlot;
+    const uint32_t triBase = mesh->triBase, numTriangles = mesh->numTriangles;
+    u = uPrim * mesh->primIntegral;
+    const uint32_t primIndex = guidedSearchCdf(s.primCdf + triBase, s.primGuide + (size_t)geomInstSlot * (kPrimGuideSize + 1),
+                                               kPrimGuideSize, uPrim, u);
+    const float primProb = __ldg(s.primProb + triBase + primIndex);
+    lightProb *= primProb;
+
+    const uint32_t lt = __ldg(s.lightTriBase + inst->geomBase + geomInstIndexInInst) + primIndex;
+    const float4* e = s.lightTris + 6 * (size_t)lt;
+    const float4 e0 = __ldg(e + 0), e1 = __ldg(e + 1), e2 = __ldg(e + 2), e3 = __ldg(e + 3), e4 = __ldg(e + 4), e5 = __ldg(e + 5);
+    const f3 pA(e0.x, e0.y, e0.z), pB(e1.x, e1.y, e1.z), pC(e2.x, e2.y, e2.z);
+    const f3 nA(e1.w, e2.w, e3.x), nB(e3.y, e3.z, e3.w), nC(e4.x, e4.y, e4.z);
+
+    // A Low-Distortion Map Between Triangle and Square (:485-498)
+    float bcA = 0.5f * u0;
+    float bcB = 0.5f * u1;
+    const float offset = bcB - bcA;
+    if (offset > 0)
+        bcB += offset;
+    else
+        bcA -= offset;
+    const float bcC = 1 - (bcA + bcB);
+
+    const float recArea = e0.w;
+    *areaPDensity = lightProb * recArea;
+
+    lightSample->position = bcA * pA + bcB * pB + bcC * pC;
+    lightSample->atInfinity = 0;
+    lightSample->normal = bcA * nA + bcB * nB + bcC * nC;
+    lightSample->normal = normalize(mul3x3(inst->normalMatrix, lightSample->normal));
+    lightSample->emittance = f3(e5.x, e5.y, e5.z);
+}
+
+GFX_D bool traceVisibility(const DevScene &s, const f3 &org, const f3 &dir, float tmax) {
+    // ray statistics: one atomic per warp per call site (lanes currently active here)
+    const uint32_t active = __activemask();
+    if ((threadIdx.x + threadIdx.y * blockDim.x) % 32 == (uint32_t)(__ffs(active) - 1))
+        atomicAdd(s.rayCounter, (unsigned long long)__popc(active));
+    const Hit h = traverseBvh<true>(s.bvh, org, dir, 0.0f, tmax);
+    return h.storageIndex == 0xFFFFFFFFu;
+}
+
+GFX_D bool evaluateVisibility(const DevScene &s, const f3 &shadingPoint, const LightSample &ls) { // :559-582
+    f3 shadowRayDir = ls.atInfinity ? ls.position : (ls.position - shadingPoint);
+    const float dist2 = sqLength(shadowRayDir);
+    float dist = sqrtf(dist2);
+    shadowRayDir /= dist;
+    if (ls.atInfinity)
+        dist = 1e+10f;
+    return traceVisibility(s, shadingPoint, shadowRayDir, dist * 0.9999f);
+}
+
+template <bool withVisibility>
+GFX_D f3 performDirectLighting(const DevScene &s, const f3 &shadingPoint, const f3 &vOutLocal,
+                               const ReferenceFrame &shadingFrame, const BSDF &bsdf, const LightSample &ls) { // :518-557
+    f3 shadowRayDir = ls.atInfinity ? ls.position : (ls.position - shadingPoint);
+    const float dist2 = sqLength(shadowRayDir);
+    float dist = sqrtf(dist2);
+    shadowRayDir /= dist;
+    const f3 shadowRayDirLocal = shadingFrame.toLocal(shadowRayDir);
+
+    const float lpCos = dot(-shadowRayDir, ls.normal);
+    const float spCos = shadowRayDirLocal.z;
+
+    float visibility = 1.0f;
+    if (withVisibility) {
+        if (ls.atInfinity)
+            dist = 1e+10f;
+        if (!traceVisibility(s, shadingPoint, shadowRayDir, dist * 0.9999f))
+            visibility = 0.0f;
+    }
+
+    if (visibility > 0 && lpCos > 0) {
+        const f3 Le = ls.emittance / kPi;
+        const f3 fsValue = bsdf.evaluate(vOutLocal, shadowRayDirLocal);
+        const float G = lpCos * fabsf(spCos) / dist2;
+        return fsValue * Le * G;
+    }
+    return f3(0.0f);
+}
+
+GFX_D BSDF setupBsdf(const DevScene &s, uint32_t matSlot) {
+    const GfxMaterialDesc* m = s.materials + matSlot;
+    BSDF b;
+    b.setup(m->bsdfType, m->p0, m->p1, m->p2);
+    return b;
+}
+
+} // namespace gfx

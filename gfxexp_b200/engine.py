@@ -151,6 +151,10 @@ class Context:
     def restir(self, params, pass_id: int, stream=None):
         self._check(self.lib.gfx_restir_launch(self.h, stream, C.byref(params), pass_id), "gfx_restir_launch")
 
+    def pathtrace(self, params, variant: int = abi.PT_BASELINE, stream=None):
+        """one sample per pixel of the path tracer (path_tracing_main.cpp:1780-1789) from the current G-buffer"""
+        self._check(self.lib.gfx_pathtrace_launch(self.h, stream, C.byref(params), variant), "gfx_pathtrace_launch")
+
     def svgf(self, params, pass_id: int, stage: int = 0, stream=None):
         self._check(self.lib.gfx_svgf_launch(self.h, stream, C.byref(params), pass_id, stage), "gfx_svgf_launch")
 

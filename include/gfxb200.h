@@ -187,6 +187,9 @@ typedef struct GfxFrameParams {
      * feedback1stFilteredResult, enableTemporalAA, modulateAlbedo, taaHistoryLength; svgf_main.cpp:1730-1736) */
     uint32_t svgfFlags;                /* GfxSVGFFlags */
     uint32_t taaHistoryLength;         /* 16 by default */
+    /* path tracers (path_tracing_shared.h PerFramePipelineLaunchParameters::maxPathLength; 5 by default,
+     * path_tracing_main.cpp:1555) */
+    uint32_t maxPathLength;
 } GfxFrameParams;
 
 typedef enum GfxSVGFFlags {
@@ -206,6 +209,11 @@ typedef enum GfxReSTIRPass {
     GFX_RESTIR_SPATIAL_UNBIASED = 4,
     GFX_RESTIR_SHADING = 5                      /* shading */
 } GfxReSTIRPass;
+
+/* path tracer entry points (path_tracing/path_tracing_main.cpp:52-57 PathTracingEntryPoint) */
+typedef enum GfxPathTraceVariant {
+    GFX_PT_BASELINE = 0                         /* pathTraceBaseline */
+} GfxPathTraceVariant;
 
 /* SVGF entry points (svgf/svgf_main.cpp:2127-2172) */
 typedef enum GfxSVGFPass {
@@ -297,6 +305,10 @@ int gfx_gbuffer_launch(gfx_ctx* ctx, void* stream, const GfxFrameParams* params)
 int gfx_restir_launch(gfx_ctx* ctx, void* stream, const GfxFrameParams* params, int pass);
 /* replaces the svgf.cu kernels (svgf_main.cpp:2127-2172) */
 int gfx_svgf_launch(gfx_ctx* ctx, void* stream, const GfxFrameParams* params, int pass, uint32_t stage);
+/* replaces pathTracing.setEntryPoint(variant) + pathTracing.optixPipeline.launch (path_tracing_main.cpp:1780-1789):
+ * one sample per pixel of the unidirectional path tracer (NEE + MIS + Russian roulette, params->maxPathLength)
+ * starting from the G-buffer of params->bufferIndex; running mean into GFX_BUFFER_BEAUTY_ACCUM. */
+int gfx_pathtrace_launch(gfx_ctx* ctx, void* stream, const GfxFrameParams* params, int variant);
 
 /* ---- NRC network (network_interface.h:14-28) ------------------------------------------ */
 typedef struct gfx_nrc gfx_nrc;

@@ -64,6 +64,8 @@ void orc_restir_setup_neighbor_table(orc_frame* f);
 void* orc_buffer_ptr(orc_frame* f, int bufferId, uint32_t index, size_t* bytes);
 void orc_gbuffer(orc_frame* f, const GfxFrameParams* p, int numThreads);
 void orc_restir(orc_frame* f, const GfxFrameParams* p, int pass, int numThreads);
+/* unidirectional path tracer (GfxPathTraceVariant); returns the number of rays traced */
+uint64_t orc_pathtrace(orc_frame* f, const GfxFrameParams* p, int variant, int numThreads);
 /* primary rays of the G-buffer pass (for the trace-only benchmarks) */
 void orc_generate_primary_rays(const GfxFrameParams* p, uint32_t width, uint32_t height, GfxRay* rays);
 

@@ -1211,3 +1211,8 @@ extern "C" void orc_restir(orc_frame* f, const GfxFrameParams* p, int pass, int 
         }
     }
 }
+
+// ---------------------------------------------------------------------------------------
+// path tracing (path_tracing/gpu_kernels/optix_pathtracing_kernels.cu)
+// ---------------------------------------------------------------------------------------
+#include "pathtrace.inl"

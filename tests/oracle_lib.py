@@ -72,6 +72,8 @@ def lib() -> C.CDLL:
         L.orc_buffer_ptr.argtypes = [vp, C.c_int, C.c_uint32, C.POINTER(C.c_size_t)]
         L.orc_gbuffer.argtypes = [vp, C.POINTER(abi.GfxFrameParams), C.c_int]
         L.orc_restir.argtypes = [vp, C.POINTER(abi.GfxFrameParams), C.c_int, C.c_int]
+        L.orc_pathtrace.argtypes = [vp, C.POINTER(abi.GfxFrameParams), C.c_int, C.c_int]
+        L.orc_pathtrace.restype = C.c_uint64
         L.orc_generate_primary_rays.argtypes = [C.POINTER(abi.GfxFrameParams), C.c_uint32, C.c_uint32, vp]
         L.orc_svgf_create.restype = vp
         L.orc_svgf_create.argtypes = [vp, C.c_uint32, C.c_uint32]
@@ -189,6 +191,10 @@ class OracleFrame:
 
     def restir(self, params, pass_id: int, threads: int = 0):
         lib().orc_restir(self.h, C.byref(params), pass_id, threads)
+
+    def pathtrace(self, params, variant: int = 0, threads: int = 0) -> int:
+        """one sample per pixel of the path tracer; returns the number of rays traced"""
+        return int(lib().orc_pathtrace(self.h, C.byref(params), variant, threads))
 
 
 class OracleSvgf:
