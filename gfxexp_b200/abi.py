@@ -61,7 +61,8 @@ class GfxFrameParams(C.Structure):
                 ("useUnbiasedEstimator", c_u32), ("resetFlowBuffer", c_u32), ("enableJittering", c_u32),
                 ("currentReservoirIndex", c_u32), ("spatialNeighborBaseIndex", c_u32),
                 ("tileOriginY", c_u32), ("tileRows", c_u32), ("svgfFlags", c_u32), ("taaHistoryLength", c_u32),
-                ("maxPathLength", c_u32)]
+                ("maxPathLength", c_u32),
+                ("sceneAabbMin", c_f * 3), ("sceneAabbMax", c_f * 3), ("radianceScale", c_f)]
 
 
 NODE_DTYPE = np.dtype([("quantBoxOrigin", np.float32, 3), ("quantBoxExpScale", np.uint8, 3),
@@ -78,14 +79,17 @@ assert NODE_DTYPE.itemsize == 80 and TRI_DTYPE.itemsize == 48 and HIT_DTYPE.item
 
 # enums
 TRACE_CLOSEST, TRACE_ANY, TRACE_STATS = 0, 1, 2
-PT_BASELINE = 0  # GfxPathTraceVariant
+PT_BASELINE, PT_NRC = 0, 1  # GfxPathTraceVariant
 (RESTIR_INITIAL_RIS, RESTIR_INITIAL_AND_TEMPORAL_BIASED, RESTIR_INITIAL_AND_TEMPORAL_UNBIASED,
  RESTIR_SPATIAL_BIASED, RESTIR_SPATIAL_UNBIASED, RESTIR_SHADING) = range(6)
 (SVGF_TEMPORAL_ACCUMULATE, SVGF_ESTIMATE_VARIANCE, SVGF_ATROUS, SVGF_FILL_BACKGROUND, SVGF_MODULATE_TAA) = range(5)
 SVGF_IS_FIRST_FRAME, SVGF_ENABLE_TEMPORAL_ACCUMULATION, SVGF_FEEDBACK_1ST, SVGF_ENABLE_TAA, SVGF_MODULATE_ALBEDO = 1, 2, 4, 8, 16
 (BUF_GBUFFER0, BUF_GBUFFER1, BUF_GBUFFER2, BUF_GBUFFER3, BUF_RNG, BUF_RESERVOIR, BUF_RESERVOIR_INFO,
  BUF_BEAUTY_ACCUM, BUF_ALBEDO_ACCUM, BUF_NORMAL_ACCUM, BUF_SVGF_LIGHTING_VARIANCE, BUF_SVGF_FINAL,
- BUF_SVGF_MOMENTS, BUF_SVGF_PREV_LIGHTING, BUF_SVGF_ALBEDO, BUF_SVGF_DEPTH) = range(16)
+ BUF_SVGF_MOMENTS, BUF_SVGF_PREV_LIGHTING, BUF_SVGF_ALBEDO, BUF_SVGF_DEPTH,
+ BUF_NRC_INFERENCE_QUERY, BUF_NRC_TERMINAL_INFO, BUF_NRC_INFERRED_RADIANCE, BUF_NRC_FRAME_CONTRIBUTION,
+ BUF_NRC_TRAIN_QUERY, BUF_NRC_TRAIN_TARGET, BUF_NRC_TRAIN_VERTEX_INFO, BUF_NRC_TRAIN_SUFFIX_TERMINAL,
+ BUF_NRC_STATE) = range(25)
 
 # logical per-pixel layout of each downloadable buffer: (numpy dtype, elements per pixel, planes)
 BUFFER_LAYOUT = {
@@ -188,7 +192,61 @@ def default_frame_params(scene, width: int, height: int) -> GfxFrameParams:
     p.svgfFlags = SVGF_ENABLE_TEMPORAL_ACCUMULATION | SVGF_FEEDBACK_1ST | SVGF_ENABLE_TAA | SVGF_MODULATE_ALBEDO
     p.taaHistoryLength = 16
     p.maxPathLength = 5
+    lo, hi = scene_aabb(scene)
+    p.sceneAabbMin = (c_f * 3)(*lo)
+    p.sceneAabbMax = (c_f * 3)(*hi)
+    p.radianceScale = 1.0
     return p
+
+
+NRC_TRAIN_BUFFER_SIZE = 2 * 65536   # shared::trainBufferSize (neural_radiance_caching_shared.h:8-9)
+NRC_TRAINING_DATA_PER_FRAME = 65536
+NRC_INVALID_VERTEX = 0x007FFFFF     # shared::invalidVertexDataIndex
+(NRC_STATE_NUM_TRAINING_DATA, NRC_STATE_TILE_SIZE, NRC_STATE_OFFSET_UNBIASED_TILE, NRC_STATE_OFFSET_TRAINING_PATH,
+ NRC_STATE_TARGET_MIN, NRC_STATE_TARGET_MAX, NRC_STATE_TARGET_AVG, NRC_STATE_NUM_INFERENCE_QUERIES) = 0, 2, 6, 7, 8, 11, 20, 26
+
+
+def nrc_num_suffixes(width: int, height: int) -> int:
+    return ((width + 3) // 4) * ((height + 3) // 4)
+
+
+def nrc_query_capacity(width: int, height: int) -> int:
+    return (width * height + nrc_num_suffixes(width, height) + 127) // 128 * 128
+
+
+def linear_buffer_layout(buffer_id: int, width: int, height: int):
+    """(numpy dtype, columns, rows) of the NRC buffers, which are linear rather than image shaped"""
+    n = width * height
+    return {
+        BUF_NRC_INFERENCE_QUERY: (np.float32, 14, nrc_query_capacity(width, height)),
+        BUF_NRC_TERMINAL_INFO: (np.uint32, 4, n),
+        BUF_NRC_INFERRED_RADIANCE: (np.float32, 3, nrc_query_capacity(width, height)),
+        BUF_NRC_FRAME_CONTRIBUTION: (np.float32, 3, n),
+        BUF_NRC_TRAIN_QUERY: (np.float32, 14, NRC_TRAIN_BUFFER_SIZE),
+        BUF_NRC_TRAIN_TARGET: (np.float32, 3, NRC_TRAIN_BUFFER_SIZE),
+        BUF_NRC_TRAIN_VERTEX_INFO: (np.uint32, 4, NRC_TRAIN_BUFFER_SIZE),
+        BUF_NRC_TRAIN_SUFFIX_TERMINAL: (np.uint32, 1, nrc_num_suffixes(width, height)),
+        BUF_NRC_STATE: (np.uint32, 1, 32),
+    }.get(buffer_id)
+
+
+def scene_aabb(scene):
+    """world-space bounds of every instanced vertex (stands in for scene.initialSceneAabb, which the reference host
+    accumulates from transformed group boxes, neural_radiance_caching_main.cpp:1096)"""
+    cached = getattr(scene, "_aabb_cache", None)
+    if cached is not None:
+        return cached
+    lo = np.full(3, np.inf, dtype=np.float32)
+    hi = np.full(3, -np.inf, dtype=np.float32)
+    for inst in scene.instances:
+        m = np.asarray(inst.transform, dtype=np.float32).reshape(3, 4)
+        for slot in inst.mesh_slots:
+            v = np.asarray(scene.meshes[slot].positions, dtype=np.float32).reshape(-1, 3)
+            w = (v @ m[:, :3].T + m[:, 3]).astype(np.float32)
+            lo = np.minimum(lo, w.min(axis=0))
+            hi = np.maximum(hi, w.max(axis=0))
+    scene._aabb_cache = ([float(x) for x in lo], [float(x) for x in hi])
+    return scene._aabb_cache
 
 
 _DECLS = {
@@ -218,6 +276,12 @@ _DECLS = {
     "gfx_restir_launch": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxFrameParams), C.c_int]),
     "gfx_svgf_launch": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxFrameParams), C.c_int, c_u32]),
     "gfx_pathtrace_launch": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxFrameParams), C.c_int]),
+    "gfx_nrc_preprocess": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxFrameParams), c_u32, c_u32, C.c_int]),
+    "gfx_nrc_frame_infer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gfx_nrc_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxFrameParams)]),
+    "gfx_nrc_propagate": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxFrameParams)]),
+    "gfx_nrc_shuffle": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxFrameParams)]),
+    "gfx_nrc_frame_train": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]),
     "gfx_nrc_create": (C.c_int, [C.c_void_p, c_u32, c_f, C.POINTER(C.c_void_p)]),
     "gfx_nrc_destroy": (None, [C.c_void_p]),
     "gfx_nrc_infer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_u32]),

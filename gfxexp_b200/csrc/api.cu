@@ -34,6 +34,13 @@ void FrameState::release() {
     cudaFree(stats); cudaFree(rng); cudaFree(beauty); cudaFree(albedo); cudaFree(normal); cudaFree(neighborDeltas);
     cudaFree(svgfPrevLighting); cudaFree(svgfAlbedo); cudaFree(svgfPrevScreenPos);
     cudaFree(ptAlphaPdf); cudaFree(ptRadiance); cudaFree(ptExtHits); cudaFree(ptShadowPending); cudaFree(ptCounters);
+    cudaFree(nrc.inferenceQuery); cudaFree(nrc.terminalInfo); cudaFree(nrc.inferredRadiance); cudaFree(nrc.frameContribution);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(nrc.trainQuery[i]); cudaFree(nrc.trainTarget[i]);
+    }
+    cudaFree(nrc.trainVertexInfo); cudaFree(nrc.suffixTerminal); cudaFree(nrc.shufflers); cudaFree(nrc.state);
+    cudaFree(nrc.pathA); cudaFree(nrc.pathB); cudaFree(nrc.shadowPending2); cudaFree(nrc.tilePrev); cudaFree(nrc.tileSuffixEnded);
+    cudaFree(nrc.stagedFlags); cudaFree(nrc.stagedIndex); cudaFree(nrc.stagedQuery); cudaFree(nrc.stagedThroughput); cudaFree(nrc.stagedNEE);
     *this = FrameState();
 }
 
@@ -84,6 +91,10 @@ DevFrameParams makeDevParams(const gfx_ctx* ctx, const GfxFrameParams* p) {
     d.spatialNeighborBaseIndex = p->spatialNeighborBaseIndex;
     d.y0 = p->tileOriginY;
     d.y1 = p->tileRows ? min(ctx->frame.H, p->tileOriginY + p->tileRows) : ctx->frame.H;
+    d.maxPathLength = p->maxPathLength;
+    d.sceneAabbMin = f3(p->sceneAabbMin[0], p->sceneAabbMin[1], p->sceneAabbMin[2]);
+    d.sceneAabbMax = f3(p->sceneAabbMax[0], p->sceneAabbMax[1], p->sceneAabbMax[2]);
+    d.radianceScale = p->radianceScale;
     return d;
 }
 
@@ -638,6 +649,25 @@ static void* bufferPtr(gfx_ctx* ctx, int id, uint32_t index, size_t* bytes) {
     case GFX_BUF_SVGF_DEPTH: p = F.svgfDepth[i]; b = n * 4; break;
     default: break;
     }
+    if (id >= GFX_BUF_NRC_INFERENCE_QUERY && id <= GFX_BUF_NRC_STATE) {
+        if (ensureNrcFrame(ctx) != GFX_OK) {
+            if (bytes) *bytes = 0;
+            return nullptr;
+        }
+        const FrameState::Nrc &N = F.nrc;
+        switch (id) {
+        case GFX_BUF_NRC_INFERENCE_QUERY: p = N.inferenceQuery; b = (size_t)N.queryCapacity * 56; break;
+        case GFX_BUF_NRC_TERMINAL_INFO: p = N.terminalInfo; b = n * 16; break;
+        case GFX_BUF_NRC_INFERRED_RADIANCE: p = N.inferredRadiance; b = (size_t)N.queryCapacity * 12; break;
+        case GFX_BUF_NRC_FRAME_CONTRIBUTION: p = N.frameContribution; b = n * 12; break;
+        case GFX_BUF_NRC_TRAIN_QUERY: p = N.trainQuery[i]; b = (size_t)131072 * 56; break;
+        case GFX_BUF_NRC_TRAIN_TARGET: p = N.trainTarget[i]; b = (size_t)131072 * 12; break;
+        case GFX_BUF_NRC_TRAIN_VERTEX_INFO: p = N.trainVertexInfo; b = (size_t)131072 * 16; break;
+        case GFX_BUF_NRC_TRAIN_SUFFIX_TERMINAL: p = N.suffixTerminal; b = (size_t)N.numSuffixes * 4; break;
+        case GFX_BUF_NRC_STATE: p = N.state; b = 32 * 4; break;
+        default: break;
+        }
+    }
     if (bytes) *bytes = b;
     return p;
 }
@@ -715,5 +745,27 @@ int gfx_pathtrace_launch(gfx_ctx* ctx, void* stream, const GfxFrameParams* param
         return GFX_ERR_NOT_READY;
     return launchPathTrace(ctx, (cudaStream_t)stream, params, variant);
 }
+
+int gfx_nrc_preprocess(gfx_ctx* ctx, void* stream, const GfxFrameParams* params, uint32_t offsetToSelectUnbiasedTile,
+                       uint32_t offsetToSelectTrainingPath, int isNewSequence) {
+    CHECK_CTX(ctx);
+    if (!params)
+        return GFX_ERR_INVALID_ARGUMENT;
+    if (!ctx->frame.created)
+        return GFX_ERR_NOT_READY;
+    return launchNrcPreprocess(ctx, (cudaStream_t)stream, params, offsetToSelectUnbiasedTile, offsetToSelectTrainingPath, isNewSequence);
+}
+
+static int nrcPass(gfx_ctx* ctx, void* stream, const GfxFrameParams* params, int pass) {
+    CHECK_CTX(ctx);
+    if (!params)
+        return GFX_ERR_INVALID_ARGUMENT;
+    if (!ctx->frame.created)
+        return GFX_ERR_NOT_READY;
+    return launchNrcPass(ctx, (cudaStream_t)stream, params, pass);
+}
+int gfx_nrc_accumulate(gfx_ctx* ctx, void* stream, const GfxFrameParams* params) { return nrcPass(ctx, stream, params, 0); }
+int gfx_nrc_propagate(gfx_ctx* ctx, void* stream, const GfxFrameParams* params) { return nrcPass(ctx, stream, params, 1); }
+int gfx_nrc_shuffle(gfx_ctx* ctx, void* stream, const GfxFrameParams* params) { return nrcPass(ctx, stream, params, 2); }
 
 } // extern "C"

@@ -82,6 +82,33 @@ struct FrameState {
     uint4* ptExtHits = nullptr;
     float4* ptShadowPending = nullptr;
     uint32_t* ptCounters = nullptr;
+    // NRC frame buffers (nrc_pathtrace.cu), allocated on first use; layouts in include/gfxb200.h GFX_BUF_NRC_*
+    struct Nrc {
+        uint32_t numSuffixes = 0, queryCapacity = 0;
+        float* inferenceQuery = nullptr;
+        uint4* terminalInfo = nullptr;
+        float* inferredRadiance = nullptr;
+        float* frameContribution = nullptr;
+        float* trainQuery[2] = { nullptr, nullptr };
+        float* trainTarget[2] = { nullptr, nullptr };
+        uint4* trainVertexInfo = nullptr;
+        uint32_t* suffixTerminal = nullptr;
+        uint32_t* shufflers = nullptr;
+        uint32_t* state = nullptr;          // 32 words, see GFX_BUF_NRC_STATE
+        // per-path state of the wavefront NRC path tracer (per pixel) ...
+        float4* pathA = nullptr;            // primaryPathSpread, curSqrtPathSpread, flags|pathLength, linearTileIndex
+        float4* pathB = nullptr;            // prevLocalThroughput
+        float4* shadowPending2 = nullptr;   // per shadow slot: unoccluded directContNEE, tile (or ~0)
+        // ... and per tile (one training path per tile)
+        uint32_t* tilePrev = nullptr;       // prevTrainDataIndex
+        uint32_t* tileSuffixEnded = nullptr;// trainingSuffixEndsWithCache
+        uint32_t* stagedFlags = nullptr;    // want | fromRayGen<<1 | pathLength<<8
+        uint32_t* stagedIndex = nullptr;    // index the vertex staged in this round received
+        float* stagedQuery = nullptr;       // 14 floats
+        float4* stagedThroughput = nullptr;
+        float4* stagedNEE = nullptr;
+        bool created = false;
+    } nrc;
     // SVGF state
     float4* svgfLighting[2] = { nullptr, nullptr };  // lighting rgb + variance, ping-pong
     float4* svgfMoments[2] = { nullptr, nullptr };   // first/second luminance moments + history length
@@ -131,5 +158,11 @@ int launchGBuffer(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* p);
 int launchReSTIR(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* p, int pass);
 int launchSVGF(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* p, int pass, uint32_t stage);
 int launchPathTrace(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* p, int variant);
+int launchPathTraceNrc(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* p);
+int ensurePathTraceBuffers(gfx_ctx* ctx);
+int ensureNrcFrame(gfx_ctx* ctx);
+int launchNrcPreprocess(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* p, uint32_t offsetToSelectUnbiasedTile,
+                        uint32_t offsetToSelectTrainingPath, int isNewSequence);
+int launchNrcPass(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* p, int pass); // 0 accumulate, 1 propagate, 2 shuffle
 DevFrameParams makeDevParams(const gfx_ctx* ctx, const GfxFrameParams* p);
 } // namespace gfx

@@ -251,7 +251,10 @@ constexpr uint32_t kATileBytes = kTileRows * kWidth * 2; // 16 KB: 8 K-chunks x 
 __global__ void __launch_bounds__(128) k_nrcInfer(NrcLevels levels, const __half* __restrict__ table,
                                                   const uint4* __restrict__ ummaWeights, uint32_t numHiddenLayers,
                                                   const float* __restrict__ input, float* __restrict__ output,
-                                                  uint32_t numData) {
+                                                  uint32_t numDataImm, const uint32_t* __restrict__ numDataPtr) {
+    // the batch size either comes with the launch or lives in device memory (NRC frame: W*H + #tiles, known
+    // only on the device; the reference synchronises with the host for it)
+    const uint32_t numData = numDataPtr ? *numDataPtr : numDataImm;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sA = smem;                                    // activation tile (A operand)
     uint8_t* sW = smem + kATileBytes;                      // all weight blobs (B operands)
@@ -615,6 +618,8 @@ using namespace gfx;
 
 extern "C" {
 
+int gfx_nrc_train(gfx_nrc* n, void* stream, const float* inputData, const float* targetData, uint32_t numData, float* lossOnHost);
+
 int gfx_nrc_create(gfx_ctx* ctx, uint32_t numHiddenLayers, float learningRate, gfx_nrc** out) {
     if (!ctx || !out)
         return GFX_ERR_INVALID_ARGUMENT;
@@ -685,16 +690,8 @@ int gfx_nrc_get_params(gfx_nrc* n, void* hostHalfParams, size_t bytes) {
     return GFX_OK;
 }
 
-int gfx_nrc_infer(gfx_nrc* n, void* stream, const float* inputData, float* predictionData, uint32_t numData) {
-    if (!n || (!inputData && numData) || (!predictionData && numData))
-        return GFX_ERR_INVALID_ARGUMENT;
-    if (numData & 0x7F) { // network_interface.cu:143 Assert((numData & 0x7F) == 0)
-        n->ctx->setError("gfx_nrc_infer: numData must be a multiple of 128");
-        return GFX_ERR_INVALID_ARGUMENT;
-    }
-    if (numData == 0)
-        return GFX_OK;
-    cudaStream_t s = (cudaStream_t)stream;
+static int nrcInferLaunch(gfx_nrc* n, cudaStream_t s, const float* inputData, float* predictionData, uint32_t numData,
+                          const uint32_t* numDataPtr) {
     if (n->ummaDirty) {
         k_nrcPrepWeights<<<32, 256, 0, s>>>(n->paramsEma, n->numHiddenLayers, reinterpret_cast<__half*>(n->ummaWeights));
         n->ctx->launches++;
@@ -705,13 +702,55 @@ int gfx_nrc_infer(gfx_nrc* n, void* stream, const float* inputData, float* predi
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const uint32_t numTiles = numData / kTileRows;
+    const uint32_t numTiles = numData / kTileRows; // upper bound when numDataPtr is given
     const uint32_t grid = numTiles < (uint32_t)sms * 6 ? numTiles : (uint32_t)sms * 6;
     k_nrcInfer<<<grid, 128, smem, s>>>(n->levels, n->paramsEma + n->numMatrixWeights, n->ummaWeights, n->numHiddenLayers,
-                                       inputData, predictionData, numData);
+                                       inputData, predictionData, numData, numDataPtr);
     n->ctx->launches++;
     NRC_CUDA(n, cudaGetLastError());
     return GFX_OK;
+}
+
+int gfx_nrc_infer(gfx_nrc* n, void* stream, const float* inputData, float* predictionData, uint32_t numData) {
+    if (!n || (!inputData && numData) || (!predictionData && numData))
+        return GFX_ERR_INVALID_ARGUMENT;
+    if (numData & 0x7F) { // network_interface.cu:143 Assert((numData & 0x7F) == 0)
+        n->ctx->setError("gfx_nrc_infer: numData must be a multiple of 128");
+        return GFX_ERR_INVALID_ARGUMENT;
+    }
+    if (numData == 0)
+        return GFX_OK;
+    return nrcInferLaunch(n, (cudaStream_t)stream, inputData, predictionData, numData, nullptr);
+}
+
+int gfx_nrc_frame_infer(gfx_ctx* ctx, gfx_nrc* n, void* stream) {
+    if (!ctx || !n || n->ctx != ctx)
+        return GFX_ERR_INVALID_ARGUMENT;
+    if (!ctx->frame.created)
+        return GFX_ERR_NOT_READY;
+    const int rc = ensureNrcFrame(ctx);
+    if (rc != GFX_OK)
+        return rc;
+    const FrameState::Nrc &N = ctx->frame.nrc;
+    // numInferenceQueries = pad128(W*H + #tiles) was left in the state block by gfx_nrc_preprocess
+    return nrcInferLaunch(n, (cudaStream_t)stream, N.inferenceQuery, N.inferredRadiance, N.queryCapacity, N.state + 26);
+}
+
+int gfx_nrc_frame_train(gfx_ctx* ctx, gfx_nrc* n, void* stream, float* lossOnHost) {
+    if (!ctx || !n || n->ctx != ctx)
+        return GFX_ERR_INVALID_ARGUMENT;
+    if (!ctx->frame.created)
+        return GFX_ERR_NOT_READY;
+    int rc = ensureNrcFrame(ctx);
+    if (rc != GFX_OK)
+        return rc;
+    const FrameState::Nrc &N = ctx->frame.nrc;
+    // neural_radiance_caching_main.cpp:2350-2365: four steps over quarters of the shuffled 65 536 records
+    const uint32_t batchSize = 65536 / 4;
+    for (uint32_t step = 0; step < 4 && rc == GFX_OK; ++step)
+        rc = gfx_nrc_train(n, stream, N.trainQuery[1] + (size_t)step * batchSize * 14, N.trainTarget[1] + (size_t)step * batchSize * 3,
+                           batchSize, step == 3 ? lossOnHost : nullptr);
+    return rc;
 }
 
 int gfx_nrc_train(gfx_nrc* n, void* stream, const float* inputData, const float* targetData, uint32_t numData, float* lossOnHost) {

@@ -1,0 +1,262 @@
+// pathtrace.cuh — the pieces every wavefront path tracer of this library shares (pathtrace.cu: path_tracing's
+// pathTraceBaseline; nrc_pathtrace.cu: neural_radiance_caching's pathTraceNRC): surface-point reconstruction
+// (computeSurfacePoint<>, path_tracing_shared.h:484-621 and its copies in the other *_shared.h), the vertex
+// shading step = next event estimation + BSDF sampling (optix_pathtracing_kernels.cu:18-71, 136-146, 283-299),
+// compacted ray queues and the writers of the persistent trace kernel.
+#pragma once
+#include "wavefront.cuh"
+#include "lighting.cuh"
+#include "context.h"
+
+namespace gfx {
+
+constexpr uint32_t kMaxPathRounds = 64;
+
+struct DevPathState {
+    float4* alphaPdf;      // per pixel: alpha.rgb, prevDirPDensity
+    float4* radiance;      // per pixel: contribution.rgb
+    float4* extRays[2];    // per slot: (org, tmin) (dir, tmax)
+    uint32_t* extPixel[2]; // per slot: pixel index
+    uint4* extHits;        // per slot: geomIndex, primIndex, bcB, bcC
+    float4* shadowRays;    // per slot
+    uint32_t* shadowPixel; // per slot
+    float4* shadowPending; // per slot: alpha * NEE value if unoccluded, w = scale (misWeight / areaPDensity)
+    uint32_t* counters;    // per round: extCount, extFetch, shadowCount, shadowFetch
+};
+
+DevPathState makePathState(const gfx_ctx* ctx); // pathtrace.cu
+
+struct SurfacePoint {
+    f3 positionInWorld, shadingNormalInWorld, texCoord0DirInWorld, geometricNormalInWorld;
+    float hypAreaPDensity;
+};
+
+struct TriangleVertices {
+    f3 pA, pB, pC, nA, nB, nC, tA, tB, tC;
+};
+GFX_D TriangleVertices fetchTriangle(const DevScene &s, const DevMesh &mesh, uint32_t primIndex) {
+    const uint4 tri = __ldg(s.triangles + mesh.triBase + primIndex);
+    const float4* vA = s.vertices + 3 * (size_t)(mesh.vertexBase + tri.x);
+    const float4* vB = s.vertices + 3 * (size_t)(mesh.vertexBase + tri.y);
+    const float4* vC = s.vertices + 3 * (size_t)(mesh.vertexBase + tri.z);
+    const float4 a0 = __ldg(vA), a1 = __ldg(vA + 1), a2 = __ldg(vA + 2);
+    const float4 b0 = __ldg(vB), b1 = __ldg(vB + 1), b2 = __ldg(vB + 2);
+    const float4 c0 = __ldg(vC), c1 = __ldg(vC + 1), c2 = __ldg(vC + 2);
+    TriangleVertices t;
+    t.pA = f3(a0.x, a0.y, a0.z); t.pB = f3(b0.x, b0.y, b0.z); t.pC = f3(c0.x, c0.y, c0.z);
+    t.nA = f3(a1.x, a1.y, a1.z); t.nB = f3(b1.x, b1.y, b1.z); t.nC = f3(c1.x, c1.y, c1.z);
+    t.tA = f3(a2.x, a2.y, a2.z); t.tB = f3(b2.x, b2.y, b2.z); t.tC = f3(c2.x, c2.y, c2.z);
+    return t;
+}
+
+// path_tracing_shared.h:582-621 (first hit, from GBuffer0's quantised barycentrics)
+GFX_D void computeSurfacePointFromGBuffer(const DevScene &s, const DevInstance* inst, const DevMesh &mesh,
+                                          uint32_t primIndex, float bcB, float bcC, SurfacePoint* sp) {
+    const TriangleVertices t = fetchTriangle(s, mesh, primIndex);
+    const float bcA = 1 - (bcB + bcC);
+    const f3 positionInObj = bcA * t.pA + bcB * t.pB + bcC * t.pC;
+    sp->positionInWorld = xfmPoint(inst->transform, positionInObj);
+    sp->geometricNormalInWorld = normalize(mul3x3(inst->normalMatrix, cross(t.pB - t.pA, t.pC - t.pA)));
+    const f3 shadingNormalInObj = bcA * t.nA + bcB * t.nB + bcC * t.nC;
+    const f3 texCoord0DirInObj = bcA * t.tA + bcB * t.tB + bcC * t.tC;
+    sp->shadingNormalInWorld = normalize(mul3x3(inst->normalMatrix, shadingNormalInObj));
+    sp->texCoord0DirInWorld = xfmVector(inst->transform, texCoord0DirInObj);
+    sp->texCoord0DirInWorld = normalize(
+        sp->texCoord0DirInWorld - dot(sp->shadingNormalInWorld, sp->texCoord0DirInWorld) * sp->shadingNormalInWorld);
+    if (!allFinite(sp->shadingNormalInWorld)) {
+        sp->geometricNormalInWorld = f3(0, 0, 1);
+        sp->shadingNormalInWorld = f3(0, 0, 1);
+        sp->texCoord0DirInWorld = f3(1, 0, 0);
+    }
+    if (!allFinite(sp->texCoord0DirInWorld)) {
+        f3 bitangent;
+        makeCoordinateSystem(sp->shadingNormalInWorld, &sp->texCoord0DirInWorld, &bitangent);
+    }
+    sp->hypAreaPDensity = 0.0f;
+}
+
+// path_tracing_shared.h:484-580 with computeHypotheticalAreaPDensity = true, useSolidAngleSampling = false
+GFX_D void computeSurfacePointAtHit(const DevScene &s, const DevInstance* inst, const DevMesh &mesh,
+                                    uint32_t primIndex, float bcB, float bcC, SurfacePoint* sp) {
+    const TriangleVertices t = fetchTriangle(s, mesh, primIndex);
+    const f3 pA = xfmPoint(inst->transform, t.pA);
+    const f3 pB = xfmPoint(inst->transform, t.pB);
+    const f3 pC = xfmPoint(inst->transform, t.pC);
+    const float bcA = 1 - (bcB + bcC);
+
+    sp->positionInWorld = bcA * pA + bcB * pB + bcC * pC;
+    const f3 shadingNormalInObj = bcA * t.nA + bcB * t.nB + bcC * t.nC;
+    const f3 texCoord0DirInObj = bcA * t.tA + bcB * t.tB + bcC * t.tC;
+
+    sp->geometricNormalInWorld = cross(pB - pA, pC - pA);
+    const float area = 0.5f * length(sp->geometricNormalInWorld);
+    sp->geometricNormalInWorld = sp->geometricNormalInWorld / (2 * area);
+
+    sp->shadingNormalInWorld = normalize(mul3x3(inst->normalMatrix, shadingNormalInObj));
+    sp->texCoord0DirInWorld = normalize(xfmVector(inst->transform, texCoord0DirInObj));
+    if (!allFinite(sp->shadingNormalInWorld)) {
+        sp->shadingNormalInWorld = f3(0, 0, 1);
+        sp->texCoord0DirInWorld = f3(1, 0, 0);
+    }
+    if (!allFinite(sp->texCoord0DirInWorld)) {
+        f3 bitangent;
+        makeCoordinateSystem(sp->shadingNormalInWorld, &sp->texCoord0DirInWorld, &bitangent);
+    }
+
+    // hypothetical density with which explicit light sampling would have produced this point (:535-575)
+    float lightProb = 1.0f;
+    const float instImportance = inst->geomIntegral;
+    lightProb *= (pow2f(inst->uniformScale) * instImportance) / __ldg(s.instIntegral);
+    lightProb *= mesh.primIntegral / instImportance;
+    if (!isfinite(lightProb)) {
+        sp->hypAreaPDensity = 0.0f;
+        return;
+    }
+    lightProb *= mesh.primIntegral == 0.0f ? 0.0f : __ldg(s.primWeights + mesh.triBase + primIndex) / mesh.primIntegral;
+    sp->hypAreaPDensity = lightProb / area;
+}
+
+// one slot of a compacted queue per requesting lane; one atomic per warp
+GFX_D uint32_t allocQueueSlot(uint32_t* counter, bool want, uint32_t lane) {
+    const uint32_t mask = __ballot_sync(0xFFFFFFFFu, want);
+    if (mask == 0)
+        return 0;
+    const int leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if ((int)lane == leader)
+        base = atomicAdd(counter, (uint32_t)__popc(mask));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    return base + __popc(mask & ((1u << lane) - 1u));
+}
+
+// The part of a path vertex both programs share: next event estimation (optix_pathtracing_kernels.cu:18-71)
+// and BSDF sampling of the next direction (:136-146 / :283-299).  Rays are only requested here.
+struct VertexOutput {
+    bool wantShadow, wantExtension;
+    f3 shadowDir;
+    float shadowTmax;
+    float4 pending;
+    f3 nextDir;
+    f3 alpha;
+    float dirPDensity;
+    // for the NRC training records: the NEE estimate without the path throughput (directContNEE) as it is if no
+    // shadow ray was requested or the ray turns out occluded, and as it is if the ray turns out unoccluded
+    f3 directContNEE, neeUnoccluded;
+    f3 localThroughput;
+};
+
+GFX_D void shadeVertex(const DevScene &s, const f3 &positionInWorld, const f3 &vOutLocal, const ReferenceFrame &shadingFrame,
+                       const BSDF &bsdf, PCG32RNG &rng, f3 alpha, f3* radiance, VertexOutput* out) {
+    // ---- next event estimation
+    out->wantShadow = false;
+    out->directContNEE = f3(0.0f);
+    out->neeUnoccluded = f3(0.0f);
+    {
+        const float uLight = rng.getFloat0cTo1o();
+        const float u0 = rng.getFloat0cTo1o();
+        const float u1 = rng.getFloat0cTo1o();
+        LightSample lightSample;
+        float areaPDensity = 0.0f;
+        sampleLight(s, uLight, u0, u1, &lightSample, &areaPDensity);
+        if (areaPDensity > 0.0f) {
+            f3 shadowRay = lightSample.position - positionInWorld;
+            const float dist2 = sqLength(shadowRay);
+            const float dist = sqrtf(dist2);
+            shadowRay /= dist;
+            const f3 vInLocal = shadingFrame.toLocal(shadowRay);
+            const float lpCos = fabsf(dot(shadowRay, lightSample.normal));
+            float bsdfPDensity = bsdf.evaluatePDF(vOutLocal, vInLocal) * lpCos / dist2;
+            if (!isfinite(bsdfPDensity))
+                bsdfPDensity = 0.0f;
+            const float lightPDensity = areaPDensity;
+            const float misWeight = pow2f(lightPDensity) / (pow2f(bsdfPDensity) + pow2f(lightPDensity));
+            const float scale = misWeight / areaPDensity;
+            // performDirectLighting<.., true> = visibility * value; the ray is only needed when value != 0
+            const f3 value = performDirectLighting<false>(s, positionInWorld, vOutLocal, shadingFrame, bsdf, lightSample);
+            const f3 nee = value * scale;
+            const f3 unoccluded = alpha * nee;
+            out->neeUnoccluded = nee;
+            if (value.x == 0.0f && value.y == 0.0f && value.z == 0.0f) {
+                *radiance += unoccluded; // 0 (or NaN for a non-finite scale) whatever the visibility
+                out->directContNEE = nee;
+            }
+            else {
+                out->directContNEE = f3(0.0f) * scale;
+                out->wantShadow = true;
+                out->shadowDir = shadowRay;
+                out->shadowTmax = dist * 0.9999f;
+                out->pending = make_float4(unoccluded.x, unoccluded.y, unoccluded.z, scale);
+            }
+        }
+    }
+    // ---- next direction
+    f3 vInLocal;
+    float dirPDensity;
+    const float uDir0 = rng.getFloat0cTo1o();
+    const float uDir1 = rng.getFloat0cTo1o();
+    out->localThroughput = bsdf.sampleThroughput(vOutLocal, uDir0, uDir1, &vInLocal, &dirPDensity);
+    alpha *= out->localThroughput;
+    out->nextDir = shadingFrame.fromLocal(vInLocal);
+    out->alpha = alpha;
+    out->dirPDensity = dirPDensity;
+    // the path extension loop (:161-165) stops on an invalid sample before tracing anything
+    out->wantExtension = dirPDensity > 0.0f && isfinite(dirPDensity);
+}
+
+GFX_D void emitRays(const DevScene &s, const DevPathState &ps, uint32_t* roundCounters, uint32_t nextQueue, uint32_t lane,
+                    uint32_t pix, const f3 &positionInWorld, const VertexOutput &v, bool alive) {
+    const bool wantShadow = alive && v.wantShadow;
+    const bool wantExt = alive && v.wantExtension;
+    const uint32_t shadowSlot = allocQueueSlot(roundCounters + 2, wantShadow, lane);
+    const uint32_t extSlot = allocQueueSlot(roundCounters + 0, wantExt, lane);
+    if (wantShadow) {
+        ps.shadowRays[2 * (size_t)shadowSlot] = make_float4(positionInWorld.x, positionInWorld.y, positionInWorld.z, 0.0f);
+        ps.shadowRays[2 * (size_t)shadowSlot + 1] = make_float4(v.shadowDir.x, v.shadowDir.y, v.shadowDir.z, v.shadowTmax);
+        ps.shadowPixel[shadowSlot] = pix;
+        ps.shadowPending[shadowSlot] = v.pending;
+    }
+    if (wantExt) {
+        ps.extRays[nextQueue][2 * (size_t)extSlot] = make_float4(positionInWorld.x, positionInWorld.y, positionInWorld.z, 0.0f);
+        ps.extRays[nextQueue][2 * (size_t)extSlot + 1] = make_float4(v.nextDir.x, v.nextDir.y, v.nextDir.z, 3.402823466e+38f);
+        ps.extPixel[nextQueue][extSlot] = pix;
+    }
+    // ray statistics (frame.stats[0]): one atomic per warp
+    const uint32_t n = __popc(__ballot_sync(0xFFFFFFFFu, wantShadow)) + __popc(__ballot_sync(0xFFFFFFFFu, wantExt));
+    if (lane == 0 && n)
+        atomicAdd(s.rayCounter, (unsigned long long)n);
+}
+
+struct ExtensionHitWriter { // closest hit -> what the closest-hit program reads from OptiX (HitPointParameter::get)
+    uint4* hits;
+    template <bool ANY_HIT, bool STATS>
+    GFX_D void write(uint32_t ray, const TraversalState &st) const {
+        const Hit &h = st.best;
+        const bool isHit = h.storageIndex != 0xFFFFFFFFu;
+        hits[ray] = make_uint4(h.geomIndex, isHit ? h.primIndex : 0xFFFFFFFFu, __float_as_uint(h.bcB), __float_as_uint(h.bcC));
+    }
+};
+
+struct ShadowAccumulateWriter { // visibility * (alpha * f * Le * G * misWeight / p) of performNextEventEstimation
+    const uint32_t* shadowPixel;
+    const float4* pending;
+    float4* radiance;
+    template <bool ANY_HIT, bool STATS>
+    GFX_D void write(uint32_t ray, const TraversalState &st) const {
+        const float4 c = pending[ray];
+        const bool unoccluded = st.best.storageIndex == 0xFFFFFFFFu;
+        if (!unoccluded && isfinite(c.w))
+            return; // alpha * (0 * scale) = 0
+        float4* dst = radiance + shadowPixel[ray]; // at most one shadow ray per path and round: no race
+        float4 r = *dst;
+        if (unoccluded) {
+            r.x += c.x; r.y += c.y; r.z += c.z;
+        }
+        else {
+            const float nan = __int_as_float(0x7FC00000);
+            r.x += nan; r.y += nan; r.z += nan;
+        }
+        *dst = r;
+    }
+};
+
+} // namespace gfx

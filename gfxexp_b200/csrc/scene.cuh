@@ -122,6 +122,9 @@ struct DevFrameParams {
     uint32_t useUnbiasedEstimator, resetFlowBuffer, enableJittering;
     uint32_t currentReservoirIndex, spatialNeighborBaseIndex;
     uint32_t y0, y1; // rows owned by this rank
+    uint32_t maxPathLength;
+    f3 sceneAabbMin, sceneAabbMax;
+    float radianceScale;
 };
 
 } // namespace gfx

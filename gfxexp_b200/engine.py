@@ -158,6 +158,57 @@ class Context:
     def svgf(self, params, pass_id: int, stage: int = 0, stream=None):
         self._check(self.lib.gfx_svgf_launch(self.h, stream, C.byref(params), pass_id, stage), "gfx_svgf_launch")
 
+    # -- NRC frame (neural_radiance_caching_main.cpp:2270-2368) -------------------------------------
+    def download_linear(self, buffer_id: int, index: int = 0, stream=None) -> np.ndarray:
+        """NRC buffers (GFX_BUF_NRC_*) as [rows, cols]"""
+        dtype, cols, rows = abi.linear_buffer_layout(buffer_id, self.width, self.height)
+        arr = np.empty((rows, cols), dtype=dtype)
+        self._check(self.lib.gfx_buffer_download(self.h, stream, buffer_id, index, arr.ctypes.data, arr.nbytes),
+                    "gfx_buffer_download")
+        return arr
+
+    def nrc_preprocess(self, params, offset_unbiased_tile: int, offset_training_path: int, new_sequence: bool, stream=None):
+        self._check(self.lib.gfx_nrc_preprocess(self.h, stream, C.byref(params), offset_unbiased_tile & 0xFFFFFFFF,
+                                                offset_training_path & 0xFFFFFFFF, 1 if new_sequence else 0),
+                    "gfx_nrc_preprocess")
+
+    def nrc_frame_infer(self, net: "NeuralRadianceCache", stream=None):
+        self._check(self.lib.gfx_nrc_frame_infer(self.h, net.h, stream), "gfx_nrc_frame_infer")
+
+    def nrc_accumulate(self, params, stream=None):
+        self._check(self.lib.gfx_nrc_accumulate(self.h, stream, C.byref(params)), "gfx_nrc_accumulate")
+
+    def nrc_propagate(self, params, stream=None):
+        self._check(self.lib.gfx_nrc_propagate(self.h, stream, C.byref(params)), "gfx_nrc_propagate")
+
+    def nrc_shuffle(self, params, stream=None):
+        self._check(self.lib.gfx_nrc_shuffle(self.h, stream, C.byref(params)), "gfx_nrc_shuffle")
+
+    def nrc_frame_train(self, net: "NeuralRadianceCache", want_loss: bool = False, stream=None):
+        loss = C.c_float()
+        self._check(self.lib.gfx_nrc_frame_train(self.h, net.h, stream, C.byref(loss) if want_loss else None),
+                    "gfx_nrc_frame_train")
+        return loss.value if want_loss else None
+
+    def nrc_frame(self, net: "NeuralRadianceCache", params, frame_index: int, offsets, train: bool = True,
+                  want_loss: bool = False, stream=None):
+        """One frame of neural_radiance_caching_main.cpp:2256-2368 with useNRC: G-buffer, preprocessNRC, pathTraceNRC,
+        infer, accumulate and (when training) propagate, shuffle, 4 training steps.  `offsets` are the two
+        perFrameRng() draws of :2273-2275.  Everything is enqueued on `stream`; nothing synchronises with the host
+        unless the loss is requested."""
+        params.frameIndex = frame_index
+        params.bufferIndex = frame_index % 2
+        self.gbuffer(params, stream)
+        self.nrc_preprocess(params, offsets[0], offsets[1], frame_index == 0, stream)
+        self.pathtrace(params, abi.PT_NRC, stream)
+        self.nrc_frame_infer(net, stream)
+        self.nrc_accumulate(params, stream)
+        if train:
+            self.nrc_propagate(params, stream)
+            self.nrc_shuffle(params, stream)
+            return self.nrc_frame_train(net, want_loss, stream)
+        return None
+
 
 class NeuralRadianceCache:
     """Mirror of the reference's NeuralRadianceCache facade (neural_radiance_caching/network_interface.h:14-28):

@@ -190,6 +190,12 @@ typedef struct GfxFrameParams {
     /* path tracers (path_tracing_shared.h PerFramePipelineLaunchParameters::maxPathLength; 5 by default,
      * path_tracing_main.cpp:1555) */
     uint32_t maxPathLength;
+    /* NRC / ReGIR: scene.initialSceneAabb (neural_radiance_caching_main.cpp:1096,1139; regir_main.cpp:1012), the
+     * box positions are normalised to, and PerFramePipelineLaunchParameters::radianceScale (10^log10RadianceScale,
+     * neural_radiance_caching_main.cpp:2241) */
+    float sceneAabbMin[3];
+    float sceneAabbMax[3];
+    float radianceScale;
 } GfxFrameParams;
 
 typedef enum GfxSVGFFlags {
@@ -212,7 +218,9 @@ typedef enum GfxReSTIRPass {
 
 /* path tracer entry points (path_tracing/path_tracing_main.cpp:52-57 PathTracingEntryPoint) */
 typedef enum GfxPathTraceVariant {
-    GFX_PT_BASELINE = 0                         /* pathTraceBaseline */
+    GFX_PT_BASELINE = 0,                        /* pathTraceBaseline */
+    GFX_PT_NRC = 1                              /* pathTraceNRC (neural_radiance_caching_main.cpp:2281-2289):
+                                                 * needs gfx_nrc_preprocess first; fills the NRC buffers below */
 } GfxPathTraceVariant;
 
 /* SVGF entry points (svgf/svgf_main.cpp:2127-2172) */
@@ -241,7 +249,20 @@ typedef enum GfxBufferId {
     GFX_BUF_SVGF_MOMENTS = 12,  /* float x4 : firstMoment, secondMoment, sampleInfo(u32), 0 */
     GFX_BUF_SVGF_PREV_LIGHTING = 13, /* float x4 : prevNoisyLightingBuffer */
     GFX_BUF_SVGF_ALBEDO = 14,   /* float x4 : dhReflectance */
-    GFX_BUF_SVGF_DEPTH = 15     /* float : GL-style depth, background 1.0 */
+    GFX_BUF_SVGF_DEPTH = 15,    /* float : GL-style depth, background 1.0 */
+    /* NRC frame buffers (neural_radiance_caching_shared.h:258-279); linear, not image shaped.
+     * numSuffixes = ceil(W/4) * ceil(H/4) (= W*H/16 of neural_radiance_caching_main.cpp:1151 for multiples of 4) */
+    GFX_BUF_NRC_INFERENCE_QUERY = 16,   /* float x14 RadianceQuery x pad128(W*H + numSuffixes) */
+    GFX_BUF_NRC_TERMINAL_INFO = 17,     /* uint32 x4 x W*H : alpha rgb (float bits), hasQuery | pathLength<<1 | isTrainingPixel<<9 | isUnbiasedTile<<10 */
+    GFX_BUF_NRC_INFERRED_RADIANCE = 18, /* float x3 x pad128(W*H + numSuffixes) */
+    GFX_BUF_NRC_FRAME_CONTRIBUTION = 19,/* float x3 x W*H : perFrameContributionBuffer */
+    GFX_BUF_NRC_TRAIN_QUERY = 20,       /* [2] float x14 x 131072 : [0] path tracer output, [1] shuffled */
+    GFX_BUF_NRC_TRAIN_TARGET = 21,      /* [2] float x3 x 131072 */
+    GFX_BUF_NRC_TRAIN_VERTEX_INFO = 22, /* uint32 x4 x 131072 : localThroughput rgb, prevVertexDataIndex | pathLength<<23 */
+    GFX_BUF_NRC_TRAIN_SUFFIX_TERMINAL = 23, /* uint32 x numSuffixes : prevVertexDataIndex | hasQuery<<23 | pathLength<<24 */
+    GFX_BUF_NRC_STATE = 24              /* uint32 x32 : numTrainingData[2], tileSize[2][2], offsetToSelectUnbiasedTile,
+                                         * offsetToSelectTrainingPath, targetMin/Max (ordered ints) [2][2][3] at 8,
+                                         * targetAvg [2][3] at 20, numInferenceQueries at 26 */
 } GfxBufferId;
 
 /* ---- context ------------------------------------------------------------------------- */
@@ -322,6 +343,22 @@ int gfx_nrc_train(gfx_nrc* nrc, void* stream, const float* inputData, const floa
 int gfx_nrc_get_params(gfx_nrc* nrc, void* hostHalfParams, size_t bytes);
 int gfx_nrc_set_params(gfx_nrc* nrc, const void* hostHalfParams, size_t bytes);
 uint32_t gfx_nrc_num_params(gfx_nrc* nrc);
+
+/* ---- NRC frame: the launches around gfx_pathtrace_launch(GFX_PT_NRC) (neural_radiance_caching_main.cpp:2270-2368).
+ * Buffers live in the frame (GFX_BUF_NRC_*); nothing in the sequence reads back to the host. ------------- */
+/* replaces kernelPreprocessNRC (:2270-2276; nrc_setup_kernels.cu:6-49): tile-size controller, training-suffix reset */
+int gfx_nrc_preprocess(gfx_ctx* ctx, void* stream, const GfxFrameParams* params, uint32_t offsetToSelectUnbiasedTile,
+                       uint32_t offsetToSelectTrainingPath, int isNewSequence);
+/* replaces neuralRadianceCache.infer on inferenceRadianceQueryBuffer (:2309-2316); the query count
+ * pad128(W*H + #tiles) is read from device memory instead of synchronising with the host (:2291-2304) */
+int gfx_nrc_frame_infer(gfx_ctx* ctx, gfx_nrc* nrc, void* stream);
+/* replaces kernelAccumulateInferredRadianceValues / kernelPropagateRadianceValues / kernelShuffleTrainingData
+ * (:2320-2348; nrc_setup_kernels.cu:51-92, 94-138, 140-216) */
+int gfx_nrc_accumulate(gfx_ctx* ctx, void* stream, const GfxFrameParams* params);
+int gfx_nrc_propagate(gfx_ctx* ctx, void* stream, const GfxFrameParams* params);
+int gfx_nrc_shuffle(gfx_ctx* ctx, void* stream, const GfxFrameParams* params);
+/* replaces the four neuralRadianceCache.train steps on quarters of the shuffled records (:2350-2365) */
+int gfx_nrc_frame_train(gfx_ctx* ctx, gfx_nrc* nrc, void* stream, float* lossOnHost);
 
 #ifdef __cplusplus
 }

@@ -66,6 +66,13 @@ void orc_gbuffer(orc_frame* f, const GfxFrameParams* p, int numThreads);
 void orc_restir(orc_frame* f, const GfxFrameParams* p, int pass, int numThreads);
 /* unidirectional path tracer (GfxPathTraceVariant); returns the number of rays traced */
 uint64_t orc_pathtrace(orc_frame* f, const GfxFrameParams* p, int variant, int numThreads);
+/* NRC bookkeeping kernels (nrc_setup_kernels.cu): preprocessNRC, accumulateInferredRadianceValues,
+ * propagateRadianceValues, shuffleTrainingData; buffers via orc_buffer_ptr(GFX_BUF_NRC_*) */
+void orc_nrc_preprocess(orc_frame* f, const GfxFrameParams* p, uint32_t offsetToSelectUnbiasedTile,
+                        uint32_t offsetToSelectTrainingPath, int isNewSequence);
+void orc_nrc_accumulate(orc_frame* f, const GfxFrameParams* p);
+void orc_nrc_propagate(orc_frame* f, const GfxFrameParams* p);
+void orc_nrc_shuffle(orc_frame* f, const GfxFrameParams* p);
 /* primary rays of the G-buffer pass (for the trace-only benchmarks) */
 void orc_generate_primary_rays(const GfxFrameParams* p, uint32_t width, uint32_t height, GfxRay* rays);
 

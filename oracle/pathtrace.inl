@@ -250,9 +250,12 @@ static void pathTracePixel(orc_frame* f, const GfxFrameParams* p, const Camera &
     f->beauty[pix] = F4{ colorResult.x, colorResult.y, colorResult.z, 1.0f };
 }
 
+static uint64_t nrcPathTrace(orc_frame* f, const GfxFrameParams* p, int numThreads); // nrc_pathtrace.inl
+
 extern "C" uint64_t orc_pathtrace(orc_frame* f, const GfxFrameParams* p, int variant, int numThreads) {
     if (numThreads <= 0) numThreads = omp_get_max_threads();
-    (void)variant; // GFX_PT_BASELINE only
+    if (variant == GFX_PT_NRC)
+        return nrcPathTrace(f, p, numThreads);
     const Camera camera = makeCamera(p->camera);
     const uint32_t W = f->W, H = f->H;
     const uint32_t y0 = p->tileOriginY, y1 = p->tileRows ? std::min(H, p->tileOriginY + p->tileRows) : H;

@@ -375,6 +375,7 @@ struct orc_frame {
     std::vector<GB1> reservoirInfo[2]; // recPDFEstimate, targetDensity
     std::vector<F4> beauty, albedo, normal;
     std::vector<float2> neighborDeltas;
+    struct orc_nrc_frame* nrc = nullptr; // NRC buffers, created on first use (nrc_pathtrace.inl)
 };
 
 extern "C" orc_frame* orc_frame_create(orc_scene* s, uint32_t W, uint32_t H) {
@@ -397,7 +398,12 @@ extern "C" orc_frame* orc_frame_create(orc_scene* s, uint32_t W, uint32_t H) {
     f->normal.assign(n, F4{ 0, 0, 0, 0 });
     return f;
 }
-extern "C" void orc_frame_destroy(orc_frame* f) { delete f; }
+static void nrcFrameDestroy(struct orc_nrc_frame* n);
+extern "C" void orc_frame_destroy(orc_frame* f) {
+    if (f->nrc)
+        nrcFrameDestroy(f->nrc);
+    delete f;
+}
 
 extern "C" void orc_rng_seed(orc_frame* f, uint64_t seed) { // restir_di_main.cpp:1309-1321
     std::mt19937_64 rngSeed(seed);
@@ -443,6 +449,7 @@ extern "C" void orc_restir_setup_neighbor_table(orc_frame* f) { // restir_di_mai
     }
 }
 
+static void* nrcBufferPtr(orc_frame* f, int id, uint32_t index, size_t* bytes);
 extern "C" void* orc_buffer_ptr(orc_frame* f, int id, uint32_t index, size_t* bytes) {
     const size_t n = (size_t)f->W * f->H;
     void* p = nullptr;
@@ -458,7 +465,7 @@ extern "C" void* orc_buffer_ptr(orc_frame* f, int id, uint32_t index, size_t* by
     case GFX_BUF_BEAUTY_ACCUM: p = f->beauty.data(); b = n * 16; break;
     case GFX_BUF_ALBEDO_ACCUM: p = f->albedo.data(); b = n * 16; break;
     case GFX_BUF_NORMAL_ACCUM: p = f->normal.data(); b = n * 16; break;
-    default: break;
+    default: return nrcBufferPtr(f, id, index, bytes);
     }
     if (bytes) *bytes = b;
     return p;
@@ -1216,3 +1223,4 @@ extern "C" void orc_restir(orc_frame* f, const GfxFrameParams* p, int pass, int 
 // path tracing (path_tracing/gpu_kernels/optix_pathtracing_kernels.cu)
 // ---------------------------------------------------------------------------------------
 #include "pathtrace.inl"
+#include "nrc_pathtrace.inl"

@@ -74,6 +74,9 @@ def lib() -> C.CDLL:
         L.orc_restir.argtypes = [vp, C.POINTER(abi.GfxFrameParams), C.c_int, C.c_int]
         L.orc_pathtrace.argtypes = [vp, C.POINTER(abi.GfxFrameParams), C.c_int, C.c_int]
         L.orc_pathtrace.restype = C.c_uint64
+        L.orc_nrc_preprocess.argtypes = [vp, C.POINTER(abi.GfxFrameParams), C.c_uint32, C.c_uint32, C.c_int]
+        for name in ("orc_nrc_accumulate", "orc_nrc_propagate", "orc_nrc_shuffle"):
+            getattr(L, name).argtypes = [vp, C.POINTER(abi.GfxFrameParams)]
         L.orc_generate_primary_rays.argtypes = [C.POINTER(abi.GfxFrameParams), C.c_uint32, C.c_uint32, vp]
         L.orc_svgf_create.restype = vp
         L.orc_svgf_create.argtypes = [vp, C.c_uint32, C.c_uint32]
@@ -195,6 +198,30 @@ class OracleFrame:
     def pathtrace(self, params, variant: int = 0, threads: int = 0) -> int:
         """one sample per pixel of the path tracer; returns the number of rays traced"""
         return int(lib().orc_pathtrace(self.h, C.byref(params), variant, threads))
+
+
+    # -- NRC frame (nrc_setup_kernels.cu) -----------------------------------------------------------
+    def linear_buffer(self, buffer_id: int, index: int = 0, copy: bool = True) -> np.ndarray:
+        """NRC buffers (GFX_BUF_NRC_*) as [rows, cols]; copy=False returns a writable view of the oracle's memory"""
+        nbytes = C.c_size_t()
+        ptr = lib().orc_buffer_ptr(self.h, buffer_id, index, C.byref(nbytes))
+        dtype, cols, rows = abi.linear_buffer_layout(buffer_id, self.W, self.H)
+        assert nbytes.value == rows * cols * np.dtype(dtype).itemsize, (buffer_id, nbytes.value, rows, cols)
+        raw = (C.c_uint8 * nbytes.value).from_address(ptr)
+        arr = np.frombuffer(raw, dtype=dtype).reshape(rows, cols)
+        return arr.copy() if copy else arr
+
+    def nrc_preprocess(self, params, offset_unbiased_tile: int, offset_training_path: int, new_sequence: bool):
+        lib().orc_nrc_preprocess(self.h, C.byref(params), offset_unbiased_tile, offset_training_path, 1 if new_sequence else 0)
+
+    def nrc_accumulate(self, params):
+        lib().orc_nrc_accumulate(self.h, C.byref(params))
+
+    def nrc_propagate(self, params):
+        lib().orc_nrc_propagate(self.h, C.byref(params))
+
+    def nrc_shuffle(self, params):
+        lib().orc_nrc_shuffle(self.h, C.byref(params))
 
 
 class OracleSvgf:
