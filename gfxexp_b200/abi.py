@@ -62,7 +62,9 @@ class GfxFrameParams(C.Structure):
                 ("currentReservoirIndex", c_u32), ("spatialNeighborBaseIndex", c_u32),
                 ("tileOriginY", c_u32), ("tileRows", c_u32), ("svgfFlags", c_u32), ("taaHistoryLength", c_u32),
                 ("maxPathLength", c_u32),
-                ("sceneAabbMin", c_f * 3), ("sceneAabbMax", c_f * 3), ("radianceScale", c_f)]
+                ("sceneAabbMin", c_f * 3), ("sceneAabbMax", c_f * 3), ("radianceScale", c_f),
+                ("regirGridDim", c_u32 * 3), ("regirLog2NumCandidatesPerLightSlot", c_u32),
+                ("regirLog2NumCandidatesPerCell", c_u32), ("regirEnableCellRandomization", c_u32)]
 
 
 NODE_DTYPE = np.dtype([("quantBoxOrigin", np.float32, 3), ("quantBoxExpScale", np.uint8, 3),
@@ -79,7 +81,7 @@ assert NODE_DTYPE.itemsize == 80 and TRI_DTYPE.itemsize == 48 and HIT_DTYPE.item
 
 # enums
 TRACE_CLOSEST, TRACE_ANY, TRACE_STATS = 0, 1, 2
-PT_BASELINE, PT_NRC = 0, 1  # GfxPathTraceVariant
+PT_BASELINE, PT_NRC, PT_REGIR = 0, 1, 2  # GfxPathTraceVariant
 (RESTIR_INITIAL_RIS, RESTIR_INITIAL_AND_TEMPORAL_BIASED, RESTIR_INITIAL_AND_TEMPORAL_UNBIASED,
  RESTIR_SPATIAL_BIASED, RESTIR_SPATIAL_UNBIASED, RESTIR_SHADING) = range(6)
 (SVGF_TEMPORAL_ACCUMULATE, SVGF_ESTIMATE_VARIANCE, SVGF_ATROUS, SVGF_FILL_BACKGROUND, SVGF_MODULATE_TAA) = range(5)
@@ -89,7 +91,8 @@ SVGF_IS_FIRST_FRAME, SVGF_ENABLE_TEMPORAL_ACCUMULATION, SVGF_FEEDBACK_1ST, SVGF_
  BUF_SVGF_MOMENTS, BUF_SVGF_PREV_LIGHTING, BUF_SVGF_ALBEDO, BUF_SVGF_DEPTH,
  BUF_NRC_INFERENCE_QUERY, BUF_NRC_TERMINAL_INFO, BUF_NRC_INFERRED_RADIANCE, BUF_NRC_FRAME_CONTRIBUTION,
  BUF_NRC_TRAIN_QUERY, BUF_NRC_TRAIN_TARGET, BUF_NRC_TRAIN_VERTEX_INFO, BUF_NRC_TRAIN_SUFFIX_TERMINAL,
- BUF_NRC_STATE) = range(25)
+ BUF_NRC_STATE, BUF_REGIR_SLOTS, BUF_REGIR_SLOT_RNG, BUF_REGIR_CELL_ACCESSES, BUF_REGIR_LAST_ACCESS,
+ BUF_REGIR_NUM_ACTIVE_CELLS) = range(30)
 
 # logical per-pixel layout of each downloadable buffer: (numpy dtype, elements per pixel, planes)
 BUFFER_LAYOUT = {
@@ -196,6 +199,10 @@ def default_frame_params(scene, width: int, height: int) -> GfxFrameParams:
     p.sceneAabbMin = (c_f * 3)(*lo)
     p.sceneAabbMax = (c_f * 3)(*hi)
     p.radianceScale = 1.0
+    p.regirGridDim = (c_u32 * 3)(32, 8, 32)
+    p.regirLog2NumCandidatesPerLightSlot = 3
+    p.regirLog2NumCandidatesPerCell = 2
+    p.regirEnableCellRandomization = 1
     return p
 
 
@@ -214,9 +221,21 @@ def nrc_query_capacity(width: int, height: int) -> int:
     return (width * height + nrc_num_suffixes(width, height) + 127) // 128 * 128
 
 
-def linear_buffer_layout(buffer_id: int, width: int, height: int):
-    """(numpy dtype, columns, rows) of the NRC buffers, which are linear rather than image shaped"""
+REGIR_SLOTS_PER_CELL = 512  # shared::kNumLightSlotsPerCell
+
+
+def linear_buffer_layout(buffer_id: int, width: int, height: int, params=None):
+    """(numpy dtype, columns, rows) of the NRC / ReGIR buffers, which are linear rather than image shaped"""
     n = width * height
+    if BUF_REGIR_SLOTS <= buffer_id <= BUF_REGIR_NUM_ACTIVE_CELLS:
+        dim = [int(d) for d in params.regirGridDim] if params is not None else [32, 8, 32]
+        if 0 in dim:
+            dim = [32, 8, 32]
+        cells = dim[0] * dim[1] * dim[2]
+        return {BUF_REGIR_SLOTS: (np.uint32, 16, cells * REGIR_SLOTS_PER_CELL),
+                BUF_REGIR_SLOT_RNG: (np.uint64, 1, cells * REGIR_SLOTS_PER_CELL),
+                BUF_REGIR_CELL_ACCESSES: (np.uint32, 1, cells), BUF_REGIR_LAST_ACCESS: (np.uint32, 1, cells),
+                BUF_REGIR_NUM_ACTIVE_CELLS: (np.uint32, 1, 2)}[buffer_id]
     return {
         BUF_NRC_INFERENCE_QUERY: (np.float32, 14, nrc_query_capacity(width, height)),
         BUF_NRC_TERMINAL_INFO: (np.uint32, 4, n),
@@ -276,6 +295,8 @@ _DECLS = {
     "gfx_restir_launch": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxFrameParams), C.c_int]),
     "gfx_svgf_launch": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxFrameParams), C.c_int, c_u32]),
     "gfx_pathtrace_launch": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxFrameParams), C.c_int]),
+    "gfx_regir_build_cells": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxFrameParams), c_u32, C.c_int]),
+    "gfx_regir_update_access": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxFrameParams), c_u32]),
     "gfx_nrc_preprocess": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxFrameParams), c_u32, c_u32, C.c_int]),
     "gfx_nrc_frame_infer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "gfx_nrc_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxFrameParams)]),

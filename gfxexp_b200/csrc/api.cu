@@ -34,6 +34,8 @@ void FrameState::release() {
     cudaFree(stats); cudaFree(rng); cudaFree(beauty); cudaFree(albedo); cudaFree(normal); cudaFree(neighborDeltas);
     cudaFree(svgfPrevLighting); cudaFree(svgfAlbedo); cudaFree(svgfPrevScreenPos);
     cudaFree(ptAlphaPdf); cudaFree(ptRadiance); cudaFree(ptExtHits); cudaFree(ptShadowPending); cudaFree(ptCounters);
+    cudaFree(regir.slots[0]); cudaFree(regir.slots[1]); cudaFree(regir.slotRngs); cudaFree(regir.perCellNumAccesses);
+    cudaFree(regir.lastAccessFrameIndices); cudaFree(regir.numActiveCells);
     cudaFree(nrc.inferenceQuery); cudaFree(nrc.terminalInfo); cudaFree(nrc.inferredRadiance); cudaFree(nrc.frameContribution);
     for (int i = 0; i < 2; ++i) {
         cudaFree(nrc.trainQuery[i]); cudaFree(nrc.trainTarget[i]);
@@ -668,6 +670,17 @@ static void* bufferPtr(gfx_ctx* ctx, int id, uint32_t index, size_t* bytes) {
         default: break;
         }
     }
+    if (id >= GFX_BUF_REGIR_SLOTS && id <= GFX_BUF_REGIR_NUM_ACTIVE_CELLS && F.regir.created) {
+        const FrameState::Regir &R = F.regir;
+        switch (id) {
+        case GFX_BUF_REGIR_SLOTS: p = R.slots[i]; b = (size_t)R.numSlots * 64; break;
+        case GFX_BUF_REGIR_SLOT_RNG: p = R.slotRngs; b = (size_t)R.numSlots * 8; break;
+        case GFX_BUF_REGIR_CELL_ACCESSES: p = R.perCellNumAccesses; b = (size_t)R.numCells * 4; break;
+        case GFX_BUF_REGIR_LAST_ACCESS: p = R.lastAccessFrameIndices; b = (size_t)R.numCells * 4; break;
+        case GFX_BUF_REGIR_NUM_ACTIVE_CELLS: p = R.numActiveCells; b = 8; break;
+        default: break;
+        }
+    }
     if (bytes) *bytes = b;
     return p;
 }
@@ -744,6 +757,24 @@ int gfx_pathtrace_launch(gfx_ctx* ctx, void* stream, const GfxFrameParams* param
     if (!ctx->frame.created || !ctx->bvh.ready)
         return GFX_ERR_NOT_READY;
     return launchPathTrace(ctx, (cudaStream_t)stream, params, variant);
+}
+
+int gfx_regir_build_cells(gfx_ctx* ctx, void* stream, const GfxFrameParams* params, uint32_t frameIndex, int useTemporalReuse) {
+    CHECK_CTX(ctx);
+    if (!params)
+        return GFX_ERR_INVALID_ARGUMENT;
+    if (!ctx->frame.created)
+        return GFX_ERR_NOT_READY;
+    return launchRegirBuildCells(ctx, (cudaStream_t)stream, params, frameIndex, useTemporalReuse);
+}
+
+int gfx_regir_update_access(gfx_ctx* ctx, void* stream, const GfxFrameParams* params, uint32_t frameIndex) {
+    CHECK_CTX(ctx);
+    if (!params)
+        return GFX_ERR_INVALID_ARGUMENT;
+    if (!ctx->frame.created)
+        return GFX_ERR_NOT_READY;
+    return launchRegirUpdateAccess(ctx, (cudaStream_t)stream, params, frameIndex);
 }
 
 int gfx_nrc_preprocess(gfx_ctx* ctx, void* stream, const GfxFrameParams* params, uint32_t offsetToSelectUnbiasedTile,

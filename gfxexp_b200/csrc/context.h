@@ -109,6 +109,18 @@ struct FrameState {
         float4* stagedNEE = nullptr;
         bool created = false;
     } nrc;
+    // ReGIR grid (regir.cu), (re)allocated by gfx_regir_build_cells when the grid dimensions change
+    struct Regir {
+        uint32_t dim[3] = { 0, 0, 0 };
+        uint32_t numCells = 0, numSlots = 0;
+        float gridOrigin[3] = { 0, 0, 0 }, gridCellSize[3] = { 0, 0, 0 };
+        float4* slots[2] = { nullptr, nullptr };
+        unsigned long long* slotRngs = nullptr;
+        uint32_t* perCellNumAccesses = nullptr;
+        uint32_t* lastAccessFrameIndices = nullptr;
+        uint32_t* numActiveCells = nullptr;
+        bool created = false;
+    } regir;
     // SVGF state
     float4* svgfLighting[2] = { nullptr, nullptr };  // lighting rgb + variance, ping-pong
     float4* svgfMoments[2] = { nullptr, nullptr };   // first/second luminance moments + history length
@@ -161,6 +173,9 @@ int launchPathTrace(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* p, 
 int launchPathTraceNrc(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* p);
 int ensurePathTraceBuffers(gfx_ctx* ctx);
 int ensureNrcFrame(gfx_ctx* ctx);
+int launchRegirBuildCells(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* p, uint32_t frameIndex, int useTemporalReuse);
+int launchRegirUpdateAccess(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* p, uint32_t frameIndex);
+void releaseRegir(gfx_ctx* ctx);
 int launchNrcPreprocess(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* p, uint32_t offsetToSelectUnbiasedTile,
                         uint32_t offsetToSelectTrainingPath, int isNewSequence);
 int launchNrcPass(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* p, int pass); // 0 accumulate, 1 propagate, 2 shuffle

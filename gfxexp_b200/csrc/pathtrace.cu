@@ -24,8 +24,38 @@
 
 namespace gfx {
 
+// One path vertex: NEE + next direction.  The ReGIR variant (regir/gpu_kernels/optix_pathtracing_kernels.cu) draws its
+// light sample from the cell reservoirs and runs the length limit and a Russian roulette of the ray-generation
+// loop *before* the extension ray is traced (:254-263, `if constexpr (useReGIR || ...)`), in addition to the
+// roulette of the closest-hit program.
+template <bool REGIR>
+GFX_D void shadeVertexVariant(const DevScene &s, const DevRegir &rg, const DevFrameParams &p, const f3 &positionInWorld,
+                              const f3 &vOutLocal, const ReferenceFrame &shadingFrame, const BSDF &bsdf, PCG32RNG &rng, f3 alpha,
+                              uint32_t pathLength, f3* radiance, VertexOutput* out) {
+    if (REGIR) {
+        neeRegir(s, rg, positionInWorld, vOutLocal, shadingFrame, bsdf, rng, alpha, radiance, out);
+        sampleNextDirection(vOutLocal, shadingFrame, bsdf, rng, alpha, out);
+        if (out->wantExtension) {
+            if (pathLength + 1 >= p.maxPathLength) {
+                out->wantExtension = false;
+            }
+            else {
+                const float continueProb = fminf(sRGB_calcLuminance(out->alpha) / sRGB_calcLuminance(f3(1.0f)), 1.0f);
+                if (rng.getFloat0cTo1o() >= continueProb)
+                    out->wantExtension = false;
+                else
+                    out->alpha /= continueProb;
+            }
+        }
+    }
+    else {
+        shadeVertex(s, positionInWorld, vOutLocal, shadingFrame, bsdf, rng, alpha, radiance, out);
+    }
+}
+
 // pathTrace_rayGen_generic up to the path extension loop (:73-160)
-__global__ void __launch_bounds__(64) k_ptFirstHit(DevScene s, DevFrame f, DevFrameParams p, DevPathState ps) {
+template <bool REGIR>
+__global__ void __launch_bounds__(64) k_ptFirstHit(DevScene s, DevFrame f, DevFrameParams p, DevPathState ps, DevRegir rg) {
     const uint32_t x = blockIdx.x * 8 + threadIdx.x;
     const uint32_t y = p.y0 + blockIdx.y * 8 + threadIdx.y;
     const uint32_t lane = (threadIdx.x + threadIdx.y * blockDim.x) & 31u;
@@ -60,7 +90,7 @@ __global__ void __launch_bounds__(64) k_ptFirstHit(DevScene s, DevFrame f, DevFr
             if (vOutLocal.z > 0 && mat->hasEmittance)
                 radiance += alpha * f3(mat->emittance[0], mat->emittance[1], mat->emittance[2]) / kPi;
             const BSDF bsdf = setupBsdf(s, mesh.materialSlot);
-            shadeVertex(s, positionInWorld, vOutLocal, shadingFrame, bsdf, rng, alpha, &radiance, &v);
+            shadeVertexVariant<REGIR>(s, rg, p, positionInWorld, vOutLocal, shadingFrame, bsdf, rng, alpha, 1u, &radiance, &v);
             f.rng[pix] = rng.state;
             ps.alphaPdf[pix] = make_float4(v.alpha.x, v.alpha.y, v.alpha.z, v.dirPDensity);
             alive = true;
@@ -72,7 +102,9 @@ __global__ void __launch_bounds__(64) k_ptFirstHit(DevScene s, DevFrame f, DevFr
 
 // pathTrace_closestHit_generic (:218-300) + the bookkeeping of the path extension loop (:161-194) for the
 // compacted queue of live paths; `round` = pathLength - 2 selects the queue parity and the counters.
-__global__ void __launch_bounds__(64) k_ptBounce(DevScene s, DevFrame f, DevPathState ps, uint32_t round, uint32_t maxLengthTerminate) {
+template <bool REGIR>
+__global__ void __launch_bounds__(64) k_ptBounce(DevScene s, DevFrame f, DevFrameParams p, DevPathState ps, DevRegir rg, uint32_t round,
+                                                 uint32_t maxLengthTerminate) {
     const uint32_t curQueue = round & 1u, nextQueue = curQueue ^ 1u;
     const uint32_t* roundCounters = ps.counters + 4 * round;
     uint32_t* nextCounters = ps.counters + 4 * (round + 1);
@@ -108,6 +140,8 @@ __global__ void __launch_bounds__(64) k_ptBounce(DevScene s, DevFrame f, DevPath
                 const DevMesh mesh = s.meshes[im.y];
                 SurfacePoint sp;
                 computeSurfacePointAtHit(s, inst, mesh, hit.y, __uint_as_float(hit.z), __uint_as_float(hit.w), &sp);
+                if (REGIR) // regir's closest-hit program never computes it (uninitialised in the reference): defined as 0
+                    sp.hypAreaPDensity = 0.0f;
                 const GfxMaterialDesc* mat = s.materials + mesh.materialSlot;
 
                 const f3 vOut = normalize(-rayDir);
@@ -131,7 +165,7 @@ __global__ void __launch_bounds__(64) k_ptBounce(DevScene s, DevFrame f, DevPath
                 if (!(rng.getFloat0cTo1o() >= continueProb || maxLengthTerminate)) {
                     alpha /= continueProb;
                     const BSDF bsdf = setupBsdf(s, mesh.materialSlot);
-                    shadeVertex(s, positionInWorld, vOutLocal, shadingFrame, bsdf, rng, alpha, &radiance, &v);
+                    shadeVertexVariant<REGIR>(s, rg, p, positionInWorld, vOutLocal, shadingFrame, bsdf, rng, alpha, round + 2, &radiance, &v);
                     ps.alphaPdf[pix] = make_float4(v.alpha.x, v.alpha.y, v.alpha.z, v.dirPDensity);
                     alive = true;
                 }
@@ -199,28 +233,40 @@ DevPathState makePathState(const gfx_ctx* ctx) {
 int launchPathTrace(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* params, int variant) {
     if (variant == GFX_PT_NRC)
         return launchPathTraceNrc(ctx, stream, params);
-    if (variant != GFX_PT_BASELINE) {
+    if (variant != GFX_PT_BASELINE && variant != GFX_PT_REGIR) {
         ctx->setError("gfx_pathtrace_launch: unknown variant");
         return GFX_ERR_INVALID_ARGUMENT;
+    }
+    const bool regir = variant == GFX_PT_REGIR;
+    if (regir && !ctx->frame.regir.created) {
+        ctx->setError("gfx_pathtrace_launch(GFX_PT_REGIR): call gfx_regir_build_cells first");
+        return GFX_ERR_NOT_READY;
     }
     const int rc = ensurePathTraceBuffers(ctx);
     if (rc != GFX_OK)
         return rc;
     FrameState &F = ctx->frame;
-    const DevFrameParams p = makeDevParams(ctx, params);
+    DevFrameParams p = makeDevParams(ctx, params);
     if (p.y1 <= p.y0)
         return GFX_OK;
+    p.maxPathLength = params->maxPathLength ? params->maxPathLength : 5u; // 0 = the hosts' default
     const DevScene s = ctx->devScene();
     const DevFrame f = ctx->devFrame();
     const DevPathState ps = makePathState(ctx);
+    DevRegir rg = {};
+    if (regir)
+        rg = makeDevRegir(ctx, params);
 
-    const uint32_t maxPathLength = params->maxPathLength ? params->maxPathLength : 5u;
+    const uint32_t maxPathLength = p.maxPathLength;
     const uint32_t numRounds = min(max(maxPathLength, 2u) - 1u, kMaxPathRounds); // pathLength = 2 .. maxPathLength
     GFX_CUDA(ctx, cudaMemsetAsync(F.ptCounters, 0, (kMaxPathRounds + 1) * 16, stream));
 
     const dim3 block(8, 8);
     const dim3 grid((F.W + 7) / 8, (p.y1 - p.y0 + 7) / 8);
-    k_ptFirstHit<<<grid, block, 0, stream>>>(s, f, p, ps);
+    if (regir)
+        k_ptFirstHit<true><<<grid, block, 0, stream>>>(s, f, p, ps, rg);
+    else
+        k_ptFirstHit<false><<<grid, block, 0, stream>>>(s, f, p, ps, rg);
     ctx->launches++;
     const int traceGrid = wavefrontGrid();
     int sms = 148;
@@ -232,7 +278,10 @@ int launchPathTrace(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* par
         k_traceWavefront<true, false><<<traceGrid, 128, 0, stream>>>(s.bvh, ps.shadowRays, c + 2, 0u, c + 3, shadowWriter);
         k_traceWavefront<false, false><<<traceGrid, 128, 0, stream>>>(s.bvh, ps.extRays[round & 1], c + 0, 0u, c + 1, extWriter);
         const uint32_t maxLengthTerminate = (round + 2 >= maxPathLength || round + 1 == numRounds) ? 1u : 0u;
-        k_ptBounce<<<sms * 16, 64, 0, stream>>>(s, f, ps, round, maxLengthTerminate);
+        if (regir)
+            k_ptBounce<true><<<sms * 16, 64, 0, stream>>>(s, f, p, ps, rg, round, maxLengthTerminate);
+        else
+            k_ptBounce<false><<<sms * 16, 64, 0, stream>>>(s, f, p, ps, rg, round, maxLengthTerminate);
         ctx->launches += 3;
     }
     // the last round requests no rays (maxLengthTerminate), nothing is left in flight

@@ -145,51 +145,51 @@ struct VertexOutput {
     f3 localThroughput;
 };
 
-GFX_D void shadeVertex(const DevScene &s, const f3 &positionInWorld, const f3 &vOutLocal, const ReferenceFrame &shadingFrame,
-                       const BSDF &bsdf, PCG32RNG &rng, f3 alpha, f3* radiance, VertexOutput* out) {
-    // ---- next event estimation
+GFX_D void neeBaseline(const DevScene &s, const f3 &positionInWorld, const f3 &vOutLocal, const ReferenceFrame &shadingFrame,
+                       const BSDF &bsdf, PCG32RNG &rng, const f3 &alpha, f3* radiance, VertexOutput* out) {
     out->wantShadow = false;
     out->directContNEE = f3(0.0f);
     out->neeUnoccluded = f3(0.0f);
-    {
-        const float uLight = rng.getFloat0cTo1o();
-        const float u0 = rng.getFloat0cTo1o();
-        const float u1 = rng.getFloat0cTo1o();
-        LightSample lightSample;
-        float areaPDensity = 0.0f;
-        sampleLight(s, uLight, u0, u1, &lightSample, &areaPDensity);
-        if (areaPDensity > 0.0f) {
-            f3 shadowRay = lightSample.position - positionInWorld;
-            const float dist2 = sqLength(shadowRay);
-            const float dist = sqrtf(dist2);
-            shadowRay /= dist;
-            const f3 vInLocal = shadingFrame.toLocal(shadowRay);
-            const float lpCos = fabsf(dot(shadowRay, lightSample.normal));
-            float bsdfPDensity = bsdf.evaluatePDF(vOutLocal, vInLocal) * lpCos / dist2;
-            if (!isfinite(bsdfPDensity))
-                bsdfPDensity = 0.0f;
-            const float lightPDensity = areaPDensity;
-            const float misWeight = pow2f(lightPDensity) / (pow2f(bsdfPDensity) + pow2f(lightPDensity));
-            const float scale = misWeight / areaPDensity;
-            // performDirectLighting<.., true> = visibility * value; the ray is only needed when value != 0
-            const f3 value = performDirectLighting<false>(s, positionInWorld, vOutLocal, shadingFrame, bsdf, lightSample);
-            const f3 nee = value * scale;
-            const f3 unoccluded = alpha * nee;
-            out->neeUnoccluded = nee;
-            if (value.x == 0.0f && value.y == 0.0f && value.z == 0.0f) {
-                *radiance += unoccluded; // 0 (or NaN for a non-finite scale) whatever the visibility
-                out->directContNEE = nee;
-            }
-            else {
-                out->directContNEE = f3(0.0f) * scale;
-                out->wantShadow = true;
-                out->shadowDir = shadowRay;
-                out->shadowTmax = dist * 0.9999f;
-                out->pending = make_float4(unoccluded.x, unoccluded.y, unoccluded.z, scale);
-            }
+    const float uLight = rng.getFloat0cTo1o();
+    const float u0 = rng.getFloat0cTo1o();
+    const float u1 = rng.getFloat0cTo1o();
+    LightSample lightSample;
+    float areaPDensity = 0.0f;
+    sampleLight(s, uLight, u0, u1, &lightSample, &areaPDensity);
+    if (areaPDensity > 0.0f) {
+        f3 shadowRay = lightSample.position - positionInWorld;
+        const float dist2 = sqLength(shadowRay);
+        const float dist = sqrtf(dist2);
+        shadowRay /= dist;
+        const f3 vInLocal = shadingFrame.toLocal(shadowRay);
+        const float lpCos = fabsf(dot(shadowRay, lightSample.normal));
+        float bsdfPDensity = bsdf.evaluatePDF(vOutLocal, vInLocal) * lpCos / dist2;
+        if (!isfinite(bsdfPDensity))
+            bsdfPDensity = 0.0f;
+        const float lightPDensity = areaPDensity;
+        const float misWeight = pow2f(lightPDensity) / (pow2f(bsdfPDensity) + pow2f(lightPDensity));
+        const float scale = misWeight / areaPDensity;
+        // performDirectLighting<.., true> = visibility * value; the ray is only needed when value != 0
+        const f3 value = performDirectLighting<false>(s, positionInWorld, vOutLocal, shadingFrame, bsdf, lightSample);
+        const f3 nee = value * scale;
+        const f3 unoccluded = alpha * nee;
+        out->neeUnoccluded = nee;
+        if (value.x == 0.0f && value.y == 0.0f && value.z == 0.0f) {
+            *radiance += unoccluded; // 0 (or NaN for a non-finite scale) whatever the visibility
+            out->directContNEE = nee;
+        }
+        else {
+            out->directContNEE = f3(0.0f) * scale;
+            out->wantShadow = true;
+            out->shadowDir = shadowRay;
+            out->shadowTmax = dist * 0.9999f;
+            out->pending = make_float4(unoccluded.x, unoccluded.y, unoccluded.z, scale);
         }
     }
-    // ---- next direction
+}
+
+GFX_D void sampleNextDirection(const f3 &vOutLocal, const ReferenceFrame &shadingFrame, const BSDF &bsdf, PCG32RNG &rng, f3 alpha,
+                               VertexOutput* out) {
     f3 vInLocal;
     float dirPDensity;
     const float uDir0 = rng.getFloat0cTo1o();
@@ -201,6 +201,118 @@ GFX_D void shadeVertex(const DevScene &s, const f3 &positionInWorld, const f3 &v
     out->dirPDensity = dirPDensity;
     // the path extension loop (:161-165) stops on an invalid sample before tracing anything
     out->wantExtension = dirPDensity > 0.0f && isfinite(dirPDensity);
+}
+
+GFX_D void shadeVertex(const DevScene &s, const f3 &positionInWorld, const f3 &vOutLocal, const ReferenceFrame &shadingFrame,
+                       const BSDF &bsdf, PCG32RNG &rng, f3 alpha, f3* radiance, VertexOutput* out) {
+    neeBaseline(s, positionInWorld, vOutLocal, shadingFrame, bsdf, rng, alpha, radiance, out);
+    sampleNextDirection(vOutLocal, shadingFrame, bsdf, rng, alpha, out);
+}
+
+// ---- ReGIR (regir.cu builds the cell reservoirs; the path tracer resamples them) -------------------------
+constexpr uint32_t kNumLightSlotsPerCell = 512; // regir_shared.h:7
+
+struct DevRegir {
+    float4* slots[2];            // one 64-byte record per light slot, see GFX_BUF_REGIR_SLOTS
+    unsigned long long* slotRngs;
+    uint32_t* perCellNumAccesses;
+    uint32_t* lastAccessFrameIndices;
+    uint32_t* numActiveCells;    // [2]
+    uint32_t dimX, dimY, dimZ, numCells;
+    f3 gridOrigin, gridCellSize;
+    uint32_t log2NumCandidatesPerLightSlot, log2NumCandidatesPerCell, enableCellRandomization, bufferIndex;
+};
+DevRegir makeDevRegir(const gfx_ctx* ctx, const GfxFrameParams* p); // regir.cu
+
+// regir_shared.h:731-742; the float -> uint32 conversion saturates like cvt.rzi.u32.f32
+GFX_D uint32_t calcCellLinearIndex(const DevRegir &rg, const f3 &positionInWorld) {
+    const f3 relPos = positionInWorld - rg.gridOrigin;
+    const uint32_t ix = min(dm_f2uint(relPos.x / rg.gridCellSize.x), rg.dimX - 1);
+    const uint32_t iy = min(dm_f2uint(relPos.y / rg.gridCellSize.y), rg.dimY - 1);
+    const uint32_t iz = min(dm_f2uint(relPos.z / rg.gridCellSize.z), rg.dimZ - 1);
+    return iz * rg.dimX * rg.dimY + iy * rg.dimX + ix;
+}
+
+// sampleFromCell + performNextEventEstimation<true> (regir/gpu_kernels/optix_pathtracing_kernels.cu:18-101)
+GFX_D void neeRegir(const DevScene &s, const DevRegir &rg, const f3 &positionInWorld, const f3 &vOutLocal,
+                    const ReferenceFrame &shadingFrame, const BSDF &bsdf, PCG32RNG &rng, const f3 &alpha, f3* radiance,
+                    VertexOutput* out) {
+    out->wantShadow = false;
+    out->directContNEE = f3(0.0f);
+    out->neeUnoccluded = f3(0.0f);
+    f3 randomOffset(0.0f);
+    if (rg.enableCellRandomization) {
+        const float o0 = -0.5f + rng.getFloat0cTo1o();
+        const float o1 = -0.5f + rng.getFloat0cTo1o();
+        const float o2 = -0.5f + rng.getFloat0cTo1o();
+        randomOffset = rg.gridCellSize * f3(o0, o1, o2);
+    }
+    const uint32_t cellLinearIndex = calcCellLinearIndex(rg, positionInWorld + randomOffset);
+    const uint32_t resStartIndex = kNumLightSlotsPerCell * cellLinearIndex;
+    { // atomicAdd(&perCellNumAccesses[cell], 1u), aggregated over the lanes of the warp that touch the same cell
+        const uint32_t peers = __match_any_sync(__activemask(), cellLinearIndex);
+        if ((threadIdx.x + threadIdx.y * blockDim.x) % 32 == (uint32_t)(__ffs(peers) - 1))
+            atomicAdd(rg.perCellNumAccesses + cellLinearIndex, (uint32_t)__popc(peers));
+    }
+
+    const uint32_t numResampling = 1u << rg.log2NumCandidatesPerCell;
+    float sumWeights = 0.0f;
+    uint32_t combinedStreamLength = 0;
+    f3 selectedContribution(0.0f), selectedPosition(0.0f);
+    float selectedTargetPDensity = 0.0f;
+    const float4* slots = rg.slots[rg.bufferIndex];
+    for (uint32_t i = 0; i < numResampling; ++i) {
+        // mapPrimarySampleToDiscrete (common_shared.h:140-150)
+        const uint32_t lightSlotIdx = resStartIndex + min(dm_f2uint(rng.getFloat0cTo1o() * kNumLightSlotsPerCell), kNumLightSlotsPerCell - 1);
+        const float4* rec = slots + 4 * (size_t)lightSlotIdx;
+        const float4 r0 = rec[0], r1 = rec[1], r2 = rec[2];
+        const uint32_t m = __float_as_uint(r1.w);
+        const uint32_t streamLength = m & 0x7FFFFFFFu;
+        combinedStreamLength += streamLength;
+        const float recPDFEstimate = r2.w;
+        if (recPDFEstimate == 0.0f)
+            continue;
+        LightSample ls;
+        ls.emittance = f3(r0.x, r0.y, r0.z);
+        ls.position = f3(r1.x, r1.y, r1.z);
+        ls.normal = f3(r2.x, r2.y, r2.z);
+        ls.atInfinity = m >> 31;
+        const f3 cont = performDirectLighting<false>(s, positionInWorld, vOutLocal, shadingFrame, bsdf, ls);
+        const float targetPDensity = convertToWeight(cont);
+        const float weight = targetPDensity * recPDFEstimate * streamLength;
+        // Reservoir::update
+        sumWeights += weight;
+        if (rng.getFloat0cTo1o() < weight / sumWeights) {
+            selectedContribution = cont;
+            selectedPosition = ls.position;
+            selectedTargetPDensity = targetPDensity;
+        }
+    }
+    const float weightForEstimate = 1.0f / combinedStreamLength;
+    float recProbDensityEstimate = weightForEstimate * sumWeights / selectedTargetPDensity;
+    if (!isfinite(recProbDensityEstimate))
+        recProbDensityEstimate = 0.0f;
+    if (recProbDensityEstimate > 0.0f) {
+        // ret = unshadowedContribution * (visibility * recProbDensityEstimate)
+        const f3 cont = selectedContribution;
+        const f3 nee = cont * (1.0f * recProbDensityEstimate);
+        const f3 unoccluded = alpha * nee;
+        out->neeUnoccluded = nee;
+        if (cont.x == 0.0f && cont.y == 0.0f && cont.z == 0.0f) {
+            *radiance += unoccluded;
+            out->directContNEE = nee;
+        }
+        else {
+            f3 shadowRayDir = selectedPosition - positionInWorld; // evaluateVisibility (regir_shared.h:544-566)
+            const float dist = sqrtf(sqLength(shadowRayDir));
+            shadowRayDir /= dist;
+            out->directContNEE = cont * (0.0f * recProbDensityEstimate);
+            out->wantShadow = true;
+            out->shadowDir = shadowRayDir;
+            out->shadowTmax = dist * 0.9999f;
+            out->pending = make_float4(unoccluded.x, unoccluded.y, unoccluded.z, (cont.x + cont.y + cont.z) * 0.0f);
+        }
+    }
 }
 
 GFX_D void emitRays(const DevScene &s, const DevPathState &ps, uint32_t* roundCounters, uint32_t nextQueue, uint32_t lane,

@@ -159,13 +159,32 @@ class Context:
         self._check(self.lib.gfx_svgf_launch(self.h, stream, C.byref(params), pass_id, stage), "gfx_svgf_launch")
 
     # -- NRC frame (neural_radiance_caching_main.cpp:2270-2368) -------------------------------------
-    def download_linear(self, buffer_id: int, index: int = 0, stream=None) -> np.ndarray:
-        """NRC buffers (GFX_BUF_NRC_*) as [rows, cols]"""
-        dtype, cols, rows = abi.linear_buffer_layout(buffer_id, self.width, self.height)
+    def download_linear(self, buffer_id: int, index: int = 0, stream=None, params=None) -> np.ndarray:
+        """NRC / ReGIR buffers (GFX_BUF_NRC_*, GFX_BUF_REGIR_*) as [rows, cols]"""
+        dtype, cols, rows = abi.linear_buffer_layout(buffer_id, self.width, self.height, params)
         arr = np.empty((rows, cols), dtype=dtype)
         self._check(self.lib.gfx_buffer_download(self.h, stream, buffer_id, index, arr.ctypes.data, arr.nbytes),
                     "gfx_buffer_download")
         return arr
+
+    # -- ReGIR (regir_main.cpp:2033-2068) -----------------------------------------------------------
+    def regir_build_cells(self, params, frame_index: int, temporal: bool, stream=None):
+        self._check(self.lib.gfx_regir_build_cells(self.h, stream, C.byref(params), frame_index & 0xFFFFFFFF, 1 if temporal else 0),
+                    "gfx_regir_build_cells")
+
+    def regir_update_access(self, params, frame_index: int, stream=None):
+        self._check(self.lib.gfx_regir_update_access(self.h, stream, C.byref(params), frame_index & 0xFFFFFFFF),
+                    "gfx_regir_update_access")
+
+    def regir_frame(self, params, frame_index: int, temporal: bool = True, stream=None):
+        """one ReGIR frame (regir_main.cpp:2022-2068): G-buffer, cell reservoirs (+ temporal reuse after the first
+        frame of a sequence), path tracing with reservoir-based NEE, last-access bookkeeping"""
+        params.frameIndex = frame_index
+        params.bufferIndex = frame_index % 2
+        self.gbuffer(params, stream)
+        self.regir_build_cells(params, frame_index, temporal and frame_index > 0, stream)
+        self.pathtrace(params, abi.PT_REGIR, stream)
+        self.regir_update_access(params, frame_index, stream)
 
     def nrc_preprocess(self, params, offset_unbiased_tile: int, offset_training_path: int, new_sequence: bool, stream=None):
         self._check(self.lib.gfx_nrc_preprocess(self.h, stream, C.byref(params), offset_unbiased_tile & 0xFFFFFFFF,

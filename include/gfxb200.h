@@ -188,7 +188,8 @@ typedef struct GfxFrameParams {
     uint32_t svgfFlags;                /* GfxSVGFFlags */
     uint32_t taaHistoryLength;         /* 16 by default */
     /* path tracers (path_tracing_shared.h PerFramePipelineLaunchParameters::maxPathLength; 5 by default,
-     * path_tracing_main.cpp:1555) */
+     * path_tracing_main.cpp:1519).  0 selects that default for GFX_PT_BASELINE / GFX_PT_REGIR and means
+     * "no limit" for GFX_PT_NRC, as in neural_radiance_caching_main.cpp:2246 (infBounces) */
     uint32_t maxPathLength;
     /* NRC / ReGIR: scene.initialSceneAabb (neural_radiance_caching_main.cpp:1096,1139; regir_main.cpp:1012), the
      * box positions are normalised to, and PerFramePipelineLaunchParameters::radianceScale (10^log10RadianceScale,
@@ -196,6 +197,12 @@ typedef struct GfxFrameParams {
     float sceneAabbMin[3];
     float sceneAabbMax[3];
     float radianceScale;
+    /* ReGIR (regir_shared.h:247-249, regir_main.cpp:1109,1733-1736): grid over sceneAabb (0,0,0 = 32 x 8 x 32),
+     * 2^3 candidates per light slot, 2^2 resampled slots per shading point, jittered cell lookup */
+    uint32_t regirGridDim[3];
+    uint32_t regirLog2NumCandidatesPerLightSlot;
+    uint32_t regirLog2NumCandidatesPerCell;
+    uint32_t regirEnableCellRandomization;
 } GfxFrameParams;
 
 typedef enum GfxSVGFFlags {
@@ -219,8 +226,10 @@ typedef enum GfxReSTIRPass {
 /* path tracer entry points (path_tracing/path_tracing_main.cpp:52-57 PathTracingEntryPoint) */
 typedef enum GfxPathTraceVariant {
     GFX_PT_BASELINE = 0,                        /* pathTraceBaseline */
-    GFX_PT_NRC = 1                              /* pathTraceNRC (neural_radiance_caching_main.cpp:2281-2289):
+    GFX_PT_NRC = 1,                             /* pathTraceNRC (neural_radiance_caching_main.cpp:2281-2289):
                                                  * needs gfx_nrc_preprocess first; fills the NRC buffers below */
+    GFX_PT_REGIR = 2                            /* regir's pathTraceReGIR (regir_main.cpp:2051-2057): NEE resamples the
+                                                 * cell reservoirs built by gfx_regir_build_cells */
 } GfxPathTraceVariant;
 
 /* SVGF entry points (svgf/svgf_main.cpp:2127-2172) */
@@ -260,9 +269,17 @@ typedef enum GfxBufferId {
     GFX_BUF_NRC_TRAIN_TARGET = 21,      /* [2] float x3 x 131072 */
     GFX_BUF_NRC_TRAIN_VERTEX_INFO = 22, /* uint32 x4 x 131072 : localThroughput rgb, prevVertexDataIndex | pathLength<<23 */
     GFX_BUF_NRC_TRAIN_SUFFIX_TERMINAL = 23, /* uint32 x numSuffixes : prevVertexDataIndex | hasQuery<<23 | pathLength<<24 */
-    GFX_BUF_NRC_STATE = 24              /* uint32 x32 : numTrainingData[2], tileSize[2][2], offsetToSelectUnbiasedTile,
+    GFX_BUF_NRC_STATE = 24,             /* uint32 x32 : numTrainingData[2], tileSize[2][2], offsetToSelectUnbiasedTile,
                                          * offsetToSelectTrainingPath, targetMin/Max (ordered ints) [2][2][3] at 8,
                                          * targetAvg [2][3] at 20, numInferenceQueries at 26 */
+    /* ReGIR grid (regir_shared.h:207-216); numSlots = numCells * 512 */
+    GFX_BUF_REGIR_SLOTS = 25,           /* [2] 16 words x numSlots : Reservoir<LightSample> + ReservoirInfo as one 64-byte record:
+                                         * emittance3 sumWeights | position3 streamLength|atInfinity<<31 | normal3 recPDFEstimate |
+                                         * targetDensity 0 0 0 */
+    GFX_BUF_REGIR_SLOT_RNG = 26,        /* uint64 x numSlots : lightSlotRngs */
+    GFX_BUF_REGIR_CELL_ACCESSES = 27,   /* uint32 x numCells : perCellNumAccesses */
+    GFX_BUF_REGIR_LAST_ACCESS = 28,     /* uint32 x numCells : lastAccessFrameIndices */
+    GFX_BUF_REGIR_NUM_ACTIVE_CELLS = 29 /* uint32 x2 : numActiveCellsArray */
 } GfxBufferId;
 
 /* ---- context ------------------------------------------------------------------------- */
@@ -330,6 +347,14 @@ int gfx_svgf_launch(gfx_ctx* ctx, void* stream, const GfxFrameParams* params, in
  * one sample per pixel of the unidirectional path tracer (NEE + MIS + Russian roulette, params->maxPathLength)
  * starting from the G-buffer of params->bufferIndex; running mean into GFX_BUFFER_BEAUTY_ACCUM. */
 int gfx_pathtrace_launch(gfx_ctx* ctx, void* stream, const GfxFrameParams* params, int variant);
+
+/* ---- ReGIR cell reservoirs (regir_main.cpp:2033-2068) --------------------------------- */
+/* replaces kernelBuildCellReservoirs / kernelBuildCellReservoirsAndTemporalReuse (build_cell_reservoirs.cu:71-233):
+ * streaming RIS of 2^log2NumCandidatesPerLightSlot light samples per slot against the intensity reaching the cell,
+ * optionally merged with the slot's reservoir of the previous frame; cells unused for more than 8 frames are skipped */
+int gfx_regir_build_cells(gfx_ctx* ctx, void* stream, const GfxFrameParams* params, uint32_t frameIndex, int useTemporalReuse);
+/* replaces kernelUpdateLastAccessFrameIndices (build_cell_reservoirs.cu:235-248), after the path tracer */
+int gfx_regir_update_access(gfx_ctx* ctx, void* stream, const GfxFrameParams* params, uint32_t frameIndex);
 
 /* ---- NRC network (network_interface.h:14-28) ------------------------------------------ */
 typedef struct gfx_nrc gfx_nrc;

@@ -66,6 +66,10 @@ void orc_gbuffer(orc_frame* f, const GfxFrameParams* p, int numThreads);
 void orc_restir(orc_frame* f, const GfxFrameParams* p, int pass, int numThreads);
 /* unidirectional path tracer (GfxPathTraceVariant); returns the number of rays traced */
 uint64_t orc_pathtrace(orc_frame* f, const GfxFrameParams* p, int variant, int numThreads);
+/* ReGIR (build_cell_reservoirs.cu): buildCellReservoirs[AndTemporalReuse], updateLastAccessFrameIndices;
+ * buffers via orc_buffer_ptr(GFX_BUF_REGIR_*) once the grid exists */
+void orc_regir_build_cells(orc_frame* f, const GfxFrameParams* p, uint32_t frameIndex, int useTemporalReuse, int numThreads);
+void orc_regir_update_access(orc_frame* f, const GfxFrameParams* p, uint32_t frameIndex);
 /* NRC bookkeeping kernels (nrc_setup_kernels.cu): preprocessNRC, accumulateInferredRadianceValues,
  * propagateRadianceValues, shuffleTrainingData; buffers via orc_buffer_ptr(GFX_BUF_NRC_*) */
 void orc_nrc_preprocess(orc_frame* f, const GfxFrameParams* p, uint32_t offsetToSelectUnbiasedTile,

@@ -144,7 +144,7 @@ static void pathTracePixel(orc_frame* f, const GfxFrameParams* p, const Camera &
     const GB0 gb0 = f->gb0[bufIdx][pix];
     const float bcB = decodeBarycentric((uint16_t)(gb0.qbc & 0xFFFFu));
     const float bcC = decodeBarycentric((uint16_t)(gb0.qbc >> 16));
-    const uint32_t maxPathLength = p->maxPathLength;
+    const uint32_t maxPathLength = p->maxPathLength ? p->maxPathLength : 5u; // 0 = the hosts' default (path_tracing_main.cpp:1519)
 
     float3 contribution(0.001f, 0.001f, 0.001f);
     if (gb0.instSlot != 0xFFFFFFFFu) {
@@ -251,11 +251,14 @@ static void pathTracePixel(orc_frame* f, const GfxFrameParams* p, const Camera &
 }
 
 static uint64_t nrcPathTrace(orc_frame* f, const GfxFrameParams* p, int numThreads); // nrc_pathtrace.inl
+static uint64_t regirPathTrace(orc_frame* f, const GfxFrameParams* p, int numThreads); // regir.inl
 
 extern "C" uint64_t orc_pathtrace(orc_frame* f, const GfxFrameParams* p, int variant, int numThreads) {
     if (numThreads <= 0) numThreads = omp_get_max_threads();
     if (variant == GFX_PT_NRC)
         return nrcPathTrace(f, p, numThreads);
+    if (variant == GFX_PT_REGIR)
+        return regirPathTrace(f, p, numThreads);
     const Camera camera = makeCamera(p->camera);
     const uint32_t W = f->W, H = f->H;
     const uint32_t y0 = p->tileOriginY, y1 = p->tileRows ? std::min(H, p->tileOriginY + p->tileRows) : H;

@@ -376,6 +376,7 @@ struct orc_frame {
     std::vector<F4> beauty, albedo, normal;
     std::vector<float2> neighborDeltas;
     struct orc_nrc_frame* nrc = nullptr; // NRC buffers, created on first use (nrc_pathtrace.inl)
+    struct orc_regir* regir = nullptr;   // ReGIR grid, created on first use (regir.inl)
 };
 
 extern "C" orc_frame* orc_frame_create(orc_scene* s, uint32_t W, uint32_t H) {
@@ -399,9 +400,12 @@ extern "C" orc_frame* orc_frame_create(orc_scene* s, uint32_t W, uint32_t H) {
     return f;
 }
 static void nrcFrameDestroy(struct orc_nrc_frame* n);
+static void regirDestroy(struct orc_regir* r);
 extern "C" void orc_frame_destroy(orc_frame* f) {
     if (f->nrc)
         nrcFrameDestroy(f->nrc);
+    if (f->regir)
+        regirDestroy(f->regir);
     delete f;
 }
 
@@ -450,6 +454,7 @@ extern "C" void orc_restir_setup_neighbor_table(orc_frame* f) { // restir_di_mai
 }
 
 static void* nrcBufferPtr(orc_frame* f, int id, uint32_t index, size_t* bytes);
+static void* regirBufferPtr(orc_frame* f, int id, uint32_t index, size_t* bytes);
 extern "C" void* orc_buffer_ptr(orc_frame* f, int id, uint32_t index, size_t* bytes) {
     const size_t n = (size_t)f->W * f->H;
     void* p = nullptr;
@@ -465,7 +470,10 @@ extern "C" void* orc_buffer_ptr(orc_frame* f, int id, uint32_t index, size_t* by
     case GFX_BUF_BEAUTY_ACCUM: p = f->beauty.data(); b = n * 16; break;
     case GFX_BUF_ALBEDO_ACCUM: p = f->albedo.data(); b = n * 16; break;
     case GFX_BUF_NORMAL_ACCUM: p = f->normal.data(); b = n * 16; break;
-    default: return nrcBufferPtr(f, id, index, bytes);
+    default:
+        if (id >= GFX_BUF_REGIR_SLOTS)
+            return regirBufferPtr(f, id, index, bytes);
+        return nrcBufferPtr(f, id, index, bytes);
     }
     if (bytes) *bytes = b;
     return p;
@@ -1224,3 +1232,4 @@ extern "C" void orc_restir(orc_frame* f, const GfxFrameParams* p, int pass, int 
 // ---------------------------------------------------------------------------------------
 #include "pathtrace.inl"
 #include "nrc_pathtrace.inl"
+#include "regir.inl"

@@ -74,6 +74,8 @@ def lib() -> C.CDLL:
         L.orc_restir.argtypes = [vp, C.POINTER(abi.GfxFrameParams), C.c_int, C.c_int]
         L.orc_pathtrace.argtypes = [vp, C.POINTER(abi.GfxFrameParams), C.c_int, C.c_int]
         L.orc_pathtrace.restype = C.c_uint64
+        L.orc_regir_build_cells.argtypes = [vp, C.POINTER(abi.GfxFrameParams), C.c_uint32, C.c_int, C.c_int]
+        L.orc_regir_update_access.argtypes = [vp, C.POINTER(abi.GfxFrameParams), C.c_uint32]
         L.orc_nrc_preprocess.argtypes = [vp, C.POINTER(abi.GfxFrameParams), C.c_uint32, C.c_uint32, C.c_int]
         for name in ("orc_nrc_accumulate", "orc_nrc_propagate", "orc_nrc_shuffle"):
             getattr(L, name).argtypes = [vp, C.POINTER(abi.GfxFrameParams)]
@@ -201,15 +203,22 @@ class OracleFrame:
 
 
     # -- NRC frame (nrc_setup_kernels.cu) -----------------------------------------------------------
-    def linear_buffer(self, buffer_id: int, index: int = 0, copy: bool = True) -> np.ndarray:
-        """NRC buffers (GFX_BUF_NRC_*) as [rows, cols]; copy=False returns a writable view of the oracle's memory"""
+    def linear_buffer(self, buffer_id: int, index: int = 0, copy: bool = True, params=None) -> np.ndarray:
+        """NRC / ReGIR buffers (GFX_BUF_NRC_*, GFX_BUF_REGIR_*) as [rows, cols]; copy=False returns a writable view of
+        the oracle's memory"""
         nbytes = C.c_size_t()
         ptr = lib().orc_buffer_ptr(self.h, buffer_id, index, C.byref(nbytes))
-        dtype, cols, rows = abi.linear_buffer_layout(buffer_id, self.W, self.H)
+        dtype, cols, rows = abi.linear_buffer_layout(buffer_id, self.W, self.H, params)
         assert nbytes.value == rows * cols * np.dtype(dtype).itemsize, (buffer_id, nbytes.value, rows, cols)
         raw = (C.c_uint8 * nbytes.value).from_address(ptr)
         arr = np.frombuffer(raw, dtype=dtype).reshape(rows, cols)
         return arr.copy() if copy else arr
+
+    def regir_build_cells(self, params, frame_index: int, temporal: bool, threads: int = 0):
+        lib().orc_regir_build_cells(self.h, C.byref(params), frame_index & 0xFFFFFFFF, 1 if temporal else 0, threads)
+
+    def regir_update_access(self, params, frame_index: int):
+        lib().orc_regir_update_access(self.h, C.byref(params), frame_index & 0xFFFFFFFF)
 
     def nrc_preprocess(self, params, offset_unbiased_tile: int, offset_training_path: int, new_sequence: bool):
         lib().orc_nrc_preprocess(self.h, C.byref(params), offset_unbiased_tile, offset_training_path, 1 if new_sequence else 0)
