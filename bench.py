@@ -333,12 +333,16 @@ def run_gpu(args):
     roofline = None
     breakdown = {}
     if driver is None:
-        timers = {}
+        # every kernel launch bracketed by CUDA events on its stream inside the library (gfx_timing_enable)
+        ctx.timing_enable(True)
+        ctx.timing_read()
         for _ in range(args.steps):
-            frame_launches(ctx, params, frame, nsp, timers)
+            frame_launches(ctx, params, frame, nsp, None)
             frame += 1
-        torch.cuda.synchronize()
-        breakdown = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in timers.items()}
+        timing = ctx.timing_read()
+        ctx.timing_enable(False)
+        breakdown = {k: ms / n for k, (ms, n) in timing.items()}                 # ms per launch
+        launches_per_frame = {k: n / args.steps for k, (ms, n) in timing.items()}
         dominant = max(breakdown, key=breakdown.get)
         # traversal statistics of this BVH for the rays the dominant kernel traces
         from tests import oracle_lib as O  # only for the primary-ray generator (host arithmetic)
@@ -362,13 +366,18 @@ def run_gpu(args):
         trav_primary = 80 * n_int_p + 52 * n_tri_p + 64
         trav_shadow = 80 * n_int_s + 52 * n_tri_s + 64
         # algorithmic bytes per pixel, SURVEY.md §8(d): struct sizes of the reference + traversal counters
+        # per launch; the wavefront trace kernel serves ~0.94 (initial) / ~0.94 (shading) rays per pixel
+        rays_vis = (rays_per_px - 1.0) / 2.0
         alg = {
             "gbuffer": 56 + 32 + trav_primary + 3 * 48 + 16,
-            "initial_ris": 120 + trav_shadow,
-            "initial_temporal_ris": 120 + 112 + trav_shadow,
+            "ris_candidates": 120,                     # + 32 x ~250 B of L2-side light-table gathers per pixel
+            "ris_resolve_temporal": 112 + 9,
+            "ris_megakernel": 120 + 112 + trav_shadow,
+            "trace_visibility": rays_vis * trav_shadow,
             "spatial_ris": 592,
-            "shading": 120 + trav_shadow,
-            "light_dist": 0,
+            "shading_rays": 104 + 36,
+            "shading": 120,
+            "shading_megakernel": 120 + trav_shadow,
         }
         hbm_peak, peak_src = measured_peaks()
         bytes_per_launch = alg.get(dominant, 0) * px
@@ -378,7 +387,8 @@ def run_gpu(args):
                     "algorithmic_bytes_per_launch": bytes_per_launch, "ms_per_launch": breakdown[dominant],
                     "traversal": {"primary_nodes_per_ray": n_int_p, "primary_tris_per_ray": n_tri_p,
                                   "shadow_nodes_per_ray": n_int_s, "shadow_tris_per_ray": n_tri_s},
-                    "per_kernel": {k: {"ms": breakdown[k], "GBps": alg.get(k, 0) * px / (breakdown[k] * 1e-3) / 1e9}
+                    "per_kernel": {k: {"ms_per_launch": breakdown[k], "launches_per_frame": launches_per_frame[k],
+                                       "GBps": alg.get(k, 0) * px / (breakdown[k] * 1e-3) / 1e9}
                                    for k in breakdown}}
 
     # ---- CPU baseline: the oracle on the host cores, bounded sample (rank 0, N=1 only) -------------

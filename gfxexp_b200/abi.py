@@ -51,6 +51,10 @@ class GfxCamera(C.Structure):
     _fields_ = [("aspect", c_f), ("fovY", c_f), ("position", c_f * 3), ("orientation", c_f * 9)]
 
 
+class GfxKernelTiming(C.Structure):
+    _fields_ = [("label", C.c_char * 48), ("totalMs", c_f), ("launches", c_u32)]
+
+
 class GfxFrameParams(C.Structure):
     _fields_ = [("camera", GfxCamera), ("prevCamera", GfxCamera),
                 ("numAccumFrames", c_u32), ("frameIndex", c_u32), ("bufferIndex", c_u32),
@@ -295,6 +299,8 @@ _DECLS = {
     "gfx_restir_launch": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxFrameParams), C.c_int]),
     "gfx_svgf_launch": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxFrameParams), C.c_int, c_u32]),
     "gfx_pathtrace_launch": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxFrameParams), C.c_int]),
+    "gfx_timing_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "gfx_timing_read": (C.c_int, [C.c_void_p, C.c_void_p, c_u32, C.POINTER(c_u32)]),
     "gfx_regir_build_cells": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxFrameParams), c_u32, C.c_int]),
     "gfx_regir_update_access": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxFrameParams), c_u32]),
     "gfx_nrc_preprocess": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxFrameParams), c_u32, c_u32, C.c_int]),

@@ -759,6 +759,41 @@ int gfx_pathtrace_launch(gfx_ctx* ctx, void* stream, const GfxFrameParams* param
     return launchPathTrace(ctx, (cudaStream_t)stream, params, variant);
 }
 
+int gfx_timing_enable(gfx_ctx* ctx, int enable) {
+    CHECK_CTX(ctx);
+    ctx->timer.enabled = enable != 0;
+    return GFX_OK;
+}
+
+int gfx_timing_read(gfx_ctx* ctx, GfxKernelTiming* out, uint32_t capacity, uint32_t* numWritten) {
+    CHECK_CTX(ctx);
+    if (!out || !numWritten)
+        return GFX_ERR_INVALID_ARGUMENT;
+    GFX_CUDA(ctx, cudaDeviceSynchronize());
+    uint32_t n = 0;
+    for (const KernelTimer::Rec &r : ctx->timer.recs) {
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, r.start, r.stop);
+        uint32_t k = 0;
+        while (k < n && strncmp(out[k].label, r.label, sizeof(out[k].label) - 1) != 0)
+            ++k;
+        if (k == n) {
+            if (n == capacity)
+                continue;
+            memset(&out[n], 0, sizeof(out[n]));
+            strncpy(out[n].label, r.label, sizeof(out[n].label) - 1);
+            ++n;
+        }
+        out[k].totalMs += ms;
+        out[k].launches += 1;
+        ctx->timer.pool.push_back(r.start);
+        ctx->timer.pool.push_back(r.stop);
+    }
+    ctx->timer.recs.clear();
+    *numWritten = n;
+    return GFX_OK;
+}
+
 int gfx_regir_build_cells(gfx_ctx* ctx, void* stream, const GfxFrameParams* params, uint32_t frameIndex, int useTemporalReuse) {
     CHECK_CTX(ctx);
     if (!params)

@@ -135,8 +135,31 @@ struct FrameState {
 
 } // namespace gfx
 
+// Per-kernel CUDA-event timing (gfx_timing_enable / gfx_timing_read): every launch site is wrapped in a KernelTimerScope;
+// when timing is off the scope is a branch on a bool.
+struct KernelTimer {
+    struct Rec {
+        const char* label;
+        cudaEvent_t start, stop;
+    };
+    bool enabled = false;
+    std::vector<Rec> recs;
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t get() {
+        if (!pool.empty()) {
+            cudaEvent_t e = pool.back();
+            pool.pop_back();
+            return e;
+        }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
+    }
+};
+
 struct gfx_ctx {
     int device = 0;
+    KernelTimer timer;
     std::string lastError;
     uint64_t launches = 0;
     uint32_t* traceFetchCounter = nullptr; // device counter of the wavefront trace kernel
@@ -148,6 +171,26 @@ struct gfx_ctx {
     gfx::DevScene devScene() const;
     gfx::DevFrame devFrame() const;
 };
+
+struct KernelTimerScope {
+    gfx_ctx* ctx;
+    cudaStream_t stream;
+    size_t index;
+    bool on;
+    KernelTimerScope(gfx_ctx* c, cudaStream_t s, const char* label) : ctx(c), stream(s), index(0), on(c->timer.enabled) {
+        if (!on)
+            return;
+        KernelTimer::Rec r{ label, c->timer.get(), c->timer.get() };
+        cudaEventRecord(r.start, s);
+        index = c->timer.recs.size();
+        c->timer.recs.push_back(r);
+    }
+    ~KernelTimerScope() {
+        if (on)
+            cudaEventRecord(ctx->timer.recs[index].stop, stream);
+    }
+};
+#define GFX_TIMED(ctx, stream, label) KernelTimerScope timedScope_##__LINE__(ctx, stream, label)
 
 #define GFX_CUDA(ctx, call) \
     do { \

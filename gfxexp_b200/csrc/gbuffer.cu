@@ -171,6 +171,7 @@ int launchGBuffer(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* param
         return GFX_OK;
     const dim3 block(8, 8);
     const dim3 grid((ctx->frame.W + 7) / 8, (p.y1 - p.y0 + 7) / 8);
+    GFX_TIMED(ctx, stream, "gbuffer");
     k_gbuffer<<<grid, block, 0, stream>>>(ctx->devScene(), ctx->devFrame(), p);
     ctx->launches++;
     GFX_CUDA(ctx, cudaGetLastError());

@@ -704,6 +704,7 @@ static int nrcInferLaunch(gfx_nrc* n, cudaStream_t s, const float* inputData, fl
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const uint32_t numTiles = numData / kTileRows; // upper bound when numDataPtr is given
     const uint32_t grid = numTiles < (uint32_t)sms * 6 ? numTiles : (uint32_t)sms * 6;
+    GFX_TIMED(n->ctx, s, "nrc_infer");
     k_nrcInfer<<<grid, 128, smem, s>>>(n->levels, n->paramsEma + n->numMatrixWeights, n->ummaWeights, n->numHiddenLayers,
                                        inputData, predictionData, numData, numDataPtr);
     n->ctx->launches++;
@@ -766,16 +767,18 @@ int gfx_nrc_train(gfx_nrc* n, void* stream, const float* inputData, const float*
     NRC_CUDA(n, cudaMemsetAsync(n->loss, 0, 4, s));
     const size_t smem = ((size_t)n->numMatrixWeights + (size_t)(n->numHiddenLayers + 2) * 128 * kRowStride) * 2;
     NRC_CUDA(n, cudaFuncSetAttribute(k_nrcTrain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { GFX_TIMED(n->ctx, s, "nrc_train_fwd_bwd");
     k_nrcTrain<<<numData / 128, 128, smem, s>>>(n->levels, n->params, n->numMatrixWeights, n->numHiddenLayers, inputData,
-                                                targetData, numData, n->grads, n->loss);
+                                                targetData, numData, n->grads, n->loss); }
     n->ctx->launches++;
     ++n->globalStep;
     const float emaDecay = 0.99f;
     const float emaDebiasOld = 1 - (float)pow((double)emaDecay, (double)(n->globalStep - 1));
     const float emaDebiasNew = 1.0f / (1 - (float)pow((double)emaDecay, (double)n->globalStep));
+    { GFX_TIMED(n->ctx, s, "nrc_adam_ema");
     k_nrcAdamEma<<<(n->numParams + 255) / 256, 256, 0, s>>>(n->numParams, n->numMatrixWeights, n->learningRate, emaDebiasOld,
                                                             emaDebiasNew, n->grads, n->master, n->params, n->paramsEma,
-                                                            n->m1, n->m2, n->steps);
+                                                            n->m1, n->m2, n->steps); }
     n->ctx->launches++;
     n->ummaDirty = true;
     NRC_CUDA(n, cudaGetLastError());

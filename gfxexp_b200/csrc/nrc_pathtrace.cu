@@ -683,9 +683,10 @@ int launchPathTraceNrc(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* 
     const dim3 block(8, 8);
     const dim3 grid((F.W + 7) / 8, (F.H + 7) / 8);
     const uint32_t scatterGrid = (n.numSuffixes + 127) / 128;
-    k_nrcFirstHit<<<grid, block, 0, stream>>>(s, f, p, ps, n);
-    k_nrcCommitScan<<<1, 1024, 0, stream>>>(n, p.bufferIndex);
-    k_nrcCommitScatter<<<scatterGrid, 128, 0, stream>>>(n, numPixels);
+    { GFX_TIMED(ctx, stream, "nrc_first_hit"); k_nrcFirstHit<<<grid, block, 0, stream>>>(s, f, p, ps, n); }
+    { GFX_TIMED(ctx, stream, "nrc_commit");
+      k_nrcCommitScan<<<1, 1024, 0, stream>>>(n, p.bufferIndex);
+      k_nrcCommitScatter<<<scatterGrid, 128, 0, stream>>>(n, numPixels); }
     ctx->launches += 3;
     const int traceGrid = wavefrontGrid();
     int sms = 148;
@@ -694,11 +695,12 @@ int launchPathTraceNrc(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* 
     const ExtensionHitWriter extWriter{ ps.extHits };
     for (uint32_t round = 0; round < numRounds; ++round) {
         uint32_t* c = F.ptCounters + 4 * round;
-        k_traceWavefront<true, false><<<traceGrid, 128, 0, stream>>>(s.bvh, ps.shadowRays, c + 2, 0u, c + 3, shadowWriter);
-        k_traceWavefront<false, false><<<traceGrid, 128, 0, stream>>>(s.bvh, ps.extRays[round & 1], c + 0, 0u, c + 1, extWriter);
-        k_nrcBounce<<<sms * 16, 64, 0, stream>>>(s, f, p, ps, n, round);
-        k_nrcCommitScan<<<1, 1024, 0, stream>>>(n, p.bufferIndex);
-        k_nrcCommitScatter<<<scatterGrid, 128, 0, stream>>>(n, numPixels);
+        { GFX_TIMED(ctx, stream, "nrc_trace_shadow"); k_traceWavefront<true, false><<<traceGrid, 128, 0, stream>>>(s.bvh, ps.shadowRays, c + 2, 0u, c + 3, shadowWriter); }
+        { GFX_TIMED(ctx, stream, "nrc_trace_extension"); k_traceWavefront<false, false><<<traceGrid, 128, 0, stream>>>(s.bvh, ps.extRays[round & 1], c + 0, 0u, c + 1, extWriter); }
+        { GFX_TIMED(ctx, stream, "nrc_bounce"); k_nrcBounce<<<sms * 16, 64, 0, stream>>>(s, f, p, ps, n, round); }
+        { GFX_TIMED(ctx, stream, "nrc_commit");
+          k_nrcCommitScan<<<1, 1024, 0, stream>>>(n, p.bufferIndex);
+          k_nrcCommitScatter<<<scatterGrid, 128, 0, stream>>>(n, numPixels); }
         ctx->launches += 5;
     }
     // shadow rays requested by the last round (a training path may still have sampled a light there)

@@ -263,10 +263,11 @@ int launchPathTrace(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* par
 
     const dim3 block(8, 8);
     const dim3 grid((F.W + 7) / 8, (p.y1 - p.y0 + 7) / 8);
+    { GFX_TIMED(ctx, stream, "pt_first_hit");
     if (regir)
         k_ptFirstHit<true><<<grid, block, 0, stream>>>(s, f, p, ps, rg);
     else
-        k_ptFirstHit<false><<<grid, block, 0, stream>>>(s, f, p, ps, rg);
+        k_ptFirstHit<false><<<grid, block, 0, stream>>>(s, f, p, ps, rg); }
     ctx->launches++;
     const int traceGrid = wavefrontGrid();
     int sms = 148;
@@ -275,9 +276,10 @@ int launchPathTrace(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* par
     const ExtensionHitWriter extWriter{ ps.extHits };
     for (uint32_t round = 0; round < numRounds; ++round) {
         uint32_t* c = F.ptCounters + 4 * round;
-        k_traceWavefront<true, false><<<traceGrid, 128, 0, stream>>>(s.bvh, ps.shadowRays, c + 2, 0u, c + 3, shadowWriter);
-        k_traceWavefront<false, false><<<traceGrid, 128, 0, stream>>>(s.bvh, ps.extRays[round & 1], c + 0, 0u, c + 1, extWriter);
+        { GFX_TIMED(ctx, stream, "pt_trace_shadow"); k_traceWavefront<true, false><<<traceGrid, 128, 0, stream>>>(s.bvh, ps.shadowRays, c + 2, 0u, c + 3, shadowWriter); }
+        { GFX_TIMED(ctx, stream, "pt_trace_extension"); k_traceWavefront<false, false><<<traceGrid, 128, 0, stream>>>(s.bvh, ps.extRays[round & 1], c + 0, 0u, c + 1, extWriter); }
         const uint32_t maxLengthTerminate = (round + 2 >= maxPathLength || round + 1 == numRounds) ? 1u : 0u;
+        GFX_TIMED(ctx, stream, "pt_bounce");
         if (regir)
             k_ptBounce<true><<<sms * 16, 64, 0, stream>>>(s, f, p, ps, rg, round, maxLengthTerminate);
         else
@@ -286,7 +288,7 @@ int launchPathTrace(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* par
     }
     // the last round requests no rays (maxLengthTerminate), nothing is left in flight
     const uint32_t numPixels = (p.y1 - p.y0) * F.W;
-    k_ptAccumulate<<<(numPixels + 255) / 256, 256, 0, stream>>>(f, p, ps);
+    { GFX_TIMED(ctx, stream, "pt_accumulate"); k_ptAccumulate<<<(numPixels + 255) / 256, 256, 0, stream>>>(f, p, ps); }
     ctx->launches++;
     GFX_CUDA(ctx, cudaGetLastError());
     return GFX_OK;

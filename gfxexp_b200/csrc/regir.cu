@@ -244,6 +244,7 @@ int launchRegirBuildCells(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParam
     const DevRegir rg = makeDevRegir(ctx, params);
     const DevScene s = ctx->devScene();
     const uint32_t grid = (ctx->frame.regir.numSlots + 127) / 128;
+    GFX_TIMED(ctx, stream, "regir_build_cells");
     if (useTemporalReuse)
         k_regirBuildCells<true><<<grid, 128, 0, stream>>>(s, rg, frameIndex);
     else

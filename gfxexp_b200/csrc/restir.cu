@@ -604,28 +604,28 @@ int launchReSTIR(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* params
 #define RIS_LAUNCH(T, U) \
     if (wave && p.reuseVisibility) { \
         int rc_ = resetVisibilityQueue(ctx, stream); if (rc_) return rc_; \
-        k_initialAndTemporalRIS<T, U, 1><<<grid, block, 0, stream>>>(s, f, p); ctx->launches++; \
+        { GFX_TIMED(ctx, stream, "ris_candidates"); k_initialAndTemporalRIS<T, U, 1><<<grid, block, 0, stream>>>(s, f, p); } ctx->launches++; \
         rc_ = traceVisibilityQueue(ctx, stream); if (rc_) return rc_; \
-        k_initialAndTemporalRIS<T, U, 2><<<grid, block, 0, stream>>>(s, f, p); \
+        { GFX_TIMED(ctx, stream, "ris_resolve_temporal"); k_initialAndTemporalRIS<T, U, 2><<<grid, block, 0, stream>>>(s, f, p); } \
     } else { \
-        k_initialAndTemporalRIS<T, U, 0><<<grid, block, 0, stream>>>(s, f, p); \
+        { GFX_TIMED(ctx, stream, "ris_megakernel"); k_initialAndTemporalRIS<T, U, 0><<<grid, block, 0, stream>>>(s, f, p); } \
     }
     switch (pass) {
     case GFX_RESTIR_INITIAL_RIS: RIS_LAUNCH(false, false); break;
     case GFX_RESTIR_INITIAL_AND_TEMPORAL_BIASED: RIS_LAUNCH(true, false); break;
     case GFX_RESTIR_INITIAL_AND_TEMPORAL_UNBIASED: RIS_LAUNCH(true, true); break;
-    case GFX_RESTIR_SPATIAL_BIASED: k_spatialRIS<false><<<grid, block, 0, stream>>>(s, f, p); break;
-    case GFX_RESTIR_SPATIAL_UNBIASED: k_spatialRIS<true><<<grid, block, 0, stream>>>(s, f, p); break;
+    case GFX_RESTIR_SPATIAL_BIASED: { GFX_TIMED(ctx, stream, "spatial_ris"); k_spatialRIS<false><<<grid, block, 0, stream>>>(s, f, p); } break;
+    case GFX_RESTIR_SPATIAL_UNBIASED: { GFX_TIMED(ctx, stream, "spatial_ris_unbiased"); k_spatialRIS<true><<<grid, block, 0, stream>>>(s, f, p); } break;
     case GFX_RESTIR_SHADING: {
         const bool visDone = p.reuseVisibility && (!p.enableTemporalReuse || (p.enableSpatialReuse && p.useUnbiasedEstimator));
         if (wave && !visDone) {
             int rc_ = resetVisibilityQueue(ctx, stream); if (rc_) return rc_;
-            k_shadingRays<<<grid, block, 0, stream>>>(s, f, p); ctx->launches++;
+            { GFX_TIMED(ctx, stream, "shading_rays"); k_shadingRays<<<grid, block, 0, stream>>>(s, f, p); } ctx->launches++;
             rc_ = traceVisibilityQueue(ctx, stream); if (rc_) return rc_;
-            k_shading<true><<<grid, block, 0, stream>>>(s, f, p);
+            { GFX_TIMED(ctx, stream, "shading"); k_shading<true><<<grid, block, 0, stream>>>(s, f, p); }
         }
         else {
-            k_shading<false><<<grid, block, 0, stream>>>(s, f, p);
+            { GFX_TIMED(ctx, stream, "shading_megakernel"); k_shading<false><<<grid, block, 0, stream>>>(s, f, p); }
         }
         break;
     }

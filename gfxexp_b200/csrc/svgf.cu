@@ -458,17 +458,17 @@ int launchSVGF(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* params, 
     const dim3 block(32, 8);
     const dim3 grid((F.W + 31) / 32, (p.y1 - p.y0 + 7) / 8);
     switch (pass) {
-    case GFX_SVGF_TEMPORAL_ACCUMULATE: k_svgfTemporal<<<grid, block, 0, stream>>>(s, p); break;
-    case GFX_SVGF_ESTIMATE_VARIANCE: k_svgfVariance<<<grid, block, 0, stream>>>(s, p); break;
+    case GFX_SVGF_TEMPORAL_ACCUMULATE: { GFX_TIMED(ctx, stream, "svgf_temporal"); k_svgfTemporal<<<grid, block, 0, stream>>>(s, p); } break;
+    case GFX_SVGF_ESTIMATE_VARIANCE: { GFX_TIMED(ctx, stream, "svgf_variance"); k_svgfVariance<<<grid, block, 0, stream>>>(s, p); } break;
     case GFX_SVGF_ATROUS:
         if (stage > 4) {
             ctx->setError("gfx_svgf_launch: à-trous stage must be 0..4 (svgf.cu:232-239)");
             return GFX_ERR_INVALID_ARGUMENT;
         }
-        k_svgfATrous<<<grid, block, 0, stream>>>(s, p, stage);
+        { GFX_TIMED(ctx, stream, "svgf_atrous"); k_svgfATrous<<<grid, block, 0, stream>>>(s, p, stage); }
         break;
-    case GFX_SVGF_FILL_BACKGROUND: k_svgfBackground<<<grid, block, 0, stream>>>(s, p, stage); break;
-    case GFX_SVGF_MODULATE_TAA: k_svgfModulateTAA<<<grid, block, 0, stream>>>(s, p, stage); break;
+    case GFX_SVGF_FILL_BACKGROUND: { GFX_TIMED(ctx, stream, "svgf_background"); k_svgfBackground<<<grid, block, 0, stream>>>(s, p, stage); } break;
+    case GFX_SVGF_MODULATE_TAA: { GFX_TIMED(ctx, stream, "svgf_modulate_taa"); k_svgfModulateTAA<<<grid, block, 0, stream>>>(s, p, stage); } break;
     default:
         ctx->setError("gfx_svgf_launch: unknown pass");
         return GFX_ERR_INVALID_ARGUMENT;

@@ -55,6 +55,7 @@ int traceRays(gfx_ctx* ctx, cudaStream_t stream, const GfxRay* dRays, uint32_t n
     uint32_t* counter = ctx->traceFetchCounter;
     GFX_CUDA(ctx, cudaMemsetAsync(counter, 0, 4, stream));
     const int grid = min(wavefrontGrid(), (int)((numRays + 127) / 128));
+    GFX_TIMED(ctx, stream, "trace_batch");
     switch (mode) {
     case GFX_TRACE_CLOSEST: k_traceWavefront<false, false><<<grid, 128, 0, stream>>>(dev.bvh, r, nullptr, numRays, counter, w); break;
     case GFX_TRACE_ANY: k_traceWavefront<true, false><<<grid, 128, 0, stream>>>(dev.bvh, r, nullptr, numRays, counter, w); break;
@@ -78,6 +79,7 @@ int traceVisibilityQueue(gfx_ctx* ctx, cudaStream_t stream) {
     const DevScene dev = ctx->devScene();
     const FrameState &F = ctx->frame;
     VisibilityWriter w{ F.rayPixel, F.visibility };
+    GFX_TIMED(ctx, stream, "trace_visibility");
     k_traceWavefront<true, false><<<wavefrontGrid(), 128, 0, stream>>>(dev.bvh, F.rayQueue, F.rayCounters, 0u, F.rayCounters + 1, w);
     ctx->launches++;
     GFX_CUDA(ctx, cudaGetLastError());

@@ -144,6 +144,16 @@ class Context:
         self._check(self.lib.gfx_stats_read(self.h, stream, out, 1 if reset else 0), "gfx_stats_read")
         return [int(v) for v in out]
 
+    def timing_enable(self, on: bool = True):
+        self._check(self.lib.gfx_timing_enable(self.h, 1 if on else 0), "gfx_timing_enable")
+
+    def timing_read(self) -> dict:
+        """{kernel label: (total ms, launches)} since the last read; CUDA events around every kernel launch"""
+        buf = (abi.GfxKernelTiming * 64)()
+        n = abi.c_u32()
+        self._check(self.lib.gfx_timing_read(self.h, buf, 64, C.byref(n)), "gfx_timing_read")
+        return {buf[i].label.decode(): (float(buf[i].totalMs), int(buf[i].launches)) for i in range(n.value)}
+
     # -- launches -------------------------------------------------------------------------------
     def gbuffer(self, params, stream=None):
         self._check(self.lib.gfx_gbuffer_launch(self.h, stream, C.byref(params)), "gfx_gbuffer_launch")

@@ -290,6 +290,17 @@ int gfx_synchronize(gfx_ctx* ctx, void* stream);
 /* number of kernels this library has launched since the context was created */
 uint64_t gfx_kernel_launch_count(gfx_ctx* ctx);
 
+/* per-kernel timing for bench.py's roofline: when enabled every kernel launch of this library is bracketed by CUDA
+ * events on its stream; gfx_timing_read synchronises, sums the elapsed times per kernel label since the last read
+ * and returns the number of labels written (at most `capacity`). */
+typedef struct GfxKernelTiming {
+    char label[48];
+    float totalMs;
+    uint32_t launches;
+} GfxKernelTiming;
+int gfx_timing_enable(gfx_ctx* ctx, int enable);
+int gfx_timing_read(gfx_ctx* ctx, GfxKernelTiming* out, uint32_t capacity, uint32_t* numWritten);
+
 /* ---- scene, acceleration structure, light distributions ------------------------------ */
 /* replaces Scene::initialize + createTriangleMeshes/createInstance uploads
  * (common/common_host.h:912-969, common/common_host.cpp:2178-2429,2582-2656) */

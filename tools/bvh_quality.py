@@ -1,0 +1,57 @@
+#!/usr/bin/env python
+"""How much of the frame time is BVH quality?  Renders config-2 frames with (a) the GPU LBVH and (b) the CPU oracle's
+SBVH (bvh::buildGeometryBVH<8> restatement) imported through gfx_bvh_import, and prints ms/frame plus the mean
+traversal statistics of the primary rays for both.  Diagnostic tool (loads the oracle: not part of the product path)."""
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from gfxexp_b200 import abi, engine, scenes
+from tests import oracle_lib
+
+
+def measure(ctx, scene, w, h, tag):
+    r = engine.ReSTIRRenderer(ctx, scene, w, h)
+    for _ in range(3):
+        r.render_frame()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for _ in range(10):
+        r.render_frame()
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[1]) / 10
+    rays = oracle_lib.primary_rays(r.params, w, h)
+    hits = ctx.trace(rays[::7].copy(), abi.TRACE_CLOSEST | abi.TRACE_STATS)
+    ud = hits["instUserData"]
+    info = ctx.bvh_info()
+    return {"bvh": tag, "ms_per_frame": ms, "nodes_per_primary_ray": float((ud & 0xFFFF).mean()),
+            "tris_per_primary_ray": float((ud >> 16).mean()), "numNodes": info.numNodes, "numPrimRefs": info.numPrimRefs}
+
+
+def main():
+    small = "--small" in sys.argv
+    scene = scenes.small_city_scene() if small else scenes.bistro_class_scene()
+    w, h = (640, 360) if small else (1920, 1080)
+    ctx = engine.Context(0)
+    ctx.upload_scene(scene)
+    ctx.build_bvh()
+    ctx.create_frame(w, h)
+    print(json.dumps(measure(ctx, scene, w, h, "gpu-lbvh")))
+    t = time.time()
+    osc = oracle_lib.OracleScene(scene)
+    nodes, refs, tris = osc.export_bvh()
+    print(f"oracle SBVH build {time.time() - t:.1f}s", file=sys.stderr)
+    ctx.import_bvh(nodes, refs, tris)
+    ctx.create_frame(w, h)
+    print(json.dumps(measure(ctx, scene, w, h, "oracle-sbvh")))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,121 @@
+#!/usr/bin/env python
+"""Per-stage timings of the non-headline rows of SURVEY.md §8 on the config-2 scene at 1920x1080 (CUDA events around
+each stage, inputs resident): path tracer (P1), NRC frame (N1-N5), ReGIR frame (C1), SVGF passes (V1-V4).
+One JSON line per stage; `--small` uses the small city at 640x360 for a quick functional run."""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from gfxexp_b200 import abi, engine, scenes
+
+
+class Timer:
+    def __init__(self):
+        self.acc = {}
+
+    def run(self, name, fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        self.acc.setdefault(name, []).append((e0, e1))
+        return out
+
+    def result(self, skip=0):
+        torch.cuda.synchronize()
+        return {k: float(np.mean([a.elapsed_time(b) for a, b in v[skip:]])) for k, v in self.acc.items()}
+
+
+def main():
+    small = "--small" in sys.argv
+    scene = scenes.small_city_scene() if small else scenes.bistro_class_scene()
+    w, h = (640, 360) if small else (1920, 1080)
+    frames, warm = 12, 4
+    ctx = engine.Context(0)
+    ctx.upload_scene(scene)
+    ctx.build_bvh()
+    ctx.create_frame(w, h)
+    ctx.build_light_distributions(0)
+    p = abi.default_frame_params(scene, w, h)
+    npx = w * h
+
+    # ---- P1 path tracer
+    t = Timer()
+    ctx.read_stats(reset=True)
+    for f in range(frames):
+        p.numAccumFrames = f
+        t.run("gbuffer", lambda: ctx.gbuffer(p))
+        if f == warm:
+            torch.cuda.synchronize()
+            ctx.read_stats(reset=True)
+        t.run("pathtrace", lambda: ctx.pathtrace(p))
+    r = t.result(warm)
+    rays = ctx.read_stats()[0] / (frames - warm)
+    print(json.dumps({"stage": "pathtrace_baseline", "ms": r["pathtrace"], "gbuffer_ms": r["gbuffer"], "rays_per_frame": rays,
+                      "Mrays_per_s": rays / ((r["pathtrace"] + r["gbuffer"]) * 1e-3) / 1e6, "width": w, "height": h}))
+
+    # ---- C1 ReGIR
+    t = Timer()
+    p = abi.default_frame_params(scene, w, h)
+    for f in range(frames):
+        p.frameIndex, p.bufferIndex, p.numAccumFrames = f, f % 2, f
+        ctx.gbuffer(p)
+        t.run("build_cells", lambda: ctx.regir_build_cells(p, f, f > 0))
+        t.run("pathtrace_regir", lambda: ctx.pathtrace(p, abi.PT_REGIR))
+        t.run("update_access", lambda: ctx.regir_update_access(p, f))
+    r = t.result(warm)
+    active = int(ctx.download_linear(abi.BUF_REGIR_NUM_ACTIVE_CELLS, params=p)[(frames - 1) % 2, 0])
+    slots = active * abi.REGIR_SLOTS_PER_CELL
+    print(json.dumps({"stage": "regir", **r, "active_cells": active,
+                      "build_GBps_algorithmic": 128.0 * slots / (r["build_cells"] * 1e-3) / 1e9}))
+
+    # ---- N1-N5 NRC frame
+    t = Timer()
+    p = abi.default_frame_params(scene, w, h)
+    net = engine.NeuralRadianceCache(ctx, 2, 1e-2)
+    net.set_params(engine.random_nrc_params(net.num_params, 64 * 64 * 2 + 16 * 64, grid_amplitude=0.1))
+    rng = np.random.default_rng(0)
+    nrc_frames = 24 if not small else frames
+    for f in range(nrc_frames):
+        p.frameIndex, p.bufferIndex, p.numAccumFrames = f, f % 2, f
+        off = [int(rng.integers(0, 2 ** 32)) for _ in range(2)]
+        ctx.gbuffer(p)
+        t.run("preprocess", lambda: ctx.nrc_preprocess(p, off[0], off[1], f == 0))
+        t.run("pathtrace_nrc", lambda: ctx.pathtrace(p, abi.PT_NRC))
+        t.run("infer", lambda: ctx.nrc_frame_infer(net))
+        t.run("accumulate", lambda: ctx.nrc_accumulate(p))
+        t.run("propagate", lambda: ctx.nrc_propagate(p))
+        t.run("shuffle", lambda: ctx.nrc_shuffle(p))
+        t.run("train", lambda: ctx.nrc_frame_train(net))
+    r = t.result(nrc_frames // 2)
+    st = ctx.download_linear(abi.BUF_NRC_STATE)[:, 0]
+    b = (nrc_frames - 1) % 2
+    nq = int(st[abi.NRC_STATE_NUM_INFERENCE_QUERIES])
+    print(json.dumps({"stage": "nrc_frame", **r, "total_ms": sum(r.values()), "num_training_data": int(st[b]),
+                      "tile": [int(st[2 + 2 * b]), int(st[3 + 2 * b])], "inference_queries": nq,
+                      "infer_TFLOPs": 18432.0 * nq / (r["infer"] * 1e-3) / 1e12,
+                      "train_TFLOPs": 55296.0 * 65536 / (r["train"] * 1e-3) / 1e12}))
+    net.close()
+
+    # ---- V1-V4 SVGF on the ReSTIR frame (config 4)
+    t = Timer()
+    ren = engine.ReSTIRRenderer(ctx, scene, w, h)
+    for f in range(frames):
+        ren.render_frame()
+        for pass_id, stage in engine.svgf_frame_passes(ren.params, f):
+            name = {abi.SVGF_TEMPORAL_ACCUMULATE: "temporal", abi.SVGF_ESTIMATE_VARIANCE: "variance", abi.SVGF_ATROUS: "atrous",
+                    abi.SVGF_FILL_BACKGROUND: "background", abi.SVGF_MODULATE_TAA: "modulate_taa"}[pass_id]
+            t.run(name, lambda: ctx.svgf(ren.params, pass_id, stage))
+    r = t.result(0)
+    # a-trous runs 5x per frame: result() averaged per launch
+    total = r["temporal"] + r["variance"] + 5 * r["atrous"] + r["background"] + r["modulate_taa"]
+    print(json.dumps({"stage": "svgf", **{k + "_ms_per_launch": v for k, v in r.items()}, "total_ms_per_frame": total,
+                      "GBps_algorithmic": 456.0 * npx / (total * 1e-3) / 1e9}))
+
+
+if __name__ == "__main__":
+    main()
