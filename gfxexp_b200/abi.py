@@ -68,7 +68,9 @@ class GfxFrameParams(C.Structure):
                 ("maxPathLength", c_u32),
                 ("sceneAabbMin", c_f * 3), ("sceneAabbMax", c_f * 3), ("radianceScale", c_f),
                 ("regirGridDim", c_u32 * 3), ("regirLog2NumCandidatesPerLightSlot", c_u32),
-                ("regirLog2NumCandidatesPerCell", c_u32), ("regirEnableCellRandomization", c_u32)]
+                ("regirLog2NumCandidatesPerCell", c_u32), ("regirEnableCellRandomization", c_u32),
+                ("reuseVisibilityForTemporal", c_u32), ("reuseVisibilityForSpatiotemporal", c_u32),
+                ("radiusThresholdForSpatialVisReuse", c_f)]
 
 
 NODE_DTYPE = np.dtype([("quantBoxOrigin", np.float32, 3), ("quantBoxExpScale", np.uint8, 3),
@@ -87,7 +89,8 @@ assert NODE_DTYPE.itemsize == 80 and TRI_DTYPE.itemsize == 48 and HIT_DTYPE.item
 TRACE_CLOSEST, TRACE_ANY, TRACE_STATS = 0, 1, 2
 PT_BASELINE, PT_NRC, PT_REGIR = 0, 1, 2  # GfxPathTraceVariant
 (RESTIR_INITIAL_RIS, RESTIR_INITIAL_AND_TEMPORAL_BIASED, RESTIR_INITIAL_AND_TEMPORAL_UNBIASED,
- RESTIR_SPATIAL_BIASED, RESTIR_SPATIAL_UNBIASED, RESTIR_SHADING) = range(6)
+ RESTIR_SPATIAL_BIASED, RESTIR_SPATIAL_UNBIASED, RESTIR_SHADING, RESTIR_PRESAMPLE_LIGHTS, RESTIR_PER_PIXEL_RIS,
+ RESTIR_TRACE_SHADOW_RAYS, RESTIR_SHADE_AND_RESAMPLE) = range(10)
 (SVGF_TEMPORAL_ACCUMULATE, SVGF_ESTIMATE_VARIANCE, SVGF_ATROUS, SVGF_FILL_BACKGROUND, SVGF_MODULATE_TAA) = range(5)
 SVGF_IS_FIRST_FRAME, SVGF_ENABLE_TEMPORAL_ACCUMULATION, SVGF_FEEDBACK_1ST, SVGF_ENABLE_TAA, SVGF_MODULATE_ALBEDO = 1, 2, 4, 8, 16
 (BUF_GBUFFER0, BUF_GBUFFER1, BUF_GBUFFER2, BUF_GBUFFER3, BUF_RNG, BUF_RESERVOIR, BUF_RESERVOIR_INFO,
@@ -96,14 +99,14 @@ SVGF_IS_FIRST_FRAME, SVGF_ENABLE_TEMPORAL_ACCUMULATION, SVGF_FEEDBACK_1ST, SVGF_
  BUF_NRC_INFERENCE_QUERY, BUF_NRC_TERMINAL_INFO, BUF_NRC_INFERRED_RADIANCE, BUF_NRC_FRAME_CONTRIBUTION,
  BUF_NRC_TRAIN_QUERY, BUF_NRC_TRAIN_TARGET, BUF_NRC_TRAIN_VERTEX_INFO, BUF_NRC_TRAIN_SUFFIX_TERMINAL,
  BUF_NRC_STATE, BUF_REGIR_SLOTS, BUF_REGIR_SLOT_RNG, BUF_REGIR_CELL_ACCESSES, BUF_REGIR_LAST_ACCESS,
- BUF_REGIR_NUM_ACTIVE_CELLS) = range(30)
+ BUF_REGIR_NUM_ACTIVE_CELLS, BUF_SAMPLE_VISIBILITY, BUF_PRESAMPLED_LIGHTS, BUF_PRESAMPLE_RNG) = range(33)
 
 # logical per-pixel layout of each downloadable buffer: (numpy dtype, elements per pixel, planes)
 BUFFER_LAYOUT = {
     BUF_GBUFFER0: (np.uint32, 4, 1), BUF_GBUFFER1: (np.float32, 2, 1), BUF_GBUFFER2: (np.uint32, 4, 1),
     BUF_GBUFFER3: (np.uint32, 4, 1), BUF_RNG: (np.uint64, 1, 1), BUF_RESERVOIR: (np.uint32, 4, 3),
     BUF_RESERVOIR_INFO: (np.float32, 2, 1), BUF_BEAUTY_ACCUM: (np.float32, 4, 1),
-    BUF_ALBEDO_ACCUM: (np.float32, 4, 1), BUF_NORMAL_ACCUM: (np.float32, 4, 1),
+    BUF_ALBEDO_ACCUM: (np.float32, 4, 1), BUF_NORMAL_ACCUM: (np.float32, 4, 1), BUF_SAMPLE_VISIBILITY: (np.uint32, 1, 1),
     BUF_SVGF_LIGHTING_VARIANCE: (np.float32, 4, 1), BUF_SVGF_FINAL: (np.float32, 4, 1),
     BUF_SVGF_MOMENTS: (np.uint32, 4, 1), BUF_SVGF_PREV_LIGHTING: (np.float32, 4, 1),
     BUF_SVGF_ALBEDO: (np.float32, 4, 1), BUF_SVGF_DEPTH: (np.float32, 1, 1),
@@ -207,6 +210,9 @@ def default_frame_params(scene, width: int, height: int) -> GfxFrameParams:
     p.regirLog2NumCandidatesPerLightSlot = 3
     p.regirLog2NumCandidatesPerCell = 2
     p.regirEnableCellRandomization = 1
+    p.reuseVisibilityForTemporal = 1
+    p.reuseVisibilityForSpatiotemporal = 0
+    p.radiusThresholdForSpatialVisReuse = 10.0
     return p
 
 
@@ -231,6 +237,10 @@ REGIR_SLOTS_PER_CELL = 512  # shared::kNumLightSlotsPerCell
 def linear_buffer_layout(buffer_id: int, width: int, height: int, params=None):
     """(numpy dtype, columns, rows) of the NRC / ReGIR buffers, which are linear rather than image shaped"""
     n = width * height
+    if buffer_id == BUF_PRESAMPLED_LIGHTS:
+        return (np.uint32, 12, 128 * 1024)
+    if buffer_id == BUF_PRESAMPLE_RNG:
+        return (np.uint64, 1, 128 * 1024)
     if BUF_REGIR_SLOTS <= buffer_id <= BUF_REGIR_NUM_ACTIVE_CELLS:
         dim = [int(d) for d in params.regirGridDim] if params is not None else [32, 8, 32]
         if 0 in dim:

@@ -34,6 +34,8 @@ void FrameState::release() {
     cudaFree(stats); cudaFree(rng); cudaFree(beauty); cudaFree(albedo); cudaFree(normal); cudaFree(neighborDeltas);
     cudaFree(svgfPrevLighting); cudaFree(svgfAlbedo); cudaFree(svgfPrevScreenPos);
     cudaFree(ptAlphaPdf); cudaFree(ptRadiance); cudaFree(ptExtHits); cudaFree(ptShadowPending); cudaFree(ptCounters);
+    cudaFree(rearch.preSampledLights); cudaFree(rearch.rngs); cudaFree(rearch.sampleVis[0]); cudaFree(rearch.sampleVis[1]);
+    cudaFree(rearch.rays); cudaFree(rearch.rayPixel); cudaFree(rearch.rayMask); cudaFree(rearch.counters);
     cudaFree(regir.slots[0]); cudaFree(regir.slots[1]); cudaFree(regir.slotRngs); cudaFree(regir.perCellNumAccesses);
     cudaFree(regir.lastAccessFrameIndices); cudaFree(regir.numActiveCells);
     cudaFree(nrc.inferenceQuery); cudaFree(nrc.terminalInfo); cudaFree(nrc.inferredRadiance); cudaFree(nrc.frameContribution);
@@ -97,6 +99,9 @@ DevFrameParams makeDevParams(const gfx_ctx* ctx, const GfxFrameParams* p) {
     d.sceneAabbMin = f3(p->sceneAabbMin[0], p->sceneAabbMin[1], p->sceneAabbMin[2]);
     d.sceneAabbMax = f3(p->sceneAabbMax[0], p->sceneAabbMax[1], p->sceneAabbMax[2]);
     d.radianceScale = p->radianceScale;
+    d.reuseVisibilityForTemporal = p->reuseVisibilityForTemporal;
+    d.reuseVisibilityForSpatiotemporal = p->reuseVisibilityForSpatiotemporal;
+    d.radiusThresholdForSpatialVisReuse = p->radiusThresholdForSpatialVisReuse;
     return d;
 }
 
@@ -670,6 +675,19 @@ static void* bufferPtr(gfx_ctx* ctx, int id, uint32_t index, size_t* bytes) {
         default: break;
         }
     }
+    if (id >= GFX_BUF_SAMPLE_VISIBILITY && id <= GFX_BUF_PRESAMPLE_RNG) {
+        if (ensureRearch(ctx, 0) != GFX_OK) {
+            if (bytes) *bytes = 0;
+            return nullptr;
+        }
+        const FrameState::Rearch &R = F.rearch;
+        switch (id) {
+        case GFX_BUF_SAMPLE_VISIBILITY: p = R.sampleVis[i]; b = n * 4; break;
+        case GFX_BUF_PRESAMPLED_LIGHTS: p = R.preSampledLights; b = (size_t)131072 * 48; break;
+        case GFX_BUF_PRESAMPLE_RNG: p = R.rngs; b = (size_t)131072 * 8; break;
+        default: break;
+        }
+    }
     if (id >= GFX_BUF_REGIR_SLOTS && id <= GFX_BUF_REGIR_NUM_ACTIVE_CELLS && F.regir.created) {
         const FrameState::Regir &R = F.regir;
         switch (id) {
@@ -738,6 +756,8 @@ int gfx_restir_launch(gfx_ctx* ctx, void* stream, const GfxFrameParams* params, 
         ctx->setError("gfx_restir_launch: BVH or frame buffers missing");
         return GFX_ERR_NOT_READY;
     }
+    if (pass >= GFX_RESTIR_PRESAMPLE_LIGHTS)
+        return launchReSTIRRearch(ctx, (cudaStream_t)stream, params, pass);
     return launchReSTIR(ctx, (cudaStream_t)stream, params, pass);
 }
 

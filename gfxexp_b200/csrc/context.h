@@ -109,6 +109,18 @@ struct FrameState {
         float4* stagedNEE = nullptr;
         bool created = false;
     } nrc;
+    // rearchitected ReSTIR (restir_rearch.cu), allocated on first use
+    struct Rearch {
+        float4* preSampledLights = nullptr;   // 128 x 1024 x 48 B
+        unsigned long long* rngs = nullptr;
+        uint32_t* sampleVis[2] = { nullptr, nullptr };
+        float4* rays = nullptr;
+        uint32_t* rayPixel = nullptr;
+        uint32_t* rayMask = nullptr;
+        uint32_t* counters = nullptr;
+        uint32_t raysPerPixel = 0;
+        bool created = false;
+    } rearch;
     // ReGIR grid (regir.cu), (re)allocated by gfx_regir_build_cells when the grid dimensions change
     struct Regir {
         uint32_t dim[3] = { 0, 0, 0 };
@@ -211,6 +223,8 @@ int traceVisibilityQueue(gfx_ctx* ctx, cudaStream_t stream);
 int buildLightDistributions(gfx_ctx* ctx, cudaStream_t stream, uint32_t bufferIndex);
 int launchGBuffer(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* p);
 int launchReSTIR(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* p, int pass);
+int launchReSTIRRearch(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* p, int pass);
+int ensureRearch(gfx_ctx* ctx, uint32_t raysPerPixel);
 int launchSVGF(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* p, int pass, uint32_t stage);
 int launchPathTrace(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* p, int variant);
 int launchPathTraceNrc(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* p);

@@ -125,6 +125,8 @@ struct DevFrameParams {
     uint32_t maxPathLength;
     f3 sceneAabbMin, sceneAabbMax;
     float radianceScale;
+    uint32_t reuseVisibilityForTemporal, reuseVisibilityForSpatiotemporal;
+    float radiusThresholdForSpatialVisReuse;
 };
 
 } // namespace gfx

@@ -323,6 +323,29 @@ def restir_frame_passes(params, frame_index: int, num_spatial_passes: int = 1, t
     yield ("restir", abi.RESTIR_SHADING)
 
 
+def restir_rearch_frame_passes(params, frame_index: int, temporal: bool = True, spatial: bool = True, unbiased: bool = False):
+    """The launch list of one frame of the rearchitected ReSTIR renderer (restir_di_main.cpp:2321-2366, 2423-2493).  Yields
+    (kind, pass_id) with `params` mutated in place as the host mutates plp: reservoirs ping-pong once per frame,
+    spatialNeighborBaseIndex advances by one, and the first frame of a sequence selects the entry points without reuse
+    (here: enableTemporalReuse / enableSpatialReuse = 0 for the launches of that frame)."""
+    params.frameIndex = frame_index
+    params.bufferIndex = frame_index % 2
+    params.useUnbiasedEstimator = 1 if unbiased else 0
+    new_sequence = frame_index == 0
+    params.resetFlowBuffer = 1 if new_sequence else 0
+    params.currentReservoirIndex = frame_index % 2          # (lastReservoirIndex + 1) % 2
+    params.spatialNeighborBaseIndex = frame_index           # ++lastSpatialNeighborBaseIndex per frame
+    yield ("gbuffer", None)
+    yield ("restir", abi.RESTIR_PRESAMPLE_LIGHTS)
+    yield ("restir", abi.RESTIR_PER_PIXEL_RIS)
+    params.enableTemporalReuse = 1 if (temporal and not new_sequence) else 0
+    params.enableSpatialReuse = 1 if (spatial and not new_sequence) else 0
+    yield ("restir", abi.RESTIR_TRACE_SHADOW_RAYS)
+    yield ("restir", abi.RESTIR_SHADE_AND_RESAMPLE)
+    params.enableTemporalReuse = 1 if temporal else 0
+    params.enableSpatialReuse = 1 if spatial else 0
+
+
 def svgf_frame_passes(params, frame_index: int, num_filtering_stages: int = 5):
     """The launch list of the SVGF part of a frame (svgf/svgf_main.cpp:2118-2172): temporal accumulation of
     the demodulated lighting, variance estimate, 5 a-trous stages, background fill, albedo modulation + TAA.

@@ -203,6 +203,10 @@ typedef struct GfxFrameParams {
     uint32_t regirLog2NumCandidatesPerLightSlot;
     uint32_t regirLog2NumCandidatesPerCell;
     uint32_t regirEnableCellRandomization;
+    /* rearchitected ReSTIR (restir_di_main.cpp:1945-1949, 2326-2335) */
+    uint32_t reuseVisibilityForTemporal;        /* true by default */
+    uint32_t reuseVisibilityForSpatiotemporal;  /* false by default */
+    float radiusThresholdForSpatialVisReuse;    /* 10 px by default */
 } GfxFrameParams;
 
 typedef enum GfxSVGFFlags {
@@ -220,7 +224,14 @@ typedef enum GfxReSTIRPass {
     GFX_RESTIR_INITIAL_AND_TEMPORAL_UNBIASED = 2,
     GFX_RESTIR_SPATIAL_BIASED = 3,              /* performSpatialRISBiased */
     GFX_RESTIR_SPATIAL_UNBIASED = 4,
-    GFX_RESTIR_SHADING = 5                      /* shading */
+    GFX_RESTIR_SHADING = 5,                     /* shading */
+    /* rearchitected renderer (restir_di_main.cpp:2423-2493; RearchitectedReSTIREntryPoint :76-87).  The
+     * temporal / spatial / unbiased variants of the last two are selected by params->enableTemporalReuse,
+     * enableSpatialReuse (pass 0 for both on the first frame of a sequence) and useUnbiasedEstimator. */
+    GFX_RESTIR_PRESAMPLE_LIGHTS = 6,            /* performLightPreSampling: 128 subsets x 1024 lights */
+    GFX_RESTIR_PER_PIXEL_RIS = 7,               /* performPerPixelRIS: candidates from the tile's subset */
+    GFX_RESTIR_TRACE_SHADOW_RAYS = 8,           /* traceShadowRays[With{Temporal,Spatial,SpatioTemporal}Reuse{Biased,Unbiased}] */
+    GFX_RESTIR_SHADE_AND_RESAMPLE = 9           /* shadeAndResample[With{Temporal,Spatial,Spatiotemporal}Reuse] */
 } GfxReSTIRPass;
 
 /* path tracer entry points (path_tracing/path_tracing_main.cpp:52-57 PathTracingEntryPoint) */
@@ -279,7 +290,11 @@ typedef enum GfxBufferId {
     GFX_BUF_REGIR_SLOT_RNG = 26,        /* uint64 x numSlots : lightSlotRngs */
     GFX_BUF_REGIR_CELL_ACCESSES = 27,   /* uint32 x numCells : perCellNumAccesses */
     GFX_BUF_REGIR_LAST_ACCESS = 28,     /* uint32 x numCells : lastAccessFrameIndices */
-    GFX_BUF_REGIR_NUM_ACTIVE_CELLS = 29 /* uint32 x2 : numActiveCellsArray */
+    GFX_BUF_REGIR_NUM_ACTIVE_CELLS = 29,/* uint32 x2 : numActiveCellsArray */
+    /* rearchitected ReSTIR */
+    GFX_BUF_SAMPLE_VISIBILITY = 30,     /* [2] uint32 per pixel : SampleVisibility bits (restir_di_shared.h:146-164) */
+    GFX_BUF_PRESAMPLED_LIGHTS = 31,     /* 12 words x 131072 : emittance3 areaPDensity | position3 atInfinity | normal3 0 */
+    GFX_BUF_PRESAMPLE_RNG = 32          /* uint64 x 131072 : lightPreSamplingRngs */
 } GfxBufferId;
 
 /* ---- context ------------------------------------------------------------------------- */

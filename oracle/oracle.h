@@ -66,6 +66,8 @@ void orc_gbuffer(orc_frame* f, const GfxFrameParams* p, int numThreads);
 void orc_restir(orc_frame* f, const GfxFrameParams* p, int pass, int numThreads);
 /* unidirectional path tracer (GfxPathTraceVariant); returns the number of rays traced */
 uint64_t orc_pathtrace(orc_frame* f, const GfxFrameParams* p, int variant, int numThreads);
+/* rearchitected ReSTIR passes GFX_RESTIR_PRESAMPLE_LIGHTS .. GFX_RESTIR_SHADE_AND_RESAMPLE; returns shadow rays traced */
+uint64_t orc_restir_rearch(orc_frame* f, const GfxFrameParams* p, int pass, int numThreads);
 /* ReGIR (build_cell_reservoirs.cu): buildCellReservoirs[AndTemporalReuse], updateLastAccessFrameIndices;
  * buffers via orc_buffer_ptr(GFX_BUF_REGIR_*) once the grid exists */
 void orc_regir_build_cells(orc_frame* f, const GfxFrameParams* p, uint32_t frameIndex, int useTemporalReuse, int numThreads);

@@ -377,6 +377,7 @@ struct orc_frame {
     std::vector<float2> neighborDeltas;
     struct orc_nrc_frame* nrc = nullptr; // NRC buffers, created on first use (nrc_pathtrace.inl)
     struct orc_regir* regir = nullptr;   // ReGIR grid, created on first use (regir.inl)
+    struct orc_rearch* rearch = nullptr; // rearchitected ReSTIR state (restir_rearch.inl)
 };
 
 extern "C" orc_frame* orc_frame_create(orc_scene* s, uint32_t W, uint32_t H) {
@@ -401,11 +402,14 @@ extern "C" orc_frame* orc_frame_create(orc_scene* s, uint32_t W, uint32_t H) {
 }
 static void nrcFrameDestroy(struct orc_nrc_frame* n);
 static void regirDestroy(struct orc_regir* r);
+static void rearchDestroy(struct orc_rearch* r);
 extern "C" void orc_frame_destroy(orc_frame* f) {
     if (f->nrc)
         nrcFrameDestroy(f->nrc);
     if (f->regir)
         regirDestroy(f->regir);
+    if (f->rearch)
+        rearchDestroy(f->rearch);
     delete f;
 }
 
@@ -455,6 +459,7 @@ extern "C" void orc_restir_setup_neighbor_table(orc_frame* f) { // restir_di_mai
 
 static void* nrcBufferPtr(orc_frame* f, int id, uint32_t index, size_t* bytes);
 static void* regirBufferPtr(orc_frame* f, int id, uint32_t index, size_t* bytes);
+static void* rearchBufferPtr(orc_frame* f, int id, uint32_t index, size_t* bytes);
 extern "C" void* orc_buffer_ptr(orc_frame* f, int id, uint32_t index, size_t* bytes) {
     const size_t n = (size_t)f->W * f->H;
     void* p = nullptr;
@@ -471,6 +476,8 @@ extern "C" void* orc_buffer_ptr(orc_frame* f, int id, uint32_t index, size_t* by
     case GFX_BUF_ALBEDO_ACCUM: p = f->albedo.data(); b = n * 16; break;
     case GFX_BUF_NORMAL_ACCUM: p = f->normal.data(); b = n * 16; break;
     default:
+        if (id >= GFX_BUF_SAMPLE_VISIBILITY)
+            return rearchBufferPtr(f, id, index, bytes);
         if (id >= GFX_BUF_REGIR_SLOTS)
             return regirBufferPtr(f, id, index, bytes);
         return nrcBufferPtr(f, id, index, bytes);
@@ -1233,3 +1240,9 @@ extern "C" void orc_restir(orc_frame* f, const GfxFrameParams* p, int pass, int 
 #include "pathtrace.inl"
 #include "nrc_pathtrace.inl"
 #include "regir.inl"
+#include "restir_rearch.inl"
+
+extern "C" uint64_t orc_restir_rearch(orc_frame* f, const GfxFrameParams* p, int pass, int numThreads) {
+    if (numThreads <= 0) numThreads = omp_get_max_threads();
+    return restirRearch(f, p, pass, numThreads);
+}

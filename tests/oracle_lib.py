@@ -74,6 +74,8 @@ def lib() -> C.CDLL:
         L.orc_restir.argtypes = [vp, C.POINTER(abi.GfxFrameParams), C.c_int, C.c_int]
         L.orc_pathtrace.argtypes = [vp, C.POINTER(abi.GfxFrameParams), C.c_int, C.c_int]
         L.orc_pathtrace.restype = C.c_uint64
+        L.orc_restir_rearch.argtypes = [vp, C.POINTER(abi.GfxFrameParams), C.c_int, C.c_int]
+        L.orc_restir_rearch.restype = C.c_uint64
         L.orc_regir_build_cells.argtypes = [vp, C.POINTER(abi.GfxFrameParams), C.c_uint32, C.c_int, C.c_int]
         L.orc_regir_update_access.argtypes = [vp, C.POINTER(abi.GfxFrameParams), C.c_uint32]
         L.orc_nrc_preprocess.argtypes = [vp, C.POINTER(abi.GfxFrameParams), C.c_uint32, C.c_uint32, C.c_int]
@@ -213,6 +215,10 @@ class OracleFrame:
         raw = (C.c_uint8 * nbytes.value).from_address(ptr)
         arr = np.frombuffer(raw, dtype=dtype).reshape(rows, cols)
         return arr.copy() if copy else arr
+
+    def restir_rearch(self, params, pass_id: int, threads: int = 0) -> int:
+        """rearchitected ReSTIR passes (RESTIR_PRESAMPLE_LIGHTS .. RESTIR_SHADE_AND_RESAMPLE); returns shadow rays traced"""
+        return int(lib().orc_restir_rearch(self.h, C.byref(params), pass_id, threads))
 
     def regir_build_cells(self, params, frame_index: int, temporal: bool, threads: int = 0):
         lib().orc_regir_build_cells(self.h, C.byref(params), frame_index & 0xFFFFFFFF, 1 if temporal else 0, threads)
