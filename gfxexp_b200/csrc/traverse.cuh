@@ -105,42 +105,60 @@ GFX_D bool traverseStep(const DevBvh &bvh, TraversalState &st) {
     const float by = (__uint_as_float(n0.y) - st.org.y) * st.idir.y;
     const float bz = (__uint_as_float(n0.z) - st.org.z) * st.idir.z;
 
+    // The sign of the ray direction decides which quantised plane of each axis is entered first, once per node and
+    // axis instead of a min/max pair per child (same t values as min(tlo, thi) / max(tlo, thi)).
+    const bool sx = st.idir.x < 0.0f, sy = st.idir.y < 0.0f, sz = st.idir.z < 0.0f;
+    const uint32_t nearX[2] = { sx ? n3.z : n2.x, sx ? n3.w : n2.y }, farX[2] = { sx ? n2.x : n3.z, sx ? n2.y : n3.w };
+    const uint32_t nearY[2] = { sy ? n4.x : n2.z, sy ? n4.y : n2.w }, farY[2] = { sy ? n2.z : n4.x, sy ? n2.w : n4.y };
+    const uint32_t nearZ[2] = { sz ? n4.z : n3.x, sz ? n4.w : n3.y }, farZ[2] = { sz ? n3.x : n4.z, sz ? n3.y : n4.w };
+    const uint32_t invalidNearX = sx ? 0u : 255u, invalidFarX = sx ? 255u : 0u; // (qminx, qmaxx) = (255, 0) marks an empty slot
+
     uint32_t keys[8];
 #pragma unroll
     for (int slot = 0; slot < 8; ++slot) {
-        const int sh = 8 * (slot & 3);
-        const uint32_t qminx = ((slot < 4 ? n2.x : n2.y) >> sh) & 0xFFu;
-        const uint32_t qminy = ((slot < 4 ? n2.z : n2.w) >> sh) & 0xFFu;
-        const uint32_t qminz = ((slot < 4 ? n3.x : n3.y) >> sh) & 0xFFu;
-        const uint32_t qmaxx = ((slot < 4 ? n3.z : n3.w) >> sh) & 0xFFu;
-        const uint32_t qmaxy = ((slot < 4 ? n4.x : n4.y) >> sh) & 0xFFu;
-        const uint32_t qmaxz = ((slot < 4 ? n4.z : n4.w) >> sh) & 0xFFu;
-        const bool valid = (qminx != 255u) || (qmaxx != 0u);
-        const float tlx = __fmaf_rn((float)qminx, ax, bx), thx = __fmaf_rn((float)qmaxx, ax, bx);
-        const float tly = __fmaf_rn((float)qminy, ay, by), thy = __fmaf_rn((float)qmaxy, ay, by);
-        const float tlz = __fmaf_rn((float)qminz, az, bz), thz = __fmaf_rn((float)qmaxz, az, bz);
-        const float tn = fmaxf(fmaxf(fminf(tlx, thx), fminf(tly, thy)), fmaxf(fminf(tlz, thz), st.tmin));
-        const float tf = fminf(fminf(fmaxf(tlx, thx), fmaxf(tly, thy)), fminf(fmaxf(tlz, thz), st.best.dist));
+        const int sh = 8 * (slot & 3), w = slot >> 2;
+        const uint32_t qnx = (nearX[w] >> sh) & 0xFFu, qfx = (farX[w] >> sh) & 0xFFu;
+        const uint32_t qny = (nearY[w] >> sh) & 0xFFu, qfy = (farY[w] >> sh) & 0xFFu;
+        const uint32_t qnz = (nearZ[w] >> sh) & 0xFFu, qfz = (farZ[w] >> sh) & 0xFFu;
+        const bool valid = (qnx != invalidNearX) || (qfx != invalidFarX);
+        const float tnx = __fmaf_rn((float)qnx, ax, bx), tfx = __fmaf_rn((float)qfx, ax, bx);
+        const float tny = __fmaf_rn((float)qny, ay, by), tfy = __fmaf_rn((float)qfy, ay, by);
+        const float tnz = __fmaf_rn((float)qnz, az, bz), tfz = __fmaf_rn((float)qfz, az, bz);
+        const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, st.tmin));
+        const float tf = fminf(fminf(tfx, tfy), fminf(tfz, st.best.dist));
         const bool hit = valid && (tn <= tf * 1.00001f);
         const uint32_t isInternal = (internalMask >> slot) & 1u;
         keys[slot] = hit ? ((isInternal << 31) | ((__float_as_uint(tn) >> 1) & 0x7FFFFFF8u) | (uint32_t)slot)
                          : 0xFFFFFFFFu;
     }
-    // 19-comparator network, ascending: leaf hits (near..far), internal hits (near..far), misses
+    // 19-comparator network, ascending: leaf hits (near..far), internal hits (near..far), misses.
+    // Visibility rays stop at the first hit whatever the order, so they only need leaves before internal nodes:
+    // GFX_ANYHIT_UNSORTED (A/B switch) skips the network and keeps the slot order within each group.
+#if defined(GFX_ANYHIT_UNSORTED)
+    if (!ANY_HIT) {
+#endif
     GFX_CSWAP(keys[0], keys[2]); GFX_CSWAP(keys[1], keys[3]); GFX_CSWAP(keys[4], keys[6]); GFX_CSWAP(keys[5], keys[7]);
     GFX_CSWAP(keys[0], keys[4]); GFX_CSWAP(keys[1], keys[5]); GFX_CSWAP(keys[2], keys[6]); GFX_CSWAP(keys[3], keys[7]);
     GFX_CSWAP(keys[0], keys[1]); GFX_CSWAP(keys[2], keys[3]); GFX_CSWAP(keys[4], keys[5]); GFX_CSWAP(keys[6], keys[7]);
     GFX_CSWAP(keys[2], keys[4]); GFX_CSWAP(keys[3], keys[5]);
     GFX_CSWAP(keys[1], keys[4]); GFX_CSWAP(keys[3], keys[6]);
     GFX_CSWAP(keys[1], keys[2]); GFX_CSWAP(keys[3], keys[4]); GFX_CSWAP(keys[5], keys[6]);
+#if defined(GFX_ANYHIT_UNSORTED)
+    }
+#endif
 
     // ---- leaf children: intersect their triangle chains now (shrinks best.dist before descending)
     const uint32_t leafBase = n1.y;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const uint32_t key = keys[k];
-        if (key >= 0x80000000u)
+        if (key >= 0x80000000u) {
+#if defined(GFX_ANYHIT_UNSORTED)
+            if (ANY_HIT)
+                continue;
+#endif
             break;
+        }
         const uint32_t slot = key & 7u;
         const float tn = __uint_as_float((key & 0x7FFFFFF8u) << 1);
         if (tn > st.best.dist)

@@ -26,11 +26,16 @@ def _random_rays(info, n, seed):
     return rays
 
 
-@pytest.mark.parametrize("scene_fn,w,h", [(scenes.tiny_city_scene, 160, 96), (scenes.small_city_scene, 320, 200)])
-def test_lbvh_format_and_closest_hit(gfx_ctx, oracle, scene_fn, w, h):
+BVH_BUILD_FAST = 0x100  # GFX_BVH_BUILD_FAST: Karras LBVH hierarchy instead of the default PLOC clustering
+
+
+@pytest.mark.parametrize("scene_fn,w,h,flags", [(scenes.tiny_city_scene, 160, 96, 0), (scenes.small_city_scene, 320, 200, 0),
+                                                (scenes.small_city_scene, 320, 200, BVH_BUILD_FAST),
+                                                (scenes.tiny_city_scene, 160, 96, BVH_BUILD_FAST | 2)])
+def test_lbvh_format_and_closest_hit(gfx_ctx, oracle, scene_fn, w, h, flags):
     scene = scene_fn()
     gfx_ctx.upload_scene(scene)
-    gfx_ctx.build_bvh()
+    gfx_ctx.build_bvh(flags)
     info = gfx_ctx.bvh_info()
     assert info.numTriangles == scene.num_triangles
     assert info.numPrimRefs == info.numTriangles  # LBVH never duplicates references

@@ -41,9 +41,24 @@ def main():
     w, h = (640, 360) if small else (1920, 1080)
     ctx = engine.Context(0)
     ctx.upload_scene(scene)
-    ctx.build_bvh()
-    ctx.create_frame(w, h)
-    print(json.dumps(measure(ctx, scene, w, h, "gpu-lbvh")))
+    variants = [("gpu-lbvh (GFX_BVH_BUILD_FAST)", 0x100), ("gpu-ploc (default)", 0)]
+    if "--sweep" in sys.argv:
+        variants = [(f"ploc r={r} maxLeaf={ml}", (r << 16) | ml) for r in (16, 32, 64) for ml in (2, 3, 4, 6)] + \
+                   [(f"lbvh maxLeaf={ml}", 0x100 | ml) for ml in (2, 3, 6)]
+    for tag, flags in variants:
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ctx.build_bvh(flags)
+        torch.cuda.synchronize()
+        ev[0].record()
+        ctx.build_bvh(flags)
+        ev[1].record()
+        torch.cuda.synchronize()
+        ctx.create_frame(w, h)
+        res = measure(ctx, scene, w, h, tag)
+        res["build_ms"] = ev[0].elapsed_time(ev[1])
+        print(json.dumps(res))
+    if "--no-sbvh" in sys.argv:
+        return
     t = time.time()
     osc = oracle_lib.OracleScene(scene)
     nodes, refs, tris = osc.export_bvh()
