@@ -15,6 +15,10 @@ void SceneState::release() {
     cudaFree(primWeights); cudaFree(primCdf); cudaFree(geomWeights); cudaFree(geomCdf);
     cudaFree(instWeights); cudaFree(instCdf); cudaFree(instIntegral);
     cudaFree(primProb); cudaFree(geomProb); cudaFree(instProb); cudaFree(lightTris); cudaFree(lightTriBase); cudaFree(emissiveGeoms); cudaFree(instGuide); cudaFree(primGuide);
+    for (int i = 0; i < 2; ++i) {
+        if (pinnedInstances[i]) cudaFreeHost(pinnedInstances[i]);
+        if (pinnedInstancesFree[i]) cudaEventDestroy(pinnedInstancesFree[i]);
+    }
     *this = SceneState();
 }
 void BvhState::release() {
@@ -376,10 +380,21 @@ int gfx_scene_update_instances(gfx_ctx* ctx, void* stream, const GfxInstanceDesc
         d.uniformScale = instances[i].uniformScale;
     }
     S.lightTrisDirty = true;
-    // geomIntegral lives on the device copy only: patch the transform part of each record
-    for (uint32_t i = 0; i < numInstances; ++i)
-        GFX_CUDA(ctx, cudaMemcpyAsync(S.instances + i, &S.hostInstances[i], offsetof(DevInstance, firstMeshSlot),
-                                      cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    // geomIntegral lives on the device copy only: patch the transform part of every record with ONE strided copy
+    // out of pinned memory (double-buffered so that the host may run a frame ahead of the device)
+    const size_t bytes = (size_t)numInstances * sizeof(DevInstance);
+    if (!S.pinnedInstances[0]) {
+        for (int i = 0; i < 2; ++i) {
+            GFX_CUDA(ctx, cudaMallocHost(&S.pinnedInstances[i], bytes));
+            GFX_CUDA(ctx, cudaEventCreateWithFlags(&S.pinnedInstancesFree[i], cudaEventDisableTiming));
+        }
+    }
+    const uint32_t slot = S.pinnedInstancesNext++ & 1u;
+    GFX_CUDA(ctx, cudaEventSynchronize(S.pinnedInstancesFree[slot]));
+    memcpy(S.pinnedInstances[slot], S.hostInstances.data(), bytes);
+    GFX_CUDA(ctx, cudaMemcpy2DAsync(S.instances, sizeof(DevInstance), S.pinnedInstances[slot], sizeof(DevInstance),
+                                    offsetof(DevInstance, firstMeshSlot), numInstances, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    GFX_CUDA(ctx, cudaEventRecord(S.pinnedInstancesFree[slot], (cudaStream_t)stream));
     return GFX_OK;
 }
 

@@ -40,6 +40,10 @@ struct SceneState {
     bool lightTrisDirty = true;
     std::vector<DevMesh> hostMeshes;
     std::vector<DevInstance> hostInstances;
+    // pinned staging for gfx_scene_update_instances (per-frame instance animation)
+    DevInstance* pinnedInstances[2] = { nullptr, nullptr };
+    cudaEvent_t pinnedInstancesFree[2] = { nullptr, nullptr };
+    uint32_t pinnedInstancesNext = 0;
     void release();
 };
 
