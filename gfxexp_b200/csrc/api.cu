@@ -36,7 +36,7 @@ void FrameState::release() {
     }
     cudaFree(rayQueue); cudaFree(rayPixel); cudaFree(rayCounters); cudaFree(visibility);
     cudaFree(stats); cudaFree(rng); cudaFree(beauty); cudaFree(albedo); cudaFree(normal); cudaFree(neighborDeltas);
-    cudaFree(svgfPrevLighting); cudaFree(svgfAlbedo); cudaFree(svgfPrevScreenPos);
+    cudaFree(svgfPrevLighting); cudaFree(svgfAlbedo); cudaFree(svgfPrevScreenPos); cudaFree(svgfNormal);
     cudaFree(ptAlphaPdf); cudaFree(ptRadiance); cudaFree(ptExtHits); cudaFree(ptShadowPending); cudaFree(ptCounters);
     cudaFree(rearch.preSampledLights); cudaFree(rearch.rngs); cudaFree(rearch.sampleVis[0]); cudaFree(rearch.sampleVis[1]);
     cudaFree(rearch.rays); cudaFree(rearch.rayPixel); cudaFree(rearch.rayMask); cudaFree(rearch.counters);
@@ -547,6 +547,8 @@ int gfx_frame_create(gfx_ctx* ctx, uint32_t W, uint32_t H) {
     }
     GFX_CUDA(ctx, cudaMalloc(&F.svgfPrevLighting, n * 16));
     GFX_CUDA(ctx, cudaMemset(F.svgfPrevLighting, 0, n * 16));
+    GFX_CUDA(ctx, cudaMalloc(&F.svgfNormal, n * 16));
+    GFX_CUDA(ctx, cudaMemset(F.svgfNormal, 0, n * 16));
     GFX_CUDA(ctx, cudaMalloc(&F.svgfAlbedo, n * 16));
     GFX_CUDA(ctx, cudaMemset(F.svgfAlbedo, 0, n * 16));
     GFX_CUDA(ctx, cudaMalloc(&F.svgfPrevScreenPos, n * 8));

@@ -142,6 +142,7 @@ struct FrameState {
     float4* svgfMoments[2] = { nullptr, nullptr };   // first/second luminance moments + history length
     float4* svgfPrevLighting = nullptr;
     float4* svgfAlbedo = nullptr;
+    float4* svgfNormal = nullptr;
     float2* svgfPrevScreenPos = nullptr;
     float4* svgfFinal[2] = { nullptr, nullptr };
     float* svgfDepth[2] = { nullptr, nullptr };

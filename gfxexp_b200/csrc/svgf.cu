@@ -32,6 +32,8 @@ struct DevSvgf {
     float4* prevLighting;
     float4* albedo;
     float* depth[2];
+    float4* normal;           // decoded shading normal of the current frame (written by the temporal pass): the filters
+                              // read it instead of running decodeVector (two sincos) per tap and stage
     float4* finalLighting[2];
     float2* prevScreenPos;
     float m22, m23;
@@ -80,6 +82,7 @@ __global__ void __launch_bounds__(256) k_svgfTemporal(DevSvgf s, DevFrameParams 
     const uint32_t materialSlot = gb3.w;
     if (instSlot == 0xFFFFFFFFu) {
         s.depth[curBufIdx][pix] = 1.0f;
+        s.normal[pix] = make_float4(0, 0, 0, 0);
         s.lighting[0][pix] = make_float4(0, 0, 0, 0);
         s.moments[curBufIdx][pix] = make_float4(0, 0, 0, 0);
         return;
@@ -87,6 +90,7 @@ __global__ void __launch_bounds__(256) k_svgfTemporal(DevSvgf s, DevFrameParams 
     const float4 gb2 = s.gb2[curBufIdx][pix];
     const f3 positionInWorld(gb2.x, gb2.y, gb2.z);
     const f3 shadingNormalInWorld = decodeVector(gb3.x);
+    s.normal[pix] = make_float4(shadingNormalInWorld.x, shadingNormalInWorld.y, shadingNormalInWorld.z, 0.0f);
 
     const f3 posInView = mul3x3(p.camera.invOrientation, positionInWorld - p.camera.position);
     const float zv = -posInView.z;
@@ -201,7 +205,7 @@ __global__ void __launch_bounds__(256) k_svgfVariance(DevSvgf s, DevFrameParams 
         const float vnbDepth = depthBuf[(size_t)(y + dy) * W + x];
         const float dzdx = (hnbDepth - depth) * dx;
         const float dzdy = (vnbDepth - depth) * dy;
-        const f3 normal = decodeVector(s.gb3[curBufIdx][pix].x);
+        const f3 normal = xyz(s.normal[pix]);
         float sumWeights = centerWeight;
         for (int i = -3; i <= 3; ++i) {
             const int nbPixY = y + i;
@@ -219,7 +223,7 @@ __global__ void __launch_bounds__(256) k_svgfVariance(DevSvgf s, DevFrameParams 
                 const float nbDepth = depthBuf[nb];
                 if (nbDepth == 1.0f)
                     continue;
-                const f3 nbNormal = decodeVector(s.gb3[curBufIdx][nb].x);
+                const f3 nbNormal = xyz(s.normal[nb]);
                 const float wz = calcDepthWeight(nbDepth, depth, dzdx, dzdy, j, i);
                 const float wn = calcNormalWeight(nbNormal, normal);
                 const float weight = hx * hy * wz * wn;
@@ -253,7 +257,7 @@ __global__ void __launch_bounds__(256) k_svgfATrous(DevSvgf s, DevFrameParams p,
     const float luminance = sRGB_calcLuminance(xyz(srcLv));
 
     const float* __restrict__ depthBuf = s.depth[curBufIdx];
-    const uint4* __restrict__ gb3 = s.gb3[curBufIdx];
+    const float4* __restrict__ normals = s.normal;
     const float depth = __ldg(depthBuf + pix);
     const int32_t dx = x < W / 2 ? 1 : -1;
     const int32_t dy = y < H / 2 ? 1 : -1;
@@ -261,7 +265,7 @@ __global__ void __launch_bounds__(256) k_svgfATrous(DevSvgf s, DevFrameParams p,
     const float vnbDepth = __ldg(depthBuf + (size_t)(y + dy) * W + x);
     const float dzdx = (hnbDepth - depth) * dx;
     const float dzdy = (vnbDepth - depth) * dy;
-    const f3 normal = decodeVector(__ldg(gb3 + pix).x);
+    const f3 normal = xyz(__ldg(normals + pix));
 
     const float gaussKernel[] = { 1 / 4.0f, 1 / 2.0f, 1 / 4.0f };
     float sumLocalVars = 0.0f;
@@ -298,7 +302,7 @@ __global__ void __launch_bounds__(256) k_svgfATrous(DevSvgf s, DevFrameParams p,
         const float nbDepth = __ldg(depthBuf + nb);
         if (nbDepth == 1.0f)
             continue;
-        const f3 nbNormal = decodeVector(__ldg(gb3 + nb).x);
+        const f3 nbNormal = xyz(__ldg(normals + nb));
         const float wz = calcDepthWeight(nbDepth, depth, dzdx, dzdy, ox, oy);
         const float wn = calcNormalWeight(nbNormal, normal);
         const float4 nbLv = __ldg(src + nb);
@@ -447,6 +451,7 @@ int launchSVGF(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* params, 
     s.prevLighting = F.svgfPrevLighting;
     s.albedo = F.svgfAlbedo;
     s.prevScreenPos = F.svgfPrevScreenPos;
+    s.normal = F.svgfNormal;
     // camera(aspect, fovY, 0.1, 1000) depth row (svgf_main.cpp:1473-1478, basic_types.h:4899-4917)
     const float nearZ = 0.1f, farZ = 1000.0f;
     const float dz = farZ - nearZ;

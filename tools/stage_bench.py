@@ -42,79 +42,103 @@ def main():
     ctx.build_light_distributions(0)
     p = abi.default_frame_params(scene, w, h)
     npx = w * h
+    only = sys.argv[sys.argv.index("--only") + 1].split(",") if "--only" in sys.argv else None
 
-    # ---- P1 path tracer
-    t = Timer()
-    ctx.read_stats(reset=True)
-    for f in range(frames):
-        p.numAccumFrames = f
-        t.run("gbuffer", lambda: ctx.gbuffer(p))
-        if f == warm:
-            torch.cuda.synchronize()
-            ctx.read_stats(reset=True)
-        t.run("pathtrace", lambda: ctx.pathtrace(p))
-    r = t.result(warm)
-    rays = ctx.read_stats()[0] / (frames - warm)
-    print(json.dumps({"stage": "pathtrace_baseline", "ms": r["pathtrace"], "gbuffer_ms": r["gbuffer"], "rays_per_frame": rays,
-                      "Mrays_per_s": rays / ((r["pathtrace"] + r["gbuffer"]) * 1e-3) / 1e6, "width": w, "height": h}))
+    def want(name):
+        return only is None or name in only
 
-    # ---- C1 ReGIR
-    t = Timer()
-    p = abi.default_frame_params(scene, w, h)
-    for f in range(frames):
-        p.frameIndex, p.bufferIndex, p.numAccumFrames = f, f % 2, f
-        ctx.gbuffer(p)
-        t.run("build_cells", lambda: ctx.regir_build_cells(p, f, f > 0))
-        t.run("pathtrace_regir", lambda: ctx.pathtrace(p, abi.PT_REGIR))
-        t.run("update_access", lambda: ctx.regir_update_access(p, f))
-    r = t.result(warm)
-    active = int(ctx.download_linear(abi.BUF_REGIR_NUM_ACTIVE_CELLS, params=p)[(frames - 1) % 2, 0])
-    slots = active * abi.REGIR_SLOTS_PER_CELL
-    print(json.dumps({"stage": "regir", **r, "active_cells": active,
-                      "build_GBps_algorithmic": 128.0 * slots / (r["build_cells"] * 1e-3) / 1e9}))
+    def stage_pathtrace():
+        nonlocal p
+        # ---- P1 path tracer
+        t = Timer()
+        ctx.read_stats(reset=True)
+        for f in range(frames):
+            p.numAccumFrames = f
+            t.run("gbuffer", lambda: ctx.gbuffer(p))
+            if f == warm:
+                torch.cuda.synchronize()
+                ctx.read_stats(reset=True)
+            t.run("pathtrace", lambda: ctx.pathtrace(p))
+        r = t.result(warm)
+        rays = ctx.read_stats()[0] / (frames - warm)
+        print(json.dumps({"stage": "pathtrace_baseline", "ms": r["pathtrace"], "gbuffer_ms": r["gbuffer"], "rays_per_frame": rays,
+                          "Mrays_per_s": rays / ((r["pathtrace"] + r["gbuffer"]) * 1e-3) / 1e6, "width": w, "height": h}))
 
-    # ---- N1-N5 NRC frame
-    t = Timer()
-    p = abi.default_frame_params(scene, w, h)
-    net = engine.NeuralRadianceCache(ctx, 2, 1e-2)
-    net.set_params(engine.random_nrc_params(net.num_params, 64 * 64 * 2 + 16 * 64, grid_amplitude=0.1))
-    rng = np.random.default_rng(0)
-    nrc_frames = 24 if not small else frames
-    for f in range(nrc_frames):
-        p.frameIndex, p.bufferIndex, p.numAccumFrames = f, f % 2, f
-        off = [int(rng.integers(0, 2 ** 32)) for _ in range(2)]
-        ctx.gbuffer(p)
-        t.run("preprocess", lambda: ctx.nrc_preprocess(p, off[0], off[1], f == 0))
-        t.run("pathtrace_nrc", lambda: ctx.pathtrace(p, abi.PT_NRC))
-        t.run("infer", lambda: ctx.nrc_frame_infer(net))
-        t.run("accumulate", lambda: ctx.nrc_accumulate(p))
-        t.run("propagate", lambda: ctx.nrc_propagate(p))
-        t.run("shuffle", lambda: ctx.nrc_shuffle(p))
-        t.run("train", lambda: ctx.nrc_frame_train(net))
-    r = t.result(nrc_frames // 2)
-    st = ctx.download_linear(abi.BUF_NRC_STATE)[:, 0]
-    b = (nrc_frames - 1) % 2
-    nq = int(st[abi.NRC_STATE_NUM_INFERENCE_QUERIES])
-    print(json.dumps({"stage": "nrc_frame", **r, "total_ms": sum(r.values()), "num_training_data": int(st[b]),
-                      "tile": [int(st[2 + 2 * b]), int(st[3 + 2 * b])], "inference_queries": nq,
-                      "infer_TFLOPs": 18432.0 * nq / (r["infer"] * 1e-3) / 1e12,
-                      "train_TFLOPs": 55296.0 * 65536 / (r["train"] * 1e-3) / 1e12}))
-    net.close()
+    if want("pathtrace"):
+        stage_pathtrace()
 
-    # ---- V1-V4 SVGF on the ReSTIR frame (config 4)
-    t = Timer()
-    ren = engine.ReSTIRRenderer(ctx, scene, w, h)
-    for f in range(frames):
-        ren.render_frame()
-        for pass_id, stage in engine.svgf_frame_passes(ren.params, f):
-            name = {abi.SVGF_TEMPORAL_ACCUMULATE: "temporal", abi.SVGF_ESTIMATE_VARIANCE: "variance", abi.SVGF_ATROUS: "atrous",
-                    abi.SVGF_FILL_BACKGROUND: "background", abi.SVGF_MODULATE_TAA: "modulate_taa"}[pass_id]
-            t.run(name, lambda: ctx.svgf(ren.params, pass_id, stage))
-    r = t.result(0)
-    # a-trous runs 5x per frame: result() averaged per launch
-    total = r["temporal"] + r["variance"] + 5 * r["atrous"] + r["background"] + r["modulate_taa"]
-    print(json.dumps({"stage": "svgf", **{k + "_ms_per_launch": v for k, v in r.items()}, "total_ms_per_frame": total,
-                      "GBps_algorithmic": 456.0 * npx / (total * 1e-3) / 1e9}))
+    def stage_regir():
+        nonlocal p
+        # ---- C1 ReGIR
+        t = Timer()
+        p = abi.default_frame_params(scene, w, h)
+        for f in range(frames):
+            p.frameIndex, p.bufferIndex, p.numAccumFrames = f, f % 2, f
+            ctx.gbuffer(p)
+            t.run("build_cells", lambda: ctx.regir_build_cells(p, f, f > 0))
+            t.run("pathtrace_regir", lambda: ctx.pathtrace(p, abi.PT_REGIR))
+            t.run("update_access", lambda: ctx.regir_update_access(p, f))
+        r = t.result(warm)
+        active = int(ctx.download_linear(abi.BUF_REGIR_NUM_ACTIVE_CELLS, params=p)[(frames - 1) % 2, 0])
+        slots = active * abi.REGIR_SLOTS_PER_CELL
+        print(json.dumps({"stage": "regir", **r, "active_cells": active,
+                          "build_GBps_algorithmic": 128.0 * slots / (r["build_cells"] * 1e-3) / 1e9}))
+
+    if want("regir"):
+        stage_regir()
+
+    def stage_nrc():
+        nonlocal p
+        # ---- N1-N5 NRC frame
+        t = Timer()
+        p = abi.default_frame_params(scene, w, h)
+        net = engine.NeuralRadianceCache(ctx, 2, 1e-2)
+        net.set_params(engine.random_nrc_params(net.num_params, 64 * 64 * 2 + 16 * 64, grid_amplitude=0.1))
+        rng = np.random.default_rng(0)
+        nrc_frames = 24 if not small else frames
+        for f in range(nrc_frames):
+            p.frameIndex, p.bufferIndex, p.numAccumFrames = f, f % 2, f
+            off = [int(rng.integers(0, 2 ** 32)) for _ in range(2)]
+            ctx.gbuffer(p)
+            t.run("preprocess", lambda: ctx.nrc_preprocess(p, off[0], off[1], f == 0))
+            t.run("pathtrace_nrc", lambda: ctx.pathtrace(p, abi.PT_NRC))
+            t.run("infer", lambda: ctx.nrc_frame_infer(net))
+            t.run("accumulate", lambda: ctx.nrc_accumulate(p))
+            t.run("propagate", lambda: ctx.nrc_propagate(p))
+            t.run("shuffle", lambda: ctx.nrc_shuffle(p))
+            t.run("train", lambda: ctx.nrc_frame_train(net))
+        r = t.result(nrc_frames // 2)
+        st = ctx.download_linear(abi.BUF_NRC_STATE)[:, 0]
+        b = (nrc_frames - 1) % 2
+        nq = int(st[abi.NRC_STATE_NUM_INFERENCE_QUERIES])
+        print(json.dumps({"stage": "nrc_frame", **r, "total_ms": sum(r.values()), "num_training_data": int(st[b]),
+                          "tile": [int(st[2 + 2 * b]), int(st[3 + 2 * b])], "inference_queries": nq,
+                          "infer_TFLOPs": 18432.0 * nq / (r["infer"] * 1e-3) / 1e12,
+                          "train_TFLOPs": 55296.0 * 65536 / (r["train"] * 1e-3) / 1e12}))
+        net.close()
+
+    if want("nrc"):
+        stage_nrc()
+
+    def stage_svgf():
+        nonlocal p
+        # ---- V1-V4 SVGF on the ReSTIR frame (config 4)
+        t = Timer()
+        ren = engine.ReSTIRRenderer(ctx, scene, w, h)
+        for f in range(frames):
+            ren.render_frame()
+            for pass_id, stage in engine.svgf_frame_passes(ren.params, f):
+                name = {abi.SVGF_TEMPORAL_ACCUMULATE: "temporal", abi.SVGF_ESTIMATE_VARIANCE: "variance", abi.SVGF_ATROUS: "atrous",
+                        abi.SVGF_FILL_BACKGROUND: "background", abi.SVGF_MODULATE_TAA: "modulate_taa"}[pass_id]
+                t.run(name, lambda: ctx.svgf(ren.params, pass_id, stage))
+        r = t.result(0)
+        # a-trous runs 5x per frame: result() averaged per launch
+        total = r["temporal"] + r["variance"] + 5 * r["atrous"] + r["background"] + r["modulate_taa"]
+        print(json.dumps({"stage": "svgf", **{k + "_ms_per_launch": v for k, v in r.items()}, "total_ms_per_frame": total,
+                          "GBps_algorithmic": 456.0 * npx / (total * 1e-3) / 1e9}))
+
+    if want("svgf"):
+        stage_svgf()
 
 
 if __name__ == "__main__":
