@@ -99,6 +99,11 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
+# (profiles/r01_summary.md): 114.8 + 142.4 MB for the RIS candidate kernel, 84.6 + 10.9 MB for the visibility trace
+NCU_DRAM_TRAFFIC = {"ris_candidates": 257.2e6, "trace_visibility": 95.5e6}
+
+
 def frame_launches(ctx, params, frame_index, num_spatial_passes, timers=None):
     """Issue one frame; with `timers` (dict name -> list of (start, end) events) bracket every launch."""
     from gfxexp_b200 import engine
@@ -404,7 +409,7 @@ def run_gpu(args):
         bytes_per_launch = alg.get(dominant, 0) * px
         achieved = bytes_per_launch / (breakdown[dominant] * 1e-3) / 1e9
         roofline = {"kernel": dominant, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / hbm_peak, "traffic": NCU_DRAM_TRAFFIC.get(dominant), "traffic_source": "ncu --set full, profiles/r01_summary.md", "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": bytes_per_launch, "ms_per_launch": breakdown[dominant],
                     "traversal": {"primary_nodes_per_ray": n_int_p, "primary_tris_per_ray": n_tri_p,
                                   "shadow_nodes_per_ray": n_int_s, "shadow_tris_per_ray": n_tri_s},
@@ -461,7 +466,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="gfxb200", choices=["gfxb200", "reference"])
     ap.add_argument("--cpu-rows", type=int, default=48, help="rows of the CPU-baseline strip sample")
-    ap.add_argument("--rays-per-px", type=float, default=2.62, help="--impl reference: rays per pixel (GPU-counted)")
+    ap.add_argument("--rays-per-px", type=float, default=2.883, help="--impl reference: rays per pixel (GPU-counted)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -48,7 +48,8 @@ struct gfx_nrc {
     float* m1 = nullptr;
     float* m2 = nullptr;
     uint32_t* steps = nullptr;
-    float* grads = nullptr;       // fp32, loss-scaled
+    unsigned long long* grads = nullptr; // loss-scaled gradients as 64-bit fixed point (2^-30 units): integer atomics
+                                         // commute, so a training step is bit-reproducible whatever the block schedule
     float* loss = nullptr;        // device scalar
     uint4* ummaWeights = nullptr; // EMA MLP weights in the tcgen05 shared-memory layout
     uint32_t globalStep = 0;
@@ -379,12 +380,21 @@ __global__ void __launch_bounds__(128) k_nrcInfer(NrcLevels levels, const __half
 // ---------------------------------------------------------------------------------------------
 // training step on CUDA cores: block = 128 samples
 // ---------------------------------------------------------------------------------------------
+// deterministic gradient accumulation: 2^-30 fixed point in 64 bits (range +-8.6e9, resolution 9.3e-10 on loss-scaled values)
+constexpr float kGradFixedScale = 1073741824.0f;
+GFX_D void atomicAddFixed(unsigned long long* p, float v) {
+    atomicAdd(p, (unsigned long long)__float2ll_rn(v * kGradFixedScale));
+}
+GFX_D float fixedToFloat(unsigned long long v) {
+    return (float)((double)(long long)v * (1.0 / 1073741824.0));
+}
+
 constexpr uint32_t kRowStride = 66; // halves per activation row in shared memory (conflict-free rows)
 
 __global__ void __launch_bounds__(128) k_nrcTrain(NrcLevels levels, const __half* __restrict__ params, uint32_t numMatrixWeights,
                                                   uint32_t numHiddenLayers, const float* __restrict__ input,
                                                   const float* __restrict__ target, uint32_t numData,
-                                                  float* __restrict__ grads, float* __restrict__ lossOut) {
+                                                  unsigned long long* __restrict__ grads, float* __restrict__ lossOut) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t H = numHiddenLayers;
     __half* sW = reinterpret_cast<__half*>(smem);                              // numMatrixWeights
@@ -468,7 +478,7 @@ __global__ void __launch_bounds__(128) k_nrcTrain(NrcLevels levels, const __half
             for (uint32_t s = 0; s < 128; ++s)
                 acc += __half2float(sD[s * kRowStride + j]) * __half2float(hin[s * kRowStride + i]);
             if (acc != 0.0f)
-                atomicAdd(grads + base + p, acc);
+                atomicAddFixed(grads + base + p, acc);
         }
         const __half* W = sW + (size_t)H * kWidth * kWidth;
         const __half* myIn = hin + (size_t)tid * kRowStride;
@@ -494,7 +504,7 @@ __global__ void __launch_bounds__(128) k_nrcTrain(NrcLevels levels, const __half
             for (uint32_t s = 0; s < 128; ++s)
                 acc += __half2float(sD[s * kRowStride + j]) * __half2float(hin[s * kRowStride + i]);
             if (acc != 0.0f)
-                atomicAdd(grads + base + p, acc);
+                atomicAddFixed(grads + base + p, acc);
         }
         const __half* W = sW + (size_t)layer * kWidth * kWidth;
         const __half* myIn = hin + (size_t)tid * kRowStride;
@@ -513,7 +523,7 @@ __global__ void __launch_bounds__(128) k_nrcTrain(NrcLevels levels, const __half
 
     // hash-grid backward (kernel_grid_backward, grid.h:306-429): scatter the first 32 input gradients
     if (valid) {
-        float* gGrid = grads + numMatrixWeights;
+        unsigned long long* gGrid = grads + numMatrixWeights;
         const float* in = input + (size_t)q * kInputDims;
         for (uint32_t l = 0; l < kLevels; ++l) {
             const NrcLevel lv = levels.l[l];
@@ -542,8 +552,8 @@ __global__ void __launch_bounds__(128) k_nrcTrain(NrcLevels levels, const __half
                     }
                 }
                 const uint32_t gi = lv.offset * 2 + nrcGridIndex(lv, local);
-                atomicAdd(gGrid + gi, weight * g0);
-                atomicAdd(gGrid + gi + 1, weight * g1);
+                atomicAddFixed(gGrid + gi, weight * g0);
+                atomicAddFixed(gGrid + gi + 1, weight * g1);
             }
         }
     }
@@ -559,15 +569,15 @@ __global__ void __launch_bounds__(128) k_nrcTrain(NrcLevels levels, const __half
 
 // adam_step (adam.h:49-115) + ema_step_half_precision (ema.h:61-77); clears the gradient for the next step
 __global__ void k_nrcAdamEma(uint32_t numParams, uint32_t numMatrixWeights, float learningRate, float emaDebiasOld,
-                             float emaDebiasNew, float* __restrict__ grads, float* __restrict__ master,
+                             float emaDebiasNew, unsigned long long* __restrict__ grads, float* __restrict__ master,
                              __half* __restrict__ params, __half* __restrict__ paramsEma, float* __restrict__ m1,
                              float* __restrict__ m2, uint32_t* __restrict__ steps) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= numParams)
         return;
     const float beta1 = 0.9f, beta2 = 0.99f, epsilon = 1e-15f, l2Reg = 1e-6f, emaDecay = 0.99f;
-    float gradient = __half2float(__float2half(grads[i])) / kLossScale;
-    grads[i] = 0.0f;
+    float gradient = __half2float(__float2half(fixedToFloat(grads[i]))) / kLossScale;
+    grads[i] = 0ull;
     const bool matrix = i < numMatrixWeights;
     if (matrix || gradient != 0) {
         const float weightFp = master[i];
@@ -641,7 +651,7 @@ int gfx_nrc_create(gfx_ctx* ctx, uint32_t numHiddenLayers, float learningRate, g
     GFX_CUDA(ctx, cudaMalloc(&n->m1, P * 4));
     GFX_CUDA(ctx, cudaMalloc(&n->m2, P * 4));
     GFX_CUDA(ctx, cudaMalloc(&n->steps, P * 4));
-    GFX_CUDA(ctx, cudaMalloc(&n->grads, P * 4));
+    GFX_CUDA(ctx, cudaMalloc(&n->grads, P * 8));
     GFX_CUDA(ctx, cudaMalloc(&n->loss, 16));
     GFX_CUDA(ctx, cudaMalloc(&n->ummaWeights, (size_t)n->numMatrixWeights * 2));
     GFX_CUDA(ctx, cudaMemset(n->params, 0, P * 2));
@@ -650,7 +660,7 @@ int gfx_nrc_create(gfx_ctx* ctx, uint32_t numHiddenLayers, float learningRate, g
     GFX_CUDA(ctx, cudaMemset(n->m1, 0, P * 4));
     GFX_CUDA(ctx, cudaMemset(n->m2, 0, P * 4));
     GFX_CUDA(ctx, cudaMemset(n->steps, 0, P * 4));
-    GFX_CUDA(ctx, cudaMemset(n->grads, 0, P * 4));
+    GFX_CUDA(ctx, cudaMemset(n->grads, 0, P * 8));
     *out = n;
     return GFX_OK;
 }
@@ -676,7 +686,7 @@ int gfx_nrc_set_params(gfx_nrc* n, const void* hostHalfParams, size_t bytes) {
     NRC_CUDA(n, cudaMemset(n->m1, 0, P * 4));
     NRC_CUDA(n, cudaMemset(n->m2, 0, P * 4));
     NRC_CUDA(n, cudaMemset(n->steps, 0, P * 4));
-    NRC_CUDA(n, cudaMemset(n->grads, 0, P * 4));
+    NRC_CUDA(n, cudaMemset(n->grads, 0, P * 8));
     n->globalStep = 0;
     n->ummaDirty = true;
     NRC_CUDA(n, cudaDeviceSynchronize());

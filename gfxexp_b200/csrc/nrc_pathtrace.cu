@@ -523,12 +523,15 @@ __global__ void __launch_bounds__(64) k_nrcBounce(DevScene s, DevFrame f, DevFra
 }
 
 // numbers the training vertices staged in this round in tile order: a single block scans the per-tile flags ...
-__global__ void __launch_bounds__(1024) k_nrcCommitScan(DevNrc n, uint32_t bufIdx) {
+__global__ void __launch_bounds__(1024) k_nrcCommitScan(DevNrc n, uint32_t bufIdx, uint32_t W, uint32_t H) {
     __shared__ uint32_t warpSums[32];
     __shared__ uint32_t blockTotal;
     const uint32_t tid = threadIdx.x;
-    const uint32_t chunk = (n.numSuffixes + blockDim.x - 1) / blockDim.x;
-    const uint32_t begin = min(tid * chunk, n.numSuffixes), end = min(begin + chunk, n.numSuffixes);
+    // only the tiles of this frame's tile size can hold a staged vertex
+    const uint32_t tileSizeX = n.state[NRC_TILE_SIZE + 2 * bufIdx], tileSizeY = n.state[NRC_TILE_SIZE + 2 * bufIdx + 1];
+    const uint32_t numTiles = min(((W + tileSizeX - 1) / tileSizeX) * ((H + tileSizeY - 1) / tileSizeY), n.numSuffixes);
+    const uint32_t chunk = (numTiles + blockDim.x - 1) / blockDim.x;
+    const uint32_t begin = min(tid * chunk, numTiles), end = min(begin + chunk, numTiles);
     uint32_t local = 0;
     for (uint32_t t = begin; t < end; ++t)
         local += n.stagedFlags[t] & 1u;
@@ -685,7 +688,7 @@ int launchPathTraceNrc(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* 
     const uint32_t scatterGrid = (n.numSuffixes + 127) / 128;
     { GFX_TIMED(ctx, stream, "nrc_first_hit"); k_nrcFirstHit<<<grid, block, 0, stream>>>(s, f, p, ps, n); }
     { GFX_TIMED(ctx, stream, "nrc_commit");
-      k_nrcCommitScan<<<1, 1024, 0, stream>>>(n, p.bufferIndex);
+      k_nrcCommitScan<<<1, 1024, 0, stream>>>(n, p.bufferIndex, F.W, F.H);
       k_nrcCommitScatter<<<scatterGrid, 128, 0, stream>>>(n, numPixels); }
     ctx->launches += 3;
     const int traceGrid = wavefrontGrid();
@@ -699,7 +702,7 @@ int launchPathTraceNrc(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* 
         { GFX_TIMED(ctx, stream, "nrc_trace_extension"); k_traceWavefront<false, false><<<traceGrid, 128, 0, stream>>>(s.bvh, ps.extRays[round & 1], c + 0, 0u, c + 1, extWriter); }
         { GFX_TIMED(ctx, stream, "nrc_bounce"); k_nrcBounce<<<sms * 16, 64, 0, stream>>>(s, f, p, ps, n, round); }
         { GFX_TIMED(ctx, stream, "nrc_commit");
-          k_nrcCommitScan<<<1, 1024, 0, stream>>>(n, p.bufferIndex);
+          k_nrcCommitScan<<<1, 1024, 0, stream>>>(n, p.bufferIndex, F.W, F.H);
           k_nrcCommitScatter<<<scatterGrid, 128, 0, stream>>>(n, numPixels); }
         ctx->launches += 5;
     }

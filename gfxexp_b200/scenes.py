@@ -413,3 +413,26 @@ def teapot_like_scene(obj_path: str | None = None) -> Scene:
     # camera: translate(0,133.3,200) * rotY(180) * rotX(25)  (nrtdsm/nrtdsm_sandbox.cpp:3137-3146)
     ori = (rot_y(180.0) @ rot_x(25.0)).astype(F32)
     return Scene(meshes, mats, instances, np.array([0.0, 133.3, 200.0], dtype=F32), ori, math.radians(50.0), "teapot")
+
+
+def save_scene_bin(scene: Scene, path: str, width: int = 64, height: int = 64) -> None:
+    """Flat binary scene file for the headless C++ host (host/gfx_headless.cpp): 'GFXS', counts, per-mesh arrays, the
+    material / instance tables in the layouts of include/gfxb200.h, and the default GfxFrameParams of this scene."""
+    import ctypes as C
+
+    from . import abi
+    sa = abi.SceneArrays(scene)
+    params = abi.default_frame_params(scene, width, height)
+    with open(path, "wb") as f:
+        f.write(b"GFXS")
+        f.write(np.asarray([len(scene.meshes), scene.materials.shape[0], len(scene.instances), sa.slots.shape[0],
+                            C.sizeof(abi.GfxFrameParams)], dtype=np.uint32).tobytes())
+        for m in scene.meshes:
+            f.write(np.asarray([m.positions.shape[0], m.triangles.shape[0], m.material], dtype=np.uint32).tobytes())
+            for a, dt in ((m.positions, np.float32), (m.normals, np.float32), (m.tangents, np.float32), (m.texcoords, np.float32),
+                          (m.triangles, np.uint32)):
+                f.write(np.ascontiguousarray(a, dtype=dt).tobytes())
+        f.write(np.ascontiguousarray(scene.materials).tobytes())
+        f.write(bytes(sa.instances))
+        f.write(sa.slots.tobytes())
+        f.write(bytes(params))

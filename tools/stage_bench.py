@@ -42,6 +42,17 @@ def main():
     ctx.build_light_distributions(0)
     p = abi.default_frame_params(scene, w, h)
     npx = w * h
+
+    def kernel_breakdown(fn, reps=4):
+        """per-kernel ms per frame (CUDA events inside the library) of `fn`, averaged over `reps` calls"""
+        ctx.timing_enable(True)
+        ctx.timing_read()
+        for i in range(reps):
+            fn(i)
+        t = ctx.timing_read()
+        ctx.timing_enable(False)
+        return {k: round(ms / reps, 4) for k, (ms, n) in sorted(t.items(), key=lambda kv: -kv[1][0])}
+
     only = sys.argv[sys.argv.index("--only") + 1].split(",") if "--only" in sys.argv else None
 
     def want(name):
@@ -61,6 +72,11 @@ def main():
             t.run("pathtrace", lambda: ctx.pathtrace(p))
         r = t.result(warm)
         rays = ctx.read_stats()[0] / (frames - warm)
+
+        def pt_once(i):
+            p.numAccumFrames = frames + i
+            ctx.pathtrace(p)
+        print(json.dumps({"stage": "pathtrace_baseline_kernels", **kernel_breakdown(pt_once)}))
         print(json.dumps({"stage": "pathtrace_baseline", "ms": r["pathtrace"], "gbuffer_ms": r["gbuffer"], "rays_per_frame": rays,
                           "Mrays_per_s": rays / ((r["pathtrace"] + r["gbuffer"]) * 1e-3) / 1e6, "width": w, "height": h}))
 
@@ -79,7 +95,16 @@ def main():
             t.run("pathtrace_regir", lambda: ctx.pathtrace(p, abi.PT_REGIR))
             t.run("update_access", lambda: ctx.regir_update_access(p, f))
         r = t.result(warm)
-        active = int(ctx.download_linear(abi.BUF_REGIR_NUM_ACTIVE_CELLS, params=p)[(frames - 1) % 2, 0])
+
+        def regir_once(i):
+            f = frames + i
+            p.frameIndex, p.bufferIndex, p.numAccumFrames = f, f % 2, f
+            ctx.gbuffer(p)
+            ctx.regir_build_cells(p, f, True)
+            ctx.pathtrace(p, abi.PT_REGIR)
+            ctx.regir_update_access(p, f)
+        print(json.dumps({"stage": "regir_kernels", **kernel_breakdown(regir_once)}))
+        active = int(ctx.download_linear(abi.BUF_REGIR_NUM_ACTIVE_CELLS, params=p)[(frames + 3) % 2, 0])
         slots = active * abi.REGIR_SLOTS_PER_CELL
         print(json.dumps({"stage": "regir", **r, "active_cells": active,
                           "build_GBps_algorithmic": 128.0 * slots / (r["build_cells"] * 1e-3) / 1e9}))
@@ -108,8 +133,14 @@ def main():
             t.run("shuffle", lambda: ctx.nrc_shuffle(p))
             t.run("train", lambda: ctx.nrc_frame_train(net))
         r = t.result(nrc_frames // 2)
+
+        def nrc_once(i):
+            f = nrc_frames + i
+            p.numAccumFrames = f
+            ctx.nrc_frame(net, p, f, [int(rng.integers(0, 2 ** 32)) for _ in range(2)], train=True)
+        print(json.dumps({"stage": "nrc_kernels", **kernel_breakdown(nrc_once)}))
         st = ctx.download_linear(abi.BUF_NRC_STATE)[:, 0]
-        b = (nrc_frames - 1) % 2
+        b = (nrc_frames + 3) % 2
         nq = int(st[abi.NRC_STATE_NUM_INFERENCE_QUERIES])
         print(json.dumps({"stage": "nrc_frame", **r, "total_ms": sum(r.values()), "num_training_data": int(st[b]),
                           "tile": [int(st[2 + 2 * b]), int(st[3 + 2 * b])], "inference_queries": nq,
