@@ -104,7 +104,6 @@ static void buildLightDistributions(orc_scene* s) {
 }
 
 extern "C" orc_scene* orc_scene_create(const GfxSceneDesc* d, const OrcBuildConfig* cfg, int numThreads) {
-    (void)numThreads;
     orc_scene* s = new orc_scene();
     s->meshes.resize(d->numMeshes);
     for (uint32_t i = 0; i < d->numMeshes; ++i) {
@@ -151,7 +150,10 @@ extern "C" orc_scene* orc_scene_create(const GfxSceneDesc* d, const OrcBuildConf
     bc.minNumPrimsPerLeaf = cfg->minNumPrimsPerLeaf;
     bc.maxNumPrimsPerLeaf = cfg->maxNumPrimsPerLeaf;
     const auto t0 = std::chrono::steady_clock::now();
-    buildGeometryBVH(geoms.data(), (uint32_t)geoms.size(), bc, &s->bvh);
+    // numThreads < 0: no SBVH build; the caller imports a BVH built elsewhere (orc_bvh_import) before tracing.
+    // Used to validate / walk a GPU-built BVH of a scene whose single-threaded CPU build would take minutes.
+    if (numThreads >= 0)
+        buildGeometryBVH(geoms.data(), (uint32_t)geoms.size(), bc, &s->bvh);
     const auto t1 = std::chrono::steady_clock::now();
     s->buildSeconds = std::chrono::duration<double>(t1 - t0).count();
 

@@ -106,10 +106,11 @@ def lib() -> C.CDLL:
 
 
 class OracleScene:
-    def __init__(self, scene, cfg: OrcBuildConfig | None = None):
+    def __init__(self, scene, cfg: OrcBuildConfig | None = None, build_bvh: bool = True):
+        """build_bvh=False skips the (single-threaded) SBVH build: import_bvh() must follow before anything traces"""
         self.arrays = abi.SceneArrays(scene)
         self.cfg = cfg or reference_build_config()
-        self.h = lib().orc_scene_create(C.byref(self.arrays.desc), C.byref(self.cfg), 0)
+        self.h = lib().orc_scene_create(C.byref(self.arrays.desc), C.byref(self.cfg), 0 if build_bvh else -1)
         assert self.h
 
     def close(self):
