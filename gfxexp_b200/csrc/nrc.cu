@@ -52,6 +52,8 @@ struct gfx_nrc {
                                          // commute, so a training step is bit-reproducible whatever the block schedule
     float* loss = nullptr;        // device scalar
     uint4* ummaWeights = nullptr; // EMA MLP weights in the tcgen05 shared-memory layout
+    uint4* trainBlobFwd = nullptr; // training weights, tcgen05 layouts: W_l [N x 64] and W_l^T [64 x K] K-major blobs
+    uint4* trainBlobT = nullptr;
     uint32_t globalStep = 0;
     bool ummaDirty = true;
 };
@@ -88,7 +90,7 @@ GFX_D void nrcEncode(const NrcLevels &levels, const __half* __restrict__ table, 
 #pragma unroll
     for (uint32_t d = 0; d < kInputDims; ++d)
         q[d] = in[d];
-    __half feat[8];
+    uint4 featPacked = make_uint4(0, 0, 0, 0);
 #pragma unroll 1 // measured on B200: unrolling (more gathers in flight, 62 regs) is 6 % slower than 1 level at a time
     for (uint32_t l = 0; l < kLevels; ++l) {
         const NrcLevel lv = levels.l[l];
@@ -122,10 +124,23 @@ GFX_D void nrcEncode(const NrcLevels &levels, const __half* __restrict__ table, 
             r0 = __float2half(__half2float(r0) + __half2float(__float2half(weight * __low2float(v))));
             r1 = __float2half(__half2float(r1) + __half2float(__float2half(weight * __high2float(v))));
         }
-        feat[(l & 3) * 2 + 0] = r0;
-        feat[(l & 3) * 2 + 1] = r1;
-        if ((l & 3) == 3)
+        // four levels make one 16-byte chunk; selects instead of an indexed array keep the features in registers
+        const uint32_t pair = (uint32_t)__half_as_ushort(r0) | ((uint32_t)__half_as_ushort(r1) << 16);
+        const uint32_t slot = l & 3;
+        if (slot == 0) featPacked.x = pair;
+        else if (slot == 1) featPacked.y = pair;
+        else if (slot == 2) featPacked.z = pair;
+        else {
+            featPacked.w = pair;
+            const uint32_t w4[4] = { featPacked.x, featPacked.y, featPacked.z, featPacked.w };
+            __half feat[8];
+#pragma unroll
+            for (uint32_t e = 0; e < 4; ++e) {
+                feat[2 * e] = __ushort_as_half((unsigned short)(w4[e] & 0xFFFFu));
+                feat[2 * e + 1] = __ushort_as_half((unsigned short)(w4[e] >> 16));
+            }
             emit(l >> 2, feat);
+        }
     }
     // OneBlob: 5 dims x 4 bins -> features 32..51, identity 52..57, ones 58..63
     __half tail[32];
@@ -266,13 +281,23 @@ __global__ void __launch_bounds__(128) k_nrcInfer(NrcLevels levels, const __half
     const uint32_t warp = tid >> 5;
     const uint32_t weightBytes = (numHiddenLayers * kWidth * kWidth + kPaddedOutput * kWidth) * 2;
 
-    // resident weights: straight 16-byte copies of the pre-arranged blob
-    for (uint32_t i = tid; i < weightBytes / 16; i += blockDim.x)
-        reinterpret_cast<uint4*>(sW)[i] = __ldg(ummaWeights + i);
+    // resident weights: ONE bulk asynchronous copy (TMA engine, cp.async.bulk) of the pre-arranged 18 KB blob into shared
+    // memory, completion signalled on an mbarrier by transaction bytes
+    __shared__ __align__(8) uint64_t weightBar;
     if (tid == 0) {
         mbarInit(&bar, 1);
+        mbarInit(&weightBar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#ifndef GFX_NRC_INFER_NO_TMA
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smemU32(&weightBar)), "r"(weightBytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(smemU32(sW)), "l"(ummaWeights), "r"(weightBytes), "r"(smemU32(&weightBar)) : "memory");
+#endif
     }
+#ifdef GFX_NRC_INFER_NO_TMA
+    for (uint32_t i = tid; i < weightBytes / 16; i += 128)
+        reinterpret_cast<uint4*>(sW)[i] = __ldg(ummaWeights + i);
+#endif
     if (warp == 0) { // TMEM: 64 fp32 accumulator columns x 128 lanes
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smemU32(&tmemBaseShared)), "r"(64u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -281,6 +306,9 @@ __global__ void __launch_bounds__(128) k_nrcInfer(NrcLevels levels, const __half
     tcFenceBefore();
     __syncthreads();
     tcFenceAfter();
+#ifndef GFX_NRC_INFER_NO_TMA
+    mbarWait(&weightBar, 0); // the weight blob has landed (async proxy write: visible to tcgen05.mma without a proxy fence)
+#endif
     const uint32_t tmemBase = tmemBaseShared;
     const uint32_t tmemRow = tmemBase + ((warp * 32u) << 16); // this warp's 32 lanes
 
@@ -567,6 +595,331 @@ __global__ void __launch_bounds__(128) k_nrcTrain(NrcLevels levels, const __half
         atomicAdd(lossOut, sLoss[0] + sLoss[1] + sLoss[2] + sLoss[3]);
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_nrcTrainTc: the same training step with every matrix product on tcgen05 (forward, data gradients, weight gradients).
+//
+// Per CTA = 128 samples (kernel_mlp_fused + kernel_mlp_fused_backward of tiny-cuda-nn work on the same 128-row chunks,
+// ext/tiny-cuda-nn/src/fully_fused_mlp.cu:47-129, 150-259; the weight gradients are its three split-K CUTLASS GEMMs,
+// :822-873).  All operands are K-major core-matrix tiles in shared memory:
+//   forward        Z_l     [128 x N]  = A_l [128 x 64]            x W_l^T   (B = W_l blob  [N x 64],  as in k_nrcInfer)
+//   data gradient  dA_l    [128 x 64] = dZ_l [128 x K]            x W_l     (B = W_l^T blob [64 x K], K = 64 or 16)
+//   weight grad    dW_l    [K x 64]   = dZ_l^T [K(<=64) x 128]    x A_l     (A = transposed dZ tile, B = transposed A_l tile,
+//                                                                            K = 128 samples; issued with M = 128, rows >= 64
+//                                                                            of the accumulator are ignored)
+// The transposed tiles are written by the threads that own the rows (each thread holds its sample's dZ row in registers
+// and re-reads its A_l row).  Accumulators live in three 64-column TMEM regions; one tcgen05.commit per phase.
+// Rounding points match k_nrcTrain (activations and gradients are fp16 between layers, fp32 accumulation inside).
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kTTileBytes = 64 * 128 * 2; // transposed tile: 16 K-chunks x 64 rows x 16 B
+
+__global__ void k_nrcPrepTrainWeights(const __half* __restrict__ w, uint32_t numHiddenLayers, __half* __restrict__ blobFwd,
+                                      __half* __restrict__ blobT) {
+    const uint32_t total = numHiddenLayers * kWidth * kWidth + kPaddedOutput * kWidth;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        uint32_t layer = i / (kWidth * kWidth), rem = i % (kWidth * kWidth), N = kWidth;
+        if (layer >= numHiddenLayers) {
+            layer = numHiddenLayers;
+            rem = i - numHiddenLayers * kWidth * kWidth;
+            N = kPaddedOutput;
+        }
+        const uint32_t j = rem / kWidth, in = rem % kWidth; // W_l[j][in]
+        // forward blob: B[n = j][k = in]
+        blobFwd[layer * kWidth * kWidth + (in / 8) * (N * 8) + j * 8 + (in % 8)] = w[i];
+        // transposed blob: B[n = in][k = j], 64 rows per K-chunk
+        blobT[layer * kWidth * kWidth + (j / 8) * (kWidth * 8) + in * 8 + (j % 8)] = w[i];
+    }
+}
+
+__global__ void __launch_bounds__(128) k_nrcTrainTc(NrcLevels levels, const __half* __restrict__ params, uint32_t numMatrixWeights,
+                                                    uint32_t numHiddenLayers, const uint4* __restrict__ blobFwd,
+                                                    const uint4* __restrict__ blobT, const float* __restrict__ input,
+                                                    const float* __restrict__ target, uint32_t numData,
+                                                    unsigned long long* __restrict__ grads, float* __restrict__ lossOut) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t H = numHiddenLayers;
+    const uint32_t weightBytes = numMatrixWeights * 2;
+    uint8_t* sWf = smem;                                   // forward blobs
+    uint8_t* sWt = sWf + weightBytes;                      // transposed blobs
+    uint8_t* sAct = sWt + weightBytes;                     // (H + 1) activation tiles A_0..A_H, 16 KB each
+    uint8_t* sDz = sAct + (H + 1) * kATileBytes;           // dZ tile [128 x 64] (K-major, rows = samples)
+    uint8_t* sDzT = sDz + kATileBytes;                     // dZ^T tile [64 x 128] (rows = neurons, K = samples)
+    uint8_t* sActT = sDzT + kTTileBytes;                   // A_l^T tile [64 x 128]; the M = 128 read of sDzT spills into it
+    __shared__ __align__(8) uint64_t bar, weightBar;
+    __shared__ uint32_t tmemBaseShared;
+    __shared__ float sLoss[4];
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t warp = tid >> 5;
+    const uint32_t q = blockIdx.x * 128 + tid;
+    const bool valid = q < numData;
+    const __half* table = params + numMatrixWeights;
+
+    if (tid == 0) {
+        mbarInit(&bar, 1);
+        mbarInit(&weightBar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smemU32(&weightBar)), "r"(2 * weightBytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(smemU32(sWf)), "l"(blobFwd), "r"(weightBytes), "r"(smemU32(&weightBar)) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(smemU32(sWt)), "l"(blobT), "r"(weightBytes), "r"(smemU32(&weightBar)) : "memory");
+    }
+    if (warp == 0) { // TMEM: 3 accumulators of 64 fp32 columns (forward / data gradient / weight gradient) -> 256 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smemU32(&tmemBaseShared)), "r"(256u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+
+    // encode this thread's sample into A_0
+    if (valid) {
+        nrcEncode(levels, table, input + (size_t)q * kInputDims, [&](uint32_t c, const __half* f) {
+            uint4 v;
+            v.x = (uint32_t)__half_as_ushort(f[0]) | ((uint32_t)__half_as_ushort(f[1]) << 16);
+            v.y = (uint32_t)__half_as_ushort(f[2]) | ((uint32_t)__half_as_ushort(f[3]) << 16);
+            v.z = (uint32_t)__half_as_ushort(f[4]) | ((uint32_t)__half_as_ushort(f[5]) << 16);
+            v.w = (uint32_t)__half_as_ushort(f[6]) | ((uint32_t)__half_as_ushort(f[7]) << 16);
+            *reinterpret_cast<uint4*>(sAct + c * (kTileRows * 16) + tid * 16) = v;
+        });
+    }
+    else {
+#pragma unroll
+        for (uint32_t c = 0; c < 8; ++c)
+            *reinterpret_cast<uint4*>(sAct + c * (kTileRows * 16) + tid * 16) = make_uint4(0, 0, 0, 0);
+    }
+    fenceProxyAsync();
+    tcFenceBefore();
+    __syncthreads();
+    tcFenceAfter();
+    mbarWait(&weightBar, 0);
+    const uint32_t tmemBase = tmemBaseShared;
+    const uint32_t tmemRow = tmemBase + ((warp * 32u) << 16);
+    const uint32_t tmemFwd = 0, tmemDa = 64, tmemDw = 128; // column offsets
+    const uint32_t idesc64 = makeInstrDesc(128, kWidth), idesc16 = makeInstrDesc(128, kPaddedOutput);
+    uint32_t phase = 0;
+
+    // ---- forward
+    for (uint32_t layer = 0; layer <= H; ++layer) {
+        const bool last = layer == H;
+        const uint32_t N = last ? kPaddedOutput : kWidth;
+        if (tid == 0) {
+            tcFenceAfter();
+            const uint32_t aAddr = smemU32(sAct + layer * kATileBytes);
+            const uint32_t wLayer = smemU32(sWf) + layer * kWidth * kWidth * 2;
+#pragma unroll
+            for (uint32_t k = 0; k < kWidth / 16; ++k)
+                umma(tmemBase + tmemFwd, makeSmemDesc(aAddr + 2 * k * (kTileRows * 16), kTileRows * 16, 128),
+                     makeSmemDesc(wLayer + 2 * k * (N * 16), N * 16, 128), last ? idesc16 : idesc64, k > 0 ? 1u : 0u);
+            ummaCommit(&bar);
+        }
+        mbarWait(&bar, phase);
+        phase ^= 1;
+        tcFenceAfter();
+        if (!last) {
+            uint8_t* next = sAct + (layer + 1) * kATileBytes;
+#pragma unroll
+            for (uint32_t half_ = 0; half_ < 2; ++half_) {
+                uint32_t r[32];
+                tmemLoad32(tmemRow + tmemFwd + half_ * 32, r);
+                tmemWaitLd();
+#pragma unroll
+                for (uint32_t c = 0; c < 4; ++c) {
+                    uint32_t packed[4];
+#pragma unroll
+                    for (uint32_t e = 0; e < 4; ++e) {
+                        const float a = fmaxf(__uint_as_float(r[c * 8 + 2 * e]), 0.0f);
+                        const float b = fmaxf(__uint_as_float(r[c * 8 + 2 * e + 1]), 0.0f);
+                        packed[e] = (uint32_t)__half_as_ushort(__float2half(a)) | ((uint32_t)__half_as_ushort(__float2half(b)) << 16);
+                    }
+                    *reinterpret_cast<uint4*>(next + (half_ * 4 + c) * (kTileRows * 16) + tid * 16) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                }
+            }
+            fenceProxyAsync();
+            tcFenceBefore();
+            __syncthreads();
+        }
+    }
+
+    // ---- loss + dL/dy (relative_l2_luminance.h:41-88)
+    __half d[64]; // this sample's gradient row of the current layer (dZ_l), fp16 like tiny-cuda-nn's backward buffers
+    float localLoss = 0.0f;
+    {
+        uint32_t r[4];
+        tmemLoad4(tmemRow + tmemFwd, r);
+        tmemWaitLd();
+        const __half o[3] = { __float2half(__uint_as_float(r[0])), __float2half(__uint_as_float(r[1])), __float2half(__uint_as_float(r[2])) };
+        const uint32_t nTotal = numData * kOutputDims;
+        const float rr = __half2float(o[0]), gg = __half2float(o[1]), bb = __half2float(o[2]);
+        const float luminance = 0.299f * rr + 0.587f * gg + 0.114f * bb;
+        const float denom = luminance * luminance + 0.01f;
+#pragma unroll
+        for (uint32_t k = 0; k < kPaddedOutput; ++k) {
+            float gr = 0.0f;
+            if (k < kOutputDims && valid) {
+                const float difference = __half2float(o[k]) - target[(size_t)q * kOutputDims + k];
+                localLoss += difference * difference / denom / nTotal;
+                gr = kLossScale * (2 * difference / denom) / nTotal;
+            }
+            d[k] = __float2half(gr);
+        }
+    }
+
+    // ---- backward, layer H (output, K = 16) down to 0
+    for (int layer = (int)H; layer >= 0; --layer) {
+        const uint32_t K = layer == (int)H ? kPaddedOutput : kWidth; // width of dZ_l
+        const uint8_t* aTile = sAct + layer * kATileBytes;
+        // dZ_l: row-major tile for the data gradient, transposed tile for the weight gradient; A_l transposed
+#pragma unroll
+        for (uint32_t c = 0; c < 8; ++c) {
+            if (c >= K / 8)
+                break;
+            uint4 v;
+            v.x = (uint32_t)__half_as_ushort(d[c * 8 + 0]) | ((uint32_t)__half_as_ushort(d[c * 8 + 1]) << 16);
+            v.y = (uint32_t)__half_as_ushort(d[c * 8 + 2]) | ((uint32_t)__half_as_ushort(d[c * 8 + 3]) << 16);
+            v.z = (uint32_t)__half_as_ushort(d[c * 8 + 4]) | ((uint32_t)__half_as_ushort(d[c * 8 + 5]) << 16);
+            v.w = (uint32_t)__half_as_ushort(d[c * 8 + 6]) | ((uint32_t)__half_as_ushort(d[c * 8 + 7]) << 16);
+            *reinterpret_cast<uint4*>(sDz + c * (kTileRows * 16) + tid * 16) = v;
+        }
+        {
+            __half* dzT = reinterpret_cast<__half*>(sDzT + (tid / 8) * (64 * 16) + (tid % 8) * 2);
+#pragma unroll
+            for (uint32_t j = 0; j < 64; ++j)
+                if (j < K)
+                    dzT[j * 8] = d[j]; // element (row j, k = tid) of a [64 x 128] K-major tile
+            __half* aT = reinterpret_cast<__half*>(sActT + (tid / 8) * (64 * 16) + (tid % 8) * 2);
+#pragma unroll
+            for (uint32_t c = 0; c < 8; ++c) {
+                const uint4 v = *reinterpret_cast<const uint4*>(aTile + c * (kTileRows * 16) + tid * 16);
+                const uint32_t w4[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+                for (uint32_t e = 0; e < 4; ++e) {
+                    aT[(c * 8 + 2 * e) * 8] = __ushort_as_half((unsigned short)(w4[e] & 0xFFFFu));
+                    aT[(c * 8 + 2 * e + 1) * 8] = __ushort_as_half((unsigned short)(w4[e] >> 16));
+                }
+            }
+        }
+        fenceProxyAsync();
+        tcFenceBefore();
+        __syncthreads();
+        if (tid == 0) {
+            tcFenceAfter();
+            // data gradient dA_l = dZ_l x W_l  (K steps of 16 over dZ's width)
+            const uint32_t dzAddr = smemU32(sDz);
+            const uint32_t wtLayer = smemU32(sWt) + layer * kWidth * kWidth * 2;
+            for (uint32_t k = 0; k < K / 16; ++k)
+                umma(tmemBase + tmemDa, makeSmemDesc(dzAddr + 2 * k * (kTileRows * 16), kTileRows * 16, 128),
+                     makeSmemDesc(wtLayer + 2 * k * (kWidth * 16), kWidth * 16, 128), idesc64, k > 0 ? 1u : 0u);
+            // weight gradient dW_l = dZ_l^T x A_l  (K = 128 samples)
+            const uint32_t dzTAddr = smemU32(sDzT), aTAddr = smemU32(sActT);
+#pragma unroll
+            for (uint32_t k = 0; k < kTileRows / 16; ++k)
+                umma(tmemBase + tmemDw, makeSmemDesc(dzTAddr + 2 * k * (64 * 16), 64 * 16, 128),
+                     makeSmemDesc(aTAddr + 2 * k * (64 * 16), 64 * 16, 128), idesc64, k > 0 ? 1u : 0u);
+            ummaCommit(&bar);
+        }
+        mbarWait(&bar, phase);
+        phase ^= 1;
+        tcFenceAfter();
+
+        // weight gradient rows 0..K-1 -> fixed-point global accumulation (thread j owns output neuron j); tcgen05.ld is
+        // warp-collective, so whole warps take part and only the lanes that own a valid row accumulate
+        if (warp < (K + 31) / 32) {
+            const uint32_t base = (uint32_t)layer * kWidth * kWidth + tid * kWidth;
+#pragma unroll
+            for (uint32_t half_ = 0; half_ < 2; ++half_) {
+                uint32_t r[32];
+                tmemLoad32(tmemRow + tmemDw + half_ * 32, r);
+                tmemWaitLd();
+                if (tid < K) {
+#pragma unroll
+                    for (uint32_t i = 0; i < 32; ++i) {
+                        const float g = __uint_as_float(r[i]);
+                        if (g != 0.0f)
+                            atomicAddFixed(grads + base + half_ * 32 + i, g);
+                    }
+                }
+            }
+        }
+        // data gradient row -> dZ_{l-1} (ReLU mask of A_l = relu(Z_{l-1})), or the encoder gradient for layer 0
+        {
+            __half dNext[64];
+#pragma unroll
+            for (uint32_t half_ = 0; half_ < 2; ++half_) {
+                uint32_t r[32];
+                tmemLoad32(tmemRow + tmemDa + half_ * 32, r);
+                tmemWaitLd();
+#pragma unroll
+                for (uint32_t c = 0; c < 4; ++c) {
+                    const uint4 av = *reinterpret_cast<const uint4*>(aTile + (half_ * 4 + c) * (kTileRows * 16) + tid * 16);
+                    const uint32_t w4[4] = { av.x, av.y, av.z, av.w };
+#pragma unroll
+                    for (uint32_t e = 0; e < 8; ++e) {
+                        const __half act = __ushort_as_half((unsigned short)((w4[e >> 1] >> (16 * (e & 1))) & 0xFFFFu));
+                        const float g = __uint_as_float(r[c * 8 + e]);
+                        dNext[half_ * 32 + c * 8 + e] = (layer > 0 && !(__half2float(act) > 0.0f)) ? __float2half(0.0f) : __float2half(g);
+                    }
+                }
+            }
+#pragma unroll
+            for (uint32_t i = 0; i < 64; ++i)
+                d[i] = dNext[i];
+        }
+        tcFenceBefore();
+        __syncthreads(); // everyone is done with the tiles and the accumulators of this layer
+        tcFenceAfter();
+    }
+
+    // ---- hash-grid backward (kernel_grid_backward, grid.h:306-429): scatter the first 32 input gradients (parked in
+    // this thread's row of the dZ tile so that the level loop can index them)
+    __half* gradRow = reinterpret_cast<__half*>(sDz + (size_t)tid * 64);
+#pragma unroll
+    for (uint32_t i = 0; i < 32; ++i)
+        gradRow[i] = d[i];
+    if (valid) {
+        unsigned long long* gGrid = grads + numMatrixWeights;
+        const float* in = input + (size_t)q * kInputDims;
+        for (uint32_t l = 0; l < kLevels; ++l) {
+            const NrcLevel lv = levels.l[l];
+            const float g0 = __half2float(gradRow[l * 2 + 0]), g1 = __half2float(gradRow[l * 2 + 1]);
+            if (g0 == 0.0f && g1 == 0.0f)
+                continue;
+            float pos[3];
+            uint32_t posGrid[3];
+            for (uint32_t dd = 0; dd < 3; ++dd) {
+                pos[dd] = in[dd] * lv.scale + 0.5f;
+                const int tmp = (int)floorf(pos[dd]);
+                posGrid[dd] = (uint32_t)tmp;
+                pos[dd] -= (float)tmp;
+            }
+            for (uint32_t idx = 0; idx < 8; ++idx) {
+                float weight = 1;
+                uint32_t local[3];
+                for (uint32_t dd = 0; dd < 3; ++dd) {
+                    if ((idx & (1u << dd)) == 0) {
+                        weight *= 1 - pos[dd];
+                        local[dd] = posGrid[dd];
+                    }
+                    else {
+                        weight *= pos[dd];
+                        local[dd] = posGrid[dd] + 1;
+                    }
+                }
+                const uint32_t gi = lv.offset * 2 + nrcGridIndex(lv, local);
+                atomicAddFixed(gGrid + gi, weight * g0);
+                atomicAddFixed(gGrid + gi + 1, weight * g1);
+            }
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1)
+        localLoss += __shfl_xor_sync(0xFFFFFFFFu, localLoss, off);
+    if ((tid & 31) == 0)
+        sLoss[warp] = localLoss;
+    tcFenceBefore();
+    __syncthreads();
+    if (tid == 0)
+        atomicAdd(lossOut, sLoss[0] + sLoss[1] + sLoss[2] + sLoss[3]);
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmemBase), "r"(256u) : "memory");
+}
+
 // adam_step (adam.h:49-115) + ema_step_half_precision (ema.h:61-77); clears the gradient for the next step
 __global__ void k_nrcAdamEma(uint32_t numParams, uint32_t numMatrixWeights, float learningRate, float emaDebiasOld,
                              float emaDebiasNew, unsigned long long* __restrict__ grads, float* __restrict__ master,
@@ -654,6 +1007,8 @@ int gfx_nrc_create(gfx_ctx* ctx, uint32_t numHiddenLayers, float learningRate, g
     GFX_CUDA(ctx, cudaMalloc(&n->grads, P * 8));
     GFX_CUDA(ctx, cudaMalloc(&n->loss, 16));
     GFX_CUDA(ctx, cudaMalloc(&n->ummaWeights, (size_t)n->numMatrixWeights * 2));
+    GFX_CUDA(ctx, cudaMalloc(&n->trainBlobFwd, (size_t)n->numMatrixWeights * 2));
+    GFX_CUDA(ctx, cudaMalloc(&n->trainBlobT, (size_t)n->numMatrixWeights * 2));
     GFX_CUDA(ctx, cudaMemset(n->params, 0, P * 2));
     GFX_CUDA(ctx, cudaMemset(n->paramsEma, 0, P * 2));
     GFX_CUDA(ctx, cudaMemset(n->master, 0, P * 4));
@@ -669,7 +1024,7 @@ void gfx_nrc_destroy(gfx_nrc* n) {
     if (!n)
         return;
     cudaFree(n->params); cudaFree(n->paramsEma); cudaFree(n->master); cudaFree(n->m1); cudaFree(n->m2);
-    cudaFree(n->steps); cudaFree(n->grads); cudaFree(n->loss); cudaFree(n->ummaWeights);
+    cudaFree(n->steps); cudaFree(n->grads); cudaFree(n->loss); cudaFree(n->ummaWeights); cudaFree(n->trainBlobFwd); cudaFree(n->trainBlobT);
     delete n;
 }
 
@@ -775,11 +1130,29 @@ int gfx_nrc_train(gfx_nrc* n, void* stream, const float* inputData, const float*
         return GFX_OK;
     cudaStream_t s = (cudaStream_t)stream;
     NRC_CUDA(n, cudaMemsetAsync(n->loss, 0, 4, s));
-    const size_t smem = ((size_t)n->numMatrixWeights + (size_t)(n->numHiddenLayers + 2) * 128 * kRowStride) * 2;
-    NRC_CUDA(n, cudaFuncSetAttribute(k_nrcTrain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    { GFX_TIMED(n->ctx, s, "nrc_train_fwd_bwd");
-    k_nrcTrain<<<numData / 128, 128, smem, s>>>(n->levels, n->params, n->numMatrixWeights, n->numHiddenLayers, inputData,
-                                                targetData, numData, n->grads, n->loss); }
+    // Fully-connected layers on tcgen05 (forward, data gradient and weight gradient); the CUDA-core kernel stays for deep
+    // networks whose activation tiles do not fit in shared memory and as the A/B switch GFX_NRC_TRAIN_CUDACORES=1.
+    const char* cudaCoresEnv = getenv("GFX_NRC_TRAIN_CUDACORES");
+    const bool forceCudaCores = cudaCoresEnv && cudaCoresEnv[0] == '1';
+    if (n->numHiddenLayers <= 3 && !forceCudaCores) {
+        const size_t smem = (size_t)n->numMatrixWeights * 4 + (size_t)(n->numHiddenLayers + 1) * kATileBytes + 3 * (size_t)kATileBytes;
+        NRC_CUDA(n, cudaFuncSetAttribute(k_nrcTrainTc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        { GFX_TIMED(n->ctx, s, "nrc_train_prep_weights");
+        k_nrcPrepTrainWeights<<<32, 256, 0, s>>>(n->params, n->numHiddenLayers, reinterpret_cast<__half*>(n->trainBlobFwd),
+                                                 reinterpret_cast<__half*>(n->trainBlobT)); }
+        n->ctx->launches++;
+        { GFX_TIMED(n->ctx, s, "nrc_train_fwd_bwd");
+        k_nrcTrainTc<<<numData / 128, 128, smem, s>>>(n->levels, n->params, n->numMatrixWeights, n->numHiddenLayers,
+                                                      n->trainBlobFwd, n->trainBlobT, inputData, targetData, numData, n->grads,
+                                                      n->loss); }
+    }
+    else {
+        const size_t smem = ((size_t)n->numMatrixWeights + (size_t)(n->numHiddenLayers + 2) * 128 * kRowStride) * 2;
+        NRC_CUDA(n, cudaFuncSetAttribute(k_nrcTrain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        { GFX_TIMED(n->ctx, s, "nrc_train_fwd_bwd");
+        k_nrcTrain<<<numData / 128, 128, smem, s>>>(n->levels, n->params, n->numMatrixWeights, n->numHiddenLayers, inputData,
+                                                    targetData, numData, n->grads, n->loss); }
+    }
     n->ctx->launches++;
     ++n->globalStep;
     const float emaDecay = 0.99f;

@@ -1,5 +1,5 @@
-"""GPU parity: the NRC network (fused hash-grid/one-blob/identity encoding + tcgen05 MLP inference, CUDA-core
-training step) vs the CPU oracle.  Tensor-core accumulation order is hardware-defined, so the bar is
+"""GPU parity: the NRC network (fused hash-grid/one-blob/identity encoding + tcgen05 MLP inference and training step;
+the CUDA-core training kernel is the A/B arm and the deep-network fallback) vs the CPU oracle.  Tensor-core accumulation order is hardware-defined, so the bar is
 <= 1e-3 relative L2 on inference (BASELINE.json north_star) and agreement of loss curves / weights on training."""
 import numpy as np
 import pytest
@@ -77,3 +77,54 @@ def test_training_tracks_oracle(gfx_ctx, oracle):
     torch.cuda.synchronize()
     assert _rel_l2(out.cpu().numpy(), onet.infer(q)) <= 2e-2
     gnet.close()
+
+
+def test_tensor_core_training_matches_cuda_core_training(gfx_ctx):
+    """The tcgen05 training kernel (forward, data and weight gradients as MMAs) and the CUDA-core kernel implement the
+    same step with the same fp16 rounding points; only the fp32 accumulation order differs."""
+    import os
+    import torch
+    n = 8192
+    q = _queries(n, 21)
+    target = np.stack([0.5 + 0.4 * np.sin(6 * q[:, 0]), q[:, 1] * q[:, 8], 0.3 + 0.5 * q[:, 2]], axis=1).astype(np.float32)
+    dq, dt = torch.from_numpy(q).cuda(), torch.from_numpy(target).cuda()
+    results = {}
+    for arm in ("0", "1"):
+        os.environ["GFX_NRC_TRAIN_CUDACORES"] = arm
+        try:
+            net = engine.NeuralRadianceCache(gfx_ctx, 2, 1e-2)
+            net.set_params(engine.random_nrc_params(net.num_params, 64 * 64 * 2 + 16 * 64, seed=3))
+            losses = [net.train(dq, dt, n, want_loss=True) for _ in range(10)]
+            out = torch.empty((n, 3), dtype=torch.float32, device="cuda")
+            net.infer(dq, out, n)
+            torch.cuda.synchronize()
+            results[arm] = (np.array(losses), out.cpu().numpy())
+            net.close()
+        finally:
+            os.environ.pop("GFX_NRC_TRAIN_CUDACORES", None)
+    (l0, o0), (l1, o1) = results["0"], results["1"]
+    assert np.isfinite(l0).all() and np.isfinite(o0).all()
+    assert abs(l0[0] - l1[0]) <= 1e-5 * abs(l1[0])        # same forward pass on the same weights
+    assert np.abs(l0 - l1).max() <= 0.03 * l1.max(), (l0, l1)
+    assert l0[-1] < 0.5 * l0[0]
+    assert _rel_l2(o0, o1) <= 2e-2, _rel_l2(o0, o1)
+
+
+def test_tensor_core_training_is_deterministic(gfx_ctx):
+    import torch
+    n = 4096
+    q = _queries(n, 22)
+    target = np.stack([q[:, 0], q[:, 1], q[:, 2]], axis=1).astype(np.float32)
+    dq, dt = torch.from_numpy(q).cuda(), torch.from_numpy(target).cuda()
+    outs = []
+    for _ in range(2):
+        net = engine.NeuralRadianceCache(gfx_ctx, 2, 1e-2)
+        net.set_params(engine.random_nrc_params(net.num_params, 64 * 64 * 2 + 16 * 64, seed=5))
+        for _ in range(6):
+            net.train(dq, dt, n)
+        out = torch.empty((n, 3), dtype=torch.float32, device="cuda")
+        net.infer(dq, out, n)
+        torch.cuda.synchronize()
+        outs.append(out.cpu().numpy())
+        net.close()
+    assert np.array_equal(outs[0], outs[1])

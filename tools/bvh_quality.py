@@ -42,6 +42,8 @@ def main():
     ctx = engine.Context(0)
     ctx.upload_scene(scene)
     variants = [("gpu-lbvh (GFX_BVH_BUILD_FAST)", 0x100), ("gpu-ploc (default)", 0)]
+    if "--ploc-only" in sys.argv:
+        variants = variants[1:]
     if "--sweep" in sys.argv:
         variants = [(f"ploc r={r} maxLeaf={ml}", (r << 16) | ml) for r in (16, 32, 64) for ml in (2, 3, 4, 6)] + \
                    [(f"lbvh maxLeaf={ml}", 0x100 | ml) for ml in (2, 3, 6)]
@@ -59,6 +61,16 @@ def main():
         print(json.dumps(res))
     if "--no-sbvh" in sys.argv:
         return
+    if "--sah-nosplit" in sys.argv:
+        cfg = oracle_lib.reference_build_config()
+        cfg.splittingBudget = 0.0
+        t = time.time()
+        osc0 = oracle_lib.OracleScene(scene, cfg)
+        nodes, refs, tris = osc0.export_bvh()
+        print(f"oracle SAH (no spatial splits) build {time.time() - t:.1f}s", file=sys.stderr)
+        ctx.import_bvh(nodes, refs, tris)
+        ctx.create_frame(w, h)
+        print(json.dumps(measure(ctx, scene, w, h, "oracle-sah-nosplit")))
     t = time.time()
     osc = oracle_lib.OracleScene(scene)
     nodes, refs, tris = osc.export_bvh()
