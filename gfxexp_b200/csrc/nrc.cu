@@ -67,6 +67,49 @@ GFX_D float quarticCdf(float x, float invRadius) { // tiny-cuda-nn common_device
     return fmaxf(0.0f, fminf(1.0f, (15.0f / 16.0f) * u * (1 - (2.0f / 3.0f) * u2 + (1.0f / 5.0f) * u4) + 0.5f));
 }
 
+// index % size without an integer division: hashed levels have power-of-two tables, dense levels only wrap for
+// out-of-range positions
+GFX_D uint32_t nrcWrap(uint32_t index, uint32_t size) {
+    if ((size & (size - 1u)) == 0u)
+        return index & (size - 1u);
+    return index < size ? index : index % size;
+}
+
+// grid_index (grid.h:76-111) for the 8 corners of one cell: the per-axis terms of the dense stride sum or of the
+// coherent prime hash are computed once, a corner is one 3-input add/xor plus the wrap. Everything that depends only
+// on the level is warp-uniform.
+struct NrcCellIndexer {
+    uint32_t term[3][2];
+    uint32_t size;
+    bool hashed;
+    GFX_D NrcCellIndexer(const NrcLevel &lv, const uint32_t posGrid[3]) {
+        size = lv.hashmapSize;
+        uint32_t stride = 1;
+        uint32_t strides[3];
+        bool used[3];
+#pragma unroll
+        for (uint32_t dim = 0; dim < 3; ++dim) {
+            used[dim] = stride <= lv.hashmapSize;
+            strides[dim] = stride;
+            if (used[dim])
+                stride *= lv.resolution;
+        }
+        hashed = lv.hashmapSize < stride;
+        const uint32_t primes[3] = { 1u, 2654435761u, 805459861u };
+#pragma unroll
+        for (uint32_t dim = 0; dim < 3; ++dim) {
+            const uint32_t m = hashed ? primes[dim] : (used[dim] ? strides[dim] : 0u);
+            term[dim][0] = posGrid[dim] * m;
+            term[dim][1] = term[dim][0] + m;
+        }
+    }
+    // corner bit d of idx selects posGrid[d] + 1; returns the index of the first of the two features
+    GFX_D uint32_t corner(uint32_t idx) const {
+        const uint32_t a = term[0][idx & 1u], b = term[1][(idx >> 1) & 1u], c = term[2][(idx >> 2) & 1u];
+        return nrcWrap(hashed ? (a ^ b ^ c) : (a + b + c), size) * 2u;
+    }
+};
+
 GFX_D uint32_t nrcGridIndex(const NrcLevel &lv, const uint32_t pos[3]) { // grid.h:76-111
     uint32_t stride = 1;
     uint32_t index = 0;
@@ -90,8 +133,11 @@ GFX_D void nrcEncode(const NrcLevels &levels, const __half* __restrict__ table, 
 #pragma unroll
     for (uint32_t d = 0; d < kInputDims; ++d)
         q[d] = in[d];
-    uint4 featPacked = make_uint4(0, 0, 0, 0);
-#pragma unroll 1 // measured on B200: unrolling (more gathers in flight, 62 regs) is 6 % slower than 1 level at a time
+    __half feat[8];
+    // Measured on B200 (profiles/r01_summary.md, NRC inference A/B): this exact shape - one level at a time, the 8 gathers
+    // interleaved with their index arithmetic - is 10 % faster than issuing the 8 gathers back to back, than 2x/4x
+    // unrolling and than a division-free index; the encoder is bound by the L1's divergent-gather rate, not by issue.
+#pragma unroll 1
     for (uint32_t l = 0; l < kLevels; ++l) {
         const NrcLevel lv = levels.l[l];
         const __half2* grid = reinterpret_cast<const __half2*>(table + (size_t)lv.offset * 2);
@@ -124,23 +170,10 @@ GFX_D void nrcEncode(const NrcLevels &levels, const __half* __restrict__ table, 
             r0 = __float2half(__half2float(r0) + __half2float(__float2half(weight * __low2float(v))));
             r1 = __float2half(__half2float(r1) + __half2float(__float2half(weight * __high2float(v))));
         }
-        // four levels make one 16-byte chunk; selects instead of an indexed array keep the features in registers
-        const uint32_t pair = (uint32_t)__half_as_ushort(r0) | ((uint32_t)__half_as_ushort(r1) << 16);
-        const uint32_t slot = l & 3;
-        if (slot == 0) featPacked.x = pair;
-        else if (slot == 1) featPacked.y = pair;
-        else if (slot == 2) featPacked.z = pair;
-        else {
-            featPacked.w = pair;
-            const uint32_t w4[4] = { featPacked.x, featPacked.y, featPacked.z, featPacked.w };
-            __half feat[8];
-#pragma unroll
-            for (uint32_t e = 0; e < 4; ++e) {
-                feat[2 * e] = __ushort_as_half((unsigned short)(w4[e] & 0xFFFFu));
-                feat[2 * e + 1] = __ushort_as_half((unsigned short)(w4[e] >> 16));
-            }
+        feat[(l & 3) * 2 + 0] = r0;
+        feat[(l & 3) * 2 + 1] = r1;
+        if ((l & 3) == 3)
             emit(l >> 2, feat);
-        }
     }
     // OneBlob: 5 dims x 4 bins -> features 32..51, identity 52..57, ones 58..63
     __half tail[32];
@@ -281,20 +314,21 @@ __global__ void __launch_bounds__(128) k_nrcInfer(NrcLevels levels, const __half
     const uint32_t warp = tid >> 5;
     const uint32_t weightBytes = (numHiddenLayers * kWidth * kWidth + kPaddedOutput * kWidth) * 2;
 
-    // resident weights: ONE bulk asynchronous copy (TMA engine, cp.async.bulk) of the pre-arranged 18 KB blob into shared
-    // memory, completion signalled on an mbarrier by transaction bytes
+    // resident weights (18 KB, once per persistent CTA): cooperative 16-byte copies. -DGFX_NRC_INFER_TMA switches to one
+    // cp.async.bulk + mbarrier like the training kernel; measured neutral for the copy itself and 7 % slower overall
+    // because of the code ptxas then generates for the encoder (profiles/r01_summary.md), so it is off here.
     __shared__ __align__(8) uint64_t weightBar;
     if (tid == 0) {
         mbarInit(&bar, 1);
         mbarInit(&weightBar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-#ifndef GFX_NRC_INFER_NO_TMA
+#ifdef GFX_NRC_INFER_TMA
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smemU32(&weightBar)), "r"(weightBytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      :: "r"(smemU32(sW)), "l"(ummaWeights), "r"(weightBytes), "r"(smemU32(&weightBar)) : "memory");
 #endif
     }
-#ifdef GFX_NRC_INFER_NO_TMA
+#ifndef GFX_NRC_INFER_TMA
     for (uint32_t i = tid; i < weightBytes / 16; i += 128)
         reinterpret_cast<uint4*>(sW)[i] = __ldg(ummaWeights + i);
 #endif
@@ -306,7 +340,7 @@ __global__ void __launch_bounds__(128) k_nrcInfer(NrcLevels levels, const __half
     tcFenceBefore();
     __syncthreads();
     tcFenceAfter();
-#ifndef GFX_NRC_INFER_NO_TMA
+#ifdef GFX_NRC_INFER_TMA
     mbarWait(&weightBar, 0); // the weight blob has landed (async proxy write: visible to tcgen05.mma without a proxy fence)
 #endif
     const uint32_t tmemBase = tmemBaseShared;
@@ -566,20 +600,14 @@ __global__ void __launch_bounds__(128) k_nrcTrain(NrcLevels levels, const __half
                 posGrid[dd] = (uint32_t)tmp;
                 pos[dd] -= (float)tmp;
             }
+            const NrcCellIndexer indexer(lv, posGrid);
+#pragma unroll
             for (uint32_t idx = 0; idx < 8; ++idx) {
                 float weight = 1;
-                uint32_t local[3];
-                for (uint32_t dd = 0; dd < 3; ++dd) {
-                    if ((idx & (1u << dd)) == 0) {
-                        weight *= 1 - pos[dd];
-                        local[dd] = posGrid[dd];
-                    }
-                    else {
-                        weight *= pos[dd];
-                        local[dd] = posGrid[dd] + 1;
-                    }
-                }
-                const uint32_t gi = lv.offset * 2 + nrcGridIndex(lv, local);
+#pragma unroll
+                for (uint32_t dd = 0; dd < 3; ++dd)
+                    weight *= (idx & (1u << dd)) == 0 ? 1 - pos[dd] : pos[dd];
+                const uint32_t gi = lv.offset * 2 + indexer.corner(idx);
                 atomicAddFixed(gGrid + gi, weight * g0);
                 atomicAddFixed(gGrid + gi + 1, weight * g1);
             }
@@ -889,20 +917,14 @@ __global__ void __launch_bounds__(128) k_nrcTrainTc(NrcLevels levels, const __ha
                 posGrid[dd] = (uint32_t)tmp;
                 pos[dd] -= (float)tmp;
             }
+            const NrcCellIndexer indexer(lv, posGrid);
+#pragma unroll
             for (uint32_t idx = 0; idx < 8; ++idx) {
                 float weight = 1;
-                uint32_t local[3];
-                for (uint32_t dd = 0; dd < 3; ++dd) {
-                    if ((idx & (1u << dd)) == 0) {
-                        weight *= 1 - pos[dd];
-                        local[dd] = posGrid[dd];
-                    }
-                    else {
-                        weight *= pos[dd];
-                        local[dd] = posGrid[dd] + 1;
-                    }
-                }
-                const uint32_t gi = lv.offset * 2 + nrcGridIndex(lv, local);
+#pragma unroll
+                for (uint32_t dd = 0; dd < 3; ++dd)
+                    weight *= (idx & (1u << dd)) == 0 ? 1 - pos[dd] : pos[dd];
+                const uint32_t gi = lv.offset * 2 + indexer.corner(idx);
                 atomicAddFixed(gGrid + gi, weight * g0);
                 atomicAddFixed(gGrid + gi + 1, weight * g1);
             }
