@@ -21,6 +21,9 @@
 #include "scene.cuh"
 #include "context.h"
 #include <cub/cub.cuh>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 namespace gfx {
 
@@ -473,6 +476,295 @@ __global__ void k_plocMerge(int m, int n, const uint32_t* __restrict__ clusters,
     out[i] = node;
 }
 
+// ---- 4''. binned SAH, top-down ----------------------------------------------------------------
+// Default hierarchy for static scenes.  Level-synchronous: every open node of a level is split by ONE thread block
+// (1024 threads for nodes above kSahBigNode triangles, 64 below), which
+//   1. reduces the node's AABB and the bounds of its triangle centroids,
+//   2. bins the centroids into 16 bins on each axis (shared-memory atomics on order-preserving integer images of the
+//      float bounds, so the result does not depend on the order of the atomics),
+//   3. evaluates the 3 x 15 split planes with the surface-area heuristic  A_L N_L + A_R N_R  (Wald 2007),
+//   4. partitions its slice of the triangle order stably (ballot ranks + running offsets) and opens two children.
+// The reference builds its hierarchy with the same heuristic on the CPU (bvh_builder.cpp:656-1125, binned object
+// splits + spatial splits); the 8-wide collapse below is shared with the other two hierarchies.
+constexpr uint32_t kSahBins = 16;
+constexpr uint32_t kSahBigNode = 4096;
+
+struct SahArgs {
+    uint32_t n;
+    const float4* triLo;
+    const float4* triHi;
+    uint32_t* order;      // triangle ids, partitioned in place level by level
+    uint32_t* scratch;
+    uint32_t* childL;
+    uint32_t* childR;
+    uint32_t* count;
+    float4* boxLo;
+    float4* boxHi;
+    uint32_t* counters;   // [0] next small-list size, [1] next big-list size, [2] internal nodes allocated
+    const uint4* listIn;  // (node, start, end, -)
+    uint4* smallOut;
+    uint4* bigOut;
+    uint32_t listSize;
+};
+
+template <uint32_t BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_sahSplit(SahArgs a) {
+    constexpr uint32_t WARPS = BLOCK / 32;
+    __shared__ uint32_t sBoundsLo[2][3], sBoundsHi[2][3];            // [0] AABB, [1] centroid bounds (ordered ints)
+    // one private copy of the bins per warp keeps the shared-memory atomics of a 1024-thread block from serialising on
+    // 16 addresses; copy 0 receives the reduction
+    __shared__ uint32_t sBinLo[WARPS][3][kSahBins][3], sBinHi[WARPS][3][kSahBins][3], sBinCount[WARPS][3][kSahBins];
+    __shared__ float sAxisCost[3];
+    __shared__ uint32_t sAxisPlane[3], sAxisLeft[3];
+    __shared__ uint32_t sSplitAxis, sSplitPlane, sNumLeft;
+    __shared__ uint32_t sWarpL[WARPS], sWarpR[WARPS];
+    __shared__ uint32_t sRunL, sRunR;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint4 rec = a.listIn[blockIdx.x];
+    const uint32_t node = rec.x, start = rec.y, end = rec.z;
+    const uint32_t num = end - start;
+
+    if (tid < 3) {
+        sBoundsLo[0][tid] = sBoundsLo[1][tid] = 0xFFFFFFFFu;
+        sBoundsHi[0][tid] = sBoundsHi[1][tid] = 0u;
+    }
+    for (uint32_t i = tid; i < WARPS * 3 * kSahBins * 3; i += BLOCK) {
+        (&sBinLo[0][0][0][0])[i] = 0xFFFFFFFFu;
+        (&sBinHi[0][0][0][0])[i] = 0u;
+    }
+    for (uint32_t i = tid; i < WARPS * 3 * kSahBins; i += BLOCK)
+        (&sBinCount[0][0][0])[i] = 0u;
+    __syncthreads();
+
+    // 1. bounds
+    {
+        float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
+        float clo[3] = { INFINITY, INFINITY, INFINITY }, chi[3] = { -INFINITY, -INFINITY, -INFINITY };
+        for (uint32_t i = start + tid; i < end; i += BLOCK) {
+            const uint32_t t = a.order[i];
+            const float4 l = a.triLo[t], h = a.triHi[t];
+            const float bl[3] = { l.x, l.y, l.z }, bh[3] = { h.x, h.y, h.z };
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const float c = 0.5f * bl[d] + 0.5f * bh[d];
+                lo[d] = fminf(lo[d], bl[d]); hi[d] = fmaxf(hi[d], bh[d]);
+                clo[d] = fminf(clo[d], c); chi[d] = fmaxf(chi[d], c);
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            for (int off = 16; off > 0; off >>= 1) {
+                lo[d] = fminf(lo[d], __shfl_xor_sync(0xFFFFFFFFu, lo[d], off));
+                hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xFFFFFFFFu, hi[d], off));
+                clo[d] = fminf(clo[d], __shfl_xor_sync(0xFFFFFFFFu, clo[d], off));
+                chi[d] = fmaxf(chi[d], __shfl_xor_sync(0xFFFFFFFFu, chi[d], off));
+            }
+            if (lane == 0) {
+                atomicMin(&sBoundsLo[0][d], orderedFromFloat(lo[d]));
+                atomicMax(&sBoundsHi[0][d], orderedFromFloat(hi[d]));
+                atomicMin(&sBoundsLo[1][d], orderedFromFloat(clo[d]));
+                atomicMax(&sBoundsHi[1][d], orderedFromFloat(chi[d]));
+            }
+        }
+    }
+    __syncthreads();
+    float cLo[3], binScale[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        cLo[d] = floatFromOrdered(sBoundsLo[1][d]);
+        const float ext = floatFromOrdered(sBoundsHi[1][d]) - cLo[d];
+        binScale[d] = ext > 0.0f ? (float)kSahBins / ext : 0.0f;
+    }
+    if (tid == 0) {
+        a.boxLo[node] = make_float4(floatFromOrdered(sBoundsLo[0][0]), floatFromOrdered(sBoundsLo[0][1]), floatFromOrdered(sBoundsLo[0][2]), 0.0f);
+        a.boxHi[node] = make_float4(floatFromOrdered(sBoundsHi[0][0]), floatFromOrdered(sBoundsHi[0][1]), floatFromOrdered(sBoundsHi[0][2]), 0.0f);
+        a.count[node] = num;
+    }
+    auto binOf = [&](float c, int d) -> uint32_t {
+        const float f = (c - cLo[d]) * binScale[d];
+        const uint32_t b = (uint32_t)fmaxf(f, 0.0f);
+        return b < kSahBins - 1 ? b : kSahBins - 1;
+    };
+
+    // 2. binning.  Each thread walks a contiguous run of the slice: neighbours in the (initially Morton) order fall
+    // into the same bin, so a strided assignment would make all lanes of a warp hit one address per atomic.
+    const uint32_t perThread = (num + BLOCK - 1) / BLOCK;
+    const uint32_t runBegin = min(end, start + tid * perThread), runEnd = min(end, runBegin + perThread);
+    for (uint32_t i = runBegin; i < runEnd; ++i) {
+        const uint32_t t = a.order[i];
+        const float4 l = a.triLo[t], h = a.triHi[t];
+        const float bl[3] = { l.x, l.y, l.z }, bh[3] = { h.x, h.y, h.z };
+        const uint32_t ol[3] = { orderedFromFloat(l.x), orderedFromFloat(l.y), orderedFromFloat(l.z) };
+        const uint32_t oh[3] = { orderedFromFloat(h.x), orderedFromFloat(h.y), orderedFromFloat(h.z) };
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const uint32_t b = binOf(0.5f * bl[d] + 0.5f * bh[d], d);
+            atomicAdd(&sBinCount[warp][d][b], 1u);
+#pragma unroll
+            for (int e = 0; e < 3; ++e) {
+                atomicMin(&sBinLo[warp][d][b][e], ol[e]);
+                atomicMax(&sBinHi[warp][d][b][e], oh[e]);
+            }
+        }
+    }
+    __syncthreads();
+    if (WARPS > 1) {
+        for (uint32_t i = tid; i < 3 * kSahBins * 3; i += BLOCK) {
+            uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+            for (uint32_t w = 0; w < WARPS; ++w) {
+                lo = min(lo, (&sBinLo[w][0][0][0])[i]);
+                hi = max(hi, (&sBinHi[w][0][0][0])[i]);
+            }
+            (&sBinLo[0][0][0][0])[i] = lo;
+            (&sBinHi[0][0][0][0])[i] = hi;
+        }
+        for (uint32_t i = tid; i < 3 * kSahBins; i += BLOCK) {
+            uint32_t c = 0;
+            for (uint32_t w = 0; w < WARPS; ++w)
+                c += (&sBinCount[w][0][0])[i];
+            (&sBinCount[0][0][0])[i] = c;
+        }
+        __syncthreads();
+    }
+
+    // 3. plane evaluation, one thread per axis
+    if (tid < 3) {
+        const int d = (int)tid;
+        float rightArea[kSahBins];
+        uint32_t rightCount[kSahBins];
+        float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
+        uint32_t cnt = 0;
+        for (int b = (int)kSahBins - 1; b >= 1; --b) {
+            if (sBinCount[0][d][b]) {
+                for (int e = 0; e < 3; ++e) {
+                    lo[e] = fminf(lo[e], floatFromOrdered(sBinLo[0][d][b][e]));
+                    hi[e] = fmaxf(hi[e], floatFromOrdered(sBinHi[0][d][b][e]));
+                }
+                cnt += sBinCount[0][d][b];
+            }
+            const float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
+            rightArea[b] = cnt ? ex * ey + ey * ez + ez * ex : 0.0f;
+            rightCount[b] = cnt;
+        }
+        for (int e = 0; e < 3; ++e) { lo[e] = INFINITY; hi[e] = -INFINITY; }
+        cnt = 0;
+        float bestCost = INFINITY;
+        uint32_t bestPlane = 0, bestLeft = 0;
+        for (int b = 0; b < (int)kSahBins - 1; ++b) { // plane b+1: bins 0..b left
+            if (sBinCount[0][d][b]) {
+                for (int e = 0; e < 3; ++e) {
+                    lo[e] = fminf(lo[e], floatFromOrdered(sBinLo[0][d][b][e]));
+                    hi[e] = fmaxf(hi[e], floatFromOrdered(sBinHi[0][d][b][e]));
+                }
+                cnt += sBinCount[0][d][b];
+            }
+            if (cnt == 0 || rightCount[b + 1] == 0)
+                continue;
+            const float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
+            const float cost = (ex * ey + ey * ez + ez * ex) * (float)cnt + rightArea[b + 1] * (float)rightCount[b + 1];
+            if (cost < bestCost) {
+                bestCost = cost;
+                bestPlane = (uint32_t)b + 1;
+                bestLeft = cnt;
+            }
+        }
+        sAxisCost[d] = bestCost;
+        sAxisPlane[d] = bestPlane;
+        sAxisLeft[d] = bestLeft;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t axis = 0;
+        if (sAxisCost[1] < sAxisCost[axis]) axis = 1;
+        if (sAxisCost[2] < sAxisCost[axis]) axis = 2;
+        sSplitAxis = axis;
+        sSplitPlane = sAxisPlane[axis];       // 0: all centroids coincide -> split the slice in the middle
+        sNumLeft = sAxisPlane[axis] ? sAxisLeft[axis] : num / 2;
+        sRunL = 0;
+        sRunR = 0;
+    }
+    __syncthreads();
+    const uint32_t axis = sSplitAxis, plane = sSplitPlane, numLeft = sNumLeft;
+
+    // 4. stable partition through the scratch buffer
+    if (plane) {
+        for (uint32_t base = start; base < end; base += BLOCK) {
+            const uint32_t i = base + tid;
+            const bool valid = i < end;
+            uint32_t t = 0;
+            bool left = false;
+            if (valid) {
+                t = a.order[i];
+                const float4 l = a.triLo[t], h = a.triHi[t];
+                const float c = axis == 0 ? 0.5f * l.x + 0.5f * h.x : axis == 1 ? 0.5f * l.y + 0.5f * h.y : 0.5f * l.z + 0.5f * h.z;
+                left = binOf(c, (int)axis) < plane;
+            }
+            const uint32_t ballotL = __ballot_sync(0xFFFFFFFFu, valid && left);
+            const uint32_t ballotR = __ballot_sync(0xFFFFFFFFu, valid && !left);
+            if (lane == 0) {
+                sWarpL[warp] = __popc(ballotL);
+                sWarpR[warp] = __popc(ballotR);
+            }
+            __syncthreads();
+            uint32_t offL = sRunL, offR = sRunR, totL = 0, totR = 0;
+            for (uint32_t w = 0; w < WARPS; ++w) {
+                if (w < warp) { offL += sWarpL[w]; offR += sWarpR[w]; }
+                totL += sWarpL[w]; totR += sWarpR[w];
+            }
+            if (valid) {
+                const uint32_t lt = (1u << lane) - 1u;
+                if (left)
+                    a.scratch[start + offL + __popc(ballotL & lt)] = t;
+                else
+                    a.scratch[start + numLeft + offR + __popc(ballotR & lt)] = t;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                sRunL += totL;
+                sRunR += totR;
+            }
+            __syncthreads();
+        }
+        for (uint32_t i = start + tid; i < end; i += BLOCK)
+            a.order[i] = a.scratch[i];
+    }
+
+    // 5. children
+    if (tid == 0) {
+        uint32_t refs[2];
+        const uint32_t ranges[2][2] = { { start, start + numLeft }, { start + numLeft, end } };
+        for (int c = 0; c < 2; ++c) {
+            const uint32_t cnum = ranges[c][1] - ranges[c][0];
+            if (cnum == 1) {
+                refs[c] = 0x80000000u | ranges[c][0];
+            }
+            else {
+                const uint32_t idx = atomicAdd(a.counters + 2, 1u);
+                refs[c] = idx;
+                const uint4 out = make_uint4(idx, ranges[c][0], ranges[c][1], 0u);
+                if (cnum > kSahBigNode)
+                    a.bigOut[atomicAdd(a.counters + 1, 1u)] = out;
+                else
+                    a.smallOut[atomicAdd(a.counters + 0, 1u)] = out;
+            }
+        }
+        a.childL[node] = refs[0];
+        a.childR[node] = refs[1];
+    }
+}
+
+// leaf boxes in their final order
+__global__ void k_sahLeafBoxes(int n, const uint32_t* __restrict__ order, const float4* __restrict__ triLo,
+                               const float4* __restrict__ triHi, float4* boxLo, float4* boxHi) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n)
+        return;
+    const uint32_t t = order[j];
+    boxLo[(n - 1) + j] = triLo[t];
+    boxHi[(n - 1) + j] = triHi[t];
+}
+
 struct PlocValid {
     __device__ __forceinline__ bool operator()(const uint32_t &v) const { return v != 0xFFFFFFFFu; }
 };
@@ -549,6 +841,63 @@ int buildBvh(gfx_ctx* ctx, cudaStream_t stream, uint32_t flags) {
             k_hierarchy<<<(n - 1 + 255) / 256, 256, 0, stream>>>((int)n, keysSorted, childL, childR, rangeFirst, rangeLast, parentI, parentL); ctx->launches++;
         }
         k_refit<<<blocks, 256, 0, stream>>>((int)n, idsSorted, triLo, triHi, childL, childR, parentI, parentL, arrive, boxLo, boxHi); ctx->launches++;
+    }
+    else if (!(flags & GFX_BVH_BUILD_PLOC)) {
+        // binned SAH, top-down: small-node lists ping-pong between keys / keysSorted (n/2 records of 16 B each), big-node
+        // lists are tiny; counters = { next small, next big, internal nodes allocated }
+        uint4* smallLists[2] = { reinterpret_cast<uint4*>(keys), reinterpret_cast<uint4*>(keysSorted) };
+        uint4* bigLists[2] = { nullptr, nullptr };
+        const uint32_t bigCapacity = n / kSahBigNode + 2;
+        GFX_CUDA(ctx, cudaMalloc(&bigLists[0], (size_t)bigCapacity * 16));
+        GFX_CUDA(ctx, cudaMalloc(&bigLists[1], (size_t)bigCapacity * 16));
+        SahArgs sa;
+        sa.n = n;
+        sa.triLo = triLo; sa.triHi = triHi;
+        sa.order = idsSorted; sa.scratch = ids;
+        sa.childL = childL; sa.childR = childR; sa.count = rangeFirst;
+        sa.boxLo = boxLo; sa.boxHi = boxHi;
+        sa.counters = counters;
+        uint32_t sizes[2] = { n > kSahBigNode ? 0u : 1u, n > kSahBigNode ? 1u : 0u }; // { small, big } of the current level
+        const uint4 rootRec = make_uint4(0u, 0u, n, 0u);
+        GFX_CUDA(ctx, cudaMemcpyAsync(sizes[1] ? bigLists[0] : smallLists[0], &rootRec, 16, cudaMemcpyHostToDevice, stream));
+        uint32_t hostSah[3] = { 0u, 0u, 1u }; // node 0 = root
+        GFX_CUDA(ctx, cudaMemcpyAsync(counters, hostSah, 12, cudaMemcpyHostToDevice, stream));
+        int cur = 0;
+        uint32_t depth = 0;
+        const bool profile = getenv("GFX_BVH_SAH_PROFILE") != nullptr;
+        while (sizes[0] + sizes[1] > 0) {
+            const auto t0 = std::chrono::steady_clock::now();
+            sa.smallOut = smallLists[cur ^ 1];
+            sa.bigOut = bigLists[cur ^ 1];
+            if (sizes[1]) {
+                sa.listIn = bigLists[cur];
+                sa.listSize = sizes[1];
+                k_sahSplit<1024><<<sizes[1], 1024, 0, stream>>>(sa); ctx->launches++;
+            }
+            if (sizes[0]) {
+                sa.listIn = smallLists[cur];
+                sa.listSize = sizes[0];
+                k_sahSplit<64><<<sizes[0], 64, 0, stream>>>(sa); ctx->launches++;
+            }
+            GFX_CUDA(ctx, cudaMemcpyAsync(hostSah, counters, 12, cudaMemcpyDeviceToHost, stream));
+            GFX_CUDA(ctx, cudaStreamSynchronize(stream));
+            if (profile)
+                fprintf(stderr, "sah level %u: %u small + %u big nodes, %.3f ms\n", depth, sizes[0], sizes[1],
+                        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+            sizes[0] = hostSah[0];
+            sizes[1] = hostSah[1];
+            const uint32_t zeros[2] = { 0u, 0u };
+            GFX_CUDA(ctx, cudaMemcpyAsync(counters, zeros, 8, cudaMemcpyHostToDevice, stream));
+            cur ^= 1;
+            if (++depth > 4096 || sizes[1] > bigCapacity) {
+                cudaFree(bigLists[0]); cudaFree(bigLists[1]);
+                ctx->setError("gfx_bvh_build: SAH split did not converge");
+                return GFX_ERR_CUDA;
+            }
+        }
+        cudaFree(bigLists[0]); cudaFree(bigLists[1]);
+        k_sahLeafBoxes<<<blocks, 256, 0, stream>>>((int)n, idsSorted, triLo, triHi, boxLo, boxHi); ctx->launches++;
+        rootRef = 0u;
     }
     else {
         // PLOC: clusters ping-pong between parentI / parentL, nearest neighbours in arrive, node counter in counters[3]

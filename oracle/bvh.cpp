@@ -895,7 +895,12 @@ static inline HitObject traverseImpl(const GeometryBVH &bvh, const float3 &rayOr
                     ++stats->numAabbTests;
                 const AABB aabb = nodeChildAabb(intNode, slot);
                 float hitDistMin, hitDistMax;
-                if (aabb.intersectRay(rayOrg, rayDir, distMin, ret.dist, &hitDistMin, &hitDistMax)) {
+                // The reference culls a child box against the current closest distance exactly (:1393); a triangle whose
+                // computed distance is an ulp inside a box whose computed entry is an ulp outside is then lost, and which
+                // of two near-equal hits survives depends on the tree.  The canonical / any-hit modes (the parity modes)
+                // widen the far bound by 1e-5 like the CUDA traverser, so that they equal the brute-force answer.
+                const float cullDist = mode == HitMode::FirstFound ? ret.dist : ret.dist * 1.00001f;
+                if (aabb.intersectRay(rayOrg, rayDir, distMin, cullDist, &hitDistMin, &hitDistMax)) {
                     const bool isLeaf = ((intNode.internalMask >> slot) & 1) == 0;
                     const float dist = 0.5f * (hitDistMin + hitDistMax);
                     keys[slot] = (floatToOrderedUInt(dist) >> 1) | ((isLeaf ? 0u : 1u) << 31);

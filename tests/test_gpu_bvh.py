@@ -26,11 +26,15 @@ def _random_rays(info, n, seed):
     return rays
 
 
-BVH_BUILD_FAST = 0x100  # GFX_BVH_BUILD_FAST: Karras LBVH hierarchy instead of the default PLOC clustering
+BVH_BUILD_FAST = 0x100  # GFX_BVH_BUILD_FAST: Karras LBVH hierarchy
+BVH_BUILD_PLOC = 0x200  # GFX_BVH_BUILD_PLOC: PLOC clustering; the default (0) is the top-down binned-SAH hierarchy
 
 
 @pytest.mark.parametrize("scene_fn,w,h,flags", [(scenes.tiny_city_scene, 160, 96, 0), (scenes.small_city_scene, 320, 200, 0),
                                                 (scenes.small_city_scene, 320, 200, BVH_BUILD_FAST),
+                                                (scenes.small_city_scene, 320, 200, BVH_BUILD_PLOC),
+                                                (scenes.tiny_city_scene, 160, 96, BVH_BUILD_PLOC | 4),
+                                                (scenes.tiny_city_scene, 160, 96, 1), (scenes.small_city_scene, 320, 200, 8),
                                                 (scenes.tiny_city_scene, 160, 96, BVH_BUILD_FAST | 2)])
 def test_lbvh_format_and_closest_hit(gfx_ctx, oracle, scene_fn, w, h, flags):
     scene = scene_fn()

@@ -46,7 +46,7 @@ def test_config2_full_size_properties(gfx_ctx, oracle):
     rays = np.concatenate([rays, extra])
 
     results = {}
-    for tag, flags in (("ploc", 0), ("lbvh", BVH_BUILD_FAST)):
+    for tag, flags in (("sah", 0), ("ploc", 0x200), ("lbvh", BVH_BUILD_FAST)):
         gfx_ctx.build_bvh(flags)
         info = gfx_ctx.bvh_info()
         assert info.numTriangles == scene.num_triangles == info.numPrimRefs

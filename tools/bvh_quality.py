@@ -41,7 +41,7 @@ def main():
     w, h = (640, 360) if small else (1920, 1080)
     ctx = engine.Context(0)
     ctx.upload_scene(scene)
-    variants = [("gpu-lbvh (GFX_BVH_BUILD_FAST)", 0x100), ("gpu-ploc (default)", 0)]
+    variants = [("gpu-lbvh (GFX_BVH_BUILD_FAST)", 0x100), ("gpu-ploc (GFX_BVH_BUILD_PLOC)", 0x200), ("gpu-sah (default)", 0)]
     if "--ploc-only" in sys.argv:
         variants = variants[1:]
     if "--sweep" in sys.argv:
