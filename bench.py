@@ -232,7 +232,8 @@ def run_gpu(args):
 
     if world > 1:
         from gfxexp_b200 import multigpu
-        driver = multigpu.StripDriver(ctx, params, WIDTH, HEIGHT, rank, world)
+        # seam rows travel as one-sided pushes over NVLink peer memory; GFX_MULTIGPU_NCCL=1 selects NCCL send/recv (A/B)
+        driver = multigpu.StripDriver(ctx, params, WIDTH, HEIGHT, rank, world, peer=os.environ.get("GFX_MULTIGPU_NCCL") != "1")
     else:
         driver = None
 
@@ -443,7 +444,9 @@ def run_gpu(args):
                    "emissive_triangles": scene.num_emissive_triangles, "rays_per_pixel": rays_per_px,
                    "l2": "inputs larger than L2 (BVH %.0f MB + %.0f MB of per-pixel state per frame)" % (
                        (info.numTriangles * 52 + info.numNodes * 80) / 1e6, WIDTH * HEIGHT * 400 / 1e6),
-                   "parallelism": "screen strips x%d" % world if world > 1 else "1 GPU",
+                   "parallelism": ("screen strips x%d, seam rows by %s, beauty strips all-gathered with NCCL" % (
+                       world, "one-sided NVLink peer-memory pushes" if driver.backend.peer_ready else "NCCL send/recv"))
+                   if world > 1 else "1 GPU",
                    "bvh_build_ms": bvh_build_ms, "scene_upload_s": upload_s},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": e2e_ms / args.steps, "fps": 1e3 * args.steps / e2e_ms,

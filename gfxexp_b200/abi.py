@@ -102,6 +102,8 @@ SVGF_IS_FIRST_FRAME, SVGF_ENABLE_TEMPORAL_ACCUMULATION, SVGF_FEEDBACK_1ST, SVGF_
  BUF_REGIR_NUM_ACTIVE_CELLS, BUF_SAMPLE_VISIBILITY, BUF_PRESAMPLED_LIGHTS, BUF_PRESAMPLE_RNG) = range(33)
 
 # logical per-pixel layout of each downloadable buffer: (numpy dtype, elements per pixel, planes)
+BUF_PEER_FLAGS = -1  # GFX_BUF_PEER_FLAGS: the flag block of the peer exchange (csrc/peer.cu)
+
 BUFFER_LAYOUT = {
     BUF_GBUFFER0: (np.uint32, 4, 1), BUF_GBUFFER1: (np.float32, 2, 1), BUF_GBUFFER2: (np.uint32, 4, 1),
     BUF_GBUFFER3: (np.uint32, 4, 1), BUF_RNG: (np.uint64, 1, 1), BUF_RESERVOIR: (np.uint32, 4, 3),
@@ -311,6 +313,13 @@ _DECLS = {
     "gfx_pathtrace_launch": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxFrameParams), C.c_int]),
     "gfx_timing_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "gfx_timing_read": (C.c_int, [C.c_void_p, C.c_void_p, c_u32, C.POINTER(c_u32)]),
+    "gfx_peer_export": (C.c_int, [C.c_void_p, C.c_int, c_u32, C.c_void_p]),
+    "gfx_peer_open": (C.c_int, [C.c_void_p, c_u32, C.c_int, c_u32, C.c_void_p]),
+    "gfx_peer_push_rows": (C.c_int, [C.c_void_p, C.c_void_p, c_u32, C.c_int, c_u32, c_u32, c_u32]),
+    "gfx_peer_signal": (C.c_int, [C.c_void_p, C.c_void_p, c_u32, c_u32, c_u32]),
+    "gfx_peer_wait": (C.c_int, [C.c_void_p, C.c_void_p, c_u32, c_u32]),
+    "gfx_peer_status": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(c_u32)]),
+    "gfx_peer_close": (C.c_int, [C.c_void_p]),
     "gfx_regir_build_cells": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxFrameParams), c_u32, C.c_int]),
     "gfx_regir_update_access": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxFrameParams), c_u32]),
     "gfx_nrc_preprocess": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxFrameParams), c_u32, c_u32, C.c_int]),

@@ -204,6 +204,7 @@ int gfx_ctx_create(int device, gfx_ctx** out) {
 void gfx_ctx_destroy(gfx_ctx* ctx) {
     if (!ctx)
         return;
+    gfx_peer_close(ctx);
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     ctx->frame.release();

@@ -6,8 +6,10 @@ offsets.  Per frame:
 
   1. G-buffer for the owned rows plus `halo` rows on each side (stateless, recomputed instead of sent)
   2. initial(+temporal) RIS on the owned rows                                    - no communication
-  3. send/recv of the reservoir + reservoir-info halo rows with the neighbour ranks (the spatial pass
-     gathers within `spatialNeighborRadius` pixels, restir_di_main.cpp:2069; default 20)
+  3. exchange of the reservoir + reservoir-info halo rows with the neighbour ranks (the spatial pass
+     gathers within `spatialNeighborRadius` pixels, restir_di_main.cpp:2069; default 20).  On GPUs this is a
+     one-sided push over NVLink peer memory: each rank's kernels store its seam rows into the neighbour's
+     buffers and raise a sequence flag there (csrc/peer.cu); the gloo/CPU arm uses send/recv.
   4. spatial RIS pass(es) on the owned rows (halo exchange again after every pass that feeds another)
   5. shading on the owned rows, exchange of the final reservoir halo (next frame's temporal reuse)
   6. all-gather of the composited beauty strips: the one mandatory collective
@@ -58,9 +60,30 @@ class GpuBackend:
     def new_tensor(self, numel: int) -> torch.Tensor:
         return torch.empty(numel, dtype=torch.float32, device=f"cuda:{self.ctx.device}")
 
+    # -- one-sided seam exchange over peer memory -------------------------------------------------------
+    PEER_BUFFERS = [(abi.BUF_RESERVOIR, 0), (abi.BUF_RESERVOIR, 1), (abi.BUF_RESERVOIR_INFO, 0), (abi.BUF_RESERVOIR_INFO, 1)]
+
+    def enable_peer(self, rank: int, world: int):
+        """Exchange IPC handles with the neighbour ranks (all ranks must call this; one all_gather_object)."""
+        mine = {"flags": self.ctx.peer_export(abi.BUF_PEER_FLAGS, 0)}
+        for b, i in self.PEER_BUFFERS:
+            mine[(b, i)] = self.ctx.peer_export(b, i)
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine)
+        for link, other in ((0, rank - 1), (1, rank + 1)):
+            if 0 <= other < world:
+                self.ctx.peer_open(link, abi.BUF_PEER_FLAGS, 0, everyone[other]["flags"])
+                for b, i in self.PEER_BUFFERS:
+                    self.ctx.peer_open(link, b, i, everyone[other][(b, i)])
+        self.peer_ready = True
+        self.peer_seq = 0
+
+    peer_ready = False
+
 
 class StripDriver:
-    def __init__(self, backend_or_ctx, params, width: int, height: int, rank: int, world: int, halo: int = 24):
+    def __init__(self, backend_or_ctx, params, width: int, height: int, rank: int, world: int, halo: int = 24,
+                 peer: bool = True):
         self.backend = GpuBackend(backend_or_ctx) if isinstance(backend_or_ctx, engine.Context) else backend_or_ctx
         self.params = params
         self.W, self.H = width, height
@@ -75,6 +98,8 @@ class StripDriver:
         if params.enableJittering:
             raise ValueError("strip sharding recomputes G-buffer halo rows; sub-pixel jitter would double-advance their RNG")
         self.composited = self.backend.new_tensor(width * height * 4)
+        if world > 1 and isinstance(self.backend, GpuBackend) and peer:
+            self.backend.enable_peer(rank, world)
 
     # -- helpers --------------------------------------------------------------------------------------
     def _tile(self, lo: int, hi: int):
@@ -92,6 +117,8 @@ class StripDriver:
         """Neighbour exchange of `halo` seam rows for the given [(buffer_id, index)] list."""
         if self.world == 1:
             return
+        if getattr(self.backend, "peer_ready", False):
+            return self._exchange_halo_peer(buffers)
         ops = []
         for buffer_id, index in buffers:
             if self.rank > 0:  # my top rows go up, their bottom rows come down
@@ -109,6 +136,27 @@ class StripDriver:
         if ops:
             for work in dist.batch_isend_irecv(ops):
                 work.wait()
+
+    def _exchange_halo_peer(self, buffers):
+        """Push my seam rows into the neighbours' buffers, raise their flags, wait for mine (csrc/peer.cu)."""
+        b = self.backend
+        ctx = b.ctx
+        b.peer_seq += 1
+        seq = b.peer_seq
+        up, down = self.rank > 0, self.rank < self.world - 1
+        for buffer_id, index in buffers:
+            if up:
+                ctx.peer_push_rows(0, buffer_id, index, self.y0, min(self.y0 + self.halo, self.y1))
+            if down:
+                ctx.peer_push_rows(1, buffer_id, index, max(self.y1 - self.halo, self.y0), self.y1)
+        if up:
+            ctx.peer_signal(0, 1, seq)   # I am the upper neighbour's lower neighbour: its flag word 1
+        if down:
+            ctx.peer_signal(1, 0, seq)
+        if up:
+            ctx.peer_wait(0, seq)
+        if down:
+            ctx.peer_wait(1, seq)
 
     # -- one frame ------------------------------------------------------------------------------------
     def render_frame(self, frame_index: int, num_spatial_passes: int = 1, unbiased: bool = False):

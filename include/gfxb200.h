@@ -316,6 +316,22 @@ typedef struct GfxKernelTiming {
 int gfx_timing_enable(gfx_ctx* ctx, int enable);
 int gfx_timing_read(gfx_ctx* ctx, GfxKernelTiming* out, uint32_t capacity, uint32_t* numWritten);
 
+/* ---- multi-GPU: one-sided seam-row exchange over NVLink peer memory (csrc/peer.cu) -------------------------------
+ * The reference is a single-GPU program; a strip-sharded frame needs the reservoirs of `halo` rows across
+ * each seam.  Each rank exports the IPC handles of its reservoir buffers and of its flag block
+ * (bufferId = GFX_BUF_PEER_FLAGS), the neighbours open them (link 0 = the rank above, 1 = the rank below), and an
+ * exchange is: push my seam rows into the neighbour's buffer, raise sequence `value` in its flag word, wait for my own
+ * flag word to reach `value`.  All calls are asynchronous on `stream`.  gfx_peer_status reports whether a wait timed out
+ * (neighbour died): the GPU is never left spinning. */
+#define GFX_BUF_PEER_FLAGS (-1)
+int gfx_peer_export(gfx_ctx* ctx, int bufferId, uint32_t index, void* handle64);
+int gfx_peer_open(gfx_ctx* ctx, uint32_t link, int bufferId, uint32_t index, const void* handle64);
+int gfx_peer_push_rows(gfx_ctx* ctx, void* stream, uint32_t link, int bufferId, uint32_t index, uint32_t rowLo, uint32_t rowHi);
+int gfx_peer_signal(gfx_ctx* ctx, void* stream, uint32_t link, uint32_t flagIndex, uint32_t value);
+int gfx_peer_wait(gfx_ctx* ctx, void* stream, uint32_t flagIndex, uint32_t value);
+int gfx_peer_status(gfx_ctx* ctx, void* stream, uint32_t* timedOut);
+int gfx_peer_close(gfx_ctx* ctx);
+
 /* ---- scene, acceleration structure, light distributions ------------------------------ */
 /* replaces Scene::initialize + createTriangleMeshes/createInstance uploads
  * (common/common_host.h:912-969, common/common_host.cpp:2178-2429,2582-2656) */

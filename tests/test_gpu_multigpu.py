@@ -1,5 +1,6 @@
-"""2-GPU parity (skipped on a 1-GPU box): the NCCL strip-sharded frame composited on rank 0 is bit-identical to
-the single-GPU frame of the same library."""
+"""2-GPU parity (skipped on a 1-GPU box): the strip-sharded frame composited on rank 0 is bit-identical to the single-GPU
+frame of the same library, with the seam rows exchanged by one-sided pushes over NVLink peer memory (csrc/peer.cu) and
+with NCCL send/recv."""
 import os
 import socket
 import sys
@@ -12,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 W, H, FRAMES = 320, 192, 3
 
 
-def _worker(rank, world, port, result_path):
+def _worker(rank, world, port, result_path, peer):
     import torch
     import torch.distributed as dist
     sys.path.insert(0, ROOT)
@@ -27,12 +28,14 @@ def _worker(rank, world, port, result_path):
     ctx.build_bvh()
     ctx.create_frame(W, H)
     p = abi.default_frame_params(scene, W, H)
-    driver = multigpu.StripDriver(ctx, p, W, H, rank, world)
+    driver = multigpu.StripDriver(ctx, p, W, H, rank, world, peer=peer)
+    assert driver.backend.peer_ready == peer
     outs = []
     for f in range(FRAMES):
         driver.render_frame(f, num_spatial_passes=2)
         torch.cuda.synchronize()
         outs.append(driver.composited.cpu().numpy().copy())
+    assert not ctx.peer_timed_out()
     if rank == 0:
         np.save(result_path, np.stack(outs))
     dist.barrier()
@@ -40,7 +43,8 @@ def _worker(rank, world, port, result_path):
     ctx.close()
 
 
-def test_two_gpu_strips_equal_single_gpu(tmp_path, gfx_ctx):
+@pytest.mark.parametrize("peer", [True, False])
+def test_two_gpu_strips_equal_single_gpu(tmp_path, gfx_ctx, peer):
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
@@ -51,7 +55,7 @@ def test_two_gpu_strips_equal_single_gpu(tmp_path, gfx_ctx):
     port = s.getsockname()[1]
     s.close()
     result = str(tmp_path / "composited.npy")
-    mp.spawn(_worker, args=(2, port, result), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, result, peer), nprocs=2, join=True)
     got = np.load(result)
 
     scene = scenes.small_city_scene()
