@@ -203,6 +203,31 @@ def main():
                                   "inference + 4 training steps"}))
         net.close()
 
+    def stage_rearch():
+        # ---- rearchitected ReSTIR DI (R5): presampled lights, per-tile subsets, <= 3 / 7 shadow rays per pixel
+        for unbiased in (False, True):
+            pr = abi.default_frame_params(scene, w, h)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            n_frames, n_warm = 20, 5
+            for f in range(n_frames + n_warm):
+                if f == n_warm:
+                    ctx.timing_enable(True)
+                    ctx.timing_read()
+                    ev[0].record()
+                pr.numAccumFrames = f
+                ctx.build_light_distributions(f % 2)
+                for kind, pid in engine.restir_rearch_frame_passes(pr, f, True, True, unbiased):
+                    ctx.gbuffer(pr) if kind == "gbuffer" else ctx.restir(pr, pid)
+            ev[1].record()
+            torch.cuda.synchronize()
+            per = {k: round(v[0] / n_frames, 4) for k, v in ctx.timing_read().items()}
+            ctx.timing_enable(False)
+            ms = ev[0].elapsed_time(ev[1]) / n_frames
+            print(json.dumps({"stage": "restir_rearchitected_unbiased" if unbiased else "restir_rearchitected_biased",
+                              "ms_per_frame_with_timing_events": ms, "fps": 1e3 / ms, "per_kernel_ms": per}))
+
+    if want("rearch"):
+        stage_rearch()
     if want("combined"):
         stage_combined()
 
