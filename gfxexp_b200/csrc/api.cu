@@ -22,7 +22,7 @@ void SceneState::release() {
     *this = SceneState();
 }
 void BvhState::release() {
-    cudaFree(nodes); cudaFree(primRefs); cudaFree(tris); cudaFree(sceneBounds);
+    cudaFree(nodes); cudaFree(primRefs); cudaFree(tris); cudaFree(leafTris); cudaFree(sceneBounds);
     uint32_t* keepFlag = overflowFlag;
     *this = BvhState();
     overflowFlag = keepFlag;
@@ -139,6 +139,7 @@ DevScene gfx_ctx::devScene() const {
     d.bvh.nodes = reinterpret_cast<const uint4*>(bvh.nodes);
     d.bvh.primRefs = bvh.primRefs;
     d.bvh.tris = bvh.tris;
+    d.bvh.leafTris = bvh.leafTris;
     d.bvh.numNodes = bvh.numNodes;
     d.bvh.overflowFlag = bvh.overflowFlag;
     return d;
@@ -406,7 +407,9 @@ int gfx_bvh_build(gfx_ctx* ctx, void* stream, uint32_t flags) {
         return GFX_ERR_NOT_READY;
     }
     GFX_CUDA(ctx, cudaSetDevice(ctx->device));
-    const int rc = buildBvh(ctx, (cudaStream_t)stream, flags);
+    int rc = buildBvh(ctx, (cudaStream_t)stream, flags);
+    if (rc == GFX_OK)
+        rc = finishBvh(ctx, (cudaStream_t)stream);
     if (rc == GFX_OK)
         ctx->bvh.ready = true;
     return rc;
@@ -457,6 +460,9 @@ int gfx_bvh_import(gfx_ctx* ctx, const GfxBvhNode8* nodes, uint32_t numNodes, co
     B.numNodes = numNodes;
     B.numPrimRefs = numPrimRefs;
     B.numTris = numTris;
+    if (int rc = finishBvh(ctx, nullptr))
+        return rc;
+    GFX_CUDA(ctx, cudaStreamSynchronize(nullptr));
     B.ready = true;
     return GFX_OK;
 }

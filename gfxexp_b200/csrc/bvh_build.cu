@@ -987,4 +987,37 @@ int buildBvh(gfx_ctx* ctx, cudaStream_t stream, uint32_t flags) {
     return GFX_OK;
 }
 
+// ---- 7. traversal tables ------------------------------------------------------------------------
+// The reference layout keeps triangles in scene order behind a PrimitiveReference indirection (common_shared.h:1012-1025).
+// The traverser reads a second copy in leaf order: leafTris[i] = tris[primRefs[i] & 0x7FFFFFFF] with the reference word
+// (storage index + end-of-leaf bit) in the padding field, so a leaf costs one dependent fetch instead of two and the
+// triangles of a leaf - and of the sibling leaves of a node - are adjacent in memory.
+__global__ void k_leafTris(uint32_t numPrimRefs, const uint32_t* __restrict__ primRefs, const float4* __restrict__ tris,
+                           float4* __restrict__ leafTris) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= numPrimRefs)
+        return;
+    const uint32_t pr = primRefs[i];
+    const float4* src = tris + 3 * (size_t)(pr & 0x7FFFFFFFu);
+    float4* dst = leafTris + 3 * (size_t)i;
+    dst[0] = src[0];
+    dst[1] = src[1];
+    float4 t2 = src[2];
+    t2.w = __uint_as_float(pr);
+    dst[2] = t2;
+}
+
+int finishBvh(gfx_ctx* ctx, cudaStream_t stream) {
+    BvhState &B = ctx->bvh;
+    cudaFree(B.leafTris);
+    B.leafTris = nullptr;
+    GFX_CUDA(ctx, cudaMalloc(&B.leafTris, (size_t)max(B.numPrimRefs, 1u) * 48));
+    if (B.numPrimRefs) {
+        k_leafTris<<<(B.numPrimRefs + 255) / 256, 256, 0, stream>>>(B.numPrimRefs, B.primRefs, B.tris, B.leafTris);
+        ctx->launches++;
+        GFX_CUDA(ctx, cudaGetLastError());
+    }
+    return GFX_OK;
+}
+
 } // namespace gfx

@@ -51,6 +51,7 @@ struct BvhState {
     void* nodes = nullptr;       // GfxBvhNode8[numNodes]
     uint32_t* primRefs = nullptr;
     float4* tris = nullptr;      // GfxTriangleStorage[numTris]
+    float4* leafTris = nullptr;  // traversal copy: TriangleStorage per primitive reference, in leaf order (see finishBvh)
     uint32_t* sceneBounds = nullptr;
     uint32_t* overflowFlag = nullptr;
     uint32_t numNodes = 0, numPrimRefs = 0, numTris = 0, levels = 0;
@@ -222,6 +223,7 @@ struct KernelTimerScope {
 
 namespace gfx {
 int buildBvh(gfx_ctx* ctx, cudaStream_t stream, uint32_t flags);
+int finishBvh(gfx_ctx* ctx, cudaStream_t stream); // derived traversal tables of a built or imported BVH
 int traceRays(gfx_ctx* ctx, cudaStream_t stream, const GfxRay* dRays, uint32_t numRays, GfxHitObject* dHits, int mode);
 int resetVisibilityQueue(gfx_ctx* ctx, cudaStream_t stream);
 int traceVisibilityQueue(gfx_ctx* ctx, cudaStream_t stream);

@@ -45,7 +45,8 @@ static_assert(sizeof(DevInstance) % 16 == 0, "DevInstance must stay 16-byte alig
 struct DevBvh {
     const uint4* nodes;     // 5 x uint4 per node
     const uint32_t* primRefs;
-    const float4* tris;     // 3 x float4 per triangle
+    const float4* tris;     // 3 x float4 per triangle (reference layout, indexed by TriangleStorage index)
+    const float4* leafTris; // 3 x float4 per primitive reference, leaf order; .w of the third = primRef word
     uint32_t numNodes;
     uint32_t* overflowFlag; // set to 1 if a traversal stack overflowed (checked by the host)
 };

@@ -166,12 +166,12 @@ GFX_D bool traverseStep(const DevBvh &bvh, TraversalState &st) {
         const uint32_t metas = slot < 4 ? n1.z : n1.w;
         uint32_t idx = leafBase + ((metas >> (8 * (slot & 3))) & 0xFFu);
         while (true) {
-            const uint32_t pr = __ldg(bvh.primRefs + idx);
-            const uint32_t si = pr & 0x7FFFFFFFu;
-            const float4* tp = bvh.tris + 3 * (size_t)si;
+            const float4* tp = bvh.leafTris + 3 * (size_t)idx;
             const float4 t0 = __ldg(tp + 0);
             const float4 t1 = __ldg(tp + 1);
             const float4 t2 = __ldg(tp + 2);
+            const uint32_t pr = __float_as_uint(t2.w); // PrimitiveReference word: storage index | end-of-leaf << 31
+            const uint32_t si = pr & 0x7FFFFFFFu;
             float hitDist, bcB, bcC;
             if (STATS)
                 ++st.best.statTris;
