@@ -84,10 +84,68 @@ GFX_D void traverseInit(TraversalState &st, const f3 &org, const f3 &dir, float 
     st.sp = 0;
 }
 
-// Processes node st.nodeIdx: slab-tests its children, intersects the triangle chains of the leaf
-// children that are hit, selects the next internal node.  Returns false when the traversal is finished.
+// Leaf children whose triangle tests have been postponed (wavefront kernel): the start of the triangle chain and the
+// entry distance of the leaf box.  A node step appends at most 8.
+constexpr int kPendingLeaves = 12;
+struct PendingLeaves {
+    uint32_t idx[kPendingLeaves];
+    float tn[kPendingLeaves];
+    int n;
+};
+
+// One triangle of a leaf chain (leaf-ordered storage).  Returns true when an any-hit ray has found its occluder.
 template <bool ANY_HIT, bool STATS>
-GFX_D bool traverseStep(const DevBvh &bvh, TraversalState &st) {
+GFX_D bool testLeafTriangle(const DevBvh &bvh, TraversalState &st, uint32_t idx, bool* endOfChain) {
+    const float4* tp = bvh.leafTris + 3 * (size_t)idx;
+    const float4 t0 = __ldg(tp + 0);
+    const float4 t1 = __ldg(tp + 1);
+    const float4 t2 = __ldg(tp + 2);
+    const uint32_t pr = __float_as_uint(t2.w); // PrimitiveReference word: storage index | end-of-leaf << 31
+    const uint32_t si = pr & 0x7FFFFFFFu;
+    *endOfChain = (pr >> 31) != 0;
+    float hitDist, bcB, bcC;
+    if (STATS)
+        ++st.best.statTris;
+    const bool hit = testRayVsTriangle(st.org, st.dir, st.tmin, st.tmax,
+                                       f3(t0.x, t0.y, t0.z), f3(t0.w, t1.x, t1.y), f3(t1.z, t1.w, t2.x),
+                                       &hitDist, &bcB, &bcC);
+    if (hit && (hitDist < st.best.dist || (hitDist == st.best.dist && si < st.best.storageIndex))) {
+        st.best.dist = hitDist;
+        st.best.storageIndex = si;
+        st.best.geomIndex = __float_as_uint(t2.y);
+        st.best.primIndex = __float_as_uint(t2.z);
+        st.best.bcB = bcB;
+        st.best.bcC = bcC;
+        if (ANY_HIT)
+            return true;
+    }
+    return false;
+}
+
+// Advances the newest postponed leaf of this lane by one triangle.  Returns true when an any-hit ray is occluded.
+template <bool ANY_HIT, bool STATS>
+GFX_D bool testPendingTriangle(const DevBvh &bvh, TraversalState &st, PendingLeaves &pend) {
+    const int top = pend.n - 1;
+    if (pend.tn[top] > st.best.dist) { // a closer hit has been found since the leaf was postponed
+        pend.n = top;
+        return false;
+    }
+    const uint32_t idx = pend.idx[top];
+    bool end;
+    if (testLeafTriangle<ANY_HIT, STATS>(bvh, st, idx, &end))
+        return true;
+    if (end)
+        pend.n = top;
+    else
+        pend.idx[top] = idx + 1;
+    return false;
+}
+
+// Processes node st.nodeIdx: slab-tests its children, intersects the triangle chains of the leaf
+// children that are hit (or, with `pend`, postpones them), selects the next internal node.  Returns false when the
+// traversal is finished.
+template <bool ANY_HIT, bool STATS, bool DEFER = false>
+GFX_D bool traverseStep(const DevBvh &bvh, TraversalState &st, PendingLeaves* pend = nullptr) {
     const uint4* np = bvh.nodes + 5 * (size_t)st.nodeIdx;
     const uint4 n0 = __ldg(np + 0);
     const uint4 n1 = __ldg(np + 1);
@@ -165,30 +223,17 @@ GFX_D bool traverseStep(const DevBvh &bvh, TraversalState &st) {
             continue;
         const uint32_t metas = slot < 4 ? n1.z : n1.w;
         uint32_t idx = leafBase + ((metas >> (8 * (slot & 3))) & 0xFFu);
+        if (DEFER) {
+            pend->idx[pend->n] = idx;
+            pend->tn[pend->n] = tn;
+            ++pend->n;
+            continue;
+        }
         while (true) {
-            const float4* tp = bvh.leafTris + 3 * (size_t)idx;
-            const float4 t0 = __ldg(tp + 0);
-            const float4 t1 = __ldg(tp + 1);
-            const float4 t2 = __ldg(tp + 2);
-            const uint32_t pr = __float_as_uint(t2.w); // PrimitiveReference word: storage index | end-of-leaf << 31
-            const uint32_t si = pr & 0x7FFFFFFFu;
-            float hitDist, bcB, bcC;
-            if (STATS)
-                ++st.best.statTris;
-            const bool hit = testRayVsTriangle(st.org, st.dir, st.tmin, st.tmax,
-                                               f3(t0.x, t0.y, t0.z), f3(t0.w, t1.x, t1.y), f3(t1.z, t1.w, t2.x),
-                                               &hitDist, &bcB, &bcC);
-            if (hit && (hitDist < st.best.dist || (hitDist == st.best.dist && si < st.best.storageIndex))) {
-                st.best.dist = hitDist;
-                st.best.storageIndex = si;
-                st.best.geomIndex = __float_as_uint(t2.y);
-                st.best.primIndex = __float_as_uint(t2.z);
-                st.best.bcB = bcB;
-                st.best.bcC = bcC;
-                if (ANY_HIT)
-                    return false;
-            }
-            if (pr >> 31)
+            bool end;
+            if (testLeafTriangle<ANY_HIT, STATS>(bvh, st, idx, &end))
+                return false;
+            if (end)
                 break;
             ++idx;
         }
