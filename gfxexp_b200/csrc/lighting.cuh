@@ -56,11 +56,14 @@ GFX_D float remapCdf(const float* __restrict__ cdf, uint32_t numValues, float in
     return (u - lCDF) / (rCDF - lCDF);
 }
 
-GFX_D void sampleLight(const DevScene &s, float ul, float u0, float u1, LightSample* lightSample, float* areaPDensity) {
-    // restir_di_shared.h:320-516 with sampleEnvLight = false, useSolidAngleSampling = false.
-    // The three DiscreteDistribution1D::sample calls are spelled out; weights[idx] / integral comes
-    // from the pre-divided prob tables and the triangle operands from the lightTris table (lights.cu),
-    // both produced by the reference's own expressions, so the result is bit-identical.
+// The three DiscreteDistribution1D::sample calls of sampleLight (instance, geometry instance, primitive) spelled out;
+// weights[idx] / integral comes from the pre-divided prob tables.  Returns false on sampleLight's probability-0 early outs.
+struct LightTrianglePick {
+    const DevInstance* inst;
+    uint32_t lightTri;   // index into the lightTris table (lights.cu)
+    float lightProb;
+};
+GFX_D bool pickLightTriangle(const DevScene &s, float ul, LightTrianglePick* pick) {
     float lightProb = 1.0f;
 
     // instance
@@ -71,10 +74,8 @@ GFX_D void sampleLight(const DevScene &s, float ul, float u0, float u1, LightSam
     const float instProb = __ldg(s.instProb + instSlot);
     lightProb *= instProb;
     const DevInstance* inst = s.instances + instSlot;
-    if (instProb == 0.0f) {
-        *areaPDensity = 0.0f;
-        return;
-    }
+    if (instProb == 0.0f)
+        return false;
 
     // geometry instance
     const uint32_t firstMeshSlot = inst->firstMeshSlot, numMeshSlots = inst->numMeshSlots;
@@ -85,44 +86,113 @@ GFX_D void sampleLight(const DevScene &s, float ul, float u0, float u1, LightSam
     const float geomInstProb = __ldg(s.geomProb + firstMeshSlot + geomInstIndexInInst);
     const uint32_t geomInstSlot = __ldg(s.instanceMeshSlots + firstMeshSlot + geomInstIndexInInst);
     lightProb *= geomInstProb;
-    if (geomInstProb == 0.0f) {
-        *areaPDensity = 0.0f;
-        return;
-    }
+    if (geomInstProb == 0.0f)
+        return false;
 
     // primitive
     const DevMesh* mesh = s.meshes + geomInstSlot;
-    const uint32_t triBase = mesh->triBase, numTriangles = mesh->numTriangles;
+    const uint32_t triBase = mesh->triBase;
     u = uPrim * mesh->primIntegral;
     const uint32_t primIndex = guidedSearchCdf(s.primCdf + triBase, s.primGuide + (size_t)geomInstSlot * (kPrimGuideSize + 1),
                                                kPrimGuideSize, uPrim, u);
     const float primProb = __ldg(s.primProb + triBase + primIndex);
     lightProb *= primProb;
 
-    const uint32_t lt = __ldg(s.lightTriBase + inst->geomBase + geomInstIndexInInst) + primIndex;
-    const float4* e = s.lightTris + 6 * (size_t)lt;
+    pick->inst = inst;
+    pick->lightTri = __ldg(s.lightTriBase + inst->geomBase + geomInstIndexInInst) + primIndex;
+    pick->lightProb = lightProb;
+    return true;
+}
+
+// A Low-Distortion Map Between Triangle and Square (restir_di_shared.h:485-498)
+GFX_D void squareToTriangle(float u0, float u1, float* bcA, float* bcB, float* bcC) {
+    float a = 0.5f * u0;
+    float b = 0.5f * u1;
+    const float offset = b - a;
+    if (offset > 0)
+        b += offset;
+    else
+        a -= offset;
+    *bcA = a;
+    *bcB = b;
+    *bcC = 1 - (a + b);
+}
+
+GFX_D void sampleLight(const DevScene &s, float ul, float u0, float u1, LightSample* lightSample, float* areaPDensity) {
+    // restir_di_shared.h:320-516 with sampleEnvLight = false, useSolidAngleSampling = false; the triangle operands come
+    // from the lightTris table (lights.cu), produced by the reference's own expressions, so the result is bit-identical.
+    LightTrianglePick pick;
+    if (!pickLightTriangle(s, ul, &pick)) {
+        *areaPDensity = 0.0f;
+        return;
+    }
+    const float4* e = s.lightTris + 6 * (size_t)pick.lightTri;
     const float4 e0 = __ldg(e + 0), e1 = __ldg(e + 1), e2 = __ldg(e + 2), e3 = __ldg(e + 3), e4 = __ldg(e + 4), e5 = __ldg(e + 5);
     const f3 pA(e0.x, e0.y, e0.z), pB(e1.x, e1.y, e1.z), pC(e2.x, e2.y, e2.z);
     const f3 nA(e1.w, e2.w, e3.x), nB(e3.y, e3.z, e3.w), nC(e4.x, e4.y, e4.z);
-
-    // A Low-Distortion Map Between Triangle and Square (:485-498)
-    float bcA = 0.5f * u0;
-    float bcB = 0.5f * u1;
-    const float offset = bcB - bcA;
-    if (offset > 0)
-        bcB += offset;
-    else
-        bcA -= offset;
-    const float bcC = 1 - (bcA + bcB);
+    float bcA, bcB, bcC;
+    squareToTriangle(u0, u1, &bcA, &bcB, &bcC);
 
     const float recArea = e0.w;
-    *areaPDensity = lightProb * recArea;
+    *areaPDensity = pick.lightProb * recArea;
 
     lightSample->position = bcA * pA + bcB * pB + bcC * pC;
     lightSample->atInfinity = 0;
     lightSample->normal = bcA * nA + bcB * nB + bcC * nC;
-    lightSample->normal = normalize(mul3x3(inst->normalMatrix, lightSample->normal));
+    lightSample->normal = normalize(mul3x3(pick.inst->normalMatrix, lightSample->normal));
     lightSample->emittance = f3(e5.x, e5.y, e5.z);
+}
+
+// sampleLight for the RIS candidate loop, fetching the 96-byte light triangle in three steps and stopping as soon as
+// the candidate is certain to contribute RGB(0) to this shading point.  ncu: the candidate kernel runs the L1 data pipe
+// at 84 % of its wavefront rate (535 M wavefronts for 77 M load instructions - every lane reads a different light), and
+// the six 16-byte fetches of the light triangle are three quarters of them; ~70 % of the candidates are dark.
+//   step 1: the three vertices -> sample position.  Below the shading horizon (the BRDFs return RGB(0) when
+//           vGiven.z * vSampled.z <= 0)?  -> dark, 3 fetches and the instance's normal matrix saved;
+//   step 2: the vertex normals -> un-normalised light normal.  Facing away (lpCos <= 0)? -> dark, 1 fetch saved;
+//   step 3: the emittance, the normalisation: the full sample.
+// Both tests run on un-normalised vectors with a relative margin of 1e-3 on the cosine - three orders of magnitude above
+// the rounding of the exact evaluation - so borderline samples go on to the exact path and no decision ever differs from
+// performDirectLighting's; NaNs and a zero distance fail the comparisons and also go on.  Returns true for "dark" (then
+// *areaPDensity is the sample's density and is positive); otherwise the outputs are sampleLight's, bit for bit.
+GFX_D bool sampleLightUnlessDark(const DevScene &s, float ul, float u0, float u1, const f3 &shadingPoint,
+                                 const f3 &shadingNormal, float vOutLocalZ, LightSample* lightSample, float* areaPDensity) {
+    LightTrianglePick pick;
+    if (!pickLightTriangle(s, ul, &pick)) {
+        *areaPDensity = 0.0f;
+        return false;
+    }
+    const float4* e = s.lightTris + 6 * (size_t)pick.lightTri;
+    const float4 e0 = __ldg(e + 0), e1 = __ldg(e + 1), e2 = __ldg(e + 2);
+    const f3 pA(e0.x, e0.y, e0.z), pB(e1.x, e1.y, e1.z), pC(e2.x, e2.y, e2.z);
+    float bcA, bcB, bcC;
+    squareToTriangle(u0, u1, &bcA, &bcB, &bcC);
+    const float recArea = e0.w;
+    const float density = pick.lightProb * recArea;
+    *areaPDensity = density;
+    const f3 position = bcA * pA + bcB * pB + bcC * pC;
+
+    const float k = 1e-6f; // (1e-3)^2
+    const f3 d = position - shadingPoint;
+    const float dd = sqLength(d);
+    const float b = dot(d, shadingNormal) * vOutLocalZ; // < 0: light and viewer on opposite sides of the surface
+    if (density > 0.0f && b < 0.0f && b * b > k * dd * (vOutLocalZ * vOutLocalZ))
+        return true;
+
+    const float4 e3 = __ldg(e + 3), e4 = __ldg(e + 4);
+    const f3 nA(e1.w, e2.w, e3.x), nB(e3.y, e3.z, e3.w), nC(e4.x, e4.y, e4.z);
+    f3 normal = bcA * nA + bcB * nB + bcC * nC;
+    normal = mul3x3(pick.inst->normalMatrix, normal);
+    const float a = dot(d, normal); // > 0: the emitter faces away from the shading point
+    if (density > 0.0f && a > 0.0f && a * a > k * dd * sqLength(normal))
+        return true;
+
+    const float4 e5 = __ldg(e + 5);
+    lightSample->position = position;
+    lightSample->atInfinity = 0;
+    lightSample->normal = normalize(normal);
+    lightSample->emittance = f3(e5.x, e5.y, e5.z);
+    return false;
 }
 
 GFX_D bool traceVisibility(const DevScene &s, const f3 &org, const f3 &dir, float tmax) {

@@ -73,7 +73,12 @@ GFX_D bool risPixel(const DevScene &s, const DevFrame &f, const DevFrameParams &
         float probDensity;
         const float u0 = rng.getFloat0cTo1o();
         const float u1 = rng.getFloat0cTo1o();
-        sampleLight(s, ul, u0, u1, &lightSample, &probDensity);
+        // staged fetch of the light triangle: certainly-dark candidates stop early (their contribution is exactly
+        // RGB(0): the reservoir is untouched and only the acceptance draw is consumed, as in the dead path below)
+        if (sampleLightUnlessDark(s, ul, u0, u1, positionInWorld, shadingNormalInWorld, vOutLocal.z, &lightSample, &probDensity)) {
+            (void)rng.getFloat0cTo1o();
+            continue;
+        }
         probDensity *= probToSampleCurLightType;
         // Dead candidates (light faces away, or lies below the shading horizon: ~70 % of them) contribute exactly
         // RGB(0) (performDirectLighting returns RGB(0) before any arithmetic when lpCos <= 0, and the BRDFs
