@@ -100,8 +100,13 @@ class ClockSampler:
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
-# (profiles/r01_summary.md): 114.8 + 142.4 MB for the RIS candidate kernel, 84.6 + 10.9 MB for the visibility trace
-NCU_DRAM_TRAFFIC = {"ris_candidates": 257.2e6, "trace_visibility": 95.5e6}
+# (profiles/r01_summary.md): 114.7 + 143.0 MB for the RIS candidate kernel (r01f), 84.6 + 10.9 MB for the visibility trace
+NCU_DRAM_TRAFFIC = {"ris_candidates": 257.7e6, "trace_visibility": 95.5e6}
+# what actually bounds the dominant kernel (same capture): the L1 data pipe, not HBM
+NCU_NOTE = {"ris_candidates": {"l1tex_data_pipe_lsu_wavefronts_pct_of_peak": 79.6, "l1_load_wavefronts_per_launch": 422.3e6,
+                               "issue_active_pct": 54.3, "warps_active_pct": 36.1,
+                               "reading": "bound by L1 wavefronts of divergent table gathers (every lane samples a different "
+                                          "light); DRAM traffic equals the algorithmic bytes"}}
 
 
 def frame_launches(ctx, params, frame_index, num_spatial_passes, timers=None):
@@ -410,7 +415,7 @@ def run_gpu(args):
         bytes_per_launch = alg.get(dominant, 0) * px
         achieved = bytes_per_launch / (breakdown[dominant] * 1e-3) / 1e9
         roofline = {"kernel": dominant, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": achieved / hbm_peak, "traffic": NCU_DRAM_TRAFFIC.get(dominant), "traffic_source": "ncu --set full, profiles/r01_summary.md", "peak_source": peak_src,
+                    "frac": achieved / hbm_peak, "traffic": NCU_DRAM_TRAFFIC.get(dominant), "traffic_source": "ncu --set full, profiles/r01_summary.md", "ncu": NCU_NOTE.get(dominant), "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": bytes_per_launch, "ms_per_launch": breakdown[dominant],
                     "traversal": {"primary_nodes_per_ray": n_int_p, "primary_tris_per_ray": n_tri_p,
                                   "shadow_nodes_per_ray": n_int_s, "shadow_tris_per_ray": n_tri_s},
