@@ -169,6 +169,21 @@ class SceneArrays:
         self.desc.numInstanceMeshSlots = self.slots.shape[0]
 
 
+def make_instance_descs(instances):
+    """GfxInstanceDesc[] for gfx_scene_update_instances: same (firstMeshSlot, numMeshSlots) numbering as SceneArrays"""
+    insts = (GfxInstanceDesc * len(instances))()
+    first = 0
+    for i, inst in enumerate(instances):
+        insts[i].transform = (c_f * 12)(*np.asarray(inst.transform, dtype=np.float32).reshape(-1))
+        insts[i].curToPrevTransform = (c_f * 12)(*np.asarray(inst.cur_to_prev, dtype=np.float32).reshape(-1))
+        insts[i].normalMatrix = (c_f * 9)(*np.asarray(inst.normal_matrix, dtype=np.float32).reshape(-1))
+        insts[i].uniformScale = inst.uniform_scale
+        insts[i].firstMeshSlot = first
+        insts[i].numMeshSlots = len(inst.mesh_slots)
+        first += len(inst.mesh_slots)
+    return insts
+
+
 def make_camera(scene, width: int, height: int) -> GfxCamera:
     cam = GfxCamera()
     cam.aspect = float(np.float32(width) / np.float32(height))

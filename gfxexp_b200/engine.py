@@ -62,6 +62,12 @@ class Context:
         self._scene_arrays = abi.SceneArrays(scene)
         self._check(self.lib.gfx_scene_upload(self.h, C.byref(self._scene_arrays.desc)), "gfx_scene_upload")
 
+    def update_instances(self, instance_descs, stream=None):
+        """per-frame instance update (InstanceController::update): new transforms, curToPrevTransform, normal matrices;
+        follow with build_bvh (GFX_BVH_BUILD_FAST for per-frame rebuilds) and build_light_distributions"""
+        self._check(self.lib.gfx_scene_update_instances(self.h, stream, instance_descs, len(instance_descs)),
+                    "gfx_scene_update_instances")
+
     def build_bvh(self, flags: int = 0, stream=None):
         self._check(self.lib.gfx_bvh_build(self.h, stream, flags), "gfx_bvh_build")
 

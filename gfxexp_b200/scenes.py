@@ -210,6 +210,19 @@ def make_instance(mesh_slots, translate=(0, 0, 0), yaw_deg=0.0, scale=1.0, pitch
     return Instance(m32, ident, nm, float(F32(scale)), list(mesh_slots))
 
 
+def move_instance(prev: Instance, translate=(0, 0, 0), yaw_deg=0.0, scale=1.0, pitch_deg=0.0) -> Instance:
+    """The instance one animation step later (InstanceController::update, common/common_host.h:798-856): a new T * R * S
+    and curToPrevTransform = prevTransform * inverse(curTransform), which the G-buffer pass uses for motion vectors."""
+    cur = make_instance(prev.mesh_slots, translate, yaw_deg, scale, pitch_deg)
+
+    def to44(m34):
+        m = np.eye(4, dtype=np.float64)
+        m[:3, :] = np.asarray(m34, dtype=np.float64)
+        return m
+    cur_to_prev = (to44(prev.transform) @ np.linalg.inv(to44(cur.transform)))[:3, :].astype(F32)
+    return Instance(cur.transform, cur_to_prev, cur.normal_matrix, cur.uniform_scale, list(prev.mesh_slots))
+
+
 def _random_materials(rng: np.random.Generator, count: int) -> np.ndarray:
     mats = np.zeros(count, dtype=MATERIAL_DTYPE)
     q_diffuse = rng.integers(30, 230, size=(count, 3), dtype=np.int64)

@@ -43,6 +43,8 @@ enum { ORC_TRACE_FIRST_FOUND = 0, ORC_TRACE_CANONICAL = 1, ORC_TRACE_BRUTE_FORCE
 /* scene = flattened geometries + SBVH (bvh::buildGeometryBVH<8>) + light distributions */
 orc_scene* orc_scene_create(const GfxSceneDesc* scene, const OrcBuildConfig* cfg, int numThreads);
 void orc_scene_destroy(orc_scene* s);
+/* new instance transforms -> rebuild of the world-space BVH and of the light distributions; 0 on success */
+int orc_scene_update_instances(orc_scene* s, const GfxInstanceDesc* instances, uint32_t numInstances);
 double orc_scene_build_seconds(orc_scene* s);
 void orc_bvh_info(orc_scene* s, GfxBvhInfo* info);
 void orc_bvh_export(orc_scene* s, GfxBvhNode8* nodes, uint32_t* primRefs, GfxTriangleStorage* tris);

@@ -49,6 +49,7 @@ struct orc_scene {
     float instIntegral = 0.0f;
     double buildSeconds = 0.0;
     float sceneMin[3], sceneMax[3];
+    OrcBuildConfig buildConfig;
 };
 
 // sequential fp32 exclusive scan (stands in for ext/cubd ExclusiveSum)
@@ -103,31 +104,17 @@ static void buildLightDistributions(orc_scene* s) {
     s->instIntegral = exclusiveScan(s->instWeights, s->instCdf);
 }
 
-extern "C" orc_scene* orc_scene_create(const GfxSceneDesc* d, const OrcBuildConfig* cfg, int numThreads) {
-    orc_scene* s = new orc_scene();
-    s->meshes.resize(d->numMeshes);
-    for (uint32_t i = 0; i < d->numMeshes; ++i) {
-        const GfxMeshDesc &md = d->meshes[i];
-        MeshData &m = s->meshes[i];
-        m.numVertices = md.numVertices;
-        m.numTriangles = md.numTriangles;
-        m.materialSlot = md.materialSlot;
-        m.positions.assign(md.positions, md.positions + 3 * (size_t)md.numVertices);
-        m.normals.assign(md.normals, md.normals + 3 * (size_t)md.numVertices);
-        m.tangents.assign(md.tangents, md.tangents + 3 * (size_t)md.numVertices);
-        m.texcoords.assign(md.texcoords, md.texcoords + 2 * (size_t)md.numVertices);
-        m.triangles.assign(md.triangles, md.triangles + 3 * (size_t)md.numTriangles);
-    }
-    s->materials.assign(d->materials, d->materials + d->numMaterials);
-    s->instances.resize(d->numInstances);
-    for (uint32_t i = 0; i < d->numInstances; ++i)
-        s->instances[i].desc = d->instances[i];
-    s->instanceMeshSlots.assign(d->instanceMeshSlots, d->instanceMeshSlots + d->numInstanceMeshSlots);
-
+// world-space side of the scene: flattened geometry, BVH, bounds, light distributions
+static void rebuildWorld(orc_scene* s, int numThreads) {
+    const OrcBuildConfig* cfg = &s->buildConfig;
+    s->geomToInst.clear();
+    s->geomToMesh.clear();
+    s->bvh = GeometryBVH();
+    const uint32_t numInstances = (uint32_t)s->instances.size();
     // flatten (instance, mesh) pairs into bvh::Geometry records in instance order
     std::vector<Geometry> geoms;
-    for (uint32_t i = 0; i < d->numInstances; ++i) {
-        const GfxInstanceDesc &inst = d->instances[i];
+    for (uint32_t i = 0; i < numInstances; ++i) {
+        const GfxInstanceDesc &inst = s->instances[i].desc;
         for (uint32_t k = 0; k < inst.numMeshSlots; ++k) {
             const uint32_t meshSlot = s->instanceMeshSlots[inst.firstMeshSlot + k];
             const MeshData &m = s->meshes[meshSlot];
@@ -168,7 +155,48 @@ extern "C" orc_scene* orc_scene_create(const GfxSceneDesc* d, const OrcBuildConf
         s->sceneMax[i] = box.maxP[i];
     }
     buildLightDistributions(s);
+}
+
+extern "C" orc_scene* orc_scene_create(const GfxSceneDesc* d, const OrcBuildConfig* cfg, int numThreads) {
+    orc_scene* s = new orc_scene();
+    s->meshes.resize(d->numMeshes);
+    for (uint32_t i = 0; i < d->numMeshes; ++i) {
+        const GfxMeshDesc &md = d->meshes[i];
+        MeshData &m = s->meshes[i];
+        m.numVertices = md.numVertices;
+        m.numTriangles = md.numTriangles;
+        m.materialSlot = md.materialSlot;
+        m.positions.assign(md.positions, md.positions + 3 * (size_t)md.numVertices);
+        m.normals.assign(md.normals, md.normals + 3 * (size_t)md.numVertices);
+        m.tangents.assign(md.tangents, md.tangents + 3 * (size_t)md.numVertices);
+        m.texcoords.assign(md.texcoords, md.texcoords + 2 * (size_t)md.numVertices);
+        m.triangles.assign(md.triangles, md.triangles + 3 * (size_t)md.numTriangles);
+    }
+    s->materials.assign(d->materials, d->materials + d->numMaterials);
+    s->instances.resize(d->numInstances);
+    for (uint32_t i = 0; i < d->numInstances; ++i)
+        s->instances[i].desc = d->instances[i];
+    s->instanceMeshSlots.assign(d->instanceMeshSlots, d->instanceMeshSlots + d->numInstanceMeshSlots);
+
+    s->buildConfig = *cfg;
+    rebuildWorld(s, numThreads);
     return s;
+}
+
+// InstanceController::update (common/common_host.h:798-856) as seen from the hot path: new instance transforms (with their
+// curToPrevTransform and normal matrices) arrive from the host, the acceleration structure over the moved geometry is
+// rebuilt (Scene::updateASs) and the light distribution is recomputed (instance importances depend on the scale).
+extern "C" int orc_scene_update_instances(orc_scene* s, const GfxInstanceDesc* instances, uint32_t numInstances) {
+    if (!s || !instances || numInstances != s->instances.size())
+        return -1;
+    for (uint32_t i = 0; i < numInstances; ++i) {
+        if (instances[i].firstMeshSlot != s->instances[i].desc.firstMeshSlot ||
+            instances[i].numMeshSlots != s->instances[i].desc.numMeshSlots)
+            return -2; // the topology of the scene is fixed; only transforms animate
+        s->instances[i].desc = instances[i];
+    }
+    rebuildWorld(s, 0);
+    return 0;
 }
 extern "C" void orc_scene_destroy(orc_scene* s) { delete s; }
 extern "C" double orc_scene_build_seconds(orc_scene* s) { return s->buildSeconds; }

@@ -54,6 +54,8 @@ def lib() -> C.CDLL:
         L.orc_scene_create.restype = vp
         L.orc_scene_create.argtypes = [C.POINTER(abi.GfxSceneDesc), C.POINTER(OrcBuildConfig), C.c_int]
         L.orc_scene_destroy.argtypes = [vp]
+        L.orc_scene_update_instances.restype = C.c_int
+        L.orc_scene_update_instances.argtypes = [vp, C.POINTER(abi.GfxInstanceDesc), C.c_uint32]
         L.orc_scene_build_seconds.restype = C.c_double
         L.orc_scene_build_seconds.argtypes = [vp]
         L.orc_bvh_info.argtypes = [vp, C.POINTER(abi.GfxBvhInfo)]
@@ -120,6 +122,11 @@ class OracleScene:
 
     def __del__(self):
         self.close()
+
+    def update_instances(self, instance_descs):
+        """new instance transforms: rebuilds the world-space SBVH and the light distributions"""
+        rc = lib().orc_scene_update_instances(self.h, instance_descs, len(instance_descs))
+        assert rc == 0, rc
 
     @property
     def build_seconds(self) -> float:
