@@ -3,6 +3,7 @@
 each stage, inputs resident): path tracer (P1), NRC frame (N1-N5), ReGIR frame (C1), SVGF passes (V1-V4).
 One JSON line per stage; `--small` uses the small city at 640x360 for a quick functional run."""
 import json
+import time
 import os
 import sys
 
@@ -226,6 +227,52 @@ def main():
             print(json.dumps({"stage": "restir_rearchitected_unbiased" if unbiased else "restir_rearchitected_biased",
                               "ms_per_frame_with_timing_events": ms, "fps": 1e3 / ms, "per_kernel_ms": per}))
 
+    def stage_animated():
+        # ---- every frame 10 % of the instances move (InstanceController::update), the BVH is rebuilt with the
+        # LBVH builder and the light distributions are recomputed before the ReSTIR DI frame
+        from gfxexp_b200 import scenes as sc
+        pa = abi.default_frame_params(scene, w, h)
+        movers = list(range(1, len(scene.instances), 10))
+        current = list(scene.instances)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        n_frames, n_warm = 10, 3
+        descs_per_frame = []
+        for f in range(n_frames + n_warm):
+            nxt = list(current)
+            for i in movers:
+                t = np.asarray(current[i].transform, dtype=np.float64)
+                scale = float(np.linalg.norm(t[:, 0]))
+                yaw = float(np.degrees(np.arctan2(t[0, 2], t[0, 0])))
+                nxt[i] = sc.move_instance(current[i], translate=(t[0, 3] + 0.02, t[1, 3], t[2, 3]), yaw_deg=yaw + 1.0, scale=scale)
+            current = nxt
+            descs_per_frame.append(abi.make_instance_descs(current))
+        ctx.timing_enable(False)
+        build_ms = []
+        for f in range(n_frames + n_warm):
+            if f == n_warm:
+                torch.cuda.synchronize()
+                ev[0].record()
+            ctx.update_instances(descs_per_frame[f])
+            t0 = time.perf_counter()
+            ctx.build_bvh(0x100)
+            if f >= n_warm:
+                torch.cuda.synchronize()
+                build_ms.append((time.perf_counter() - t0) * 1e3)
+            ctx.build_light_distributions(f % 2)
+            for kind, pid in engine.restir_frame_passes(pa, f, 1, True, False):
+                ctx.gbuffer(pa) if kind == "gbuffer" else ctx.restir(pa, pid)
+        ev[1].record()
+        torch.cuda.synchronize()
+        ms = ev[0].elapsed_time(ev[1]) / n_frames
+        print(json.dumps({"stage": "restir_di_animated", "ms_per_frame": ms, "fps": 1e3 / ms, "moving_instances": len(movers),
+                          "lbvh_rebuild_ms_wall": float(np.mean(build_ms)), "triangles": int(scene.num_triangles),
+                          "note": "instance update + LBVH rebuild (GFX_BVH_BUILD_FAST) + light distributions + ReSTIR DI frame"}))
+        ctx.upload_scene(scene)
+        ctx.build_bvh()
+        ctx.create_frame(w, h)
+
+    if want("animated"):
+        stage_animated()
     if want("rearch"):
         stage_rearch()
     if want("combined"):
