@@ -51,6 +51,11 @@ class GfxCamera(C.Structure):
     _fields_ = [("aspect", c_f), ("fovY", c_f), ("position", c_f * 3), ("orientation", c_f * 9)]
 
 
+class GfxPresentParams(C.Structure):
+    _fields_ = [("sourceBuffer", C.c_int32), ("sourceIndex", c_u32), ("mode", C.c_int32), ("flags", c_u32),
+                ("brightnessScale", c_f), ("alphaForOverride", c_f)]
+
+
 class GfxKernelTiming(C.Structure):
     _fields_ = [("label", C.c_char * 48), ("totalMs", c_f), ("launches", c_u32)]
 
@@ -102,6 +107,9 @@ SVGF_IS_FIRST_FRAME, SVGF_ENABLE_TEMPORAL_ACCUMULATION, SVGF_FEEDBACK_1ST, SVGF_
  BUF_REGIR_NUM_ACTIVE_CELLS, BUF_SAMPLE_VISIBILITY, BUF_PRESAMPLED_LIGHTS, BUF_PRESAMPLE_RNG) = range(33)
 
 # logical per-pixel layout of each downloadable buffer: (numpy dtype, elements per pixel, planes)
+BUF_PRESENT_RGBA8 = 33
+PRESENT_COLOR, PRESENT_NORMAL = 0, 1
+PRESENT_TONE_MAP, PRESENT_SRGB_GAMMA, PRESENT_FLIP_Y = 1, 2, 4
 BUF_PEER_FLAGS = -1  # GFX_BUF_PEER_FLAGS: the flag block of the peer exchange (csrc/peer.cu)
 
 BUFFER_LAYOUT = {
@@ -111,7 +119,7 @@ BUFFER_LAYOUT = {
     BUF_ALBEDO_ACCUM: (np.float32, 4, 1), BUF_NORMAL_ACCUM: (np.float32, 4, 1), BUF_SAMPLE_VISIBILITY: (np.uint32, 1, 1),
     BUF_SVGF_LIGHTING_VARIANCE: (np.float32, 4, 1), BUF_SVGF_FINAL: (np.float32, 4, 1),
     BUF_SVGF_MOMENTS: (np.uint32, 4, 1), BUF_SVGF_PREV_LIGHTING: (np.float32, 4, 1),
-    BUF_SVGF_ALBEDO: (np.float32, 4, 1), BUF_SVGF_DEPTH: (np.float32, 1, 1),
+    BUF_SVGF_ALBEDO: (np.float32, 4, 1), BUF_SVGF_DEPTH: (np.float32, 1, 1), BUF_PRESENT_RGBA8: (np.uint32, 1, 1),
 }
 
 
@@ -328,6 +336,7 @@ _DECLS = {
     "gfx_pathtrace_launch": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxFrameParams), C.c_int]),
     "gfx_timing_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "gfx_timing_read": (C.c_int, [C.c_void_p, C.c_void_p, c_u32, C.POINTER(c_u32)]),
+    "gfx_present_launch": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxPresentParams)]),
     "gfx_peer_export": (C.c_int, [C.c_void_p, C.c_int, c_u32, C.c_void_p]),
     "gfx_peer_open": (C.c_int, [C.c_void_p, c_u32, C.c_int, c_u32, C.c_void_p]),
     "gfx_peer_push_rows": (C.c_int, [C.c_void_p, C.c_void_p, c_u32, C.c_int, c_u32, c_u32, c_u32]),

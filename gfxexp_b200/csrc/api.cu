@@ -35,6 +35,7 @@ void FrameState::release() {
         cudaFree(ptExtRays[i]); cudaFree(ptExtPixel[i]);
     }
     cudaFree(rayQueue); cudaFree(rayPixel); cudaFree(rayCounters); cudaFree(visibility);
+    cudaFree(presentRgba8);
     cudaFree(stats); cudaFree(rng); cudaFree(beauty); cudaFree(albedo); cudaFree(normal); cudaFree(neighborDeltas);
     cudaFree(svgfPrevLighting); cudaFree(svgfAlbedo); cudaFree(svgfPrevScreenPos); cudaFree(svgfNormal);
     cudaFree(ptAlphaPdf); cudaFree(ptRadiance); cudaFree(ptExtHits); cudaFree(ptShadowPending); cudaFree(ptCounters);
@@ -670,6 +671,7 @@ static void* bufferPtr(gfx_ctx* ctx, int id, uint32_t index, size_t* bytes) {
     case GFX_BUF_RESERVOIR: p = F.reservoir[i]; b = n * 48; break;
     case GFX_BUF_RESERVOIR_INFO: p = F.reservoirInfo[i]; b = n * 8; break;
     case GFX_BUF_BEAUTY_ACCUM: p = F.beauty; b = n * 16; break;
+    case GFX_BUF_PRESENT_RGBA8: p = F.presentRgba8; b = F.presentRgba8 ? n * 4 : 0; break;
     case GFX_BUF_ALBEDO_ACCUM: p = F.albedo; b = n * 16; break;
     case GFX_BUF_NORMAL_ACCUM: p = F.normal; b = n * 16; break;
     case GFX_BUF_SVGF_LIGHTING_VARIANCE: p = F.svgfLighting[i]; b = n * 16; break;
@@ -783,6 +785,16 @@ int gfx_restir_launch(gfx_ctx* ctx, void* stream, const GfxFrameParams* params, 
     if (pass >= GFX_RESTIR_PRESAMPLE_LIGHTS)
         return launchReSTIRRearch(ctx, (cudaStream_t)stream, params, pass);
     return launchReSTIR(ctx, (cudaStream_t)stream, params, pass);
+}
+
+int gfx_present_launch(gfx_ctx* ctx, void* stream, const GfxPresentParams* params) {
+    CHECK_CTX(ctx);
+    if (!params)
+        return GFX_ERR_INVALID_ARGUMENT;
+    if (!ctx->frame.created)
+        return GFX_ERR_NOT_READY;
+    GFX_CUDA(ctx, cudaSetDevice(ctx->device));
+    return launchPresent(ctx, (cudaStream_t)stream, params);
 }
 
 int gfx_svgf_launch(gfx_ctx* ctx, void* stream, const GfxFrameParams* params, int pass, uint32_t stage) {

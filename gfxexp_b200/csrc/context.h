@@ -70,6 +70,7 @@ struct FrameState {
     float4* reservoir[2] = { nullptr, nullptr };
     float2* reservoirInfo[2] = { nullptr, nullptr };
     float4* beauty = nullptr;
+    uint32_t* presentRgba8 = nullptr; // gfx_present_launch output, allocated on first use
     float4* albedo = nullptr;
     float4* normal = nullptr;
     float2* neighborDeltas = nullptr;
@@ -223,7 +224,8 @@ struct KernelTimerScope {
 
 namespace gfx {
 int buildBvh(gfx_ctx* ctx, cudaStream_t stream, uint32_t flags);
-int finishBvh(gfx_ctx* ctx, cudaStream_t stream); // derived traversal tables of a built or imported BVH
+int finishBvh(gfx_ctx* ctx, cudaStream_t stream);
+int launchPresent(gfx_ctx* ctx, cudaStream_t stream, const GfxPresentParams* params); // derived traversal tables of a built or imported BVH
 int traceRays(gfx_ctx* ctx, cudaStream_t stream, const GfxRay* dRays, uint32_t numRays, GfxHitObject* dHits, int mode);
 int resetVisibilityQueue(gfx_ctx* ctx, cudaStream_t stream);
 int traceVisibilityQueue(gfx_ctx* ctx, cudaStream_t stream);

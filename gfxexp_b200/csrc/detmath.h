@@ -181,3 +181,49 @@ DM_HD float dm_exp(float x) {
     }
     return p * dm_u2f((uint32_t)(ki + 127) << 23);
 }
+
+// log(x) for x > 0 (normal or subnormal); Cephes logf.  Used by dm_pow for the sRGB transfer function of the output side.
+DM_HD float dm_log(float x) {
+    if (!(x > 0.0f)) return x == 0.0f ? -INFINITY : NAN;
+    if (x == INFINITY) return INFINITY;
+    // frexp through the exponent field: x = m * 2^e with m in [0.5, 1)
+    int32_t e = 0;
+    uint32_t bits = dm_f2u(x);
+    if ((bits >> 23) == 0u) { // subnormal: scale by 2^24 first
+        x = x * 16777216.0f;
+        bits = dm_f2u(x);
+        e = -24;
+    }
+    e += (int32_t)(bits >> 23) - 126;
+    float m = dm_u2f((bits & 0x007FFFFFu) | 0x3F000000u);
+    if (m < 0.707106781186547524f) {
+        e -= 1;
+        m = m + m - 1.0f;
+    }
+    else {
+        m = m - 1.0f;
+    }
+    const float z = m * m;
+    float y = 7.0376836292e-2f * m + -1.1514610310e-1f;
+    y = y * m + 1.1676998740e-1f;
+    y = y * m + -1.2420140846e-1f;
+    y = y * m + 1.4249322787e-1f;
+    y = y * m + -1.6668057665e-1f;
+    y = y * m + 2.0000714765e-1f;
+    y = y * m + -2.4999993993e-1f;
+    y = y * m + 3.3333331174e-1f;
+    y = y * m * z;
+    const float fe = (float)e;
+    y = y + -2.12194440e-4f * fe;
+    y = y + -0.5f * z;
+    float r = m + y;
+    r = r + 0.693359375f * fe;
+    return r;
+}
+
+// x^y for x >= 0 as exp(y log x): accurate to a few ULP for the exponents of the sRGB curves (|y log x| < 10), which is
+// far below one 8-bit code; what matters is that both sides compute the same bits.
+DM_HD float dm_pow(float x, float y) {
+    if (x == 0.0f) return y > 0.0f ? 0.0f : (y == 0.0f ? 1.0f : INFINITY);
+    return dm_exp(y * dm_log(x));
+}

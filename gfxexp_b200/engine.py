@@ -190,6 +190,15 @@ class Context:
     def restir(self, params, pass_id: int, stream=None):
         self._check(self.lib.gfx_restir_launch(self.h, stream, C.byref(params), pass_id), "gfx_restir_launch")
 
+    def present(self, source_buffer: int = abi.BUF_BEAUTY_ACCUM, source_index: int = 0, mode: int = abi.PRESENT_COLOR,
+                flags: int = abi.PRESENT_TONE_MAP | abi.PRESENT_SRGB_GAMMA, brightness_scale: float = 1.0,
+                alpha_override: float = 1.0, stream=None) -> np.ndarray:
+        """accumulation buffer -> tone-mapped, sRGB-encoded RGBA8 [H, W] uint32 (R | G << 8 | B << 16 | A << 24), the
+        packing of the reference's saveImage(path, w, h, const uint32_t*)"""
+        pp = abi.GfxPresentParams(source_buffer, source_index, mode, flags, brightness_scale, alpha_override)
+        self._check(self.lib.gfx_present_launch(self.h, stream, C.byref(pp)), "gfx_present_launch")
+        return self.download(abi.BUF_PRESENT_RGBA8)
+
     def pathtrace(self, params, variant: int = abi.PT_BASELINE, stream=None):
         """one sample per pixel of the path tracer (path_tracing_main.cpp:1780-1789) from the current G-buffer"""
         self._check(self.lib.gfx_pathtrace_launch(self.h, stream, C.byref(params), variant), "gfx_pathtrace_launch")

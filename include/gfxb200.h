@@ -294,7 +294,9 @@ typedef enum GfxBufferId {
     /* rearchitected ReSTIR */
     GFX_BUF_SAMPLE_VISIBILITY = 30,     /* [2] uint32 per pixel : SampleVisibility bits (restir_di_shared.h:146-164) */
     GFX_BUF_PRESAMPLED_LIGHTS = 31,     /* 12 words x 131072 : emittance3 areaPDensity | position3 atInfinity | normal3 0 */
-    GFX_BUF_PRESAMPLE_RNG = 32          /* uint64 x 131072 : lightPreSamplingRngs */
+    GFX_BUF_PRESAMPLE_RNG = 32,         /* uint64 x 131072 : lightPreSamplingRngs */
+    /* output side */
+    GFX_BUF_PRESENT_RGBA8 = 33          /* uint32 per pixel, R | G << 8 | B << 16 | A << 24 : gfx_present_launch */
 } GfxBufferId;
 
 /* ---- context ------------------------------------------------------------------------- */
@@ -315,6 +317,29 @@ typedef struct GfxKernelTiming {
 } GfxKernelTiming;
 int gfx_timing_enable(gfx_ctx* ctx, int enable);
 int gfx_timing_read(gfx_ctx* ctx, GfxKernelTiming* out, uint32_t capacity, uint32_t* numWritten);
+
+/* ---- output side -------------------------------------------------------------------------------------
+ * What the reference does between the accumulation buffers and a picture: copyToLinearBuffers + visualizeToOutputBuffer
+ * (restir_di/gpu_kernels/copy_buffers.cu:6-28,32-80: normals are normalised and shown as 0.5 + 0.5 n), the display shader's
+ * tone map (common/shaders/drawOptiXResult.frag; the screenshot path saveImage(float4*, SDRImageSaverConfig),
+ * common/common_host.cpp:2859-2897, is the same arithmetic on the CPU): non-finite colours -> 0,
+ * lum = sRGB luminance, colour *= (1 - exp(-brightnessScale * lum)) / lum, then sRGB_gamma_s (basic_types.h:5405-5410) and
+ * 8-bit packing min(uint(v * 255), 255).  The packed image is what the reference's own
+ * saveImage(path, width, height, const uint32_t*) (common_host.cpp:2715) writes with stb. */
+typedef enum GfxPresentMode { GFX_PRESENT_COLOR = 0, GFX_PRESENT_NORMAL = 1 } GfxPresentMode;
+#define GFX_PRESENT_TONE_MAP 1u
+#define GFX_PRESENT_SRGB_GAMMA 2u
+#define GFX_PRESENT_FLIP_Y 4u
+typedef struct GfxPresentParams {
+    int32_t sourceBuffer;      /* a float4-per-pixel frame buffer: GFX_BUF_BEAUTY_ACCUM, _ALBEDO_ACCUM, _NORMAL_ACCUM, GFX_BUF_SVGF_FINAL ... */
+    uint32_t sourceIndex;
+    int32_t mode;              /* GfxPresentMode */
+    uint32_t flags;            /* GFX_PRESENT_* */
+    float brightnessScale;     /* 10^brightness of the reference UI */
+    float alphaForOverride;    /* >= 0: written instead of the source alpha (SDRImageSaverConfig::alphaForOverride) */
+} GfxPresentParams;
+/* writes GFX_BUF_PRESENT_RGBA8 (read it with gfx_buffer_download or gfx_buffer_device_ptr) */
+int gfx_present_launch(gfx_ctx* ctx, void* stream, const GfxPresentParams* params);
 
 /* ---- multi-GPU: one-sided seam-row exchange over NVLink peer memory (csrc/peer.cu) -------------------------------
  * The reference is a single-GPU program; a strip-sharded frame needs the reservoirs of `halo` rows across

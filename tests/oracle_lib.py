@@ -65,6 +65,7 @@ def lib() -> C.CDLL:
         L.orc_bvh_validate.argtypes = [vp, C.c_char_p, C.c_size_t]
         L.orc_trace.argtypes = [vp, vp, C.c_uint32, vp, C.c_int, C.POINTER(OrcTraversalStats), C.c_int]
         L.orc_light_dist_export.argtypes = [vp, vp, vp, C.POINTER(C.c_float)]
+        L.orc_present.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(abi.GfxPresentParams), vp]
         L.orc_frame_create.restype = vp
         L.orc_frame_create.argtypes = [vp, C.c_uint32, C.c_uint32]
         L.orc_frame_destroy.argtypes = [vp]
@@ -105,6 +106,16 @@ def lib() -> C.CDLL:
         L.orc_nrc_train.argtypes = [vp, vp, vp, C.c_uint32]
         _lib = L
     return _lib
+
+
+def present(rgba: np.ndarray, mode: int = 0, flags: int = 3, brightness_scale: float = 1.0, alpha_override: float = 1.0) -> np.ndarray:
+    """the reference's output side on a float4 image [H, W, 4] -> packed RGBA8 [H, W] uint32 (oracle/present.cpp)"""
+    src = np.ascontiguousarray(rgba, dtype=np.float32)
+    h, w = src.shape[:2]
+    out = np.empty((h, w), dtype=np.uint32)
+    pp = abi.GfxPresentParams(0, 0, mode, flags, brightness_scale, alpha_override)
+    lib().orc_present(src.ctypes.data_as(C.c_void_p), w, h, C.byref(pp), out.ctypes.data_as(C.c_void_p))
+    return out
 
 
 class OracleScene:
