@@ -95,6 +95,8 @@ class StripDriver:
         self.rows = rows
         if rows * world != height:
             raise ValueError(f"height {height} must be divisible by the number of ranks {world} (equal all-gather chunks)")
+        if world > 1 and rows < halo:
+            raise ValueError(f"{rows} rows per rank < halo {halo}: the seam exchange only reaches the adjacent rank")
         if params.enableJittering:
             raise ValueError("strip sharding recomputes G-buffer halo rows; sub-pixel jitter would double-advance their RNG")
         self.composited = self.backend.new_tensor(width * height * 4)

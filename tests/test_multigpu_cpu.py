@@ -46,7 +46,7 @@ class OracleBackend:
         return torch.empty(numel, dtype=torch.float32)
 
 
-def _worker(rank, world, port, result_path):
+def _worker(rank, world, port, result_path, H=H):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -76,10 +76,11 @@ def _free_port():
     return port
 
 
-def test_two_rank_strips_equal_single_process(tmp_path, oracle):
+@pytest.mark.parametrize("world,H", [(2, 64), (4, 128)])  # 4 ranks: the two middle ranks exchange seams on both sides
+def test_strips_equal_single_process(tmp_path, oracle, world, H):
     from gfxexp_b200 import abi, engine, scenes
     result = str(tmp_path / "composited.npy")
-    mp.spawn(_worker, args=(2, _free_port(), result), nprocs=2, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), result, H), nprocs=world, join=True)
     got = np.load(result)
 
     scene = scenes.tiny_city_scene()
@@ -106,3 +107,6 @@ def test_strip_partition_rejects_ragged_heights():
             return torch.empty(n)
     with pytest.raises(ValueError):
         multigpu.StripDriver(Dummy(), p, 64, 50, 0, 4)
+    p = abi.default_frame_params(scene, 64, 64)
+    with pytest.raises(ValueError):     # 16 rows per rank < 24 halo rows: a seam would have to cross two ranks
+        multigpu.StripDriver(Dummy(), p, 64, 64, 0, 4)
