@@ -56,6 +56,42 @@ GFX_D float remapCdf(const float* __restrict__ cdf, uint32_t numValues, float in
     return (u - lCDF) / (rCDF - lCDF);
 }
 
+// The light-sampling fields of an instance and its normal matrix, as scalar loads or (GFX_WIDE_TABLE_LOADS, scene.cuh) as
+// wide ones; the values are the same either way.
+struct InstanceSampling {
+    uint32_t firstMeshSlot, numMeshSlots;
+    float geomIntegral;
+    uint32_t geomBase;
+};
+GFX_D InstanceSampling loadInstanceSampling(const DevInstance* inst) {
+    InstanceSampling r;
+#if GFX_WIDE_TABLE_LOADS
+    static_assert(offsetof(DevInstance, firstMeshSlot) % 16 == 0, "the sampling fields must start a 16-byte line");
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(&inst->firstMeshSlot));
+    r.firstMeshSlot = q.x;
+    r.numMeshSlots = q.y;
+    r.geomIntegral = __uint_as_float(q.z);
+    r.geomBase = q.w;
+#else
+    r.firstMeshSlot = inst->firstMeshSlot;
+    r.numMeshSlots = inst->numMeshSlots;
+    r.geomIntegral = inst->geomIntegral;
+    r.geomBase = inst->geomBase;
+#endif
+    return r;
+}
+GFX_D f3 applyNormalMatrix(const DevInstance* inst, const f3 &n) {
+#if GFX_WIDE_TABLE_LOADS
+    static_assert(offsetof(DevInstance, normalMatrix) % 16 == 0, "the normal matrix must start a 16-byte line");
+    const float4 a = __ldg(reinterpret_cast<const float4*>(inst->normalMatrix));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(inst->normalMatrix) + 1);
+    const float m[9] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, __ldg(inst->normalMatrix + 8) };
+    return mul3x3(m, n);
+#else
+    return mul3x3(inst->normalMatrix, n);
+#endif
+}
+
 // The three DiscreteDistribution1D::sample calls of sampleLight (instance, geometry instance, primitive) spelled out;
 // weights[idx] / integral comes from the pre-divided prob tables.  Returns false on sampleLight's probability-0 early outs.
 struct LightTrianglePick {
@@ -78,8 +114,15 @@ GFX_D bool pickLightTriangle(const DevScene &s, float ul, LightTrianglePick* pic
         return false;
 
     // geometry instance
+#if GFX_WIDE_TABLE_LOADS
+    const InstanceSampling is = loadInstanceSampling(inst);
+    const uint32_t firstMeshSlot = is.firstMeshSlot, numMeshSlots = is.numMeshSlots;
+    const float geomIntegral = is.geomIntegral;
+    const uint32_t geomBase = is.geomBase;
+#else
     const uint32_t firstMeshSlot = inst->firstMeshSlot, numMeshSlots = inst->numMeshSlots;
     const float geomIntegral = inst->geomIntegral;
+#endif
     u = uGeomInst * geomIntegral;
     const uint32_t geomInstIndexInInst = searchCdf(s.geomCdf + firstMeshSlot, numMeshSlots, u);
     const float uPrim = remapCdf(s.geomCdf + firstMeshSlot, numMeshSlots, geomIntegral, geomInstIndexInInst, u);
@@ -99,7 +142,11 @@ GFX_D bool pickLightTriangle(const DevScene &s, float ul, LightTrianglePick* pic
     lightProb *= primProb;
 
     pick->inst = inst;
+#if GFX_WIDE_TABLE_LOADS
+    pick->lightTri = __ldg(s.lightTriBase + geomBase + geomInstIndexInInst) + primIndex;
+#else
     pick->lightTri = __ldg(s.lightTriBase + inst->geomBase + geomInstIndexInInst) + primIndex;
+#endif
     pick->lightProb = lightProb;
     return true;
 }
@@ -139,7 +186,7 @@ GFX_D void sampleLight(const DevScene &s, float ul, float u0, float u1, LightSam
     lightSample->position = bcA * pA + bcB * pB + bcC * pC;
     lightSample->atInfinity = 0;
     lightSample->normal = bcA * nA + bcB * nB + bcC * nC;
-    lightSample->normal = normalize(mul3x3(pick.inst->normalMatrix, lightSample->normal));
+    lightSample->normal = normalize(applyNormalMatrix(pick.inst, lightSample->normal));
     lightSample->emittance = f3(e5.x, e5.y, e5.z);
 }
 
@@ -182,7 +229,7 @@ GFX_D bool sampleLightUnlessDark(const DevScene &s, float ul, float u0, float u1
     const float4 e3 = __ldg(e + 3), e4 = __ldg(e + 4);
     const f3 nA(e1.w, e2.w, e3.x), nB(e3.y, e3.z, e3.w), nC(e4.x, e4.y, e4.z);
     f3 normal = bcA * nA + bcB * nB + bcC * nC;
-    normal = mul3x3(pick.inst->normalMatrix, normal);
+    normal = applyNormalMatrix(pick.inst, normal);
     const float a = dot(d, normal); // > 0: the emitter faces away from the shading point
     if (density > 0.0f && a > 0.0f && a * a > k * dd * sqLength(normal))
         return true;

@@ -29,16 +29,30 @@ struct DevMesh {
     uint32_t pad[3];
 };
 
+// GFX_WIDE_TABLE_LOADS (compile-time, default 0): the light-sampling chain reads an instance's four sampling fields with one
+// 128-bit load and its normal matrix with 2 x 128 + 1 x 32 bits instead of 4 + 9 scalar loads.  ncu source view of the RIS
+// candidate kernel (profiles/r01_summary.md, r01f): those 13 divergent scalar loads are 502 M of its 1 210 M L1 tag requests
+// and the kernel runs at 80 % of the L1 data-pipe rate.  Written at the end of round 1 without GPU time left to validate
+// it, therefore off; the values loaded are identical, so parity is not at stake once it is switched on and measured.
+#ifndef GFX_WIDE_TABLE_LOADS
+#define GFX_WIDE_TABLE_LOADS 0
+#endif
+
 struct DevInstance {
     float transform[12];
     float curToPrevTransform[12];
     float normalMatrix[9];
     float uniformScale;
+#if GFX_WIDE_TABLE_LOADS
+    uint32_t pad[2];       // the four light-sampling fields below then start a 16-byte line (offset 144): one 128-bit load
+#endif
     uint32_t firstMeshSlot;
     uint32_t numMeshSlots;
     float geomIntegral;    // lightGeomInstDist.integral()
     uint32_t geomBase;     // index of this instance's first flattened geometry (instance order)
+#if !GFX_WIDE_TABLE_LOADS
     uint32_t pad[2];
+#endif
 };
 static_assert(sizeof(DevInstance) % 16 == 0, "DevInstance must stay 16-byte aligned");
 
