@@ -37,6 +37,20 @@ def test_oracle_reproduces_golden(oracle):
     _check(G.run_all(G.OracleBackend(scenes.tiny_city_scene())), digests, arrays)
 
 
+def test_oracle_reproduces_extra_golden(oracle):
+    """output side + instance animation: CPU-only digests, see make_golden_extra.py"""
+    from tests.golden import make_golden_extra as GX
+    want = {}
+    with open(os.path.join(GOLDEN_DIR, "golden_r01_extra.sha256")) as f:
+        for line in f:
+            h, name = line.split()[:2]
+            want[name] = h
+    got = GX.run_all()
+    assert set(got) == set(want)
+    for name, arr in got.items():
+        assert GX.digest(arr) == want[name], f"{name} differs from its golden digest"
+
+
 class _GpuBackend:
     def __init__(self, ctx, scene):
         self.ctx, self.scene = ctx, scene
