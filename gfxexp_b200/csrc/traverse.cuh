@@ -86,6 +86,10 @@ GFX_D void traverseInit(TraversalState &st, const f3 &org, const f3 &dir, float 
 
 // Leaf children whose triangle tests have been postponed (wavefront kernel): the start of the triangle chain and the
 // entry distance of the leaf box.  A node step appends at most 8.
+#ifndef GFX_TRAVERSE_PREDICATED_PUSH
+#define GFX_TRAVERSE_PREDICATED_PUSH 0
+#endif
+
 constexpr int kPendingLeaves = 12;
 struct PendingLeaves {
     uint32_t idx[kPendingLeaves];
@@ -241,6 +245,46 @@ GFX_D bool traverseStep(const DevBvh &bvh, TraversalState &st, PendingLeaves* pe
 
     // ---- internal children: nearest becomes the next node, the others are pushed far -> near
     const uint32_t childBase = n1.x;
+#if GFX_TRAVERSE_PREDICATED_PUSH
+    // Branch-free variant (compile-time, default off: written after the GPU budget of round 1 was spent, so unvalidated).
+    // The loop below compiles to eight separately reconverging blocks around local-memory stores, which hold 41 % of the
+    // trace kernel's stall samples at 8-10 active lanes (profiles/r01_summary.md).  Here every surviving internal child
+    // gets its stack position from a population count - rank = number of farther survivors - and the stores are
+    // predicated; the nearest survivor becomes the next node.  Same survivors, same stack order as the loop.
+    {
+        uint32_t survivors = 0u;
+        uint32_t childNode[8], childT[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t key = keys[k];
+            const uint32_t slot = key & 7u;
+            childT[k] = (key & 0x7FFFFFF8u) << 1; // truncated entry distance (<= true tn)
+            childNode[k] = childBase + __popc(internalMask & ((1u << slot) - 1u));
+            const bool survives = key != 0xFFFFFFFFu && key >= 0x80000000u && !(__uint_as_float(childT[k]) > st.best.dist);
+            survivors |= survives ? (1u << k) : 0u;
+        }
+        if (survivors) {
+            const int nearest = __ffs(survivors) - 1;
+#pragma unroll
+            for (int k = 7; k >= 1; --k) { // position 0 can only be the nearest survivor
+                const uint32_t at = (uint32_t)st.sp + __popc(survivors >> (k + 1));
+                if (((survivors >> k) & 1u) && k != nearest) {
+                    if (at < (uint32_t)kStackSize)
+                        st.stack[at] = make_uint2(childNode[k], childT[k]);
+                    else if (bvh.overflowFlag)
+                        *bvh.overflowFlag = 1u;
+                }
+            }
+            st.sp = min(st.sp + __popc(survivors) - 1, kStackSize);
+            uint32_t next = childNode[0];
+#pragma unroll
+            for (int k = 1; k < 8; ++k)
+                next = k == nearest ? childNode[k] : next;
+            st.nodeIdx = next;
+            return true;
+        }
+    }
+#else
     uint32_t next = 0xFFFFFFFFu, nextT = 0u;
 #pragma unroll
     for (int k = 7; k >= 0; --k) {
@@ -264,6 +308,7 @@ GFX_D bool traverseStep(const DevBvh &bvh, TraversalState &st, PendingLeaves* pe
         st.nodeIdx = next;
         return true;
     }
+#endif
     while (st.sp > 0) {
         const uint2 e = st.stack[--st.sp];
         if (__uint_as_float(e.y) <= st.best.dist) {
