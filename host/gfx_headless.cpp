@@ -12,6 +12,7 @@
 // Output: the accumulated beauty buffer (float4 per pixel, row-major) after <frames> frames, plus one line of JSON
 // with the mean milliseconds per frame (wall clock around a synchronised loop).
 #include "gfxb200.h"
+#include "png_writer.h"
 
 #include <chrono>
 #include <cstdio>
@@ -95,7 +96,7 @@ void loadScene(const char* path, uint32_t width, uint32_t height, SceneFile* s) 
 
 int main(int argc, char** argv) {
     if (argc < 7) {
-        fprintf(stderr, "usage: %s <scene.bin> <renderer> <width> <height> <frames> <out.raw> [nrc_params.f16]\n", argv[0]);
+        fprintf(stderr, "usage: %s <scene.bin> <renderer> <width> <height> <frames> <out.raw | out.png> [nrc_params.f16]\n", argv[0]);
         return 2;
     }
     const std::string renderer = argv[2];
@@ -211,12 +212,25 @@ int main(int argc, char** argv) {
             totalMs += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         }
 
-        std::vector<float> beauty((size_t)width * height * 4);
-        check(gfx, gfx_buffer_download(gfx, nullptr, GFX_BUF_BEAUTY_ACCUM, 0, beauty.data(), beauty.size() * 4), "gfx_buffer_download");
-        FILE* of = fopen(argv[6], "wb");
-        if (!of || fwrite(beauty.data(), 4, beauty.size(), of) != beauty.size())
-            throw std::runtime_error("cannot write the output image");
-        fclose(of);
+        const std::string outPath = argv[6];
+        if (outPath.size() > 4 && outPath.compare(outPath.size() - 4, 4, ".png") == 0) {
+            // the reference's screenshot: tone map + sRGB gamma on the accumulated beauty (saveImage with
+            // SDRImageSaverConfig, common_host.cpp:2859-2897; brightness 0 -> scale 10^0), written as PNG
+            GfxPresentParams pp = { GFX_BUF_BEAUTY_ACCUM, 0, GFX_PRESENT_COLOR, GFX_PRESENT_TONE_MAP | GFX_PRESENT_SRGB_GAMMA, 1.0f, 1.0f };
+            check(gfx, gfx_present_launch(gfx, nullptr, &pp), "gfx_present_launch");
+            std::vector<uint32_t> image((size_t)width * height);
+            check(gfx, gfx_buffer_download(gfx, nullptr, GFX_BUF_PRESENT_RGBA8, 0, image.data(), image.size() * 4), "gfx_buffer_download");
+            if (!gfxhost::writePng(outPath.c_str(), width, height, image.data()))
+                throw std::runtime_error("cannot write the output image");
+        }
+        else {
+            std::vector<float> beauty((size_t)width * height * 4);
+            check(gfx, gfx_buffer_download(gfx, nullptr, GFX_BUF_BEAUTY_ACCUM, 0, beauty.data(), beauty.size() * 4), "gfx_buffer_download");
+            FILE* of = fopen(outPath.c_str(), "wb");
+            if (!of || fwrite(beauty.data(), 4, beauty.size(), of) != beauty.size())
+                throw std::runtime_error("cannot write the output image");
+            fclose(of);
+        }
         printf("{\"renderer\": \"%s\", \"width\": %u, \"height\": %u, \"frames\": %d, \"ms_per_frame\": %.4f, \"kernel_launches\": %llu}\n",
                renderer.c_str(), width, height, frames, totalMs / frames, (unsigned long long)gfx_kernel_launch_count(gfx));
     }
