@@ -64,6 +64,8 @@ void orc_frame_destroy(orc_frame* f);
 void orc_rng_seed(orc_frame* f, uint64_t seed);
 void orc_restir_setup_neighbor_table(orc_frame* f);
 void* orc_buffer_ptr(orc_frame* f, int bufferId, uint32_t index, size_t* bytes);
+/* measurement aid: enable / read-and-reset the candidate statistics of the initial RIS loop (5 counters, see render.cpp) */
+void orc_ris_stats(int enable, unsigned long long* out5);
 /* output side: float4 image -> tone-mapped / sRGB-encoded RGBA8 (present.cpp) */
 void orc_present(const float* srcRGBA, uint32_t width, uint32_t height, const GfxPresentParams* config, uint32_t* image);
 void orc_gbuffer(orc_frame* f, const GfxFrameParams* p, int numThreads);

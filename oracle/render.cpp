@@ -879,6 +879,17 @@ struct ShadingPoint { // the common prologue of the three ReSTIR programs
     BSDF bsdf;
 };
 
+// candidate statistics of the initial RIS loop: [0] zero density, [1] below the shading horizon, [2] light faces away,
+// [3] otherwise exactly zero, [4] contributing
+static bool g_risStatsEnabled = false;
+static unsigned long long g_risStats[5] = { 0, 0, 0, 0, 0 };
+extern "C" void orc_ris_stats(int enable, unsigned long long* out5) {
+    if (out5)
+        for (int i = 0; i < 5; ++i) out5[i] = g_risStats[i];
+    for (int i = 0; i < 5; ++i) g_risStats[i] = 0;
+    g_risStatsEnabled = enable != 0;
+}
+
 template <bool withTemporalRIS, bool useUnbiasedEstimator>
 static void performInitialAndTemporalRIS(orc_frame* f, const GfxFrameParams* p, const Camera &camera, const Camera &prevCamera,
                                          uint32_t x, uint32_t y) { // optix_restir_di_kernels.cu:14-287
@@ -928,6 +939,15 @@ static void performInitialAndTemporalRIS(orc_frame* f, const GfxFrameParams* p, 
         probDensity *= probToSampleCurLightType;
         const float targetDensity = convertToWeight(cont);
         const float weight = targetDensity / probDensity;
+        if (g_risStatsEnabled) { // measurement aid for the CUDA side's staged light fetch; does not touch the results
+            const float3 d = lightSample.position - positionInWorld;
+            const bool belowHorizon = dot(d, shadingNormalInWorld) * vOutLocal.z <= 0.0f;
+            const bool facesAway = dot(d, lightSample.normal) >= 0.0f;
+            const bool dark = cont.x == 0.0f && cont.y == 0.0f && cont.z == 0.0f;
+            const int bucket = !(probDensity > 0.0f) ? 0 : belowHorizon ? 1 : facesAway ? 2 : dark ? 3 : 4;
+#pragma omp atomic
+            g_risStats[bucket] += 1;
+        }
         if (reservoir.update(lightSample, weight, rng.getFloat0cTo1o()))
             selectedTargetDensity = targetDensity;
     }
