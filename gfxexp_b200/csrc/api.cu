@@ -345,7 +345,7 @@ int gfx_scene_upload(gfx_ctx* ctx, const GfxSceneDesc* sd) {
     GFX_CUDA(ctx, cudaMalloc(&S.primProb, (numTris ? numTris : 4) * 4));
     GFX_CUDA(ctx, cudaMalloc(&S.geomProb, (sd->numInstanceMeshSlots ? sd->numInstanceMeshSlots : 4) * 4));
     GFX_CUDA(ctx, cudaMalloc(&S.instProb, (sd->numInstances ? sd->numInstances : 4) * 4));
-    GFX_CUDA(ctx, cudaMalloc(&S.lightTris, (size_t)(numLightTris ? numLightTris : 1) * 96));
+    GFX_CUDA(ctx, cudaMalloc(&S.lightTris, (size_t)(numLightTris ? numLightTris : 1) * 16 * kLightTriStride));
     GFX_CUDA(ctx, upload(&S.lightTriBase, lightTriBase.data(), lightTriBase.size() * 4));
     GFX_CUDA(ctx, upload(&S.emissiveGeoms, emissiveGeoms.data(), emissiveGeoms.size() * 4));
     GFX_CUDA(ctx, cudaMalloc(&S.instGuide, (kInstGuideSize + 1) * 4));

@@ -173,7 +173,7 @@ GFX_D void sampleLight(const DevScene &s, float ul, float u0, float u1, LightSam
         *areaPDensity = 0.0f;
         return;
     }
-    const float4* e = s.lightTris + 6 * (size_t)pick.lightTri;
+    const float4* e = s.lightTris + kLightTriStride * (size_t)pick.lightTri;
     const float4 e0 = __ldg(e + 0), e1 = __ldg(e + 1), e2 = __ldg(e + 2), e3 = __ldg(e + 3), e4 = __ldg(e + 4), e5 = __ldg(e + 5);
     const f3 pA(e0.x, e0.y, e0.z), pB(e1.x, e1.y, e1.z), pC(e2.x, e2.y, e2.z);
     const f3 nA(e1.w, e2.w, e3.x), nB(e3.y, e3.z, e3.w), nC(e4.x, e4.y, e4.z);
@@ -209,7 +209,23 @@ GFX_D bool sampleLightUnlessDark(const DevScene &s, float ul, float u0, float u1
         *areaPDensity = 0.0f;
         return false;
     }
-    const float4* e = s.lightTris + 6 * (size_t)pick.lightTri;
+    const float4* e = s.lightTris + kLightTriStride * (size_t)pick.lightTri;
+#if GFX_LIGHT_CULL_SPHERES
+    {   // step 0: the whole triangle lies below the shading horizon if its bounding sphere does - with twice the margin of the
+        // per-sample test below, so that every sample point of the triangle would pass that test too:
+        //   -dot(q - p, n) sgn >= t - r |n|  and  |q - p| <= |c - p| + r   for every q in the sphere
+        const float4 sphere = __ldg(e + 6);
+        const f3 dc = f3(sphere.x, sphere.y, sphere.z) - shadingPoint;
+        const float r = sphere.w;
+        const float t = -(dot(dc, shadingNormal) * vOutLocalZ);          // > 0: centre on the far side of the surface
+        const float margin = t - 1.001f * r * fabsf(vOutLocalZ);
+        if (r >= 0.0f && pick.lightProb > 0.0f && margin > 0.0f &&
+            margin * margin > 8e-6f * (sqLength(dc) + r * r) * (vOutLocalZ * vOutLocalZ)) {
+            *areaPDensity = pick.lightProb; // any positive number: the caller only asks whether the density is positive
+            return true;
+        }
+    }
+#endif
     const float4 e0 = __ldg(e + 0), e1 = __ldg(e + 1), e2 = __ldg(e + 2);
     const f3 pA(e0.x, e0.y, e0.z), pB(e1.x, e1.y, e1.z), pC(e2.x, e2.y, e2.z);
     float bcA, bcB, bcC;

@@ -138,7 +138,7 @@ __global__ void k_lightTris(DevScene scene, const uint32_t* __restrict__ emissiv
     const DevInstance* inst = scene.instances + im.x;
     const DevMesh mesh = scene.meshes[im.y];
     const GfxMaterialDesc* mat = scene.materials + mesh.materialSlot;
-    float4* out = const_cast<float4*>(scene.lightTris) + 6 * (size_t)scene.lightTriBase[g];
+    float4* out = const_cast<float4*>(scene.lightTris) + kLightTriStride * (size_t)scene.lightTriBase[g];
     for (uint32_t prim = threadIdx.x; prim < mesh.numTriangles; prim += blockDim.x) {
         const uint4 tri = scene.triangles[mesh.triBase + prim];
         const float4* vA = scene.vertices + 3 * (size_t)(mesh.vertexBase + tri.x);
@@ -156,13 +156,21 @@ __global__ void k_lightTris(DevScene scene, const uint32_t* __restrict__ emissiv
             emittance = f3(1.0f, 1.0f, 1.0f);
             emittance *= f3(mat->emittance[0], mat->emittance[1], mat->emittance[2]);
         }
-        float4* o = out + 6 * (size_t)prim;
+        float4* o = out + kLightTriStride * (size_t)prim;
         o[0] = make_float4(pA.x, pA.y, pA.z, recArea);
         o[1] = make_float4(pB.x, pB.y, pB.z, a1.x);
         o[2] = make_float4(pC.x, pC.y, pC.z, a1.y);
         o[3] = make_float4(a1.z, b1.x, b1.y, b1.z);
         o[4] = make_float4(c1.x, c1.y, c1.z, 0.0f);
         o[5] = make_float4(emittance.x, emittance.y, emittance.z, 0.0f);
+#if GFX_LIGHT_CULL_SPHERES
+        {   // bounding sphere of the world-space triangle, slightly inflated; negative radius = never cull (degenerate area)
+            const f3 c = (pA + pB + pC) * (1.0f / 3.0f);
+            const float r2 = fmaxf(fmaxf(sqLength(pA - c), sqLength(pB - c)), sqLength(pC - c));
+            const bool usable = recArea > 0.0f && isfinite(recArea) && isfinite(r2);
+            o[6] = make_float4(c.x, c.y, c.z, usable ? sqrtf(r2) * 1.0001f + 1e-30f : -1.0f);
+        }
+#endif
     }
 }
 

@@ -38,6 +38,16 @@ struct DevMesh {
 #define GFX_WIDE_TABLE_LOADS 0
 #endif
 
+// GFX_LIGHT_CULL_SPHERES (compile-time, default 0): every light-triangle record gets a seventh float4, the bounding sphere of
+// the world-space triangle (centre, radius; radius < 0 = never cull), read first by sampleLightUnlessDark: on config 2 65 % of
+// the RIS candidates lie below the shading horizon (tools/ris_candidate_stats.py) and most of them can be rejected from the
+// sphere alone - one 16-byte fetch instead of three.  Like GFX_WIDE_TABLE_LOADS: written after round 1's GPU minutes were
+// spent, unvalidated, therefore off; the default build's SASS is unchanged.
+#ifndef GFX_LIGHT_CULL_SPHERES
+#define GFX_LIGHT_CULL_SPHERES 0
+#endif
+constexpr uint32_t kLightTriStride = GFX_LIGHT_CULL_SPHERES ? 7u : 6u; // float4 per light triangle
+
 struct DevInstance {
     float transform[12];
     float curToPrevTransform[12];

@@ -2,13 +2,15 @@
 # A/B of the compile-time variants that round 1 left switched off (see profiles/r01_summary.md):
 #   GFX_WIDE_TABLE_LOADS=1         128-bit loads of the instance record in the light-sampling chain
 #   GFX_TRAVERSE_PREDICATED_PUSH=1 branch-free push of the surviving internal children in the traversal
-# Step 1 (here, no GPU):   tools/ab_flags.sh build     -> build_ab/libgfxb200_{wide,push,both}.so
+#   GFX_LIGHT_CULL_SPHERES=1       bounding sphere per light triangle, read before its vertices (RIS candidates)
+# Step 1 (here, no GPU):   tools/ab_flags.sh build     -> build_ab/libgfxb200_{wide,push,spheres,all}.so
 # Step 2 (under gpurun):   tools/ab_flags.sh run       -> parity suite + bench line per variant (GFXB200_LIB selects the library)
 set -u
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
 cd "$ROOT"
 declare -A FLAGS=( [wide]="-DGFX_WIDE_TABLE_LOADS=1" [push]="-DGFX_TRAVERSE_PREDICATED_PUSH=1"
-                   [both]="-DGFX_WIDE_TABLE_LOADS=1 -DGFX_TRAVERSE_PREDICATED_PUSH=1" )
+                   [spheres]="-DGFX_LIGHT_CULL_SPHERES=1 -DGFX_WIDE_TABLE_LOADS=1"
+                   [all]="-DGFX_WIDE_TABLE_LOADS=1 -DGFX_TRAVERSE_PREDICATED_PUSH=1 -DGFX_LIGHT_CULL_SPHERES=1" )
 if [ "${1:-}" = "build" ]; then
     mkdir -p build_ab
     for v in "${!FLAGS[@]}"; do
@@ -20,7 +22,7 @@ if [ "${1:-}" = "build" ]; then
         echo "built build_ab/libgfxb200_$v.so (${FLAGS[$v]})"
     done
 elif [ "${1:-}" = "run" ]; then
-    for lib in gfxexp_b200/libgfxb200.so build_ab/libgfxb200_wide.so build_ab/libgfxb200_push.so build_ab/libgfxb200_both.so; do
+    for lib in gfxexp_b200/libgfxb200.so build_ab/libgfxb200_wide.so build_ab/libgfxb200_push.so build_ab/libgfxb200_spheres.so build_ab/libgfxb200_all.so; do
         [ -f "$lib" ] || continue
         echo "== $lib"
         GFXB200_LIB=$lib timeout -s KILL 300 python -m pytest tests -m gpu -x -q --deselect tests/test_gpu_host_cpp.py 2>&1 | tail -2
