@@ -14,7 +14,8 @@
 // fp32 accumulation inside each dot product (the hardware order of a half-accumulating HMMA is not
 // specified, so the tensor-core kernels are compared at 1e-3 relative L2, not bit-exactly).
 // Parity unpinned by the reference (it has no NRC vectors); pinned by finite-difference gradient
-// checks and loss descent in tests/test_oracle_nrc.py.
+// checks and loss descent in tests/test_oracle_nrc.py.  The encoding half (hash grid, one-blob) has a comparison against the
+// reference's own tiny-cuda-nn kernels prepared in oracle/ref_tcnn + tests/tcnn_ref_check.py; it has not run yet.
 // Parameter layout (this repo's own, shared with the CUDA library): MLP matrices [out][in] in layer
 // order (first 64x64, hidden 64x64 ..., last 16x64), then the hash-grid table level by level.
 #include <cstdint>
