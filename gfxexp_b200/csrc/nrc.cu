@@ -180,18 +180,16 @@ GFX_D void nrcEncode(const NrcLevels &levels, const __half* __restrict__ table, 
 #pragma unroll
     for (uint32_t d = 0; d < 5; ++d) {
         const float x = q[3 + d];
-        float leftCdf[4];
+        // kernel_one_blob_soa (tiny-cuda-nn oneblob.h:110-139; the composite encoding runs its nested encodings on SoA
+        // slices): CDF at the five bin boundaries k / 4, each summed over the three periodic images
+        float leftCdf = quarticCdf(-x, 4.0f) + quarticCdf(-x - 1.0f, 4.0f) + quarticCdf(-x + 1.0f, 4.0f);
 #pragma unroll
-        for (uint32_t b = 0; b < 4; ++b) {
-            const float lb = 0.25f * (float)b; // scalbnf(b, -2)
-            leftCdf[b] = quarticCdf(lb - x, 4.0f) + quarticCdf(lb - x - 1.0f, 4.0f) + quarticCdf(lb - x + 1.0f, 4.0f);
-        }
-#pragma unroll
-        for (uint32_t b = 0; b < 4; ++b) {
-            float rightCdf = leftCdf[(b + 1) & 3];
-            if (b == 3)
-                rightCdf += 1;
-            tail[d * 4 + b] = __float2half(rightCdf - leftCdf[b]);
+        for (uint32_t k = 0; k < 4; ++k) {
+            const float rightBoundary = 0.25f * (float)(k + 1); // scalbnf(k + 1, -2)
+            const float rightCdf = quarticCdf(rightBoundary - x, 4.0f) + quarticCdf(rightBoundary - x - 1.0f, 4.0f) +
+                                   quarticCdf(rightBoundary - x + 1.0f, 4.0f);
+            tail[d * 4 + k] = __float2half(rightCdf - leftCdf);
+            leftCdf = rightCdf;
         }
     }
 #pragma unroll

@@ -5,7 +5,7 @@
 //   Composite encoding       HashGrid(3 dims, 16 levels, F=2, T=2^15, base 16, scale 2)
 //                            + OneBlob(5 dims x 4 bins) + Identity(6 dims), padded 58 -> 64 with ones
 //     kernel_grid<half,3,2>  encodings/grid.h:132-304 ; grid_index/fast_hash :76-111 ; level sizing :885-922
-//     pos_fract              common_device.h:425-431 ; quartic_cdf :478-483 ; one_blob_subwarp_aligned oneblob.h:47-69
+//     pos_fract              common_device.h:425-431 ; quartic_cdf :478-483 ; kernel_one_blob_soa oneblob.h:110-139
 //   FullyFusedMLP            64 neurons, n hidden layers, ReLU, linear output 3 (padded 16)
 //                            src/fully_fused_mlp.cu:47-129 (forward), :150-259,:499-557 (backward)
 //   RelativeL2Luminance      losses/relative_l2_luminance.h:41-88, loss scale 128 (trainer.h:187)
@@ -136,19 +136,21 @@ static void encode(const orc_nrc* n, const half* table, const float* in, half* o
         out[l * 2 + 0] = result[0];
         out[l * 2 + 1] = result[1];
     }
-    // OneBlob, 5 dims x 4 bins (oneblob.h:47-69,83-108): wrap-around quartic CDF differences
+    // OneBlob, 5 dims x 4 bins.  The Composite encoding hands every nested encoding an SoA slice (all three prefer SoA:
+    // composite.h:253-262, grid.h:1257, oneblob.h:299, identity.h:173), so OneBlobEncoding::forward_impl takes its SoA branch
+    // (oneblob.h:219-232) and the kernel is kernel_one_blob_soa (oneblob.h:110-139): the CDF at each of the five bin
+    // boundaries k / 4 is summed over the three periodic images, and a bin is the difference of consecutive boundaries.
+    // (The AoS kernel, :83-108 with one_blob_subwarp_aligned :47-69, closes the last bin with "first boundary + 1" instead,
+    // which differs in the last bit of ~0.3 % of the last-bin features.)
     for (uint32_t d = 0; d < 5; ++d) {
         const float x = in[3 + d];
-        float leftCdf[4];
-        for (uint32_t b = 0; b < 4; ++b) {
-            const float lb = std::scalbn((float)b, -2);
-            leftCdf[b] = quarticCdf(lb - x, 4.0f) + quarticCdf(lb - x - 1.0f, 4.0f) + quarticCdf(lb - x + 1.0f, 4.0f);
-        }
-        for (uint32_t b = 0; b < 4; ++b) {
-            float rightCdf = leftCdf[(b + 1) & 3];
-            if (b == 3)
-                rightCdf += 1;
-            out[32 + d * 4 + b] = f2h(rightCdf - leftCdf[b]);
+        float leftCdf = quarticCdf(-x, 4.0f) + quarticCdf(-x - 1.0f, 4.0f) + quarticCdf(-x + 1.0f, 4.0f);
+        for (uint32_t k = 0; k < 4; ++k) {
+            const float rightBoundary = std::scalbn((float)(k + 1), -2);
+            const float rightCdf = quarticCdf(rightBoundary - x, 4.0f) + quarticCdf(rightBoundary - x - 1.0f, 4.0f) +
+                                   quarticCdf(rightBoundary - x + 1.0f, 4.0f);
+            out[32 + d * 4 + k] = f2h(rightCdf - leftCdf);
+            leftCdf = rightCdf;
         }
     }
     // Identity, 6 dims (identity.h), then padding with ones (oneblob.h:102-104 style "bias-like" pad)

@@ -48,3 +48,38 @@ def test_training_learns_target(oracle):
     assert losses[-1] < 0.25 * losses[0], losses[::8]
     pred = net.infer(q)
     assert np.mean((pred - target) ** 2) < 0.05
+
+
+def test_one_blob_follows_the_soa_kernel(oracle):
+    """The reference's composite encoding runs OneBlob on an SoA slice, i.e. tiny-cuda-nn's kernel_one_blob_soa
+    (oneblob.h:110-139): features 32..51 of the oracle's encoding equal a float32 numpy transcription of that kernel bit for
+    bit (numpy float32 arithmetic is IEEE, one rounding per operation, like the oracle's)."""
+    f = np.float32
+    rng = np.random.default_rng(3)
+    n = 20000
+    q = rng.uniform(0.0, 1.0, size=(n, 14)).astype(f)
+    q[:200, 3:8] = rng.choice(np.array([0.0, 0.25, 0.5, 0.75, 1.0], dtype=f), size=(200, 5))
+    net = oracle.OracleNrc(2, 1e-2)
+    net.set_params(np.zeros(net.num_params, dtype=np.float16))
+    got = net.encode(q).view(np.uint16).reshape(n, 64)[:, 32:52]
+
+    def qc(x):
+        u = (x * f(4.0)).astype(f)
+        u2 = (u * u).astype(f)
+        u4 = (u2 * u2).astype(f)
+        inner = ((f(1.0) - (f(f(2.0) / f(3.0)) * u2).astype(f)).astype(f) + (f(f(1.0) / f(5.0)) * u4).astype(f)).astype(f)
+        v = (((f(f(15.0) / f(16.0)) * u).astype(f) * inner).astype(f) + f(0.5)).astype(f)
+        return np.maximum(f(0.0), np.minimum(f(1.0), v)).astype(f)
+
+    def cdf3(t):
+        return ((qc(t) + qc((t - f(1.0)).astype(f))).astype(f) + qc((t + f(1.0)).astype(f))).astype(f)
+
+    want = np.empty((n, 20), dtype=np.uint16)
+    for d in range(5):
+        x = q[:, 3 + d]
+        left = cdf3((-x).astype(f))
+        for k in range(4):
+            right = cdf3((f(0.25 * (k + 1)) - x).astype(f))
+            want[:, d * 4 + k] = (right - left).astype(f).astype(np.float16).view(np.uint16)
+            left = right
+    assert np.array_equal(got, want), int((got != want).sum())
