@@ -93,6 +93,7 @@ assert NODE_DTYPE.itemsize == 80 and TRI_DTYPE.itemsize == 48 and HIT_DTYPE.item
 # enums
 TRACE_CLOSEST, TRACE_ANY, TRACE_STATS = 0, 1, 2
 PT_BASELINE, PT_NRC, PT_REGIR = 0, 1, 2  # GfxPathTraceVariant
+NRC_READ_MASTER, NRC_READ_TRAINING, NRC_READ_INFERENCE, NRC_READ_GRADIENTS = 0, 1, 2, 3  # gfx_nrc_read
 (RESTIR_INITIAL_RIS, RESTIR_INITIAL_AND_TEMPORAL_BIASED, RESTIR_INITIAL_AND_TEMPORAL_UNBIASED,
  RESTIR_SPATIAL_BIASED, RESTIR_SPATIAL_UNBIASED, RESTIR_SHADING, RESTIR_PRESAMPLE_LIGHTS, RESTIR_PER_PIXEL_RIS,
  RESTIR_TRACE_SHADOW_RAYS, RESTIR_SHADE_AND_RESAMPLE) = range(10)
@@ -322,6 +323,7 @@ _DECLS = {
     "gfx_trace_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, c_u32, C.c_void_p, C.c_int]),
     "gfx_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, c_u32, C.c_void_p, C.c_int]),
     "gfx_light_dist_build": (C.c_int, [C.c_void_p, C.c_void_p, c_u32]),
+    "gfx_light_pick_debug": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, c_u32, C.c_void_p, C.c_void_p]),
     "gfx_light_dist_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(c_f)]),
     "gfx_frame_create": (C.c_int, [C.c_void_p, c_u32, c_u32]),
     "gfx_rng_seed": (C.c_int, [C.c_void_p, C.c_uint64]),
@@ -356,6 +358,9 @@ _DECLS = {
     "gfx_nrc_destroy": (None, [C.c_void_p]),
     "gfx_nrc_infer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_u32]),
     "gfx_nrc_train": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_u32, C.POINTER(c_f)]),
+    "gfx_nrc_reset": (C.c_int, [C.c_void_p, c_u32]),
+    "gfx_nrc_read": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
+    "gfx_nrc_keep_gradients": (C.c_int, [C.c_void_p, C.c_int]),
     "gfx_nrc_get_params": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "gfx_nrc_set_params": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "gfx_nrc_num_params": (c_u32, [C.c_void_p]),

@@ -15,7 +15,11 @@ void SceneState::release() {
     cudaFree(primWeights); cudaFree(primCdf); cudaFree(geomWeights); cudaFree(geomCdf);
     cudaFree(instWeights); cudaFree(instCdf); cudaFree(instIntegral);
     cudaFree(primProb); cudaFree(geomProb); cudaFree(instProb); cudaFree(lightTris); cudaFree(lightTriBase); cudaFree(emissiveGeoms); cudaFree(instGuide); cudaFree(primGuide);
+    cudaFree(pickGuide); cudaFree(pickPieces); cudaFree(pickKeyAt); cudaFree(pickBoundaries); cudaFree(pickCounters); cudaFree(pickSortTemp);
+    if (pickFlagsHost) cudaFreeHost(pickFlagsHost);
+    if (pickFlagsEvent) cudaEventDestroy(pickFlagsEvent);
     for (int i = 0; i < 2; ++i) {
+        cudaFree(pickQueue[i]); cudaFree(pickSortKeys[i]); cudaFree(pickSortVals[i]);
         if (pinnedInstances[i]) cudaFreeHost(pinnedInstances[i]);
         if (pinnedInstancesFree[i]) cudaEventDestroy(pinnedInstancesFree[i]);
     }
@@ -133,6 +137,8 @@ DevScene gfx_ctx::devScene() const {
     d.instProb = scene.instProb;
     d.lightTris = scene.lightTris;
     d.lightTriBase = scene.lightTriBase;
+    d.pickGuide = scene.pickGuide;
+    d.pickPieces = scene.pickPieces;
     d.instGuide = scene.instGuide;
     d.primGuide = scene.primGuide;
     d.numInstances = scene.numInstances;
@@ -351,6 +357,25 @@ int gfx_scene_upload(gfx_ctx* ctx, const GfxSceneDesc* sd) {
     GFX_CUDA(ctx, cudaMalloc(&S.instGuide, (kInstGuideSize + 1) * 4));
     GFX_CUDA(ctx, cudaMemset(S.instGuide, 0, (kInstGuideSize + 1) * 4));
     GFX_CUDA(ctx, cudaMalloc(&S.primGuide, (size_t)(sd->numMeshes ? sd->numMeshes : 1) * (kPrimGuideSize + 1) * 4));
+    // flattened light pick: every reachable (instance, geometry, primitive) position is one piece at most
+    S.pickCapacity = numLightTris + sd->numInstanceMeshSlots + sd->numInstances + 64;
+    GFX_CUDA(ctx, cudaMalloc(&S.pickGuide, (size_t)kPickGuideSize * 4));
+    GFX_CUDA(ctx, cudaMemset(S.pickGuide, 0xC0, (size_t)kPickGuideSize * 4)); // kPickPure | kPickNone until the first build
+    GFX_CUDA(ctx, cudaMalloc(&S.pickPieces, ((size_t)S.pickCapacity + 2) * 8));
+    GFX_CUDA(ctx, cudaMemset(S.pickPieces, 0xFF, ((size_t)S.pickCapacity + 2) * 8));
+    GFX_CUDA(ctx, cudaMalloc(&S.pickKeyAt, ((size_t)kPickGuideSize + 1) * 4));
+    GFX_CUDA(ctx, cudaMalloc(&S.pickBoundaries, (size_t)S.pickCapacity * 8));
+    GFX_CUDA(ctx, cudaMalloc(&S.pickCounters, 16));
+    for (int i = 0; i < 2; ++i) {
+        GFX_CUDA(ctx, cudaMalloc(&S.pickQueue[i], (size_t)S.pickCapacity * 16));
+        GFX_CUDA(ctx, cudaMalloc(&S.pickSortKeys[i], (size_t)S.pickCapacity * 4));
+        GFX_CUDA(ctx, cudaMalloc(&S.pickSortVals[i], (size_t)S.pickCapacity * 4));
+    }
+    S.pickSortTempBytes = lightPickSortTempBytes(S.pickCapacity);
+    GFX_CUDA(ctx, cudaMalloc(&S.pickSortTemp, S.pickSortTempBytes));
+    GFX_CUDA(ctx, cudaMallocHost(&S.pickFlagsHost, 4));
+    *S.pickFlagsHost = 0;
+    GFX_CUDA(ctx, cudaEventCreateWithFlags(&S.pickFlagsEvent, cudaEventDisableTiming));
     S.numEmissiveGeoms = (uint32_t)emissiveGeoms.size();
     S.numLightTris = numLightTris;
     GFX_CUDA(ctx, cudaMemset(S.instIntegral, 0, 16));
@@ -509,6 +534,15 @@ int gfx_light_dist_build(gfx_ctx* ctx, void* stream, uint32_t bufferIndex) {
     if (!ctx->scene.uploaded)
         return GFX_ERR_NOT_READY;
     return buildLightDistributions(ctx, (cudaStream_t)stream, bufferIndex);
+}
+
+int gfx_light_pick_debug(gfx_ctx* ctx, void* stream, const float* ul, uint32_t n, uint32_t* keysFlat, uint32_t* keysChain) {
+    CHECK_CTX(ctx);
+    if (!ctx->scene.uploaded || ctx->scene.pickDirty)
+        return GFX_ERR_NOT_READY;
+    if (!ul || !keysFlat || !keysChain)
+        return GFX_ERR_INVALID_ARGUMENT;
+    return debugLightPick(ctx, (cudaStream_t)stream, ul, n, keysFlat, keysChain);
 }
 
 int gfx_light_dist_export(gfx_ctx* ctx, float* instWeights, float* instCdf, float* integral) {

@@ -38,6 +38,21 @@ struct SceneState {
     bool uploaded = false;
     bool staticLightDistsBuilt = false;
     bool lightTrisDirty = true;
+    // flattened light pick (scene.cuh, lights.cu): tables + the scratch its stream-ordered rebuild needs
+    uint32_t* pickGuide = nullptr;         // kPickGuideSize
+    uint2* pickPieces = nullptr;           // pickCapacity + 2
+    uint32_t* pickKeyAt = nullptr;         // kPickGuideSize + 1
+    uint4* pickQueue[2] = { nullptr, nullptr };
+    uint2* pickBoundaries = nullptr;
+    uint32_t* pickCounters = nullptr;      // 4 words
+    uint32_t* pickSortKeys[2] = { nullptr, nullptr };
+    uint32_t* pickSortVals[2] = { nullptr, nullptr };
+    void* pickSortTemp = nullptr;
+    size_t pickSortTempBytes = 0;
+    uint32_t pickCapacity = 0;
+    uint32_t* pickFlagsHost = nullptr;     // pinned
+    cudaEvent_t pickFlagsEvent = nullptr;
+    bool pickFlagsPending = false, pickBuiltOnce = false, pickDirty = true;
     std::vector<DevMesh> hostMeshes;
     std::vector<DevInstance> hostInstances;
     // pinned staging for gfx_scene_update_instances (per-frame instance animation)
@@ -230,6 +245,8 @@ int traceRays(gfx_ctx* ctx, cudaStream_t stream, const GfxRay* dRays, uint32_t n
 int resetVisibilityQueue(gfx_ctx* ctx, cudaStream_t stream);
 int traceVisibilityQueue(gfx_ctx* ctx, cudaStream_t stream);
 int buildLightDistributions(gfx_ctx* ctx, cudaStream_t stream, uint32_t bufferIndex);
+int debugLightPick(gfx_ctx* ctx, cudaStream_t stream, const float* dUl, uint32_t n, uint32_t* dFlat, uint32_t* dChain);
+size_t lightPickSortTempBytes(uint32_t capacity);
 int launchGBuffer(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* p);
 int launchReSTIR(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* p, int pass);
 int launchReSTIRRearch(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* p, int pass);

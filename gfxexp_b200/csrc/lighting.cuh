@@ -56,50 +56,20 @@ GFX_D float remapCdf(const float* __restrict__ cdf, uint32_t numValues, float in
     return (u - lCDF) / (rCDF - lCDF);
 }
 
-// The light-sampling fields of an instance and its normal matrix, as scalar loads or (GFX_WIDE_TABLE_LOADS, scene.cuh) as
-// wide ones; the values are the same either way.
-struct InstanceSampling {
-    uint32_t firstMeshSlot, numMeshSlots;
-    float geomIntegral;
-    uint32_t geomBase;
-};
-GFX_D InstanceSampling loadInstanceSampling(const DevInstance* inst) {
-    InstanceSampling r;
-#if GFX_WIDE_TABLE_LOADS
-    static_assert(offsetof(DevInstance, firstMeshSlot) % 16 == 0, "the sampling fields must start a 16-byte line");
-    const uint4 q = __ldg(reinterpret_cast<const uint4*>(&inst->firstMeshSlot));
-    r.firstMeshSlot = q.x;
-    r.numMeshSlots = q.y;
-    r.geomIntegral = __uint_as_float(q.z);
-    r.geomBase = q.w;
-#else
-    r.firstMeshSlot = inst->firstMeshSlot;
-    r.numMeshSlots = inst->numMeshSlots;
-    r.geomIntegral = inst->geomIntegral;
-    r.geomBase = inst->geomBase;
-#endif
-    return r;
-}
+// the normal matrix of an instance: two 128-bit loads + one scalar (DevInstance::normalMatrix starts a 16-byte line)
 GFX_D f3 applyNormalMatrix(const DevInstance* inst, const f3 &n) {
-#if GFX_WIDE_TABLE_LOADS
-    static_assert(offsetof(DevInstance, normalMatrix) % 16 == 0, "the normal matrix must start a 16-byte line");
     const float4 a = __ldg(reinterpret_cast<const float4*>(inst->normalMatrix));
     const float4 b = __ldg(reinterpret_cast<const float4*>(inst->normalMatrix) + 1);
     const float m[9] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, __ldg(inst->normalMatrix + 8) };
     return mul3x3(m, n);
-#else
-    return mul3x3(inst->normalMatrix, n);
-#endif
 }
 
-// The three DiscreteDistribution1D::sample calls of sampleLight (instance, geometry instance, primitive) spelled out;
-// weights[idx] / integral comes from the pre-divided prob tables.  Returns false on sampleLight's probability-0 early outs.
-struct LightTrianglePick {
-    const DevInstance* inst;
-    uint32_t lightTri;   // index into the lightTris table (lights.cu)
-    float lightProb;
-};
-GFX_D bool pickLightTriangle(const DevScene &s, float ul, LightTrianglePick* pick) {
+// The three DiscreteDistribution1D::sample calls of sampleLight (instance, geometry instance, primitive;
+// restir_di_shared.h:356-409, common_shared.h:209-246) spelled out; weights[idx] / integral comes from the pre-divided prob
+// tables.  This is the DEFINITION of the light pick; the kernels use its flattened form (pickLightTriangle below), which
+// lights.cu derives from it.  Returns a key: the index of the light record, or kPickNone | position for sampleLight's
+// probability-0 early outs (distinct positions give distinct keys, so that equal keys at two values of ul mean "same piece").
+GFX_D uint32_t chainPickLightTriangle(const DevScene &s, float ul, float* lightProbOut) {
     float lightProb = 1.0f;
 
     // instance
@@ -111,18 +81,11 @@ GFX_D bool pickLightTriangle(const DevScene &s, float ul, LightTrianglePick* pic
     lightProb *= instProb;
     const DevInstance* inst = s.instances + instSlot;
     if (instProb == 0.0f)
-        return false;
+        return kPickNone | 0x20000000u | instSlot;
 
     // geometry instance
-#if GFX_WIDE_TABLE_LOADS
-    const InstanceSampling is = loadInstanceSampling(inst);
-    const uint32_t firstMeshSlot = is.firstMeshSlot, numMeshSlots = is.numMeshSlots;
-    const float geomIntegral = is.geomIntegral;
-    const uint32_t geomBase = is.geomBase;
-#else
     const uint32_t firstMeshSlot = inst->firstMeshSlot, numMeshSlots = inst->numMeshSlots;
     const float geomIntegral = inst->geomIntegral;
-#endif
     u = uGeomInst * geomIntegral;
     const uint32_t geomInstIndexInInst = searchCdf(s.geomCdf + firstMeshSlot, numMeshSlots, u);
     const float uPrim = remapCdf(s.geomCdf + firstMeshSlot, numMeshSlots, geomIntegral, geomInstIndexInInst, u);
@@ -130,7 +93,7 @@ GFX_D bool pickLightTriangle(const DevScene &s, float ul, LightTrianglePick* pic
     const uint32_t geomInstSlot = __ldg(s.instanceMeshSlots + firstMeshSlot + geomInstIndexInInst);
     lightProb *= geomInstProb;
     if (geomInstProb == 0.0f)
-        return false;
+        return kPickNone | (firstMeshSlot + geomInstIndexInInst);
 
     // primitive
     const DevMesh* mesh = s.meshes + geomInstSlot;
@@ -141,14 +104,27 @@ GFX_D bool pickLightTriangle(const DevScene &s, float ul, LightTrianglePick* pic
     const float primProb = __ldg(s.primProb + triBase + primIndex);
     lightProb *= primProb;
 
-    pick->inst = inst;
-#if GFX_WIDE_TABLE_LOADS
-    pick->lightTri = __ldg(s.lightTriBase + geomBase + geomInstIndexInInst) + primIndex;
-#else
-    pick->lightTri = __ldg(s.lightTriBase + inst->geomBase + geomInstIndexInInst) + primIndex;
-#endif
-    pick->lightProb = lightProb;
-    return true;
+    *lightProbOut = lightProb;
+    return __ldg(s.lightTriBase + inst->geomBase + geomInstIndexInInst) + primIndex;
+}
+
+// The flattened pick (scene.cuh, lights.cu): key of the piece that contains ul.
+GFX_D uint32_t pickLightTriangle(const DevScene &s, float ul) {
+    const uint32_t b = min(dm_f2uint(ul * (float)kPickGuideSize), kPickGuideSize - 1); // exact: a power-of-two product, floored
+    const uint32_t g = __ldg(s.pickGuide + b);
+    if (g & kPickPure)
+        return g & ~kPickPure;
+    const uint32_t ulBits = __float_as_uint(ul);
+    uint32_t idx = g;
+    uint2 piece = __ldg(s.pickPieces + idx);
+    for (;;) {
+        const uint2 next = __ldg(s.pickPieces + idx + 1);
+        if (next.x > ulBits)
+            break;
+        piece = next;
+        ++idx;
+    }
+    return piece.y;
 }
 
 // A Low-Distortion Map Between Triangle and Square (restir_di_shared.h:485-498)
@@ -167,71 +143,70 @@ GFX_D void squareToTriangle(float u0, float u1, float* bcA, float* bcB, float* b
 
 GFX_D void sampleLight(const DevScene &s, float ul, float u0, float u1, LightSample* lightSample, float* areaPDensity) {
     // restir_di_shared.h:320-516 with sampleEnvLight = false, useSolidAngleSampling = false; the triangle operands come
-    // from the lightTris table (lights.cu), produced by the reference's own expressions, so the result is bit-identical.
-    LightTrianglePick pick;
-    if (!pickLightTriangle(s, ul, &pick)) {
+    // from the light records (lights.cu), produced by the reference's own expressions, so the result is bit-identical.
+    const uint32_t key = pickLightTriangle(s, ul);
+    if (key & kPickNone) {
         *areaPDensity = 0.0f;
         return;
     }
-    const float4* e = s.lightTris + kLightTriStride * (size_t)pick.lightTri;
-    const float4 e0 = __ldg(e + 0), e1 = __ldg(e + 1), e2 = __ldg(e + 2), e3 = __ldg(e + 3), e4 = __ldg(e + 4), e5 = __ldg(e + 5);
-    const f3 pA(e0.x, e0.y, e0.z), pB(e1.x, e1.y, e1.z), pC(e2.x, e2.y, e2.z);
-    const f3 nA(e1.w, e2.w, e3.x), nB(e3.y, e3.z, e3.w), nC(e4.x, e4.y, e4.z);
+    const float4* e = s.lightTris + kLightTriStride * (size_t)key;
+    const float4 e1 = __ldg(e + 1), e2 = __ldg(e + 2), e3 = __ldg(e + 3), e4 = __ldg(e + 4), e5 = __ldg(e + 5), e6 = __ldg(e + 6);
+    const f3 pA(e1.x, e1.y, e1.z), pB(e2.x, e2.y, e2.z), pC(e3.x, e3.y, e3.z);
+    const f3 nA(e4.x, e4.y, e4.z), nB(e4.w, e5.x, e5.y), nC(e5.z, e5.w, e6.x);
     float bcA, bcB, bcC;
     squareToTriangle(u0, u1, &bcA, &bcB, &bcC);
 
-    const float recArea = e0.w;
-    *areaPDensity = pick.lightProb * recArea;
+    const float recArea = e1.w;
+    *areaPDensity = e2.w * recArea;
 
     lightSample->position = bcA * pA + bcB * pB + bcC * pC;
     lightSample->atInfinity = 0;
     lightSample->normal = bcA * nA + bcB * nB + bcC * nC;
-    lightSample->normal = normalize(applyNormalMatrix(pick.inst, lightSample->normal));
-    lightSample->emittance = f3(e5.x, e5.y, e5.z);
+    lightSample->normal = normalize(applyNormalMatrix(s.instances + __float_as_uint(e3.w), lightSample->normal));
+    lightSample->emittance = f3(e6.y, e6.z, e6.w);
 }
 
-// sampleLight for the RIS candidate loop, fetching the 96-byte light triangle in three steps and stopping as soon as
-// the candidate is certain to contribute RGB(0) to this shading point.  ncu: the candidate kernel runs the L1 data pipe
-// at 84 % of its wavefront rate (535 M wavefronts for 77 M load instructions - every lane reads a different light), and
-// the six 16-byte fetches of the light triangle are three quarters of them; ~70 % of the candidates are dark.
+// sampleLight for the RIS candidate loop, fetching the 128-byte light record in three steps and stopping as soon as
+// the candidate is certain to contribute RGB(0) to this shading point.  ncu (round 1): the candidate kernel ran the L1 data
+// pipe at 80-84 % of its wavefront rate - every lane reads a different light, so every load instruction of the sampling chain
+// is up to 32 wavefronts - and ~70 % of the candidates are dark (65 % lie below the shading horizon).
+//   step 0: the bounding sphere of the light triangle (16 bytes).  Wholly below the shading horizon -> dark;
 //   step 1: the three vertices -> sample position.  Below the shading horizon (the BRDFs return RGB(0) when
-//           vGiven.z * vSampled.z <= 0)?  -> dark, 3 fetches and the instance's normal matrix saved;
-//   step 2: the vertex normals -> un-normalised light normal.  Facing away (lpCos <= 0)? -> dark, 1 fetch saved;
-//   step 3: the emittance, the normalisation: the full sample.
-// Both tests run on un-normalised vectors with a relative margin of 1e-3 on the cosine - three orders of magnitude above
-// the rounding of the exact evaluation - so borderline samples go on to the exact path and no decision ever differs from
-// performDirectLighting's; NaNs and a zero distance fail the comparisons and also go on.  Returns true for "dark" (then
-// *areaPDensity is the sample's density and is positive); otherwise the outputs are sampleLight's, bit for bit.
+//           vGiven.z * vSampled.z <= 0)?  -> dark;
+//   step 2: the vertex normals and the instance's normal matrix -> un-normalised light normal.  Facing away (lpCos <= 0)?
+//           -> dark; otherwise the emittance, the normalisation: the full sample.
+// The tests run on un-normalised vectors with a relative margin of 1e-3 on the cosine (the sphere test with twice that, so
+// that every sample point of the triangle would pass the per-sample test too; tests/cpp/sphere_cull_check.cpp) - three orders
+// of magnitude above the rounding of the exact evaluation - so borderline samples go on to the exact path and no decision ever
+// differs from performDirectLighting's; NaNs and a zero distance fail the comparisons and also go on.  Returns true for "dark"
+// (then *areaPDensity is positive); otherwise the outputs are sampleLight's, bit for bit.
 GFX_D bool sampleLightUnlessDark(const DevScene &s, float ul, float u0, float u1, const f3 &shadingPoint,
                                  const f3 &shadingNormal, float vOutLocalZ, LightSample* lightSample, float* areaPDensity) {
-    LightTrianglePick pick;
-    if (!pickLightTriangle(s, ul, &pick)) {
+    const uint32_t key = pickLightTriangle(s, ul);
+    if (key & kPickNone) {
         *areaPDensity = 0.0f;
         return false;
     }
-    const float4* e = s.lightTris + kLightTriStride * (size_t)pick.lightTri;
-#if GFX_LIGHT_CULL_SPHERES
-    {   // step 0: the whole triangle lies below the shading horizon if its bounding sphere does - with twice the margin of the
-        // per-sample test below, so that every sample point of the triangle would pass that test too:
+    const float4* e = s.lightTris + kLightTriStride * (size_t)key;
+    {   // step 0: the whole triangle lies below the shading horizon if its bounding sphere does:
         //   -dot(q - p, n) sgn >= t - r |n|  and  |q - p| <= |c - p| + r   for every q in the sphere
-        const float4 sphere = __ldg(e + 6);
+        // (radius >= 0 also says that the selection density of this light is a positive finite number)
+        const float4 sphere = __ldg(e + 0);
         const f3 dc = f3(sphere.x, sphere.y, sphere.z) - shadingPoint;
         const float r = sphere.w;
         const float t = -(dot(dc, shadingNormal) * vOutLocalZ);          // > 0: centre on the far side of the surface
         const float margin = t - 1.001f * r * fabsf(vOutLocalZ);
-        if (r >= 0.0f && pick.lightProb > 0.0f && margin > 0.0f &&
-            margin * margin > 8e-6f * (sqLength(dc) + r * r) * (vOutLocalZ * vOutLocalZ)) {
-            *areaPDensity = pick.lightProb; // any positive number: the caller only asks whether the density is positive
+        if (r >= 0.0f && margin > 0.0f && margin * margin > 8e-6f * (sqLength(dc) + r * r) * (vOutLocalZ * vOutLocalZ)) {
+            *areaPDensity = 1.0f; // any positive number: the caller only asks whether the density is positive
             return true;
         }
     }
-#endif
-    const float4 e0 = __ldg(e + 0), e1 = __ldg(e + 1), e2 = __ldg(e + 2);
-    const f3 pA(e0.x, e0.y, e0.z), pB(e1.x, e1.y, e1.z), pC(e2.x, e2.y, e2.z);
+    const float4 e1 = __ldg(e + 1), e2 = __ldg(e + 2), e3 = __ldg(e + 3);
+    const f3 pA(e1.x, e1.y, e1.z), pB(e2.x, e2.y, e2.z), pC(e3.x, e3.y, e3.z);
     float bcA, bcB, bcC;
     squareToTriangle(u0, u1, &bcA, &bcB, &bcC);
-    const float recArea = e0.w;
-    const float density = pick.lightProb * recArea;
+    const float recArea = e1.w;
+    const float density = e2.w * recArea;
     *areaPDensity = density;
     const f3 position = bcA * pA + bcB * pB + bcC * pC;
 
@@ -242,19 +217,20 @@ GFX_D bool sampleLightUnlessDark(const DevScene &s, float ul, float u0, float u1
     if (density > 0.0f && b < 0.0f && b * b > k * dd * (vOutLocalZ * vOutLocalZ))
         return true;
 
-    const float4 e3 = __ldg(e + 3), e4 = __ldg(e + 4);
-    const f3 nA(e1.w, e2.w, e3.x), nB(e3.y, e3.z, e3.w), nC(e4.x, e4.y, e4.z);
+    const float4 e4 = __ldg(e + 4), e5 = __ldg(e + 5);
+    const f3 nA(e4.x, e4.y, e4.z), nB(e4.w, e5.x, e5.y);
+    const float4 e6 = __ldg(e + 6);
+    const f3 nC(e5.z, e5.w, e6.x);
     f3 normal = bcA * nA + bcB * nB + bcC * nC;
-    normal = applyNormalMatrix(pick.inst, normal);
+    normal = applyNormalMatrix(s.instances + __float_as_uint(e3.w), normal);
     const float a = dot(d, normal); // > 0: the emitter faces away from the shading point
     if (density > 0.0f && a > 0.0f && a * a > k * dd * sqLength(normal))
         return true;
 
-    const float4 e5 = __ldg(e + 5);
     lightSample->position = position;
     lightSample->atInfinity = 0;
     lightSample->normal = normalize(normal);
-    lightSample->emittance = f3(e5.x, e5.y, e5.z);
+    lightSample->emittance = f3(e6.y, e6.z, e6.w);
     return false;
 }
 

@@ -19,8 +19,9 @@
 //    (inst.transform * v.position), recArea = 2 / |cross|, the object-space vertex normals and the
 //    material emittance, i.e. the operands sampleLight (restir_di_shared.h:417-425,485-511) would
 //    recompute for each of the 66 M candidates per frame.
-#include "scene.cuh"
+#include "lighting.cuh"
 #include "context.h"
+#include <cub/device/device_radix_sort.cuh>
 
 namespace gfx {
 
@@ -157,21 +158,165 @@ __global__ void k_lightTris(DevScene scene, const uint32_t* __restrict__ emissiv
             emittance *= f3(mat->emittance[0], mat->emittance[1], mat->emittance[2]);
         }
         float4* o = out + kLightTriStride * (size_t)prim;
-        o[0] = make_float4(pA.x, pA.y, pA.z, recArea);
-        o[1] = make_float4(pB.x, pB.y, pB.z, a1.x);
-        o[2] = make_float4(pC.x, pC.y, pC.z, a1.y);
-        o[3] = make_float4(a1.z, b1.x, b1.y, b1.z);
-        o[4] = make_float4(c1.x, c1.y, c1.z, 0.0f);
-        o[5] = make_float4(emittance.x, emittance.y, emittance.z, 0.0f);
-#if GFX_LIGHT_CULL_SPHERES
-        {   // bounding sphere of the world-space triangle, slightly inflated; negative radius = never cull (degenerate area)
-            const f3 c = (pA + pB + pC) * (1.0f / 3.0f);
-            const float r2 = fmaxf(fmaxf(sqLength(pA - c), sqLength(pB - c)), sqLength(pC - c));
-            const bool usable = recArea > 0.0f && isfinite(recArea) && isfinite(r2);
-            o[6] = make_float4(c.x, c.y, c.z, usable ? sqrtf(r2) * 1.0001f + 1e-30f : -1.0f);
-        }
-#endif
+        // bounding sphere of the world-space triangle, slightly inflated; negative radius = never cull (degenerate area)
+        const f3 c = (pA + pB + pC) * (1.0f / 3.0f);
+        const float r2 = fmaxf(fmaxf(sqLength(pA - c), sqLength(pB - c)), sqLength(pC - c));
+        const bool usable = recArea > 0.0f && isfinite(recArea) && isfinite(r2);
+        const float radius = usable ? sqrtf(r2) * 1.0001f + 1e-30f : -1.0f;
+        o[0] = make_float4(c.x, c.y, c.z, -1.0f);   // k_pickLightProbs switches the cull on once the density is known
+        o[1] = make_float4(pA.x, pA.y, pA.z, recArea);
+        o[2] = make_float4(pB.x, pB.y, pB.z, 0.0f); // lightProb: k_pickLightProbs
+        o[3] = make_float4(pC.x, pC.y, pC.z, __uint_as_float(im.x));
+        o[4] = make_float4(a1.x, a1.y, a1.z, b1.x);
+        o[5] = make_float4(b1.y, b1.z, c1.x, c1.y);
+        o[6] = make_float4(c1.z, emittance.x, emittance.y, emittance.z);
+        o[7] = make_float4(radius, 0.0f, 0.0f, 0.0f);
     }
+}
+
+// ---- flattened light pick (scene.cuh) -------------------------------------------------------------------------------------
+// Every float ul in [0, 1) is a bit pattern in [0, kPickMaxUlBits]; positive floats order like their bit patterns.  The chain
+// (chainPickLightTriangle) is monotone in ul - u = ul * integral, the CDF search and the remap (u - l) / (r - l) are each
+// monotone, so the (instance, geometry, primitive) triple grows lexicographically - hence equal keys at two bit patterns
+// mean one key in between, and all boundaries are found by refining only the intervals whose end keys differ.
+
+GFX_D uint32_t pickBucketStart(uint32_t j) { // bit pattern of j / kPickGuideSize; the end of the domain for j = kPickGuideSize
+    return j < kPickGuideSize ? __float_as_uint((float)j * (1.0f / (float)kPickGuideSize)) : kPickMaxUlBits;
+}
+GFX_D uint32_t chainKey(const DevScene &s, uint32_t ulBits) {
+    float unusedProb;
+    return chainPickLightTriangle(s, __uint_as_float(ulBits), &unusedProb);
+}
+
+__global__ void k_pickBucketKeys(DevScene scene, uint32_t* __restrict__ keyAt) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j <= kPickGuideSize)
+        keyAt[j] = chainKey(scene, pickBucketStart(j));
+}
+
+struct PickWork {
+    uint4* queue[2];        // (a, b, key(a), key(b)): key changes somewhere in (a, b]
+    uint32_t* counters;     // [0], [1] queue lengths, [2] number of boundaries, [3] error flags
+    uint2* boundaries;      // (first bit pattern of a piece, key), unsorted
+    uint32_t capacity;
+};
+GFX_D void pickEmitBoundary(const PickWork &w, uint32_t x, uint32_t key) {
+    const uint32_t at = atomicAdd(w.counters + 2, 1u);
+    if (at < w.capacity)
+        w.boundaries[at] = make_uint2(x, key);
+    else
+        atomicOr(w.counters + 3, 1u);
+}
+GFX_D void pickPushInterval(const PickWork &w, int q, uint32_t a, uint32_t b, uint32_t ka, uint32_t kb) {
+    const uint32_t at = atomicAdd(w.counters + q, 1u);
+    if (at < w.capacity)
+        w.queue[q][at] = make_uint4(a, b, ka, kb);
+    else
+        atomicOr(w.counters + 3, 1u);
+}
+
+__global__ void k_pickSeed(const uint32_t* __restrict__ keyAt, PickWork w) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= kPickGuideSize)
+        return;
+    if (j == 0)
+        pickEmitBoundary(w, 0u, keyAt[0]);
+    const uint32_t ka = keyAt[j], kb = keyAt[j + 1];
+    if (ka != kb)
+        pickPushInterval(w, 0, pickBucketStart(j), pickBucketStart(j + 1), ka, kb);
+}
+
+// one warp per interval (a, b]: 32 sub-intervals, the chain evaluated at their upper ends; intervals of at most 32 floats are
+// resolved float by float
+__global__ void __launch_bounds__(256) k_pickRefine(DevScene scene, PickWork w, int qin) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warpsPerGrid = gridDim.x * (blockDim.x >> 5);
+    const uint32_t numItems = min(w.counters[qin], w.capacity);
+    for (uint32_t item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); item < numItems; item += warpsPerGrid) {
+        const uint4 it = w.queue[qin][item];
+        const uint32_t a = it.x, n = it.y - it.x;
+        uint32_t lo, hi;
+        if (n <= 32) {
+            lo = a + min(lane, n);
+            hi = a + min(lane + 1, n);
+        }
+        else { // every sub-interval holds at least one float
+            lo = a + (uint32_t)(((uint64_t)n * lane) >> 5);
+            hi = a + (uint32_t)(((uint64_t)n * (lane + 1)) >> 5);
+        }
+        const bool live = hi > lo;
+        const uint32_t khi = hi == it.y ? it.w : (live ? chainKey(scene, hi) : it.w);
+        uint32_t klo = __shfl_up_sync(0xFFFFFFFFu, khi, 1); // live sub-intervals are contiguous from lane 0
+        if (lane == 0)
+            klo = it.z;
+        if (live && khi != klo) {
+            if (hi == lo + 1)
+                pickEmitBoundary(w, hi, khi);
+            else
+                pickPushInterval(w, qin ^ 1, lo, hi, klo, khi);
+        }
+    }
+}
+
+__global__ void k_pickResetQueue(PickWork w, int q, int last) {
+    if (last && w.counters[q ^ 1] != 0)
+        atomicOr(w.counters + 3, 2u); // intervals left after the last level
+    w.counters[q] = 0;
+}
+
+// guide entry of bucket j from the sorted pieces
+__global__ void k_pickGuide(const uint2* __restrict__ pieces, const uint32_t* __restrict__ counters, uint32_t capacity,
+                            uint32_t* __restrict__ guide) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= kPickGuideSize)
+        return;
+    const uint32_t numPieces = min(counters[2], capacity);
+    const uint32_t first = pickBucketStart(j);
+    const uint32_t last = j + 1 < kPickGuideSize ? pickBucketStart(j + 1) - 1 : kPickMaxUlBits;
+    uint32_t lo = 0, hi = numPieces; // last piece with start <= first (piece 0 starts at 0)
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (pieces[mid].x <= first)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    const bool pure = lo + 1 >= numPieces || pieces[lo + 1].x > last;
+    guide[j] = pure ? (kPickPure | pieces[lo].y) : lo;
+}
+
+// selection probability of every reachable light (the chain's own product, taken at the first float of its piece) and the
+// switch of its bounding-sphere cull
+__global__ void k_pickLightProbs(DevScene scene, const uint2* __restrict__ pieces, const uint32_t* __restrict__ counters,
+                                 uint32_t capacity) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= min(counters[2], capacity))
+        return;
+    const uint2 piece = pieces[i];
+    if (piece.y & kPickNone)
+        return;
+    float lightProb = 0.0f;
+    const uint32_t key = chainPickLightTriangle(scene, __uint_as_float(piece.x), &lightProb);
+    if (key != piece.y) { // cannot happen: the piece start was produced by this very evaluation
+        atomicOr(const_cast<uint32_t*>(counters) + 3, 4u);
+        return;
+    }
+    float4* rec = const_cast<float4*>(scene.lightTris) + kLightTriStride * (size_t)key;
+    const float recArea = rec[1].w;
+    const float density = lightProb * recArea;
+    rec[2].w = lightProb;
+    rec[0].w = (density > 0.0f && isfinite(density)) ? rec[7].x : -1.0f;
+}
+
+// debug / test entry: flattened and chain pick of arbitrary ul values side by side
+__global__ void k_pickDebug(DevScene scene, const float* __restrict__ ul, uint32_t n, uint32_t* __restrict__ flat,
+                            uint32_t* __restrict__ chain) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    float unusedProb;
+    flat[i] = pickLightTriangle(scene, ul[i]);
+    chain[i] = chainPickLightTriangle(scene, ul[i], &unusedProb);
 }
 
 // per frame: computeInstImportance (compute_light_probs.cu:115-129) + exclusive scan + finalize +
@@ -210,6 +355,8 @@ __global__ void __launch_bounds__(1024) k_instanceDist(DevScene scene, uint32_t 
     }
 }
 
+int buildLightPick(gfx_ctx* ctx, cudaStream_t stream);
+
 int buildLightDistributions(gfx_ctx* ctx, cudaStream_t stream, uint32_t /*bufferIndex*/) {
     SceneState &S = ctx->scene;
     const DevScene dev = ctx->devScene();
@@ -226,6 +373,8 @@ int buildLightDistributions(gfx_ctx* ctx, cudaStream_t stream, uint32_t /*buffer
         S.staticLightDistsBuilt = true;
         S.lightTrisDirty = true;
     }
+    if (S.lightTrisDirty)
+        S.pickDirty = true; // the records are rewritten (and the instance importances may have changed)
     if (S.lightTrisDirty && S.numEmissiveGeoms) {
         // world-space light triangles follow the instance transforms (gfx_scene_update_instances marks them dirty)
         k_lightTris<<<S.numEmissiveGeoms, 128, 0, stream>>>(dev, S.emissiveGeoms, S.numEmissiveGeoms); ctx->launches++;
@@ -241,6 +390,82 @@ int buildLightDistributions(gfx_ctx* ctx, cudaStream_t stream, uint32_t /*buffer
             GFX_CUDA(ctx, cudaFuncSetAttribute(k_instanceDist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_instanceDist<<<1, 1024, smem, stream>>>(dev, S.numInstances); ctx->launches++;
     }
+    if (S.pickDirty && S.numInstances) {
+        const int rc = buildLightPick(ctx, stream);
+        if (rc != GFX_OK)
+            return rc;
+    }
+    GFX_CUDA(ctx, cudaGetLastError());
+    return GFX_OK;
+}
+
+// Rebuilds the flattened light pick from the distributions just built (stream-ordered; see the notes above k_pickBucketKeys).
+int buildLightPick(gfx_ctx* ctx, cudaStream_t stream) {
+    SceneState &S = ctx->scene;
+    const DevScene dev = ctx->devScene();
+    if (S.pickFlagsPending) { // error flags of the previous (asynchronously checked) rebuild
+        GFX_CUDA(ctx, cudaEventSynchronize(S.pickFlagsEvent));
+        S.pickFlagsPending = false;
+        if (*S.pickFlagsHost) {
+            ctx->setError("gfx_light_dist_build: the flattened light pick overflowed its tables (flags " + std::to_string(*S.pickFlagsHost) + ")");
+            return GFX_ERR_UNSUPPORTED;
+        }
+    }
+    PickWork w;
+    w.queue[0] = S.pickQueue[0];
+    w.queue[1] = S.pickQueue[1];
+    w.counters = S.pickCounters;
+    w.boundaries = S.pickBoundaries;
+    w.capacity = S.pickCapacity;
+    GFX_CUDA(ctx, cudaMemsetAsync(S.pickCounters, 0, 16, stream));
+    GFX_CUDA(ctx, cudaMemsetAsync(S.pickBoundaries, 0xFF, (size_t)S.pickCapacity * 8, stream));
+    k_pickBucketKeys<<<(kPickGuideSize + 256) / 256, 256, 0, stream>>>(dev, S.pickKeyAt); ctx->launches++;
+    k_pickSeed<<<kPickGuideSize / 256, 256, 0, stream>>>(S.pickKeyAt, w); ctx->launches++;
+    // an interval holds at most 2^30 floats (bucket 0: all floats below 2^-17) and shrinks 32-fold per level
+    const int numLevels = 8;
+    for (int level = 0; level < numLevels; ++level) {
+        const int qin = level & 1;
+        k_pickRefine<<<296, 256, 0, stream>>>(dev, w, qin); ctx->launches++;
+        k_pickResetQueue<<<1, 1, 0, stream>>>(w, qin, level == numLevels - 1); ctx->launches++;
+    }
+    // pieces = boundaries sorted by their first bit pattern; the unused tail (0xFFFFFFFF starts) terminates the scans
+    GFX_CUDA(ctx, cudaMemcpy2DAsync(S.pickSortKeys[0], 4, &S.pickBoundaries[0].x, 8, 4, S.pickCapacity, cudaMemcpyDeviceToDevice, stream));
+    GFX_CUDA(ctx, cudaMemcpy2DAsync(S.pickSortVals[0], 4, &S.pickBoundaries[0].y, 8, 4, S.pickCapacity, cudaMemcpyDeviceToDevice, stream));
+    size_t tempBytes = S.pickSortTempBytes;
+    GFX_CUDA(ctx, cub::DeviceRadixSort::SortPairs(S.pickSortTemp, tempBytes, S.pickSortKeys[0], S.pickSortKeys[1], S.pickSortVals[0],
+                                                  S.pickSortVals[1], (int)S.pickCapacity, 0, 32, stream));
+    ctx->launches += 3;
+    GFX_CUDA(ctx, cudaMemcpy2DAsync(&S.pickPieces[0].x, 8, S.pickSortKeys[1], 4, 4, S.pickCapacity, cudaMemcpyDeviceToDevice, stream));
+    GFX_CUDA(ctx, cudaMemcpy2DAsync(&S.pickPieces[0].y, 8, S.pickSortVals[1], 4, 4, S.pickCapacity, cudaMemcpyDeviceToDevice, stream));
+    k_pickGuide<<<kPickGuideSize / 256, 256, 0, stream>>>(S.pickPieces, S.pickCounters, S.pickCapacity, S.pickGuide); ctx->launches++;
+    k_pickLightProbs<<<(S.pickCapacity + 255) / 256, 256, 0, stream>>>(dev, S.pickPieces, S.pickCounters, S.pickCapacity); ctx->launches++;
+    GFX_CUDA(ctx, cudaMemcpyAsync(S.pickFlagsHost, S.pickCounters + 3, 4, cudaMemcpyDeviceToHost, stream));
+    GFX_CUDA(ctx, cudaEventRecord(S.pickFlagsEvent, stream));
+    S.pickFlagsPending = true;
+    if (!S.pickBuiltOnce) { // the first build is checked at once (scene set-up is not on the per-frame path)
+        GFX_CUDA(ctx, cudaEventSynchronize(S.pickFlagsEvent));
+        S.pickFlagsPending = false;
+        if (*S.pickFlagsHost) {
+            ctx->setError("gfx_light_dist_build: the flattened light pick overflowed its tables (flags " + std::to_string(*S.pickFlagsHost) + ")");
+            return GFX_ERR_UNSUPPORTED;
+        }
+        S.pickBuiltOnce = true;
+    }
+    S.pickDirty = false;
+    return GFX_OK;
+}
+
+size_t lightPickSortTempBytes(uint32_t capacity) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
+                                    (uint32_t*)nullptr, (int)capacity, 0, 32, (cudaStream_t)0);
+    return bytes ? bytes : 16;
+}
+
+int debugLightPick(gfx_ctx* ctx, cudaStream_t stream, const float* dUl, uint32_t n, uint32_t* dFlat, uint32_t* dChain) {
+    if (n)
+        k_pickDebug<<<(n + 255) / 256, 256, 0, stream>>>(ctx->devScene(), dUl, n, dFlat, dChain);
+    ctx->launches++;
     GFX_CUDA(ctx, cudaGetLastError());
     return GFX_OK;
 }

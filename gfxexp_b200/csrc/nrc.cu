@@ -19,6 +19,9 @@
 // samples, weights and activations in shared memory, dW reduced per block then atomically added.
 #include "context.h"
 #include <cuda_fp16.h>
+#include <random>
+#include <vector>
+#include <cmath>
 
 namespace gfx {
 
@@ -54,6 +57,8 @@ struct gfx_nrc {
     uint4* ummaWeights = nullptr; // EMA MLP weights in the tcgen05 shared-memory layout
     uint4* trainBlobFwd = nullptr; // training weights, tcgen05 layouts: W_l [N x 64] and W_l^T [64 x K] K-major blobs
     uint4* trainBlobT = nullptr;
+    float* gradsFloat = nullptr;   // gfx_nrc_keep_gradients: the loss-scaled gradients of the last training step
+    bool keepGradients = false;
     uint32_t globalStep = 0;
     bool ummaDirty = true;
 };
@@ -971,6 +976,20 @@ __global__ void k_nrcAdamEma(uint32_t numParams, uint32_t numMatrixWeights, floa
     paramsEma[i] = __float2half(filtered);
 }
 
+// gfx_nrc_keep_gradients: the gradients k_nrcAdamEma is about to consume, as the half values tiny-cuda-nn would hold
+// (loss-scaled by 128), widened to float
+__global__ void k_nrcKeepGradients(uint32_t n, const unsigned long long* __restrict__ grads, float* __restrict__ dst) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        dst[i] = __half2float(__float2half(fixedToFloat(grads[i])));
+}
+
+__global__ void k_nrcFloatToHalf(uint32_t n, const float* __restrict__ src, __half* __restrict__ dst) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        dst[i] = __float2half(src[i]);
+}
+
 __global__ void k_nrcHalfToFloat(uint32_t n, const __half* __restrict__ src, float* __restrict__ dst) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n)
@@ -993,6 +1012,67 @@ static void setupLevels(gfx_nrc* n) { // grid.h:885-922
     n->numParams = n->numMatrixWeights + offset * 2;
 }
 
+// tiny-cuda-nn's pcg32 (dependencies/pcg32/pcg32.h:46-116): 64-bit LCG, XSH-RR output
+struct Pcg32 {
+    uint64_t state, inc;
+    explicit Pcg32(uint64_t initstate, uint64_t initseq = 1u) {
+        state = 0u;
+        inc = (initseq << 1u) | 1u;
+        nextUint();
+        state += initstate;
+        nextUint();
+    }
+    uint32_t nextUint() {
+        const uint64_t oldstate = state;
+        state = oldstate * 0x5851f42d4c957f2dULL + inc;
+        const uint32_t xorshifted = (uint32_t)(((oldstate >> 18u) ^ oldstate) >> 27u);
+        const uint32_t rot = (uint32_t)(oldstate >> 59u);
+        return (xorshifted >> rot) | (xorshifted << ((~rot + 1u) & 31));
+    }
+    float nextFloat() {
+        union { uint32_t u; float f; } x;
+        x.u = (nextUint() >> 9) | 0x3f800000u;
+        return x.f - 1.0f;
+    }
+};
+
+// The parameters a freshly constructed tcnn::Trainer holds (trainer.h:54-60, 72-109): rng = pcg32{seed_seq{seed}[0]};
+// NetworkWithInputEncoding::initialize_params (network_with_input_encoding.h:133-156) initialises the network first -
+// FullyFusedMLP: every weight matrix Xavier-uniform on the host, next_float() * 2 * scale - scale with
+// scale = sqrt(6 / (fan_in + fan_out)) (fully_fused_mlp.cu:922-949, gpu_matrix.h:292-307) - then the encoding: the hash grid
+// U(-1e-4, 1e-4) by generate_random_uniform (grid.h:1267-1272, random.h:65-100), a kernel in which thread i jumps the stream
+// ahead by 4 i and writes elements i, i + T, i + 2T, i + 3T (T = total threads) with val * (upper - lower) + lower, one FMA
+// under nvcc's default contraction.  One-blob and identity have no parameters.
+static void tcnnInitialParams(uint32_t seed, uint32_t numHiddenLayers, uint32_t numMatrixWeights, uint32_t numParams,
+                              std::vector<float>* master) {
+    std::seed_seq seq{ seed };
+    std::vector<uint32_t> seeds(2);
+    seq.generate(seeds.begin(), seeds.end());
+    Pcg32 rng(seeds.front());
+    master->assign(numParams, 0.0f);
+    size_t pos = 0;
+    for (uint32_t m = 0; m <= numHiddenLayers; ++m) {
+        const uint32_t rows = m == numHiddenLayers ? kPaddedOutput : kWidth, cols = kWidth; // fan_out = rows, fan_in = cols
+        const float scale = 1.0f * std::sqrt(6.0f / (float)(cols + rows));
+        for (uint32_t i = 0; i < rows * cols; ++i)
+            (*master)[pos++] = rng.nextFloat() * 2.0f * scale - scale;
+    }
+    const size_t n = numParams - numMatrixWeights;
+    const size_t threadsNeeded = (n + 3) / 4;
+    const size_t totalThreads = (threadsNeeded + 127) / 128 * 128; // n_blocks_linear(n_threads) * n_threads_linear
+    std::vector<float> stream(totalThreads * 4);
+    for (float &f : stream)
+        f = rng.nextFloat();
+    const float upper = 1e-4f, lower = -1e-4f;
+    for (size_t i = 0; i < totalThreads; ++i)
+        for (size_t j = 0; j < 4; ++j) {
+            const size_t idx = i + totalThreads * j;
+            if (idx >= n)
+                break;
+            (*master)[numMatrixWeights + idx] = fmaf(stream[i * 4 + j], upper - lower, lower);
+        }
+}
+
 } // namespace gfx
 
 using namespace gfx;
@@ -1002,6 +1082,8 @@ using namespace gfx;
 extern "C" {
 
 int gfx_nrc_train(gfx_nrc* n, void* stream, const float* inputData, const float* targetData, uint32_t numData, float* lossOnHost);
+int gfx_nrc_reset(gfx_nrc* n, uint32_t seed);
+void gfx_nrc_destroy(gfx_nrc* n);
 
 int gfx_nrc_create(gfx_ctx* ctx, uint32_t numHiddenLayers, float learningRate, gfx_nrc** out) {
     if (!ctx || !out)
@@ -1036,7 +1118,63 @@ int gfx_nrc_create(gfx_ctx* ctx, uint32_t numHiddenLayers, float learningRate, g
     GFX_CUDA(ctx, cudaMemset(n->m2, 0, P * 4));
     GFX_CUDA(ctx, cudaMemset(n->steps, 0, P * 4));
     GFX_CUDA(ctx, cudaMemset(n->grads, 0, P * 8));
+    const int rc = gfx_nrc_reset(n, 1337u); // tcnn::Trainer's default seed: a fresh cache equals the reference's fresh cache
+    if (rc != GFX_OK) {
+        gfx_nrc_destroy(n);
+        return rc;
+    }
     *out = n;
+    return GFX_OK;
+}
+
+int gfx_nrc_reset(gfx_nrc* n, uint32_t seed) {
+    if (!n)
+        return GFX_ERR_INVALID_ARGUMENT;
+    const size_t P = n->numParams;
+    std::vector<float> master;
+    tcnnInitialParams(seed, n->numHiddenLayers, n->numMatrixWeights, n->numParams, &master);
+    NRC_CUDA(n, cudaMemcpy(n->master, master.data(), P * 4, cudaMemcpyHostToDevice));
+    k_nrcFloatToHalf<<<(n->numParams + 255) / 256, 256>>>(n->numParams, n->master, n->params); // trainer.h:104-107
+    n->ctx->launches++;
+    NRC_CUDA(n, cudaMemset(n->paramsEma, 0, P * 2)); // EmaOptimizer::allocate zeroes the inference weights (ema.h:88-100)
+    NRC_CUDA(n, cudaMemset(n->m1, 0, P * 4));
+    NRC_CUDA(n, cudaMemset(n->m2, 0, P * 4));
+    NRC_CUDA(n, cudaMemset(n->steps, 0, P * 4));
+    NRC_CUDA(n, cudaMemset(n->grads, 0, P * 8));
+    n->globalStep = 0;
+    n->ummaDirty = true;
+    NRC_CUDA(n, cudaDeviceSynchronize());
+    return GFX_OK;
+}
+
+int gfx_nrc_keep_gradients(gfx_nrc* n, int on) {
+    if (!n)
+        return GFX_ERR_INVALID_ARGUMENT;
+    if (on && !n->gradsFloat)
+        NRC_CUDA(n, cudaMalloc(&n->gradsFloat, (size_t)n->numParams * 4));
+    n->keepGradients = on != 0;
+    return GFX_OK;
+}
+
+int gfx_nrc_read(gfx_nrc* n, int which, void* hostOut, size_t bytes) {
+    if (!n || !hostOut)
+        return GFX_ERR_INVALID_ARGUMENT;
+    const size_t P = n->numParams;
+    const void* src = nullptr;
+    size_t need = P * 2;
+    switch (which) {
+    case GFX_NRC_READ_MASTER: src = n->master; need = P * 4; break;
+    case GFX_NRC_READ_TRAINING: src = n->params; break;
+    case GFX_NRC_READ_INFERENCE: src = n->paramsEma; break;
+    case GFX_NRC_READ_GRADIENTS: src = n->gradsFloat; need = P * 4; break;
+    default: return GFX_ERR_INVALID_ARGUMENT;
+    }
+    if (!src)
+        return GFX_ERR_NOT_READY;
+    if (bytes != need)
+        return GFX_ERR_INVALID_ARGUMENT;
+    NRC_CUDA(n, cudaDeviceSynchronize());
+    NRC_CUDA(n, cudaMemcpy(hostOut, src, need, cudaMemcpyDeviceToHost));
     return GFX_OK;
 }
 
@@ -1044,7 +1182,7 @@ void gfx_nrc_destroy(gfx_nrc* n) {
     if (!n)
         return;
     cudaFree(n->params); cudaFree(n->paramsEma); cudaFree(n->master); cudaFree(n->m1); cudaFree(n->m2);
-    cudaFree(n->steps); cudaFree(n->grads); cudaFree(n->loss); cudaFree(n->ummaWeights); cudaFree(n->trainBlobFwd); cudaFree(n->trainBlobT);
+    cudaFree(n->steps); cudaFree(n->grads); cudaFree(n->loss); cudaFree(n->ummaWeights); cudaFree(n->trainBlobFwd); cudaFree(n->trainBlobT); cudaFree(n->gradsFloat);
     delete n;
 }
 
@@ -1174,6 +1312,10 @@ int gfx_nrc_train(gfx_nrc* n, void* stream, const float* inputData, const float*
                                                     targetData, numData, n->grads, n->loss); }
     }
     n->ctx->launches++;
+    if (n->keepGradients) {
+        k_nrcKeepGradients<<<(n->numParams + 255) / 256, 256, 0, s>>>(n->numParams, n->grads, n->gradsFloat);
+        n->ctx->launches++;
+    }
     ++n->globalStep;
     const float emaDecay = 0.99f;
     const float emaDebiasOld = 1 - (float)pow((double)emaDecay, (double)(n->globalStep - 1));

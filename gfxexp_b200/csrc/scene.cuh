@@ -13,6 +13,7 @@
 //    along x), reservoirs as three float4 planes.
 #pragma once
 #include "vec.cuh"
+#include <cstddef>
 #include "../../include/gfxb200.h"
 
 namespace gfx {
@@ -29,41 +30,42 @@ struct DevMesh {
     uint32_t pad[3];
 };
 
-// GFX_WIDE_TABLE_LOADS (compile-time, default 0): the light-sampling chain reads an instance's four sampling fields with one
-// 128-bit load and its normal matrix with 2 x 128 + 1 x 32 bits instead of 4 + 9 scalar loads.  ncu source view of the RIS
-// candidate kernel (profiles/r01_summary.md, r01f): those 13 divergent scalar loads are 502 M of its 1 210 M L1 tag requests
-// and the kernel runs at 80 % of the L1 data-pipe rate.  Written at the end of round 1 without GPU time left to validate
-// it, therefore off; the values loaded are identical, so parity is not at stake once it is switched on and measured.
-#ifndef GFX_WIDE_TABLE_LOADS
-#define GFX_WIDE_TABLE_LOADS 0
-#endif
+// Light records (lights.cu): one 128-byte, 128-byte-aligned record per triangle of every emissive geometry, i.e. ONE cache line
+// per RIS candidate, ordered so that sampleLightUnlessDark (lighting.cuh) can stop after the first 16 bytes for most candidates:
+//   q0 (centre.xyz, radius)   bounding sphere of the world-space triangle; radius < 0 = never cull (degenerate area, or the
+//                             selection density lightProb * recArea is not a positive finite number)
+//   q1 (pA.xyz, recArea)  q2 (pB.xyz, lightProb)  q3 (pC.xyz, instance slot)      -> sample position, area density
+//   q4 (nA.xyz, nB.x)     q5 (nB.yz, nC.xy)       q6 (nC.z, emittance.rgb)        -> light normal, emittance
+//   q7 unused
+// Positions, recArea, normals and emittance are produced by the very expressions of sampleLight (restir_di_shared.h:417-425,
+// 485-511) and lightProb by the products of DiscreteDistribution1D::sample's probabilities (:356-409), so reading them is
+// bit-identical to recomputing them.
+constexpr uint32_t kLightTriStride = 8u; // float4 per light record
 
-// GFX_LIGHT_CULL_SPHERES (compile-time, default 0): every light-triangle record gets a seventh float4, the bounding sphere of
-// the world-space triangle (centre, radius; radius < 0 = never cull), read first by sampleLightUnlessDark: on config 2 65 % of
-// the RIS candidates lie below the shading horizon (tools/ris_candidate_stats.py) and most of them can be rejected from the
-// sphere alone - one 16-byte fetch instead of three.  Like GFX_WIDE_TABLE_LOADS: written after round 1's GPU minutes were
-// spent, unvalidated, therefore off; the default build's SASS is unchanged.
-#ifndef GFX_LIGHT_CULL_SPHERES
-#define GFX_LIGHT_CULL_SPHERES 0
-#endif
-constexpr uint32_t kLightTriStride = GFX_LIGHT_CULL_SPHERES ? 7u : 6u; // float4 per light triangle
+// Flattened light pick (lights.cu, k_pick*): sampleLight's three nested DiscreteDistribution1D::sample calls (instance ->
+// geometry instance -> primitive, each a CDF search plus a remap of u) are a pure, monotone, piecewise-constant function of
+// the one random number ul.  Its pieces are found once per light-distribution change by evaluating the exact chain
+// (chainPickLightTriangle, lighting.cuh) at interval end points and refining every interval whose ends disagree, down to adjacent
+// floats; a candidate then costs one guide-table read (+ a short scan of the piece starts in the 6 % of buckets that hold a
+// boundary) instead of ~25 dependent loads.  Exact by construction for every float ul in [0, 1).
+constexpr uint32_t kPickGuideBits = 17;
+constexpr uint32_t kPickGuideSize = 1u << kPickGuideBits;
+constexpr uint32_t kPickPure = 0x80000000u;      // guide entry: bit 31 set = the whole bucket maps to key (low 31 bits)
+constexpr uint32_t kPickNone = 0x40000000u;      // key: bit 30 set = sampleLight's probability-0 early out (no light)
+constexpr uint32_t kPickMaxUlBits = 0x3F7FFFFFu; // largest float below 1
 
 struct DevInstance {
     float transform[12];
     float curToPrevTransform[12];
     float normalMatrix[9];
     float uniformScale;
-#if GFX_WIDE_TABLE_LOADS
-    uint32_t pad[2];       // the four light-sampling fields below then start a 16-byte line (offset 144): one 128-bit load
-#endif
     uint32_t firstMeshSlot;
     uint32_t numMeshSlots;
     float geomIntegral;    // lightGeomInstDist.integral()
     uint32_t geomBase;     // index of this instance's first flattened geometry (instance order)
-#if !GFX_WIDE_TABLE_LOADS
     uint32_t pad[2];
-#endif
 };
+static_assert(offsetof(DevInstance, normalMatrix) % 16 == 0, "the normal matrix is read with two 128-bit loads + one scalar");
 static_assert(sizeof(DevInstance) % 16 == 0, "DevInstance must stay 16-byte aligned");
 
 struct DevBvh {
@@ -94,12 +96,14 @@ struct DevScene {
     const float* primProb;
     const float* geomProb;
     const float* instProb;
-    // world-space table of the triangles of every emissive geometry, 6 float4 each:
-    // (pA, recArea) (pB, nA.x) (pC, nA.y) (nA.z, nB) (nC, -) (emittance, -); lightTriBase[g] = first entry
-    // of flattened geometry g or 0xFFFFFFFF.  Values are produced by the very expressions of
-    // sampleLight (restir_di_shared.h:417-425,485-511), so reading them is bit-identical to recomputing.
+    // light records of the triangles of every emissive geometry (layout above); lightTriBase[g] = first record of flattened
+    // geometry g or 0xFFFFFFFF
     const float4* lightTris;
     const uint32_t* lightTriBase;
+    // flattened light pick: guide[b] for ul in [b, b + 1) / kPickGuideSize is kPickPure | key, or the index of the piece that
+    // holds the bucket's first float; pieces = (first float bit pattern, key) sorted by start, terminated by 0xFFFFFFFF starts
+    const uint32_t* pickGuide;
+    const uint2* pickPieces;
     // guide tables for the CDF searches: guide[b] = search(cdf, fl(b / G * integral)), b = 0..G, so the
     // answer for u = fl(ul * integral) with ul in [b/G, (b+1)/G) lies in [guide[b], guide[b+1]]
     // (rounding is monotone) and a short scan finishes the exact search.

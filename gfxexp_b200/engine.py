@@ -303,6 +303,20 @@ class NeuralRadianceCache:
         self.ctx._check(self.ctx.lib.gfx_nrc_get_params(self.h, out.ctypes.data, out.nbytes), "gfx_nrc_get_params")
         return out
 
+    def reset(self, seed: int = 1337):
+        """re-initialise like a fresh tcnn::Trainer with this seed (gfx_nrc_create does it with 1337, the reference's)"""
+        self.ctx._check(self.ctx.lib.gfx_nrc_reset(self.h, seed), "gfx_nrc_reset")
+
+    def keep_gradients(self, on: bool = True):
+        self.ctx._check(self.ctx.lib.gfx_nrc_keep_gradients(self.h, 1 if on else 0), "gfx_nrc_keep_gradients")
+
+    def read(self, which: int) -> np.ndarray:
+        """abi.NRC_READ_MASTER / _GRADIENTS -> float32[num_params]; _TRAINING / _INFERENCE -> float16[num_params]"""
+        dtype = np.float32 if which in (abi.NRC_READ_MASTER, abi.NRC_READ_GRADIENTS) else np.float16
+        out = np.empty(self.num_params, dtype=dtype)
+        self.ctx._check(self.ctx.lib.gfx_nrc_read(self.h, which, out.ctypes.data, out.nbytes), "gfx_nrc_read")
+        return out
+
     @staticmethod
     def _ptr(t):
         return t if isinstance(t, int) else t.data_ptr()

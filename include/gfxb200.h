@@ -391,6 +391,10 @@ int gfx_trace(gfx_ctx* ctx, void* stream, const GfxRay* rays, uint32_t numRays,
 /* replaces Scene::setupLightGeomDistributions (static part, once) and
  * Scene::setupLightInstDistribution (per frame) + ext/cubd ExclusiveSum */
 int gfx_light_dist_build(gfx_ctx* ctx, void* stream, uint32_t bufferIndex);
+/* test hook for the flattened light pick that gfx_light_dist_build derives from those distributions: for n DEVICE floats ul in
+ * [0, 1) writes the key (light-record index, or bit 30 set for sampleLight's probability-0 early outs,
+ * restir_di_shared.h:356-409) found by the flattened table and by the three nested DiscreteDistribution1D::sample calls */
+int gfx_light_pick_debug(gfx_ctx* ctx, void* stream, const float* ul, uint32_t n, uint32_t* keysFlat, uint32_t* keysChain);
 /* host read-back of the instance-level distribution for parity: weights/cdf sized numInstances */
 int gfx_light_dist_export(gfx_ctx* ctx, float* instWeights, float* instCdf, float* integral);
 
@@ -438,6 +442,22 @@ void gfx_nrc_destroy(gfx_nrc* nrc);
 int gfx_nrc_infer(gfx_nrc* nrc, void* stream, const float* inputData, float* predictionData, uint32_t numData);
 int gfx_nrc_train(gfx_nrc* nrc, void* stream, const float* inputData, const float* targetData,
                   uint32_t numData, float* lossOnHost);
+/* gfx_nrc_create leaves the cache as NeuralRadianceCache::initialize leaves tiny-cuda-nn's Trainer (seed 1337): Xavier-uniform MLP
+ * matrices and U(-1e-4, 1e-4) hash-grid entries drawn from pcg32 in tiny-cuda-nn's order (trainer.h:54-109, gpu_matrix.h:292-307,
+ * grid.h:1267-1272, random.h:65-100), fp32 master = those values, training weights = their halves, inference (EMA) weights and
+ * optimizer state zero.  gfx_nrc_reset re-initialises with another Trainer seed. */
+int gfx_nrc_reset(gfx_nrc* nrc, uint32_t seed);
+/* state read-back for parity tests.  which: MASTER fp32[numParams]; TRAINING / INFERENCE half[numParams];
+ * GRADIENTS fp32[numParams] = the loss-scaled (x128) gradients of the last gfx_nrc_train, rounded to half like
+ * tiny-cuda-nn's gradient buffer (only after gfx_nrc_keep_gradients(nrc, 1)) */
+#define GFX_NRC_READ_MASTER 0
+#define GFX_NRC_READ_TRAINING 1
+#define GFX_NRC_READ_INFERENCE 2
+#define GFX_NRC_READ_GRADIENTS 3
+int gfx_nrc_read(gfx_nrc* nrc, int which, void* hostOut, size_t bytes);
+int gfx_nrc_keep_gradients(gfx_nrc* nrc, int on);
+/* inference (EMA) weights as halves; gfx_nrc_set_params installs the same values as training, inference and master weights and
+ * clears the optimizer state */
 int gfx_nrc_get_params(gfx_nrc* nrc, void* hostHalfParams, size_t bytes);
 int gfx_nrc_set_params(gfx_nrc* nrc, const void* hostHalfParams, size_t bytes);
 uint32_t gfx_nrc_num_params(gfx_nrc* nrc);

@@ -10,12 +10,18 @@
 //                            src/fully_fused_mlp.cu:47-129 (forward), :150-259,:499-557 (backward)
 //   RelativeL2Luminance      losses/relative_l2_luminance.h:41-88, loss scale 128 (trainer.h:187)
 //   Adam + EMA(0.99)         optimizers/adam.h:49-115, optimizers/ema.h:46-121 (half-precision EMA)
-// Arithmetic model: fp16 storage of weights/activations/gradients exactly where tcnn stores halves,
-// fp32 accumulation inside each dot product (the hardware order of a half-accumulating HMMA is not
-// specified, so the tensor-core kernels are compared at 1e-3 relative L2, not bit-exactly).
-// Parity unpinned by the reference (it has no NRC vectors); pinned by finite-difference gradient
-// checks and loss descent in tests/test_oracle_nrc.py.  The encoding half (hash grid, one-blob) has a comparison against the
-// reference's own tiny-cuda-nn kernels prepared in oracle/ref_tcnn + tests/tcnn_ref_check.py; it has not run yet.
+// Arithmetic model: fp16 storage of weights/activations/gradients exactly where tcnn stores halves.  Two accumulation modes
+// for the fully-connected layers (orc_nrc_set_accumulate_half):
+//   0 (default)  fp32 accumulation of each 64-term dot product, one rounding to half per layer - what this repo's tcgen05
+//                kernels compute (fp16 operands, fp32 TMEM accumulators);
+//   1            tiny-cuda-nn's own model: kernel_mlp_fused keeps its wmma accumulator fragments in __half
+//                (fully_fused_mlp.cu:68, backward :198), i.e. the running sum is rounded to half after every 16-wide k step
+//                of the 16x16x16 HMMA (the order INSIDE one HMMA is hardware-defined: compared at 1e-3 relative L2).
+// Pinned against the reference's own code on the GPU box: the encoding bit for bit (oracle/ref_tcnn/tcnn_ref.cu,
+// tests/test_gpu_tcnn_ref.py), the network forward / one training step's gradients / the weights after four steps / the
+// pcg32{1337} initial parameters against tiny-cuda-nn's NetworkWithInputEncoding + Trainer built from network_interface.cu's
+// config (oracle/ref_tcnn/tcnn_nrc.cu, tests/tcnn_nrc_check.py, tests/test_gpu_tcnn_nrc.py).  CPU-side it is pinned by
+// finite-difference gradient checks and loss descent in tests/test_oracle_nrc.py.
 // Parameter layout (this repo's own, shared with the CUDA library): MLP matrices [out][in] in layer
 // order (first 64x64, hidden 64x64 ..., last 16x64), then the hash-grid table level by level.
 #include <cstdint>
@@ -63,7 +69,27 @@ struct orc_nrc {
     std::vector<float> m1, m2;      // Adam moments
     std::vector<uint32_t> steps;    // per-parameter step counters (adam.h:108)
     uint32_t globalStep = 0;
+    int accumulateHalf = 0;         // see the header: 1 = tiny-cuda-nn's half accumulator fragments
+    std::vector<float> lastGradients; // loss-scaled gradients of the last training step, rounded to half like tcnn's buffer
 };
+
+// one output of a fully-connected layer: sum_i w[i * stride] * x[i]
+static inline float dotLayer(const orc_nrc* n, const half* w, size_t stride, const half* x, uint32_t count) {
+    if (!n->accumulateHalf) {
+        float acc = 0.0f;
+        for (uint32_t i = 0; i < count; ++i)
+            acc += h2f(w[i * stride]) * h2f(x[i]);
+        return acc;
+    }
+    half acc = f2h(0.0f);
+    for (uint32_t c = 0; c < count; c += 16) {
+        float partial = 0.0f;
+        for (uint32_t i = c; i < c + 16 && i < count; ++i)
+            partial += h2f(w[i * stride]) * h2f(x[i]);
+        acc = f2h(h2f(acc) + partial);
+    }
+    return h2f(acc);
+}
 
 static void setupLevels(orc_nrc* n) { // grid.h:885-922
     uint32_t offset = 0;
@@ -167,20 +193,14 @@ static void mlpForward(const orc_nrc* n, const half* w, const half* x, half* act
         const half* W = w + (size_t)layer * kWidth * kWidth;
         half* o = acts + (size_t)layer * kWidth;
         for (uint32_t j = 0; j < kWidth; ++j) {
-            float acc = 0.0f;
-            for (uint32_t i = 0; i < kWidth; ++i)
-                acc += h2f(W[j * kWidth + i]) * h2f(in[i]);
+            const float acc = dotLayer(n, W + j * kWidth, 1, in, kWidth);
             o[j] = f2h(std::fmax(acc, 0.0f)); // ReLU, stored as half (fully_fused_mlp.cu:93-112)
         }
         in = o;
     }
     const half* W = w + (size_t)n->numHiddenLayers * kWidth * kWidth;
-    for (uint32_t j = 0; j < kPaddedOutput; ++j) {
-        float acc = 0.0f;
-        for (uint32_t i = 0; i < kWidth; ++i)
-            acc += h2f(W[j * kWidth + i]) * h2f(in[i]);
-        out[j] = f2h(acc);
-    }
+    for (uint32_t j = 0; j < kPaddedOutput; ++j)
+        out[j] = f2h(dotLayer(n, W + j * kWidth, 1, in, kWidth));
 }
 
 extern "C" {
@@ -213,6 +233,28 @@ void orc_nrc_set_params(orc_nrc* n, const uint16_t* halfBits) {
     std::fill(n->m2.begin(), n->m2.end(), 0.0f);
     std::fill(n->steps.begin(), n->steps.end(), 0u);
     n->globalStep = 0;
+}
+void orc_nrc_set_accumulate_half(orc_nrc* n, int on) { n->accumulateHalf = on; }
+// the state of a freshly constructed tcnn::Trainer (trainer.h:72-109, ema.h:88-100): fp32 master = the given values, training
+// weights = their halves, inference (EMA) weights and optimizer state zero
+void orc_nrc_init_master(orc_nrc* n, const float* master) {
+    for (uint32_t i = 0; i < n->numParams; ++i) {
+        n->master[i] = master[i];
+        n->params[i] = f2h(master[i]);
+        n->paramsEma[i] = f2h(0.0f);
+    }
+    std::fill(n->m1.begin(), n->m1.end(), 0.0f);
+    std::fill(n->m2.begin(), n->m2.end(), 0.0f);
+    std::fill(n->steps.begin(), n->steps.end(), 0u);
+    n->globalStep = 0;
+}
+void orc_nrc_get_master(orc_nrc* n, float* out) { std::memcpy(out, n->master.data(), (size_t)n->numParams * 4); }
+// loss-scaled (x128) gradients of the last orc_nrc_train, as the halves tcnn's gradient buffer would hold, widened to float
+int orc_nrc_get_gradients(orc_nrc* n, float* out) {
+    if (n->lastGradients.size() != n->numParams)
+        return 1;
+    std::memcpy(out, n->lastGradients.data(), (size_t)n->numParams * 4);
+    return 0;
 }
 void orc_nrc_get_params(orc_nrc* n, uint16_t* out, int ema) {
     std::memcpy(out, ema ? n->paramsEma.data() : n->params.data(), (size_t)n->numParams * 2);
@@ -288,9 +330,7 @@ float orc_nrc_train(orc_nrc* n, const float* in, const float* target, uint32_t n
                             gW[j * kWidth + i] += dj * h2f(hin[i]);
                 }
                 for (uint32_t i = 0; i < kWidth; ++i) {
-                    float acc = 0.0f;
-                    for (uint32_t j = 0; j < kPaddedOutput; ++j)
-                        acc += h2f(W[j * kWidth + i]) * h2f(dOut[j]);
+                    const float acc = dotLayer(n, W + i, kWidth, dOut, kPaddedOutput);
                     // ReLU backward on the stored forward activation (fully_fused_mlp.cu:163-176)
                     dCur[i] = (H > 0 && !(h2f(hin[i]) > 0.0f)) ? f2h(0.0f) : f2h(acc);
                 }
@@ -307,9 +347,7 @@ float orc_nrc_train(orc_nrc* n, const float* in, const float* target, uint32_t n
                 }
                 half dNext[64];
                 for (uint32_t i = 0; i < kWidth; ++i) {
-                    float acc = 0.0f;
-                    for (uint32_t j = 0; j < kWidth; ++j)
-                        acc += h2f(W[j * kWidth + i]) * h2f(dCur[j]);
+                    const float acc = dotLayer(n, W + i, kWidth, dCur, kWidth);
                     dNext[i] = (layer > 0 && !(h2f(hin[i]) > 0.0f)) ? f2h(0.0f) : f2h(acc);
                 }
                 std::memcpy(dCur, dNext, sizeof(dCur));
@@ -328,6 +366,9 @@ float orc_nrc_train(orc_nrc* n, const float* in, const float* target, uint32_t n
         for (uint32_t i = 0; i < n->numParams; ++i)
             grad[i] += tgrad[t][i];
 
+    n->lastGradients.resize(n->numParams);
+    for (uint32_t i = 0; i < n->numParams; ++i)
+        n->lastGradients[i] = h2f(f2h(grad[i]));
     // Adam (adam.h:49-115) on half gradients, then EMA (ema.h:61-77,103-121)
     ++n->globalStep;
     const float beta1 = 0.9f, beta2 = 0.99f, epsilon = 1e-15f, l2Reg = 1e-6f;

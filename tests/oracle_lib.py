@@ -102,6 +102,11 @@ def lib() -> C.CDLL:
         L.orc_nrc_get_params.argtypes = [vp, vp, C.c_int]
         L.orc_nrc_encode.argtypes = [vp, vp, C.c_uint32, vp, C.c_int]
         L.orc_nrc_infer.argtypes = [vp, vp, vp, C.c_uint32]
+        L.orc_nrc_set_accumulate_half.argtypes = [vp, C.c_int]
+        L.orc_nrc_init_master.argtypes = [vp, vp]
+        L.orc_nrc_get_master.argtypes = [vp, vp]
+        L.orc_nrc_get_gradients.argtypes = [vp, vp]
+        L.orc_nrc_get_gradients.restype = C.c_int
         L.orc_nrc_train.restype = C.c_float
         L.orc_nrc_train.argtypes = [vp, vp, vp, C.c_uint32]
         _lib = L
@@ -308,6 +313,26 @@ class OracleNrc:
     def get_params(self, ema: bool = True) -> np.ndarray:
         out = np.empty(self.num_params, dtype=np.float16)
         lib().orc_nrc_get_params(self.h, out.ctypes.data, 1 if ema else 0)
+        return out
+
+    def set_accumulate_half(self, on: bool):
+        """fully-connected layers with tiny-cuda-nn's half accumulator fragments (oracle/nrc.cpp header) instead of fp32"""
+        lib().orc_nrc_set_accumulate_half(self.h, 1 if on else 0)
+
+    def init_master(self, master_f32: np.ndarray):
+        """the state of a fresh tcnn::Trainer: fp32 master weights, their halves as training weights, zero EMA weights"""
+        m = np.ascontiguousarray(master_f32, dtype=np.float32)
+        assert m.shape[0] == self.num_params
+        lib().orc_nrc_init_master(self.h, m.ctypes.data)
+
+    def get_master(self) -> np.ndarray:
+        out = np.empty(self.num_params, dtype=np.float32)
+        lib().orc_nrc_get_master(self.h, out.ctypes.data)
+        return out
+
+    def get_gradients(self) -> np.ndarray:
+        out = np.empty(self.num_params, dtype=np.float32)
+        assert lib().orc_nrc_get_gradients(self.h, out.ctypes.data) == 0, "no training step yet"
         return out
 
     def encode(self, queries: np.ndarray, ema: bool = True) -> np.ndarray:
