@@ -360,6 +360,7 @@ _DECLS = {
     "gfx_nrc_train": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_u32, C.POINTER(c_f)]),
     "gfx_nrc_reset": (C.c_int, [C.c_void_p, c_u32]),
     "gfx_nrc_read": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
+    "gfx_nrc_encode_debug": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, c_u32, C.c_void_p]),
     "gfx_nrc_keep_gradients": (C.c_int, [C.c_void_p, C.c_int]),
     "gfx_nrc_get_params": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "gfx_nrc_set_params": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),

@@ -137,6 +137,7 @@ DevScene gfx_ctx::devScene() const {
     d.instProb = scene.instProb;
     d.lightTris = scene.lightTris;
     d.lightTriBase = scene.lightTriBase;
+    d.numLightTris = scene.numLightTris;
     d.pickGuide = scene.pickGuide;
     d.pickPieces = scene.pickPieces;
     d.instGuide = scene.instGuide;

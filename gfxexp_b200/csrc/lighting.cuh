@@ -105,11 +105,18 @@ GFX_D uint32_t chainPickLightTriangle(const DevScene &s, float ul, float* lightP
     lightProb *= primProb;
 
     *lightProbOut = lightProb;
-    return __ldg(s.lightTriBase + inst->geomBase + geomInstIndexInInst) + primIndex;
+    const uint32_t base = __ldg(s.lightTriBase + inst->geomBase + geomInstIndexInInst);
+    if (base == 0xFFFFFFFFu) // a geometry without an emitter: only reachable when every weight is 0 (0 / 0 probabilities)
+        return kPickNone | 0x10000000u | (firstMeshSlot + geomInstIndexInInst);
+    return base + primIndex;
 }
 
 // The flattened pick (scene.cuh, lights.cu): key of the piece that contains ul.
 GFX_D uint32_t pickLightTriangle(const DevScene &s, float ul) {
+#ifdef GFX_AB_CHAIN_PICK // A/B: the definition instead of its flattened form
+    float unusedProb;
+    return chainPickLightTriangle(s, ul, &unusedProb);
+#endif
     const uint32_t b = min(dm_f2uint(ul * (float)kPickGuideSize), kPickGuideSize - 1); // exact: a power-of-two product, floored
     const uint32_t g = __ldg(s.pickGuide + b);
     if (g & kPickPure)
@@ -196,7 +203,12 @@ GFX_D bool sampleLightUnlessDark(const DevScene &s, float ul, float u0, float u1
         const float r = sphere.w;
         const float t = -(dot(dc, shadingNormal) * vOutLocalZ);          // > 0: centre on the far side of the surface
         const float margin = t - 1.001f * r * fabsf(vOutLocalZ);
-        if (r >= 0.0f && margin > 0.0f && margin * margin > 8e-6f * (sqLength(dc) + r * r) * (vOutLocalZ * vOutLocalZ)) {
+#ifdef GFX_AB_NO_SPHERE
+        const bool sphereCull = false;
+#else
+        const bool sphereCull = true;
+#endif
+        if (sphereCull && r >= 0.0f && margin > 0.0f && margin * margin > 8e-6f * (sqLength(dc) + r * r) * (vOutLocalZ * vOutLocalZ)) {
             *areaPDensity = 1.0f; // any positive number: the caller only asks whether the density is positive
             return true;
         }

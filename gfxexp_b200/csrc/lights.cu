@@ -297,7 +297,7 @@ __global__ void k_pickLightProbs(DevScene scene, const uint2* __restrict__ piece
         return;
     float lightProb = 0.0f;
     const uint32_t key = chainPickLightTriangle(scene, __uint_as_float(piece.x), &lightProb);
-    if (key != piece.y) { // cannot happen: the piece start was produced by this very evaluation
+    if (key != piece.y || key >= scene.numLightTris) { // cannot happen: the piece start was produced by this very evaluation
         atomicOr(const_cast<uint32_t*>(counters) + 3, 4u);
         return;
     }

@@ -57,6 +57,9 @@ struct gfx_nrc {
     uint4* ummaWeights = nullptr; // EMA MLP weights in the tcgen05 shared-memory layout
     uint4* trainBlobFwd = nullptr; // training weights, tcgen05 layouts: W_l [N x 64] and W_l^T [64 x K] K-major blobs
     uint4* trainBlobT = nullptr;
+    float4* positions = nullptr;   // split inference scratch: packed query positions, grid features [tile][level][row] half2
+    __half2* features = nullptr;
+    uint32_t scratchQueries = 0;
     float* gradsFloat = nullptr;   // gfx_nrc_keep_gradients: the loss-scaled gradients of the last training step
     bool keepGradients = false;
     uint32_t globalStep = 0;
@@ -130,6 +133,31 @@ GFX_D uint32_t nrcGridIndex(const NrcLevel &lv, const uint32_t pos[3]) { // grid
     return (index % lv.hashmapSize) * 2u;
 }
 
+// OneBlob: 5 dims x 4 bins -> features 32..51, identity 52..57, ones 58..63 (q = the 14 query floats; q[0..2] unused)
+GFX_D void nrcEncodeTail(const float* q, __half* tail) {
+#pragma unroll
+    for (uint32_t d = 0; d < 5; ++d) {
+        const float x = q[3 + d];
+        // kernel_one_blob_soa (tiny-cuda-nn oneblob.h:110-139; the composite encoding runs its nested encodings on SoA
+        // slices): CDF at the five bin boundaries k / 4, each summed over the three periodic images
+        float leftCdf = quarticCdf(-x, 4.0f) + quarticCdf(-x - 1.0f, 4.0f) + quarticCdf(-x + 1.0f, 4.0f);
+#pragma unroll
+        for (uint32_t k = 0; k < 4; ++k) {
+            const float rightBoundary = 0.25f * (float)(k + 1); // scalbnf(k + 1, -2)
+            const float rightCdf = quarticCdf(rightBoundary - x, 4.0f) + quarticCdf(rightBoundary - x - 1.0f, 4.0f) +
+                                   quarticCdf(rightBoundary - x + 1.0f, 4.0f);
+            tail[d * 4 + k] = __float2half(rightCdf - leftCdf);
+            leftCdf = rightCdf;
+        }
+    }
+#pragma unroll
+    for (uint32_t d = 0; d < 6; ++d)
+        tail[20 + d] = __float2half(q[8 + d]);
+#pragma unroll
+    for (uint32_t k = 26; k < 32; ++k)
+        tail[k] = __float2half(1.0f);
+}
+
 // Encodes one query into 64 halves, delivered 8 at a time (chunk c = features 8c..8c+7) through `emit`.
 // Arithmetic mirrors oracle/nrc.cpp::encode (half accumulation of the trilinear blend like kernel_grid).
 template <typename Emit>
@@ -180,29 +208,8 @@ GFX_D void nrcEncode(const NrcLevels &levels, const __half* __restrict__ table, 
         if ((l & 3) == 3)
             emit(l >> 2, feat);
     }
-    // OneBlob: 5 dims x 4 bins -> features 32..51, identity 52..57, ones 58..63
     __half tail[32];
-#pragma unroll
-    for (uint32_t d = 0; d < 5; ++d) {
-        const float x = q[3 + d];
-        // kernel_one_blob_soa (tiny-cuda-nn oneblob.h:110-139; the composite encoding runs its nested encodings on SoA
-        // slices): CDF at the five bin boundaries k / 4, each summed over the three periodic images
-        float leftCdf = quarticCdf(-x, 4.0f) + quarticCdf(-x - 1.0f, 4.0f) + quarticCdf(-x + 1.0f, 4.0f);
-#pragma unroll
-        for (uint32_t k = 0; k < 4; ++k) {
-            const float rightBoundary = 0.25f * (float)(k + 1); // scalbnf(k + 1, -2)
-            const float rightCdf = quarticCdf(rightBoundary - x, 4.0f) + quarticCdf(rightBoundary - x - 1.0f, 4.0f) +
-                                   quarticCdf(rightBoundary - x + 1.0f, 4.0f);
-            tail[d * 4 + k] = __float2half(rightCdf - leftCdf);
-            leftCdf = rightCdf;
-        }
-    }
-#pragma unroll
-    for (uint32_t d = 0; d < 6; ++d)
-        tail[20 + d] = __float2half(q[8 + d]);
-#pragma unroll
-    for (uint32_t k = 26; k < 32; ++k)
-        tail[k] = __float2half(1.0f);
+    nrcEncodeTail(q, tail);
 #pragma unroll
     for (uint32_t c = 0; c < 4; ++c)
         emit(4 + c, tail + 8 * c);
@@ -440,6 +447,320 @@ __global__ void __launch_bounds__(128) k_nrcInfer(NrcLevels levels, const __half
     __syncthreads();
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmemBase), "r"(64u) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// Inference, split form (default): the hash grid is the part of the network that is bound by divergent gathers - 128 dependent
+// 4-byte reads per query out of a 2 MB table, i.e. 128 L1 wavefronts at ~2 clocks each (ncu, round 1: tensor pipe 0.9 % active;
+// the fused kernel above and tiny-cuda-nn's kernel_grid both sit at 1.5-1.8 ms for 2.1 M queries on a B200).  One LEVEL of the
+// table is only 128 KB, though (level 0: 16 KB), which fits in a B200 SM's shared memory, where a 32-lane gather costs ~3 clocks
+// instead of ~66.  So:
+//   k_nrcPackPositions   positions of the [N][14] queries -> float4 stream (read once per level below);
+//   k_nrcGridEncode      grid = 16 levels x R replicas, one CTA per SM: the CTA pulls ITS level's table into shared memory with
+//                        cp.async.bulk (TMA) + mbarrier once, then streams its share of the queries through it: coalesced
+//                        position read, 8 shared-memory gathers, trilinear blend in half exactly like kernel_grid
+//                        (grid.h:132-255), coalesced half2 store into features[tile][level][row] (8 KB per 128-query tile);
+//   k_nrcInferMlp        per 128-query tile: two TMA bulk copies bring the tile's queries (7 KB) and grid features (8 KB) into
+//                        shared memory (double-buffered: the next tile is in flight), the threads add one-blob + identity and
+//                        lay the A tile out in UMMA core matrices, tcgen05.mma runs the 64->64->...->16 MLP as above, and the
+//                        radiance leaves through a TMA bulk store.
+// The features are the same halves, bit for bit, as nrcEncode's (tests/test_gpu_nrc.py::test_split_encoding_is_bit_exact).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_nrcPackPositions(const float* __restrict__ input, float4* __restrict__ positions, uint32_t numDataImm,
+                                   const uint32_t* __restrict__ numDataPtr) {
+    const uint32_t numData = numDataPtr ? *numDataPtr : numDataImm;
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < numData; q += gridDim.x * blockDim.x) {
+        const float* in = input + (size_t)q * kInputDims;
+        positions[q] = make_float4(in[0], in[1], in[2], 0.0f);
+    }
+}
+
+GFX_D void bulkLoad(void* smemDst, const void* globalSrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smemU32(smemDst)), "l"(globalSrc), "r"(bytes), "r"(smemU32(bar)) : "memory");
+}
+GFX_D void mbarExpectTx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smemU32(bar)), "r"(bytes) : "memory");
+}
+
+constexpr uint32_t kEncodeThreads = 1024;
+constexpr uint32_t kTileFeatureBytes = kLevels * 128 * 4; // 8 KB per 128-query tile: [level][row] half2
+
+__global__ void __launch_bounds__(kEncodeThreads, 1) k_nrcGridEncode(NrcLevels levels, const __half* __restrict__ table,
+                                                                      const float4* __restrict__ positions,
+                                                                      __half2* __restrict__ features, uint32_t replicas,
+                                                                      uint32_t numDataImm, const uint32_t* __restrict__ numDataPtr) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    const uint32_t numData = numDataPtr ? *numDataPtr : numDataImm;
+    const uint32_t level = blockIdx.x / replicas, replica = blockIdx.x % replicas;
+    const NrcLevel lv = levels.l[level];
+    const uint32_t tableBytes = lv.hashmapSize * 4u;
+    if (threadIdx.x == 0) {
+        mbarInit(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbarExpectTx(&bar, tableBytes);
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(table + (size_t)lv.offset * 2);
+        for (uint32_t off = 0; off < tableBytes; off += 32768u)
+            bulkLoad(smem + off, src + off, min(32768u, tableBytes - off), &bar);
+    }
+    __syncthreads();
+    mbarWait(&bar, 0);
+    const __half2* grid = reinterpret_cast<const __half2*>(smem);
+
+    // this replica's share of the 128-query tiles
+    const uint32_t numTiles = (numData + 127u) / 128u;
+    const uint32_t tilesPer = (numTiles + replicas - 1) / replicas;
+    const uint32_t qBegin = min(replica * tilesPer, numTiles) * 128u;
+    const uint32_t qEnd = min(min((replica + 1) * tilesPer, numTiles) * 128u, numData);
+
+    // level constants of grid_index (grid.h:76-111), hoisted: dense levels add strides, hashed levels xor prime products
+    uint32_t stride = 1, strides[3];
+    bool used[3];
+#pragma unroll
+    for (uint32_t dim = 0; dim < 3; ++dim) {
+        used[dim] = stride <= lv.hashmapSize;
+        strides[dim] = stride;
+        if (used[dim])
+            stride *= lv.resolution;
+    }
+    const bool hashed = lv.hashmapSize < stride;
+    const uint32_t primes[3] = { 1u, 2654435761u, 805459861u };
+    uint32_t mul[3];
+#pragma unroll
+    for (uint32_t dim = 0; dim < 3; ++dim)
+        mul[dim] = hashed ? primes[dim] : (used[dim] ? strides[dim] : 0u);
+    const uint32_t size = lv.hashmapSize;
+    const bool pow2 = (size & (size - 1u)) == 0u;
+
+    for (uint32_t q = qBegin + threadIdx.x; q < qEnd; q += kEncodeThreads) {
+        const float4 p = __ldg(positions + q);
+        const float in[3] = { p.x, p.y, p.z };
+        float pos[3];
+        uint32_t term[3][2];
+#pragma unroll
+        for (uint32_t d = 0; d < 3; ++d) { // pos_fract, common_device.h:425-431
+            pos[d] = in[d] * lv.scale + 0.5f;
+            const int tmp = (int)floorf(pos[d]);
+            pos[d] -= (float)tmp;
+            term[d][0] = (uint32_t)tmp * mul[d];
+            term[d][1] = term[d][0] + mul[d];
+        }
+        __half2 r = __floats2half2_rn(0.0f, 0.0f);
+#pragma unroll
+        for (uint32_t idx = 0; idx < 8; ++idx) {
+            float weight = 1;
+#pragma unroll
+            for (uint32_t d = 0; d < 3; ++d)
+                weight *= (idx & (1u << d)) == 0 ? 1 - pos[d] : pos[d];
+            const uint32_t a = term[0][idx & 1u], b = term[1][(idx >> 1) & 1u], c = term[2][(idx >> 2) & 1u];
+            uint32_t index = hashed ? (a ^ b ^ c) : (a + b + c);
+            index = pow2 ? (index & (size - 1u)) : (index < size ? index : index % size);
+            const float2 v = __half22float2(grid[index]);
+            // result += (half)(weight * (float)value) in half precision (grid.h:233-238); __hadd2 rounds the exact sum once,
+            // which equals the float-add-then-round-to-half the oracle spells out (the fp32 sum of two halves only rounds when
+            // the smaller one is below a quarter ulp of the larger)
+            r = __hadd2(r, __floats2half2_rn(weight * v.x, weight * v.y));
+        }
+        features[((size_t)(q >> 7) * kLevels + level) * 128u + (q & 127u)] = r;
+    }
+}
+
+// queries of one tile and its grid features, landed by TMA
+struct NrcTileStage {
+    float query[128 * kInputDims];    // 7168 B
+    __half2 feat[kLevels * 128];      // 8192 B
+};
+
+__global__ void __launch_bounds__(128) k_nrcInferMlp(const uint4* __restrict__ ummaWeights, uint32_t numHiddenLayers,
+                                                     const float* __restrict__ input, const __half2* __restrict__ features,
+                                                     float* __restrict__ output, uint32_t numDataImm,
+                                                     const uint32_t* __restrict__ numDataPtr) {
+    const uint32_t numData = numDataPtr ? *numDataPtr : numDataImm;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sA = smem;                                                        // activation tile (A operand), 16 KB
+    NrcTileStage* stage = reinterpret_cast<NrcTileStage*>(smem + kATileBytes); // 2 x 15 KB
+    float* sOut = reinterpret_cast<float*>(smem + kATileBytes + 2 * sizeof(NrcTileStage)); // 128 x 3 floats
+    uint8_t* sW = smem + kATileBytes + 2 * sizeof(NrcTileStage) + 128 * kOutputDims * 4;   // weight blobs (B operands)
+    __shared__ __align__(8) uint64_t bar, stageBar[2];
+    __shared__ uint32_t tmemBaseShared;
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t warp = tid >> 5;
+    const uint32_t weightBytes = (numHiddenLayers * kWidth * kWidth + kPaddedOutput * kWidth) * 2;
+    const uint32_t numTiles = numData / kTileRows;
+
+    auto requestTile = [&](uint32_t tile, uint32_t b) { // thread 0 only
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbarExpectTx(&stageBar[b], (uint32_t)sizeof(NrcTileStage));
+        bulkLoad(stage[b].query, input + (size_t)tile * 128 * kInputDims, 128 * kInputDims * 4, &stageBar[b]);
+        bulkLoad(stage[b].feat, features + (size_t)tile * kLevels * 128, kTileFeatureBytes, &stageBar[b]);
+    };
+
+    if (tid == 0) {
+        mbarInit(&bar, 1);
+        mbarInit(&stageBar[0], 1);
+        mbarInit(&stageBar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (blockIdx.x < numTiles)
+            requestTile(blockIdx.x, 0);
+    }
+    for (uint32_t i = tid; i < weightBytes / 16; i += 128)
+        reinterpret_cast<uint4*>(sW)[i] = __ldg(ummaWeights + i);
+    if (warp == 0) { // TMEM: 64 fp32 accumulator columns x 128 lanes
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smemU32(&tmemBaseShared)), "r"(64u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fenceProxyAsync();
+    tcFenceBefore();
+    __syncthreads();
+    tcFenceAfter();
+    const uint32_t tmemBase = tmemBaseShared;
+    const uint32_t tmemRow = tmemBase + ((warp * 32u) << 16); // this warp's 32 lanes
+
+    const uint32_t aAddr = smemU32(sA);
+    const uint32_t wAddr = smemU32(sW);
+    const uint32_t idescHidden = makeInstrDesc(128, kWidth);
+    const uint32_t idescOut = makeInstrDesc(128, kPaddedOutput);
+    uint32_t phase = 0, stagePhase0 = 0, stagePhase1 = 0, buf = 0;
+
+    for (uint32_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x, buf ^= 1u) {
+        // prefetch the next tile into the other buffer (every thread finished reading it one tile ago: the end-of-tile barrier)
+        if (tid == 0 && tile + gridDim.x < numTiles)
+            requestTile(tile + gridDim.x, buf ^ 1u);
+        if (buf == 0) {
+            mbarWait(&stageBar[0], stagePhase0);
+            stagePhase0 ^= 1u;
+        }
+        else {
+            mbarWait(&stageBar[1], stagePhase1);
+            stagePhase1 ^= 1u;
+        }
+        const NrcTileStage &st = stage[buf];
+
+        // ---- this thread's row of the A tile: chunk c (8 features = 16 B) at c * 2048 + row * 16
+#pragma unroll
+        for (uint32_t c = 0; c < 4; ++c) { // hash grid: levels 4c .. 4c + 3
+            uint4 v;
+            v.x = *reinterpret_cast<const uint32_t*>(&st.feat[(4 * c + 0) * 128 + tid]);
+            v.y = *reinterpret_cast<const uint32_t*>(&st.feat[(4 * c + 1) * 128 + tid]);
+            v.z = *reinterpret_cast<const uint32_t*>(&st.feat[(4 * c + 2) * 128 + tid]);
+            v.w = *reinterpret_cast<const uint32_t*>(&st.feat[(4 * c + 3) * 128 + tid]);
+            *reinterpret_cast<uint4*>(sA + c * (kTileRows * 16) + tid * 16) = v;
+        }
+        {
+            float q[kInputDims];
+            q[0] = q[1] = q[2] = 0.0f;
+#pragma unroll
+            for (uint32_t d = 3; d < kInputDims; ++d)
+                q[d] = st.query[tid * kInputDims + d];
+            __half tail[32];
+            nrcEncodeTail(q, tail);
+#pragma unroll
+            for (uint32_t c = 0; c < 4; ++c) {
+                uint4 v;
+                const __half* f = tail + 8 * c;
+                v.x = (uint32_t)__half_as_ushort(f[0]) | ((uint32_t)__half_as_ushort(f[1]) << 16);
+                v.y = (uint32_t)__half_as_ushort(f[2]) | ((uint32_t)__half_as_ushort(f[3]) << 16);
+                v.z = (uint32_t)__half_as_ushort(f[4]) | ((uint32_t)__half_as_ushort(f[5]) << 16);
+                v.w = (uint32_t)__half_as_ushort(f[6]) | ((uint32_t)__half_as_ushort(f[7]) << 16);
+                *reinterpret_cast<uint4*>(sA + (4 + c) * (kTileRows * 16) + tid * 16) = v;
+            }
+        }
+
+        for (uint32_t layer = 0; layer <= numHiddenLayers; ++layer) {
+            const bool last = layer == numHiddenLayers;
+            const uint32_t N = last ? kPaddedOutput : kWidth;
+            // make the generic-proxy writes of sA visible to the tensor core, order against previous tcgen05.ld
+            fenceProxyAsync();
+            tcFenceBefore();
+            __syncthreads();
+            if (tid == 0) {
+                tcFenceAfter();
+                const uint32_t wLayer = wAddr + layer * kWidth * kWidth * 2;
+#pragma unroll
+                for (uint32_t k = 0; k < kWidth / 16; ++k) {
+                    const uint64_t aDesc = makeSmemDesc(aAddr + 2 * k * (kTileRows * 16), kTileRows * 16, 128);
+                    const uint64_t bDesc = makeSmemDesc(wLayer + 2 * k * (N * 16), N * 16, 128);
+                    umma(tmemBase, aDesc, bDesc, last ? idescOut : idescHidden, k > 0 ? 1u : 0u);
+                }
+                ummaCommit(&bar);
+            }
+            mbarWait(&bar, phase);
+            phase ^= 1;
+            tcFenceAfter();
+            if (!last) {
+#pragma unroll
+                for (uint32_t half_ = 0; half_ < 2; ++half_) {
+                    uint32_t r[32];
+                    tmemLoad32(tmemRow + half_ * 32, r);
+                    tmemWaitLd();
+#pragma unroll
+                    for (uint32_t c = 0; c < 4; ++c) {
+                        uint32_t packed[4];
+#pragma unroll
+                        for (uint32_t e = 0; e < 4; ++e) {
+                            const float a = fmaxf(__uint_as_float(r[c * 8 + 2 * e]), 0.0f);
+                            const float b = fmaxf(__uint_as_float(r[c * 8 + 2 * e + 1]), 0.0f);
+                            packed[e] = (uint32_t)__half_as_ushort(__float2half(a)) | ((uint32_t)__half_as_ushort(__float2half(b)) << 16);
+                        }
+                        *reinterpret_cast<uint4*>(sA + (half_ * 4 + c) * (kTileRows * 16) + tid * 16) =
+                            make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                    }
+                }
+            }
+            else {
+                uint32_t r[4];
+                tmemLoad4(tmemRow, r);
+                tmemWaitLd();
+                // the previous tile's bulk store must have read sOut before it is overwritten
+                if (tid == 0)
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncthreads();
+                // trim_and_cast_from: half output -> float
+                sOut[tid * kOutputDims + 0] = __half2float(__float2half(__uint_as_float(r[0])));
+                sOut[tid * kOutputDims + 1] = __half2float(__float2half(__uint_as_float(r[1])));
+                sOut[tid * kOutputDims + 2] = __half2float(__float2half(__uint_as_float(r[2])));
+            }
+        }
+        // all warps are done reading TMEM / the A tile / the stage before the next tile overwrites them
+        fenceProxyAsync();
+        tcFenceBefore();
+        __syncthreads();
+        tcFenceAfter();
+        if (tid == 0) { // radiance of the tile: one TMA bulk store of 1536 contiguous bytes
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         :: "l"(output + (size_t)tile * 128 * kOutputDims), "r"(smemU32(sOut)), "r"(128u * kOutputDims * 4u) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    if (tid == 0)
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    tcFenceBefore();
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmemBase), "r"(64u) : "memory");
+}
+
+// test hook: the 64 encoded halves per query as the split pipeline produces them (pack -> grid encode -> tail)
+__global__ void k_nrcAssembleEncoding(const float* __restrict__ input, const __half2* __restrict__ features, uint32_t numData,
+                                      __half* __restrict__ out) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= numData)
+        return;
+    __half* o = out + (size_t)q * 64;
+    for (uint32_t l = 0; l < kLevels; ++l) {
+        const __half2 v = features[((size_t)(q >> 7) * kLevels + l) * 128u + (q & 127u)];
+        o[2 * l] = __low2half(v);
+        o[2 * l + 1] = __high2half(v);
+    }
+    float qv[kInputDims];
+    for (uint32_t d = 0; d < kInputDims; ++d)
+        qv[d] = input[(size_t)q * kInputDims + d];
+    __half tail[32];
+    nrcEncodeTail(qv, tail);
+    for (uint32_t k = 0; k < 32; ++k)
+        o[32 + k] = tail[k];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1182,7 +1503,7 @@ void gfx_nrc_destroy(gfx_nrc* n) {
     if (!n)
         return;
     cudaFree(n->params); cudaFree(n->paramsEma); cudaFree(n->master); cudaFree(n->m1); cudaFree(n->m2);
-    cudaFree(n->steps); cudaFree(n->grads); cudaFree(n->loss); cudaFree(n->ummaWeights); cudaFree(n->trainBlobFwd); cudaFree(n->trainBlobT); cudaFree(n->gradsFloat);
+    cudaFree(n->steps); cudaFree(n->grads); cudaFree(n->loss); cudaFree(n->ummaWeights); cudaFree(n->trainBlobFwd); cudaFree(n->trainBlobT); cudaFree(n->gradsFloat); cudaFree(n->positions); cudaFree(n->features);
     delete n;
 }
 
@@ -1213,6 +1534,40 @@ int gfx_nrc_get_params(gfx_nrc* n, void* hostHalfParams, size_t bytes) {
     return GFX_OK;
 }
 
+static int nrcEnsureScratch(gfx_nrc* n, uint32_t numQueries) {
+    if (numQueries <= n->scratchQueries)
+        return GFX_OK;
+    cudaFree(n->positions);
+    cudaFree(n->features);
+    n->positions = nullptr;
+    n->features = nullptr;
+    n->scratchQueries = 0;
+    NRC_CUDA(n, cudaMalloc(&n->positions, (size_t)numQueries * 16));
+    NRC_CUDA(n, cudaMalloc(&n->features, (size_t)numQueries * kLevels * 4));
+    n->scratchQueries = numQueries;
+    return GFX_OK;
+}
+
+// pack + grid encode (the two kernels in front of k_nrcInferMlp); numData (or *numDataPtr) is a multiple of 128
+static int nrcGridEncodeLaunch(gfx_nrc* n, cudaStream_t s, const float* inputData, uint32_t numData, const uint32_t* numDataPtr,
+                               bool emaTable) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    { GFX_TIMED(n->ctx, s, "nrc_pack_positions");
+    k_nrcPackPositions<<<sms * 4, 256, 0, s>>>(inputData, n->positions, numData, numDataPtr); }
+    n->ctx->launches++;
+    const uint32_t replicas = (uint32_t)sms / kLevels > 0 ? (uint32_t)sms / kLevels : 1u;
+    const size_t smem = (size_t)(1u << kLog2HashmapSize) * 4;
+    NRC_CUDA(n, cudaFuncSetAttribute(k_nrcGridEncode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { GFX_TIMED(n->ctx, s, "nrc_grid_encode");
+    k_nrcGridEncode<<<kLevels * replicas, kEncodeThreads, smem, s>>>(n->levels, (emaTable ? n->paramsEma : n->params) + n->numMatrixWeights,
+                                                                     n->positions, n->features, replicas, numData, numDataPtr); }
+    n->ctx->launches++;
+    NRC_CUDA(n, cudaGetLastError());
+    return GFX_OK;
+}
+
 static int nrcInferLaunch(gfx_nrc* n, cudaStream_t s, const float* inputData, float* predictionData, uint32_t numData,
                           const uint32_t* numDataPtr) {
     if (n->ummaDirty) {
@@ -1220,16 +1575,52 @@ static int nrcInferLaunch(gfx_nrc* n, cudaStream_t s, const float* inputData, fl
         n->ctx->launches++;
         n->ummaDirty = false;
     }
-    const size_t smem = kATileBytes + (size_t)n->numMatrixWeights * 2;
-    NRC_CUDA(n, cudaFuncSetAttribute(k_nrcInfer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const uint32_t numTiles = numData / kTileRows; // upper bound when numDataPtr is given
-    const uint32_t grid = numTiles < (uint32_t)sms * 6 ? numTiles : (uint32_t)sms * 6;
+    // GFX_NRC_INFER_FUSED=1: the one-kernel form (encode by L2 gathers inside the MLP kernel), the A/B arm; it is also the
+    // path for buffers the TMA bulk copies cannot take (not 16-byte aligned)
+    const char* fusedEnv = getenv("GFX_NRC_INFER_FUSED");
+    const bool aligned = (reinterpret_cast<uintptr_t>(inputData) & 15u) == 0 && (reinterpret_cast<uintptr_t>(predictionData) & 15u) == 0;
+    if ((fusedEnv && fusedEnv[0] == '1') || !aligned) {
+        const size_t smem = kATileBytes + (size_t)n->numMatrixWeights * 2;
+        NRC_CUDA(n, cudaFuncSetAttribute(k_nrcInfer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const uint32_t grid = numTiles < (uint32_t)sms * 6 ? numTiles : (uint32_t)sms * 6;
+        GFX_TIMED(n->ctx, s, "nrc_infer");
+        k_nrcInfer<<<grid, 128, smem, s>>>(n->levels, n->paramsEma + n->numMatrixWeights, n->ummaWeights, n->numHiddenLayers,
+                                           inputData, predictionData, numData, numDataPtr);
+        n->ctx->launches++;
+        NRC_CUDA(n, cudaGetLastError());
+        return GFX_OK;
+    }
+    int rc = nrcEnsureScratch(n, numData);
+    if (rc != GFX_OK)
+        return rc;
+    rc = nrcGridEncodeLaunch(n, s, inputData, numData, numDataPtr, true);
+    if (rc != GFX_OK)
+        return rc;
+    const size_t smem = kATileBytes + 2 * sizeof(NrcTileStage) + 128 * kOutputDims * 4 + (size_t)n->numMatrixWeights * 2;
+    NRC_CUDA(n, cudaFuncSetAttribute(k_nrcInferMlp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint32_t ctasPerSm = (uint32_t)(220 * 1024 / (smem + 1024));
+    const uint32_t maxGrid = (uint32_t)sms * (ctasPerSm ? ctasPerSm : 1u);
+    const uint32_t grid = numTiles < maxGrid ? numTiles : maxGrid;
     GFX_TIMED(n->ctx, s, "nrc_infer");
-    k_nrcInfer<<<grid, 128, smem, s>>>(n->levels, n->paramsEma + n->numMatrixWeights, n->ummaWeights, n->numHiddenLayers,
-                                       inputData, predictionData, numData, numDataPtr);
+    k_nrcInferMlp<<<grid, 128, smem, s>>>(n->ummaWeights, n->numHiddenLayers, inputData, n->features, predictionData, numData, numDataPtr);
+    n->ctx->launches++;
+    NRC_CUDA(n, cudaGetLastError());
+    return GFX_OK;
+}
+
+// test hook (gfx_nrc_encode_debug): the encoded network input of numData queries, [numData][64] halves, through the split path
+static int nrcEncodeDebug(gfx_nrc* n, cudaStream_t s, const float* inputData, uint32_t numData, void* outHalf) {
+    int rc = nrcEnsureScratch(n, numData);
+    if (rc != GFX_OK)
+        return rc;
+    rc = nrcGridEncodeLaunch(n, s, inputData, numData, nullptr, true);
+    if (rc != GFX_OK)
+        return rc;
+    k_nrcAssembleEncoding<<<(numData + 127) / 128, 128, 0, s>>>(inputData, n->features, numData, reinterpret_cast<__half*>(outHalf));
     n->ctx->launches++;
     NRC_CUDA(n, cudaGetLastError());
     return GFX_OK;
@@ -1245,6 +1636,14 @@ int gfx_nrc_infer(gfx_nrc* n, void* stream, const float* inputData, float* predi
     if (numData == 0)
         return GFX_OK;
     return nrcInferLaunch(n, (cudaStream_t)stream, inputData, predictionData, numData, nullptr);
+}
+
+int gfx_nrc_encode_debug(gfx_nrc* n, void* stream, const float* inputData, uint32_t numData, void* outHalf) {
+    if (!n || !inputData || !outHalf || (numData & 0x7F))
+        return GFX_ERR_INVALID_ARGUMENT;
+    if (numData == 0)
+        return GFX_OK;
+    return nrcEncodeDebug(n, (cudaStream_t)stream, inputData, numData, outHalf);
 }
 
 int gfx_nrc_frame_infer(gfx_ctx* ctx, gfx_nrc* n, void* stream) {

@@ -100,6 +100,7 @@ struct DevScene {
     // geometry g or 0xFFFFFFFF
     const float4* lightTris;
     const uint32_t* lightTriBase;
+    uint32_t numLightTris;
     // flattened light pick: guide[b] for ul in [b, b + 1) / kPickGuideSize is kPickPure | key, or the index of the piece that
     // holds the bucket's first float; pieces = (first float bit pattern, key) sorted by start, terminated by 0xFFFFFFFF starts
     const uint32_t* pickGuide;

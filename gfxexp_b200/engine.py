@@ -303,6 +303,15 @@ class NeuralRadianceCache:
         self.ctx._check(self.ctx.lib.gfx_nrc_get_params(self.h, out.ctypes.data, out.nbytes), "gfx_nrc_get_params")
         return out
 
+    def encode(self, queries, num_data: int, stream=None) -> np.ndarray:
+        """test hook: the encoded network input [num_data][64] float16 as the inference kernels produce it"""
+        import torch
+        out = torch.empty((num_data, 64), dtype=torch.float16, device="cuda")
+        self.ctx._check(self.ctx.lib.gfx_nrc_encode_debug(self.h, stream, self._ptr(queries), num_data, out.data_ptr()),
+                        "gfx_nrc_encode_debug")
+        torch.cuda.synchronize()
+        return out.cpu().numpy()
+
     def reset(self, seed: int = 1337):
         """re-initialise like a fresh tcnn::Trainer with this seed (gfx_nrc_create does it with 1337, the reference's)"""
         self.ctx._check(self.ctx.lib.gfx_nrc_reset(self.h, seed), "gfx_nrc_reset")

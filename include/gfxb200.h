@@ -456,6 +456,9 @@ int gfx_nrc_reset(gfx_nrc* nrc, uint32_t seed);
 #define GFX_NRC_READ_GRADIENTS 3
 int gfx_nrc_read(gfx_nrc* nrc, int which, void* hostOut, size_t bytes);
 int gfx_nrc_keep_gradients(gfx_nrc* nrc, int on);
+/* test hook: the encoded network input (HashGrid 32 | OneBlob 20 | Identity 6 | ones 6 = 64 halves per query; kernel_grid
+ * grid.h:132-255, kernel_one_blob_soa oneblob.h:110-139) of numData DEVICE queries as gfx_nrc_infer's kernels produce it */
+int gfx_nrc_encode_debug(gfx_nrc* nrc, void* stream, const float* inputData, uint32_t numData, void* outHalf);
 /* inference (EMA) weights as halves; gfx_nrc_set_params installs the same values as training, inference and master weights and
  * clears the optimizer state */
 int gfx_nrc_get_params(gfx_nrc* nrc, void* hostHalfParams, size_t bytes);

@@ -52,8 +52,8 @@ def test_flat_pick_equals_the_sampling_chain(gfx_ctx, scene_name):
     _check(gfx_ctx, np.arange(0, n, dtype=np.uint32).view(np.float32), "denormals")
     # guide-bucket edges +- 2 floats
     j = np.arange(1, 1 << 17, dtype=np.uint32)
-    edges = (j.astype(np.float32) / np.float32(1 << 17)).view(np.uint32)
-    around = np.concatenate([edges + np.uint32(d) for d in (-2, -1, 0, 1, 2)]).astype(np.uint32)
+    edges = (j.astype(np.float32) / np.float32(1 << 17)).view(np.uint32).astype(np.int64)
+    around = np.concatenate([edges + d for d in (-2, -1, 0, 1, 2)]).astype(np.uint32)
     _check(gfx_ctx, around.view(np.float32), "bucket edges")
     # piece boundaries: bisect between lattice neighbours with different keys down to adjacent floats, check +-2 around them
     order = np.argsort(lattice.view(np.uint32))

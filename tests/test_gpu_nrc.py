@@ -42,6 +42,50 @@ def test_inference_matches_oracle(gfx_ctx, oracle, hidden, amp):
     gnet.close()
 
 
+def test_split_encoding_is_bit_exact(gfx_ctx, oracle):
+    """the encoded network input of the split inference path (positions packed, one hash-grid level per CTA with the level's
+    table staged in shared memory by TMA, one-blob + identity in the MLP kernel) equals the oracle's - which is pinned bit for
+    bit against tiny-cuda-nn's kernel_grid / kernel_one_blob_soa (tests/test_gpu_tcnn_ref.py) - in every half"""
+    import torch
+    onet = oracle.OracleNrc(2, 1e-2)
+    params = engine.random_nrc_params(onet.num_params, onet.num_matrix_weights, seed=3, grid_amplitude=0.5)
+    onet.set_params(params)
+    gnet = engine.NeuralRadianceCache(gfx_ctx, 2, 1e-2)
+    gnet.set_params(params)
+    n = 128 * 150 + 128  # not a multiple of the replica count
+    q = _queries(n, 9)
+    rng = np.random.default_rng(4)
+    q[:64, :3] = 0.0
+    q[64:128, :3] = 1.0
+    q[128:256, :3] = (rng.integers(0, 17, size=(128, 3)) / 16.0).astype(np.float32)   # level-0 cell corners
+    q[256:384, :3] = (rng.integers(0, 513, size=(128, 3)) / 512.0).astype(np.float32)  # finer cell corners
+    q[384:512, 3:8] = rng.choice([0.0, 0.25, 0.5, 0.75, 1.0], size=(128, 5)).astype(np.float32)
+    got = gnet.encode(torch.from_numpy(q).cuda(), n).view(np.uint16)
+    want = onet.encode(q).view(np.uint16).reshape(n, 64)
+    bad = np.argwhere(got != want)
+    assert bad.size == 0, f"{len(bad)} halves differ, first {bad[:5].tolist()}"
+    gnet.close()
+
+
+def test_fused_and_split_inference_agree(gfx_ctx, monkeypatch):
+    """GFX_NRC_INFER_FUSED=1 (hash-grid gathers from L2 inside the MLP kernel, the A/B arm) and the default split path feed the
+    same halves to the same tcgen05 MLP: identical radiance"""
+    import torch
+    gnet = engine.NeuralRadianceCache(gfx_ctx, 2, 1e-2)
+    gnet.set_params(engine.random_nrc_params(gnet.num_params, 64 * 64 * 2 + 16 * 64, seed=5, grid_amplitude=0.5))
+    n = 128 * 77
+    dq = torch.from_numpy(_queries(n, 2)).cuda()
+    a = torch.empty((n, 3), device="cuda")
+    b = torch.empty((n, 3), device="cuda")
+    gnet.infer(dq, a, n)
+    monkeypatch.setenv("GFX_NRC_INFER_FUSED", "1")
+    gnet.infer(dq, b, n)
+    monkeypatch.delenv("GFX_NRC_INFER_FUSED")
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+    gnet.close()
+
+
 def test_infer_rejects_unpadded_batch(gfx_ctx):
     import torch
     gnet = engine.NeuralRadianceCache(gfx_ctx, 2, 1e-2)

@@ -8,9 +8,8 @@
 set -u
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
 cd "$ROOT"
-declare -A FLAGS=( [wide]="-DGFX_WIDE_TABLE_LOADS=1" [push]="-DGFX_TRAVERSE_PREDICATED_PUSH=1"
-                   [spheres]="-DGFX_LIGHT_CULL_SPHERES=1 -DGFX_WIDE_TABLE_LOADS=1"
-                   [all]="-DGFX_WIDE_TABLE_LOADS=1 -DGFX_TRAVERSE_PREDICATED_PUSH=1 -DGFX_LIGHT_CULL_SPHERES=1" )
+declare -A FLAGS=( [nosphere]="-DGFX_AB_NO_SPHERE" [chainpick]="-DGFX_AB_CHAIN_PICK" [push]="-DGFX_TRAVERSE_PREDICATED_PUSH=1" )
+if [ -n "${AB_ONLY:-}" ]; then for k in "${!FLAGS[@]}"; do [[ " $AB_ONLY " == *" $k "* ]] || unset "FLAGS[$k]"; done; fi
 if [ "${1:-}" = "build" ]; then
     mkdir -p build_ab
     for v in "${!FLAGS[@]}"; do
