@@ -15,7 +15,7 @@ void SceneState::release() {
     cudaFree(primWeights); cudaFree(primCdf); cudaFree(geomWeights); cudaFree(geomCdf);
     cudaFree(instWeights); cudaFree(instCdf); cudaFree(instIntegral);
     cudaFree(primProb); cudaFree(geomProb); cudaFree(instProb); cudaFree(lightTris); cudaFree(lightTriBase); cudaFree(emissiveGeoms); cudaFree(instGuide); cudaFree(primGuide);
-    cudaFree(pickGuide); cudaFree(pickPieces); cudaFree(pickKeyAt); cudaFree(pickBoundaries); cudaFree(pickCounters); cudaFree(pickSortTemp);
+    cudaFree(pickGuide); cudaFree(normalMats); cudaFree(pickPieces); cudaFree(pickKeyAt); cudaFree(pickBoundaries); cudaFree(pickCounters); cudaFree(pickSortTemp);
     if (pickFlagsHost) cudaFreeHost(pickFlagsHost);
     if (pickFlagsEvent) cudaEventDestroy(pickFlagsEvent);
     for (int i = 0; i < 2; ++i) {
@@ -140,6 +140,7 @@ DevScene gfx_ctx::devScene() const {
     d.numLightTris = scene.numLightTris;
     d.pickGuide = scene.pickGuide;
     d.pickPieces = scene.pickPieces;
+    d.normalMats = scene.normalMats;
     d.instGuide = scene.instGuide;
     d.primGuide = scene.primGuide;
     d.numInstances = scene.numInstances;
@@ -360,8 +361,9 @@ int gfx_scene_upload(gfx_ctx* ctx, const GfxSceneDesc* sd) {
     GFX_CUDA(ctx, cudaMalloc(&S.primGuide, (size_t)(sd->numMeshes ? sd->numMeshes : 1) * (kPrimGuideSize + 1) * 4));
     // flattened light pick: every reachable (instance, geometry, primitive) position is one piece at most
     S.pickCapacity = numLightTris + sd->numInstanceMeshSlots + sd->numInstances + 64;
-    GFX_CUDA(ctx, cudaMalloc(&S.pickGuide, (size_t)kPickGuideSize * 4));
-    GFX_CUDA(ctx, cudaMemset(S.pickGuide, 0xC0, (size_t)kPickGuideSize * 4)); // kPickPure | kPickNone until the first build
+    GFX_CUDA(ctx, cudaMalloc(&S.pickGuide, (size_t)kPickGuideSize * 32));
+    GFX_CUDA(ctx, cudaMemset(S.pickGuide, 0xC0, (size_t)kPickGuideSize * 32)); // kPickPure | kPickNone until the first build
+    GFX_CUDA(ctx, cudaMalloc(&S.normalMats, (size_t)(sd->numInstances ? sd->numInstances : 1) * kNormalMatStride * 16));
     GFX_CUDA(ctx, cudaMalloc(&S.pickPieces, ((size_t)S.pickCapacity + 2) * 8));
     GFX_CUDA(ctx, cudaMemset(S.pickPieces, 0xFF, ((size_t)S.pickCapacity + 2) * 8));
     GFX_CUDA(ctx, cudaMalloc(&S.pickKeyAt, ((size_t)kPickGuideSize + 1) * 4));

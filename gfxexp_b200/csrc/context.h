@@ -39,7 +39,8 @@ struct SceneState {
     bool staticLightDistsBuilt = false;
     bool lightTrisDirty = true;
     // flattened light pick (scene.cuh, lights.cu): tables + the scratch its stream-ordered rebuild needs
-    uint32_t* pickGuide = nullptr;         // kPickGuideSize
+    float4* pickGuide = nullptr;           // 2 x kPickGuideSize
+    float4* normalMats = nullptr;          // kNormalMatStride x numInstances
     uint2* pickPieces = nullptr;           // pickCapacity + 2
     uint32_t* pickKeyAt = nullptr;         // kPickGuideSize + 1
     uint4* pickQueue[2] = { nullptr, nullptr };

@@ -56,11 +56,28 @@ GFX_D float remapCdf(const float* __restrict__ cdf, uint32_t numValues, float in
     return (u - lCDF) / (rCDF - lCDF);
 }
 
-// the normal matrix of an instance: two 128-bit loads + one scalar (DevInstance::normalMatrix starts a 16-byte line)
-GFX_D f3 applyNormalMatrix(const DevInstance* inst, const f3 &n) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(inst->normalMatrix));
-    const float4 b = __ldg(reinterpret_cast<const float4*>(inst->normalMatrix) + 1);
-    const float m[9] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, __ldg(inst->normalMatrix + 8) };
+// sm_100's 256-bit read-only load (LDG.E.256): one L1 tag lookup for 32 bytes.  volatile: ptxas would otherwise hoist the
+// later stages' loads of sampleLightUnlessDark above the dark tests (it did, ncu round 2: all nine record loads were issued by
+// every survivor of the sphere test), which is exactly the traffic the staging is there to avoid.
+struct F8 { float4 lo, hi; };
+GFX_D F8 ldg256(const float4* p) {
+    F8 r;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
+                 : "l"(p));
+    return r;
+}
+GFX_D float ldg32v(const float* p) {
+    float r;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+
+// the normal matrix of an instance out of the compact table (scene.cuh): one 256-bit load + one scalar
+GFX_D f3 applyNormalMatrix(const DevScene &s, uint32_t instSlot, const f3 &n) {
+    const float4* mp = s.normalMats + (size_t)kNormalMatStride * instSlot;
+    const F8 a = ldg256(mp);
+    const float m[9] = { a.lo.x, a.lo.y, a.lo.z, a.lo.w, a.hi.x, a.hi.y, a.hi.z, a.hi.w, ldg32v(reinterpret_cast<const float*>(mp + 2)) };
     return mul3x3(m, n);
 }
 
@@ -111,18 +128,39 @@ GFX_D uint32_t chainPickLightTriangle(const DevScene &s, float ul, float* lightP
     return base + primIndex;
 }
 
-// The flattened pick (scene.cuh, lights.cu): key of the piece that contains ul.
-GFX_D uint32_t pickLightTriangle(const DevScene &s, float ul) {
+// The flattened pick (scene.cuh, lights.cu): the piece that contains ul - its key and the head of its light record (cull
+// sphere, area density, instance slot), which for a pure bucket arrives with the guide entry itself.
+struct LightPick {
+    uint32_t key;      // light record index, or kPickNone set
+    float4 sphere;     // centre, radius (< 0: do not cull)
+    float density;     // lightProb * recArea
+    uint32_t instSlot;
+};
+GFX_D LightPick pickLight(const DevScene &s, float ul) {
+    LightPick r;
 #ifdef GFX_AB_CHAIN_PICK // A/B: the definition instead of its flattened form
     float unusedProb;
-    return chainPickLightTriangle(s, ul, &unusedProb);
+    r.key = chainPickLightTriangle(s, ul, &unusedProb);
+    if (!(r.key & kPickNone)) {
+        const F8 h0 = ldg256(s.lightTris + kLightTriStride * (size_t)r.key);
+        r.sphere = h0.lo;
+        r.density = h0.hi.x;
+        r.instSlot = __float_as_uint(h0.hi.y);
+    }
+    return r;
 #endif
     const uint32_t b = min(dm_f2uint(ul * (float)kPickGuideSize), kPickGuideSize - 1); // exact: a power-of-two product, floored
-    const uint32_t g = __ldg(s.pickGuide + b);
-    if (g & kPickPure)
-        return g & ~kPickPure;
+    const F8 g = ldg256(s.pickGuide + 2 * (size_t)b);
+    const uint32_t head = __float_as_uint(g.lo.x);
+    if (head & kPickPure) {
+        r.key = head & ~kPickPure;
+        r.sphere = make_float4(g.lo.y, g.lo.z, g.lo.w, g.hi.x);
+        r.density = g.hi.y;
+        r.instSlot = __float_as_uint(g.hi.z);
+        return r;
+    }
     const uint32_t ulBits = __float_as_uint(ul);
-    uint32_t idx = g;
+    uint32_t idx = head;
     uint2 piece = __ldg(s.pickPieces + idx);
     for (;;) {
         const uint2 next = __ldg(s.pickPieces + idx + 1);
@@ -131,8 +169,19 @@ GFX_D uint32_t pickLightTriangle(const DevScene &s, float ul) {
         piece = next;
         ++idx;
     }
-    return piece.y;
+    r.key = piece.y;
+    r.sphere = make_float4(0.0f, 0.0f, 0.0f, -1.0f);
+    r.density = 0.0f;
+    r.instSlot = 0;
+    if (!(r.key & kPickNone)) {
+        const F8 h0 = ldg256(s.lightTris + kLightTriStride * (size_t)r.key);
+        r.sphere = h0.lo;
+        r.density = h0.hi.x;
+        r.instSlot = __float_as_uint(h0.hi.y);
+    }
+    return r;
 }
+GFX_D uint32_t pickLightTriangle(const DevScene &s, float ul) { return pickLight(s, ul).key; }
 
 // A Low-Distortion Map Between Triangle and Square (restir_di_shared.h:485-498)
 GFX_D void squareToTriangle(float u0, float u1, float* bcA, float* bcB, float* bcC) {
@@ -151,37 +200,37 @@ GFX_D void squareToTriangle(float u0, float u1, float* bcA, float* bcB, float* b
 GFX_D void sampleLight(const DevScene &s, float ul, float u0, float u1, LightSample* lightSample, float* areaPDensity) {
     // restir_di_shared.h:320-516 with sampleEnvLight = false, useSolidAngleSampling = false; the triangle operands come
     // from the light records (lights.cu), produced by the reference's own expressions, so the result is bit-identical.
-    const uint32_t key = pickLightTriangle(s, ul);
-    if (key & kPickNone) {
+    const LightPick pick = pickLight(s, ul);
+    if (pick.key & kPickNone) {
         *areaPDensity = 0.0f;
         return;
     }
-    const float4* e = s.lightTris + kLightTriStride * (size_t)key;
-    const float4 e1 = __ldg(e + 1), e2 = __ldg(e + 2), e3 = __ldg(e + 3), e4 = __ldg(e + 4), e5 = __ldg(e + 5), e6 = __ldg(e + 6);
-    const f3 pA(e1.x, e1.y, e1.z), pB(e2.x, e2.y, e2.z), pC(e3.x, e3.y, e3.z);
-    const f3 nA(e4.x, e4.y, e4.z), nB(e4.w, e5.x, e5.y), nC(e5.z, e5.w, e6.x);
+    const float4* e = s.lightTris + kLightTriStride * (size_t)pick.key;
+    const F8 h1 = ldg256(e + 2), h2 = ldg256(e + 4), h3 = ldg256(e + 6);
+    const f3 pA(h1.lo.x, h1.lo.y, h1.lo.z), pB(h1.lo.w, h1.hi.x, h1.hi.y), pC(h1.hi.z, h1.hi.w, h2.lo.x);
+    const f3 nA(h2.lo.y, h2.lo.z, h2.lo.w), nB(h2.hi.x, h2.hi.y, h2.hi.z), nC(h2.hi.w, h3.lo.x, h3.lo.y);
     float bcA, bcB, bcC;
     squareToTriangle(u0, u1, &bcA, &bcB, &bcC);
 
-    const float recArea = e1.w;
-    *areaPDensity = e2.w * recArea;
+    *areaPDensity = pick.density;
 
     lightSample->position = bcA * pA + bcB * pB + bcC * pC;
     lightSample->atInfinity = 0;
     lightSample->normal = bcA * nA + bcB * nB + bcC * nC;
-    lightSample->normal = normalize(applyNormalMatrix(s.instances + __float_as_uint(e3.w), lightSample->normal));
-    lightSample->emittance = f3(e6.y, e6.z, e6.w);
+    lightSample->normal = normalize(applyNormalMatrix(s, pick.instSlot, lightSample->normal));
+    lightSample->emittance = f3(h3.lo.z, h3.lo.w, h3.hi.x);
 }
 
-// sampleLight for the RIS candidate loop, fetching the 128-byte light record in three steps and stopping as soon as
-// the candidate is certain to contribute RGB(0) to this shading point.  ncu (round 1): the candidate kernel ran the L1 data
-// pipe at 80-84 % of its wavefront rate - every lane reads a different light, so every load instruction of the sampling chain
-// is up to 32 wavefronts - and ~70 % of the candidates are dark (65 % lie below the shading horizon).
-//   step 0: the bounding sphere of the light triangle (16 bytes).  Wholly below the shading horizon -> dark;
-//   step 1: the three vertices -> sample position.  Below the shading horizon (the BRDFs return RGB(0) when
+// sampleLight for the RIS candidate loop, fetching the 128-byte light record in steps and stopping as soon as the candidate is
+// certain to contribute RGB(0) to this shading point.  ncu: the candidate kernel is bound by the L1 data pipe's wavefront rate
+// (every lane reads a different light, so every load instruction of the sampling chain is up to 32 wavefronts) and by issue
+// slots; ~70 % of the candidates are dark (65 % lie below the shading horizon).
+//   step 0: the bounding sphere of the light triangle - it arrived with the pick (guide entry).  Wholly below the shading
+//           horizon -> dark, no further load;
+//   step 1: the three vertices (2 x 256 bits) -> sample position.  Below the shading horizon (the BRDFs return RGB(0) when
 //           vGiven.z * vSampled.z <= 0)?  -> dark;
-//   step 2: the vertex normals and the instance's normal matrix -> un-normalised light normal.  Facing away (lpCos <= 0)?
-//           -> dark; otherwise the emittance, the normalisation: the full sample.
+//   step 2: the vertex normals, the emittance (256 bits) and the instance's normal matrix (256 + 32 bits) -> un-normalised light
+//           normal.  Facing away (lpCos <= 0)? -> dark; otherwise the normalisation: the full sample.
 // The tests run on un-normalised vectors with a relative margin of 1e-3 on the cosine (the sphere test with twice that, so
 // that every sample point of the triangle would pass the per-sample test too; tests/cpp/sphere_cull_check.cpp) - three orders
 // of magnitude above the rounding of the exact evaluation - so borderline samples go on to the exact path and no decision ever
@@ -189,18 +238,16 @@ GFX_D void sampleLight(const DevScene &s, float ul, float u0, float u1, LightSam
 // (then *areaPDensity is positive); otherwise the outputs are sampleLight's, bit for bit.
 GFX_D bool sampleLightUnlessDark(const DevScene &s, float ul, float u0, float u1, const f3 &shadingPoint,
                                  const f3 &shadingNormal, float vOutLocalZ, LightSample* lightSample, float* areaPDensity) {
-    const uint32_t key = pickLightTriangle(s, ul);
-    if (key & kPickNone) {
+    const LightPick pick = pickLight(s, ul);
+    if (pick.key & kPickNone) {
         *areaPDensity = 0.0f;
         return false;
     }
-    const float4* e = s.lightTris + kLightTriStride * (size_t)key;
     {   // step 0: the whole triangle lies below the shading horizon if its bounding sphere does:
         //   -dot(q - p, n) sgn >= t - r |n|  and  |q - p| <= |c - p| + r   for every q in the sphere
         // (radius >= 0 also says that the selection density of this light is a positive finite number)
-        const float4 sphere = __ldg(e + 0);
-        const f3 dc = f3(sphere.x, sphere.y, sphere.z) - shadingPoint;
-        const float r = sphere.w;
+        const f3 dc = f3(pick.sphere.x, pick.sphere.y, pick.sphere.z) - shadingPoint;
+        const float r = pick.sphere.w;
         const float t = -(dot(dc, shadingNormal) * vOutLocalZ);          // > 0: centre on the far side of the surface
         const float margin = t - 1.001f * r * fabsf(vOutLocalZ);
 #ifdef GFX_AB_NO_SPHERE
@@ -213,12 +260,12 @@ GFX_D bool sampleLightUnlessDark(const DevScene &s, float ul, float u0, float u1
             return true;
         }
     }
-    const float4 e1 = __ldg(e + 1), e2 = __ldg(e + 2), e3 = __ldg(e + 3);
-    const f3 pA(e1.x, e1.y, e1.z), pB(e2.x, e2.y, e2.z), pC(e3.x, e3.y, e3.z);
+    const float4* e = s.lightTris + kLightTriStride * (size_t)pick.key;
+    const F8 h1 = ldg256(e + 2), h2 = ldg256(e + 4);
+    const f3 pA(h1.lo.x, h1.lo.y, h1.lo.z), pB(h1.lo.w, h1.hi.x, h1.hi.y), pC(h1.hi.z, h1.hi.w, h2.lo.x);
     float bcA, bcB, bcC;
     squareToTriangle(u0, u1, &bcA, &bcB, &bcC);
-    const float recArea = e1.w;
-    const float density = e2.w * recArea;
+    const float density = pick.density;
     *areaPDensity = density;
     const f3 position = bcA * pA + bcB * pB + bcC * pC;
 
@@ -229,12 +276,10 @@ GFX_D bool sampleLightUnlessDark(const DevScene &s, float ul, float u0, float u1
     if (density > 0.0f && b < 0.0f && b * b > k * dd * (vOutLocalZ * vOutLocalZ))
         return true;
 
-    const float4 e4 = __ldg(e + 4), e5 = __ldg(e + 5);
-    const f3 nA(e4.x, e4.y, e4.z), nB(e4.w, e5.x, e5.y);
-    const float4 e6 = __ldg(e + 6);
-    const f3 nC(e5.z, e5.w, e6.x);
+    const F8 h3 = ldg256(e + 6);
+    const f3 nA(h2.lo.y, h2.lo.z, h2.lo.w), nB(h2.hi.x, h2.hi.y, h2.hi.z), nC(h2.hi.w, h3.lo.x, h3.lo.y);
     f3 normal = bcA * nA + bcB * nB + bcC * nC;
-    normal = applyNormalMatrix(s.instances + __float_as_uint(e3.w), normal);
+    normal = applyNormalMatrix(s, pick.instSlot, normal);
     const float a = dot(d, normal); // > 0: the emitter faces away from the shading point
     if (density > 0.0f && a > 0.0f && a * a > k * dd * sqLength(normal))
         return true;
@@ -242,7 +287,7 @@ GFX_D bool sampleLightUnlessDark(const DevScene &s, float ul, float u0, float u1
     lightSample->position = position;
     lightSample->atInfinity = 0;
     lightSample->normal = normalize(normal);
-    lightSample->emittance = f3(e6.y, e6.z, e6.w);
+    lightSample->emittance = f3(h3.lo.z, h3.lo.w, h3.hi.x);
     return false;
 }
 

@@ -164,13 +164,13 @@ __global__ void k_lightTris(DevScene scene, const uint32_t* __restrict__ emissiv
         const bool usable = recArea > 0.0f && isfinite(recArea) && isfinite(r2);
         const float radius = usable ? sqrtf(r2) * 1.0001f + 1e-30f : -1.0f;
         o[0] = make_float4(c.x, c.y, c.z, -1.0f);   // k_pickLightProbs switches the cull on once the density is known
-        o[1] = make_float4(pA.x, pA.y, pA.z, recArea);
-        o[2] = make_float4(pB.x, pB.y, pB.z, 0.0f); // lightProb: k_pickLightProbs
-        o[3] = make_float4(pC.x, pC.y, pC.z, __uint_as_float(im.x));
-        o[4] = make_float4(a1.x, a1.y, a1.z, b1.x);
-        o[5] = make_float4(b1.y, b1.z, c1.x, c1.y);
-        o[6] = make_float4(c1.z, emittance.x, emittance.y, emittance.z);
-        o[7] = make_float4(radius, 0.0f, 0.0f, 0.0f);
+        o[1] = make_float4(0.0f, __uint_as_float(im.x), recArea, 0.0f); // density: k_pickLightProbs; recArea parked in .z for it
+        o[2] = make_float4(pA.x, pA.y, pA.z, pB.x);
+        o[3] = make_float4(pB.y, pB.z, pC.x, pC.y);
+        o[4] = make_float4(pC.z, a1.x, a1.y, a1.z);
+        o[5] = make_float4(b1.x, b1.y, b1.z, c1.x);
+        o[6] = make_float4(c1.y, c1.z, emittance.x, emittance.y);
+        o[7] = make_float4(emittance.z, radius, 0.0f, 0.0f);
     }
 }
 
@@ -264,9 +264,9 @@ __global__ void k_pickResetQueue(PickWork w, int q, int last) {
     w.counters[q] = 0;
 }
 
-// guide entry of bucket j from the sorted pieces
-__global__ void k_pickGuide(const uint2* __restrict__ pieces, const uint32_t* __restrict__ counters, uint32_t capacity,
-                            uint32_t* __restrict__ guide) {
+// guide entry of bucket j from the sorted pieces (after k_pickLightProbs: a pure bucket copies its light's H0)
+__global__ void k_pickGuide(DevScene scene, const uint2* __restrict__ pieces, const uint32_t* __restrict__ counters, uint32_t capacity,
+                            float4* __restrict__ guide) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= kPickGuideSize)
         return;
@@ -282,7 +282,32 @@ __global__ void k_pickGuide(const uint2* __restrict__ pieces, const uint32_t* __
             hi = mid;
     }
     const bool pure = lo + 1 >= numPieces || pieces[lo + 1].x > last;
-    guide[j] = pure ? (kPickPure | pieces[lo].y) : lo;
+    float4 g0 = make_float4(__uint_as_float(lo), 0.0f, 0.0f, 0.0f), g1 = make_float4(-1.0f, 0.0f, 0.0f, 0.0f);
+    if (pure) {
+        const uint32_t key = pieces[lo].y;
+        g0.x = __uint_as_float(kPickPure | key);
+        if (!(key & kPickNone)) {
+            const float4* rec = scene.lightTris + kLightTriStride * (size_t)key;
+            const float4 q0 = rec[0], q1 = rec[1];
+            g0.y = q0.x; g0.z = q0.y; g0.w = q0.z;
+            g1 = make_float4(q0.w, q1.x, q1.y, 0.0f);
+        }
+    }
+    guide[2 * (size_t)j] = g0;
+    guide[2 * (size_t)j + 1] = g1;
+}
+
+// compact normal-matrix table (scene.cuh)
+__global__ void k_normalMats(DevScene scene, uint32_t numInstances) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= numInstances)
+        return;
+    const float* m = scene.instances[i].normalMatrix;
+    float4* o = const_cast<float4*>(scene.normalMats) + (size_t)kNormalMatStride * i;
+    o[0] = make_float4(m[0], m[1], m[2], m[3]);
+    o[1] = make_float4(m[4], m[5], m[6], m[7]);
+    o[2] = make_float4(m[8], 0.0f, 0.0f, 0.0f);
+    o[3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 }
 
 // selection probability of every reachable light (the chain's own product, taken at the first float of its piece) and the
@@ -302,10 +327,10 @@ __global__ void k_pickLightProbs(DevScene scene, const uint2* __restrict__ piece
         return;
     }
     float4* rec = const_cast<float4*>(scene.lightTris) + kLightTriStride * (size_t)key;
-    const float recArea = rec[1].w;
-    const float density = lightProb * recArea;
-    rec[2].w = lightProb;
-    rec[0].w = (density > 0.0f && isfinite(density)) ? rec[7].x : -1.0f;
+    const float recArea = rec[1].z;
+    const float density = lightProb * recArea; // sampleLight's areaPDensity (restir_di_shared.h:409,496), the one product
+    rec[1].x = density;
+    rec[0].w = (density > 0.0f && isfinite(density)) ? rec[7].y : -1.0f;
 }
 
 // debug / test entry: flattened and chain pick of arbitrary ul values side by side
@@ -437,8 +462,9 @@ int buildLightPick(gfx_ctx* ctx, cudaStream_t stream) {
     ctx->launches += 3;
     GFX_CUDA(ctx, cudaMemcpy2DAsync(&S.pickPieces[0].x, 8, S.pickSortKeys[1], 4, 4, S.pickCapacity, cudaMemcpyDeviceToDevice, stream));
     GFX_CUDA(ctx, cudaMemcpy2DAsync(&S.pickPieces[0].y, 8, S.pickSortVals[1], 4, 4, S.pickCapacity, cudaMemcpyDeviceToDevice, stream));
-    k_pickGuide<<<kPickGuideSize / 256, 256, 0, stream>>>(S.pickPieces, S.pickCounters, S.pickCapacity, S.pickGuide); ctx->launches++;
     k_pickLightProbs<<<(S.pickCapacity + 255) / 256, 256, 0, stream>>>(dev, S.pickPieces, S.pickCounters, S.pickCapacity); ctx->launches++;
+    k_pickGuide<<<kPickGuideSize / 256, 256, 0, stream>>>(dev, S.pickPieces, S.pickCounters, S.pickCapacity, S.pickGuide); ctx->launches++;
+    k_normalMats<<<(S.numInstances + 127) / 128, 128, 0, stream>>>(dev, S.numInstances); ctx->launches++;
     GFX_CUDA(ctx, cudaMemcpyAsync(S.pickFlagsHost, S.pickCounters + 3, 4, cudaMemcpyDeviceToHost, stream));
     GFX_CUDA(ctx, cudaEventRecord(S.pickFlagsEvent, stream));
     S.pickFlagsPending = true;

@@ -30,24 +30,31 @@ struct DevMesh {
     uint32_t pad[3];
 };
 
-// Light records (lights.cu): one 128-byte, 128-byte-aligned record per triangle of every emissive geometry, i.e. ONE cache line
-// per RIS candidate, ordered so that sampleLightUnlessDark (lighting.cuh) can stop after the first 16 bytes for most candidates:
-//   q0 (centre.xyz, radius)   bounding sphere of the world-space triangle; radius < 0 = never cull (degenerate area, or the
-//                             selection density lightProb * recArea is not a positive finite number)
-//   q1 (pA.xyz, recArea)  q2 (pB.xyz, lightProb)  q3 (pC.xyz, instance slot)      -> sample position, area density
-//   q4 (nA.xyz, nB.x)     q5 (nB.yz, nC.xy)       q6 (nC.z, emittance.rgb)        -> light normal, emittance
-//   q7 unused
-// Positions, recArea, normals and emittance are produced by the very expressions of sampleLight (restir_di_shared.h:417-425,
-// 485-511) and lightProb by the products of DiscreteDistribution1D::sample's probabilities (:356-409), so reading them is
-// bit-identical to recomputing them.
+// Light records (lights.cu): one 128-byte, 128-byte-aligned record per triangle of every emissive geometry = ONE cache line per
+// RIS candidate, read with sm_100's 256-bit loads (LDG.E.256: one L1 tag lookup per 32 bytes per lane instead of two) in the
+// order sampleLightUnlessDark (lighting.cuh) needs them - ncu on the candidate kernel: every load of the sampling chain is a
+// divergent gather, i.e. one L1 wavefront per lane per instruction, so the number of load INSTRUCTIONS per candidate is what the
+// L1 data pipe charges for:
+//   H0 = q0 (centre.xyz, radius) q1 (density, instance slot, -, -)   cull sphere of the world-space triangle (radius < 0 = never
+//        cull: degenerate area, or the selection density lightProb * recArea is not a positive finite number) and the area
+//        density lightProb * recArea; a copy of H0 sits in the pick guide, so only the 6 % impure buckets read it from here
+//   H1 = q2 (pA.xyz, pB.x) q3 (pB.yz, pC.xy)     H2 = q4 (pC.z, nA.xyz) q5 (nB.xyz, nC.x)      -> sample position
+//   H3 = q6 (nC.yz, E.rg) q7 (E.b, radius before the density switch, -, -)                     -> light normal, emittance
+// Positions, normals, emittance are produced by the very expressions of sampleLight (restir_di_shared.h:417-425, 485-511),
+// the density by the products of DiscreteDistribution1D::sample's probabilities (:356-409) times 2 / |cross| (:496), so reading
+// them is bit-identical to recomputing them.
 constexpr uint32_t kLightTriStride = 8u; // float4 per light record
+// normal matrices of the instances, 64-byte stride (m0..m7 | m8, -, -, -): one 256-bit + one 32-bit load
+constexpr uint32_t kNormalMatStride = 4u; // float4 per instance
 
 // Flattened light pick (lights.cu, k_pick*): sampleLight's three nested DiscreteDistribution1D::sample calls (instance ->
 // geometry instance -> primitive, each a CDF search plus a remap of u) are a pure, monotone, piecewise-constant function of
 // the one random number ul.  Its pieces are found once per light-distribution change by evaluating the exact chain
 // (chainPickLightTriangle, lighting.cuh) at interval end points and refining every interval whose ends disagree, down to adjacent
 // floats; a candidate then costs one guide-table read (+ a short scan of the piece starts in the 6 % of buckets that hold a
-// boundary) instead of ~25 dependent loads.  Exact by construction for every float ul in [0, 1).
+// boundary) instead of ~25 dependent loads.  Exact by construction for every float ul in [0, 1).  A guide entry is 32 bytes:
+// (key or piece index, centre.xyz | radius, density, instance slot, -) - for a pure bucket the light's H0 rides along, so the
+// one 256-bit read also answers the bounding-sphere test.
 constexpr uint32_t kPickGuideBits = 17;
 constexpr uint32_t kPickGuideSize = 1u << kPickGuideBits;
 constexpr uint32_t kPickPure = 0x80000000u;      // guide entry: bit 31 set = the whole bucket maps to key (low 31 bits)
@@ -101,10 +108,12 @@ struct DevScene {
     const float4* lightTris;
     const uint32_t* lightTriBase;
     uint32_t numLightTris;
-    // flattened light pick: guide[b] for ul in [b, b + 1) / kPickGuideSize is kPickPure | key, or the index of the piece that
-    // holds the bucket's first float; pieces = (first float bit pattern, key) sorted by start, terminated by 0xFFFFFFFF starts
-    const uint32_t* pickGuide;
+    // flattened light pick: guide[b] (2 x float4) for ul in [b, b + 1) / kPickGuideSize: .x of the first = kPickPure | key, or
+    // the index of the piece that holds the bucket's first float; pieces = (first float bit pattern, key) sorted by start,
+    // terminated by 0xFFFFFFFF starts
+    const float4* pickGuide;
     const uint2* pickPieces;
+    const float4* normalMats;        // kNormalMatStride float4 per instance
     // guide tables for the CDF searches: guide[b] = search(cdf, fl(b / G * integral)), b = 0..G, so the
     // answer for u = fl(ul * integral) with ul in [b/G, (b+1)/G) lies in [guide[b], guide[b+1]]
     // (rounding is monotone) and a short scan finishes the exact search.
