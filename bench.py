@@ -15,7 +15,11 @@ One JSON line on stdout (rank 0).  `value` = rays traced by the whole job per se
 everything resident in HBM; `e2e` = the same through the C ABI with per-frame host->device uploads
 (instance table + parameter blocks from pinned memory) and the device->host read of the beauty
 framebuffer inside the timed region; `roofline` = the dominant kernel against the measured HBM
-peak; `cpu_baseline` = the oracle on the host cores on a bounded sample of the same frame.
+peak; `cpu_baseline` = the oracle on the host cores on a bounded sample of the same frame.  At N = 1 the
+line also carries the rest of BASELINE.json's metric, measured in the same process on the same scene:
+`nrc` (inference / training ms, TFLOP/s, fraction of the measured sustained bf16 tensor peak),
+`north_star_frame` (ReSTIR DI + NRC in one 1080p frame: ms, fps) and `svgf` (config 4: ms per frame,
+algorithmic GB/s, fraction of the measured HBM peak).
 """
 from __future__ import annotations
 
@@ -36,6 +40,7 @@ import numpy as np  # noqa: E402
 
 WIDTH, HEIGHT = 1920, 1080
 METRIC = "Mrays/s at 1920x1080 1spp (ReSTIR DI frame: 32 candidates, temporal + 1x4 spatial reuse)"
+WORKLOAD = "restir_di config 2: bistro_class synthetic scene 1920x1080 1spp, 32 candidates, temporal + 1x4 spatial reuse"
 
 
 def measured_peaks():
@@ -45,6 +50,17 @@ def measured_peaks():
             d = json.load(fh)
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def measured_tensor_peak():
+    """sustained bf16 TFLOP/s (a kernel timed inside a long step), else the recipe's fallback"""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        if "bf16_tflops_sustained" in d:
+            return float(d["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    return 1400.0, "fallback (B200_PROFILING.md ~1.4 PFLOP/s sustained)"
 
 
 class ClockSampler:
@@ -100,13 +116,15 @@ class ClockSampler:
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
-# (profiles/r01_summary.md): 114.7 + 143.0 MB for the RIS candidate kernel (r01f), 84.6 + 10.9 MB for the visibility trace
-NCU_DRAM_TRAFFIC = {"ris_candidates": 257.7e6, "trace_visibility": 95.5e6}
-# what actually bounds the dominant kernel (same capture): the L1 data pipe, not HBM
-NCU_NOTE = {"ris_candidates": {"l1tex_data_pipe_lsu_wavefronts_pct_of_peak": 79.6, "l1_load_wavefronts_per_launch": 422.3e6,
-                               "issue_active_pct": 54.3, "warps_active_pct": 36.1,
-                               "reading": "bound by L1 wavefronts of divergent table gathers (every lane samples a different "
-                                          "light); DRAM traffic equals the algorithmic bytes"}}
+# (profiles/r02_summary.md): RIS candidate kernel (r02c), visibility trace (r01f: unchanged kernel)
+NCU_DRAM_TRAFFIC = {"ris_candidates": 264.6e6, "trace_visibility": 95.5e6}
+# what actually bounds the dominant kernel (same capture): issue slots at ~15 of 32 lanes, then the L1 data pipe - not HBM
+NCU_NOTE = {"ris_candidates": {"capture": "gpurun_out/ris_r02c.ncu-rep (profiles/r02_summary.md)",
+                               "l1tex_data_pipe_lsu_wavefronts_pct_of_peak": 58.2, "l1_load_wavefronts_per_launch": 100.4e6,
+                               "issue_active_pct": 59.4, "warps_active_pct": 36.0, "lanes_per_instruction": 14.7,
+                               "reading": "bound by instruction issue at 14.7 of 32 active lanes (70 % of the candidates leave after "
+                                          "the staged light fetch) and by the L1 wavefronts of the divergent light-record gathers; "
+                                          "DRAM traffic equals the algorithmic bytes"}}
 
 
 def frame_launches(ctx, params, frame_index, num_spatial_passes, timers=None):
@@ -167,8 +185,42 @@ def cpu_reference_step(O, oframe, params, rows, halo, num_spatial_passes, thread
     return t
 
 
+def tcnn_reference_timing():
+    """The reference's own NRC kernels (tiny-cuda-nn built from /root/reference into oracle/_ref/libtcnn_nrc.so, see
+    oracle/ref_tcnn) timed on this GPU: ms per inference of a 1080p frame's queries and per 16 384-sample training step."""
+    path = os.path.join(ROOT, "oracle", "_ref", "libtcnn_nrc.so")
+    if not os.path.exists(path):
+        return {"unavailable": "oracle/_ref/libtcnn_nrc.so not built"}
+    try:
+        lib = C.CDLL(path)
+        vp, u32 = C.c_void_p, C.c_uint32
+        lib.tcnn_nrc_create.argtypes = [u32, u32, C.c_float, C.POINTER(vp)]
+        lib.tcnn_nrc_time_infer.argtypes = [vp, vp, u32, u32, u32, C.POINTER(C.c_float)]
+        lib.tcnn_nrc_time_train.argtypes = [vp, vp, vp, u32, u32, u32, C.POINTER(C.c_float)]
+        lib.tcnn_nrc_destroy.argtypes = [vp]
+        h = vp()
+        if lib.tcnn_nrc_create(1, 2, 1e-2, C.byref(h)) != 0:
+            return {"unavailable": "tcnn_nrc_create failed (no GPU?)"}
+        rng = np.random.default_rng(0)
+        n = ((WIDTH * HEIGHT + WIDTH * HEIGHT // 48 + 127) // 128) * 128
+        q = rng.uniform(0, 1, size=(n, 14)).astype(np.float32)
+        ms_inf, ms_tr = C.c_float(), C.c_float()
+        assert lib.tcnn_nrc_time_infer(h, q.ctypes.data, n, 3, 10, C.byref(ms_inf)) == 0
+        nt = 16384
+        tq, tt = q[:nt].copy(), rng.uniform(0, 1, size=(nt, 3)).astype(np.float32)
+        assert lib.tcnn_nrc_time_train(h, tq.ctypes.data, tt.ctypes.data, nt, 3, 20, C.byref(ms_tr)) == 0
+        lib.tcnn_nrc_destroy(h)
+        return {"kind": "reference (tiny-cuda-nn kernel_grid + kernel_one_blob_soa + kernel_mlp_fused, unmodified, sm_100a build)",
+                "infer_queries": n, "infer_ms": ms_inf.value, "infer_tflops": 18432.0 * n / ms_inf.value / 1e9,
+                "train_samples": nt, "train_step_ms": ms_tr.value, "train_tflops": 55296.0 * nt / ms_tr.value / 1e9}
+    except (OSError, AssertionError) as e:
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm (oracle port) on the host cores."""
+    """--impl reference: the reference's CPU algorithm (oracle port; the renderer of oracle/_ref is unbuildable) on the host
+    cores.  A step is the bounded sample itself - a full-width strip of --cpu-rows rows through every pass of the frame - and
+    `value` is the rays the oracle really traced in it per second; nothing is extrapolated into the timed numbers."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -180,29 +232,125 @@ def run_reference(args):
     oframe = O.OracleFrame(oscene, WIDTH, HEIGHT)
     params = abi.default_frame_params(scene, WIDTH, HEIGHT)
     rows, halo = args.cpu_rows, 24
-    rays_per_px = args.rays_per_px
-    times = []
+    times, rays, full_frame_s = [], [], []
     for it in range(args.warmup + args.steps):
+        O.rays_traced(reset=True)
+        t0 = time.perf_counter()
         t = cpu_reference_step(O, oframe, params, rows, halo, 1, threads)
+        dt = time.perf_counter() - t0
         if it >= args.warmup:
-            times.append(sum(t.values()))
-    frame_s = float(np.mean(times))
-    rays_per_frame = rays_per_px * WIDTH * HEIGHT
-    value = rays_per_frame / frame_s / 1e6
-    sample = (f"{rows}-row full-width strip (+{halo}-row halo for per-pixel passes) of the 1920x1080 frame per pass, "
-              f"scaled to the full frame by rows; rays/frame = {rays_per_px:.3f} rays/px (GPU-counted) x px")
+            times.append(dt)
+            rays.append(O.rays_traced(reset=True))
+            full_frame_s.append(sum(t.values()))
+    step_s = float(np.mean(times))
+    value = float(np.mean(rays)) / step_s / 1e6
+    sample = (f"{rows}-row full-width strip (+{halo}-row halo for the per-pixel passes feeding the spatial gather) of the 1920x1080 "
+              f"frame through all passes = one step; value = rays the oracle traced in the strip / its wall time")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": frame_s * 1e3, "fps": 1.0 / frame_s,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "restir_di config 2: bistro_class synthetic scene 1920x1080 1spp, 32 candidates, "
-                               "temporal + 1x4 spatial reuse", "triangles": scene.num_triangles,
+        "config": {"workload": WORKLOAD, "triangles": scene.num_triangles, "instances": len(scene.instances),
+                   "emissive_triangles": scene.num_emissive_triangles,
+                   "rays_per_step": float(np.mean(rays)), "rows_per_step": rows,
+                   "full_frame_ms_extrapolated_by_rows": float(np.mean(full_frame_s)) * 1e3,
+                   "fps_extrapolated_by_rows": 1.0 / float(np.mean(full_frame_s)),
+                   "parallelism": f"{threads} host threads (OpenMP over pixels)",
                    "bvh": "bvh::buildGeometryBVH<8> restatement (SBVH, budget .3), build %.1f s single-thread" % oscene.build_seconds},
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "nrc_reference": tcnn_reference_timing(),
     }
     print(json.dumps(line))
+
+
+def measure_nrc_and_svgf(ctx, scene, args):
+    """NRC MLP TFLOP/s (the second half of BASELINE.json's metric), the north-star frame (ReSTIR DI + NRC at 1080p) and SVGF
+    (config 4), on the config-2 scene, CUDA events on the launching stream, inputs resident.  NRC numbers come from the
+    frames themselves: the inference batch is the frame's pad128(W*H + #tiles) queries, training is the 4 x 16 384 shuffled
+    records, after a warm-up that lets the tile-size controller and the cache settle."""
+    import torch
+    from gfxexp_b200 import abi, engine
+    px = WIDTH * HEIGHT
+    hbm_peak, hbm_src = measured_peaks()
+    tpeak, tsrc = measured_tensor_peak()
+    out = {}
+    # ---- north-star frame: one G-buffer, ReSTIR DI passes, NRC path tracing + inference + 4 training steps
+    pc = abi.default_frame_params(scene, WIDTH, HEIGHT)
+    net = engine.NeuralRadianceCache(ctx, 2, 1e-2)
+    rng = np.random.default_rng(0)
+
+    def combined_frame(f):
+        pc.numAccumFrames = f
+        ctx.build_light_distributions(f % 2)
+        for kind, pid in engine.restir_frame_passes(pc, f, 1, True, False):
+            ctx.gbuffer(pc) if kind == "gbuffer" else ctx.restir(pc, pid)
+        off = [int(rng.integers(0, 2 ** 32)) for _ in range(2)]
+        ctx.nrc_preprocess(pc, off[0], off[1], f == 0)
+        ctx.pathtrace(pc, abi.PT_NRC)
+        ctx.nrc_frame_infer(net)
+        ctx.nrc_accumulate(pc)
+        ctx.nrc_propagate(pc)
+        ctx.nrc_shuffle(pc)
+        ctx.nrc_frame_train(net)
+
+    n_warm, n_frames = 16, max(args.steps, 8)
+    for f in range(n_warm):
+        combined_frame(f)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for f in range(n_warm, n_warm + n_frames):
+        combined_frame(f)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n_frames
+    out["north_star_frame"] = {"what": "ReSTIR DI (32 candidates, temporal + 1x4 spatial) + NRC (path tracing with cache "
+                                       "termination, inference, 4 training steps) in one frame, one G-buffer, 1920x1080, 1 GPU",
+                               "ms": ms, "fps": 1e3 / ms, "target_fps": 60.0, "frames_timed": n_frames}
+    # per-kernel times of the same frames (events inside the library)
+    ctx.timing_enable(True)
+    ctx.timing_read()
+    reps = 6
+    for f in range(n_warm + n_frames, n_warm + n_frames + reps):
+        combined_frame(f)
+    timing = ctx.timing_read()
+    ctx.timing_enable(False)
+    per_frame = {k: v[0] / reps for k, v in timing.items()}
+    st = ctx.download_linear(abi.BUF_NRC_STATE)[:, 0]
+    nq = int(st[abi.NRC_STATE_NUM_INFERENCE_QUERIES])
+    infer_ms = sum(per_frame.get(k, 0.0) for k in ("nrc_pack_positions", "nrc_grid_encode", "nrc_infer"))
+    train_ms = sum(per_frame.get(k, 0.0) for k in ("nrc_train_prep_weights", "nrc_train_fwd_bwd", "nrc_adam_ema"))
+    mlp_ms = per_frame.get("nrc_infer", 0.0)
+    out["nrc"] = {"infer_queries": nq, "infer_ms": infer_ms, "infer_tflops": 18432.0 * nq / infer_ms / 1e9,
+                  "tensor_frac": 18432.0 * nq / infer_ms / 1e9 / tpeak,
+                  "infer_kernels_ms": {k: per_frame.get(k, 0.0) for k in ("nrc_pack_positions", "nrc_grid_encode", "nrc_infer")},
+                  "mlp_kernel_tflops": 18432.0 * nq / mlp_ms / 1e9 if mlp_ms else None,
+                  "mlp_kernel_tensor_frac": 18432.0 * nq / mlp_ms / 1e9 / tpeak if mlp_ms else None,
+                  "train_samples": 65536, "train_ms": train_ms, "train_tflops": 55296.0 * 65536 / train_ms / 1e9,
+                  "train_tensor_frac": 55296.0 * 65536 / train_ms / 1e9 / tpeak,
+                  "flop_per_query": 18432, "flop_per_training_sample": 55296, "dtype": "f16 operands, f32 accumulate (tcgen05)",
+                  "peak": tpeak, "peak_source": tsrc,
+                  "frame_kernels_ms": {k: round(v, 4) for k, v in sorted(per_frame.items(), key=lambda kv: -kv[1])}}
+    net.close()
+    # ---- SVGF (config 4) on the ReSTIR DI output
+    ren = engine.ReSTIRRenderer(ctx, scene, WIDTH, HEIGHT)
+    svgf_ms = []
+    for f in range(10):
+        ren.render_frame()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for pass_id, stage in engine.svgf_frame_passes(ren.params, f):
+            ctx.svgf(ren.params, pass_id, stage)
+        b.record()
+        svgf_ms.append((a, b))
+    torch.cuda.synchronize()
+    sms = float(np.mean([a.elapsed_time(b) for a, b in svgf_ms[3:]]))
+    out["svgf"] = {"what": "temporal accumulation + variance + 5 a-trous stages + background + modulate/TAA on the ReSTIR DI "
+                           "frame, 1920x1080", "ms": sms, "algorithmic_bytes_per_px": 456,
+                   "GBps": 456.0 * px / sms / 1e6, "frac": 456.0 * px / sms / 1e6 / hbm_peak, "peak": hbm_peak, "peak_source": hbm_src}
+    return out
 
 
 def run_gpu(args):
@@ -377,8 +525,7 @@ def run_gpu(args):
         launches_per_frame = {k: n / args.steps for k, (ms, n) in timing.items()}
         dominant = max(breakdown, key=breakdown.get)
         # traversal statistics of this BVH for the rays the dominant kernel traces
-        from tests import oracle_lib as O  # only for the primary-ray generator (host arithmetic)
-        prim = O.primary_rays(params, WIDTH, HEIGHT)[:: 7]
+        prim = engine.primary_rays(params, WIDTH, HEIGHT)[:: 7]
         n_int_p, n_tri_p = traversal_stats(ctx, prim, abi.TRACE_CLOSEST)
         gb2 = ctx.download(abi.BUF_GBUFFER2, params.bufferIndex).view(np.float32)
         gb0 = ctx.download(abi.BUF_GBUFFER0, params.bufferIndex)
@@ -400,28 +547,47 @@ def run_gpu(args):
         # algorithmic bytes per pixel, SURVEY.md §8(d): struct sizes of the reference + traversal counters
         # per launch; the wavefront trace kernel serves ~0.94 (initial) / ~0.94 (shading) rays per pixel
         rays_vis = (rays_per_px - 1.0) / 2.0
+        # HBM-side: compulsory bytes per pixel with perfect on-chip reuse; a ray is 32 B in + 32 B out.
+        # L2-side: what a launch additionally pulls through L2 - BVH nodes / triangles per ray (the BVH, 188 MB, is re-read by
+        # every ray that visits a node), light records per RIS candidate (32 B guide entry + up to 128 B record).
         alg = {
-            "gbuffer": 56 + 32 + trav_primary + 3 * 48 + 16,
-            "ris_candidates": 120,                     # + 32 x ~250 B of L2-side light-table gathers per pixel
+            "gbuffer": 56 + 32 + 3 * 48 + 16 + 64,
+            "ris_candidates": 120,
             "ris_resolve_temporal": 112 + 9,
-            "ris_megakernel": 120 + 112 + trav_shadow,
-            "trace_visibility": rays_vis * trav_shadow,
+            "ris_megakernel": 120 + 112 + 64,
+            "trace_visibility": rays_vis * 64,
             "spatial_ris": 592,
             "shading_rays": 104 + 36,
             "shading": 120,
-            "shading_megakernel": 120 + trav_shadow,
+            "shading_megakernel": 120 + 64,
+        }
+        l2_side = {
+            "gbuffer": trav_primary - 64,
+            "ris_candidates": 32 * (32 + 0.5 * 64 + 0.35 * 96),
+            "ris_megakernel": trav_shadow - 64,
+            "trace_visibility": rays_vis * (trav_shadow - 64),
+            "shading_megakernel": trav_shadow - 64,
         }
         hbm_peak, peak_src = measured_peaks()
         bytes_per_launch = alg.get(dominant, 0) * px
         achieved = bytes_per_launch / (breakdown[dominant] * 1e-3) / 1e9
         roofline = {"kernel": dominant, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": achieved / hbm_peak, "traffic": NCU_DRAM_TRAFFIC.get(dominant), "traffic_source": "ncu --set full, profiles/r01_summary.md", "ncu": NCU_NOTE.get(dominant), "peak_source": peak_src,
+                    "frac": achieved / hbm_peak, "traffic": NCU_DRAM_TRAFFIC.get(dominant), "traffic_source": "ncu --set full, profiles/r02_summary.md", "ncu": NCU_NOTE.get(dominant), "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": bytes_per_launch, "ms_per_launch": breakdown[dominant],
                     "traversal": {"primary_nodes_per_ray": n_int_p, "primary_tris_per_ray": n_tri_p,
                                   "shadow_nodes_per_ray": n_int_s, "shadow_tris_per_ray": n_tri_s},
                     "per_kernel": {k: {"ms_per_launch": breakdown[k], "launches_per_frame": launches_per_frame[k],
-                                       "GBps": alg.get(k, 0) * px / (breakdown[k] * 1e-3) / 1e9}
-                                   for k in breakdown}}
+                                       "hbm_GBps": alg.get(k, 0) * px / (breakdown[k] * 1e-3) / 1e9,
+                                       "hbm_frac": alg.get(k, 0) * px / (breakdown[k] * 1e-3) / 1e9 / hbm_peak,
+                                       "l2_side_GBps": l2_side.get(k, 0) * px / (breakdown[k] * 1e-3) / 1e9}
+                                   for k in breakdown},
+                    "frame": {"algorithmic_bytes": 1032 * px + 64 * rays_per_px * px, "hbm_GBps": (1032 + 64 * rays_per_px) * px / (ms_per_step * 1e-3) / 1e9,
+                              "hbm_frac": (1032 + 64 * rays_per_px) * px / (ms_per_step * 1e-3) / 1e9 / hbm_peak}}
+
+    # ---- the rest of BASELINE.json's metric, same process / scene / clocks (rank 0, N = 1) ----------------------------
+    extras = {}
+    if driver is None and not args.headline_only:
+        extras = measure_nrc_and_svgf(ctx, scene, args)
 
     # ---- CPU baseline: the oracle on the host cores, bounded sample (rank 0, N=1 only) -------------
     cpu_baseline = None
@@ -443,8 +609,7 @@ def run_gpu(args):
         "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "fps": 1e3 / ms_per_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "restir_di config 2: bistro_class synthetic scene 1920x1080 1spp, 32 candidates, "
-                               "temporal + 1x4 spatial reuse",
+        "config": {"workload": WORKLOAD,
                    "triangles": info.numTriangles, "bvh_nodes": info.numNodes, "instances": len(scene.instances),
                    "emissive_triangles": scene.num_emissive_triangles, "rays_per_pixel": rays_per_px,
                    "l2": "inputs larger than L2 (BVH %.0f MB + %.0f MB of per-pixel state per frame)" % (
@@ -460,6 +625,7 @@ def run_gpu(args):
     }
     if roofline is not None:
         line["roofline"] = roofline
+    line.update(extras)
     if cpu_baseline is not None:
         line["cpu_baseline"] = cpu_baseline
     print(json.dumps(line))
@@ -476,6 +642,7 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=48, help="rows of the CPU-baseline strip sample")
     ap.add_argument("--rays-per-px", type=float, default=2.883, help="--impl reference: rays per pixel (GPU-counted)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--headline-only", action="store_true", help="skip the NRC / north-star / SVGF measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -341,6 +341,27 @@ class NeuralRadianceCache:
         return loss.value if want_loss else None
 
 
+def primary_rays(params, width: int, height: int) -> np.ndarray:
+    """pinhole primary rays of setupGBuffers (optix_gbuffer_kernels.cu:21-27): dir = normalize(orientation *
+    (vw (0.5 - x), vh (0.5 - y), 1)), x = (ix + 0.5) / W - for gfx_trace statistics and tools (the G-buffer kernel generates its
+    own rays on the device)"""
+    cam = params.camera
+    ori = np.asarray(cam.orientation[:], dtype=np.float32).reshape(3, 3)
+    vh = np.float32(2.0 * np.tan(np.float32(cam.fovY) * np.float32(0.5)))
+    vw = np.float32(cam.aspect) * vh
+    x = (np.arange(width, dtype=np.float32) + np.float32(0.5)) / np.float32(width)
+    y = (np.arange(height, dtype=np.float32) + np.float32(0.5)) / np.float32(height)
+    d = np.stack(np.broadcast_arrays((vw * (np.float32(0.5) - x))[None, :], (vh * (np.float32(0.5) - y))[:, None],
+                                     np.ones((height, width), dtype=np.float32)), axis=-1).astype(np.float32)
+    d = d @ ori.T
+    d /= np.linalg.norm(d, axis=-1, keepdims=True)
+    rays = np.zeros(width * height, dtype=abi.RAY_DTYPE)
+    rays["org"] = np.asarray(cam.position[:], dtype=np.float32)
+    rays["dir"] = d.reshape(-1, 3)
+    rays["tmax"] = np.float32(3.402823466e+38)
+    return rays
+
+
 def random_nrc_params(num_params: int, num_matrix_weights: int, seed: int = 1337, grid_amplitude: float = 1e-4) -> np.ndarray:
     """Xavier-uniform MLP matrices and U(-a, a) hash-grid entries (tcnn: gpu_matrix.h initialize_xavier_uniform,
     grid.h:1267-1272), from a numpy stream (the reference's pcg32 stream is not reproduced)."""

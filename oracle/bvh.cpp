@@ -2,6 +2,7 @@
 // CPU restatement of common/bvh_builder.cpp (builder :213-652, :656-1125; traverser :1227-1649)
 // and of the node codec in common/common_shared.h:757-917.  See bvh.h for the parity status.
 #include "bvh.h"
+#include <omp.h>
 #include <cassert>
 #include <cstdio>
 
@@ -996,12 +997,27 @@ HitObject traverse(const GeometryBVH &bvh, const float3 &rayOrg, const float3 &r
                    float distMin, float distMax, TraversalStatistics* stats) {
     return traverseImpl<HitMode::FirstFound>(bvh, rayOrg, rayDir, distMin, distMax, stats);
 }
+// rays traced through the two wrappers below (bench.py's reference arm counts its own rays): one padded counter per thread
+namespace { struct alignas(64) RayCounter { unsigned long long n = 0; }; RayCounter g_rayCounters[1024]; }
+static inline void countRay() { ++g_rayCounters[omp_get_thread_num() & 1023].n; }
+extern "C" unsigned long long orc_rays_traced(int reset) {
+    unsigned long long total = 0;
+    for (RayCounter &c : g_rayCounters) {
+        total += c.n;
+        if (reset)
+            c.n = 0;
+    }
+    return total;
+}
+
 HitObject traverseCanonical(const GeometryBVH &bvh, const float3 &rayOrg, const float3 &rayDir,
                             float distMin, float distMax) {
+    countRay();
     return traverseImpl<HitMode::Canonical>(bvh, rayOrg, rayDir, distMin, distMax, nullptr);
 }
 bool traverseAny(const GeometryBVH &bvh, const float3 &rayOrg, const float3 &rayDir,
                  float distMin, float distMax) {
+    countRay();
     const HitObject h = traverseImpl<HitMode::Any>(bvh, rayOrg, rayDir, distMin, distMax, nullptr);
     return h.primIndex != UINT32_MAX;
 }

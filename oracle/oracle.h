@@ -66,6 +66,8 @@ void orc_restir_setup_neighbor_table(orc_frame* f);
 void* orc_buffer_ptr(orc_frame* f, int bufferId, uint32_t index, size_t* bytes);
 /* measurement aid: enable / read-and-reset the candidate statistics of the initial RIS loop (5 counters, see render.cpp) */
 void orc_ris_stats(int enable, unsigned long long* out5);
+/* rays traced by the renderer entry points since the last reset (all threads) */
+unsigned long long orc_rays_traced(int reset);
 /* output side: float4 image -> tone-mapped / sRGB-encoded RGBA8 (present.cpp) */
 void orc_present(const float* srcRGBA, uint32_t width, uint32_t height, const GfxPresentParams* config, uint32_t* image);
 void orc_gbuffer(orc_frame* f, const GfxFrameParams* p, int numThreads);

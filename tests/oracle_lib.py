@@ -91,6 +91,8 @@ def lib() -> C.CDLL:
         L.orc_svgf_buffer_ptr.restype = vp
         L.orc_svgf_buffer_ptr.argtypes = [vp, C.c_int, C.c_uint32, C.POINTER(C.c_size_t)]
         L.orc_svgf_pass.argtypes = [vp, C.POINTER(abi.GfxFrameParams), C.c_int, C.c_uint32, C.c_int]
+        L.orc_rays_traced.restype = C.c_ulonglong
+        L.orc_rays_traced.argtypes = [C.c_int]
         L.orc_nrc_create.restype = vp
         L.orc_nrc_create.argtypes = [C.c_uint32, C.c_float]
         L.orc_nrc_destroy.argtypes = [vp]
@@ -351,6 +353,11 @@ class OracleNrc:
         q = np.ascontiguousarray(queries, dtype=np.float32)
         t = np.ascontiguousarray(targets, dtype=np.float32)
         return float(lib().orc_nrc_train(self.h, q.ctypes.data, t.ctypes.data, q.shape[0]))
+
+
+def rays_traced(reset: bool = True) -> int:
+    """rays the oracle's renderer entry points traced since the last reset"""
+    return int(lib().orc_rays_traced(1 if reset else 0))
 
 
 def primary_rays(params, width: int, height: int) -> np.ndarray:

@@ -1,12 +1,9 @@
 """oracle/nrc.cpp's hash-grid and one-blob encodings against the reference's own tiny-cuda-nn kernels (kernel_grid<__half,3,2>,
 kernel_one_blob_soa<__half>) compiled from /root/reference/ext/tiny-cuda-nn into oracle/_ref/libtcnn_ref.so with -fmad=false, i.e.
 under the oracle's arithmetic model (the reference's own build contracts a*b+c into FMAs, which no CPU restatement can follow
-bit for bit; what is compared here is the algorithm).
-
-Written at the end of round 1, after the GPU budget was spent: the harness compiles (SASS holds both kernels) but this test has
-never executed, hence the non-strict xfail - an XPASS in the round-end log means the NRC oracle's encoding is pinned against
-the real third-party code; an XFAIL carries the JSON diff.  The check runs in a child process so that a fault inside
-third-party kernels cannot poison this session's CUDA context."""
+bit for bit; what is compared here is the algorithm): every half bit-identical.  First passed on the round-1 driver box (XPASS);
+a plain test since round 2.  The check runs in a child process so that a fault inside third-party kernels cannot poison this
+session's CUDA context."""
 import json
 import os
 import subprocess
@@ -18,7 +15,6 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.xfail(strict=False, reason="first execution happens on the round-end GPU box (see module docstring)")
 def test_oracle_encoding_equals_tcnn_kernels():
     if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libtcnn_ref.so")):
         pytest.skip("oracle/_ref/libtcnn_ref.so not built (needs /root/reference at build time)")
