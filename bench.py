@@ -400,6 +400,8 @@ def run_gpu(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+        if driver is not None:
+            driver.check_peers()  # a seam wait that timed out would mean stale rows inside the region just timed
 
     frame = 0
     for _ in range(max(args.warmup, 3)):

@@ -14,6 +14,13 @@ offsets.  Per frame:
   5. shading on the owned rows, exchange of the final reservoir halo (next frame's temporal reuse)
   6. all-gather of the composited beauty strips: the one mandatory collective
 
+What a rank can read across a seam is `halo` rows, so the driver refuses configurations that would read further:
+`spatialNeighborRadius` must not exceed `halo`, and the temporal pass - which follows the motion vector to the previous frame's
+G-buffer and reservoirs (optix_restir_di_kernels.cu:150-153) - is only valid while no pixel moves by more than `halo` rows per
+frame: a moving camera (or animated instances) needs `max_motion_rows` stated by the caller (<= halo), and a frame whose camera
+differs from the previous one is rejected without it.  A stalled neighbour (k_peerWait's time-out, csrc/peer.cu) is detected by
+`check_peers()`, which the driver calls every `check_every` frames and callers call before trusting a timed region.
+
 The driver is backend-agnostic: `GpuBackend` drives libgfxb200 with NCCL on the device pointers,
 `tests/test_multigpu_cpu.py` drives the CPU oracle through the same code with gloo, which is how the
 host-side sharding logic is verified bit-for-bit against a single-process render.
@@ -83,7 +90,7 @@ class GpuBackend:
 
 class StripDriver:
     def __init__(self, backend_or_ctx, params, width: int, height: int, rank: int, world: int, halo: int = 24,
-                 peer: bool = True):
+                 peer: bool = True, max_motion_rows: int = 0, check_every: int = 0):
         self.backend = GpuBackend(backend_or_ctx) if isinstance(backend_or_ctx, engine.Context) else backend_or_ctx
         self.params = params
         self.W, self.H = width, height
@@ -99,6 +106,14 @@ class StripDriver:
             raise ValueError(f"{rows} rows per rank < halo {halo}: the seam exchange only reaches the adjacent rank")
         if params.enableJittering:
             raise ValueError("strip sharding recomputes G-buffer halo rows; sub-pixel jitter would double-advance their RNG")
+        if world > 1 and params.spatialNeighborRadius > halo:
+            raise ValueError(f"spatialNeighborRadius {params.spatialNeighborRadius} > halo {halo}: the spatial pass would read "
+                             "rows that are neither owned nor exchanged")
+        if max_motion_rows > halo:
+            raise ValueError(f"max_motion_rows {max_motion_rows} > halo {halo}: temporal reuse would read unexchanged rows")
+        self.max_motion_rows = max_motion_rows
+        self.check_every = check_every
+        self.frames_rendered = 0
         self.composited = self.backend.new_tensor(width * height * 4)
         if world > 1 and isinstance(self.backend, GpuBackend) and peer:
             self.backend.enable_peer(rank, world)
@@ -160,10 +175,25 @@ class StripDriver:
         if down:
             ctx.peer_wait(1, seq)
 
+    def check_peers(self):
+        """raises if a seam wait timed out since the last check (a stalled neighbour: rows of this frame may be stale)"""
+        if self.world > 1 and getattr(self.backend, "peer_ready", False):
+            if self.backend.ctx.peer_timed_out():
+                raise RuntimeError(f"rank {self.rank}: a peer seam wait timed out (csrc/peer.cu k_peerWait): frames since the "
+                                   "last check may contain stale seam rows")
+
+    @staticmethod
+    def _camera_moved(p) -> bool:
+        import ctypes as C
+        return bytes(C.string_at(C.addressof(p.camera), C.sizeof(p.camera))) != bytes(C.string_at(C.addressof(p.prevCamera), C.sizeof(p.prevCamera)))
+
     # -- one frame ------------------------------------------------------------------------------------
     def render_frame(self, frame_index: int, num_spatial_passes: int = 1, unbiased: bool = False):
         p = self.params
         b = self.backend
+        if self.world > 1 and frame_index > 0 and p.enableTemporalReuse and self.max_motion_rows == 0 and self._camera_moved(p):
+            raise ValueError("the camera moved between frames: temporal reuse follows motion vectors across strip seams, state "
+                             "max_motion_rows (<= halo) when constructing the StripDriver")
         b.light_dist(frame_index)
         lo_h, hi_h = max(0, self.y0 - self.halo), min(self.H, self.y1 + self.halo)
         spatial_seen = 0
@@ -199,3 +229,6 @@ class StripDriver:
         else:
             self.composited.copy_(self.backend.tensor(abi.BUF_BEAUTY_ACCUM, 0))
         p.tileOriginY, p.tileRows = 0, 0
+        self.frames_rendered += 1
+        if self.check_every and self.frames_rendered % self.check_every == 0:
+            self.check_peers()

@@ -1,4 +1,4 @@
-// TEST INFRASTRUCTURE (CPU): the bounding-sphere pre-test of sampleLightUnlessDark (-DGFX_LIGHT_CULL_SPHERES, lighting.cuh /
+// TEST INFRASTRUCTURE (CPU): the bounding-sphere pre-test of sampleLightUnlessDark (step 0, lighting.cuh /
 // lights.cu, transcribed) is conservative: whenever it rejects a light triangle, every sample point of that triangle lies
 // below the shading horizon with at least the 1e-3 cosine margin of the per-sample test - checked in double precision on
 // random triangles, shading points, normals and view sides, with many configurations close to the horizon.

@@ -1,4 +1,4 @@
-"""The bounding-sphere pre-test of the light-triangle fetch (-DGFX_LIGHT_CULL_SPHERES, switched off until measured on a GPU)
+"""The bounding-sphere pre-test of the light-triangle fetch (step 0 of sampleLightUnlessDark, gfxexp_b200/csrc/lighting.cuh; on since round 2)
 never rejects a triangle that has a sample point above - or within the 1e-3 cosine margin of - the shading horizon:
 3 M random configurations on the CPU, in double precision."""
 import os

@@ -68,6 +68,80 @@ def _worker(rank, world, port, result_path, H=H):
     dist.destroy_process_group()
 
 
+def _moving_camera(scene, frame):
+    from gfxexp_b200 import abi
+    cam = abi.make_camera(scene, W, H)
+    cam.position[1] += 0.12 * frame   # vertical motion: reprojected pixels cross the strip seams
+    cam.position[0] += 0.05 * frame
+    return cam
+
+
+def _worker_moving(rank, world, port, result_path):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from gfxexp_b200 import abi, multigpu, scenes
+    from tests import oracle_lib as O
+    scene = scenes.tiny_city_scene()
+    oframe = O.OracleFrame(O.OracleScene(scene), W, H)
+    p = abi.default_frame_params(scene, W, H)
+    driver = multigpu.StripDriver(OracleBackend(oframe), p, W, H, rank, world, halo=24, max_motion_rows=24)
+    outs = []
+    for f in range(FRAMES):
+        p.prevCamera = _moving_camera(scene, max(f - 1, 0))
+        p.camera = _moving_camera(scene, f)
+        driver.render_frame(f, num_spatial_passes=1)
+        outs.append(driver.composited.clone().numpy())
+    if rank == 0:
+        np.save(result_path, np.stack(outs))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_strips_equal_single_process_with_a_moving_camera(tmp_path, oracle):
+    """temporal reuse follows the motion vectors across the strip seams: with the motion inside the halo the sharded frames
+    still equal the single-process frames bit for bit"""
+    from gfxexp_b200 import abi, engine, scenes
+    result = str(tmp_path / "moving.npy")
+    mp.spawn(_worker_moving, args=(2, _free_port(), result), nprocs=2, join=True)
+    got = np.load(result)
+    scene = scenes.tiny_city_scene()
+    oframe = oracle.OracleFrame(oracle.OracleScene(scene), W, H)
+    p = abi.default_frame_params(scene, W, H)
+    for f in range(FRAMES):
+        p.prevCamera = _moving_camera(scene, max(f - 1, 0))
+        p.camera = _moving_camera(scene, f)
+        for kind, pass_id in engine.restir_frame_passes(p, f, 1):
+            oframe.gbuffer(p) if kind == "gbuffer" else oframe.restir(p, pass_id)
+        want = oframe.buffer(abi.BUF_BEAUTY_ACCUM).reshape(-1)
+        assert np.array_equal(got[f].view(np.uint32), want.view(np.uint32)), f"frame {f}: sharded frame differs"
+
+
+def test_strip_driver_refuses_what_the_halo_cannot_cover():
+    from gfxexp_b200 import abi, multigpu, scenes
+    scene = scenes.tiny_city_scene()
+
+    class Dummy:
+        def new_tensor(self, n):
+            return torch.empty(n)
+    p = abi.default_frame_params(scene, 64, 64)
+    p.spatialNeighborRadius = 30.0
+    with pytest.raises(ValueError):     # radius 30 > halo 24
+        multigpu.StripDriver(Dummy(), p, 64, 64, 0, 2)
+    p.spatialNeighborRadius = 20.0
+    with pytest.raises(ValueError):     # motion beyond the halo
+        multigpu.StripDriver(Dummy(), p, 64, 64, 0, 2, max_motion_rows=30)
+    d = multigpu.StripDriver(Dummy(), p, 64, 64, 0, 2)
+    p.enableTemporalReuse = 1
+    cam = abi.make_camera(scene, 64, 64)
+    cam.position[0] += 1.0
+    p.prevCamera = abi.make_camera(scene, 64, 64)
+    p.camera = cam
+    with pytest.raises(ValueError):     # a moving camera without a stated motion bound
+        d.render_frame(1)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
