@@ -64,20 +64,21 @@ def measured_tensor_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md).  nvidia-smi needs a few hundred
+    ms to produce its first line, longer than a 20-frame region, so the process is started once, early, and keeps logging
+    with timestamps; mark() / summary() select the lines that fall inside a region (or, if the region was shorter than the
+    sampling period, the lines nearest to it, flagged in `window`)."""
 
     def __init__(self, device: int):
         self.device = device
         self.proc = None
-        self.lines = []
-
-    def start(self):
+        self.lines = []   # (host time of arrival, parsed fields)
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -86,20 +87,26 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def start(self):
+        self.t0 = time.perf_counter()
 
     def stop(self):
+        """summary of the region [start(), now]"""
+        t1 = time.perf_counter()
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
+        time.sleep(0.12)  # let the line that covers the end of the region arrive
+        inside = [ln for t, ln in self.lines if self.t0 <= t <= t1 + 0.06]
+        window = "inside the timed region"
+        if not inside:
+            near = sorted(self.lines, key=lambda tl: min(abs(tl[0] - self.t0), abs(tl[0] - t1)))[:3]
+            inside = [ln for _, ln in near]
+            window = "nearest samples (region shorter than the 50 ms sampling period)"
         sm, smmax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in inside:
             parts = [x.strip() for x in ln.split(",")]
             if len(parts) < 7:
                 continue
@@ -112,7 +119,15 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smmax) if smmax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "window": window}
+
+    def close(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
@@ -365,6 +380,7 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
 
+    sampler = ClockSampler(local_rank)  # started now: nvidia-smi takes a while to deliver its first line
     scene = scenes.bistro_class_scene()
     ctx = engine.Context(local_rank)
     t0 = time.perf_counter()
@@ -412,7 +428,6 @@ def run_gpu(args):
     launches0 = ctx.kernel_launches
 
     # ---- timed region 1: everything resident in HBM -------------------------------------------
-    sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -493,6 +508,7 @@ def run_gpu(args):
     ev1.record()
     barrier()
     e2e_ms = ev0.elapsed_time(ev1)
+    sampler.close()
     e2e_rays = ctx.read_stats(reset=True)[0]
     if world > 1:
         t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)

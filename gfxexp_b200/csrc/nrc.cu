@@ -506,13 +506,7 @@ __global__ void __launch_bounds__(kEncodeThreads, 1) k_nrcGridEncode(NrcLevels l
     }
     __syncthreads();
     mbarWait(&bar, 0);
-    const __half2* grid = reinterpret_cast<const __half2*>(smem);
-
-    // this replica's share of the 128-query tiles
-    const uint32_t numTiles = (numData + 127u) / 128u;
-    const uint32_t tilesPer = (numTiles + replicas - 1) / replicas;
-    const uint32_t qBegin = min(replica * tilesPer, numTiles) * 128u;
-    const uint32_t qEnd = min(min((replica + 1) * tilesPer, numTiles) * 128u, numData);
+    __half2* grid = reinterpret_cast<__half2*>(smem);
 
     // level constants of grid_index (grid.h:76-111), hoisted: dense levels add strides, hashed levels xor prime products
     uint32_t stride = 1, strides[3];
@@ -525,6 +519,30 @@ __global__ void __launch_bounds__(kEncodeThreads, 1) k_nrcGridEncode(NrcLevels l
             stride *= lv.resolution;
     }
     const bool hashed = lv.hashmapSize < stride;
+
+    // Dense levels index x + y * res + z * res^2 with res a multiple of 16: the queries of a warp are consecutive pixels, whose
+    // positions typically run along ONE grid axis, so along y or z all 32 lanes would hit the same shared-memory bank (measured:
+    // the dense levels' CTAs took twice as long as the hashed ones' and set the kernel's duration).  Entries are therefore
+    // permuted inside each aligned row of 32: entry i lives at i ^ swz(i >> 5), swz(r) = (r ^ (r >> 5)) & 31 - y and z
+    // neighbours land in different banks.  Hashed levels are spread by the hash already.
+    const bool swizzle = !hashed && (lv.hashmapSize & 31u) == 0u;
+    const uint32_t swzMask = swizzle ? 31u : 0u;
+    if (swizzle) {
+        const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, numRows = lv.hashmapSize >> 5;
+        for (uint32_t row = warp; row < numRows; row += kEncodeThreads / 32) {
+            const __half2 v = grid[row * 32 + lane];
+            __syncwarp();
+            grid[row * 32 + (lane ^ ((row ^ (row >> 5)) & 31u))] = v;
+        }
+        __syncthreads();
+    }
+
+    // this replica's share of the 128-query tiles
+    const uint32_t numTiles = (numData + 127u) / 128u;
+    const uint32_t tilesPer = (numTiles + replicas - 1) / replicas;
+    const uint32_t qBegin = min(replica * tilesPer, numTiles) * 128u;
+    const uint32_t qEnd = min(min((replica + 1) * tilesPer, numTiles) * 128u, numData);
+
     const uint32_t primes[3] = { 1u, 2654435761u, 805459861u };
     uint32_t mul[3];
 #pragma unroll
@@ -556,6 +574,7 @@ __global__ void __launch_bounds__(kEncodeThreads, 1) k_nrcGridEncode(NrcLevels l
             const uint32_t a = term[0][idx & 1u], b = term[1][(idx >> 1) & 1u], c = term[2][(idx >> 2) & 1u];
             uint32_t index = hashed ? (a ^ b ^ c) : (a + b + c);
             index = pow2 ? (index & (size - 1u)) : (index < size ? index : index % size);
+            index ^= ((index >> 5) ^ (index >> 10)) & swzMask;
             const float2 v = __half22float2(grid[index]);
             // result += (half)(weight * (float)value) in half precision (grid.h:233-238); __hadd2 rounds the exact sum once,
             // which equals the float-add-then-round-to-half the oracle spells out (the fp32 sum of two halves only rounds when

@@ -51,6 +51,12 @@ GFX_D bool testRayVsTriangle( // common/bvh_builder.cpp:1251-1270
 #define GFX_CSWAP(a, b) { const uint32_t lo_ = min(a, b); const uint32_t hi_ = max(a, b); a = lo_; b = hi_; }
 
 constexpr int kStackSize = 64;
+// The wavefront kernels keep the first kSmemStack entries of every lane's stack in shared memory, laid out [entry][thread] so
+// that a warp's pushes and pops are conflict-free whatever the lanes' depths (a per-thread local-memory stack makes every push a
+// divergent store: the push / pop section held 41 % of the trace kernel's stall samples in round 1); deeper entries - rare with
+// an 8-wide tree - spill to the local array.
+constexpr int kSmemStack = 16;
+constexpr int kSmemStackThreads = 128; // block size of the wavefront kernels
 
 struct TraversalState {
     f3 org, dir, idir;
@@ -58,8 +64,22 @@ struct TraversalState {
     Hit best;
     uint32_t nodeIdx;
     int sp;
+    uint2* sstack;           // this thread's column of the shared-memory stack (wavefront kernels), else unused
     uint2 stack[kStackSize]; // (node index, truncated entry distance bits)
 };
+template <bool SMEM>
+GFX_D void stackStore(TraversalState &st, int at, const uint2 &v) {
+    if (SMEM && at < kSmemStack)
+        st.sstack[at * kSmemStackThreads] = v;
+    else
+        st.stack[SMEM ? at - kSmemStack : at] = v;
+}
+template <bool SMEM>
+GFX_D uint2 stackLoad(const TraversalState &st, int at) {
+    if (SMEM && at < kSmemStack)
+        return st.sstack[at * kSmemStackThreads];
+    return st.stack[SMEM ? at - kSmemStack : at];
+}
 
 GFX_D void traverseInit(TraversalState &st, const f3 &org, const f3 &dir, float tmin, float tmax) {
     st.org = org;
@@ -82,14 +102,11 @@ GFX_D void traverseInit(TraversalState &st, const f3 &org, const f3 &dir, float 
     st.idir = f3(1.0f / sd.x, 1.0f / sd.y, 1.0f / sd.z);
     st.nodeIdx = 0;
     st.sp = 0;
+    st.sstack = nullptr;
 }
 
 // Leaf children whose triangle tests have been postponed (wavefront kernel): the start of the triangle chain and the
 // entry distance of the leaf box.  A node step appends at most 8.
-#ifndef GFX_TRAVERSE_PREDICATED_PUSH
-#define GFX_TRAVERSE_PREDICATED_PUSH 0
-#endif
-
 constexpr int kPendingLeaves = 12;
 struct PendingLeaves {
     uint32_t idx[kPendingLeaves];
@@ -148,7 +165,7 @@ GFX_D bool testPendingTriangle(const DevBvh &bvh, TraversalState &st, PendingLea
 // Processes node st.nodeIdx: slab-tests its children, intersects the triangle chains of the leaf
 // children that are hit (or, with `pend`, postpones them), selects the next internal node.  Returns false when the
 // traversal is finished.
-template <bool ANY_HIT, bool STATS, bool DEFER = false>
+template <bool ANY_HIT, bool STATS, bool DEFER = false, bool SMEM = false>
 GFX_D bool traverseStep(const DevBvh &bvh, TraversalState &st, PendingLeaves* pend = nullptr) {
     const uint4* np = bvh.nodes + 5 * (size_t)st.nodeIdx;
     const uint4 n0 = __ldg(np + 0);
@@ -245,46 +262,8 @@ GFX_D bool traverseStep(const DevBvh &bvh, TraversalState &st, PendingLeaves* pe
 
     // ---- internal children: nearest becomes the next node, the others are pushed far -> near
     const uint32_t childBase = n1.x;
-#if GFX_TRAVERSE_PREDICATED_PUSH
-    // Branch-free variant (compile-time, default off: written after the GPU budget of round 1 was spent, so unvalidated).
-    // The loop below compiles to eight separately reconverging blocks around local-memory stores, which hold 41 % of the
-    // trace kernel's stall samples at 8-10 active lanes (profiles/r01_summary.md).  Here every surviving internal child
-    // gets its stack position from a population count - rank = number of farther survivors - and the stores are
-    // predicated; the nearest survivor becomes the next node.  Same survivors, same stack order as the loop.
-    {
-        uint32_t survivors = 0u;
-        uint32_t childNode[8], childT[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const uint32_t key = keys[k];
-            const uint32_t slot = key & 7u;
-            childT[k] = (key & 0x7FFFFFF8u) << 1; // truncated entry distance (<= true tn)
-            childNode[k] = childBase + __popc(internalMask & ((1u << slot) - 1u));
-            const bool survives = key != 0xFFFFFFFFu && key >= 0x80000000u && !(__uint_as_float(childT[k]) > st.best.dist);
-            survivors |= survives ? (1u << k) : 0u;
-        }
-        if (survivors) {
-            const int nearest = __ffs(survivors) - 1;
-#pragma unroll
-            for (int k = 7; k >= 1; --k) { // position 0 can only be the nearest survivor
-                const uint32_t at = (uint32_t)st.sp + __popc(survivors >> (k + 1));
-                if (((survivors >> k) & 1u) && k != nearest) {
-                    if (at < (uint32_t)kStackSize)
-                        st.stack[at] = make_uint2(childNode[k], childT[k]);
-                    else if (bvh.overflowFlag)
-                        *bvh.overflowFlag = 1u;
-                }
-            }
-            st.sp = min(st.sp + __popc(survivors) - 1, kStackSize);
-            uint32_t next = childNode[0];
-#pragma unroll
-            for (int k = 1; k < 8; ++k)
-                next = k == nearest ? childNode[k] : next;
-            st.nodeIdx = next;
-            return true;
-        }
-    }
-#else
+    // (A branch-free variant - stack positions from population counts, predicated stores - was measured in round 2 and is
+    // gone: same hits, but G-buffer 0.67 -> 0.80 ms and visibility trace 0.90 -> 0.94 ms, profiles/r02_summary.md.)
     uint32_t next = 0xFFFFFFFFu, nextT = 0u;
 #pragma unroll
     for (int k = 7; k >= 0; --k) {
@@ -297,7 +276,7 @@ GFX_D bool traverseStep(const DevBvh &bvh, TraversalState &st, PendingLeaves* pe
             continue;
         if (next != 0xFFFFFFFFu) {
             if (st.sp < kStackSize)
-                st.stack[st.sp++] = make_uint2(next, nextT);
+                stackStore<SMEM>(st, st.sp++, make_uint2(next, nextT));
             else if (bvh.overflowFlag)
                 *bvh.overflowFlag = 1u;
         }
@@ -308,9 +287,8 @@ GFX_D bool traverseStep(const DevBvh &bvh, TraversalState &st, PendingLeaves* pe
         st.nodeIdx = next;
         return true;
     }
-#endif
     while (st.sp > 0) {
-        const uint2 e = st.stack[--st.sp];
+        const uint2 e = stackLoad<SMEM>(st, --st.sp);
         if (__uint_as_float(e.y) <= st.best.dist) {
             st.nodeIdx = e.x;
             return true;

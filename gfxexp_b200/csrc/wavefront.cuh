@@ -34,6 +34,8 @@ GFX_D void traceWavefrontBody(const DevBvh &bvh, const float4* __restrict__ rays
         return;
     }
     const uint32_t lane = threadIdx.x & 31u;
+    __shared__ uint2 sharedStack[kSmemStack][kSmemStackThreads];
+    uint2* const myStack = &sharedStack[0][threadIdx.x];
     TraversalState st;
     bool active = false;
     uint32_t myRay = 0;
@@ -62,6 +64,7 @@ GFX_D void traceWavefrontBody(const DevBvh &bvh, const float4* __restrict__ rays
                     const float4 r0 = __ldg(rays + 2 * (size_t)r);
                     const float4 r1 = __ldg(rays + 2 * (size_t)r + 1);
                     traverseInit(st, f3(r0.x, r0.y, r0.z), f3(r1.x, r1.y, r1.z), r0.w, r1.w);
+                    st.sstack = myStack;
                     myRay = r;
                     active = true;
                 }
@@ -71,7 +74,7 @@ GFX_D void traceWavefrontBody(const DevBvh &bvh, const float4* __restrict__ rays
             break;
 #pragma unroll 1
         for (int it = 0; it < 8; ++it) {
-            if (active && !draining && !traverseStep<ANY_HIT, STATS, true>(bvh, st, &pend))
+            if (active && !draining && !traverseStep<ANY_HIT, STATS, true, true>(bvh, st, &pend))
                 draining = true;
             const uint32_t have = __ballot_sync(0xFFFFFFFFu, active && pend.n > 0);
             const uint32_t running = __ballot_sync(0xFFFFFFFFu, active && !draining);
@@ -113,6 +116,7 @@ GFX_D void traceWavefrontBody(const DevBvh &bvh, const float4* __restrict__ rays
                     const float4 r0 = __ldg(rays + 2 * (size_t)r);
                     const float4 r1 = __ldg(rays + 2 * (size_t)r + 1);
                     traverseInit(st, f3(r0.x, r0.y, r0.z), f3(r1.x, r1.y, r1.z), r0.w, r1.w);
+                    st.sstack = myStack;
                     myRay = r;
                     active = true;
                 }
@@ -123,7 +127,7 @@ GFX_D void traceWavefrontBody(const DevBvh &bvh, const float4* __restrict__ rays
         // ---- advance every active lane by up to 8 nodes, leave early once a quarter of the warp is idle
 #pragma unroll 1
         for (int it = 0; it < 8; ++it) {
-            if (active && !traverseStep<ANY_HIT, STATS>(bvh, st)) {
+            if (active && !traverseStep<ANY_HIT, STATS, false, true>(bvh, st)) {
                 writer.template write<ANY_HIT, STATS>(myRay, st);
                 active = false;
             }

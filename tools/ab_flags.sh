@@ -1,14 +1,13 @@
 #!/bin/bash
-# A/B of the compile-time variants that round 1 left switched off (see profiles/r01_summary.md):
-#   GFX_WIDE_TABLE_LOADS=1         128-bit loads of the instance record in the light-sampling chain
-#   GFX_TRAVERSE_PREDICATED_PUSH=1 branch-free push of the surviving internal children in the traversal
-#   GFX_LIGHT_CULL_SPHERES=1       bounding sphere per light triangle, read before its vertices (RIS candidates)
+# A/B builds of compile-time variants (results: profiles/r02_summary.md):
+#   GFX_AB_NO_SPHERE    light sampling without the bounding-sphere step of sampleLightUnlessDark
+#   GFX_AB_CHAIN_PICK   the three nested CDF searches instead of the flattened light pick
 # Step 1 (here, no GPU):   tools/ab_flags.sh build     -> build_ab/libgfxb200_{wide,push,spheres,all}.so
 # Step 2 (under gpurun):   tools/ab_flags.sh run       -> parity suite + bench line per variant (GFXB200_LIB selects the library)
 set -u
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
 cd "$ROOT"
-declare -A FLAGS=( [nosphere]="-DGFX_AB_NO_SPHERE" [chainpick]="-DGFX_AB_CHAIN_PICK" [push]="-DGFX_TRAVERSE_PREDICATED_PUSH=1" )
+declare -A FLAGS=( [nosphere]="-DGFX_AB_NO_SPHERE" [chainpick]="-DGFX_AB_CHAIN_PICK" )
 if [ -n "${AB_ONLY:-}" ]; then for k in "${!FLAGS[@]}"; do [[ " $AB_ONLY " == *" $k "* ]] || unset "FLAGS[$k]"; done; fi
 if [ "${1:-}" = "build" ]; then
     mkdir -p build_ab
@@ -21,11 +20,11 @@ if [ "${1:-}" = "build" ]; then
         echo "built build_ab/libgfxb200_$v.so (${FLAGS[$v]})"
     done
 elif [ "${1:-}" = "run" ]; then
-    for lib in gfxexp_b200/libgfxb200.so build_ab/libgfxb200_wide.so build_ab/libgfxb200_push.so build_ab/libgfxb200_spheres.so build_ab/libgfxb200_all.so; do
+    for lib in gfxexp_b200/libgfxb200.so build_ab/libgfxb200_nosphere.so build_ab/libgfxb200_chainpick.so; do
         [ -f "$lib" ] || continue
         echo "== $lib"
         GFXB200_LIB=$lib timeout -s KILL 300 python -m pytest tests -m gpu -x -q --deselect tests/test_gpu_host_cpp.py 2>&1 | tail -2
-        GFXB200_LIB=$lib timeout -s KILL 120 python bench.py --steps 20 --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(round(d['ms_per_step'],3), {k:round(v['ms_per_launch'],3) for k,v in d['roofline']['per_kernel'].items()})"
+        GFXB200_LIB=$lib timeout -s KILL 120 python bench.py --steps 20 --no-cpu-baseline --headline-only 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(round(d['ms_per_step'],3), {k:round(v['ms_per_launch'],3) for k,v in d['roofline']['per_kernel'].items()})"
         GFXB200_LIB=$lib timeout -s KILL 120 python tools/stage_bench.py --only pathtrace 2>/dev/null | tail -1 | cut -c1-160
     done
 else
