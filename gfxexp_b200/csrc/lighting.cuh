@@ -291,6 +291,64 @@ GFX_D bool sampleLightUnlessDark(const DevScene &s, float ul, float u0, float u1
     return false;
 }
 
+// sampleLightUnlessDark in two halves for the two-phase candidate loop of the ReSTIR initial pass (restir.cu):
+//   classifyLight    the pick and step 0 (bounding sphere) -> kLightDark, or the light's key with bit 31 = "the dark tests may
+//                    be used" (the selection density is a positive finite number; otherwise the exact path decides);
+//   finishLightSample steps 1 and 2 from the key alone (density and instance slot come from the record's H3 copy).
+constexpr uint32_t kLightDark = 0xFFFFFFFFu;
+constexpr uint32_t kLightCullable = 0x80000000u;
+GFX_D uint32_t classifyLight(const DevScene &s, float ul, const f3 &shadingPoint, const f3 &shadingNormal, float vOutLocalZ) {
+    const LightPick pick = pickLight(s, ul);
+    if (pick.key & kPickNone)
+        return kPickNone; // every "no light" key is the same to the caller
+    const f3 dc = f3(pick.sphere.x, pick.sphere.y, pick.sphere.z) - shadingPoint;
+    const float r = pick.sphere.w;
+    const float t = -(dot(dc, shadingNormal) * vOutLocalZ);
+    const float margin = t - 1.001f * r * fabsf(vOutLocalZ);
+    if (r >= 0.0f && margin > 0.0f && margin * margin > 8e-6f * (sqLength(dc) + r * r) * (vOutLocalZ * vOutLocalZ))
+        return kLightDark;
+    return pick.key | (r >= 0.0f ? kLightCullable : 0u);
+}
+// returns true for "dark"; otherwise *lightSample / *areaPDensity are sampleLight's, bit for bit
+GFX_D bool finishLightSample(const DevScene &s, uint32_t code, float u0, float u1, const f3 &shadingPoint, const f3 &shadingNormal,
+                             float vOutLocalZ, LightSample* lightSample, float* areaPDensity) {
+    if (code & kPickNone) {
+        *areaPDensity = 0.0f;
+        return false;
+    }
+    const bool cullable = (code & kLightCullable) != 0; // implies density > 0
+    const float4* e = s.lightTris + kLightTriStride * (size_t)(code & 0x3FFFFFFFu);
+    const F8 h1 = ldg256(e + 2), h2 = ldg256(e + 4);
+    const f3 pA(h1.lo.x, h1.lo.y, h1.lo.z), pB(h1.lo.w, h1.hi.x, h1.hi.y), pC(h1.hi.z, h1.hi.w, h2.lo.x);
+    float bcA, bcB, bcC;
+    squareToTriangle(u0, u1, &bcA, &bcB, &bcC);
+    const f3 position = bcA * pA + bcB * pB + bcC * pC;
+
+    const float k = 1e-6f; // (1e-3)^2
+    const f3 d = position - shadingPoint;
+    const float dd = sqLength(d);
+    const float b = dot(d, shadingNormal) * vOutLocalZ; // < 0: light and viewer on opposite sides of the surface
+    if (cullable && b < 0.0f && b * b > k * dd * (vOutLocalZ * vOutLocalZ)) {
+        *areaPDensity = 1.0f;
+        return true;
+    }
+    const F8 h3 = ldg256(e + 6);
+    const float density = h3.hi.z;
+    *areaPDensity = density;
+    const f3 nA(h2.lo.y, h2.lo.z, h2.lo.w), nB(h2.hi.x, h2.hi.y, h2.hi.z), nC(h2.hi.w, h3.lo.x, h3.lo.y);
+    f3 normal = bcA * nA + bcB * nB + bcC * nC;
+    normal = applyNormalMatrix(s, __float_as_uint(h3.hi.w), normal);
+    const float a = dot(d, normal); // > 0: the emitter faces away from the shading point
+    if (cullable && a > 0.0f && a * a > k * dd * sqLength(normal))
+        return true;
+
+    lightSample->position = position;
+    lightSample->atInfinity = 0;
+    lightSample->normal = normalize(normal);
+    lightSample->emittance = f3(h3.lo.z, h3.lo.w, h3.hi.x);
+    return false;
+}
+
 GFX_D bool traceVisibility(const DevScene &s, const f3 &org, const f3 &dir, float tmax) {
     // ray statistics: one atomic per warp per call site (lanes currently active here)
     const uint32_t active = __activemask();

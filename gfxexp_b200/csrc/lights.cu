@@ -170,7 +170,7 @@ __global__ void k_lightTris(DevScene scene, const uint32_t* __restrict__ emissiv
         o[4] = make_float4(pC.z, a1.x, a1.y, a1.z);
         o[5] = make_float4(b1.x, b1.y, b1.z, c1.x);
         o[6] = make_float4(c1.y, c1.z, emittance.x, emittance.y);
-        o[7] = make_float4(emittance.z, radius, 0.0f, 0.0f);
+        o[7] = make_float4(emittance.z, radius, 0.0f, __uint_as_float(im.x)); // .z: density, k_pickLightProbs
     }
 }
 
@@ -330,6 +330,7 @@ __global__ void k_pickLightProbs(DevScene scene, const uint2* __restrict__ piece
     const float recArea = rec[1].z;
     const float density = lightProb * recArea; // sampleLight's areaPDensity (restir_di_shared.h:409,496), the one product
     rec[1].x = density;
+    rec[7].z = density;
     rec[0].w = (density > 0.0f && isfinite(density)) ? rec[7].y : -1.0f;
 }
 

@@ -19,118 +19,30 @@ namespace gfx {
 // PHASE 1: candidates + recPDF, the visibility ray is only *requested* (wavefront form).
 // PHASE 2: applies the answered visibility, then the temporal merge.
 //
-// PHASE 1 runs the candidate loop through a per-warp survivor queue in shared memory.  ncu on the lock-step loop (round 2,
-// profiles/r02_summary.md): ~70 % of the candidates are dark and leave after the staged light fetch, so the evaluation of the
-// others (BSDF, geometry term, reservoir update: 58 % of the kernel's issue slots) ran with 9.4 of 32 lanes.  Here a lane only
-// *generates* its pixel's candidate i (4 RNG draws, flattened light pick, staged fetch with the dark tests) and appends the
-// survivors - light sample, density, the acceptance draw, the owning lane - to the warp's queue (ballot + popc, no atomics);
-// whenever 32 are queued every lane evaluates one of them against the OWNER's shading state (also in shared memory), and the
-// owners then apply their results in queue order, which is candidate order - so each pixel sees exactly the reference's
-// sequence of Reservoir::update calls (restir_di_shared.h:118-125) and draws.
-constexpr uint32_t kRisPixWords = 26, kRisEntWords = 16, kRisQueueSlots = 64;
-struct RisWarpShared {
-    float pix[kRisPixWords][32];             // owner state: position 0-2, vOutLocal 3-5, tangent 6-8, bitangent 9-11, normal 12-14,
-                                             // bsdf: type 15, diffuse 16-18, specularF0 19-21, roughness 22
-    float ent[kRisEntWords][kRisQueueSlots]; // 0 owner lane, 1 u, 2 ul, 3 u0, 4 u1, 5-7 position (-> weight, targetDensity, skip
-                                             // after evaluation), 8-10 normal, 11-13 emittance, 14 density
-};
+// PHASE 1 runs the candidate loop in two phases (TWO_PHASE).  ncu on the lock-step loop (round 2, profiles/r02_summary.md):
+// ~70 % of the candidates are dark and leave after the staged light fetch, so everything after the bounding-sphere test - 74 %
+// of the kernel's issue slots - ran with 9-16 of 32 lanes.  Phase A walks all 2^n candidates in lock step but only draws ul,
+// picks the light and tests its bounding sphere (the other three draws of a candidate are skipped with the LCG's 4-step
+// jump), leaving per lane a bit mask of survivors and their keys in shared memory.  Phase B is a per-lane loop over the
+// lane's own survivors, in candidate order: the PCG32 state at the candidate is rebuilt from the jump table, u0 / u1 / u
+// are drawn, and the candidate runs steps 1-2 of the light fetch, the BSDF and the reservoir update exactly as in the
+// lock-step loop.  A warp then iterates max-over-lanes(#survivors) ~ 20 times instead of 32, with the expensive part at
+// ~70 % instead of 30 % lane utilisation; each pixel still sees the reference's sequence of Reservoir::update calls
+// (restir_di_shared.h:118-125) and draws, so results are bit-identical.
+constexpr uint32_t kRisMaxCandidates = 32; // TWO_PHASE keeps one key per candidate and thread in shared memory
 
-struct RisSelection {
-    float ul, u0, u1;
-    bool has;
-    float sumWeights, targetDensity;
-};
-
-// evaluates queue entries [0, n) (n <= 32), lets the owners apply them in order, moves the rest of the queue to the front
-GFX_D void risFlush(const DevScene &s, RisWarpShared &w, uint32_t lane, uint32_t n, uint32_t* qCount, uint64_t* mySlots,
-                    RisSelection* sel) {
-    __syncwarp();
-    if (lane < n) {
-        const uint32_t owner = __float_as_uint(w.ent[0][lane]);
-        LightSample ls;
-        ls.position = f3(w.ent[5][lane], w.ent[6][lane], w.ent[7][lane]);
-        ls.normal = f3(w.ent[8][lane], w.ent[9][lane], w.ent[10][lane]);
-        ls.emittance = f3(w.ent[11][lane], w.ent[12][lane], w.ent[13][lane]);
-        ls.atInfinity = 0;
-        const float probDensity = w.ent[14][lane];
-        const f3 positionInWorld(w.pix[0][owner], w.pix[1][owner], w.pix[2][owner]);
-        const f3 vOutLocal(w.pix[3][owner], w.pix[4][owner], w.pix[5][owner]);
-        ReferenceFrame shadingFrame;
-        shadingFrame.tangent = f3(w.pix[6][owner], w.pix[7][owner], w.pix[8][owner]);
-        shadingFrame.bitangent = f3(w.pix[9][owner], w.pix[10][owner], w.pix[11][owner]);
-        shadingFrame.normal = f3(w.pix[12][owner], w.pix[13][owner], w.pix[14][owner]);
-        BSDF bsdf;
-        bsdf.type = __float_as_uint(w.pix[15][owner]);
-        bsdf.diffuseColor = f3(w.pix[16][owner], w.pix[17][owner], w.pix[18][owner]);
-        bsdf.specularF0Color = f3(w.pix[19][owner], w.pix[20][owner], w.pix[21][owner]);
-        bsdf.roughness = w.pix[22][owner];
-        // Dead candidates (light faces away, or lies below the shading horizon within the margin of the dark tests)
-        // contribute exactly RGB(0) (performDirectLighting returns RGB(0) before any arithmetic when lpCos <= 0, and the
-        // BRDFs return RGB(0) when vGiven.z * vSampled.z <= 0), so weight = +0 / probDensity = +0 and the reservoir is
-        // untouched: skip the three IEEE divisions, which would all take the 0/x slow path.
-        const f3 cont = performDirectLighting<false>(s, positionInWorld, vOutLocal, shadingFrame, bsdf, ls);
-        const bool deadCont = cont.x == 0.0f && cont.y == 0.0f && cont.z == 0.0f;
-        const bool skip = deadCont && probDensity > 0.0f;
-        const float targetDensity = convertToWeight(cont);
-        w.ent[5][lane] = skip ? 0.0f : targetDensity / probDensity;
-        w.ent[6][lane] = targetDensity;
-        w.ent[7][lane] = skip ? 1.0f : 0.0f;
-    }
-    __syncwarp();
-    uint32_t mine = (uint32_t)(*mySlots & ((n >= 32 ? 0ull : (1ull << n)) - 1ull));
-    while (mine) {
-        const uint32_t slot = (uint32_t)__ffs((int)mine) - 1u;
-        mine &= mine - 1u;
-        if (w.ent[7][slot] != 0.0f)
-            continue;
-        const float weight = w.ent[5][slot];
-        sel->sumWeights += weight;
-        if (w.ent[1][slot] < weight / sel->sumWeights) {
-            sel->ul = w.ent[2][slot];
-            sel->u0 = w.ent[3][slot];
-            sel->u1 = w.ent[4][slot];
-            sel->has = true;
-            sel->targetDensity = w.ent[6][slot];
-        }
-    }
-    __syncwarp();
-    const uint32_t rest = *qCount - n;
-    if (rest) { // only after a full flush (n == 32): slots 32 .. 32 + rest - 1 move to the front
-        float moved[kRisEntWords];
-        if (lane < rest) {
-#pragma unroll
-            for (uint32_t k = 0; k < kRisEntWords; ++k)
-                moved[k] = w.ent[k][n + lane];
-        }
-        __syncwarp();
-        if (lane < rest) {
-#pragma unroll
-            for (uint32_t k = 0; k < kRisEntWords; ++k)
-                w.ent[k][lane] = moved[k];
-        }
-    }
-    *mySlots = n >= 32 ? (*mySlots >> 32) : 0ull;
-    *qCount = rest;
-}
-
-template <bool withTemporalRIS, bool useUnbiasedEstimator, int PHASE, bool QUEUE>
-GFX_D bool risPixel(const DevScene &s, const DevFrame &f, const DevFrameParams &p, RayRequest* request, RisWarpShared* warpShared) {
+template <bool withTemporalRIS, bool useUnbiasedEstimator, int PHASE, bool TWO_PHASE>
+GFX_D bool risPixel(const DevScene &s, const DevFrame &f, const DevFrameParams &p, RayRequest* request, uint32_t* candidateKeys) {
     // optix_restir_di_kernels.cu:14-287
-    uint32_t x = blockIdx.x * 8 + threadIdx.x;
-    uint32_t y = p.y0 + blockIdx.y * 8 + threadIdx.y;
-    bool valid = x < f.W && y < p.y1;
-    if (!QUEUE && !valid)
+    const uint32_t x = blockIdx.x * 8 + threadIdx.x;
+    const uint32_t y = p.y0 + blockIdx.y * 8 + threadIdx.y;
+    if (x >= f.W || y >= p.y1)
         return false;
-    if (!valid) { // the queued form keeps the lane for the warp's queue: it reads a pixel of the image and writes nothing
-        x = min(x, f.W - 1);
-        y = min(y, p.y1 - 1);
-    }
     const size_t pix = (size_t)y * f.W + x;
     const uint32_t curBufIdx = p.bufferIndex;
 
     const uint4 gb0 = f.gb0[curBufIdx][pix];
-    valid = valid && gb0.x != 0xFFFFFFFFu;
-    if (!QUEUE && !valid)
+    if (gb0.x == 0xFFFFFFFFu)
         return false;
     const float4 gb2 = f.gb2[curBufIdx][pix];
     const uint4 gb3 = f.gb3[curBufIdx][pix];
@@ -150,7 +62,7 @@ GFX_D bool risPixel(const DevScene &s, const DevFrame &f, const DevFrameParams &
     const f3 shadingTangentInWorld = decodeVector(gb3.y);
     const ReferenceFrame shadingFrame(shadingNormalInWorld, shadingTangentInWorld);
     const f3 vOutLocal = shadingFrame.toLocal(vOut);
-    const BSDF bsdf = setupBsdf(s, valid ? gb3.w : 0u);
+    const BSDF bsdf = setupBsdf(s, gb3.w);
 
     const uint32_t curResIndex = p.currentReservoirIndex;
     Reservoir reservoir;
@@ -167,70 +79,56 @@ GFX_D bool risPixel(const DevScene &s, const DevFrame &f, const DevFrameParams &
     float selUl = 0.0f, selU0 = 0.0f, selU1 = 0.0f;
     bool hasSelection = false;
     float sumWeights = 0.0f;
-    if constexpr (QUEUE) {
-        RisWarpShared &w = *warpShared;
-        const uint32_t lane = (threadIdx.x + threadIdx.y * blockDim.x) & 31u;
-        {
-            const float state[kRisPixWords] = { positionInWorld.x, positionInWorld.y, positionInWorld.z, vOutLocal.x, vOutLocal.y, vOutLocal.z,
-                shadingFrame.tangent.x, shadingFrame.tangent.y, shadingFrame.tangent.z,
-                shadingFrame.bitangent.x, shadingFrame.bitangent.y, shadingFrame.bitangent.z,
-                shadingFrame.normal.x, shadingFrame.normal.y, shadingFrame.normal.z, __uint_as_float(bsdf.type),
-                bsdf.diffuseColor.x, bsdf.diffuseColor.y, bsdf.diffuseColor.z,
-                bsdf.specularF0Color.x, bsdf.specularF0Color.y, bsdf.specularF0Color.z, bsdf.roughness, 0.0f, 0.0f, 0.0f };
-#pragma unroll
-            for (uint32_t k = 0; k < 23; ++k)
-                w.pix[k][lane] = state[k];
-        }
-        RisSelection sel{ 0.0f, 0.0f, 0.0f, false, 0.0f, 0.0f };
-        uint32_t qCount = 0;
-        uint64_t mySlots = 0;
+    if (TWO_PHASE && numCandidates <= kRisMaxCandidates) {
+        uint32_t* myKeys = candidateKeys + (threadIdx.x + threadIdx.y * blockDim.x); // [candidate][64 threads]
+        const uint64_t state0 = rng.state;
+        // ---- phase A: ul, light pick, bounding sphere
+        uint32_t survivors = 0;
         for (uint32_t i = 0; i < numCandidates; ++i) {
-            bool survivor = false;
-            float ul = 0.0f, u0 = 0.0f, u1 = 0.0f, u = 0.0f, probDensity = 0.0f;
-            LightSample lightSample = emptyLightSample();
-            if (valid) {
-                ul = rng.getFloat0cTo1o();
-                u0 = rng.getFloat0cTo1o();
-                u1 = rng.getFloat0cTo1o();
-                // staged fetch of the light record: certainly-dark candidates stop early (their contribution is exactly
-                // RGB(0): the reservoir is untouched and only the acceptance draw is consumed)
-                survivor = !sampleLightUnlessDark(s, ul, u0, u1, positionInWorld, shadingNormalInWorld, vOutLocal.z, &lightSample, &probDensity);
-                u = rng.getFloat0cTo1o();
-            }
-            const uint32_t mask = __ballot_sync(0xFFFFFFFFu, survivor);
-            if (survivor) {
-                const uint32_t slot = qCount + __popc(mask & ((1u << lane) - 1u));
-                w.ent[0][slot] = __uint_as_float(lane);
-                w.ent[1][slot] = u;
-                w.ent[2][slot] = ul;
-                w.ent[3][slot] = u0;
-                w.ent[4][slot] = u1;
-                w.ent[5][slot] = lightSample.position.x;
-                w.ent[6][slot] = lightSample.position.y;
-                w.ent[7][slot] = lightSample.position.z;
-                w.ent[8][slot] = lightSample.normal.x;
-                w.ent[9][slot] = lightSample.normal.y;
-                w.ent[10][slot] = lightSample.normal.z;
-                w.ent[11][slot] = lightSample.emittance.x;
-                w.ent[12][slot] = lightSample.emittance.y;
-                w.ent[13][slot] = lightSample.emittance.z;
-                w.ent[14][slot] = probDensity; // probToSampleCurLightType = 1
-                mySlots |= 1ull << slot;
-            }
-            qCount += __popc(mask);
-            if (qCount >= 32)
-                risFlush(s, w, lane, 32, &qCount, &mySlots, &sel);
+            const float ul = pcg32Float(rng.state);
+            rng.state = rng.state * kPcg32Jump4.mul[1] + kPcg32Jump4.add[1]; // the candidate's four draws
+            const uint32_t code = classifyLight(s, ul, positionInWorld, shadingNormalInWorld, vOutLocal.z);
+            myKeys[i * 64] = code;
+            survivors |= code != kLightDark ? (1u << i) : 0u;
         }
-        if (qCount)
-            risFlush(s, w, lane, qCount, &qCount, &mySlots, &sel);
-        selUl = sel.ul;
-        selU0 = sel.u0;
-        selU1 = sel.u1;
-        hasSelection = sel.has;
-        sumWeights = sel.sumWeights;
-        selectedTargetDensity = sel.targetDensity;
-        if (!valid)
-            return false;
+        // ---- phase B: this lane's survivors, in candidate order
+        uint32_t selIdx = 0;
+        while (survivors) {
+            const uint32_t i = (uint32_t)__ffs((int)survivors) - 1u;
+            survivors &= survivors - 1u;
+            const uint32_t code = myKeys[i * 64];
+            uint64_t st = state0 * __ldg(&kPcg32Jump4.mul[i]) + __ldg(&kPcg32Jump4.add[i]); // state before the candidate's ul
+            st = st * 6364136223846793005ULL + 1;
+            const float u0 = pcg32Float(st);
+            st = st * 6364136223846793005ULL + 1;
+            const float u1 = pcg32Float(st);
+            st = st * 6364136223846793005ULL + 1;
+            LightSample lightSample = emptyLightSample();
+            float probDensity;
+            if (finishLightSample(s, code, u0, u1, positionInWorld, shadingNormalInWorld, vOutLocal.z, &lightSample, &probDensity))
+                continue;
+            const f3 cont = performDirectLighting<false>(s, positionInWorld, vOutLocal, shadingFrame, bsdf, lightSample);
+            const bool deadCont = cont.x == 0.0f && cont.y == 0.0f && cont.z == 0.0f;
+            if (deadCont && probDensity > 0.0f)
+                continue;
+            const float targetDensity = convertToWeight(cont);
+            const float weight = targetDensity / probDensity;
+            const float u = pcg32Float(st);
+            sumWeights += weight;
+            if (u < weight / sumWeights) {
+                selIdx = i;
+                hasSelection = true;
+                selectedTargetDensity = targetDensity;
+            }
+        }
+        if (hasSelection) { // the winner's three primary sample values, from the stream position of its candidate
+            uint64_t st = state0 * __ldg(&kPcg32Jump4.mul[selIdx]) + __ldg(&kPcg32Jump4.add[selIdx]);
+            selUl = pcg32Float(st);
+            st = st * 6364136223846793005ULL + 1;
+            selU0 = pcg32Float(st);
+            st = st * 6364136223846793005ULL + 1;
+            selU1 = pcg32Float(st);
+        }
     }
     else {
     for (uint32_t i = 0; i < numCandidates; ++i) {
@@ -394,16 +292,16 @@ GFX_D bool risPixel(const DevScene &s, const DevFrame &f, const DevFrameParams &
     return false;
 }
 
-template <bool withTemporalRIS, bool useUnbiasedEstimator, int PHASE, bool QUEUE = false>
+template <bool withTemporalRIS, bool useUnbiasedEstimator, int PHASE, bool TWO_PHASE = false>
 __global__ void __launch_bounds__(64) k_initialAndTemporalRIS(DevScene s, DevFrame f, DevFrameParams p) {
-    static_assert(!QUEUE || PHASE == 1, "the survivor queue belongs to the wavefront candidate pass");
+    static_assert(!TWO_PHASE || PHASE == 1, "the two-phase candidate loop belongs to the wavefront candidate pass");
     RayRequest request;
-    RisWarpShared* warpShared = nullptr;
-    if constexpr (QUEUE) {
-        __shared__ RisWarpShared shared[2]; // one per warp of the 8x8 block (rows 0-3, rows 4-7)
-        warpShared = &shared[threadIdx.y >> 2];
+    uint32_t* candidateKeys = nullptr;
+    if constexpr (TWO_PHASE) {
+        __shared__ uint32_t keys[kRisMaxCandidates * 64]; // [candidate][thread of the 8x8 block]
+        candidateKeys = keys;
     }
-    const bool want = risPixel<withTemporalRIS, useUnbiasedEstimator, PHASE, QUEUE>(s, f, p, &request, warpShared);
+    const bool want = risPixel<withTemporalRIS, useUnbiasedEstimator, PHASE, TWO_PHASE>(s, f, p, &request, candidateKeys);
     if (PHASE == 1)
         enqueueRay(f, s.rayCounter, want, request);
 }
@@ -680,13 +578,13 @@ int launchReSTIR(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* params
     // the single-kernel form with inline traversal (same results; kept for A/B measurements).
     static const bool megakernel = getenv("GFX_MEGAKERNEL") != nullptr;
     const bool wave = !megakernel;
-    // GFX_RIS_QUEUE=1: candidate loop through the per-warp survivor queue (see risFlush); 0 = lock-step loop
-    static const bool risQueue = getenv("GFX_RIS_QUEUE") && getenv("GFX_RIS_QUEUE")[0] == '1';
+    // the two-phase candidate loop (see risPixel) is the default; GFX_RIS_TWO_PHASE=0 selects the lock-step loop (A/B)
+    static const bool twoPhase = !(getenv("GFX_RIS_TWO_PHASE") && getenv("GFX_RIS_TWO_PHASE")[0] == '0');
 #define RIS_LAUNCH(T, U) \
     if (wave && p.reuseVisibility) { \
         int rc_ = resetVisibilityQueue(ctx, stream); if (rc_) return rc_; \
         { GFX_TIMED(ctx, stream, "ris_candidates"); \
-          if (risQueue) k_initialAndTemporalRIS<T, U, 1, true><<<grid, block, 0, stream>>>(s, f, p); \
+          if (twoPhase) k_initialAndTemporalRIS<T, U, 1, true><<<grid, block, 0, stream>>>(s, f, p); \
           else k_initialAndTemporalRIS<T, U, 1, false><<<grid, block, 0, stream>>>(s, f, p); } ctx->launches++; \
         rc_ = traceVisibilityQueue(ctx, stream); if (rc_) return rc_; \
         { GFX_TIMED(ctx, stream, "ris_resolve_temporal"); k_initialAndTemporalRIS<T, U, 2><<<grid, block, 0, stream>>>(s, f, p); } \

@@ -39,7 +39,8 @@ struct DevMesh {
 //        cull: degenerate area, or the selection density lightProb * recArea is not a positive finite number) and the area
 //        density lightProb * recArea; a copy of H0 sits in the pick guide, so only the 6 % impure buckets read it from here
 //   H1 = q2 (pA.xyz, pB.x) q3 (pB.yz, pC.xy)     H2 = q4 (pC.z, nA.xyz) q5 (nB.xyz, nC.x)      -> sample position
-//   H3 = q6 (nC.yz, E.rg) q7 (E.b, radius before the density switch, -, -)                     -> light normal, emittance
+//   H3 = q6 (nC.yz, E.rg) q7 (E.b, radius before the density switch, density, instance slot)   -> light normal, emittance
+//        (the second copy of density / instance slot serves callers that kept only the key of a pick, see classifyLight)
 // Positions, normals, emittance are produced by the very expressions of sampleLight (restir_di_shared.h:417-425, 485-511),
 // the density by the products of DiscreteDistribution1D::sample's probabilities (:356-409) times 2 / |cross| (:496), so reading
 // them is bit-identical to recomputing them.

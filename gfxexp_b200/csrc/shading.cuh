@@ -35,6 +35,32 @@ struct PCG32RNG { // common_shared.h:116-138
     }
 };
 
+// PCG32 jump-ahead: the state after k more draws is mul[k] * state + add[k] (the LCG composed k times); tables for
+// k = 0, 4, ..., 124 = "start of candidate i" of a 4-draws-per-candidate loop, built at compile time.
+struct Pcg32Jump {
+    uint64_t mul[33], add[33];
+    constexpr Pcg32Jump() : mul(), add() {
+        uint64_t m = 1, a = 0;
+        for (int i = 0; i <= 32; ++i) {
+            mul[i] = m;
+            add[i] = a;
+            for (int k = 0; k < 4; ++k) { // compose with one more step: s -> M s + 1
+                m = m * 6364136223846793005ULL;
+                a = a * 6364136223846793005ULL + 1ULL;
+            }
+        }
+    }
+};
+__device__ constexpr Pcg32Jump kPcg32Jump4 = Pcg32Jump();
+GFX_D uint32_t pcg32Output(uint64_t oldstate) { // the XSH-RR output function of PCG32RNG::next on a given state
+    const uint32_t xorshifted = (uint32_t)(((oldstate >> 18u) ^ oldstate) >> 27u);
+    const uint32_t rot = (uint32_t)(oldstate >> 59u);
+    return (xorshifted >> rot) | (xorshifted << ((-(int32_t)rot) & 31));
+}
+GFX_D float pcg32Float(uint64_t oldstate) {
+    return __uint_as_float((pcg32Output(oldstate) >> 9) | 0x3f800000u) - 1.0f;
+}
+
 struct DiscreteDistribution1D { // common_shared.h:175-276 (CDF variant, USE_WALKER_ALIAS_METHOD off)
     const float* weights = nullptr;
     const float* cdf = nullptr;
