@@ -308,6 +308,14 @@ def scene_aabb(scene):
     return scene._aabb_cache
 
 
+OP_LIGHT_DIST, OP_GBUFFER, OP_RESTIR, OP_PEER_PUSH_ROWS, OP_PEER_SIGNAL, OP_PEER_WAIT = 0, 1, 2, 3, 4, 5
+
+
+class GfxBatchOp(C.Structure):
+    _fields_ = [("op", c_u32), ("a", c_u32), ("b", c_u32), ("c", c_u32), ("d", c_u32), ("e", c_u32), ("pad", c_u32 * 2),
+                ("params", GfxFrameParams)]
+
+
 _DECLS = {
     "gfx_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "gfx_ctx_destroy": (None, [C.c_void_p]),
@@ -323,6 +331,7 @@ _DECLS = {
     "gfx_trace_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, c_u32, C.c_void_p, C.c_int]),
     "gfx_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, c_u32, C.c_void_p, C.c_int]),
     "gfx_light_dist_build": (C.c_int, [C.c_void_p, C.c_void_p, c_u32]),
+    "gfx_launch_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxBatchOp), c_u32]),
     "gfx_light_pick_debug": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, c_u32, C.c_void_p, C.c_void_p]),
     "gfx_light_dist_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(c_f)]),
     "gfx_frame_create": (C.c_int, [C.c_void_p, c_u32, c_u32]),

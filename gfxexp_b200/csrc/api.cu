@@ -539,6 +539,28 @@ int gfx_light_dist_build(gfx_ctx* ctx, void* stream, uint32_t bufferIndex) {
     return buildLightDistributions(ctx, (cudaStream_t)stream, bufferIndex);
 }
 
+int gfx_launch_batch(gfx_ctx* ctx, void* stream, const GfxBatchOp* ops, uint32_t numOps) {
+    CHECK_CTX(ctx);
+    if (!ops && numOps)
+        return GFX_ERR_INVALID_ARGUMENT;
+    for (uint32_t i = 0; i < numOps; ++i) {
+        const GfxBatchOp &o = ops[i];
+        int rc = GFX_ERR_INVALID_ARGUMENT;
+        switch (o.op) {
+        case GFX_OP_LIGHT_DIST: rc = gfx_light_dist_build(ctx, stream, o.a); break;
+        case GFX_OP_GBUFFER: rc = gfx_gbuffer_launch(ctx, stream, &o.params); break;
+        case GFX_OP_RESTIR: rc = gfx_restir_launch(ctx, stream, &o.params, (int)o.a); break;
+        case GFX_OP_PEER_PUSH_ROWS: rc = gfx_peer_push_rows(ctx, stream, o.a, (int)o.b, o.c, o.d, o.e); break;
+        case GFX_OP_PEER_SIGNAL: rc = gfx_peer_signal(ctx, stream, o.a, o.b, o.c); break;
+        case GFX_OP_PEER_WAIT: rc = gfx_peer_wait(ctx, stream, o.a, o.b); break;
+        default: ctx->setError("gfx_launch_batch: unknown op"); break;
+        }
+        if (rc != GFX_OK)
+            return rc;
+    }
+    return GFX_OK;
+}
+
 int gfx_light_pick_debug(gfx_ctx* ctx, void* stream, const float* ul, uint32_t n, uint32_t* keysFlat, uint32_t* keysChain) {
     CHECK_CTX(ctx);
     if (!ctx->scene.uploaded || ctx->scene.pickDirty)

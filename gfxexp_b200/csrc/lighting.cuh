@@ -136,9 +136,17 @@ struct LightPick {
     float density;     // lightProb * recArea
     uint32_t instSlot;
 };
+GFX_D F8 pickGuideFetch(const DevScene &s, float ul) { // the guide entry of ul's bucket (issue early, resolve later)
+    const uint32_t b = min(dm_f2uint(ul * (float)kPickGuideSize), kPickGuideSize - 1); // exact: a power-of-two product, floored
+    return ldg256(s.pickGuide + 2 * (size_t)b);
+}
+GFX_D LightPick pickLightFromGuide(const DevScene &s, float ul, const F8 &g);
 GFX_D LightPick pickLight(const DevScene &s, float ul) {
+#ifndef GFX_AB_CHAIN_PICK
+    return pickLightFromGuide(s, ul, pickGuideFetch(s, ul));
+#else
     LightPick r;
-#ifdef GFX_AB_CHAIN_PICK // A/B: the definition instead of its flattened form
+    // A/B (-DGFX_AB_CHAIN_PICK): the definition instead of its flattened form
     float unusedProb;
     r.key = chainPickLightTriangle(s, ul, &unusedProb);
     if (!(r.key & kPickNone)) {
@@ -149,8 +157,9 @@ GFX_D LightPick pickLight(const DevScene &s, float ul) {
     }
     return r;
 #endif
-    const uint32_t b = min(dm_f2uint(ul * (float)kPickGuideSize), kPickGuideSize - 1); // exact: a power-of-two product, floored
-    const F8 g = ldg256(s.pickGuide + 2 * (size_t)b);
+}
+GFX_D LightPick pickLightFromGuide(const DevScene &s, float ul, const F8 &g) {
+    LightPick r;
     const uint32_t head = __float_as_uint(g.lo.x);
     if (head & kPickPure) {
         r.key = head & ~kPickPure;
@@ -297,8 +306,9 @@ GFX_D bool sampleLightUnlessDark(const DevScene &s, float ul, float u0, float u1
 //   finishLightSample steps 1 and 2 from the key alone (density and instance slot come from the record's H3 copy).
 constexpr uint32_t kLightDark = 0xFFFFFFFFu;
 constexpr uint32_t kLightCullable = 0x80000000u;
-GFX_D uint32_t classifyLight(const DevScene &s, float ul, const f3 &shadingPoint, const f3 &shadingNormal, float vOutLocalZ) {
-    const LightPick pick = pickLight(s, ul);
+GFX_D uint32_t classifyLight(const DevScene &s, float ul, const F8 &guideEntry, const f3 &shadingPoint, const f3 &shadingNormal,
+                             float vOutLocalZ) {
+    const LightPick pick = pickLightFromGuide(s, ul, guideEntry);
     if (pick.key & kPickNone)
         return kPickNone; // every "no light" key is the same to the caller
     const f3 dc = f3(pick.sphere.x, pick.sphere.y, pick.sphere.z) - shadingPoint;

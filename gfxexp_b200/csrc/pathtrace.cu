@@ -22,6 +22,13 @@
 // float4 planes indexed by pixel.  The RNG draw order of every pixel is the reference's.
 #include "pathtrace.cuh"
 
+// occupancy knob of the first-hit / bounce kernels (A/B: tools/ab_flags.sh); unset = ptxas decides
+#ifdef GFX_BOUNCE_MIN_BLOCKS
+#define GFX_BOUNCE_BOUNDS GFX_BOUNCE_BOUNDS
+#else
+#define GFX_BOUNCE_BOUNDS __launch_bounds__(64)
+#endif
+
 namespace gfx {
 
 // One path vertex: NEE + next direction.  The ReGIR variant (regir/gpu_kernels/optix_pathtracing_kernels.cu) draws its
@@ -55,7 +62,7 @@ GFX_D void shadeVertexVariant(const DevScene &s, const DevRegir &rg, const DevFr
 
 // pathTrace_rayGen_generic up to the path extension loop (:73-160)
 template <bool REGIR>
-__global__ void __launch_bounds__(64) k_ptFirstHit(DevScene s, DevFrame f, DevFrameParams p, DevPathState ps, DevRegir rg) {
+__global__ void GFX_BOUNCE_BOUNDS k_ptFirstHit(DevScene s, DevFrame f, DevFrameParams p, DevPathState ps, DevRegir rg) {
     const uint32_t x = blockIdx.x * 8 + threadIdx.x;
     const uint32_t y = p.y0 + blockIdx.y * 8 + threadIdx.y;
     const uint32_t lane = (threadIdx.x + threadIdx.y * blockDim.x) & 31u;
@@ -103,7 +110,7 @@ __global__ void __launch_bounds__(64) k_ptFirstHit(DevScene s, DevFrame f, DevFr
 // pathTrace_closestHit_generic (:218-300) + the bookkeeping of the path extension loop (:161-194) for the
 // compacted queue of live paths; `round` = pathLength - 2 selects the queue parity and the counters.
 template <bool REGIR>
-__global__ void __launch_bounds__(64) k_ptBounce(DevScene s, DevFrame f, DevFrameParams p, DevPathState ps, DevRegir rg, uint32_t round,
+__global__ void GFX_BOUNCE_BOUNDS k_ptBounce(DevScene s, DevFrame f, DevFrameParams p, DevPathState ps, DevRegir rg, uint32_t round,
                                                  uint32_t maxLengthTerminate) {
     const uint32_t curQueue = round & 1u, nextQueue = curQueue ^ 1u;
     const uint32_t* roundCounters = ps.counters + 4 * round;

@@ -83,13 +83,23 @@ GFX_D bool risPixel(const DevScene &s, const DevFrame &f, const DevFrameParams &
         uint32_t* myKeys = candidateKeys + (threadIdx.x + threadIdx.y * blockDim.x); // [candidate][64 threads]
         const uint64_t state0 = rng.state;
         // ---- phase A: ul, light pick, bounding sphere
+        // (two candidates per trip so that two guide reads are in flight: the loop is a chain of dependent L2 round trips)
         uint32_t survivors = 0;
-        for (uint32_t i = 0; i < numCandidates; ++i) {
-            const float ul = pcg32Float(rng.state);
+        for (uint32_t i = 0; i < numCandidates; i += 2) {
+            const float ulA = pcg32Float(rng.state);
             rng.state = rng.state * kPcg32Jump4.mul[1] + kPcg32Jump4.add[1]; // the candidate's four draws
-            const uint32_t code = classifyLight(s, ul, positionInWorld, shadingNormalInWorld, vOutLocal.z);
-            myKeys[i * 64] = code;
-            survivors |= code != kLightDark ? (1u << i) : 0u;
+            const float ulB = pcg32Float(rng.state);
+            const F8 gA = pickGuideFetch(s, ulA);
+            const F8 gB = pickGuideFetch(s, ulB);
+            const uint32_t codeA = classifyLight(s, ulA, gA, positionInWorld, shadingNormalInWorld, vOutLocal.z);
+            myKeys[i * 64] = codeA;
+            survivors |= codeA != kLightDark ? (1u << i) : 0u;
+            if (i + 1 < numCandidates) {
+                rng.state = rng.state * kPcg32Jump4.mul[1] + kPcg32Jump4.add[1];
+                const uint32_t codeB = classifyLight(s, ulB, gB, positionInWorld, shadingNormalInWorld, vOutLocal.z);
+                myKeys[(i + 1) * 64] = codeB;
+                survivors |= codeB != kLightDark ? (2u << i) : 0u;
+            }
         }
         // ---- phase B: this lane's survivors, in candidate order
         uint32_t selIdx = 0;
@@ -292,8 +302,11 @@ GFX_D bool risPixel(const DevScene &s, const DevFrame &f, const DevFrameParams &
     return false;
 }
 
+#ifndef GFX_RIS_MIN_BLOCKS
+#define GFX_RIS_MIN_BLOCKS 16 // 64 registers: measured 1.49 ms against 1.80 ms at the 84 registers ptxas picks unconstrained (profiles/r02_summary.md)
+#endif
 template <bool withTemporalRIS, bool useUnbiasedEstimator, int PHASE, bool TWO_PHASE = false>
-__global__ void __launch_bounds__(64) k_initialAndTemporalRIS(DevScene s, DevFrame f, DevFrameParams p) {
+__global__ void __launch_bounds__(64, GFX_RIS_MIN_BLOCKS) k_initialAndTemporalRIS(DevScene s, DevFrame f, DevFrameParams p) {
     static_assert(!TWO_PHASE || PHASE == 1, "the two-phase candidate loop belongs to the wavefront candidate pass");
     RayRequest request;
     uint32_t* candidateKeys = nullptr;

@@ -44,18 +44,49 @@ class _DevicePtr:
 
 
 class GpuBackend:
+    """Launches go through gfx_launch_batch: the driver's calls are recorded into one array of GfxBatchOp records per frame and
+    handed to the library in ONE call (flush) - at 8 GPUs a strip frame is ~35 launches in ~1.3 ms of GPU time, and a Python /
+    ctypes round trip per launch made the host the bottleneck."""
+    MAX_OPS = 128
+
     def __init__(self, ctx: engine.Context):
         self.ctx = ctx
         self._views = {}
+        self._ops = (abi.GfxBatchOp * self.MAX_OPS)()
+        self._n = 0
+
+    def _record(self, op, a=0, b=0, c=0, d=0, e=0, params=None):
+        if self._n == self.MAX_OPS:
+            self.flush()
+        o = self._ops[self._n]
+        o.op, o.a, o.b, o.c, o.d, o.e = op, a, b, c, d, e
+        if params is not None:
+            import ctypes as C
+            C.memmove(C.addressof(o.params), C.addressof(params), C.sizeof(abi.GfxFrameParams))
+        self._n += 1
+
+    def flush(self):
+        if self._n:
+            n, self._n = self._n, 0
+            self.ctx._check(self.ctx.lib.gfx_launch_batch(self.ctx.h, None, self._ops, n), "gfx_launch_batch")
 
     def light_dist(self, frame_index: int):
-        self.ctx.build_light_distributions(frame_index % 2)
+        self._record(abi.OP_LIGHT_DIST, frame_index % 2)
 
     def gbuffer(self, params):
-        self.ctx.gbuffer(params)
+        self._record(abi.OP_GBUFFER, params=params)
 
     def restir(self, params, pass_id: int):
-        self.ctx.restir(params, pass_id)
+        self._record(abi.OP_RESTIR, pass_id, params=params)
+
+    def peer_push_rows(self, link, buffer_id, index, row_lo, row_hi):
+        self._record(abi.OP_PEER_PUSH_ROWS, link, buffer_id, index, row_lo, row_hi)
+
+    def peer_signal(self, link, flag_index, value):
+        self._record(abi.OP_PEER_SIGNAL, link, flag_index, value)
+
+    def peer_wait(self, flag_index, value):
+        self._record(abi.OP_PEER_WAIT, flag_index, value)
 
     def tensor(self, buffer_id: int, index: int = 0) -> torch.Tensor:
         key = (buffer_id, index)
@@ -136,6 +167,8 @@ class StripDriver:
             return
         if getattr(self.backend, "peer_ready", False):
             return self._exchange_halo_peer(buffers)
+        if hasattr(self.backend, "flush"):
+            self.backend.flush()  # the recorded launches must be in the stream before the send/recv
         ops = []
         for buffer_id, index in buffers:
             if self.rank > 0:  # my top rows go up, their bottom rows come down
@@ -157,23 +190,22 @@ class StripDriver:
     def _exchange_halo_peer(self, buffers):
         """Push my seam rows into the neighbours' buffers, raise their flags, wait for mine (csrc/peer.cu)."""
         b = self.backend
-        ctx = b.ctx
         b.peer_seq += 1
         seq = b.peer_seq
         up, down = self.rank > 0, self.rank < self.world - 1
         for buffer_id, index in buffers:
             if up:
-                ctx.peer_push_rows(0, buffer_id, index, self.y0, min(self.y0 + self.halo, self.y1))
+                b.peer_push_rows(0, buffer_id, index, self.y0, min(self.y0 + self.halo, self.y1))
             if down:
-                ctx.peer_push_rows(1, buffer_id, index, max(self.y1 - self.halo, self.y0), self.y1)
+                b.peer_push_rows(1, buffer_id, index, max(self.y1 - self.halo, self.y0), self.y1)
         if up:
-            ctx.peer_signal(0, 1, seq)   # I am the upper neighbour's lower neighbour: its flag word 1
+            b.peer_signal(0, 1, seq)   # I am the upper neighbour's lower neighbour: its flag word 1
         if down:
-            ctx.peer_signal(1, 0, seq)
+            b.peer_signal(1, 0, seq)
         if up:
-            ctx.peer_wait(0, seq)
+            b.peer_wait(0, seq)
         if down:
-            ctx.peer_wait(1, seq)
+            b.peer_wait(1, seq)
 
     def check_peers(self):
         """raises if a seam wait timed out since the last check (a stalled neighbour: rows of this frame may be stale)"""
@@ -223,6 +255,8 @@ class StripDriver:
                 cur = p.currentReservoirIndex
                 self.exchange_halo([(abi.BUF_RESERVOIR, cur), (abi.BUF_RESERVOIR_INFO, cur)])
         self._tile(0, 0)
+        if hasattr(b, "flush"):
+            b.flush()
         if self.world > 1:
             strip = self._row_slices(abi.BUF_BEAUTY_ACCUM, 0, self.y0, self.y1)[0]
             dist.all_gather_into_tensor(self.composited, strip.contiguous())

@@ -425,6 +425,28 @@ int gfx_svgf_launch(gfx_ctx* ctx, void* stream, const GfxFrameParams* params, in
  * starting from the G-buffer of params->bufferIndex; running mean into GFX_BUFFER_BEAUTY_ACCUM. */
 int gfx_pathtrace_launch(gfx_ctx* ctx, void* stream, const GfxFrameParams* params, int variant);
 
+/* ---- batched launches ------------------------------------------------------------------------
+ * One call for a list of launches (a whole strip frame of the multi-GPU driver: ~35 kernels in ~1.3 ms at 8 GPUs, where one
+ * host round trip per launch through a binding layer would make the host the bottleneck).  Each record is executed in order on
+ * `stream` exactly like the entry point it names: GFX_OP_LIGHT_DIST = gfx_light_dist_build(a = bufferIndex), GFX_OP_GBUFFER =
+ * gfx_gbuffer_launch(params), GFX_OP_RESTIR = gfx_restir_launch(params, a = pass), GFX_OP_PEER_PUSH_ROWS =
+ * gfx_peer_push_rows(a = link, b = buffer id, c = index, d = rowLo, e = rowHi), GFX_OP_PEER_SIGNAL = gfx_peer_signal(a = link,
+ * b = flag index, c = value), GFX_OP_PEER_WAIT = gfx_peer_wait(a = flag index, b = value).  Stops at the first failing record
+ * and returns its status. */
+#define GFX_OP_LIGHT_DIST 0
+#define GFX_OP_GBUFFER 1
+#define GFX_OP_RESTIR 2
+#define GFX_OP_PEER_PUSH_ROWS 3
+#define GFX_OP_PEER_SIGNAL 4
+#define GFX_OP_PEER_WAIT 5
+typedef struct GfxBatchOp {
+    uint32_t op;
+    uint32_t a, b, c, d, e;
+    uint32_t pad[2];
+    GfxFrameParams params;
+} GfxBatchOp;
+int gfx_launch_batch(gfx_ctx* ctx, void* stream, const GfxBatchOp* ops, uint32_t numOps);
+
 /* ---- ReGIR cell reservoirs (regir_main.cpp:2033-2068) --------------------------------- */
 /* replaces kernelBuildCellReservoirs / kernelBuildCellReservoirsAndTemporalReuse (build_cell_reservoirs.cu:71-233):
  * streaming RIS of 2^log2NumCandidatesPerLightSlot light samples per slot against the intensity reaching the cell,

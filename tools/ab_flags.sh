@@ -7,7 +7,7 @@
 set -u
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
 cd "$ROOT"
-declare -A FLAGS=( [nosphere]="-DGFX_AB_NO_SPHERE" [chainpick]="-DGFX_AB_CHAIN_PICK" )
+declare -A FLAGS=( [nosphere]="-DGFX_AB_NO_SPHERE" [chainpick]="-DGFX_AB_CHAIN_PICK" [occ20]="-DGFX_RIS_MIN_BLOCKS=20" [occ24]="-DGFX_RIS_MIN_BLOCKS=24" [bounce12]="-DGFX_BOUNCE_MIN_BLOCKS=12" [bounce16]="-DGFX_BOUNCE_MIN_BLOCKS=16" )
 if [ -n "${AB_ONLY:-}" ]; then for k in "${!FLAGS[@]}"; do [[ " $AB_ONLY " == *" $k "* ]] || unset "FLAGS[$k]"; done; fi
 if [ "${1:-}" = "build" ]; then
     mkdir -p build_ab
