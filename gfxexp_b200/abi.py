@@ -316,6 +316,11 @@ class GfxBatchOp(C.Structure):
                 ("params", GfxFrameParams)]
 
 
+class GfxStripFrame(C.Structure):
+    _fields_ = [(n, c_u32) for n in ("frameIndex", "numSpatialPasses", "unbiased", "temporal", "y0", "y1", "halo", "rank", "world",
+                                     "usePeer", "peerSeq")]
+
+
 _DECLS = {
     "gfx_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "gfx_ctx_destroy": (None, [C.c_void_p]),
@@ -331,6 +336,7 @@ _DECLS = {
     "gfx_trace_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, c_u32, C.c_void_p, C.c_int]),
     "gfx_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, c_u32, C.c_void_p, C.c_int]),
     "gfx_light_dist_build": (C.c_int, [C.c_void_p, C.c_void_p, c_u32]),
+    "gfx_restir_strip_frame": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxFrameParams), C.POINTER(GfxStripFrame)]),
     "gfx_launch_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxBatchOp), c_u32]),
     "gfx_light_pick_debug": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, c_u32, C.c_void_p, C.c_void_p]),
     "gfx_light_dist_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(c_f)]),

@@ -561,6 +561,79 @@ int gfx_launch_batch(gfx_ctx* ctx, void* stream, const GfxBatchOp* ops, uint32_t
     return GFX_OK;
 }
 
+int gfx_restir_strip_frame(gfx_ctx* ctx, void* stream, GfxFrameParams* p, GfxStripFrame* st) {
+    CHECK_CTX(ctx);
+    if (!p || !st || st->y1 <= st->y0 || st->y1 > ctx->frame.H || st->world == 0 || st->rank >= st->world)
+        return GFX_ERR_INVALID_ARGUMENT;
+    const uint32_t H = ctx->frame.H, f = st->frameIndex, nsp = st->numSpatialPasses;
+    const bool up = st->rank > 0, down = st->rank + 1 < st->world;
+    int rc = GFX_OK;
+#define STRIP_CALL(expr) do { rc = (expr); if (rc != GFX_OK) return rc; } while (0)
+    // seam rows of the given reservoir buffer pair: push to both neighbours, raise their flags, wait for mine (peer.cu)
+    auto exchange = [&](uint32_t reservoirIndex) -> int {
+        if (st->world == 1 || !st->usePeer)
+            return GFX_OK;
+        const uint32_t seq = ++st->peerSeq;
+        const int bufs[2] = { GFX_BUF_RESERVOIR, GFX_BUF_RESERVOIR_INFO };
+        for (int b : bufs) {
+            if (up)
+                STRIP_CALL(gfx_peer_push_rows(ctx, stream, 0, b, reservoirIndex, st->y0, st->y0 + st->halo < st->y1 ? st->y0 + st->halo : st->y1));
+            if (down)
+                STRIP_CALL(gfx_peer_push_rows(ctx, stream, 1, b, reservoirIndex, st->y1 > st->y0 + st->halo ? st->y1 - st->halo : st->y0, st->y1));
+        }
+        if (up)
+            STRIP_CALL(gfx_peer_signal(ctx, stream, 0, 1, seq)); // I am the upper neighbour's lower neighbour: its flag word 1
+        if (down)
+            STRIP_CALL(gfx_peer_signal(ctx, stream, 1, 0, seq));
+        if (up)
+            STRIP_CALL(gfx_peer_wait(ctx, stream, 0, seq));
+        if (down)
+            STRIP_CALL(gfx_peer_wait(ctx, stream, 1, seq));
+        return GFX_OK;
+    };
+    auto tile = [&](uint32_t lo, uint32_t hi) { p->tileOriginY = lo; p->tileRows = hi - lo; };
+
+    STRIP_CALL(gfx_light_dist_build(ctx, stream, f % 2));
+    // the launch list of restir_di_main.cpp:2321-2421 (gfxexp_b200/engine.py restir_frame_passes is the same list)
+    p->frameIndex = f;
+    p->bufferIndex = f % 2;
+    p->useUnbiasedEstimator = st->unbiased ? 1 : 0;
+    p->enableTemporalReuse = st->temporal ? 1 : 0;
+    p->enableSpatialReuse = nsp > 0 ? 1 : 0;
+    const bool newSequence = f == 0;
+    p->resetFlowBuffer = newSequence ? 1 : 0;
+    tile(st->y0 > st->halo ? st->y0 - st->halo : 0, st->y1 + st->halo < H ? st->y1 + st->halo : H);
+    if (st->world == 1)
+        tile(0, H);
+    STRIP_CALL(gfx_gbuffer_launch(ctx, stream, p));
+    const uint32_t base = (uint32_t)(((uint64_t)f * (1 + nsp)) % 2);
+    p->currentReservoirIndex = base;
+    tile(st->y0, st->y1);
+    const int initialPass = (p->enableTemporalReuse && !newSequence)
+        ? (st->unbiased ? GFX_RESTIR_INITIAL_AND_TEMPORAL_UNBIASED : GFX_RESTIR_INITIAL_AND_TEMPORAL_BIASED) : GFX_RESTIR_INITIAL_RIS;
+    STRIP_CALL(gfx_restir_launch(ctx, stream, p, initialPass));
+    if (nsp > 0)
+        STRIP_CALL(exchange(p->currentReservoirIndex));
+    uint32_t cur = base;
+    for (uint32_t s = 0; s < nsp; ++s) {
+        p->currentReservoirIndex = cur;
+        const uint32_t k = p->numSpatialNeighbors > 1 ? p->numSpatialNeighbors : 1;
+        p->spatialNeighborBaseIndex = (uint32_t)(((uint64_t)f * nsp * k + (uint64_t)s * p->numSpatialNeighbors) % 1024);
+        STRIP_CALL(gfx_restir_launch(ctx, stream, p, st->unbiased ? GFX_RESTIR_SPATIAL_UNBIASED : GFX_RESTIR_SPATIAL_BIASED));
+        if (s + 1 < nsp)
+            STRIP_CALL(exchange((cur + 1) % 2));
+        cur = (cur + 1) % 2;
+    }
+    p->currentReservoirIndex = cur;
+    STRIP_CALL(gfx_restir_launch(ctx, stream, p, GFX_RESTIR_SHADING));
+    // final reservoirs of the seam rows: next frame's temporal reuse may look across the seam
+    STRIP_CALL(exchange(cur));
+    tile(0, 0);
+    p->tileRows = 0;
+#undef STRIP_CALL
+    return GFX_OK;
+}
+
 int gfx_light_pick_debug(gfx_ctx* ctx, void* stream, const float* ul, uint32_t n, uint32_t* keysFlat, uint32_t* keysChain) {
     CHECK_CTX(ctx);
     if (!ctx->scene.uploaded || ctx->scene.pickDirty)

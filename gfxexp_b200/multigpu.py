@@ -117,6 +117,7 @@ class GpuBackend:
         self.peer_seq = 0
 
     peer_ready = False
+    peer_seq = 0
 
 
 class StripDriver:
@@ -145,6 +146,9 @@ class StripDriver:
         self.max_motion_rows = max_motion_rows
         self.check_every = check_every
         self.frames_rendered = 0
+        self._strip = abi.GfxStripFrame()
+        self._strip.y0, self._strip.y1, self._strip.halo = self.y0, self.y1, halo
+        self._strip.rank, self._strip.world, self._strip.usePeer = rank, world, 1
         self.composited = self.backend.new_tensor(width * height * 4)
         if world > 1 and isinstance(self.backend, GpuBackend) and peer:
             self.backend.enable_peer(rank, world)
@@ -226,6 +230,16 @@ class StripDriver:
         if self.world > 1 and frame_index > 0 and p.enableTemporalReuse and self.max_motion_rows == 0 and self._camera_moved(p):
             raise ValueError("the camera moved between frames: temporal reuse follows motion vectors across strip seams, state "
                              "max_motion_rows (<= halo) when constructing the StripDriver")
+        if isinstance(b, GpuBackend) and (self.world == 1 or b.peer_ready):
+            # the whole strip frame - ~35 launches incl. the one-sided seam exchanges - in ONE library call
+            # (gfx_restir_strip_frame, csrc/api.cu: the same launch list as below, in C++)
+            st = self._strip
+            st.frameIndex, st.numSpatialPasses, st.unbiased, st.temporal = frame_index, num_spatial_passes, int(unbiased), 1
+            st.peerSeq = b.peer_seq
+            b.ctx._check(b.ctx.lib.gfx_restir_strip_frame(b.ctx.h, None, p, st), "gfx_restir_strip_frame")
+            b.peer_seq = st.peerSeq
+            self._finish_frame()
+            return
         b.light_dist(frame_index)
         lo_h, hi_h = max(0, self.y0 - self.halo), min(self.H, self.y1 + self.halo)
         spatial_seen = 0
@@ -257,6 +271,10 @@ class StripDriver:
         self._tile(0, 0)
         if hasattr(b, "flush"):
             b.flush()
+        self._finish_frame()
+
+    def _finish_frame(self):
+        p = self.params
         if self.world > 1:
             strip = self._row_slices(abi.BUF_BEAUTY_ACCUM, 0, self.y0, self.y1)[0]
             dist.all_gather_into_tensor(self.composited, strip.contiguous())

@@ -447,6 +447,21 @@ typedef struct GfxBatchOp {
 } GfxBatchOp;
 int gfx_launch_batch(gfx_ctx* ctx, void* stream, const GfxBatchOp* ops, uint32_t numOps);
 
+/* One ReSTIR DI frame of a screen strip, every launch of it, in one call: what restir_di_main.cpp:2303-2421 does per frame
+ * (light distribution, G-buffer, initial(+temporal) RIS, spatial passes, shading; `params` is mutated between launches exactly
+ * like the host mutates plp, and left as after the last launch) restricted to the rows [y0, y1) of rank `rank` of `world`, with
+ * the G-buffer recomputed on `halo` more rows on each side and the reservoir / reservoir-info seam rows exchanged with the
+ * neighbour ranks by one-sided pushes over the peer links opened with gfx_peer_open (usePeer = 1; *peerSeq is the running
+ * sequence number of the exchanges, in/out).  world = 1 renders the full frame (y0 = 0, y1 = H).  The caller all-gathers the
+ * beauty strips afterwards (gfx_framebuffer_allgather or its own collective). */
+typedef struct GfxStripFrame {
+    uint32_t frameIndex, numSpatialPasses, unbiased, temporal;
+    uint32_t y0, y1, halo;
+    uint32_t rank, world, usePeer;
+    uint32_t peerSeq;
+} GfxStripFrame;
+int gfx_restir_strip_frame(gfx_ctx* ctx, void* stream, GfxFrameParams* params, GfxStripFrame* strip);
+
 /* ---- ReGIR cell reservoirs (regir_main.cpp:2033-2068) --------------------------------- */
 /* replaces kernelBuildCellReservoirs / kernelBuildCellReservoirsAndTemporalReuse (build_cell_reservoirs.cu:71-233):
  * streaming RIS of 2^log2NumCandidatesPerLightSlot light samples per slot against the intensity reaching the cell,
