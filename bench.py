@@ -440,6 +440,13 @@ def run_gpu(args):
     clocks = sampler.stop()
     ms_total = ev0.elapsed_time(ev1)
     rays = ctx.read_stats(reset=True)[0]
+    # the G-buffer halo rows a rank recomputes for the spatial pass are redundant work, not throughput: their primary rays
+    # are not counted (so `value` at N > 1 is the same frame's rays as at N = 1, over a shorter time)
+    halo_rays_per_frame = 0
+    if driver is not None:
+        lo_h, hi_h = max(0, driver.y0 - driver.halo), min(HEIGHT, driver.y1 + driver.halo)
+        halo_rays_per_frame = ((driver.y0 - lo_h) + (hi_h - driver.y1)) * WIDTH
+        rays -= halo_rays_per_frame * args.steps
     launches = ctx.kernel_launches - launches0
     if world > 1:
         t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
@@ -509,7 +516,7 @@ def run_gpu(args):
     barrier()
     e2e_ms = ev0.elapsed_time(ev1)
     sampler.close()
-    e2e_rays = ctx.read_stats(reset=True)[0]
+    e2e_rays = ctx.read_stats(reset=True)[0] - halo_rays_per_frame * args.steps
     if world > 1:
         t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -632,7 +639,8 @@ def run_gpu(args):
                    "emissive_triangles": scene.num_emissive_triangles, "rays_per_pixel": rays_per_px,
                    "l2": "inputs larger than L2 (BVH %.0f MB + %.0f MB of per-pixel state per frame)" % (
                        (info.numTriangles * 52 + info.numNodes * 80) / 1e6, WIDTH * HEIGHT * 400 / 1e6),
-                   "parallelism": ("screen strips x%d, seam rows by %s, beauty strips all-gathered with NCCL" % (
+                   "parallelism": ("screen strips x%d (24-row G-buffer halo recomputed per seam, its rays not counted), seam rows by %s, "
+                                   "beauty strips all-gathered with NCCL" % (
                        world, "one-sided NVLink peer-memory pushes" if driver.backend.peer_ready else "NCCL send/recv"))
                    if world > 1 else "1 GPU",
                    "bvh_build_ms": bvh_build_ms, "scene_upload_s": upload_s},

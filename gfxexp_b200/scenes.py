@@ -350,6 +350,95 @@ def city_scene(num_buildings: int = 700, building_tess=(12, 20), ground_tess: in
                  math.radians(50.0), name)
 
 
+def interior_scene(hall=(60.0, 9.0, 40.0), wall_tess: int = 200, num_columns: int = 80, column_tess: int = 30,
+                   num_props: int = 300, prop_tess: int = 24, num_emitters: int = 5000, num_materials: int = 64,
+                   seed: int = 0x2D47, name: str = "interior") -> Scene:
+    """Procedural interior ("Zero-Day-class"): a closed hall (floor, ceiling, four walls, all facing
+    inwards) with rows of columns, props on the floor and MANY SMALL EMITTERS - panel lights of two triangles each hung
+    under the ceiling and on the walls - lit with SimplePBR materials (baseColor / smoothness / metallic,
+    common/common_device.cuh:767-776, 806-826), which the city scenes do not use."""
+    rng = np.random.default_rng(seed)
+    mats = np.zeros(num_materials, dtype=MATERIAL_DTYPE)
+    q_base = rng.integers(40, 235, size=(num_materials, 3), dtype=np.int64)
+    mats["p0"] = srgb_unorm8_to_linear(q_base)
+    mats["p1"][:, 1] = (rng.integers(40, 230, size=num_materials) / 255.0).astype(F32)   # 1 - smoothness
+    mats["p1"][:, 2] = np.where(rng.random(num_materials) < 0.25, 1.0, 0.0).astype(F32) * \
+        (rng.integers(128, 256, size=num_materials) / 255.0).astype(F32)                  # metallic
+    mats["bsdfType"] = BSDF_SIMPLE_PBR
+    num_emitter_mats = 6
+    tints = np.array([[1.0, 0.9, 0.75], [0.75, 0.85, 1.0], [1.0, 0.45, 0.3], [0.4, 1.0, 0.6], [0.5, 0.55, 1.0], [1.0, 1.0, 1.0]], dtype=F32)
+    for k in range(num_emitter_mats):
+        m = mats[num_materials - 1 - k]
+        m["hasEmittance"] = 1
+        m["emittance"] = tints[k] * F32(25.0 + 5.0 * k)
+        m["p0"] = F32(0.8)
+        m["p1"] = (0.0, 0.6, 0.0)
+    body = num_materials - num_emitter_mats
+    meshes: List[Mesh] = []
+    instances: List[Instance] = []
+    hx, hy, hz = hall[0] * 0.5, hall[1], hall[2] * 0.5
+    # the shell, facing inwards
+    shell = [((-hx, 0, hz), (hall[0], 0, 0), (0, 0, -hall[2]), (0, 1, 0)),        # floor
+             ((-hx, hy, -hz), (hall[0], 0, 0), (0, 0, hall[2]), (0, -1, 0)),      # ceiling
+             ((-hx, 0, -hz), (hall[0], 0, 0), (0, hy, 0), (0, 0, 1)),             # back wall (z = -hz), facing +z
+             ((hx, 0, hz), (-hall[0], 0, 0), (0, hy, 0), (0, 0, -1)),             # front wall
+             ((-hx, 0, hz), (0, 0, -hall[2]), (0, hy, 0), (1, 0, 0)),             # left wall, facing +x
+             ((hx, 0, -hz), (0, 0, hall[2]), (0, hy, 0), (-1, 0, 0))]             # right wall
+    for k, (o, du, dv, nn) in enumerate(shell):
+        meshes.append(_merge([_grid_face(wall_tess, o, du, dv, nn, rng, 0.004)], int(rng.integers(0, body))))
+        instances.append(make_instance([len(meshes) - 1]))
+    # columns in two rows along x
+    column_slots = []
+    for _ in range(4):
+        column_slots.append(len(meshes))
+        meshes.append(make_box(column_tess, (0.9, hy, 0.9), int(rng.integers(0, body)), rng, 0.01))
+    for k in range(num_columns):
+        row = -1.0 if (k % 2) else 1.0
+        x = -hx + hall[0] * (k // 2 + 0.5) / max(num_columns // 2, 1)
+        instances.append(make_instance([column_slots[k % 4]], (x, 0.0, row * hz * 0.45), float(rng.uniform(0, 90)), 1.0))
+    # props on the floor
+    prop_slots = []
+    for k in range(8):
+        prop_slots.append(len(meshes))
+        if k % 2 == 0:
+            meshes.append(make_sphere(2 * prop_tess, prop_tess, 0.5, int(rng.integers(0, body))))
+        else:
+            meshes.append(make_box(prop_tess // 2, (1.0, 1.0, 1.0), int(rng.integers(0, body)), rng, 0.02))
+    for k in range(num_props):
+        slot = prop_slots[int(rng.integers(0, 8))]
+        y = 0.5 if slot in prop_slots[0::2] else 0.0
+        instances.append(make_instance([slot], (float(rng.uniform(-hx * 0.9, hx * 0.9)), y, float(rng.uniform(-hz * 0.9, hz * 0.9))),
+                                       float(rng.uniform(0, 360)), float(rng.uniform(0.5, 1.6))))
+    # many tiny emitters: 2-triangle panels under the ceiling (facing down) and a few per wall
+    panel_slots = []
+    for k in range(num_emitter_mats):
+        panel_slots.append(len(meshes))
+        meshes.append(make_quad_light(0.12, num_materials - 1 - k))
+    for k in range(num_emitters):
+        slot = panel_slots[int(rng.integers(0, num_emitter_mats))]
+        x, z = float(rng.uniform(-hx * 0.95, hx * 0.95)), float(rng.uniform(-hz * 0.95, hz * 0.95))
+        if k % 9 == 8:   # on a column-height ledge, tilted
+            instances.append(make_instance([slot], (x, float(rng.uniform(2.0, hy - 1.0)), z), float(rng.uniform(0, 360)),
+                                           float(rng.uniform(0.8, 2.0)), pitch_deg=float(rng.uniform(20, 70))))
+        else:
+            instances.append(make_instance([slot], (x, hy - 0.05, z), float(rng.uniform(0, 360)), float(rng.uniform(0.8, 2.0))))
+    eye = np.array([-hx * 0.8, 1.7, hz * 0.1])
+    target = np.array([hx * 0.6, 2.5, -hz * 0.2])
+    return Scene(meshes, mats, instances, eye.astype(F32), look_at_orientation(eye, target), math.radians(50.0), name)
+
+
+def zero_day_class_scene() -> Scene:
+    """Config 3 scene: ~5 M triangles, ~5 400 instances, 10 000 small emissive triangles, SimplePBR materials."""
+    return interior_scene(wall_tess=360, num_columns=80, column_tess=36, num_props=300, prop_tess=40, num_emitters=5000,
+                          name="zero_day_class")
+
+
+def small_interior_scene() -> Scene:
+    """~30 k triangles with 96 two-triangle emitters and SimplePBR materials: oracle-speed parity of config 3's ingredients."""
+    return interior_scene(hall=(16.0, 5.0, 12.0), wall_tess=24, num_columns=8, column_tess=6, num_props=16, prop_tess=8,
+                          num_emitters=96, num_materials=24, name="small_interior")
+
+
 def bistro_class_scene() -> Scene:
     """Config 2/4/5 scene: ~2.8 M triangles, ~1 000 instances, ~50 meshes, ~20 k emissive triangles."""
     return city_scene(num_buildings=760, building_tess=(14, 20), ground_tess=300, num_lamps=200, num_props=120,

@@ -5,7 +5,8 @@ be the checker: size-independent properties of the CUDA path instead.
     tie-break makes the answer a function of the triangles alone);
   * any-hit answers agree between the two trees;
   * a ReSTIR frame sequence is deterministic and equals the same sequence rendered as three row strips;
-  * a sample of pixels of the first frame equals the oracle evaluated on just those rows (48-row strip)."""
+  * a sample of pixels of the first frame equals the oracle evaluated on just those rows (80-row strip), and so do three
+    accumulated frames with temporal + spatial reuse (160-row strip, the 40 rows whose history stays inside it)."""
 import numpy as np
 import pytest
 
@@ -82,6 +83,20 @@ def test_config2_full_size_properties(gfx_ctx, oracle):
         oframe.gbuffer(po) if kind == "gbuffer" else oframe.restir(po, pid)
     want = oframe.buffer(abi.BUF_BEAUTY_ACCUM)[530:550]
     assert np.array_equal(beauty0[530:550].view(np.uint32), want.view(np.uint32)), "full-size frame differs from the oracle strip"
+
+    # the same for the temporal frames: three accumulated frames (initial; temporal + spatial; temporal + spatial) against the
+    # oracle on rows 460..619.  Every frame's spatial gather reaches 20 rows, so the rows whose whole history lies inside the
+    # strip shrink by 20 per frame: 520..559 after frame 2 (static camera: temporal reuse stays on the pixel).
+    beauty012, _ = _render(gfx_ctx, scene, 3)
+    oframe3 = oracle.OracleFrame(checker, W, H)
+    po = abi.default_frame_params(scene, W, H)
+    for f in range(3):
+        po.numAccumFrames = f
+        for kind, pid in engine.restir_frame_passes(po, f, 1, True, False):
+            po.tileOriginY, po.tileRows = 460, 160
+            oframe3.gbuffer(po) if kind == "gbuffer" else oframe3.restir(po, pid)
+    want3 = oframe3.buffer(abi.BUF_BEAUTY_ACCUM)[520:560]
+    assert np.array_equal(beauty012[520:560].view(np.uint32), want3.view(np.uint32)), "full-size temporal frames differ from the oracle strip"
 
     # determinism + strip sharding at full resolution (3 frames: initial, temporal, temporal)
     beauty1, rng1 = _render(gfx_ctx, scene, 3)

@@ -26,11 +26,13 @@ def _assert_same(got, want, tag):
                              f"{got[tuple(bad[0][:2])]} vs {want[tuple(bad[0][:2])]}")
 
 
-@pytest.mark.parametrize("max_path_length", [2, 5, 9])
-def test_pathtrace_accumulation_bit_exact(gfx_ctx, oracle, max_path_length):
+@pytest.mark.parametrize("max_path_length,scene_name", [(2, "small_city_scene"), (5, "small_city_scene"), (9, "small_city_scene"),
+                                                        (5, "small_interior_scene")])
+def test_pathtrace_accumulation_bit_exact(gfx_ctx, oracle, max_path_length, scene_name):
     """three accumulated samples per pixel in a closed scene with ~100 emitters: every pixel's radiance and RNG
-    state equal the oracle's, i.e. the wavefront reordering changes neither the draws nor the summation order"""
-    scene = scenes.small_city_scene()
+    state equal the oracle's, i.e. the wavefront reordering changes neither the draws nor the summation order
+    (small_interior_scene: SimplePBR materials, many two-triangle emitters in a closed room)"""
+    scene = getattr(scenes, scene_name)()
     w, h = 160, 90
     _, oframe = _setup(gfx_ctx, oracle, scene, w, h)
     p = abi.default_frame_params(scene, w, h)

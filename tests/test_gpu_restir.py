@@ -48,9 +48,12 @@ def test_light_distributions(gfx_ctx, oracle):
     assert integ > 0
 
 
-@pytest.mark.parametrize("unbiased", [False, True])
-def test_restir_three_frames_bit_exact(gfx_ctx, oracle, unbiased):
-    scene = scenes.small_city_scene()
+@pytest.mark.parametrize("unbiased,scene_name", [(False, "small_city_scene"), (True, "small_city_scene"),
+                                                 (False, "small_interior_scene")])
+def test_restir_three_frames_bit_exact(gfx_ctx, oracle, unbiased, scene_name):
+    # small_interior_scene: config 3's ingredients - a closed room, 96 two-triangle emitters, SimplePBR materials
+    # (common/common_device.cuh:767-776, 806-826)
+    scene = getattr(scenes, scene_name)()
     w, h = 192, 108
     oscene, oframe = _setup(gfx_ctx, oracle, scene, w, h)
     p = abi.default_frame_params(scene, w, h)
