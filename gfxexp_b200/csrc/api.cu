@@ -28,8 +28,12 @@ void SceneState::release() {
 void BvhState::release() {
     cudaFree(nodes); cudaFree(primRefs); cudaFree(tris); cudaFree(leafTris); cudaFree(sceneBounds);
     uint32_t* keepFlag = overflowFlag;
+    void* keepScratch = scratch;
+    const size_t keepScratchBytes = scratchBytes;
     *this = BvhState();
     overflowFlag = keepFlag;
+    scratch = keepScratch;
+    scratchBytes = keepScratchBytes;
 }
 void FrameState::release() {
     for (int i = 0; i < 2; ++i) {
@@ -219,6 +223,7 @@ void gfx_ctx_destroy(gfx_ctx* ctx) {
     cudaDeviceSynchronize();
     ctx->frame.release();
     ctx->bvh.release();
+    cudaFree(ctx->bvh.scratch);
     cudaFree(ctx->bvh.overflowFlag);
     cudaFree(ctx->traceFetchCounter);
     ctx->scene.release();

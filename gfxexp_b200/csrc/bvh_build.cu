@@ -783,42 +783,69 @@ int buildBvh(gfx_ctx* ctx, cudaStream_t stream, uint32_t flags) {
     if (maxLeaf > 31) maxLeaf = 31;
 
     BvhState &B = ctx->bvh;
-    B.release();
+    // Output arrays and scratch are kept between builds of the same triangle count (per-frame rebuilds of an animated scene:
+    // ~30 cudaMalloc / cudaFree pairs per build were a third of the rebuild time in round 1); anything else re-allocates.
+    if (B.builtForTris != n) {
+        B.release();
+        B.builtForTris = 0;
+    }
+    B.ready = false;
     B.numTris = n;
     if (n == 0) {
         B.numNodes = 0;
         B.numPrimRefs = 0;
         return GFX_OK;
     }
-    GFX_CUDA(ctx, cudaMalloc(&B.tris, (size_t)n * 48));
-    GFX_CUDA(ctx, cudaMalloc(&B.primRefs, (size_t)n * 4));
-    // every wide node has >= 2 children except a degenerate root, so #nodes <= n
-    GFX_CUDA(ctx, cudaMalloc(&B.nodes, (size_t)max(n, 1u) * 80));
-    GFX_CUDA(ctx, cudaMalloc(&B.sceneBounds, 6 * 4));
-
-    // scratch
+    // scratch, carved out of one arena
     float4 *triLo, *triHi, *boxLo, *boxHi;
     uint64_t *keys, *keysSorted;
     uint32_t *ids, *idsSorted, *childL, *childR, *rangeFirst, *rangeLast, *parentI, *parentL, *arrive, *counters;
     uint2 *queueA, *queueB;
-    GFX_CUDA(ctx, cudaMalloc(&triLo, (size_t)n * 16));
-    GFX_CUDA(ctx, cudaMalloc(&triHi, (size_t)n * 16));
-    GFX_CUDA(ctx, cudaMalloc(&boxLo, (size_t)(2 * n) * 16));
-    GFX_CUDA(ctx, cudaMalloc(&boxHi, (size_t)(2 * n) * 16));
-    GFX_CUDA(ctx, cudaMalloc(&keys, (size_t)n * 8));
-    GFX_CUDA(ctx, cudaMalloc(&keysSorted, (size_t)n * 8));
-    GFX_CUDA(ctx, cudaMalloc(&ids, (size_t)n * 4));
-    GFX_CUDA(ctx, cudaMalloc(&idsSorted, (size_t)n * 4));
-    GFX_CUDA(ctx, cudaMalloc(&childL, (size_t)n * 4));
-    GFX_CUDA(ctx, cudaMalloc(&childR, (size_t)n * 4));
-    GFX_CUDA(ctx, cudaMalloc(&rangeFirst, (size_t)n * 4));
-    GFX_CUDA(ctx, cudaMalloc(&rangeLast, (size_t)n * 4));
-    GFX_CUDA(ctx, cudaMalloc(&parentI, (size_t)n * 4));
-    GFX_CUDA(ctx, cudaMalloc(&parentL, (size_t)n * 4));
-    GFX_CUDA(ctx, cudaMalloc(&arrive, (size_t)n * 4));
-    GFX_CUDA(ctx, cudaMalloc(&counters, 4 * 4));
-    GFX_CUDA(ctx, cudaMalloc(&queueA, (size_t)n * 8));
-    GFX_CUDA(ctx, cudaMalloc(&queueB, (size_t)n * 8));
+    uint4* bigListStore[2];
+    void *tmp, *selTmp;
+    const uint32_t bigCapacity = n / kSahBigNode + 2;
+    size_t tmpBytes = 0, selBytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const uint32_t*)nullptr,
+                                    (uint32_t*)nullptr, (int)n, 0, 63, stream);
+    cub::DeviceSelect::If(nullptr, selBytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, PlocValid(), stream);
+    {
+        size_t offset = 0;
+        auto take = [&](size_t bytes) { const size_t at = offset; offset += (bytes + 255) & ~(size_t)255; return at; };
+        const size_t oTriLo = take((size_t)n * 16), oTriHi = take((size_t)n * 16), oBoxLo = take((size_t)2 * n * 16), oBoxHi = take((size_t)2 * n * 16);
+        const size_t oKeys = take((size_t)n * 8), oKeysSorted = take((size_t)n * 8), oIds = take((size_t)n * 4), oIdsSorted = take((size_t)n * 4);
+        const size_t oChildL = take((size_t)n * 4), oChildR = take((size_t)n * 4), oRangeFirst = take((size_t)n * 4), oRangeLast = take((size_t)n * 4);
+        const size_t oParentI = take((size_t)n * 4), oParentL = take((size_t)n * 4), oArrive = take((size_t)n * 4), oCounters = take(16);
+        const size_t oQueueA = take((size_t)n * 8), oQueueB = take((size_t)n * 8);
+        const size_t oBig0 = take((size_t)bigCapacity * 16), oBig1 = take((size_t)bigCapacity * 16);
+        const size_t oTmp = take(tmpBytes), oSel = take(selBytes);
+        if (offset > B.scratchBytes) {
+            cudaFree(B.scratch);
+            B.scratch = nullptr;
+            B.scratchBytes = 0;
+            GFX_CUDA(ctx, cudaMalloc(&B.scratch, offset));
+            B.scratchBytes = offset;
+        }
+        uint8_t* base = reinterpret_cast<uint8_t*>(B.scratch);
+        triLo = reinterpret_cast<float4*>(base + oTriLo); triHi = reinterpret_cast<float4*>(base + oTriHi);
+        boxLo = reinterpret_cast<float4*>(base + oBoxLo); boxHi = reinterpret_cast<float4*>(base + oBoxHi);
+        keys = reinterpret_cast<uint64_t*>(base + oKeys); keysSorted = reinterpret_cast<uint64_t*>(base + oKeysSorted);
+        ids = reinterpret_cast<uint32_t*>(base + oIds); idsSorted = reinterpret_cast<uint32_t*>(base + oIdsSorted);
+        childL = reinterpret_cast<uint32_t*>(base + oChildL); childR = reinterpret_cast<uint32_t*>(base + oChildR);
+        rangeFirst = reinterpret_cast<uint32_t*>(base + oRangeFirst); rangeLast = reinterpret_cast<uint32_t*>(base + oRangeLast);
+        parentI = reinterpret_cast<uint32_t*>(base + oParentI); parentL = reinterpret_cast<uint32_t*>(base + oParentL);
+        arrive = reinterpret_cast<uint32_t*>(base + oArrive); counters = reinterpret_cast<uint32_t*>(base + oCounters);
+        queueA = reinterpret_cast<uint2*>(base + oQueueA); queueB = reinterpret_cast<uint2*>(base + oQueueB);
+        bigListStore[0] = reinterpret_cast<uint4*>(base + oBig0); bigListStore[1] = reinterpret_cast<uint4*>(base + oBig1);
+        tmp = base + oTmp; selTmp = base + oSel;
+    }
+    if (B.builtForTris != n) {
+        GFX_CUDA(ctx, cudaMalloc(&B.tris, (size_t)n * 48));
+        GFX_CUDA(ctx, cudaMalloc(&B.primRefs, (size_t)n * 4));
+        // every wide node has >= 2 children except a degenerate root, so #nodes <= n
+        GFX_CUDA(ctx, cudaMalloc(&B.nodes, (size_t)max(n, 1u) * 80));
+        GFX_CUDA(ctx, cudaMalloc(&B.sceneBounds, 6 * 4));
+        B.builtForTris = n;
+    }
 
     const DevScene dev = ctx->devScene();
     const uint32_t blocks = (n + 255) / 256;
@@ -826,10 +853,6 @@ int buildBvh(gfx_ctx* ctx, cudaStream_t stream, uint32_t flags) {
     k_flatten<<<blocks, 256, 0, stream>>>(dev, S.geomTriOffsets, S.numGeoms, n, B.tris, triLo, triHi, B.sceneBounds); ctx->launches++;
     k_morton<<<blocks, 256, 0, stream>>>(n, triLo, triHi, B.sceneBounds, keys, ids); ctx->launches++;
 
-    size_t tmpBytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, keys, keysSorted, ids, idsSorted, (int)n, 0, 63, stream);
-    void* tmp = nullptr;
-    GFX_CUDA(ctx, cudaMalloc(&tmp, tmpBytes));
     cub::DeviceRadixSort::SortPairs(tmp, tmpBytes, keys, keysSorted, ids, idsSorted, (int)n, 0, 63, stream); ctx->launches += 8;
 
     uint32_t rootRef = n == 1 ? 0x80000000u : 0u;
@@ -846,10 +869,7 @@ int buildBvh(gfx_ctx* ctx, cudaStream_t stream, uint32_t flags) {
         // binned SAH, top-down: small-node lists ping-pong between keys / keysSorted (n/2 records of 16 B each), big-node
         // lists are tiny; counters = { next small, next big, internal nodes allocated }
         uint4* smallLists[2] = { reinterpret_cast<uint4*>(keys), reinterpret_cast<uint4*>(keysSorted) };
-        uint4* bigLists[2] = { nullptr, nullptr };
-        const uint32_t bigCapacity = n / kSahBigNode + 2;
-        GFX_CUDA(ctx, cudaMalloc(&bigLists[0], (size_t)bigCapacity * 16));
-        GFX_CUDA(ctx, cudaMalloc(&bigLists[1], (size_t)bigCapacity * 16));
+        uint4* bigLists[2] = { bigListStore[0], bigListStore[1] };
         SahArgs sa;
         sa.n = n;
         sa.triLo = triLo; sa.triHi = triHi;
@@ -890,12 +910,10 @@ int buildBvh(gfx_ctx* ctx, cudaStream_t stream, uint32_t flags) {
             GFX_CUDA(ctx, cudaMemcpyAsync(counters, zeros, 8, cudaMemcpyHostToDevice, stream));
             cur ^= 1;
             if (++depth > 4096 || sizes[1] > bigCapacity) {
-                cudaFree(bigLists[0]); cudaFree(bigLists[1]);
                 ctx->setError("gfx_bvh_build: SAH split did not converge");
                 return GFX_ERR_CUDA;
             }
         }
-        cudaFree(bigLists[0]); cudaFree(bigLists[1]);
         k_sahLeafBoxes<<<blocks, 256, 0, stream>>>((int)n, idsSorted, triLo, triHi, boxLo, boxHi); ctx->launches++;
         rootRef = 0u;
     }
@@ -905,10 +923,6 @@ int buildBvh(gfx_ctx* ctx, cudaStream_t stream, uint32_t flags) {
         uint32_t* numSelected = counters + 2;
         GFX_CUDA(ctx, cudaMemsetAsync(counters, 0, 16, stream));
         k_plocInit<<<blocks, 256, 0, stream>>>((int)n, idsSorted, triLo, triHi, clusters, boxLo, boxHi); ctx->launches++;
-        size_t selBytes = 0;
-        cub::DeviceSelect::If(nullptr, selBytes, clustersOut, clusters, numSelected, (int)n, PlocValid(), stream);
-        void* selTmp = nullptr;
-        GFX_CUDA(ctx, cudaMalloc(&selTmp, selBytes));
         int plocRadius = (int)((flags >> 16) & 0xFFu); // 0 = default
         if (plocRadius == 0) plocRadius = 16;
         if (plocRadius > kPlocMaxRadius) plocRadius = kPlocMaxRadius;
@@ -925,7 +939,6 @@ int buildBvh(gfx_ctx* ctx, cudaStream_t stream, uint32_t flags) {
             GFX_CUDA(ctx, cudaMemcpyAsync(&newM, numSelected, 4, cudaMemcpyDeviceToHost, stream));
             GFX_CUDA(ctx, cudaStreamSynchronize(stream));
             if (newM >= m || ++passes > 4096) {
-                cudaFree(selTmp);
                 ctx->setError("gfx_bvh_build: PLOC did not converge");
                 return GFX_ERR_CUDA;
             }
@@ -933,7 +946,6 @@ int buildBvh(gfx_ctx* ctx, cudaStream_t stream, uint32_t flags) {
         }
         GFX_CUDA(ctx, cudaMemcpyAsync(&rootRef, clusters, 4, cudaMemcpyDeviceToHost, stream));
         GFX_CUDA(ctx, cudaStreamSynchronize(stream));
-        cudaFree(selTmp);
     }
 
     // collapse, level by level
@@ -980,10 +992,6 @@ int buildBvh(gfx_ctx* ctx, cudaStream_t stream, uint32_t flags) {
         (i < 3 ? B.sceneMin[i] : B.sceneMax[i - 3]) = f;
     }
 
-    cudaFree(tmp);
-    cudaFree(triLo); cudaFree(triHi); cudaFree(boxLo); cudaFree(boxHi); cudaFree(keys); cudaFree(keysSorted);
-    cudaFree(ids); cudaFree(idsSorted); cudaFree(childL); cudaFree(childR); cudaFree(rangeFirst); cudaFree(rangeLast);
-    cudaFree(parentI); cudaFree(parentL); cudaFree(arrive); cudaFree(counters); cudaFree(queueA); cudaFree(queueB);
     return GFX_OK;
 }
 
@@ -1009,9 +1017,13 @@ __global__ void k_leafTris(uint32_t numPrimRefs, const uint32_t* __restrict__ pr
 
 int finishBvh(gfx_ctx* ctx, cudaStream_t stream) {
     BvhState &B = ctx->bvh;
-    cudaFree(B.leafTris);
-    B.leafTris = nullptr;
-    GFX_CUDA(ctx, cudaMalloc(&B.leafTris, (size_t)max(B.numPrimRefs, 1u) * 48));
+    if (B.numPrimRefs > B.leafTrisCapacity || !B.leafTris) {
+        cudaFree(B.leafTris);
+        B.leafTris = nullptr;
+        B.leafTrisCapacity = 0;
+        GFX_CUDA(ctx, cudaMalloc(&B.leafTris, (size_t)max(B.numPrimRefs, 1u) * 48));
+        B.leafTrisCapacity = max(B.numPrimRefs, 1u);
+    }
     if (B.numPrimRefs) {
         k_leafTris<<<(B.numPrimRefs + 255) / 256, 256, 0, stream>>>(B.numPrimRefs, B.primRefs, B.tris, B.leafTris);
         ctx->launches++;

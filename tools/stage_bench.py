@@ -33,7 +33,8 @@ class Timer:
 
 def main():
     small = "--small" in sys.argv
-    scene = scenes.small_city_scene() if small else scenes.bistro_class_scene()
+    scene_name = sys.argv[sys.argv.index("--scene") + 1] if "--scene" in sys.argv else None   # e.g. zero_day_class_scene (config 3)
+    scene = getattr(scenes, scene_name)() if scene_name else (scenes.small_city_scene() if small else scenes.bistro_class_scene())
     w, h = (640, 360) if small else (1920, 1080)
     frames, warm = 12, 4
     ctx = engine.Context(0)
