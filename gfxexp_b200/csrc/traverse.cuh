@@ -67,18 +67,18 @@ struct TraversalState {
     uint2* sstack;           // this thread's column of the shared-memory stack (wavefront kernels), else unused
     uint2 stack[kStackSize]; // (node index, truncated entry distance bits)
 };
-template <bool SMEM>
+template <int SMEM_STRIDE> // threads per block of the shared-memory stack, 0 = local memory only
 GFX_D void stackStore(TraversalState &st, int at, const uint2 &v) {
-    if (SMEM && at < kSmemStack)
-        st.sstack[at * kSmemStackThreads] = v;
+    if (SMEM_STRIDE > 0 && at < kSmemStack)
+        st.sstack[at * SMEM_STRIDE] = v;
     else
-        st.stack[SMEM ? at - kSmemStack : at] = v;
+        st.stack[SMEM_STRIDE > 0 ? at - kSmemStack : at] = v;
 }
-template <bool SMEM>
+template <int SMEM_STRIDE>
 GFX_D uint2 stackLoad(const TraversalState &st, int at) {
-    if (SMEM && at < kSmemStack)
-        return st.sstack[at * kSmemStackThreads];
-    return st.stack[SMEM ? at - kSmemStack : at];
+    if (SMEM_STRIDE > 0 && at < kSmemStack)
+        return st.sstack[at * SMEM_STRIDE];
+    return st.stack[SMEM_STRIDE > 0 ? at - kSmemStack : at];
 }
 
 GFX_D void traverseInit(TraversalState &st, const f3 &org, const f3 &dir, float tmin, float tmax) {
@@ -165,7 +165,7 @@ GFX_D bool testPendingTriangle(const DevBvh &bvh, TraversalState &st, PendingLea
 // Processes node st.nodeIdx: slab-tests its children, intersects the triangle chains of the leaf
 // children that are hit (or, with `pend`, postpones them), selects the next internal node.  Returns false when the
 // traversal is finished.
-template <bool ANY_HIT, bool STATS, bool DEFER = false, bool SMEM = false>
+template <bool ANY_HIT, bool STATS, bool DEFER = false, int SMEM_STRIDE = 0>
 GFX_D bool traverseStep(const DevBvh &bvh, TraversalState &st, PendingLeaves* pend = nullptr) {
     const uint4* np = bvh.nodes + 5 * (size_t)st.nodeIdx;
     const uint4 n0 = __ldg(np + 0);
@@ -276,7 +276,7 @@ GFX_D bool traverseStep(const DevBvh &bvh, TraversalState &st, PendingLeaves* pe
             continue;
         if (next != 0xFFFFFFFFu) {
             if (st.sp < kStackSize)
-                stackStore<SMEM>(st, st.sp++, make_uint2(next, nextT));
+                stackStore<SMEM_STRIDE>(st, st.sp++, make_uint2(next, nextT));
             else if (bvh.overflowFlag)
                 *bvh.overflowFlag = 1u;
         }
@@ -288,7 +288,7 @@ GFX_D bool traverseStep(const DevBvh &bvh, TraversalState &st, PendingLeaves* pe
         return true;
     }
     while (st.sp > 0) {
-        const uint2 e = stackLoad<SMEM>(st, --st.sp);
+        const uint2 e = stackLoad<SMEM_STRIDE>(st, --st.sp);
         if (__uint_as_float(e.y) <= st.best.dist) {
             st.nodeIdx = e.x;
             return true;
@@ -304,6 +304,19 @@ GFX_D Hit traverseBvh(const DevBvh &bvh, const f3 &org, const f3 &dir, const flo
     if (bvh.numNodes == 0)
         return st.best;
     while (traverseStep<ANY_HIT, STATS>(bvh, st)) {
+    }
+    return st.best;
+}
+// the same with the first kSmemStack stack entries in shared memory: `sstack` = this thread's column of a
+// [kSmemStack][STRIDE] uint2 array
+template <bool ANY_HIT, int STRIDE>
+GFX_D Hit traverseBvhSmemStack(const DevBvh &bvh, const f3 &org, const f3 &dir, const float tmin, const float tmax, uint2* sstack) {
+    TraversalState st;
+    traverseInit(st, org, dir, tmin, tmax);
+    st.sstack = sstack;
+    if (bvh.numNodes == 0)
+        return st.best;
+    while (traverseStep<ANY_HIT, false, false, STRIDE>(bvh, st)) {
     }
     return st.best;
 }

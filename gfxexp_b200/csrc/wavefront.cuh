@@ -10,6 +10,7 @@
 // is called exactly once per ray, by the lane that traced it.
 #pragma once
 #include "traverse.cuh"
+#include <cstdlib>
 
 #ifndef GFX_TRACE_FLUSH_LANES
 #define GFX_TRACE_FLUSH_LANES 16
@@ -74,7 +75,7 @@ GFX_D void traceWavefrontBody(const DevBvh &bvh, const float4* __restrict__ rays
             break;
 #pragma unroll 1
         for (int it = 0; it < 8; ++it) {
-            if (active && !draining && !traverseStep<ANY_HIT, STATS, true, true>(bvh, st, &pend))
+            if (active && !draining && !traverseStep<ANY_HIT, STATS, true, kSmemStackThreads>(bvh, st, &pend))
                 draining = true;
             const uint32_t have = __ballot_sync(0xFFFFFFFFu, active && pend.n > 0);
             const uint32_t running = __ballot_sync(0xFFFFFFFFu, active && !draining);
@@ -127,7 +128,7 @@ GFX_D void traceWavefrontBody(const DevBvh &bvh, const float4* __restrict__ rays
         // ---- advance every active lane by up to 8 nodes, leave early once a quarter of the warp is idle
 #pragma unroll 1
         for (int it = 0; it < 8; ++it) {
-            if (active && !traverseStep<ANY_HIT, STATS, false, true>(bvh, st)) {
+            if (active && !traverseStep<ANY_HIT, STATS, false, kSmemStackThreads>(bvh, st)) {
                 writer.template write<ANY_HIT, STATS>(myRay, st);
                 active = false;
             }
@@ -157,7 +158,9 @@ static inline int wavefrontGrid() {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    return sms * 8; // 8 x 128 threads = 32 warps per SM
+    // 8 x 128 threads = 32 warps per SM (56 registers would admit 9); GFX_TRACE_BLOCKS_PER_SM overrides (A/B)
+    static const int perSm = [] { const char* e = getenv("GFX_TRACE_BLOCKS_PER_SM"); const int v = e ? atoi(e) : 0; return v > 0 && v <= 32 ? v : 8; }();
+    return sms * perSm;
 }
 
 } // namespace gfx
