@@ -30,7 +30,7 @@ GFX_D void countRays(const DevFrame &frame, uint32_t n) {
         atomicAdd(frame.stats, (unsigned long long)total);
 }
 
-GFX_D uint32_t gbufferPixel(const DevScene &scene, const DevFrame &frame, const DevFrameParams &p, uint2* sstack) {
+GFX_D uint32_t gbufferPixel(const DevScene &scene, const DevFrame &frame, const DevFrameParams &p) {
     const uint32_t x = blockIdx.x * 8 + threadIdx.x;
     const uint32_t y = p.y0 + blockIdx.y * 8 + threadIdx.y;
     if (x >= frame.W || y >= p.y1)
@@ -57,7 +57,8 @@ GFX_D uint32_t gbufferPixel(const DevScene &scene, const DevFrame &frame, const 
     uint32_t matSlot = 0xFFFFFFFFu, instSlot = 0xFFFFFFFFu, geomInstSlot = 0xFFFFFFFFu, primIndex = 0xFFFFFFFFu;
     uint32_t qbcB = 0, qbcC = 0;
 
-    const Hit hit = traverseBvhSmemStack<false, 64>(scene.bvh, origin, direction, 0.0f, 3.402823466e+38f, sstack);
+    // (a shared-memory stack as in the wavefront kernels was measured here too: 0.67 -> 0.69 ms, coherent primary rays gain nothing)
+    const Hit hit = traverseBvh<false>(scene.bvh, origin, direction, 0.0f, 3.402823466e+38f);
     if (hit.storageIndex != 0xFFFFFFFFu) {
         // closest-hit program (:112-199)
         const uint2 im = __ldg(scene.geomToInstMesh + hit.geomIndex);
@@ -162,8 +163,7 @@ GFX_D uint32_t gbufferPixel(const DevScene &scene, const DevFrame &frame, const 
 }
 
 __global__ void __launch_bounds__(64) k_gbuffer(DevScene scene, DevFrame frame, DevFrameParams p) {
-    __shared__ uint2 sharedStack[kSmemStack][64]; // first entries of every thread's traversal stack (traverse.cuh)
-    countRays(frame, gbufferPixel(scene, frame, p, &sharedStack[0][threadIdx.x + threadIdx.y * 8]));
+    countRays(frame, gbufferPixel(scene, frame, p));
 }
 
 int launchGBuffer(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* params) {
