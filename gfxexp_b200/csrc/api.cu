@@ -408,14 +408,18 @@ int gfx_scene_update_instances(gfx_ctx* ctx, void* stream, const GfxInstanceDesc
         return GFX_ERR_NOT_READY;
     if (!instances || numInstances != S.numInstances)
         return GFX_ERR_INVALID_ARGUMENT;
+    bool moved = false; // light records, importances and the flattened pick follow transform / normal matrix / scale only
     for (uint32_t i = 0; i < numInstances; ++i) {
         DevInstance &d = S.hostInstances[i];
+        moved = moved || memcmp(d.transform, instances[i].transform, 48) != 0 || memcmp(d.normalMatrix, instances[i].normalMatrix, 36) != 0 ||
+                memcmp(&d.uniformScale, &instances[i].uniformScale, 4) != 0;
         memcpy(d.transform, instances[i].transform, 48);
         memcpy(d.curToPrevTransform, instances[i].curToPrevTransform, 48);
         memcpy(d.normalMatrix, instances[i].normalMatrix, 36);
         d.uniformScale = instances[i].uniformScale;
     }
-    S.lightTrisDirty = true;
+    if (moved)
+        S.lightTrisDirty = true;
     // geomIntegral lives on the device copy only: patch the transform part of every record with ONE strided copy
     // out of pinned memory (double-buffered so that the host may run a frame ahead of the device)
     const size_t bytes = (size_t)numInstances * sizeof(DevInstance);
