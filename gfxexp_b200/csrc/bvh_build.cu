@@ -488,6 +488,10 @@ __global__ void k_plocMerge(int m, int n, const uint32_t* __restrict__ clusters,
 // splits + spatial splits); the 8-wide collapse below is shared with the other two hierarchies.
 constexpr uint32_t kSahBins = 16;
 constexpr uint32_t kSahBigNode = 4096;
+// Above this a node is split by MANY blocks (k_sahHuge*): in round 1 the first five levels - one 1024-thread block per node,
+// i.e. one SM for the root's 2.87 M triangles - took 45 of the builder's 65 ms.
+constexpr uint32_t kSahHugeNode = 131072;
+constexpr uint32_t kSahHugeChunk = 8192;  // triangles per block of the multi-block passes
 
 struct SahArgs {
     uint32_t n;
@@ -500,12 +504,29 @@ struct SahArgs {
     uint32_t* count;
     float4* boxLo;
     float4* boxHi;
-    uint32_t* counters;   // [0] next small-list size, [1] next big-list size, [2] internal nodes allocated
+    uint32_t* counters;   // [0] next small-list size, [1] next big-list size, [2] internal nodes allocated, [3] next huge-list size
     const uint4* listIn;  // (node, start, end, -)
     uint4* smallOut;
     uint4* bigOut;
+    uint4* hugeOut;
     uint32_t listSize;
 };
+
+// where a child slice goes next: one-triangle leaves are references, everything else gets a node index and a work record
+__device__ __forceinline__ uint32_t sahEmitChild(const SahArgs &a, uint32_t first, uint32_t last) {
+    const uint32_t cnum = last - first;
+    if (cnum == 1)
+        return 0x80000000u | first;
+    const uint32_t idx = atomicAdd(a.counters + 2, 1u);
+    const uint4 out = make_uint4(idx, first, last, 0u);
+    if (cnum > kSahHugeNode)
+        a.hugeOut[atomicAdd(a.counters + 3, 1u)] = out;
+    else if (cnum > kSahBigNode)
+        a.bigOut[atomicAdd(a.counters + 1, 1u)] = out;
+    else
+        a.smallOut[atomicAdd(a.counters + 0, 1u)] = out;
+    return idx;
+}
 
 template <uint32_t BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_sahSplit(SahArgs a) {
@@ -732,26 +753,340 @@ __global__ void __launch_bounds__(BLOCK) k_sahSplit(SahArgs a) {
 
     // 5. children
     if (tid == 0) {
-        uint32_t refs[2];
-        const uint32_t ranges[2][2] = { { start, start + numLeft }, { start + numLeft, end } };
-        for (int c = 0; c < 2; ++c) {
-            const uint32_t cnum = ranges[c][1] - ranges[c][0];
-            if (cnum == 1) {
-                refs[c] = 0x80000000u | ranges[c][0];
-            }
-            else {
-                const uint32_t idx = atomicAdd(a.counters + 2, 1u);
-                refs[c] = idx;
-                const uint4 out = make_uint4(idx, ranges[c][0], ranges[c][1], 0u);
-                if (cnum > kSahBigNode)
-                    a.bigOut[atomicAdd(a.counters + 1, 1u)] = out;
-                else
-                    a.smallOut[atomicAdd(a.counters + 0, 1u)] = out;
+        a.childL[node] = sahEmitChild(a, start, start + numLeft);
+        a.childR[node] = sahEmitChild(a, start + numLeft, end);
+    }
+}
+
+// ---- the same split for huge nodes, spread over many blocks ------------------------------------------------------------
+// Per node one SahHugeNode record in global memory; bounds and bins are min / max / count over order-preserving integer images,
+// so the merged result - hence the chosen plane - does not depend on how the triangles are spread over blocks, and the
+// partition is stable (per-block left / right counts, a scan per node, then a scatter with those offsets): the tree is the
+// one k_sahSplit would build.
+struct SahHugeNode {
+    uint32_t boundsLo[2][3], boundsHi[2][3];   // [0] AABB, [1] centroid bounds
+    uint32_t binLo[3][kSahBins][3], binHi[3][kSahBins][3], binCount[3][kSahBins];
+    uint32_t splitAxis, splitPlane, numLeft, firstBlock;
+};
+struct SahHugeArgs {
+    SahArgs a;
+    SahHugeNode* nodes;     // one per entry of a.listIn
+    uint32_t* blockLeft;    // per block: triangles of its chunk that go left; then the block's left offset
+    uint32_t* blockRight;   // per block: right offset
+};
+// block -> (list entry, chunk) by walking the (short) list
+__device__ __forceinline__ bool sahHugeLocate(const SahArgs &a, uint32_t block, uint32_t* entry, uint32_t* chunkBegin, uint32_t* chunkEnd) {
+    uint32_t first = 0;
+    for (uint32_t e = 0; e < a.listSize; ++e) {
+        const uint4 rec = a.listIn[e];
+        const uint32_t blocks = (rec.z - rec.y + kSahHugeChunk - 1) / kSahHugeChunk;
+        if (block < first + blocks) {
+            *entry = e;
+            *chunkBegin = rec.y + (block - first) * kSahHugeChunk;
+            *chunkEnd = min(rec.z, *chunkBegin + kSahHugeChunk);
+            return true;
+        }
+        first += blocks;
+    }
+    return false;
+}
+__global__ void k_sahHugeInit(SahHugeArgs h) {
+    SahHugeNode &N = h.nodes[blockIdx.x];
+    uint32_t* w = reinterpret_cast<uint32_t*>(&N);
+    for (uint32_t i = threadIdx.x; i < sizeof(SahHugeNode) / 4; i += blockDim.x)
+        w[i] = 0u;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < 6; i += blockDim.x)
+        (&N.boundsLo[0][0])[i] = 0xFFFFFFFFu;
+    for (uint32_t i = threadIdx.x; i < 3 * kSahBins * 3; i += blockDim.x)
+        (&N.binLo[0][0][0])[i] = 0xFFFFFFFFu;
+    if (threadIdx.x == 0) { // first block of this node in the level's block numbering
+        uint32_t first = 0;
+        for (uint32_t e = 0; e < blockIdx.x; ++e)
+            first += (h.a.listIn[e].z - h.a.listIn[e].y + kSahHugeChunk - 1) / kSahHugeChunk;
+        N.firstBlock = first;
+    }
+}
+__global__ void __launch_bounds__(1024) k_sahHugeBounds(SahHugeArgs h) {
+    uint32_t entry, begin, end;
+    if (!sahHugeLocate(h.a, blockIdx.x, &entry, &begin, &end))
+        return;
+    float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
+    float clo[3] = { INFINITY, INFINITY, INFINITY }, chi[3] = { -INFINITY, -INFINITY, -INFINITY };
+    for (uint32_t i = begin + threadIdx.x; i < end; i += blockDim.x) {
+        const uint32_t t = h.a.order[i];
+        const float4 l = h.a.triLo[t], u = h.a.triHi[t];
+        const float bl[3] = { l.x, l.y, l.z }, bh[3] = { u.x, u.y, u.z };
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const float c = 0.5f * bl[d] + 0.5f * bh[d];
+            lo[d] = fminf(lo[d], bl[d]); hi[d] = fmaxf(hi[d], bh[d]);
+            clo[d] = fminf(clo[d], c); chi[d] = fmaxf(chi[d], c);
+        }
+    }
+    SahHugeNode &N = h.nodes[entry];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        for (int off = 16; off > 0; off >>= 1) {
+            lo[d] = fminf(lo[d], __shfl_xor_sync(0xFFFFFFFFu, lo[d], off));
+            hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xFFFFFFFFu, hi[d], off));
+            clo[d] = fminf(clo[d], __shfl_xor_sync(0xFFFFFFFFu, clo[d], off));
+            chi[d] = fmaxf(chi[d], __shfl_xor_sync(0xFFFFFFFFu, chi[d], off));
+        }
+        if ((threadIdx.x & 31u) == 0) {
+            atomicMin(&N.boundsLo[0][d], orderedFromFloat(lo[d]));
+            atomicMax(&N.boundsHi[0][d], orderedFromFloat(hi[d]));
+            atomicMin(&N.boundsLo[1][d], orderedFromFloat(clo[d]));
+            atomicMax(&N.boundsHi[1][d], orderedFromFloat(chi[d]));
+        }
+    }
+}
+struct SahBinning { // centroid -> bin, exactly k_sahSplit's
+    float cLo[3], binScale[3];
+    __device__ __forceinline__ SahBinning(const uint32_t (*boundsLo)[3], const uint32_t (*boundsHi)[3]) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            cLo[d] = floatFromOrdered(boundsLo[1][d]);
+            const float ext = floatFromOrdered(boundsHi[1][d]) - cLo[d];
+            binScale[d] = ext > 0.0f ? (float)kSahBins / ext : 0.0f;
+        }
+    }
+    __device__ __forceinline__ uint32_t binOf(float c, int d) const {
+        const float f = (c - cLo[d]) * binScale[d];
+        const uint32_t b = (uint32_t)fmaxf(f, 0.0f);
+        return b < kSahBins - 1 ? b : kSahBins - 1;
+    }
+};
+__global__ void __launch_bounds__(1024) k_sahHugeBin(SahHugeArgs h) {
+    constexpr uint32_t WARPS = 32;
+    __shared__ uint32_t sBinLo[WARPS][3][kSahBins][3], sBinHi[WARPS][3][kSahBins][3], sBinCount[WARPS][3][kSahBins];
+    uint32_t entry, begin, end;
+    if (!sahHugeLocate(h.a, blockIdx.x, &entry, &begin, &end))
+        return;
+    SahHugeNode &N = h.nodes[entry];
+    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    for (uint32_t i = tid; i < WARPS * 3 * kSahBins * 3; i += 1024) {
+        (&sBinLo[0][0][0][0])[i] = 0xFFFFFFFFu;
+        (&sBinHi[0][0][0][0])[i] = 0u;
+    }
+    for (uint32_t i = tid; i < WARPS * 3 * kSahBins; i += 1024)
+        (&sBinCount[0][0][0])[i] = 0u;
+    __syncthreads();
+    const SahBinning binning(N.boundsLo, N.boundsHi);
+    const uint32_t num = end - begin, perThread = (num + 1023) / 1024;
+    const uint32_t runBegin = min(end, begin + tid * perThread), runEnd = min(end, runBegin + perThread);
+    for (uint32_t i = runBegin; i < runEnd; ++i) {
+        const uint32_t t = h.a.order[i];
+        const float4 l = h.a.triLo[t], u = h.a.triHi[t];
+        const float bl[3] = { l.x, l.y, l.z }, bh[3] = { u.x, u.y, u.z };
+        const uint32_t ol[3] = { orderedFromFloat(l.x), orderedFromFloat(l.y), orderedFromFloat(l.z) };
+        const uint32_t oh[3] = { orderedFromFloat(u.x), orderedFromFloat(u.y), orderedFromFloat(u.z) };
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const uint32_t b = binning.binOf(0.5f * bl[d] + 0.5f * bh[d], d);
+            atomicAdd(&sBinCount[warp][d][b], 1u);
+#pragma unroll
+            for (int e = 0; e < 3; ++e) {
+                atomicMin(&sBinLo[warp][d][b][e], ol[e]);
+                atomicMax(&sBinHi[warp][d][b][e], oh[e]);
             }
         }
-        a.childL[node] = refs[0];
-        a.childR[node] = refs[1];
     }
+    __syncthreads();
+    for (uint32_t i = tid; i < 3 * kSahBins * 3; i += 1024) {
+        uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+        for (uint32_t w = 0; w < WARPS; ++w) {
+            lo = min(lo, (&sBinLo[w][0][0][0])[i]);
+            hi = max(hi, (&sBinHi[w][0][0][0])[i]);
+        }
+        if (lo != 0xFFFFFFFFu)
+            atomicMin(&N.binLo[0][0][0] + i, lo);
+        if (hi != 0u)
+            atomicMax(&N.binHi[0][0][0] + i, hi);
+    }
+    for (uint32_t i = tid; i < 3 * kSahBins; i += 1024) {
+        uint32_t c = 0;
+        for (uint32_t w = 0; w < WARPS; ++w)
+            c += (&sBinCount[w][0][0])[i];
+        if (c)
+            atomicAdd(&N.binCount[0][0] + i, c);
+    }
+}
+// plane evaluation (k_sahSplit step 3) and the node's box, one block of 32 threads per node
+__global__ void k_sahHugeEval(SahHugeArgs h) {
+    __shared__ float sAxisCost[3];
+    __shared__ uint32_t sAxisPlane[3], sAxisLeft[3];
+    SahHugeNode &N = h.nodes[blockIdx.x];
+    const uint4 rec = h.a.listIn[blockIdx.x];
+    const uint32_t node = rec.x, num = rec.z - rec.y;
+    const uint32_t tid = threadIdx.x;
+    if (tid < 3) {
+        const int d = (int)tid;
+        float rightArea[kSahBins];
+        uint32_t rightCount[kSahBins];
+        float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
+        uint32_t cnt = 0;
+        for (int b = (int)kSahBins - 1; b >= 1; --b) {
+            if (N.binCount[d][b]) {
+                for (int e = 0; e < 3; ++e) {
+                    lo[e] = fminf(lo[e], floatFromOrdered(N.binLo[d][b][e]));
+                    hi[e] = fmaxf(hi[e], floatFromOrdered(N.binHi[d][b][e]));
+                }
+                cnt += N.binCount[d][b];
+            }
+            const float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
+            rightArea[b] = cnt ? ex * ey + ey * ez + ez * ex : 0.0f;
+            rightCount[b] = cnt;
+        }
+        for (int e = 0; e < 3; ++e) { lo[e] = INFINITY; hi[e] = -INFINITY; }
+        cnt = 0;
+        float bestCost = INFINITY;
+        uint32_t bestPlane = 0, bestLeft = 0;
+        for (int b = 0; b < (int)kSahBins - 1; ++b) {
+            if (N.binCount[d][b]) {
+                for (int e = 0; e < 3; ++e) {
+                    lo[e] = fminf(lo[e], floatFromOrdered(N.binLo[d][b][e]));
+                    hi[e] = fmaxf(hi[e], floatFromOrdered(N.binHi[d][b][e]));
+                }
+                cnt += N.binCount[d][b];
+            }
+            if (cnt == 0 || rightCount[b + 1] == 0)
+                continue;
+            const float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
+            const float cost = (ex * ey + ey * ez + ez * ex) * (float)cnt + rightArea[b + 1] * (float)rightCount[b + 1];
+            if (cost < bestCost) {
+                bestCost = cost;
+                bestPlane = (uint32_t)b + 1;
+                bestLeft = cnt;
+            }
+        }
+        sAxisCost[d] = bestCost;
+        sAxisPlane[d] = bestPlane;
+        sAxisLeft[d] = bestLeft;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t axis = 0;
+        if (sAxisCost[1] < sAxisCost[axis]) axis = 1;
+        if (sAxisCost[2] < sAxisCost[axis]) axis = 2;
+        N.splitAxis = axis;
+        N.splitPlane = sAxisPlane[axis];
+        N.numLeft = sAxisPlane[axis] ? sAxisLeft[axis] : num / 2;
+        h.a.boxLo[node] = make_float4(floatFromOrdered(N.boundsLo[0][0]), floatFromOrdered(N.boundsLo[0][1]), floatFromOrdered(N.boundsLo[0][2]), 0.0f);
+        h.a.boxHi[node] = make_float4(floatFromOrdered(N.boundsHi[0][0]), floatFromOrdered(N.boundsHi[0][1]), floatFromOrdered(N.boundsHi[0][2]), 0.0f);
+        h.a.count[node] = num;
+    }
+}
+__device__ __forceinline__ bool sahHugeGoesLeft(const SahHugeArgs &h, const SahHugeNode &N, const SahBinning &binning, uint32_t t) {
+    const float4 l = h.a.triLo[t], u = h.a.triHi[t];
+    const uint32_t axis = N.splitAxis;
+    const float c = axis == 0 ? 0.5f * l.x + 0.5f * u.x : axis == 1 ? 0.5f * l.y + 0.5f * u.y : 0.5f * l.z + 0.5f * u.z;
+    return binning.binOf(c, (int)axis) < N.splitPlane;
+}
+__global__ void __launch_bounds__(1024) k_sahHugeCount(SahHugeArgs h) {
+    __shared__ uint32_t sLeft;
+    uint32_t entry, begin, end;
+    if (!sahHugeLocate(h.a, blockIdx.x, &entry, &begin, &end))
+        return;
+    const SahHugeNode &N = h.nodes[entry];
+    if (threadIdx.x == 0)
+        sLeft = 0;
+    __syncthreads();
+    uint32_t left = 0;
+    if (N.splitPlane) {
+        const SahBinning binning(N.boundsLo, N.boundsHi);
+        for (uint32_t i = begin + threadIdx.x; i < end; i += blockDim.x)
+            left += sahHugeGoesLeft(h, N, binning, h.a.order[i]) ? 1u : 0u;
+    }
+    for (int off = 16; off > 0; off >>= 1)
+        left += __shfl_xor_sync(0xFFFFFFFFu, left, off);
+    if ((threadIdx.x & 31u) == 0 && left)
+        atomicAdd(&sLeft, left);
+    __syncthreads();
+    if (threadIdx.x == 0)
+        h.blockLeft[blockIdx.x] = sLeft;
+}
+// per node: block offsets of the stable partition, and the two children
+__global__ void k_sahHugeOffsets(SahHugeArgs h) {
+    if (threadIdx.x != 0)
+        return;
+    const SahHugeNode &N = h.nodes[blockIdx.x];
+    const uint4 rec = h.a.listIn[blockIdx.x];
+    const uint32_t blocks = (rec.z - rec.y + kSahHugeChunk - 1) / kSahHugeChunk;
+    uint32_t offL = 0, offR = 0;
+    for (uint32_t b = 0; b < blocks; ++b) {
+        const uint32_t chunk = min(kSahHugeChunk, rec.z - rec.y - b * kSahHugeChunk);
+        const uint32_t left = h.blockLeft[N.firstBlock + b];
+        h.blockLeft[N.firstBlock + b] = offL;
+        h.blockRight[N.firstBlock + b] = offR;
+        offL += left;
+        offR += chunk - left;
+    }
+    h.a.childL[rec.x] = sahEmitChild(h.a, rec.y, rec.y + N.numLeft);
+    h.a.childR[rec.x] = sahEmitChild(h.a, rec.y + N.numLeft, rec.z);
+}
+__global__ void __launch_bounds__(1024) k_sahHugeScatter(SahHugeArgs h) {
+    constexpr uint32_t WARPS = 32;
+    __shared__ uint32_t sWarpL[WARPS], sWarpR[WARPS];
+    __shared__ uint32_t sRunL, sRunR;
+    uint32_t entry, begin, end;
+    if (!sahHugeLocate(h.a, blockIdx.x, &entry, &begin, &end))
+        return;
+    const SahHugeNode &N = h.nodes[entry];
+    if (!N.splitPlane)
+        return; // all centroids coincide: the slice is cut in the middle as it stands
+    const uint4 rec = h.a.listIn[entry];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const SahBinning binning(N.boundsLo, N.boundsHi);
+    if (tid == 0) {
+        sRunL = h.blockLeft[blockIdx.x];
+        sRunR = h.blockRight[blockIdx.x];
+    }
+    __syncthreads();
+    for (uint32_t base = begin; base < end; base += 1024) {
+        const uint32_t i = base + tid;
+        const bool valid = i < end;
+        uint32_t t = 0;
+        bool left = false;
+        if (valid) {
+            t = h.a.order[i];
+            left = sahHugeGoesLeft(h, N, binning, t);
+        }
+        const uint32_t ballotL = __ballot_sync(0xFFFFFFFFu, valid && left);
+        const uint32_t ballotR = __ballot_sync(0xFFFFFFFFu, valid && !left);
+        if (lane == 0) {
+            sWarpL[warp] = __popc(ballotL);
+            sWarpR[warp] = __popc(ballotR);
+        }
+        __syncthreads();
+        uint32_t offL = sRunL, offR = sRunR, totL = 0, totR = 0;
+        for (uint32_t w = 0; w < WARPS; ++w) {
+            if (w < warp) { offL += sWarpL[w]; offR += sWarpR[w]; }
+            totL += sWarpL[w]; totR += sWarpR[w];
+        }
+        if (valid) {
+            const uint32_t lt = (1u << lane) - 1u;
+            if (left)
+                h.a.scratch[rec.y + offL + __popc(ballotL & lt)] = t;
+            else
+                h.a.scratch[rec.y + N.numLeft + offR + __popc(ballotR & lt)] = t;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            sRunL += totL;
+            sRunR += totR;
+        }
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(1024) k_sahHugeCopyBack(SahHugeArgs h) {
+    uint32_t entry, begin, end;
+    if (!sahHugeLocate(h.a, blockIdx.x, &entry, &begin, &end))
+        return;
+    if (!h.nodes[entry].splitPlane)
+        return;
+    for (uint32_t i = begin + threadIdx.x; i < end; i += blockDim.x)
+        h.a.order[i] = h.a.scratch[i];
 }
 
 // leaf boxes in their final order
@@ -801,9 +1136,11 @@ int buildBvh(gfx_ctx* ctx, cudaStream_t stream, uint32_t flags) {
     uint64_t *keys, *keysSorted;
     uint32_t *ids, *idsSorted, *childL, *childR, *rangeFirst, *rangeLast, *parentI, *parentL, *arrive, *counters;
     uint2 *queueA, *queueB;
-    uint4* bigListStore[2];
-    void *tmp, *selTmp;
-    const uint32_t bigCapacity = n / kSahBigNode + 2;
+    uint4 *bigListStore[2], *hugeListStore[2];
+    void *tmp, *selTmp, *hugeNodeStore;
+    uint32_t* hugeBlockStore;
+    const uint32_t bigCapacity = n / kSahBigNode + 2, hugeCapacity = n / kSahHugeNode + 2;
+    const uint32_t hugeMaxBlocks = n / kSahHugeChunk + hugeCapacity + 1;
     size_t tmpBytes = 0, selBytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const uint32_t*)nullptr,
                                     (uint32_t*)nullptr, (int)n, 0, 63, stream);
@@ -817,6 +1154,8 @@ int buildBvh(gfx_ctx* ctx, cudaStream_t stream, uint32_t flags) {
         const size_t oParentI = take((size_t)n * 4), oParentL = take((size_t)n * 4), oArrive = take((size_t)n * 4), oCounters = take(16);
         const size_t oQueueA = take((size_t)n * 8), oQueueB = take((size_t)n * 8);
         const size_t oBig0 = take((size_t)bigCapacity * 16), oBig1 = take((size_t)bigCapacity * 16);
+        const size_t oHuge0 = take((size_t)hugeCapacity * 16), oHuge1 = take((size_t)hugeCapacity * 16);
+        const size_t oHugeNodes = take((size_t)hugeCapacity * sizeof(SahHugeNode)), oHugeBlocks = take((size_t)hugeMaxBlocks * 8);
         const size_t oTmp = take(tmpBytes), oSel = take(selBytes);
         if (offset > B.scratchBytes) {
             cudaFree(B.scratch);
@@ -836,6 +1175,9 @@ int buildBvh(gfx_ctx* ctx, cudaStream_t stream, uint32_t flags) {
         arrive = reinterpret_cast<uint32_t*>(base + oArrive); counters = reinterpret_cast<uint32_t*>(base + oCounters);
         queueA = reinterpret_cast<uint2*>(base + oQueueA); queueB = reinterpret_cast<uint2*>(base + oQueueB);
         bigListStore[0] = reinterpret_cast<uint4*>(base + oBig0); bigListStore[1] = reinterpret_cast<uint4*>(base + oBig1);
+        hugeListStore[0] = reinterpret_cast<uint4*>(base + oHuge0); hugeListStore[1] = reinterpret_cast<uint4*>(base + oHuge1);
+        hugeNodeStore = base + oHugeNodes;
+        hugeBlockStore = reinterpret_cast<uint32_t*>(base + oHugeBlocks);
         tmp = base + oTmp; selTmp = base + oSel;
     }
     if (B.builtForTris != n) {
@@ -870,6 +1212,7 @@ int buildBvh(gfx_ctx* ctx, cudaStream_t stream, uint32_t flags) {
         // lists are tiny; counters = { next small, next big, internal nodes allocated }
         uint4* smallLists[2] = { reinterpret_cast<uint4*>(keys), reinterpret_cast<uint4*>(keysSorted) };
         uint4* bigLists[2] = { bigListStore[0], bigListStore[1] };
+        uint4* hugeLists[2] = { hugeListStore[0], hugeListStore[1] };
         SahArgs sa;
         sa.n = n;
         sa.triLo = triLo; sa.triHi = triHi;
@@ -877,18 +1220,39 @@ int buildBvh(gfx_ctx* ctx, cudaStream_t stream, uint32_t flags) {
         sa.childL = childL; sa.childR = childR; sa.count = rangeFirst;
         sa.boxLo = boxLo; sa.boxHi = boxHi;
         sa.counters = counters;
-        uint32_t sizes[2] = { n > kSahBigNode ? 0u : 1u, n > kSahBigNode ? 1u : 0u }; // { small, big } of the current level
+        // { small, big, huge } of the current level
+        uint32_t sizes[3] = { n > kSahBigNode ? 0u : 1u, (n > kSahBigNode && n <= kSahHugeNode) ? 1u : 0u, n > kSahHugeNode ? 1u : 0u };
         const uint4 rootRec = make_uint4(0u, 0u, n, 0u);
-        GFX_CUDA(ctx, cudaMemcpyAsync(sizes[1] ? bigLists[0] : smallLists[0], &rootRec, 16, cudaMemcpyHostToDevice, stream));
-        uint32_t hostSah[3] = { 0u, 0u, 1u }; // node 0 = root
-        GFX_CUDA(ctx, cudaMemcpyAsync(counters, hostSah, 12, cudaMemcpyHostToDevice, stream));
+        GFX_CUDA(ctx, cudaMemcpyAsync(sizes[2] ? hugeLists[0] : sizes[1] ? bigLists[0] : smallLists[0], &rootRec, 16, cudaMemcpyHostToDevice, stream));
+        uint32_t hostSah[4] = { 0u, 0u, 1u, 0u }; // node 0 = root
+        GFX_CUDA(ctx, cudaMemcpyAsync(counters, hostSah, 16, cudaMemcpyHostToDevice, stream));
+        SahHugeArgs ha;
+        ha.nodes = reinterpret_cast<SahHugeNode*>(hugeNodeStore);
+        ha.blockLeft = hugeBlockStore;
+        ha.blockRight = hugeBlockStore + hugeMaxBlocks;
         int cur = 0;
         uint32_t depth = 0;
         const bool profile = getenv("GFX_BVH_SAH_PROFILE") != nullptr;
-        while (sizes[0] + sizes[1] > 0) {
+        while (sizes[0] + sizes[1] + sizes[2] > 0) {
             const auto t0 = std::chrono::steady_clock::now();
             sa.smallOut = smallLists[cur ^ 1];
             sa.bigOut = bigLists[cur ^ 1];
+            sa.hugeOut = hugeLists[cur ^ 1];
+            if (sizes[2]) { // multi-block split of the nodes above kSahHugeNode triangles
+                sa.listIn = hugeLists[cur];
+                sa.listSize = sizes[2];
+                ha.a = sa;
+                const uint32_t blocksUpper = n / kSahHugeChunk + sizes[2] + 1; // sum of ceil(num / chunk) over disjoint slices
+                k_sahHugeInit<<<sizes[2], 128, 0, stream>>>(ha);
+                k_sahHugeBounds<<<blocksUpper, 1024, 0, stream>>>(ha);
+                k_sahHugeBin<<<blocksUpper, 1024, 0, stream>>>(ha);
+                k_sahHugeEval<<<sizes[2], 32, 0, stream>>>(ha);
+                k_sahHugeCount<<<blocksUpper, 1024, 0, stream>>>(ha);
+                k_sahHugeOffsets<<<sizes[2], 32, 0, stream>>>(ha);
+                k_sahHugeScatter<<<blocksUpper, 1024, 0, stream>>>(ha);
+                k_sahHugeCopyBack<<<blocksUpper, 1024, 0, stream>>>(ha);
+                ctx->launches += 8;
+            }
             if (sizes[1]) {
                 sa.listIn = bigLists[cur];
                 sa.listSize = sizes[1];
@@ -899,17 +1263,19 @@ int buildBvh(gfx_ctx* ctx, cudaStream_t stream, uint32_t flags) {
                 sa.listSize = sizes[0];
                 k_sahSplit<64><<<sizes[0], 64, 0, stream>>>(sa); ctx->launches++;
             }
-            GFX_CUDA(ctx, cudaMemcpyAsync(hostSah, counters, 12, cudaMemcpyDeviceToHost, stream));
+            GFX_CUDA(ctx, cudaMemcpyAsync(hostSah, counters, 16, cudaMemcpyDeviceToHost, stream));
             GFX_CUDA(ctx, cudaStreamSynchronize(stream));
             if (profile)
-                fprintf(stderr, "sah level %u: %u small + %u big nodes, %.3f ms\n", depth, sizes[0], sizes[1],
+                fprintf(stderr, "sah level %u: %u small + %u big + %u huge nodes, %.3f ms\n", depth, sizes[0], sizes[1], sizes[2],
                         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
             sizes[0] = hostSah[0];
             sizes[1] = hostSah[1];
+            sizes[2] = hostSah[3];
             const uint32_t zeros[2] = { 0u, 0u };
             GFX_CUDA(ctx, cudaMemcpyAsync(counters, zeros, 8, cudaMemcpyHostToDevice, stream));
+            GFX_CUDA(ctx, cudaMemcpyAsync(counters + 3, zeros, 4, cudaMemcpyHostToDevice, stream));
             cur ^= 1;
-            if (++depth > 4096 || sizes[1] > bigCapacity) {
+            if (++depth > 4096 || sizes[1] > bigCapacity || sizes[2] > hugeCapacity) {
                 ctx->setError("gfx_bvh_build: SAH split did not converge");
                 return GFX_ERR_CUDA;
             }
