@@ -13,6 +13,7 @@
 // exchange ahead of its neighbour (every exchange waits for the neighbour's flag of the same sequence number), and
 // consecutive exchanges target different reservoir buffers, so pushed rows are never overwritten while still being read.
 #include "context.h"
+#include <dlfcn.h>
 #include <map>
 
 namespace gfx {
@@ -187,6 +188,51 @@ int gfx_peer_status(gfx_ctx* ctx, void* stream, uint32_t* timedOut) {
         return rc;
     GFX_CUDA(ctx, cudaMemcpyAsync(timedOut, P->localFlags + (kPeerFlagWords - 1), 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     GFX_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+    return GFX_OK;
+}
+
+// ncclAllGather resolved at run time: from the process image if NCCL is already loaded (torch brings its own), else libnccl.so.2
+typedef int (*NcclAllGatherFn)(const void*, void*, size_t, int, void*, cudaStream_t);
+static NcclAllGatherFn resolveNcclAllGather() {
+    static NcclAllGatherFn fn = [] {
+        void* sym = dlsym(RTLD_DEFAULT, "ncclAllGather");
+        if (!sym) {
+            void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+            if (lib)
+                sym = dlsym(lib, "ncclAllGather");
+        }
+        return reinterpret_cast<NcclAllGatherFn>(sym);
+    }();
+    return fn;
+}
+
+int gfx_framebuffer_allgather(gfx_ctx* ctx, void* ncclComm, void* stream, uint32_t rowsPerRank, void* dstFramebuffer) {
+    if (!ctx || !ncclComm || !dstFramebuffer || !ctx->frame.created || rowsPerRank == 0)
+        return GFX_ERR_INVALID_ARGUMENT;
+    const NcclAllGatherFn allGather = resolveNcclAllGather();
+    if (!allGather) {
+        ctx->setError("gfx_framebuffer_allgather: ncclAllGather not found (load NCCL in the host process)");
+        return GFX_ERR_UNSUPPORTED;
+    }
+    // the rank's own strip inside its beauty buffer: NCCL's in-place convention is sendbuff = recvbuff + rank * count, which the
+    // caller gets by passing the beauty buffer itself as dstFramebuffer; rank is implied by the communicator, so the send
+    // pointer is computed from the communicator-independent row layout only when dst is the beauty buffer
+    int rank = 0;
+    typedef int (*NcclCommUserRankFn)(void*, int*);
+    static NcclCommUserRankFn userRank = reinterpret_cast<NcclCommUserRankFn>(dlsym(RTLD_DEFAULT, "ncclCommUserRank"));
+    if (!userRank || userRank(ncclComm, &rank) != 0) {
+        ctx->setError("gfx_framebuffer_allgather: ncclCommUserRank failed");
+        return GFX_ERR_UNSUPPORTED;
+    }
+    const size_t count = (size_t)rowsPerRank * ctx->frame.W * 4; // floats per strip
+    if ((size_t)(rank + 1) * rowsPerRank > ctx->frame.H)
+        return GFX_ERR_INVALID_ARGUMENT;
+    const float* send = reinterpret_cast<const float*>(ctx->frame.beauty) + (size_t)rank * count;
+    const int rc = allGather(send, dstFramebuffer, count, 7 /* ncclFloat32 */, ncclComm, (cudaStream_t)stream);
+    if (rc != 0) {
+        ctx->setError("gfx_framebuffer_allgather: ncclAllGather returned " + std::to_string(rc));
+        return GFX_ERR_CUDA;
+    }
     return GFX_OK;
 }
 

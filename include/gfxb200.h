@@ -462,6 +462,13 @@ typedef struct GfxStripFrame {
 } GfxStripFrame;
 int gfx_restir_strip_frame(gfx_ctx* ctx, void* stream, GfxFrameParams* params, GfxStripFrame* strip);
 
+/* The one mandatory collective of a strip-sharded frame: all-gathers the composited beauty strips.  Rank r of
+ * the communicator contributes the rows [r * rowsPerRank, (r + 1) * rowsPerRank) of its GFX_BUF_BEAUTY_ACCUM; `dstFramebuffer`
+ * (DEVICE, W * H float4, may be the beauty buffer itself: in-place all-gather) receives the full frame on every rank.
+ * `ncclComm` is the host's ncclComm_t; the library resolves ncclAllGather from the NCCL the process has loaded (or
+ * libnccl.so.2) at first use, so libgfxb200.so has no link-time NCCL dependency.  Stream-ordered on `stream`. */
+int gfx_framebuffer_allgather(gfx_ctx* ctx, void* ncclComm, void* stream, uint32_t rowsPerRank, void* dstFramebuffer);
+
 /* ---- ReGIR cell reservoirs (regir_main.cpp:2033-2068) --------------------------------- */
 /* replaces kernelBuildCellReservoirs / kernelBuildCellReservoirsAndTemporalReuse (build_cell_reservoirs.cu:71-233):
  * streaming RIS of 2^log2NumCandidatesPerLightSlot light samples per slot against the intensity reaching the cell,

@@ -43,6 +43,65 @@ def _worker(rank, world, port, result_path, peer):
     ctx.close()
 
 
+def _worker_allgather(rank, world, port, result_path):
+    """gfx_framebuffer_allgather with the HOST's own ncclComm_t (created here through ctypes on the NCCL torch ships, the way a
+    C++ host would with nccl.h): every rank fills its strip of the beauty buffer, the library all-gathers in place"""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from gfxexp_b200 import abi, engine, scenes
+    import torch.cuda.nccl  # loads torch's libnccl into the process
+    nccl = C.CDLL(None)
+    uid = (C.c_byte * 128)()
+    if rank == 0:
+        assert nccl.ncclGetUniqueId(C.byref(uid)) == 0
+    ids = [bytes(uid)]
+    dist.broadcast_object_list(ids, src=0)
+    C.memmove(uid, ids[0], 128)
+    comm = C.c_void_p()
+    nccl.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_byte * 128, C.c_int]
+    assert nccl.ncclCommInitRank(C.byref(comm), world, uid, rank) == 0
+    ctx = engine.Context(rank)
+    ctx.upload_scene(scenes.tiny_city_scene())
+    ctx.create_frame(W, H)
+    rows = H // world
+    beauty = np.zeros((H, W, 4), dtype=np.float32)
+    beauty[rank * rows:(rank + 1) * rows] = rank + 1.0
+    ctx.upload(abi.BUF_BEAUTY_ACCUM, 0, beauty)
+    ptr, _ = ctx.device_ptr(abi.BUF_BEAUTY_ACCUM, 0)
+    ctx._check(ctx.lib.gfx_framebuffer_allgather(ctx.h, comm, None, rows, ptr), "gfx_framebuffer_allgather")
+    torch.cuda.synchronize()
+    got = ctx.download(abi.BUF_BEAUTY_ACCUM)
+    np.save(result_path + f".{rank}.npy", got)
+    dist.barrier()
+    nccl.ncclCommDestroy.argtypes = [C.c_void_p]
+    nccl.ncclCommDestroy(comm)
+    dist.destroy_process_group()
+    ctx.close()
+
+
+def test_framebuffer_allgather_through_the_c_abi(tmp_path):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    result = str(tmp_path / "gathered")
+    mp.spawn(_worker_allgather, args=(2, port, result), nprocs=2, join=True)
+    rows = H // 2
+    for rank in range(2):
+        got = np.load(result + f".{rank}.npy")
+        assert np.all(got[:rows] == 1.0) and np.all(got[rows:] == 2.0), f"rank {rank}: gathered frame is wrong"
+
+
 @pytest.mark.parametrize("peer", [True, False])
 def test_two_gpu_strips_equal_single_gpu(tmp_path, gfx_ctx, peer):
     import torch
