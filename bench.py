@@ -131,15 +131,16 @@ class ClockSampler:
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
-# (profiles/r02_summary.md): RIS candidate kernel (r02c), visibility trace (r01f: unchanged kernel)
-NCU_DRAM_TRAFFIC = {"ris_candidates": 264.6e6, "trace_visibility": 95.5e6}
+# (profiles/r02_summary.md): RIS candidate kernel (ris_r02), visibility trace (trace_r02)
+NCU_DRAM_TRAFFIC = {"ris_candidates": 273.2e6, "trace_visibility": 87.6e6}
 # what actually bounds the dominant kernel (same capture): issue slots at ~15 of 32 lanes, then the L1 data pipe - not HBM
-NCU_NOTE = {"ris_candidates": {"capture": "gpurun_out/ris_r02c.ncu-rep (profiles/r02_summary.md)",
-                               "l1tex_data_pipe_lsu_wavefronts_pct_of_peak": 58.2, "l1_load_wavefronts_per_launch": 100.4e6,
-                               "issue_active_pct": 59.4, "warps_active_pct": 36.0, "lanes_per_instruction": 14.7,
-                               "reading": "bound by instruction issue at 14.7 of 32 active lanes (70 % of the candidates leave after "
-                                          "the staged light fetch) and by the L1 wavefronts of the divergent light-record gathers; "
-                                          "DRAM traffic equals the algorithmic bytes"}}
+NCU_NOTE = {"ris_candidates": {"capture": "gpurun_out/ris_r02.ncu-rep (profiles/r02_summary.md section 2)",
+                               "l1tex_data_pipe_lsu_wavefronts_pct_of_peak": 73.7, "l1_load_wavefronts_per_launch": 104.8e6,
+                               "issue_active_pct": 54.4, "warps_active_pct": 46.4, "lanes_per_instruction": 19.7,
+                               "reading": "not an HBM kernel: per candidate a 32-byte guide entry and up to 128 bytes of a light record are "
+                                          "gathered per lane (94 % L2 hits) and 30 % of the candidates get an IEEE-exact BSDF evaluation; "
+                                          "bound by the L1 data pipe's wavefront rate (74 %) and instruction issue (54 %) at 46 % "
+                                          "occupancy; DRAM traffic 273 MB against 249 MB algorithmic"}}
 
 
 def frame_launches(ctx, params, frame_index, num_spatial_passes, timers=None):

@@ -16,12 +16,12 @@
 // neural_radiance_caching_main.cpp:2291-2304; here the inference launch reads its size from device memory).
 #include "pathtrace.cuh"
 
-// occupancy knob of the first-hit / bounce kernels (A/B: tools/ab_flags.sh); unset = ptxas decides
-#ifdef GFX_BOUNCE_MIN_BLOCKS
-#define GFX_BOUNCE_BOUNDS GFX_BOUNCE_BOUNDS
-#else
-#define GFX_BOUNCE_BOUNDS __launch_bounds__(64)
+// occupancy of the first-hit / bounce kernels: 16 blocks of 64 threads per SM = 64 registers (measured against the 88-128
+// ptxas picks unconstrained: path-tracer bounce 0.44 -> 0.37 ms, NRC bounce 0.58 -> 0.53 ms; profiles/r02_summary.md)
+#ifndef GFX_BOUNCE_MIN_BLOCKS
+#define GFX_BOUNCE_MIN_BLOCKS 16
 #endif
+#define GFX_BOUNCE_BOUNDS __launch_bounds__(64, GFX_BOUNCE_MIN_BLOCKS)
 
 namespace gfx {
 
