@@ -191,26 +191,26 @@ int gfx_peer_status(gfx_ctx* ctx, void* stream, uint32_t* timedOut) {
     return GFX_OK;
 }
 
-// ncclAllGather resolved at run time: from the process image if NCCL is already loaded (torch brings its own), else libnccl.so.2
-typedef int (*NcclAllGatherFn)(const void*, void*, size_t, int, void*, cudaStream_t);
-static NcclAllGatherFn resolveNcclAllGather() {
-    static NcclAllGatherFn fn = [] {
-        void* sym = dlsym(RTLD_DEFAULT, "ncclAllGather");
-        if (!sym) {
-            void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-            if (lib)
-                sym = dlsym(lib, "ncclAllGather");
-        }
-        return reinterpret_cast<NcclAllGatherFn>(sym);
-    }();
-    return fn;
+// NCCL entry points resolved at run time: from the process image if NCCL is globally visible, else from libnccl.so.2 (which
+// the loader maps to the copy the process has already loaded, e.g. torch's)
+static void* ncclSymbol(const char* name) {
+    void* sym = dlsym(RTLD_DEFAULT, name);
+    if (!sym) {
+        static void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (lib)
+            sym = dlsym(lib, name);
+    }
+    return sym;
 }
+typedef int (*NcclAllGatherFn)(const void*, void*, size_t, int, void*, cudaStream_t);
+typedef int (*NcclCommUserRankFn)(void*, int*);
 
 int gfx_framebuffer_allgather(gfx_ctx* ctx, void* ncclComm, void* stream, uint32_t rowsPerRank, void* dstFramebuffer) {
     if (!ctx || !ncclComm || !dstFramebuffer || !ctx->frame.created || rowsPerRank == 0)
         return GFX_ERR_INVALID_ARGUMENT;
-    const NcclAllGatherFn allGather = resolveNcclAllGather();
-    if (!allGather) {
+    static const NcclAllGatherFn allGather = reinterpret_cast<NcclAllGatherFn>(ncclSymbol("ncclAllGather"));
+    static const NcclCommUserRankFn userRank = reinterpret_cast<NcclCommUserRankFn>(ncclSymbol("ncclCommUserRank"));
+    if (!allGather || !userRank) {
         ctx->setError("gfx_framebuffer_allgather: ncclAllGather not found (load NCCL in the host process)");
         return GFX_ERR_UNSUPPORTED;
     }
@@ -218,9 +218,7 @@ int gfx_framebuffer_allgather(gfx_ctx* ctx, void* ncclComm, void* stream, uint32
     // caller gets by passing the beauty buffer itself as dstFramebuffer; rank is implied by the communicator, so the send
     // pointer is computed from the communicator-independent row layout only when dst is the beauty buffer
     int rank = 0;
-    typedef int (*NcclCommUserRankFn)(void*, int*);
-    static NcclCommUserRankFn userRank = reinterpret_cast<NcclCommUserRankFn>(dlsym(RTLD_DEFAULT, "ncclCommUserRank"));
-    if (!userRank || userRank(ncclComm, &rank) != 0) {
+    if (userRank(ncclComm, &rank) != 0) {
         ctx->setError("gfx_framebuffer_allgather: ncclCommUserRank failed");
         return GFX_ERR_UNSUPPORTED;
     }

@@ -55,16 +55,18 @@ def _worker_allgather(rank, world, port, result_path):
     torch.cuda.set_device(rank)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from gfxexp_b200 import abi, engine, scenes
-    import torch.cuda.nccl  # loads torch's libnccl into the process
-    nccl = C.CDLL(None)
-    uid = (C.c_byte * 128)()
+    nccl = C.CDLL("libnccl.so.2")  # the soname resolves to the copy torch has loaded
+
+    class UniqueId(C.Structure):  # ncclUniqueId, passed by value
+        _fields_ = [("internal", C.c_byte * 128)]
+    uid = UniqueId()
     if rank == 0:
         assert nccl.ncclGetUniqueId(C.byref(uid)) == 0
     ids = [bytes(uid)]
     dist.broadcast_object_list(ids, src=0)
-    C.memmove(uid, ids[0], 128)
+    C.memmove(C.byref(uid), ids[0], 128)
     comm = C.c_void_p()
-    nccl.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_byte * 128, C.c_int]
+    nccl.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, UniqueId, C.c_int]
     assert nccl.ncclCommInitRank(C.byref(comm), world, uid, rank) == 0
     ctx = engine.Context(rank)
     ctx.upload_scene(scenes.tiny_city_scene())
