@@ -366,6 +366,8 @@ _DECLS = {
     "gfx_regir_update_access": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxFrameParams), c_u32]),
     "gfx_nrc_preprocess": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxFrameParams), c_u32, c_u32, C.c_int]),
     "gfx_nrc_frame_infer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gfx_nrc_shard": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "gfx_nrc_frame_infer_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, c_u32, c_u32]),
     "gfx_nrc_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxFrameParams)]),
     "gfx_nrc_propagate": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxFrameParams)]),
     "gfx_nrc_shuffle": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxFrameParams)]),

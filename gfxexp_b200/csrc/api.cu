@@ -57,7 +57,7 @@ void FrameState::release() {
     }
     cudaFree(nrc.trainVertexInfo); cudaFree(nrc.suffixTerminal); cudaFree(nrc.shufflers); cudaFree(nrc.state);
     cudaFree(nrc.pathA); cudaFree(nrc.pathB); cudaFree(nrc.shadowPending2); cudaFree(nrc.tilePrev); cudaFree(nrc.tileSuffixEnded);
-    cudaFree(nrc.stagedFlags); cudaFree(nrc.stagedIndex); cudaFree(nrc.stagedQuery); cudaFree(nrc.stagedThroughput); cudaFree(nrc.stagedNEE);
+    cudaFree(nrc.stagedFlags); cudaFree(nrc.stagedIndex); cudaFree(nrc.stagedQuery); cudaFree(nrc.stagedThroughput); cudaFree(nrc.stagedNEE); cudaFree(nrc.shardCounts);
     *this = FrameState();
 }
 
@@ -1027,6 +1027,23 @@ static int nrcPass(gfx_ctx* ctx, void* stream, const GfxFrameParams* params, int
         return GFX_ERR_NOT_READY;
     return launchNrcPass(ctx, (cudaStream_t)stream, params, pass);
 }
+int gfx_nrc_shard(gfx_ctx* ctx, void* ncclComm, int rank, int world) {
+    CHECK_CTX(ctx);
+    if (!ctx->frame.created)
+        return GFX_ERR_NOT_READY;
+    if (ncclComm && (world < 1 || world > 64 || rank < 0 || rank >= world))
+        return GFX_ERR_INVALID_ARGUMENT;
+    const int rc = ensureNrcFrame(ctx);
+    if (rc != GFX_OK)
+        return rc;
+    FrameState::Nrc &N = ctx->frame.nrc;
+    const bool on = ncclComm != nullptr && world > 1;
+    N.shardComm = on ? ncclComm : nullptr;
+    N.shardRank = on ? rank : 0;
+    N.shardWorld = on ? world : 1;
+    return GFX_OK;
+}
+
 int gfx_nrc_accumulate(gfx_ctx* ctx, void* stream, const GfxFrameParams* params) { return nrcPass(ctx, stream, params, 0); }
 int gfx_nrc_propagate(gfx_ctx* ctx, void* stream, const GfxFrameParams* params) { return nrcPass(ctx, stream, params, 1); }
 int gfx_nrc_shuffle(gfx_ctx* ctx, void* stream, const GfxFrameParams* params) { return nrcPass(ctx, stream, params, 2); }

@@ -133,6 +133,11 @@ struct FrameState {
         float* stagedQuery = nullptr;       // 14 floats
         float4* stagedThroughput = nullptr;
         float4* stagedNEE = nullptr;
+        // strip sharding across ranks (gfx_nrc_shard): every rank traces its rows; the training vertices are numbered
+        // globally through an all-gather of the per-round counts and the records are merged before the shuffle
+        void* shardComm = nullptr;          // ncclComm_t of the ranks that share the frame
+        int shardRank = 0, shardWorld = 1;
+        uint32_t* shardCounts = nullptr;    // [0 .. world) gathered counts of this round, [64] this rank's count
         bool created = false;
     } nrc;
     // rearchitected ReSTIR (restir_rearch.cu), allocated on first use
@@ -261,6 +266,7 @@ int launchPathTrace(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* p, 
 int launchPathTraceNrc(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* p);
 int ensurePathTraceBuffers(gfx_ctx* ctx);
 int ensureNrcFrame(gfx_ctx* ctx);
+void* ncclSymbol(const char* name); // peer.cu: NCCL entry points resolved at run time from the NCCL the host process loaded
 int launchRegirBuildCells(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* p, uint32_t frameIndex, int useTemporalReuse);
 int launchRegirUpdateAccess(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* p, uint32_t frameIndex);
 void releaseRegir(gfx_ctx* ctx);

@@ -1678,6 +1678,37 @@ int gfx_nrc_frame_infer(gfx_ctx* ctx, gfx_nrc* n, void* stream) {
     return nrcInferLaunch(n, (cudaStream_t)stream, N.inferenceQuery, N.inferredRadiance, N.queryCapacity, N.state + 26);
 }
 
+int gfx_nrc_frame_infer_rows(gfx_ctx* ctx, gfx_nrc* n, void* stream, uint32_t rowLo, uint32_t rowHi) {
+    if (!ctx || !n || n->ctx != ctx)
+        return GFX_ERR_INVALID_ARGUMENT;
+    if (!ctx->frame.created)
+        return GFX_ERR_NOT_READY;
+    int rc = ensureNrcFrame(ctx);
+    if (rc != GFX_OK)
+        return rc;
+    const FrameState::Nrc &N = ctx->frame.nrc;
+    const uint32_t W = ctx->frame.W, H = ctx->frame.H;
+    if (rowLo >= rowHi || rowHi > H)
+        return GFX_ERR_INVALID_ARGUMENT;
+    const size_t numPixels = (size_t)W * H, first = (size_t)rowLo * W;
+    if ((first & 127u) || (numPixels & 127u)) {
+        ctx->setError("gfx_nrc_frame_infer_rows: rowLo * width and width * height must be multiples of the 128-query tile");
+        return GFX_ERR_INVALID_ARGUMENT;
+    }
+    // the strip's terminal queries (one per pixel; the tail of the last 128-query tile reads into the next rows, whose
+    // predictions this rank does not use) ...
+    const uint32_t numRowQueries = (uint32_t)((((size_t)(rowHi - rowLo) * W + 127) / 128) * 128);
+    const uint32_t rowQueries = (uint32_t)(first + numRowQueries <= N.queryCapacity ? numRowQueries : N.queryCapacity - first);
+    rc = nrcInferLaunch(n, (cudaStream_t)stream, N.inferenceQuery + 14 * first, N.inferredRadiance + 3 * first, rowQueries, nullptr);
+    if (rc != GFX_OK)
+        return rc;
+    // ... and the training-suffix queries of all tiles (slots of the other ranks' tiles hold stale queries: their
+    // predictions are never read here, propagation only walks the suffixes this rank traced)
+    const uint32_t suffixCapacity = (uint32_t)(N.queryCapacity - numPixels);
+    return nrcInferLaunch(n, (cudaStream_t)stream, N.inferenceQuery + 14 * numPixels, N.inferredRadiance + 3 * numPixels, suffixCapacity,
+                          N.state + 27);
+}
+
 int gfx_nrc_frame_train(gfx_ctx* ctx, gfx_nrc* n, void* stream, float* lossOnHost) {
     if (!ctx || !n || n->ctx != ctx)
         return GFX_ERR_INVALID_ARGUMENT;

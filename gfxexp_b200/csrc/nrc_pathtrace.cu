@@ -33,7 +33,7 @@ constexpr uint32_t kMaxNrcRounds = 62;                  // pathLength is a 6-bit
 
 enum { // words of the state block (GFX_BUF_NRC_STATE)
     NRC_NUM_TRAINING_DATA = 0, NRC_TILE_SIZE = 2, NRC_OFFSET_UNBIASED_TILE = 6, NRC_OFFSET_TRAINING_PATH = 7,
-    NRC_TARGET_MIN = 8, NRC_TARGET_MAX = 11, NRC_TARGET_AVG = 20, NRC_NUM_INFERENCE_QUERIES = 26
+    NRC_TARGET_MIN = 8, NRC_TARGET_MAX = 11, NRC_TARGET_AVG = 20, NRC_NUM_INFERENCE_QUERIES = 26, NRC_NUM_SUFFIX_QUERIES = 27
 };
 enum { // per-path flags (pathA.z)
     NRC_F_RENDERING_ENDS_WITH_CACHE = 1u, NRC_F_TRAINING_PATH = 2u, NRC_F_UNBIASED_TILE = 4u, NRC_F_PRIMARY_HIT = 8u
@@ -61,6 +61,8 @@ struct DevNrc {
     float* stagedQuery;
     float4* stagedThroughput;
     float4* stagedNEE;
+    uint32_t* shardCounts; // [0 .. shardWorld) the ranks' vertex counts of this round, [64] this rank's own
+    uint32_t shardRank, shardWorld;
 };
 
 static DevNrc makeDevNrc(const gfx_ctx* ctx) {
@@ -89,6 +91,9 @@ static DevNrc makeDevNrc(const gfx_ctx* ctx) {
     d.stagedQuery = N.stagedQuery;
     d.stagedThroughput = N.stagedThroughput;
     d.stagedNEE = N.stagedNEE;
+    d.shardCounts = N.shardCounts;
+    d.shardRank = (uint32_t)N.shardRank;
+    d.shardWorld = N.shardComm ? (uint32_t)N.shardWorld : 1u;
     return d;
 }
 
@@ -131,6 +136,7 @@ int ensureNrcFrame(gfx_ctx* ctx) {
     GFX_CUDA(ctx, alloc((void**)&N.stagedQuery, S * 56));
     GFX_CUDA(ctx, alloc((void**)&N.stagedThroughput, S * 16));
     GFX_CUDA(ctx, alloc((void**)&N.stagedNEE, S * 16));
+    GFX_CUDA(ctx, alloc((void**)&N.shardCounts, 128 * 4));
     // host-side initial values (neural_radiance_caching_main.cpp:1155-1193)
     std::vector<uint32_t> suffix(S, kInvalidVertexDataIndex);
     GFX_CUDA(ctx, cudaMemcpy(N.suffixTerminal, suffix.data(), S * 4, cudaMemcpyHostToDevice));
@@ -231,6 +237,7 @@ __global__ void k_nrcPreprocess(DevNrc n, uint32_t W, uint32_t H, uint32_t bufId
         // the launch size of the inference pass, computed by the host in the reference (:2301-2304)
         const uint32_t numTilesX = (W + newTileSize[0] - 1) / newTileSize[0], numTilesY = (H + newTileSize[1] - 1) / newTileSize[1];
         n.state[NRC_NUM_INFERENCE_QUERIES] = (W * H + numTilesX * numTilesY + 127) / 128 * 128;
+        n.state[NRC_NUM_SUFFIX_QUERIES] = (numTilesX * numTilesY + 127) / 128 * 128; // a strip's second launch (gfx_nrc_frame_infer_rows)
     }
     n.suffixTerminal[linearIndex] = packSuffixTerminal(kInvalidVertexDataIndex, false, 0);
     n.tilePrev[linearIndex] = kInvalidVertexDataIndex;
@@ -280,9 +287,9 @@ GFX_D void emitRaysNrc(const DevScene &s, const DevPathState &ps, const DevNrc &
 // pathTrace_raygen_generic<true> up to the path extension loop (optix_pathtracing_kernels.cu:95-283)
 __global__ void GFX_BOUNCE_BOUNDS k_nrcFirstHit(DevScene s, DevFrame f, DevFrameParams p, DevPathState ps, DevNrc n) {
     const uint32_t x = blockIdx.x * 8 + threadIdx.x;
-    const uint32_t y = blockIdx.y * 8 + threadIdx.y;
+    const uint32_t y = p.y0 + blockIdx.y * 8 + threadIdx.y;
     const uint32_t lane = (threadIdx.x + threadIdx.y * blockDim.x) & 31u;
-    const bool inside = x < f.W && y < f.H;
+    const bool inside = x < f.W && y < p.y1;
     const uint32_t pix = inside ? y * f.W + x : 0u;
 
     bool alive = false;
@@ -566,17 +573,31 @@ __global__ void __launch_bounds__(1024) k_nrcCommitScan(DevNrc n, uint32_t bufId
             blockTotal = wi;
     }
     __syncthreads();
-    uint32_t rank = n.state[NRC_NUM_TRAINING_DATA + bufIdx] + warpSums[tid >> 5] + (incl - local);
+    // sharded over ranks: the numbers are local until the ranks' counts of this round have been gathered (k_nrcCommitScatter
+    // adds the vertices of the earlier rounds and of the ranks above, k_nrcCommitAdvance moves the counter on)
+    const bool sharded = n.shardWorld > 1;
+    uint32_t rank = (sharded ? 0u : n.state[NRC_NUM_TRAINING_DATA + bufIdx]) + warpSums[tid >> 5] + (incl - local);
     for (uint32_t t = begin; t < end; ++t)
         if (n.stagedFlags[t] & 1u)
             n.stagedIndex[t] = rank++;
     __syncthreads();
-    if (tid == 0)
-        n.state[NRC_NUM_TRAINING_DATA + bufIdx] += blockTotal; // the counter keeps counting past the buffer size (:216)
+    if (tid == 0) {
+        if (sharded)
+            n.shardCounts[64] = blockTotal;
+        else
+            n.state[NRC_NUM_TRAINING_DATA + bufIdx] += blockTotal; // the counter keeps counting past the buffer size (:216)
+    }
+}
+
+__global__ void k_nrcCommitAdvance(DevNrc n, uint32_t bufIdx) {
+    uint32_t total = 0;
+    for (uint32_t r = 0; r < n.shardWorld; ++r)
+        total += n.shardCounts[r];
+    n.state[NRC_NUM_TRAINING_DATA + bufIdx] += total;
 }
 
 // ... and every staged vertex is moved to the record it was given (:213-248, :568-617)
-__global__ void k_nrcCommitScatter(DevNrc n, uint32_t numPixels) {
+__global__ void k_nrcCommitScatter(DevNrc n, uint32_t numPixels, uint32_t bufIdx) {
     const uint32_t tile = blockDim.x * blockIdx.x + threadIdx.x;
     if (tile >= n.numSuffixes)
         return;
@@ -584,7 +605,13 @@ __global__ void k_nrcCommitScatter(DevNrc n, uint32_t numPixels) {
     if (!(flags & 1u))
         return;
     n.stagedFlags[tile] = 0;
-    const uint32_t trainDataIndex = n.stagedIndex[tile];
+    uint32_t trainDataIndex = n.stagedIndex[tile];
+    if (n.shardWorld > 1) { // tile order across ranks = rank order: strips are runs of tile rows
+        trainDataIndex += n.state[NRC_NUM_TRAINING_DATA + bufIdx];
+        for (uint32_t r = 0; r < n.shardRank; ++r)
+            trainDataIndex += n.shardCounts[r];
+        n.stagedIndex[tile] = trainDataIndex;
+    }
     const uint32_t prev = n.tilePrev[tile];
     const uint32_t pathLength = flags >> 8;
     const float* query = n.stagedQuery + 14 * (size_t)tile;
@@ -611,10 +638,9 @@ __global__ void k_nrcCommitScatter(DevNrc n, uint32_t numPixels) {
 }
 
 // ray-gen epilogue (:312-346)
-__global__ void __launch_bounds__(256) k_nrcFinish(DevFrame f, DevPathState ps, DevNrc n) {
-    const uint32_t numPixels = f.W * f.H;
-    const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pix >= numPixels)
+__global__ void __launch_bounds__(256) k_nrcFinish(DevFrame f, DevPathState ps, DevNrc n, uint32_t firstPixel, uint32_t endPixel) {
+    const uint32_t pix = firstPixel + blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= endPixel)
         return;
     const float4 pa = n.pathA[pix];
     const uint32_t flags = __float_as_uint(pa.z);
@@ -672,12 +698,25 @@ int launchPathTraceNrc(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* 
     rc = ensureNrcFrame(ctx);
     if (rc != GFX_OK)
         return rc;
-    if (params->tileOriginY != 0 || (params->tileRows != 0 && params->tileRows != ctx->frame.H)) {
-        ctx->setError("gfx_pathtrace_launch(GFX_PT_NRC): the NRC path tracer works on full frames");
-        return GFX_ERR_INVALID_ARGUMENT;
-    }
     FrameState &F = ctx->frame;
     const DevFrameParams p = makeDevParams(ctx, params);
+    // a strip of rows (tileOriginY / tileRows) is one rank's share of a frame sharded with gfx_nrc_shard: the training
+    // vertices are numbered over the whole frame, so a strip without the other ranks would leave holes in the records
+    const bool sharded = F.nrc.shardComm != nullptr && F.nrc.shardWorld > 1;
+    if (!sharded && (p.y0 != 0 || p.y1 != F.H)) {
+        ctx->setError("gfx_pathtrace_launch(GFX_PT_NRC): strips need gfx_nrc_shard (the training records span the frame)");
+        return GFX_ERR_INVALID_ARGUMENT;
+    }
+    if (p.y0 >= p.y1) {
+        ctx->setError("gfx_pathtrace_launch(GFX_PT_NRC): empty strip");
+        return GFX_ERR_INVALID_ARGUMENT;
+    }
+    typedef int (*NcclAllGatherFn)(const void*, void*, size_t, int, void*, cudaStream_t);
+    static const NcclAllGatherFn allGather = reinterpret_cast<NcclAllGatherFn>(ncclSymbol("ncclAllGather"));
+    if (sharded && !allGather) {
+        ctx->setError("gfx_pathtrace_launch(GFX_PT_NRC): ncclAllGather not found (load NCCL in the host process)");
+        return GFX_ERR_UNSUPPORTED;
+    }
     const DevScene s = ctx->devScene();
     const DevFrame f = ctx->devFrame();
     const DevPathState ps = makePathState(ctx);
@@ -691,13 +730,24 @@ int launchPathTraceNrc(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* 
     GFX_CUDA(ctx, cudaMemsetAsync(F.ptCounters, 0, (kMaxPathRounds + 1) * 16, stream));
 
     const dim3 block(8, 8);
-    const dim3 grid((F.W + 7) / 8, (F.H + 7) / 8);
+    const dim3 grid((F.W + 7) / 8, (p.y1 - p.y0 + 7) / 8);
     const uint32_t scatterGrid = (n.numSuffixes + 127) / 128;
+    int commitError = 0;
+    auto commit = [&]() {
+        GFX_TIMED(ctx, stream, "nrc_commit");
+        k_nrcCommitScan<<<1, 1024, 0, stream>>>(n, p.bufferIndex, F.W, F.H);
+        if (sharded) // one word per rank and round: the only exchange the path tracer needs
+            commitError |= allGather(n.shardCounts + 64, n.shardCounts, 1, 3 /* ncclUint32 */, F.nrc.shardComm, stream);
+        k_nrcCommitScatter<<<scatterGrid, 128, 0, stream>>>(n, numPixels, p.bufferIndex);
+        ctx->launches += 2;
+        if (sharded) {
+            k_nrcCommitAdvance<<<1, 1, 0, stream>>>(n, p.bufferIndex);
+            ctx->launches++;
+        }
+    };
     { GFX_TIMED(ctx, stream, "nrc_first_hit"); k_nrcFirstHit<<<grid, block, 0, stream>>>(s, f, p, ps, n); }
-    { GFX_TIMED(ctx, stream, "nrc_commit");
-      k_nrcCommitScan<<<1, 1024, 0, stream>>>(n, p.bufferIndex, F.W, F.H);
-      k_nrcCommitScatter<<<scatterGrid, 128, 0, stream>>>(n, numPixels); }
-    ctx->launches += 3;
+    commit();
+    ctx->launches += 1;
     const int traceGrid = wavefrontGrid();
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
@@ -708,10 +758,8 @@ int launchPathTraceNrc(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* 
         { GFX_TIMED(ctx, stream, "nrc_trace_shadow"); k_traceWavefront<true, false><<<traceGrid, 128, 0, stream>>>(s.bvh, ps.shadowRays, c + 2, 0u, c + 3, shadowWriter); }
         { GFX_TIMED(ctx, stream, "nrc_trace_extension"); k_traceWavefront<false, false><<<traceGrid, 128, 0, stream>>>(s.bvh, ps.extRays[round & 1], c + 0, 0u, c + 1, extWriter); }
         { GFX_TIMED(ctx, stream, "nrc_bounce"); k_nrcBounce<<<sms * 16, 64, 0, stream>>>(s, f, p, ps, n, round); }
-        { GFX_TIMED(ctx, stream, "nrc_commit");
-          k_nrcCommitScan<<<1, 1024, 0, stream>>>(n, p.bufferIndex, F.W, F.H);
-          k_nrcCommitScatter<<<scatterGrid, 128, 0, stream>>>(n, numPixels); }
-        ctx->launches += 5;
+        commit();
+        ctx->launches += 3;
     }
     // shadow rays requested by the last round (a training path may still have sampled a light there)
     {
@@ -719,18 +767,22 @@ int launchPathTraceNrc(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* 
         k_traceWavefront<true, false><<<traceGrid, 128, 0, stream>>>(s.bvh, ps.shadowRays, c + 2, 0u, c + 3, shadowWriter);
         ctx->launches++;
     }
-    k_nrcFinish<<<(numPixels + 255) / 256, 256, 0, stream>>>(f, ps, n);
+    const uint32_t firstPixel = p.y0 * F.W, endPixel = p.y1 * F.W;
+    k_nrcFinish<<<(endPixel - firstPixel + 255) / 256, 256, 0, stream>>>(f, ps, n, firstPixel, endPixel);
     ctx->launches++;
     GFX_CUDA(ctx, cudaGetLastError());
+    if (commitError) {
+        ctx->setError("gfx_pathtrace_launch(GFX_PT_NRC): ncclAllGather of the training-vertex counts failed");
+        return GFX_ERR_CUDA;
+    }
     return GFX_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // nrc_setup_kernels.cu:51-92
 __global__ void __launch_bounds__(256) k_nrcAccumulate(DevFrame f, DevFrameParams p, DevNrc n) {
-    const uint32_t numPixels = f.W * f.H;
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= numPixels)
+    const uint32_t i = p.y0 * f.W + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.y1 * f.W)
         return;
     const uint4 t = n.terminalInfo[i];
     const f3 alpha(__uint_as_float(t.x), __uint_as_float(t.y), __uint_as_float(t.z));
@@ -873,6 +925,10 @@ int launchNrcPreprocess(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams*
     if (rc != GFX_OK)
         return rc;
     const DevNrc n = makeDevNrc(ctx);
+    if (n.shardWorld > 1) { // the ranks' records are merged by an integer sum (launchNrcPass, propagate): start from zero
+        GFX_CUDA(ctx, cudaMemsetAsync(n.trainQuery[0], 0, (size_t)kTrainBufferSize * 56, stream));
+        GFX_CUDA(ctx, cudaMemsetAsync(n.trainTarget[0], 0, (size_t)kTrainBufferSize * 12, stream));
+    }
     k_nrcPreprocess<<<(n.numSuffixes + 255) / 256, 256, 0, stream>>>(n, ctx->frame.W, ctx->frame.H, params->bufferIndex & 1,
                                                                      offsetToSelectUnbiasedTile, offsetToSelectTrainingPath,
                                                                      isNewSequence ? 1u : 0u);
@@ -889,8 +945,27 @@ int launchNrcPass(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* param
     const DevFrameParams p = makeDevParams(ctx, params);
     const uint32_t numPixels = ctx->frame.W * ctx->frame.H;
     switch (pass) {
-    case 0: k_nrcAccumulate<<<(numPixels + 255) / 256, 256, 0, stream>>>(ctx->devFrame(), p, n); break;
-    case 1: k_nrcPropagate<<<(n.numSuffixes + 127) / 128, 128, 0, stream>>>(p, n, numPixels); break;
+    case 0: k_nrcAccumulate<<<((p.y1 - p.y0) * ctx->frame.W + 255) / 256, 256, 0, stream>>>(ctx->devFrame(), p, n); break;
+    case 1:
+        k_nrcPropagate<<<(n.numSuffixes + 127) / 128, 128, 0, stream>>>(p, n, numPixels);
+        if (n.shardWorld > 1) {
+            // every rank trains on all records (the weights stay replicated): each record was written by exactly one rank
+            // and is zero elsewhere, so an unsigned integer sum over the ranks reproduces its bits
+            typedef int (*NcclAllReduceFn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+            static const NcclAllReduceFn allReduce = reinterpret_cast<NcclAllReduceFn>(ncclSymbol("ncclAllReduce"));
+            if (!allReduce) {
+                ctx->setError("gfx_nrc_propagate: ncclAllReduce not found (load NCCL in the host process)");
+                return GFX_ERR_UNSUPPORTED;
+            }
+            void* comm = ctx->frame.nrc.shardComm;
+            int e = allReduce(n.trainQuery[0], n.trainQuery[0], (size_t)kTrainBufferSize * 14, 3 /* ncclUint32 */, 0 /* ncclSum */, comm, stream);
+            e |= allReduce(n.trainTarget[0], n.trainTarget[0], (size_t)kTrainBufferSize * 3, 3, 0, comm, stream);
+            if (e) {
+                ctx->setError("gfx_nrc_propagate: ncclAllReduce of the training records failed");
+                return GFX_ERR_CUDA;
+            }
+        }
+        break;
     case 2: k_nrcShuffle<<<kNumTrainingDataPerFrame / 256, 256, 0, stream>>>(p, n); break;
     default: ctx->setError("unknown NRC pass"); return GFX_ERR_INVALID_ARGUMENT;
     }

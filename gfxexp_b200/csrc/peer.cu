@@ -63,6 +63,17 @@ __global__ void k_peerWait(uint32_t* localFlags, uint32_t flagIndex, uint32_t va
     }
 }
 
+// NCCL entry points resolved at run time: from the process image if NCCL is globally visible, else from libnccl.so.2 (which
+// the loader maps to the copy the process has already loaded, e.g. torch's)
+void* ncclSymbol(const char* name) {
+    void* sym = dlsym(RTLD_DEFAULT, name);
+    if (!sym) {
+        static void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (lib)
+            sym = dlsym(lib, name);
+    }
+    return sym;
+}
 } // namespace gfx
 
 using namespace gfx;
@@ -191,17 +202,6 @@ int gfx_peer_status(gfx_ctx* ctx, void* stream, uint32_t* timedOut) {
     return GFX_OK;
 }
 
-// NCCL entry points resolved at run time: from the process image if NCCL is globally visible, else from libnccl.so.2 (which
-// the loader maps to the copy the process has already loaded, e.g. torch's)
-static void* ncclSymbol(const char* name) {
-    void* sym = dlsym(RTLD_DEFAULT, name);
-    if (!sym) {
-        static void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-        if (lib)
-            sym = dlsym(lib, name);
-    }
-    return sym;
-}
 typedef int (*NcclAllGatherFn)(const void*, void*, size_t, int, void*, cudaStream_t);
 typedef int (*NcclCommUserRankFn)(void*, int*);
 

@@ -43,6 +43,35 @@ class _DevicePtr:
         self.__cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": "<f4", "data": (ptr, False), "version": 2}
 
 
+class NcclComm:
+    """A raw ncclComm_t over the ranks of the default torch.distributed group, created with ctypes on the NCCL the process has
+    loaded - what a C++ host has from nccl.h.  The library takes it for the collectives it issues itself
+    (gfx_framebuffer_allgather, the sharded NRC frame of gfx_nrc_shard).  The unique id travels through torch.distributed."""
+
+    def __init__(self, rank: int, world: int):
+        import ctypes as C
+
+        class UniqueId(C.Structure):  # ncclUniqueId, passed by value
+            _fields_ = [("internal", C.c_byte * 128)]
+        self.lib = C.CDLL("libnccl.so.2")  # the soname resolves to the copy torch has loaded
+        uid = UniqueId()
+        if rank == 0 and self.lib.ncclGetUniqueId(C.byref(uid)) != 0:
+            raise RuntimeError("ncclGetUniqueId failed")
+        ids = [bytes(uid)]
+        dist.broadcast_object_list(ids, src=0)
+        C.memmove(C.byref(uid), ids[0], 128)
+        self.handle = C.c_void_p()
+        self.lib.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, UniqueId, C.c_int]
+        if self.lib.ncclCommInitRank(C.byref(self.handle), world, uid, rank) != 0:
+            raise RuntimeError("ncclCommInitRank failed")
+        self.lib.ncclCommDestroy.argtypes = [C.c_void_p]
+
+    def close(self):
+        if self.handle:
+            self.lib.ncclCommDestroy(self.handle)
+            self.handle = None
+
+
 class GpuBackend:
     """Launches go through gfx_launch_batch: the driver's calls are recorded into one array of GfxBatchOp records per frame and
     handed to the library in ONE call (flush) - at 8 GPUs a strip frame is ~35 launches in ~1.3 ms of GPU time, and a Python /
@@ -223,8 +252,42 @@ class StripDriver:
         import ctypes as C
         return bytes(C.string_at(C.addressof(p.camera), C.sizeof(p.camera))) != bytes(C.string_at(C.addressof(p.prevCamera), C.sizeof(p.prevCamera)))
 
+    # -- ReSTIR DI + NRC in one frame (BASELINE config 5) ---------------------------------------------------
+    def enable_nrc(self, net: "engine.NeuralRadianceCache"):
+        """Shard the NRC half of the frame over the ranks (gfx_nrc_shard): every rank path-traces and infers its rows, the
+        training vertices are numbered over the whole frame, the records are merged, training runs replicated."""
+        if (self.y0 * self.W) % 128 or (self.W * self.H) % 128:
+            raise ValueError("NRC strips must start on a multiple of 128 pixels (the inference tile)")
+        self.net = net
+        self.comm = None
+        ctx = self.backend.ctx
+        if self.world > 1:
+            self.comm = NcclComm(self.rank, self.world)
+            ctx._check(ctx.lib.gfx_nrc_shard(ctx.h, self.comm.handle, self.rank, self.world), "gfx_nrc_shard")
+
+    def render_restir_nrc_frame(self, frame_index: int, offsets, num_spatial_passes: int = 1, unbiased: bool = False,
+                                train: bool = True):
+        """ReSTIR DI passes (as render_frame) then the NRC frame of engine.Context.nrc_frame on the same G-buffer, both on this
+        rank's rows; `offsets` are the two perFrameRng() draws (identical on all ranks).  One all-gather of the beauty strips
+        at the end."""
+        ctx, p = self.backend.ctx, self.params
+        self.render_frame(frame_index, num_spatial_passes, unbiased, composite=False)
+        self._tile(self.y0, self.y1)
+        ctx.nrc_preprocess(p, offsets[0], offsets[1], frame_index == 0)
+        ctx.pathtrace(p, abi.PT_NRC)
+        if self.world > 1:
+            ctx._check(ctx.lib.gfx_nrc_frame_infer_rows(ctx.h, self.net.h, None, self.y0, self.y1), "gfx_nrc_frame_infer_rows")
+        else:
+            ctx.nrc_frame_infer(self.net)
+        ctx.nrc_accumulate(p)
+        if train:
+            ctx.nrc_propagate(p)
+            ctx.nrc_shuffle(p)
+            ctx.nrc_frame_train(self.net)
+        self._finish_frame()
+
     # -- one frame ------------------------------------------------------------------------------------
-    def render_frame(self, frame_index: int, num_spatial_passes: int = 1, unbiased: bool = False):
+    def render_frame(self, frame_index: int, num_spatial_passes: int = 1, unbiased: bool = False, composite: bool = True):
         p = self.params
         b = self.backend
         if self.world > 1 and frame_index > 0 and p.enableTemporalReuse and self.max_motion_rows == 0 and self._camera_moved(p):
@@ -238,7 +301,8 @@ class StripDriver:
             st.peerSeq = b.peer_seq
             b.ctx._check(b.ctx.lib.gfx_restir_strip_frame(b.ctx.h, None, p, st), "gfx_restir_strip_frame")
             b.peer_seq = st.peerSeq
-            self._finish_frame()
+            if composite:
+                self._finish_frame()
             return
         b.light_dist(frame_index)
         lo_h, hi_h = max(0, self.y0 - self.halo), min(self.H, self.y1 + self.halo)
@@ -271,11 +335,17 @@ class StripDriver:
         self._tile(0, 0)
         if hasattr(b, "flush"):
             b.flush()
-        self._finish_frame()
+        if composite:
+            self._finish_frame()
 
     def _finish_frame(self):
         p = self.params
-        if self.world > 1:
+        if self.world > 1 and getattr(self, "comm", None) is not None:
+            # the library's own collective on the host's communicator (the same one the sharded NRC frame uses)
+            ctx = self.backend.ctx
+            ctx._check(ctx.lib.gfx_framebuffer_allgather(ctx.h, self.comm.handle, None, self.rows, self.composited.data_ptr()),
+                       "gfx_framebuffer_allgather")
+        elif self.world > 1:
             strip = self._row_slices(abi.BUF_BEAUTY_ACCUM, 0, self.y0, self.y1)[0]
             dist.all_gather_into_tensor(self.composited, strip.contiguous())
         else:

@@ -525,6 +525,22 @@ int gfx_nrc_shuffle(gfx_ctx* ctx, void* stream, const GfxFrameParams* params);
 /* replaces the four neuralRadianceCache.train steps on quarters of the shuffled records (:2350-2365) */
 int gfx_nrc_frame_train(gfx_ctx* ctx, gfx_nrc* nrc, void* stream, float* lossOnHost);
 
+/* ---- NRC frame sharded by strips of rows over the ranks of one node (BASELINE config 5: ReSTIR DI + NRC, 3840x2160, 8 GPUs).
+ * No counterpart in the reference (one GPU).  After gfx_nrc_shard every rank runs the sequence above on ITS rows
+ * (params->tileOriginY / tileRows; gfx_nrc_frame_infer_rows instead of gfx_nrc_frame_infer) and all ranks must make the same
+ * calls in the same order on `stream`:
+ *   - gfx_pathtrace_launch(GFX_PT_NRC) numbers the training vertices over the whole frame: per path-tracing round one
+ *     ncclAllGather of one word per rank (the vertex counts), so records, tile-size controller and buffer-overflow
+ *     behaviour are those of the unsharded frame, bit for bit;
+ *   - gfx_nrc_propagate ends with an ncclAllReduce (unsigned sum; every record is non-zero on one rank only) that leaves all
+ *     records on all ranks; gfx_nrc_shuffle / gfx_nrc_frame_train then run replicated and keep the weights identical
+ *     (the gradient accumulation is integer, hence order-independent).
+ * ncclComm is the host's ncclComm_t over exactly `world` ranks; NULL or world <= 1 switches sharding off. */
+int gfx_nrc_shard(gfx_ctx* ctx, void* ncclComm, int rank, int world);
+/* inference of the rows [rowLo, rowHi) of the frame's terminal queries + the training-suffix queries of all tiles;
+ * rowLo * width and width * height must be multiples of 128 */
+int gfx_nrc_frame_infer_rows(gfx_ctx* ctx, gfx_nrc* nrc, void* stream, uint32_t rowLo, uint32_t rowHi);
+
 #ifdef __cplusplus
 }
 #endif

@@ -87,6 +87,106 @@ def _worker_allgather(rank, world, port, result_path):
     ctx.close()
 
 
+NRC_FRAMES = 4
+
+
+def _nrc_offsets(f):
+    rng = np.random.default_rng(1000 + f)
+    return [int(rng.integers(0, 2 ** 32)) for _ in range(2)]
+
+
+def _worker_restir_nrc(rank, world, port, result_path):
+    """config 5 in small: ReSTIR DI + NRC in one frame, sharded by strips; the NRC half numbers its training vertices over
+    the whole frame (one word per rank and round all-gathered), merges the records and trains replicated"""
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from gfxexp_b200 import abi, engine, multigpu, scenes
+    scene = scenes.small_city_scene()
+    ctx = engine.Context(rank)
+    ctx.upload_scene(scene)
+    ctx.build_bvh()
+    ctx.create_frame(W, H)
+    p = abi.default_frame_params(scene, W, H)
+    p.maxPathLength = 5
+    net = engine.NeuralRadianceCache(ctx, 2, 1e-2)
+    driver = multigpu.StripDriver(ctx, p, W, H, rank, world)
+    driver.enable_nrc(net)
+    outs, states = [], []
+    for f in range(NRC_FRAMES):
+        p.numAccumFrames = f
+        driver.render_restir_nrc_frame(f, _nrc_offsets(f))
+        torch.cuda.synchronize()
+        outs.append(driver.composited.cpu().numpy().copy())
+        states.append(ctx.download_linear(abi.BUF_NRC_STATE)[:, 0].copy())
+    assert not ctx.peer_timed_out()
+    np.save(result_path + f".weights.{rank}.npy", net.read(abi.NRC_READ_MASTER))
+    np.save(result_path + f".state.{rank}.npy", np.stack(states))
+    if rank == 0:
+        np.save(result_path + ".frames.npy", np.stack(outs))
+    dist.barrier()
+    net.close()
+    driver.comm.close()
+    dist.destroy_process_group()
+    ctx.close()
+
+
+def test_restir_nrc_strips_equal_single_gpu(tmp_path, gfx_ctx):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    from gfxexp_b200 import abi, engine, scenes
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    result = str(tmp_path / "restir_nrc")
+    mp.spawn(_worker_restir_nrc, args=(2, port, result), nprocs=2, join=True)
+    got = np.load(result + ".frames.npy")
+
+    scene = scenes.small_city_scene()
+    ctx = gfx_ctx
+    ctx.upload_scene(scene)
+    ctx.build_bvh()
+    ctx.create_frame(W, H)
+    p = abi.default_frame_params(scene, W, H)
+    p.maxPathLength = 5
+    net = engine.NeuralRadianceCache(ctx, 2, 1e-2)
+    states = []
+    for f in range(NRC_FRAMES):
+        p.numAccumFrames = f
+        ctx.build_light_distributions(f % 2)
+        for kind, pass_id in engine.restir_frame_passes(p, f, 1):
+            ctx.gbuffer(p) if kind == "gbuffer" else ctx.restir(p, pass_id)
+        off = _nrc_offsets(f)
+        ctx.nrc_preprocess(p, off[0], off[1], f == 0)
+        ctx.pathtrace(p, abi.PT_NRC)
+        ctx.nrc_frame_infer(net)
+        ctx.nrc_accumulate(p)
+        ctx.nrc_propagate(p)
+        ctx.nrc_shuffle(p)
+        ctx.nrc_frame_train(net)
+        ctx.synchronize()
+        want = ctx.download(abi.BUF_BEAUTY_ACCUM).reshape(-1)
+        states.append(ctx.download_linear(abi.BUF_NRC_STATE)[:, 0].copy())
+        assert np.array_equal(got[f].view(np.uint32), want.view(np.uint32)), f"frame {f}: sharded DI + NRC frame differs"
+    want_weights = net.read(abi.NRC_READ_MASTER)
+    net.close()
+    states = np.stack(states)
+    assert states[-1][abi.NRC_STATE_NUM_TRAINING_DATA + (NRC_FRAMES - 1) % 2] > 0, "no training data: the test is vacuous"
+    for rank in range(2):
+        w = np.load(result + f".weights.{rank}.npy")
+        assert np.array_equal(w.view(np.uint32), want_weights.view(np.uint32)), f"rank {rank}: trained weights differ"
+        st = np.load(result + f".state.{rank}.npy")
+        # training-data counters and tile sizes of both buffers: words 0..5
+        assert np.array_equal(st[:, :6], states[:, :6]), f"rank {rank}: training-vertex counters / tile sizes differ"
+
+
 def test_framebuffer_allgather_through_the_c_abi(tmp_path):
     import torch
     import torch.multiprocessing as mp
