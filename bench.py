@@ -369,6 +369,90 @@ def measure_nrc_and_svgf(ctx, scene, args):
     return out
 
 
+def measure_config5(scene, args, rank, world, local_rank):
+    """BASELINE.json config 5: ReSTIR DI + NRC combined, 3840x2160, screen strips across the ranks, one all-gather of the
+    composited framebuffer.  All ranks call this.  The DI half exchanges seam rows as at 1080p; the NRC half traces and infers
+    its rows, numbers the training vertices over the whole frame (one word per rank and path-tracing round all-gathered),
+    merges the records with one integer all-reduce and trains replicated (gfx_nrc_shard, include/gfxb200.h).  A context of
+    its own: the 1080p frame of the headline stays untouched."""
+    import torch
+    import torch.distributed as dist
+    from gfxexp_b200 import abi, engine, multigpu
+    W5, H5 = 3840, 2160
+    if H5 % world:
+        return None
+    ctx = engine.Context(local_rank)
+    ctx.upload_scene(scene)
+    ctx.build_bvh()
+    ctx.create_frame(W5, H5)
+    p = abi.default_frame_params(scene, W5, H5)
+    net = engine.NeuralRadianceCache(ctx, 2, 1e-2)
+    driver = multigpu.StripDriver(ctx, p, W5, H5, rank, world)
+    driver.enable_nrc(net)
+    rng = np.random.default_rng(5)
+    frame = 0
+
+    def one_frame():
+        nonlocal frame
+        p.numAccumFrames = frame
+        driver.render_restir_nrc_frame(frame, [int(rng.integers(0, 2 ** 32)) for _ in range(2)])
+        frame += 1
+
+    for _ in range(12):  # the tile-size controller and the cache settle
+        one_frame()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    driver.check_peers()
+    ctx.read_stats(reset=True)
+    n_frames = max(args.steps, 8)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n_frames):
+        one_frame()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    driver.check_peers()
+    ms = e0.elapsed_time(e1)
+    rays = float(ctx.read_stats(reset=True)[0])
+    lo_h, hi_h = max(0, driver.y0 - driver.halo), min(H5, driver.y1 + driver.halo)
+    rays -= ((driver.y0 - lo_h) + (hi_h - driver.y1)) * W5 * n_frames  # recomputed G-buffer halo rows are not throughput
+    st = ctx.download_linear(abi.BUF_NRC_STATE)[:, 0]
+    # where the strip's frame goes: per-kernel CUDA events inside the library (this rank's launches; collectives and peer
+    # waits are the remainder against `ms`)
+    ctx.timing_enable(True)
+    ctx.timing_read()
+    reps = 6
+    for _ in range(reps):
+        one_frame()
+    torch.cuda.synchronize()
+    timing = ctx.timing_read()
+    ctx.timing_enable(False)
+    per_frame = {k: round(v[0] / reps, 4) for k, v in sorted(timing.items(), key=lambda kv: -kv[1][0])}
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        r = torch.tensor([rays], device="cuda", dtype=torch.float64)
+        dist.all_reduce(r, op=dist.ReduceOp.SUM)
+        rays = float(r.item())
+    out = {"what": "ReSTIR DI (32 candidates, temporal + 1x4 spatial) + NRC (path tracing with cache termination, inference, "
+                   "4 training steps) in one 3840x2160 frame, strips of %d rows on %d GPU(s), framebuffer all-gathered" % (H5 // world, world),
+           "n_gpus": world, "ms": ms / n_frames, "fps": 1e3 * n_frames / ms, "Mrays_per_s": rays / (ms * 1e-3) / 1e6,
+           "rays_per_pixel": rays / n_frames / (W5 * H5), "frames_timed": n_frames,
+           "training_records_last_frame": int(st[abi.NRC_STATE_NUM_TRAINING_DATA + (frame - 1) % 2]),
+           "tile_size": [int(st[abi.NRC_STATE_TILE_SIZE + 2 * ((frame - 1) % 2)]), int(st[abi.NRC_STATE_TILE_SIZE + 2 * ((frame - 1) % 2) + 1])],
+           "nrc": "inference sharded by strip, training replicated on all ranks (weights bit-identical, tests/test_gpu_multigpu.py)",
+           "rank0_kernels_ms": per_frame, "rank0_kernels_sum_ms": round(sum(per_frame.values()), 4)}
+    net.close()
+    if driver.comm is not None:
+        driver.comm.close()
+    ctx.close()
+    return out
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -530,6 +614,8 @@ def run_gpu(args):
     assert float(pinned[(frame - 1) % 2][..., 3].min()) == 1.0  # the last frame really arrived (alpha plane)
     d2h_bytes = (rows_hi - rows_lo) * WIDTH * 16
 
+    config5 = None if args.headline_only else measure_config5(scene, args, rank, world, local_rank)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -653,6 +739,8 @@ def run_gpu(args):
     if roofline is not None:
         line["roofline"] = roofline
     line.update(extras)
+    if config5 is not None:
+        line["config5"] = config5
     if cpu_baseline is not None:
         line["cpu_baseline"] = cpu_baseline
     print(json.dumps(line))

@@ -768,7 +768,8 @@ int launchPathTraceNrc(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* 
         ctx->launches++;
     }
     const uint32_t firstPixel = p.y0 * F.W, endPixel = p.y1 * F.W;
-    k_nrcFinish<<<(endPixel - firstPixel + 255) / 256, 256, 0, stream>>>(f, ps, n, firstPixel, endPixel);
+    { GFX_TIMED(ctx, stream, "nrc_finish");
+    k_nrcFinish<<<(endPixel - firstPixel + 255) / 256, 256, 0, stream>>>(f, ps, n, firstPixel, endPixel); }
     ctx->launches++;
     GFX_CUDA(ctx, cudaGetLastError());
     if (commitError) {
@@ -925,6 +926,7 @@ int launchNrcPreprocess(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams*
     if (rc != GFX_OK)
         return rc;
     const DevNrc n = makeDevNrc(ctx);
+    GFX_TIMED(ctx, stream, "nrc_preprocess");
     if (n.shardWorld > 1) { // the ranks' records are merged by an integer sum (launchNrcPass, propagate): start from zero
         GFX_CUDA(ctx, cudaMemsetAsync(n.trainQuery[0], 0, (size_t)kTrainBufferSize * 56, stream));
         GFX_CUDA(ctx, cudaMemsetAsync(n.trainTarget[0], 0, (size_t)kTrainBufferSize * 12, stream));
@@ -944,6 +946,8 @@ int launchNrcPass(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* param
     const DevNrc n = makeDevNrc(ctx);
     const DevFrameParams p = makeDevParams(ctx, params);
     const uint32_t numPixels = ctx->frame.W * ctx->frame.H;
+    static const char* const kPassLabel[3] = { "nrc_accumulate", "nrc_propagate_merge", "nrc_shuffle" };
+    GFX_TIMED(ctx, stream, kPassLabel[pass < 0 || pass > 2 ? 0 : pass]);
     switch (pass) {
     case 0: k_nrcAccumulate<<<((p.y1 - p.y0) * ctx->frame.W + 255) / 256, 256, 0, stream>>>(ctx->devFrame(), p, n); break;
     case 1:
