@@ -62,7 +62,19 @@ class NcclComm:
         C.memmove(C.byref(uid), ids[0], 128)
         self.handle = C.c_void_p()
         self.lib.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, UniqueId, C.c_int]
-        if self.lib.ncclCommInitRank(C.byref(self.handle), world, uid, rank) != 0:
+        # NCCL announces its version on stdout at the first ncclCommInitRank of a process (NCCL_DEBUG=VERSION/WARN); hosts
+        # that own stdout (bench.py prints ONE JSON line) get it on stderr instead
+        import os
+        import sys
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            rc = self.lib.ncclCommInitRank(C.byref(self.handle), world, uid, rank)
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
+        if rc != 0:
             raise RuntimeError("ncclCommInitRank failed")
         self.lib.ncclCommDestroy.argtypes = [C.c_void_p]
 
