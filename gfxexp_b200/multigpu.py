@@ -265,13 +265,18 @@ class StripDriver:
         return bytes(C.string_at(C.addressof(p.camera), C.sizeof(p.camera))) != bytes(C.string_at(C.addressof(p.prevCamera), C.sizeof(p.prevCamera)))
 
     # -- ReSTIR DI + NRC in one frame (BASELINE config 5) ---------------------------------------------------
-    def enable_nrc(self, net: "engine.NeuralRadianceCache"):
+    def enable_nrc(self, net: "engine.NeuralRadianceCache", overlap_training: bool = True):
         """Shard the NRC half of the frame over the ranks (gfx_nrc_shard): every rank path-traces and infers its rows, the
-        training vertices are numbered over the whole frame, the records are merged, training runs replicated."""
+        training vertices are numbered over the whole frame, the records are merged, training runs replicated.
+        overlap_training: the four training steps of frame f (a latency chain of small launches, replicated on every rank) run
+        on a second stream under the G-buffer / ReSTIR DI passes of frame f + 1; the next inference waits for them, so the
+        results are the same bits as in stream order."""
         if (self.y0 * self.W) % 128 or (self.W * self.H) % 128:
             raise ValueError("NRC strips must start on a multiple of 128 pixels (the inference tile)")
         self.net = net
         self.comm = None
+        self.train_stream = torch.cuda.Stream(device=f"cuda:{self.backend.ctx.device}") if overlap_training else None
+        self.trained = None
         ctx = self.backend.ctx
         if self.world > 1:
             self.comm = NcclComm(self.rank, self.world)
@@ -287,6 +292,7 @@ class StripDriver:
         self._tile(self.y0, self.y1)
         ctx.nrc_preprocess(p, offsets[0], offsets[1], frame_index == 0)
         ctx.pathtrace(p, abi.PT_NRC)
+        self.wait_training()  # the weights of the previous frame's training steps; its shuffled records may be overwritten
         if self.world > 1:
             ctx._check(ctx.lib.gfx_nrc_frame_infer_rows(ctx.h, self.net.h, None, self.y0, self.y1), "gfx_nrc_frame_infer_rows")
         else:
@@ -295,8 +301,23 @@ class StripDriver:
         if train:
             ctx.nrc_propagate(p)
             ctx.nrc_shuffle(p)
-            ctx.nrc_frame_train(self.net)
+            if self.train_stream is not None:
+                shuffled = torch.cuda.Event()
+                shuffled.record()
+                self.train_stream.wait_event(shuffled)
+                ctx.nrc_frame_train(self.net, stream=self.train_stream.cuda_stream)
+                self.trained = torch.cuda.Event()
+                self.trained.record(self.train_stream)
+            else:
+                ctx.nrc_frame_train(self.net)
         self._finish_frame()
+
+    def wait_training(self):
+        """make the current stream wait for the training steps still running on the side stream (call before timing stops
+        or before reading the weights)"""
+        if getattr(self, "trained", None) is not None:
+            torch.cuda.current_stream().wait_event(self.trained)
+            self.trained = None
 
     # -- one frame ------------------------------------------------------------------------------------
     def render_frame(self, frame_index: int, num_spatial_passes: int = 1, unbiased: bool = False, composite: bool = True):
@@ -360,6 +381,8 @@ class StripDriver:
         elif self.world > 1:
             strip = self._row_slices(abi.BUF_BEAUTY_ACCUM, 0, self.y0, self.y1)[0]
             dist.all_gather_into_tensor(self.composited, strip.contiguous())
+        elif isinstance(self.backend, GpuBackend):
+            self.composited = self.backend.tensor(abi.BUF_BEAUTY_ACCUM, 0)  # one rank: the beauty buffer is the frame
         else:
             self.composited.copy_(self.backend.tensor(abi.BUF_BEAUTY_ACCUM, 0))
         p.tileOriginY, p.tileRows = 0, 0
