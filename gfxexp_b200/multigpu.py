@@ -71,6 +71,7 @@ class NcclComm:
         os.dup2(2, 1)
         try:
             rc = self.lib.ncclCommInitRank(C.byref(self.handle), world, uid, rank)
+            C.CDLL(None).fflush(None)  # NCCL writes through C stdio: empty its buffer while fd 1 still points at stderr
         finally:
             os.dup2(saved, 1)
             os.close(saved)
