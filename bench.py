@@ -278,7 +278,7 @@ def run_reference(args):
         "gpu_launches": 0,
         "nrc_reference": tcnn_reference_timing(),
     }
-    print(json.dumps(line))
+    emit_line(line)
 
 
 def measure_nrc_and_svgf(ctx, scene, args):
@@ -746,12 +746,34 @@ def run_gpu(args):
         line["config5"] = config5
     if cpu_baseline is not None:
         line["cpu_baseline"] = cpu_baseline
-    print(json.dumps(line))
+    emit_line(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """stdout carries ONE JSON line.  Libraries print there too (NCCL announces its version through C stdio when a communicator
+    is created), so fd 1 is pointed at stderr for the whole run and the result line goes to the original stdout."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit_line(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

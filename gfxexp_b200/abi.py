@@ -39,7 +39,8 @@ class GfxSceneDesc(C.Structure):
     _fields_ = [("meshes", C.POINTER(GfxMeshDesc)), ("materials", C.POINTER(GfxMaterialDesc)),
                 ("instances", C.POINTER(GfxInstanceDesc)), ("instanceMeshSlots", C.POINTER(c_u32)),
                 ("numMeshes", c_u32), ("numMaterials", c_u32), ("numInstances", c_u32),
-                ("numInstanceMeshSlots", c_u32)]
+                ("numInstanceMeshSlots", c_u32),
+                ("envTexels", C.POINTER(c_f)), ("envWidth", c_u32), ("envHeight", c_u32)]
 
 
 class GfxBvhInfo(C.Structure):
@@ -75,7 +76,8 @@ class GfxFrameParams(C.Structure):
                 ("regirGridDim", c_u32 * 3), ("regirLog2NumCandidatesPerLightSlot", c_u32),
                 ("regirLog2NumCandidatesPerCell", c_u32), ("regirEnableCellRandomization", c_u32),
                 ("reuseVisibilityForTemporal", c_u32), ("reuseVisibilityForSpatiotemporal", c_u32),
-                ("radiusThresholdForSpatialVisReuse", c_f)]
+                ("radiusThresholdForSpatialVisReuse", c_f),
+                ("enableEnvLight", c_u32), ("envLightPowerCoeff", c_f), ("envLightRotation", c_f)]
 
 
 NODE_DTYPE = np.dtype([("quantBoxOrigin", np.float32, 3), ("quantBoxExpScale", np.uint8, 3),
@@ -176,6 +178,12 @@ class SceneArrays:
         self.desc.numMaterials = mats.shape[0]
         self.desc.numInstances = len(scene.instances)
         self.desc.numInstanceMeshSlots = self.slots.shape[0]
+        env = getattr(scene, "env_map", None)  # float32 [H, W, 4] equirectangular map, or None
+        if env is not None:
+            self.env = np.ascontiguousarray(env, dtype=np.float32)
+            assert self.env.ndim == 3 and self.env.shape[2] == 4
+            self.desc.envTexels = self.env.ctypes.data_as(C.POINTER(c_f))
+            self.desc.envHeight, self.desc.envWidth = self.env.shape[0], self.env.shape[1]
 
 
 def make_instance_descs(instances):
@@ -232,6 +240,9 @@ def default_frame_params(scene, width: int, height: int) -> GfxFrameParams:
     p.sceneAabbMin = (c_f * 3)(*lo)
     p.sceneAabbMax = (c_f * 3)(*hi)
     p.radianceScale = 1.0
+    p.enableEnvLight = 1  # used when the scene has an environment map (restir_di_main.cpp: enableEnvLight = true,
+    p.envLightPowerCoeff = 1.0  # log10EnvLightPowerCoeff = 0, envLightRotation = 0 by default)
+    p.envLightRotation = 0.0
     p.regirGridDim = (c_u32 * 3)(32, 8, 32)
     p.regirLog2NumCandidatesPerLightSlot = 3
     p.regirLog2NumCandidatesPerCell = 2
@@ -340,6 +351,7 @@ _DECLS = {
     "gfx_restir_strip_frame": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxFrameParams), C.POINTER(GfxStripFrame)]),
     "gfx_launch_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GfxBatchOp), c_u32]),
     "gfx_light_pick_debug": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, c_u32, C.c_void_p, C.c_void_p]),
+    "gfx_env_light_debug": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, c_u32, C.c_void_p]),
     "gfx_light_dist_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(c_f)]),
     "gfx_frame_create": (C.c_int, [C.c_void_p, c_u32, c_u32]),
     "gfx_rng_seed": (C.c_int, [C.c_void_p, C.c_uint64]),

@@ -15,6 +15,7 @@ void SceneState::release() {
     cudaFree(primWeights); cudaFree(primCdf); cudaFree(geomWeights); cudaFree(geomCdf);
     cudaFree(instWeights); cudaFree(instCdf); cudaFree(instIntegral);
     cudaFree(primProb); cudaFree(geomProb); cudaFree(instProb); cudaFree(lightTris); cudaFree(lightTriBase); cudaFree(emissiveGeoms); cudaFree(instGuide); cudaFree(primGuide);
+    cudaFree(envTexels); cudaFree(envPdf); cudaFree(envCdf); cudaFree(envTopPdf); cudaFree(envTopCdf);
     cudaFree(pickGuide); cudaFree(normalMats); cudaFree(pickPieces); cudaFree(pickKeyAt); cudaFree(pickBoundaries); cudaFree(pickCounters); cudaFree(pickSortTemp);
     if (pickFlagsHost) cudaFreeHost(pickFlagsHost);
     if (pickFlagsEvent) cudaEventDestroy(pickFlagsEvent);
@@ -115,6 +116,7 @@ DevFrameParams makeDevParams(const gfx_ctx* ctx, const GfxFrameParams* p) {
     d.reuseVisibilityForTemporal = p->reuseVisibilityForTemporal;
     d.reuseVisibilityForSpatiotemporal = p->reuseVisibilityForSpatiotemporal;
     d.radiusThresholdForSpatialVisReuse = p->radiusThresholdForSpatialVisReuse;
+    d.envLightRotation = p->envLightRotation;
     return d;
 }
 
@@ -155,6 +157,23 @@ DevScene gfx_ctx::devScene() const {
     d.bvh.leafTris = bvh.leafTris;
     d.bvh.numNodes = bvh.numNodes;
     d.bvh.overflowFlag = bvh.overflowFlag;
+    d.env.texels = scene.envTexels;
+    d.env.pdf = scene.envPdf;
+    d.env.cdf = scene.envCdf;
+    d.env.topPdf = scene.envTopPdf;
+    d.env.topCdf = scene.envTopCdf;
+    d.env.W = scene.envW;
+    d.env.H = scene.envH;
+    d.env.enabled = 0;
+    d.env.powerCoeff = 0.0f;
+    d.env.rotation = 0.0f;
+    return d;
+}
+DevScene gfx_ctx::devScene(const GfxFrameParams* p) const {
+    DevScene d = devScene();
+    d.env.enabled = scene.envW != 0 && p->enableEnvLight ? 1u : 0u; // plp.s->envLightTexture && plp.f->enableEnvLight
+    d.env.powerCoeff = p->envLightPowerCoeff;
+    d.env.rotation = p->envLightRotation;
     return d;
 }
 DevFrame gfx_ctx::devFrame() const {
@@ -397,6 +416,9 @@ int gfx_scene_upload(gfx_ctx* ctx, const GfxSceneDesc* sd) {
     S.numVertices = (uint32_t)numVerts;
     S.hostMeshes = meshes;
     S.hostInstances = insts;
+    const int envRc = uploadEnvLight(ctx, sd->envTexels, sd->envWidth, sd->envHeight);
+    if (envRc != GFX_OK)
+        return envRc;
     S.uploaded = true;
     return GFX_OK;
 }
@@ -650,6 +672,15 @@ int gfx_light_pick_debug(gfx_ctx* ctx, void* stream, const float* ul, uint32_t n
     if (!ul || !keysFlat || !keysChain)
         return GFX_ERR_INVALID_ARGUMENT;
     return debugLightPick(ctx, (cudaStream_t)stream, ul, n, keysFlat, keysChain);
+}
+
+int gfx_env_light_debug(gfx_ctx* ctx, void* stream, int op, const float* in, uint32_t n, float* out) {
+    CHECK_CTX(ctx);
+    if (!ctx->scene.uploaded)
+        return GFX_ERR_NOT_READY;
+    if ((n && (!in || !out)) || op < 0 || op > 2)
+        return GFX_ERR_INVALID_ARGUMENT;
+    return debugEnvLight(ctx, (cudaStream_t)stream, op, in, n, out);
 }
 
 int gfx_light_dist_export(gfx_ctx* ctx, float* instWeights, float* instCdf, float* integral) {

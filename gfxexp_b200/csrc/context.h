@@ -41,6 +41,13 @@ struct SceneState {
     // flattened light pick (scene.cuh, lights.cu): tables + the scratch its stream-ordered rebuild needs
     float4* pickGuide = nullptr;           // 2 x kPickGuideSize
     float4* normalMats = nullptr;          // kNormalMatStride x numInstances
+    // environment light (lights.cu uploadEnvLight): texels + the importance map's distributions
+    float4* envTexels = nullptr;
+    float* envPdf = nullptr;
+    float* envCdf = nullptr;
+    float* envTopPdf = nullptr;
+    float* envTopCdf = nullptr;
+    uint32_t envW = 0, envH = 0;
     uint2* pickPieces = nullptr;           // pickCapacity + 2
     uint32_t* pickKeyAt = nullptr;         // kPickGuideSize + 1
     uint4* pickQueue[2] = { nullptr, nullptr };
@@ -213,6 +220,7 @@ struct gfx_ctx {
 
     void setError(const std::string &msg) { lastError = msg; }
     gfx::DevScene devScene() const;
+    gfx::DevScene devScene(const GfxFrameParams* p) const; // + the frame's environment-light switches
     gfx::DevFrame devFrame() const;
 };
 
@@ -255,6 +263,8 @@ int traceRays(gfx_ctx* ctx, cudaStream_t stream, const GfxRay* dRays, uint32_t n
 int resetVisibilityQueue(gfx_ctx* ctx, cudaStream_t stream);
 int traceVisibilityQueue(gfx_ctx* ctx, cudaStream_t stream);
 int buildLightDistributions(gfx_ctx* ctx, cudaStream_t stream, uint32_t bufferIndex);
+int uploadEnvLight(gfx_ctx* ctx, const float* rgba, uint32_t width, uint32_t height);
+int debugEnvLight(gfx_ctx* ctx, cudaStream_t stream, int op, const float* dIn, uint32_t n, float* dOut);
 int debugLightPick(gfx_ctx* ctx, cudaStream_t stream, const float* dUl, uint32_t n, uint32_t* dFlat, uint32_t* dChain);
 size_t lightPickSortTempBytes(uint32_t capacity);
 int launchGBuffer(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* p);

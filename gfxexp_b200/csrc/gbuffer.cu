@@ -120,7 +120,7 @@ GFX_D uint32_t gbufferPixel(const DevScene &scene, const DevFrame &frame, const 
         const f3 pp = -vOut;
         float posPhi, posTheta;
         toPolarYUp(pp, &posPhi, &posTheta);
-        const float phi = posPhi + 0.0f;
+        const float phi = posPhi + p.envLightRotation;
         float u = phi / (2 * kPi);
         u -= floorf(u);
         const float v = posTheta / kPi;

@@ -230,6 +230,147 @@ GFX_D void sampleLight(const DevScene &s, float ul, float u0, float u1, LightSam
     lightSample->emittance = f3(h3.lo.z, h3.lo.w, h3.hi.x);
 }
 
+// ---- environment light ---------------------------------------------------------------------------------------------
+// RegularConstantContinuousDistribution1D::sample / evaluatePDF (common_shared.h:316-348, CDF variant)
+GFX_D float regularSample(const float* __restrict__ PDF, const float* __restrict__ CDF, uint32_t numValues, float u, float* probDensity) {
+    int idx = 0;
+    for (int d = (int)(nextPowerOf2(numValues) >> 1); d >= 1; d >>= 1) {
+        if (idx + d >= (int)numValues)
+            continue;
+        if (__ldg(CDF + idx + d) <= u)
+            idx += d;
+    }
+    const float lo = __ldg(CDF + idx);
+    const float t = (u - lo) / (__ldg(CDF + idx + 1) - lo);
+    *probDensity = __ldg(PDF + idx);
+    return (idx + t) / numValues;
+}
+GFX_D uint32_t mapPrimarySampleToDiscrete(float u01, uint32_t numValues) { // common_shared.h:142-152
+    return min(dm_f2uint(u01 * numValues), numValues - 1);
+}
+// RegularConstantContinuousDistribution2D::sample / evaluatePDF (:371-383)
+GFX_D void envSample(const DevEnvLight &e, float u0, float u1, float* d0, float* d1, float* probDensity) {
+    float topPDF;
+    *d1 = regularSample(e.topPdf, e.topCdf, e.H, u1, &topPDF);
+    const uint32_t row = mapPrimarySampleToDiscrete(*d1, e.H);
+    *d0 = regularSample(e.pdf + (size_t)row * e.W, e.cdf + (size_t)row * (e.W + 1), e.W, u0, probDensity);
+    *probDensity *= topPDF;
+}
+GFX_D float envEvaluatePDF(const DevEnvLight &e, float d0, float d1) {
+    const uint32_t row = mapPrimarySampleToDiscrete(d1, e.H);
+    const uint32_t col = min(e.W - 1, dm_f2uint(d0 * e.W));
+    return __ldg(e.topPdf + min(e.H - 1, dm_f2uint(d1 * e.H))) * __ldg(e.pdf + (size_t)row * e.W + col);
+}
+// tex2DLod<float4>(envLightTexture, u, v, 0).xyz with the reference's sampler (common_host.cpp:2664-2669: linear filter, clamp
+// addressing, normalised coordinates) in software: the texture unit's arithmetic - xB = u W - 0.5, i = floor(xB), the fraction
+// kept with 8 fractional bits, the four texels blended - spelled out in fp32
+// (the three heavier functions are out of line and take the 56-byte descriptor by value: kernels that never meet an environment
+// light keep their register budget and no kernel parameter has its address taken)
+static __device__ __noinline__ f3 envFetchOutOfLine(DevEnvLight e, float u, float v) {
+    const float xB = u * e.W - 0.5f, yB = v * e.H - 0.5f;
+    const float fx = floorf(xB), fy = floorf(yB);
+    const float a = floorf((xB - fx) * 256.0f + 0.5f) * (1.0f / 256.0f);
+    const float b = floorf((yB - fy) * 256.0f + 0.5f) * (1.0f / 256.0f);
+    const uint32_t x0 = dm_f2uint(fminf(fmaxf(fx, 0.0f), (float)(e.W - 1))), x1 = dm_f2uint(fminf(fmaxf(fx + 1.0f, 0.0f), (float)(e.W - 1)));
+    const uint32_t y0 = dm_f2uint(fminf(fmaxf(fy, 0.0f), (float)(e.H - 1))), y1 = dm_f2uint(fminf(fmaxf(fy + 1.0f, 0.0f), (float)(e.H - 1)));
+    const float4 t00 = __ldg(e.texels + (size_t)y0 * e.W + x0), t10 = __ldg(e.texels + (size_t)y0 * e.W + x1);
+    const float4 t01 = __ldg(e.texels + (size_t)y1 * e.W + x0), t11 = __ldg(e.texels + (size_t)y1 * e.W + x1);
+    const float w00 = (1 - a) * (1 - b), w10 = a * (1 - b), w01 = (1 - a) * b, w11 = a * b;
+    return w00 * f3(t00.x, t00.y, t00.z) + w10 * f3(t10.x, t10.y, t10.z) + w01 * f3(t01.x, t01.y, t01.z) + w11 * f3(t11.x, t11.y, t11.z);
+}
+GFX_D f3 envFetch(const DevEnvLight &e, float u, float v) { return envFetchOutOfLine(e, u, v); }
+// sampleLight with sampleEnvLight = true (restir_di_shared.h:330-364)
+struct EnvLightSample {
+    LightSample sample;
+    float areaPDensity;
+};
+static __device__ __noinline__ EnvLightSample sampleEnvLightOutOfLine(DevEnvLight env, float u0, float u1) {
+    EnvLightSample out;
+    LightSample* lightSample = &out.sample;
+    float* areaPDensity = &out.areaPDensity;
+    float u, v, uvPDF;
+    envSample(env, u0, u1, &u, &v, &uvPDF);
+    const float phi = 2 * kPi * u;
+    const float theta = kPi * v;
+    float posPhi = phi - env.rotation;
+    posPhi = posPhi - floorf(posPhi / (2 * kPi)) * 2 * kPi;
+    const f3 direction = fromPolarYUp(posPhi, theta);
+    lightSample->position = direction;
+    lightSample->atInfinity = 1;
+    lightSample->normal = -direction;
+    lightSample->emittance = f3(0.0f);
+    const float sinTheta = dm_sin(theta);
+    if (sinTheta == 0.0f) {
+        *areaPDensity = 0.0f;
+        return out;
+    }
+    *areaPDensity = uvPDF / (2 * kPi * kPi * sinTheta);
+    f3 emittance(kPi * env.powerCoeff);
+    emittance *= envFetchOutOfLine(env, u, v);
+    lightSample->emittance = emittance;
+    return out;
+}
+GFX_D void sampleEnvLight(const DevScene &s, float u0, float u1, LightSample* lightSample, float* areaPDensity) {
+    const EnvLightSample r = sampleEnvLightOutOfLine(s.env, u0, u1);
+    *lightSample = r.sample;
+    *areaPDensity = r.areaPDensity;
+}
+// the choice between the environment and the emitters that the streaming-RIS loops make for candidate i of n
+// (optix_restir_di_kernels.cu:72-90, build_cell_reservoirs.cu:120-139): returns sampleEnvLight, remaps ul
+GFX_D bool chooseEnvForCandidate(const DevScene &s, uint32_t i, uint32_t numCandidates, float* ul, float* probToSampleCurLightType) {
+    *probToSampleCurLightType = 1.0f;
+    if (!s.env.enabled)
+        return false;
+    if (!(__ldg(s.instIntegral) > 0.0f))
+        return true;
+    const float prob = fminf(fmaxf(kProbToSampleEnvLight * numCandidates - i, 0.0f), 1.0f);
+    if (*ul < prob) {
+        *probToSampleCurLightType = kProbToSampleEnvLight;
+        *ul = *ul / prob;
+        return true;
+    }
+    *probToSampleCurLightType = 1.0f - kProbToSampleEnvLight;
+    *ul = (*ul - prob) / (1 - prob);
+    return false;
+}
+// the path tracers' choice per next-event estimation (optix_pathtracing_kernels.cu:27-42)
+GFX_D bool chooseEnvForNee(const DevScene &s, float* uLight, float* probToSampleCurLightType) {
+    *probToSampleCurLightType = 1.0f;
+    if (!s.env.enabled)
+        return false;
+    if (!(__ldg(s.instIntegral) > 0.0f))
+        return true;
+    if (*uLight < kProbToSampleEnvLight) {
+        *probToSampleCurLightType = kProbToSampleEnvLight;
+        *uLight /= *probToSampleCurLightType;
+        return true;
+    }
+    *probToSampleCurLightType = 1.0f - kProbToSampleEnvLight;
+    *uLight = (*uLight - kProbToSampleEnvLight) / *probToSampleCurLightType;
+    return false;
+}
+// the miss programs of the path tracers (optix_pathtracing_kernels.cu:310-341; neural_radiance_caching/...:625-650, which
+// multiplies by probToSampleEnvLight unconditionally): luminance x MIS weight of the environment along rayDir
+static __device__ __noinline__ f3 evaluateEnvLightOnMissOutOfLine(DevEnvLight env, f3 rayDirIn, float prevDirPDensity, float probToSampleEnv) {
+    const f3 rayDir = normalize(rayDirIn);
+    float posPhi, theta;
+    toPolarYUp(rayDir, &posPhi, &theta);
+    float phi = posPhi + env.rotation;
+    phi = phi - floorf(phi / (2 * kPi)) * 2 * kPi;
+    const float tu = phi / (2 * kPi), tv = theta / kPi;
+    const f3 luminance = env.powerCoeff * envFetchOutOfLine(env, tu, tv);
+    const float uvPDF = envEvaluatePDF(env, tu, tv);
+    const float hypAreaPDensity = uvPDF / (2 * kPi * kPi * dm_sin(theta));
+    const float lightPDensity = probToSampleEnv * hypAreaPDensity;
+    const float bsdfPDensity = prevDirPDensity;
+    const float misWeight = pow2f(bsdfPDensity) / (pow2f(bsdfPDensity) + pow2f(lightPDensity));
+    return luminance * misWeight;
+}
+GFX_D f3 evaluateEnvLightOnMiss(const DevScene &s, const f3 &rayDir, float prevDirPDensity, bool nrcVariant) {
+    const float probToSampleEnv = (nrcVariant || __ldg(s.instIntegral) > 0.0f) ? kProbToSampleEnvLight : 1.0f;
+    return evaluateEnvLightOnMissOutOfLine(s.env, rayDir, prevDirPDensity, probToSampleEnv);
+}
+
 // sampleLight for the RIS candidate loop, fetching the 128-byte light record in steps and stopping as soon as the candidate is
 // certain to contribute RGB(0) to this shading point.  ncu: the candidate kernel is bound by the L1 data pipe's wavefront rate
 // (every lane reads a different light, so every load instruction of the sampling chain is up to 32 wavefronts) and by issue

@@ -21,6 +21,8 @@
 //    recompute for each of the 66 M candidates per frame.
 #include "lighting.cuh"
 #include "context.h"
+#include <cmath>
+#include <algorithm>
 #include <cub/device/device_radix_sort.cuh>
 
 namespace gfx {
@@ -492,6 +494,110 @@ size_t lightPickSortTempBytes(uint32_t capacity) {
 int debugLightPick(gfx_ctx* ctx, cudaStream_t stream, const float* dUl, uint32_t n, uint32_t* dFlat, uint32_t* dChain) {
     if (n)
         k_pickDebug<<<(n + 255) / 256, 256, 0, stream>>>(ctx->devScene(), dUl, n, dFlat, dChain);
+    ctx->launches++;
+    GFX_CUDA(ctx, cudaGetLastError());
+    return GFX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Environment light: what loadEnvironmentalTexture (common/common_host.cpp:2658-2711) leaves on the device.  Host work, like the
+// reference: clamp the texels to [0, 65504], importance = luminance x sin(theta of the texel centre), then one piecewise-constant
+// distribution per row and one over the row integrals (RegularConstantContinuousDistribution1D/2D::initialize, :292-357: the CDF
+// is a compensated running sum of PDF[i] / N, both normalised by the integral).
+namespace {
+struct KahanSum { // CompensatedSum_T<float>, basic_types.h:5427-5452
+    float result = 0.0f, comp = 0.0f;
+    void operator+=(float value) {
+        const float cInput = value - comp;
+        const float sumTemp = result + cInput;
+        comp = (sumTemp - result) - cInput;
+        result = sumTemp;
+    }
+};
+float regularDistribution(const float* values, uint32_t n, float* pdf, float* cdf) {
+    KahanSum sum;
+    for (uint32_t i = 0; i < n; ++i) {
+        cdf[i] = sum.result;
+        sum += values[i] / n;
+    }
+    const float integral = sum.result;
+    for (uint32_t i = 0; i < n; ++i) {
+        pdf[i] = values[i] / integral;
+        cdf[i] /= integral;
+    }
+    cdf[n] = 1.0f;
+    return integral;
+}
+} // namespace
+
+int uploadEnvLight(gfx_ctx* ctx, const float* rgba, uint32_t width, uint32_t height) {
+    SceneState &S = ctx->scene;
+    if (!rgba || !width || !height)
+        return GFX_OK;
+    const size_t n = (size_t)width * height;
+    std::vector<float4> texels(n);
+    std::vector<float> importance(n), pdf(n), cdf((size_t)(width + 1) * height), rowIntegral(height), topPdf(height), topCdf(height + 1);
+    for (uint32_t y = 0; y < height; ++y) {
+        const float theta = 3.14159265358979323846f * (y + 0.5f) / height;
+        const float sinTheta = std::sin(theta);
+        for (uint32_t x = 0; x < width; ++x) {
+            const float* src = rgba + 4 * ((size_t)y * width + x);
+            float4 t;
+            t.x = std::min(std::max(src[0], 0.0f), 65504.0f);
+            t.y = std::min(std::max(src[1], 0.0f), 65504.0f);
+            t.z = std::min(std::max(src[2], 0.0f), 65504.0f);
+            t.w = src[3];
+            texels[(size_t)y * width + x] = t;
+            importance[(size_t)y * width + x] = (0.2126729f * t.x + 0.7151522f * t.y + 0.0721750f * t.z) * sinTheta;
+        }
+    }
+    for (uint32_t y = 0; y < height; ++y)
+        rowIntegral[y] = regularDistribution(importance.data() + (size_t)y * width, width, pdf.data() + (size_t)y * width,
+                                             cdf.data() + (size_t)y * (width + 1));
+    regularDistribution(rowIntegral.data(), height, topPdf.data(), topCdf.data());
+    auto upload = [&](void** dst, const void* src, size_t bytes) {
+        cudaError_t e = cudaMalloc(dst, bytes);
+        if (e == cudaSuccess)
+            e = cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+        return e;
+    };
+    GFX_CUDA(ctx, upload((void**)&S.envTexels, texels.data(), n * 16));
+    GFX_CUDA(ctx, upload((void**)&S.envPdf, pdf.data(), n * 4));
+    GFX_CUDA(ctx, upload((void**)&S.envCdf, cdf.data(), cdf.size() * 4));
+    GFX_CUDA(ctx, upload((void**)&S.envTopPdf, topPdf.data(), topPdf.size() * 4));
+    GFX_CUDA(ctx, upload((void**)&S.envTopCdf, topCdf.data(), topCdf.size() * 4));
+    S.envW = width;
+    S.envH = height;
+    return GFX_OK;
+}
+
+// test hook (gfx_env_light_debug): the device-side importance-map sampler, its density and the software texture fetch
+__global__ void k_envDebug(DevEnvLight env, int op, const float2* in, uint32_t n, float* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const float2 ab = in[i];
+    float* o = out + 3 * (size_t)i;
+    if (op == 0) {
+        envSample(env, ab.x, ab.y, &o[0], &o[1], &o[2]);
+    }
+    else if (op == 1) {
+        o[0] = envEvaluatePDF(env, ab.x, ab.y);
+        o[1] = o[2] = 0.0f;
+    }
+    else {
+        const f3 c = envFetch(env, ab.x, ab.y);
+        o[0] = c.x; o[1] = c.y; o[2] = c.z;
+    }
+}
+int debugEnvLight(gfx_ctx* ctx, cudaStream_t stream, int op, const float* dIn, uint32_t n, float* dOut) {
+    const DevScene s = ctx->devScene();
+    if (!s.env.W) {
+        ctx->setError("gfx_env_light_debug: the scene has no environment map");
+        return GFX_ERR_NOT_READY;
+    }
+    if (n)
+        k_envDebug<<<(n + 127) / 128, 128, 0, stream>>>(s.env, op, reinterpret_cast<const float2*>(dIn), n, dOut);
     ctx->launches++;
     GFX_CUDA(ctx, cudaGetLastError());
     return GFX_OK;

@@ -354,6 +354,9 @@ __global__ void GFX_BOUNCE_BOUNDS k_nrcFirstHit(DevScene s, DevFrame f, DevFrame
                 createRadianceQuery(p, positionInWorld, shadingFrame.normal, vOut, bsdf, n.stagedQuery + 14 * (size_t)linearTileIndex);
             }
         }
+        else if (s.env.enabled) { // :323-331: the environment seen directly; the miss program left (u, v) in the barycentrics
+            radiance = s.env.powerCoeff * envFetch(s.env, decodeBarycentric((uint16_t)(gb0.w & 0xFFFFu)), decodeBarycentric((uint16_t)(gb0.w >> 16)));
+        }
         ps.radiance[pix] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
         n.pathA[pix] = make_float4(primaryPathSpread, 0.0f, __uint_as_float(flags | (1u << 8)), __uint_as_float(linearTileIndex));
     }
@@ -399,8 +402,25 @@ __global__ void GFX_BOUNCE_BOUNDS k_nrcBounce(DevScene s, DevFrame f, DevFramePa
 
             // one pass through the closest-hit program; `break` = return
             do {
-                if (hit.y == 0xFFFFFFFFu)
-                    break; // miss program: no environment light
+                if (hit.y == 0xFFFFFFFFu) { // pathTrace_miss_generic (:625-672): implicit environment light, MIS
+                    if (s.env.enabled) {
+                        const float4 r1 = ps.extRays[curQueue][2 * (size_t)slot + 1];
+                        const float4 ap = ps.alphaPdf[pix];
+                        const f3 directContImplicit = evaluateEnvLightOnMiss(s, f3(r1.x, r1.y, r1.z), ap.w, true);
+                        float4 rad = ps.radiance[pix];
+                        const f3 add = f3(ap.x, ap.y, ap.z) * directContImplicit;
+                        rad.x += add.x; rad.y += add.y; rad.z += add.z;
+                        ps.radiance[pix] = rad;
+                        const uint32_t prevTrainDataIndex = isTrainingPath ? n.tilePrev[tile] : kInvalidVertexDataIndex;
+                        if (isTrainingPath && prevTrainDataIndex != kInvalidVertexDataIndex) {
+                            const float4 pb = n.pathB[pix];
+                            const f3 addT = f3(pb.x, pb.y, pb.z) * directContImplicit;
+                            float* tgt = n.trainTarget[0] + 3 * (size_t)prevTrainDataIndex;
+                            tgt[0] += addT.x; tgt[1] += addT.y; tgt[2] += addT.z;
+                        }
+                    }
+                    break;
+                }
                 const float4 r0 = ps.extRays[curQueue][2 * (size_t)slot];
                 const float4 r1 = ps.extRays[curQueue][2 * (size_t)slot + 1];
                 const f3 rayOrigin(r0.x, r0.y, r0.z), rayDir(r1.x, r1.y, r1.z);
@@ -717,7 +737,7 @@ int launchPathTraceNrc(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* 
         ctx->setError("gfx_pathtrace_launch(GFX_PT_NRC): ncclAllGather not found (load NCCL in the host process)");
         return GFX_ERR_UNSUPPORTED;
     }
-    const DevScene s = ctx->devScene();
+    const DevScene s = ctx->devScene(params);
     const DevFrame f = ctx->devFrame();
     const DevPathState ps = makePathState(ctx);
     const DevNrc n = makeDevNrc(ctx);

@@ -102,6 +102,9 @@ __global__ void GFX_BOUNCE_BOUNDS k_ptFirstHit(DevScene s, DevFrame f, DevFrameP
             ps.alphaPdf[pix] = make_float4(v.alpha.x, v.alpha.y, v.alpha.z, v.dirPDensity);
             alive = true;
         }
+        else if (s.env.enabled) { // :200-207: the environment seen directly; the miss program left (u, v) in the barycentrics
+            radiance = s.env.powerCoeff * envFetch(s.env, decodeBarycentric((uint16_t)(gb0.w & 0xFFFFu)), decodeBarycentric((uint16_t)(gb0.w >> 16)));
+        }
         ps.radiance[pix] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
     }
     emitRays(s, ps, ps.counters, 0u, lane, pix, positionInWorld, v, alive);
@@ -178,6 +181,16 @@ __global__ void GFX_BOUNCE_BOUNDS k_ptBounce(DevScene s, DevFrame f, DevFramePar
                 }
                 f.rng[pix] = rng.state;
                 ps.radiance[pix] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
+            }
+            else if (!REGIR && s.env.enabled) { // miss program (:310-341); the ReGIR ray type's miss program is empty
+                const uint32_t missPix = ps.extPixel[curQueue][slot];
+                const float4 r1 = ps.extRays[curQueue][2 * (size_t)slot + 1];
+                const float4 ap = ps.alphaPdf[missPix];
+                const f3 implicit = evaluateEnvLightOnMiss(s, f3(r1.x, r1.y, r1.z), ap.w, false);
+                float4 rad = ps.radiance[missPix];
+                const f3 add = f3(ap.x, ap.y, ap.z) * implicit;
+                rad.x += add.x; rad.y += add.y; rad.z += add.z;
+                ps.radiance[missPix] = rad;
             }
         }
         emitRays(s, ps, nextCounters, nextQueue, lane, pix, positionInWorld, v, alive);
@@ -257,7 +270,7 @@ int launchPathTrace(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* par
     if (p.y1 <= p.y0)
         return GFX_OK;
     p.maxPathLength = params->maxPathLength ? params->maxPathLength : 5u; // 0 = the hosts' default
-    const DevScene s = ctx->devScene();
+    const DevScene s = ctx->devScene(params);
     const DevFrame f = ctx->devFrame();
     const DevPathState ps = makePathState(ctx);
     DevRegir rg = {};

@@ -105,6 +105,8 @@ GFX_D void computeSurfacePointAtHit(const DevScene &s, const DevInstance* inst, 
 
     // hypothetical density with which explicit light sampling would have produced this point (:535-575)
     float lightProb = 1.0f;
+    if (s.env.enabled) // path_tracing_shared.h:540-541
+        lightProb *= (1 - kProbToSampleEnvLight);
     const float instImportance = inst->geomIntegral;
     lightProb *= (pow2f(inst->uniformScale) * instImportance) / __ldg(s.instIntegral);
     lightProb *= mesh.primIntegral / instImportance;
@@ -150,16 +152,22 @@ GFX_D void neeBaseline(const DevScene &s, const f3 &positionInWorld, const f3 &v
     out->wantShadow = false;
     out->directContNEE = f3(0.0f);
     out->neeUnoccluded = f3(0.0f);
-    const float uLight = rng.getFloat0cTo1o();
+    float uLight = rng.getFloat0cTo1o();
+    float probToSampleCurLightType;
+    const bool selectEnvLight = chooseEnvForNee(s, &uLight, &probToSampleCurLightType); // :25-42
     const float u0 = rng.getFloat0cTo1o();
     const float u1 = rng.getFloat0cTo1o();
     LightSample lightSample;
     float areaPDensity = 0.0f;
-    sampleLight(s, uLight, u0, u1, &lightSample, &areaPDensity);
+    if (selectEnvLight)
+        sampleEnvLight(s, u0, u1, &lightSample, &areaPDensity);
+    else
+        sampleLight(s, uLight, u0, u1, &lightSample, &areaPDensity);
+    areaPDensity *= probToSampleCurLightType;
     if (areaPDensity > 0.0f) {
-        f3 shadowRay = lightSample.position - positionInWorld;
+        f3 shadowRay = lightSample.atInfinity ? lightSample.position : (lightSample.position - positionInWorld);
         const float dist2 = sqLength(shadowRay);
-        const float dist = sqrtf(dist2);
+        float dist = sqrtf(dist2);
         shadowRay /= dist;
         const f3 vInLocal = shadingFrame.toLocal(shadowRay);
         const float lpCos = fabsf(dot(shadowRay, lightSample.normal));
@@ -182,6 +190,8 @@ GFX_D void neeBaseline(const DevScene &s, const f3 &positionInWorld, const f3 &v
             out->directContNEE = f3(0.0f) * scale;
             out->wantShadow = true;
             out->shadowDir = shadowRay;
+            if (lightSample.atInfinity) // performDirectLighting<.., true>: the environment is 1e+10 away
+                dist = 1e+10f;
             out->shadowTmax = dist * 0.9999f;
             out->pending = make_float4(unoccluded.x, unoccluded.y, unoccluded.z, scale);
         }

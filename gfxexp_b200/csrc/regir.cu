@@ -81,10 +81,13 @@ static int ensureRegir(gfx_ctx* ctx, const GfxFrameParams* p) {
     return GFX_OK;
 }
 
-// build_cell_reservoirs.cu:6-69 (no environment light)
+// build_cell_reservoirs.cu:6-69
 GFX_D f3 sampleIntensity(const DevScene &s, const f3 &cellCenter, const f3 &halfCellSize, float minSquaredDistance, float uLight,
-                         float uPos0, float uPos1, LightSample* lightSample, float* probDensity) {
-    sampleLight(s, uLight, uPos0, uPos1, lightSample, probDensity);
+                         bool sampleEnv, float uPos0, float uPos1, LightSample* lightSample, float* probDensity) {
+    if (sampleEnv)
+        sampleEnvLight(s, uPos0, uPos1, lightSample, probDensity);
+    else
+        sampleLight(s, uLight, uPos0, uPos1, lightSample, probDensity);
     float dist2 = minSquaredDistance;
     float lpCos = 1;
     const bool isOutsideCell =
@@ -164,12 +167,15 @@ __global__ void __launch_bounds__(128) k_regirBuildCells(DevScene s, DevRegir rg
     // streaming RIS, target = luminous intensity reaching the cell's representative point
     const uint32_t numCandidates = 1u << rg.log2NumCandidatesPerLightSlot;
     for (uint32_t candIdx = 0; candIdx < numCandidates; ++candIdx) {
-        const float uLight = rng.getFloat0cTo1o();
+        float uLight = rng.getFloat0cTo1o();
+        float probToSampleCurLightType;
+        const bool sampleEnv = chooseEnvForCandidate(s, candIdx, numCandidates, &uLight, &probToSampleCurLightType); // :120-139
         LightSample lightSample = emptyLightSample();
         float areaPDensity = 0.0f;
         const float uPos0 = rng.getFloat0cTo1o();
         const float uPos1 = rng.getFloat0cTo1o();
-        const f3 cont = sampleIntensity(s, cellCenter, halfCellSize, minSquaredDistance, uLight, uPos0, uPos1, &lightSample, &areaPDensity);
+        const f3 cont = sampleIntensity(s, cellCenter, halfCellSize, minSquaredDistance, uLight, sampleEnv, uPos0, uPos1, &lightSample, &areaPDensity);
+        areaPDensity *= probToSampleCurLightType;
         const float targetPDensity = convertToWeight(cont);
         const float weight = targetPDensity / areaPDensity;
         if (reservoir.update(lightSample, weight, rng.getFloat0cTo1o()))
@@ -242,7 +248,7 @@ int launchRegirBuildCells(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParam
         return GFX_ERR_NOT_READY;
     }
     const DevRegir rg = makeDevRegir(ctx, params);
-    const DevScene s = ctx->devScene();
+    const DevScene s = ctx->devScene(params);
     const uint32_t grid = (ctx->frame.regir.numSlots + 127) / 128;
     GFX_TIMED(ctx, stream, "regir_build_cells");
     if (useTemporalReuse)

@@ -31,7 +31,7 @@ namespace gfx {
 // (restir_di_shared.h:118-125) and draws, so results are bit-identical.
 constexpr uint32_t kRisMaxCandidates = 32; // TWO_PHASE keeps one key per candidate and thread in shared memory
 
-template <bool withTemporalRIS, bool useUnbiasedEstimator, int PHASE, bool TWO_PHASE>
+template <bool withTemporalRIS, bool useUnbiasedEstimator, int PHASE, bool TWO_PHASE, bool ENV>
 GFX_D bool risPixel(const DevScene &s, const DevFrame &f, const DevFrameParams &p, RayRequest* request, uint32_t* candidateKeys) {
     // optix_restir_di_kernels.cu:14-287
     const uint32_t x = blockIdx.x * 8 + threadIdx.x;
@@ -78,6 +78,7 @@ GFX_D bool risPixel(const DevScene &s, const DevFrame &f, const DevFrameParams &
     // function of (ul, u0, u1)), which is bit-identical and frees registers in the hot loop.
     float selUl = 0.0f, selU0 = 0.0f, selU1 = 0.0f;
     bool hasSelection = false;
+    bool selEnv = false; // ENV: the selected candidate came from the environment map
     float sumWeights = 0.0f;
     if (TWO_PHASE && numCandidates <= kRisMaxCandidates) {
         uint32_t* myKeys = candidateKeys + (threadIdx.x + threadIdx.y * blockDim.x); // [candidate][64 threads]
@@ -142,15 +143,22 @@ GFX_D bool risPixel(const DevScene &s, const DevFrame &f, const DevFrameParams &
     }
     else {
     for (uint32_t i = 0; i < numCandidates; ++i) {
-        const float ul = rng.getFloat0cTo1o();
-        const float probToSampleCurLightType = 1.0f;
+        float ul = rng.getFloat0cTo1o();
+        float probToSampleCurLightType = 1.0f;
+        // with an environment light the first probToSampleEnvLight * numCandidates candidates sample it (:72-90)
+        bool sampleEnv = false;
+        if (ENV)
+            sampleEnv = chooseEnvForCandidate(s, i, numCandidates, &ul, &probToSampleCurLightType);
         LightSample lightSample = emptyLightSample();
         float probDensity;
         const float u0 = rng.getFloat0cTo1o();
         const float u1 = rng.getFloat0cTo1o();
+        if (ENV && sampleEnv) {
+            sampleEnvLight(s, u0, u1, &lightSample, &probDensity);
+        }
         // staged fetch of the light triangle: certainly-dark candidates stop early (their contribution is exactly
         // RGB(0): the reservoir is untouched and only the acceptance draw is consumed, as in the dead path below)
-        if (sampleLightUnlessDark(s, ul, u0, u1, positionInWorld, shadingNormalInWorld, vOutLocal.z, &lightSample, &probDensity)) {
+        else if (sampleLightUnlessDark(s, ul, u0, u1, positionInWorld, shadingNormalInWorld, vOutLocal.z, &lightSample, &probDensity)) {
             (void)rng.getFloat0cTo1o();
             continue;
         }
@@ -173,6 +181,7 @@ GFX_D bool risPixel(const DevScene &s, const DevFrame &f, const DevFrameParams &
             selUl = ul;
             selU0 = u0;
             selU1 = u1;
+            selEnv = ENV && sampleEnv;
             hasSelection = true;
             selectedTargetDensity = targetDensity;
         }
@@ -180,7 +189,10 @@ GFX_D bool risPixel(const DevScene &s, const DevFrame &f, const DevFrameParams &
     }
     if (hasSelection) {
         float unusedDensity;
-        sampleLight(s, selUl, selU0, selU1, &reservoir.sample, &unusedDensity);
+        if (ENV && selEnv)
+            sampleEnvLight(s, selU0, selU1, &reservoir.sample, &unusedDensity);
+        else
+            sampleLight(s, selUl, selU0, selU1, &reservoir.sample, &unusedDensity);
     }
     reservoir.sumWeights = sumWeights;
     reservoir.streamLength = numCandidates;
@@ -305,16 +317,17 @@ GFX_D bool risPixel(const DevScene &s, const DevFrame &f, const DevFrameParams &
 #ifndef GFX_RIS_MIN_BLOCKS
 #define GFX_RIS_MIN_BLOCKS 16 // 64 registers: measured 1.49 ms against 1.80 ms at the 84 registers ptxas picks unconstrained (profiles/r02_summary.md)
 #endif
-template <bool withTemporalRIS, bool useUnbiasedEstimator, int PHASE, bool TWO_PHASE = false>
+template <bool withTemporalRIS, bool useUnbiasedEstimator, int PHASE, bool TWO_PHASE = false, bool ENV = false>
 __global__ void __launch_bounds__(64, GFX_RIS_MIN_BLOCKS) k_initialAndTemporalRIS(DevScene s, DevFrame f, DevFrameParams p) {
     static_assert(!TWO_PHASE || PHASE == 1, "the two-phase candidate loop belongs to the wavefront candidate pass");
+    static_assert(!(TWO_PHASE && ENV), "environment-light candidates go through the lock-step loop");
     RayRequest request;
     uint32_t* candidateKeys = nullptr;
     if constexpr (TWO_PHASE) {
         __shared__ uint32_t keys[kRisMaxCandidates * 64]; // [candidate][thread of the 8x8 block]
         candidateKeys = keys;
     }
-    const bool want = risPixel<withTemporalRIS, useUnbiasedEstimator, PHASE, TWO_PHASE>(s, f, p, &request, candidateKeys);
+    const bool want = risPixel<withTemporalRIS, useUnbiasedEstimator, PHASE, TWO_PHASE, ENV>(s, f, p, &request, candidateKeys);
     if (PHASE == 1)
         enqueueRay(f, s.rayCounter, want, request);
 }
@@ -566,6 +579,10 @@ __global__ void __launch_bounds__(64) k_shading(DevScene s, DevFrame f, DevFrame
         }
         contribution += recPDFEstimate * directCont;
     }
+    else if (s.env.enabled) { // :620-629: the environment seen directly; the miss program left (u, v) in the texture coordinates
+        const f2 texCoord = decodeTexCoords(gb3.z);
+        contribution = s.env.powerCoeff * envFetch(s.env, texCoord.x, texCoord.y);
+    }
 
     f3 prevColorResult(0.0f);
     if (p.numAccumFrames > 0) {
@@ -585,7 +602,7 @@ int launchReSTIR(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* params
         return GFX_ERR_INVALID_ARGUMENT; // 4-bit fields in the reference (restir_di_shared.h:258-259)
     const dim3 block(8, 8);
     const dim3 grid((ctx->frame.W + 7) / 8, (p.y1 - p.y0 + 7) / 8);
-    const DevScene s = ctx->devScene();
+    const DevScene s = ctx->devScene(params);
     const DevFrame f = ctx->devFrame();
     // wavefront form (default): request rays -> persistent-thread trace -> resolve.  GFX_MEGAKERNEL=1 selects
     // the single-kernel form with inline traversal (same results; kept for A/B measurements).
@@ -597,12 +614,15 @@ int launchReSTIR(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* params
     if (wave && p.reuseVisibility) { \
         int rc_ = resetVisibilityQueue(ctx, stream); if (rc_) return rc_; \
         { GFX_TIMED(ctx, stream, "ris_candidates"); \
-          if (twoPhase) k_initialAndTemporalRIS<T, U, 1, true><<<grid, block, 0, stream>>>(s, f, p); \
+          if (s.env.enabled) k_initialAndTemporalRIS<T, U, 1, false, true><<<grid, block, 0, stream>>>(s, f, p); \
+          else if (twoPhase) k_initialAndTemporalRIS<T, U, 1, true><<<grid, block, 0, stream>>>(s, f, p); \
           else k_initialAndTemporalRIS<T, U, 1, false><<<grid, block, 0, stream>>>(s, f, p); } ctx->launches++; \
         rc_ = traceVisibilityQueue(ctx, stream); if (rc_) return rc_; \
         { GFX_TIMED(ctx, stream, "ris_resolve_temporal"); k_initialAndTemporalRIS<T, U, 2><<<grid, block, 0, stream>>>(s, f, p); } \
     } else { \
-        { GFX_TIMED(ctx, stream, "ris_megakernel"); k_initialAndTemporalRIS<T, U, 0><<<grid, block, 0, stream>>>(s, f, p); } \
+        { GFX_TIMED(ctx, stream, "ris_megakernel"); \
+          if (s.env.enabled) k_initialAndTemporalRIS<T, U, 0, false, true><<<grid, block, 0, stream>>>(s, f, p); \
+          else k_initialAndTemporalRIS<T, U, 0><<<grid, block, 0, stream>>>(s, f, p); } \
     }
     switch (pass) {
     case GFX_RESTIR_INITIAL_RIS: RIS_LAUNCH(false, false); break;

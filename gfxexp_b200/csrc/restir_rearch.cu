@@ -96,11 +96,27 @@ __global__ void __launch_bounds__(128) k_presampleLights(DevScene s, DevRearch r
     PCG32RNG rng{ r.rngs[linearThreadIndex] };
     LightSample ls = emptyLightSample();
     float areaPDensity = 0.0f;
+    // :12-28: with an environment light the first probToSampleEnvLight * lightSubsetSize lights of every subset sample it
+    float probToSampleCurLightType = 1.0f;
+    bool sampleEnv = false;
+    if (s.env.enabled) {
+        if (__ldg(s.instIntegral) > 0.0f) {
+            const uint32_t indexInSubset = linearThreadIndex % kLightSubsetSize;
+            sampleEnv = indexInSubset < kProbToSampleEnvLight * kLightSubsetSize;
+            probToSampleCurLightType = sampleEnv ? kProbToSampleEnvLight : (1 - kProbToSampleEnvLight);
+        }
+        else {
+            sampleEnv = true;
+        }
+    }
     const float ul = rng.getFloat0cTo1o();
     const float u0 = rng.getFloat0cTo1o();
     const float u1 = rng.getFloat0cTo1o();
-    sampleLight(s, ul, u0, u1, &ls, &areaPDensity);
-    areaPDensity *= 1.0f; // probToSampleCurLightType
+    if (sampleEnv)
+        sampleEnvLight(s, u0, u1, &ls, &areaPDensity);
+    else
+        sampleLight(s, ul, u0, u1, &ls, &areaPDensity);
+    areaPDensity *= probToSampleCurLightType;
     r.rngs[linearThreadIndex] = rng.state;
     float4* o = r.preSampledLights + 3 * (size_t)linearThreadIndex;
     o[0] = make_float4(ls.emittance.x, ls.emittance.y, ls.emittance.z, areaPDensity);
@@ -603,6 +619,10 @@ __global__ void __launch_bounds__(64) k_shadeAndResample(DevScene s, DevFrame f,
         f.reservoirInfo[curResIndex][pix] = make_float2(recPDFEstimate, selectedTargetDensity);
         f.rng[pix] = rng.state;
     }
+    else if (s.env.enabled) { // optix_restir_di_rearch_kernels.cu:648-656: the environment seen directly
+        const f2 texCoord = decodeTexCoords(gb3.z);
+        contribution = s.env.powerCoeff * envFetch(s.env, texCoord.x, texCoord.y);
+    }
 
     f3 prevColorResult(0.0f);
     if (p.numAccumFrames > 0) {
@@ -630,7 +650,7 @@ int launchReSTIRRearch(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* 
         return rc;
     const dim3 block(8, 8);
     const dim3 grid((ctx->frame.W + 7) / 8, (p.y1 - p.y0 + 7) / 8);
-    const DevScene s = ctx->devScene();
+    const DevScene s = ctx->devScene(params);
     const DevFrame f = ctx->devFrame();
     const DevRearch r = makeDevRearch(ctx);
     switch (pass) {

@@ -85,6 +85,22 @@ struct DevBvh {
     uint32_t* overflowFlag; // set to 1 if a traversal stack overflowed (checked by the host)
 };
 
+// Environment light: Scene::envLightTexture + envLightImportanceMap (restir_di_shared.h:221-222) and the per-frame
+// envLightPowerCoeff / envLightRotation / enableEnvLight (:249-250,269).  texels: W x H RGBA, clamped on upload; pdf / cdf: the H row
+// distributions (W and W + 1 values each), topPdf / topCdf: the distribution over rows (RegularConstantContinuousDistribution2D,
+// common_shared.h:283-386; built on the host like common_host.cpp:292-357).  enabled = the scene has a map and the frame wants it.
+struct DevEnvLight {
+    const float4* texels;
+    const float* pdf;
+    const float* cdf;
+    const float* topPdf;
+    const float* topCdf;
+    uint32_t W, H;
+    uint32_t enabled;
+    float powerCoeff, rotation;
+};
+constexpr float kProbToSampleEnvLight = 0.25f; // restir_di_shared.h:6 (and the other apps' *_shared.h:6)
+
 struct DevScene {
     const float4* vertices;          // 3 per vertex
     const uint4* triangles;
@@ -123,6 +139,7 @@ struct DevScene {
     uint32_t numInstances;
     unsigned long long* rayCounter;  // frame statistics: rays traced (primary + visibility)
     DevBvh bvh;
+    DevEnvLight env;
 };
 
 struct DevFrame {
@@ -167,6 +184,7 @@ struct DevFrameParams {
     float radianceScale;
     uint32_t reuseVisibilityForTemporal, reuseVisibilityForSpatiotemporal;
     float radiusThresholdForSpatialVisReuse;
+    float envLightRotation; // also without a map: the miss program of the G-buffer pass encodes (u, v) with it
 };
 
 } // namespace gfx

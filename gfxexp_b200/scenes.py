@@ -17,7 +17,7 @@ from __future__ import annotations
 
 import dataclasses
 import math
-from typing import List
+from typing import List, Optional
 
 import numpy as np
 
@@ -52,6 +52,7 @@ class Scene:
     camera_orientation: np.ndarray  # [3,3] row-major
     fov_y: float
     name: str = "scene"
+    env_map: Optional[np.ndarray] = None  # float32 [H, W, 4] equirectangular environment map (GfxSceneDesc::envTexels) or None
 
     @property
     def num_triangles(self) -> int:
@@ -65,6 +66,28 @@ class Scene:
                 if self.materials[self.meshes[m].material]["hasEmittance"]:
                     n += self.meshes[m].triangles.shape[0]
         return n
+
+
+def procedural_sky(width: int = 64, height: int = 32, sun_power: float = 40.0, seed: int = 7) -> np.ndarray:
+    """A small HDR equirectangular map in the layout loadEnvironmentalTexture expects (common/common_host.cpp:2658-2711; row 0 at
+    theta = 0, i.e. +y): a horizon-brightened blue gradient, a warm ground, a sun blob of a few texels and a little per-texel
+    noise so that no two importance values are equal.  Stands in for the -env-texture .exr the reference loads."""
+    rng = np.random.default_rng(seed)
+    v = (np.arange(height, dtype=np.float32) + 0.5) / height          # theta / pi
+    u = (np.arange(width, dtype=np.float32) + 0.5) / width            # phi / 2 pi
+    up = np.cos(np.pi * v)[:, None]                                    # +1 at the zenith
+    sky = np.stack([0.25 + 0.35 * (1 - np.abs(up)), 0.45 + 0.35 * (1 - np.abs(up)), 0.9 - 0.2 * (1 - np.abs(up))], axis=-1)
+    ground = np.array([0.18, 0.15, 0.12], dtype=np.float32)
+    img = np.where(up[..., None] >= 0, sky, ground[None, None, :]).astype(np.float32)
+    img = np.broadcast_to(img, (height, width, 3)).copy()
+    du = np.minimum(np.abs(u - 0.3), 1 - np.abs(u - 0.3))[None, :]
+    dv = (v - 0.28)[:, None]
+    sun = sun_power * np.exp(-((du * 2) ** 2 + dv ** 2) / (2 * 0.03 ** 2))
+    img += sun[..., None] * np.array([1.0, 0.9, 0.7], dtype=np.float32)
+    img *= (1 + 0.05 * rng.random((height, width, 1), dtype=np.float32))
+    out = np.ones((height, width, 4), dtype=np.float32)
+    out[..., :3] = img
+    return out
 
 
 MATERIAL_DTYPE = np.dtype([
@@ -449,6 +472,25 @@ def small_city_scene() -> Scene:
     """~60 k triangles: full-resolution GPU-vs-oracle parity in seconds."""
     return city_scene(num_buildings=36, building_tess=(5, 8), ground_tess=32, num_lamps=24, num_props=12,
                       lamp_tess=(8, 6), num_building_meshes=8, name="small_city")
+
+
+def small_city_scene_env() -> Scene:
+    """small_city_scene under an environment light (procedural_sky): emitters and the environment are both sampled."""
+    scene = small_city_scene()
+    scene.env_map = procedural_sky(64, 32)
+    scene.name = "small_city_env"
+    return scene
+
+
+def env_only_scene() -> Scene:
+    """tiny_city_scene with every emitter switched off, lit by the environment alone: lightInstDist.integral() == 0, so every
+    light sample is an environment sample (optix_restir_di_kernels.cu:87-89)."""
+    scene = tiny_city_scene()
+    scene.materials["hasEmittance"] = 0
+    scene.materials["emittance"] = 0
+    scene.env_map = procedural_sky(48, 24, sun_power=25.0, seed=11)
+    scene.name = "env_only"
+    return scene
 
 
 def tiny_city_scene() -> Scene:

@@ -39,7 +39,7 @@ struct SceneFile {
     std::vector<GfxInstanceDesc> instances;
     std::vector<uint32_t> slots;
     GfxFrameParams defaults;
-    GfxSceneDesc desc;
+    GfxSceneDesc desc = {};
 };
 
 template <typename T>

@@ -92,6 +92,14 @@ typedef struct GfxSceneDesc {
     uint32_t numMaterials;
     uint32_t numInstances;
     uint32_t numInstanceMeshSlots;
+    /* environment light: Scene::envLightTexture + envLightImportanceMap (restir_di_shared.h:221-222), what
+     * loadEnvironmentalTexture (common/common_host.cpp:2658-2711) produces from the -env-texture file.  RGBA fp32 texels of an
+     * equirectangular map, row 0 at theta = 0 (+y), column 0 at phi = 0; the library clamps them to [0, 65504] and builds the
+     * luminance x sin(theta) importance map (RegularConstantContinuousDistribution2D, common_shared.h:283-386).  Sampled with
+     * the reference's sampler (linear filter, clamp addressing) restated in software.  NULL = no environment light. */
+    const float* envTexels;
+    uint32_t envWidth;
+    uint32_t envHeight;
 } GfxSceneDesc;
 
 /* ---- BVH formats (bit-identical to the reference structs) ---------------------------- */
@@ -207,6 +215,11 @@ typedef struct GfxFrameParams {
     uint32_t reuseVisibilityForTemporal;        /* true by default */
     uint32_t reuseVisibilityForSpatiotemporal;  /* false by default */
     float radiusThresholdForSpatialVisReuse;    /* 10 px by default */
+    /* environment light (PerFramePipelineLaunchParameters::envLightPowerCoeff, envLightRotation, enableEnvLight,
+     * restir_di_shared.h:249-250,269): used when the scene has an environment map; probToSampleEnvLight = 0.25 (:6) */
+    uint32_t enableEnvLight;
+    float envLightPowerCoeff;
+    float envLightRotation;
 } GfxFrameParams;
 
 typedef enum GfxSVGFFlags {
@@ -395,6 +408,10 @@ int gfx_light_dist_build(gfx_ctx* ctx, void* stream, uint32_t bufferIndex);
  * [0, 1) writes the key (light-record index, or bit 30 set for sampleLight's probability-0 early outs,
  * restir_di_shared.h:356-409) found by the flattened table and by the three nested DiscreteDistribution1D::sample calls */
 int gfx_light_pick_debug(gfx_ctx* ctx, void* stream, const float* ul, uint32_t n, uint32_t* keysFlat, uint32_t* keysChain);
+/* test hook of the environment light (GfxSceneDesc::envTexels): n DEVICE pairs in, n DEVICE triples out.
+ * op 0: RegularConstantContinuousDistribution2D::sample(u0, u1) -> (u, v, uvPDF); 1: evaluatePDF(u, v) -> (pdf, 0, 0);
+ * 2: the software tex2DLod of the map at (u, v) -> rgb */
+int gfx_env_light_debug(gfx_ctx* ctx, void* stream, int op, const float* in, uint32_t n, float* out);
 /* host read-back of the instance-level distribution for parity: weights/cdf sized numInstances */
 int gfx_light_dist_export(gfx_ctx* ctx, float* instWeights, float* instCdf, float* integral);
 

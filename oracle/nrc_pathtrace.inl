@@ -233,8 +233,11 @@ static void nrcRayGen(orc_frame* f, orc_nrc_frame* n, const GfxFrameParams* p, c
     st.renderingPathEndsWithCache = false;
     st.trainingSuffixEndsWithCache = false;
     st.pathLength = 1;
-    if (gb0.instSlot == 0xFFFFFFFFu)
+    if (gb0.instSlot == 0xFFFFFFFFu) {
+        if (useEnvLight(s, p)) // :323-331: the environment seen directly, (u, v) left in the barycentrics by the miss program
+            st.contribution = p->envLightPowerCoeff * s->env.fetch(bcB, bcC);
         return;
+    }
 
     const InstData &inst = s->instances[gb0.instSlot];
     const MeshData &mesh = s->meshes[gb0.geomInstSlot];
@@ -262,7 +265,7 @@ static void nrcRayGen(orc_frame* f, orc_nrc_frame* n, const GfxFrameParams* p, c
         contribution += alpha * emittance / kPi;
     }
     const BSDF bsdf = setupBsdf(s, mesh.materialSlot);
-    const float3 directContNEE = performNextEventEstimation(s, positionInWorld, vOutLocal, shadingFrame, bsdf, rng, counters);
+    const float3 directContNEE = performNextEventEstimation(s, p, positionInWorld, vOutLocal, shadingFrame, bsdf, rng, counters);
     contribution += alpha * directContNEE;
 
     float3 vInLocal;
@@ -309,13 +312,23 @@ static void nrcExtend(orc_frame* f, orc_nrc_frame* n, const GfxFrameParams* p, s
 
     ++counters->closestRays;
     const HitObject hit = traverseCanonical(s->bvh, st.rayOrg, st.rayDir, 0.0f, std::numeric_limits<float>::max());
-    if (hit.primIndex == UINT32_MAX)
-        return; // miss program without an environment light
+    if (hit.primIndex == UINT32_MAX) { // pathTrace_miss_generic (:625-672)
+        if (useEnvLight(s, p)) {
+            const float3 directContImplicit = evaluateEnvLightOnMiss(s, p, st.rayDir, st.prevDirPDensity, true);
+            st.contribution += st.alpha * directContImplicit;
+            if (st.isTrainingPath && st.prevTrainDataIndex != kInvalidVertexDataIndex) {
+                float* tgt = &n->trainTarget[0][3 * (size_t)st.prevTrainDataIndex];
+                const float3 add = st.prevLocalThroughput * directContImplicit;
+                tgt[0] += add.x; tgt[1] += add.y; tgt[2] += add.z;
+            }
+        }
+        return;
+    }
 
     const InstData &inst = s->instances[s->geomToInst[hit.geomIndex]];
     const MeshData &mesh = s->meshes[s->geomToMesh[hit.geomIndex]];
     SurfacePoint sp;
-    computeSurfacePointAtHit(s, inst, mesh, hit.primIndex, hit.bcB, hit.bcC, &sp);
+    computeSurfacePointAtHit(s, p, inst, mesh, hit.primIndex, hit.bcB, hit.bcC, &sp);
     const GfxMaterialDesc &mat = s->materials[mesh.materialSlot];
 
     const float3 vOut = normalize(-st.rayDir);
@@ -396,7 +409,7 @@ static void nrcExtend(orc_frame* f, orc_nrc_frame* n, const GfxFrameParams* p, s
             vi[c] = f2u(u2f(vi[c]) * recContinueProb);
     }
 
-    const float3 directContNEE = performNextEventEstimation(s, positionInWorld, vOutLocal, shadingFrame, bsdf, st.rng, counters);
+    const float3 directContNEE = performNextEventEstimation(s, p, positionInWorld, vOutLocal, shadingFrame, bsdf, st.rng, counters);
     st.contribution += st.alpha * directContNEE;
 
     float3 vInLocal;

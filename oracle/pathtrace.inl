@@ -4,14 +4,14 @@
 //   performNextEventEstimation     path_tracing/gpu_kernels/optix_pathtracing_kernels.cu:18-71
 //   pathTrace_rayGen_generic       path_tracing/gpu_kernels/optix_pathtracing_kernels.cu:73-216
 //   pathTrace_closestHit_generic   path_tracing/gpu_kernels/optix_pathtracing_kernels.cu:218-300
-//   pathTraceBaseline miss         path_tracing/gpu_kernels/optix_pathtracing_kernels.cu:310-341 (no env light: no-op)
+//   pathTraceBaseline miss         path_tracing/gpu_kernels/optix_pathtracing_kernels.cu:310-341 (environment light, MIS)
 //   computeSurfacePoint<true,false>path_tracing/path_tracing_shared.h:484-580 (closest hit, hypothetical area pdf)
 //   computeSurfacePoint            path_tracing/path_tracing_shared.h:582-621 (first hit from GBuffer0)
 // with the compile-time switches of :12-16: useSolidAngleSampling = false, implicit + explicit light
 // sampling, MIS (power heuristic).  optixTrace -> the restated bvh::traverse (canonical tie-break);
 // optixTransform{Point,Vector,Normal}FromObjectToWorldSpace -> the instance's transform / normalMatrix
-// (OptiX internals, "parity unpinned" like every traversal result).  No bump mapping (1x1 textures),
-// no environment light.
+// (OptiX internals, "parity unpinned" like every traversal result).  No bump mapping (1x1 textures).
+// Environment light (envlight.h) when the scene has a map and params->enableEnvLight is set.
 //
 // RNG draw order per path vertex (PCG32, one state per pixel):
 //   NEE: uLight, u0, u1      BSDF sample: uDir0, uDir1      (first hit)
@@ -59,7 +59,7 @@ static void computeSurfacePointFromGBuffer(const orc_scene* s, const InstData &i
 }
 
 // path_tracing_shared.h:484-580 with computeHypotheticalAreaPDensity = true, useSolidAngleSampling = false
-static void computeSurfacePointAtHit(const orc_scene* s, const InstData &inst, const MeshData &mesh,
+static void computeSurfacePointAtHit(const orc_scene* s, const GfxFrameParams* p, const InstData &inst, const MeshData &mesh,
                                      uint32_t primIndex, float bcB, float bcC, SurfacePoint* sp) {
     const uint32_t i0 = mesh.triangles[3 * primIndex], i1 = mesh.triangles[3 * primIndex + 1], i2 = mesh.triangles[3 * primIndex + 2];
     const Affine xfm = affine(inst.desc.transform);
@@ -90,6 +90,8 @@ static void computeSurfacePointAtHit(const orc_scene* s, const InstData &inst, c
     }
 
     float lightProb = 1.0f;
+    if (useEnvLight(s, p)) // path_tracing_shared.h:540-541
+        lightProb *= (1 - kProbToSampleEnvLight);
     const float instImportance = inst.geomIntegral;
     lightProb *= (pow2(inst.desc.uniformScale) * instImportance) / s->instIntegral;
     lightProb *= mesh.primIntegral / instImportance;
@@ -102,25 +104,64 @@ static void computeSurfacePointAtHit(const orc_scene* s, const InstData &inst, c
     sp->hypAreaPDensity = lightProb / area;
 }
 
+// the miss programs of the path tracers (optix_pathtracing_kernels.cu:310-341; the NRC one :625-650 has the same body):
+// luminance * misWeight of the environment along rayDir, zero without an environment light
+static float3 evaluateEnvLightOnMiss(const orc_scene* s, const GfxFrameParams* p, const float3 &rayDirIn, float prevDirPDensity,
+                                     bool nrcVariant = false) {
+    if (!useEnvLight(s, p))
+        return float3(0.0f);
+    const float3 rayDir = normalize(rayDirIn);
+    float posPhi, theta;
+    toPolarYUp(rayDir, &posPhi, &theta);
+    float phi = posPhi + p->envLightRotation;
+    phi = phi - std::floor(phi / (2 * kPi)) * 2 * kPi;
+    const float2 texCoord(phi / (2 * kPi), theta / kPi);
+    const float3 luminance = p->envLightPowerCoeff * s->env.fetch(texCoord.x, texCoord.y);
+    const float uvPDF = s->env.evaluatePDF(texCoord.x, texCoord.y);
+    const float hypAreaPDensity = uvPDF / (2 * kPi * kPi * dm_sin(theta));
+    // the NRC app's miss program multiplies by probToSampleEnvLight unconditionally (neural_radiance_caching/.../:646)
+    const float lightPDensity = (nrcVariant || s->instIntegral > 0.0f ? kProbToSampleEnvLight : 1.0f) * hypAreaPDensity;
+    const float bsdfPDensity = prevDirPDensity;
+    const float misWeight = pow2(bsdfPDensity) / (pow2(bsdfPDensity) + pow2(lightPDensity));
+    return luminance * misWeight;
+}
+
 struct PathTraceCounters {
     uint64_t closestRays = 0, visibilityRays = 0;
 };
 
 // optix_pathtracing_kernels.cu:18-71
-static float3 performNextEventEstimation(const orc_scene* s, const float3 &shadingPoint, const float3 &vOutLocal,
+static float3 performNextEventEstimation(const orc_scene* s, const GfxFrameParams* p, const float3 &shadingPoint, const float3 &vOutLocal,
                                          const ReferenceFrame &shadingFrame, const BSDF &bsdf, PCG32RNG &rng,
                                          PathTraceCounters* counters) {
     float3 ret(0.0f);
-    const float uLight = rng.getFloat0cTo1o();
-    const float probToSampleCurLightType = 1.0f;
+    float uLight = rng.getFloat0cTo1o();
+    bool selectEnvLight = false;
+    float probToSampleCurLightType = 1.0f;
+    if (useEnvLight(s, p)) { // :27-42
+        if (s->instIntegral > 0.0f) {
+            if (uLight < kProbToSampleEnvLight) {
+                probToSampleCurLightType = kProbToSampleEnvLight;
+                uLight /= probToSampleCurLightType;
+                selectEnvLight = true;
+            }
+            else {
+                probToSampleCurLightType = 1.0f - kProbToSampleEnvLight;
+                uLight = (uLight - kProbToSampleEnvLight) / probToSampleCurLightType;
+            }
+        }
+        else {
+            selectEnvLight = true;
+        }
+    }
     LightSample lightSample;
     float areaPDensity = 0.0f;
     const float u0 = rng.getFloat0cTo1o();
     const float u1 = rng.getFloat0cTo1o();
-    sampleLight(s, uLight, u0, u1, &lightSample, &areaPDensity);
+    sampleLight(s, p, uLight, selectEnvLight, u0, u1, &lightSample, &areaPDensity);
     areaPDensity *= probToSampleCurLightType;
     if (areaPDensity > 0.0f) {
-        float3 shadowRay = lightSample.position - shadingPoint;
+        float3 shadowRay = lightSample.atInfinity ? lightSample.position : (lightSample.position - shadingPoint);
         const float dist2 = sqLength(shadowRay);
         shadowRay /= std::sqrt(dist2);
         const float3 vInLocal = shadingFrame.toLocal(shadowRay);
@@ -175,7 +216,7 @@ static void pathTracePixel(orc_frame* f, const GfxFrameParams* p, const Camera &
                 contribution += alpha * emittance / kPi;
             }
             const BSDF bsdf = setupBsdf(s, mesh->materialSlot);
-            contribution += alpha * performNextEventEstimation(s, positionInWorld, vOutLocal, shadingFrame, bsdf, rng, counters);
+            contribution += alpha * performNextEventEstimation(s, p, positionInWorld, vOutLocal, shadingFrame, bsdf, rng, counters);
 
             float3 vInLocal;
             const float uDir0 = rng.getFloat0cTo1o();
@@ -198,12 +239,14 @@ static void pathTracePixel(orc_frame* f, const GfxFrameParams* p, const Camera &
 
             ++counters->closestRays;
             const HitObject hit = traverseCanonical(s->bvh, rayOrg, rayDir, 0.0f, std::numeric_limits<float>::max());
-            if (hit.primIndex == UINT32_MAX)
-                break; // miss program: no environment light
+            if (hit.primIndex == UINT32_MAX) { // miss program (:310-341): implicit environment light sampling with MIS
+                contribution += alpha * evaluateEnvLightOnMiss(s, p, rayDir, prevDirPDensity);
+                break;
+            }
 
             inst = &s->instances[s->geomToInst[hit.geomIndex]];
             mesh = &s->meshes[s->geomToMesh[hit.geomIndex]];
-            computeSurfacePointAtHit(s, *inst, *mesh, hit.primIndex, hit.bcB, hit.bcC, &sp);
+            computeSurfacePointAtHit(s, p, *inst, *mesh, hit.primIndex, hit.bcB, hit.bcC, &sp);
             const GfxMaterialDesc &mat = s->materials[mesh->materialSlot];
 
             const float3 vOut = normalize(-rayDir);
@@ -229,7 +272,7 @@ static void pathTracePixel(orc_frame* f, const GfxFrameParams* p, const Camera &
             alpha /= continueProb;
 
             const BSDF bsdf = setupBsdf(s, mesh->materialSlot);
-            contribution += alpha * performNextEventEstimation(s, positionInWorld, vOutLocal, shadingFrame, bsdf, rng, counters);
+            contribution += alpha * performNextEventEstimation(s, p, positionInWorld, vOutLocal, shadingFrame, bsdf, rng, counters);
 
             float3 vInLocal;
             const float uDir0 = rng.getFloat0cTo1o();
@@ -240,6 +283,9 @@ static void pathTracePixel(orc_frame* f, const GfxFrameParams* p, const Camera &
             prevDirPDensity = dirPDensity;
         }
         f->rng[pix] = rng.state;
+    }
+    else if (useEnvLight(s, p)) { // :200-207: the environment seen directly; the miss program left (u, v) in the barycentrics
+        contribution = p->envLightPowerCoeff * s->env.fetch(bcB, bcC);
     }
 
     float3 prevColorResult(0.0f);

@@ -101,9 +101,10 @@ static inline LightSample emptyLightSample() { // LightSample(): atInfinity(fals
 }
 
 // build_cell_reservoirs.cu:6-69
-static float3 sampleIntensity(const orc_scene* s, const float3 &cellCenter, const float3 &halfCellSize, float minSquaredDistance,
-                              float uLight, float uPos0, float uPos1, LightSample* lightSample, float* probDensity) {
-    sampleLight(s, uLight, uPos0, uPos1, lightSample, probDensity);
+static float3 sampleIntensity(const orc_scene* s, const GfxFrameParams* p, const float3 &cellCenter, const float3 &halfCellSize,
+                              float minSquaredDistance, float uLight, bool sampleEnvLight, float uPos0, float uPos1,
+                              LightSample* lightSample, float* probDensity) {
+    sampleLight(s, p, uLight, sampleEnvLight, uPos0, uPos1, lightSample, probDensity);
     float dist2 = minSquaredDistance;
     float lpCos = 1;
     const bool isOutsideCell =
@@ -163,13 +164,33 @@ extern "C" void orc_regir_build_cells(orc_frame* f, const GfxFrameParams* p, uin
             Reservoir reservoir;
             reservoir.initialize(emptyLightSample());
             for (uint32_t candIdx = 0; candIdx < numCandidates; ++candIdx) {
-                const float uLight = rng.getFloat0cTo1o();
+                float uLight = rng.getFloat0cTo1o();
+                bool sampleEnvLight = false;
+                float probToSampleCurLightType = 1.0f;
+                if (useEnvLight(s, p)) { // build_cell_reservoirs.cu:120-139
+                    if (s->instIntegral > 0.0f) {
+                        const float prob = std::fmin(std::fmax(kProbToSampleEnvLight * numCandidates - candIdx, 0.0f), 1.0f);
+                        if (uLight < prob) {
+                            probToSampleCurLightType = kProbToSampleEnvLight;
+                            uLight = uLight / prob;
+                            sampleEnvLight = true;
+                        }
+                        else {
+                            probToSampleCurLightType = 1.0f - kProbToSampleEnvLight;
+                            uLight = (uLight - prob) / (1 - prob);
+                        }
+                    }
+                    else {
+                        sampleEnvLight = true;
+                    }
+                }
                 LightSample lightSample = emptyLightSample();
                 float areaPDensity = 0.0f;
                 const float uPos0 = rng.getFloat0cTo1o();
                 const float uPos1 = rng.getFloat0cTo1o();
-                const float3 cont = sampleIntensity(s, cellCenter, halfCellSize, minSquaredDistance, uLight, uPos0, uPos1,
+                const float3 cont = sampleIntensity(s, p, cellCenter, halfCellSize, minSquaredDistance, uLight, sampleEnvLight, uPos0, uPos1,
                                                     &lightSample, &areaPDensity);
+                areaPDensity *= probToSampleCurLightType;
                 const float targetPDensity = convertToWeight(cont);
                 const float weight = targetPDensity / areaPDensity;
                 if (reservoir.update(lightSample, weight, rng.getFloat0cTo1o()))
@@ -367,7 +388,7 @@ static void regirPathTracePixel(orc_frame* f, orc_regir* r, const GfxFrameParams
 
             inst = &s->instances[s->geomToInst[hit.geomIndex]];
             mesh = &s->meshes[s->geomToMesh[hit.geomIndex]];
-            computeSurfacePointAtHit(s, *inst, *mesh, hit.primIndex, hit.bcB, hit.bcC, &sp);
+            computeSurfacePointAtHit(s, p, *inst, *mesh, hit.primIndex, hit.bcB, hit.bcC, &sp);
             sp.hypAreaPDensity = 0.0f; // never written by computeSurfacePoint<false, ...>: see the header of this file
             const GfxMaterialDesc &mat = s->materials[mesh->materialSlot];
 
@@ -403,6 +424,9 @@ static void regirPathTracePixel(orc_frame* f, orc_regir* r, const GfxFrameParams
             prevDirPDensity = dirPDensity;
         }
         f->rng[pix] = rng.state;
+    }
+    else if (useEnvLight(s, p)) { // regir/gpu_kernels/optix_pathtracing_kernels.cu:283-290; the ReGIR ray type's miss program is empty
+        contribution = p->envLightPowerCoeff * s->env.fetch(bcB, bcC);
     }
 
     float3 prevColorResult(0.0f);

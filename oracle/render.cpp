@@ -15,6 +15,7 @@
 #include "oracle.h"
 #include "bvh.h"
 #include "shading.h"
+#include "envlight.h"
 #include <chrono>
 #include <cstdio>
 #include <random>
@@ -50,7 +51,11 @@ struct orc_scene {
     double buildSeconds = 0.0;
     float sceneMin[3], sceneMax[3];
     OrcBuildConfig buildConfig;
+    EnvLight env; // envLightTexture + envLightImportanceMap (restir_di_shared.h:221-222)
 };
+
+// plp.s->envLightTexture && plp.f->enableEnvLight
+static inline bool useEnvLight(const orc_scene* s, const GfxFrameParams* p) { return s->env.present() && p->enableEnvLight; }
 
 // sequential fp32 exclusive scan (stands in for ext/cubd ExclusiveSum)
 static float exclusiveScan(const std::vector<float> &w, std::vector<float> &cdf) {
@@ -178,6 +183,7 @@ extern "C" orc_scene* orc_scene_create(const GfxSceneDesc* d, const OrcBuildConf
         s->instances[i].desc = d->instances[i];
     s->instanceMeshSlots.assign(d->instanceMeshSlots, d->instanceMeshSlots + d->numInstanceMeshSlots);
 
+    buildEnvLight(&s->env, d->envTexels, d->envWidth, d->envHeight);
     s->buildConfig = *cfg;
     rebuildWorld(s, numThreads);
     return s;
@@ -199,6 +205,28 @@ extern "C" int orc_scene_update_instances(orc_scene* s, const GfxInstanceDesc* i
     return 0;
 }
 extern "C" void orc_scene_destroy(orc_scene* s) { delete s; }
+// test hooks of the environment light: op 0 = importance-map sample (u0, u1) -> (u, v, uvPDF), 1 = evaluatePDF(u, v) -> pdf,
+// 2 = texture fetch (u, v) -> rgb; `in` holds n pairs, `out` n triples
+extern "C" int orc_env_query(orc_scene* s, int op, const float* in, uint32_t n, float* out) {
+    if (!s->env.present())
+        return -1;
+    for (uint32_t i = 0; i < n; ++i) {
+        const float a = in[2 * i], b = in[2 * i + 1];
+        float* o = out + 3 * i;
+        if (op == 0) {
+            s->env.sample(a, b, &o[0], &o[1], &o[2]);
+        }
+        else if (op == 1) {
+            o[0] = s->env.evaluatePDF(a, b);
+            o[1] = o[2] = 0.0f;
+        }
+        else {
+            const float3 c = s->env.fetch(a, b);
+            o[0] = c.x; o[1] = c.y; o[2] = c.z;
+        }
+    }
+    return 0;
+}
 extern "C" double orc_scene_build_seconds(orc_scene* s) { return s->buildSeconds; }
 
 extern "C" void orc_bvh_info(orc_scene* s, GfxBvhInfo* info) {
@@ -680,7 +708,7 @@ extern "C" void orc_gbuffer(orc_frame* f, const GfxFrameParams* p, int numThread
                 const float3 pp = -vOut;
                 float posPhi, posTheta;
                 toPolarYUp(pp, &posPhi, &posTheta);
-                const float phi = posPhi + 0.0f; // envLightRotation = 0
+                const float phi = posPhi + p->envLightRotation;
                 float u = phi / (2 * kPi);
                 u -= std::floor(u);
                 const float v = posTheta / kPi;
@@ -727,9 +755,34 @@ extern "C" void orc_gbuffer(orc_frame* f, const GfxFrameParams* p, int numThread
 // ---------------------------------------------------------------------------------------
 static inline float convertToWeight(const float3 &c) { return (c.x + c.y + c.z) / 3; } // restir_di_shared.h:82-85
 
-static void sampleLight(const orc_scene* s, float ul, float u0, float u1, LightSample* lightSample, float* areaPDensity) {
-    // restir_di_shared.h:320-516, sampleEnvLight = false, useSolidAngleSampling = false
+static void sampleLight(const orc_scene* s, const GfxFrameParams* p, float ul, bool sampleEnvLight, float u0, float u1,
+                        LightSample* lightSample, float* areaPDensity) {
+    // restir_di_shared.h:320-516, useSolidAngleSampling = false
     float3 emittance(0.0f);
+    if (sampleEnvLight) { // :330-364
+        float u, v, uvPDF;
+        s->env.sample(u0, u1, &u, &v, &uvPDF);
+        const float phi = 2 * kPi * u;
+        const float theta = kPi * v;
+        float posPhi = phi - p->envLightRotation;
+        posPhi = posPhi - std::floor(posPhi / (2 * kPi)) * 2 * kPi;
+        const float3 direction = fromPolarYUp(posPhi, theta);
+        lightSample->position = direction;
+        lightSample->atInfinity = 1;
+        lightSample->normal = -direction;
+        lightSample->emittance = float3(0.0f); // (left unset by the reference when sin(theta) == 0)
+        // the PDF in texture space -> with respect to area: lim_{l -> inf} uvPDF / (2 pi^2 sin(theta)) / l^2
+        const float sinTheta = dm_sin(theta);
+        if (sinTheta == 0.0f) {
+            *areaPDensity = 0.0f;
+            return;
+        }
+        *areaPDensity = uvPDF / (2 * kPi * kPi * sinTheta);
+        emittance = float3(kPi * p->envLightPowerCoeff);
+        emittance *= s->env.fetch(u, v);
+        lightSample->emittance = emittance;
+        return;
+    }
     float lightProb = 1.0f;
 
     DiscreteDistribution1D lightInstDist{ s->instWeights.data(), s->instCdf.data(), s->instIntegral, (uint32_t)s->instWeights.size() };
@@ -928,13 +981,31 @@ static void performInitialAndTemporalRIS(orc_frame* f, const GfxFrameParams* p, 
     float selectedTargetDensity = 0.0f;
     const uint32_t numCandidates = 1u << p->log2NumCandidateSamples;
     for (uint32_t i = 0; i < numCandidates; ++i) {
-        const float ul = rng.getFloat0cTo1o();
-        const float probToSampleCurLightType = 1.0f;
+        float ul = rng.getFloat0cTo1o();
+        float probToSampleCurLightType = 1.0f;
+        bool sampleEnvLight = false;
+        if (useEnvLight(s, p)) { // :74-90: the first probToSampleEnvLight * numCandidates candidates go to the environment
+            if (s->instIntegral > 0.0f) {
+                const float prob = std::fmin(std::fmax(kProbToSampleEnvLight * numCandidates - i, 0.0f), 1.0f);
+                if (ul < prob) {
+                    probToSampleCurLightType = kProbToSampleEnvLight;
+                    ul = ul / prob;
+                    sampleEnvLight = true;
+                }
+                else {
+                    probToSampleCurLightType = 1.0f - kProbToSampleEnvLight;
+                    ul = (ul - prob) / (1 - prob);
+                }
+            }
+            else {
+                sampleEnvLight = true;
+            }
+        }
         LightSample lightSample;
         float probDensity;
         const float u0 = rng.getFloat0cTo1o();
         const float u1 = rng.getFloat0cTo1o();
-        sampleLight(s, ul, u0, u1, &lightSample, &probDensity);
+        sampleLight(s, p, ul, sampleEnvLight, u0, u1, &lightSample, &probDensity);
         const float3 cont = performDirectLighting<false>(s, positionInWorld, vOutLocal, shadingFrame, bsdf, lightSample);
         probDensity *= probToSampleCurLightType;
         const float targetDensity = convertToWeight(cont);
@@ -1251,6 +1322,10 @@ static void shading(orc_frame* f, const GfxFrameParams* p, const Camera &camera,
                 directCont = performDirectLighting<true>(s, positionInWorld, vOutLocal, shadingFrame, bsdf, lightSample);
         }
         contribution += recPDFEstimate * directCont;
+    }
+    else if (useEnvLight(s, p)) { // :620-629: the environment seen directly
+        const float2 texCoord = decodeTexCoords(gb3.qTexCoord);
+        contribution = p->envLightPowerCoeff * s->env.fetch(texCoord.x, texCoord.y);
     }
 
     float3 prevColorResult(0.0f);

@@ -81,7 +81,7 @@ static inline LightSample lightSampleOf(const PreSampledLight &l) {
 }
 
 // per_pixel_ris.cu:6-40
-static void performLightPreSampling(orc_frame* f, int numThreads) {
+static void performLightPreSampling(orc_frame* f, const GfxFrameParams* p, int numThreads) {
     const orc_scene* s = f->scene;
     orc_rearch* r = rearchState(f);
 #pragma omp parallel for schedule(static) num_threads(numThreads)
@@ -93,13 +93,26 @@ static void performLightPreSampling(orc_frame* f, int numThreads) {
         ls.normal = float3(0.0f);
         ls.atInfinity = 0;
         float areaPDensity = 0.0f;
+        // :12-28: the first probToSampleEnvLight * lightSubsetSize lights of every subset come from the environment
+        float probToSampleCurLightType = 1.0f;
+        bool sampleEnvLight = false;
+        if (useEnvLight(s, p)) {
+            if (s->instIntegral > 0.0f) {
+                const uint32_t indexInSubset = (uint32_t)i % kLightSubsetSize;
+                sampleEnvLight = indexInSubset < kProbToSampleEnvLight * kLightSubsetSize;
+                probToSampleCurLightType = sampleEnvLight ? kProbToSampleEnvLight : (1 - kProbToSampleEnvLight);
+            }
+            else {
+                sampleEnvLight = true;
+            }
+        }
         const float ul = rng.getFloat0cTo1o();
         const float u0 = rng.getFloat0cTo1o();
         const float u1 = rng.getFloat0cTo1o();
-        sampleLight(s, ul, u0, u1, &ls, &areaPDensity);
+        sampleLight(s, p, ul, sampleEnvLight, u0, u1, &ls, &areaPDensity);
         PreSampledLight &o = r->preSampledLights[i];
         o.emittance[0] = ls.emittance.x; o.emittance[1] = ls.emittance.y; o.emittance[2] = ls.emittance.z;
-        o.areaPDensity = areaPDensity * 1.0f; // probToSampleCurLightType
+        o.areaPDensity = areaPDensity * probToSampleCurLightType;
         o.position[0] = ls.position.x; o.position[1] = ls.position.y; o.position[2] = ls.position.z;
         o.atInfinity = ls.atInfinity;
         o.normal[0] = ls.normal.x; o.normal[1] = ls.normal.y; o.normal[2] = ls.normal.z;
@@ -501,6 +514,10 @@ static void shadeAndResample(orc_frame* f, const GfxFrameParams* p, const Camera
         f->reservoirInfo[curResIndex][pix] = GB1{ recPDFEstimate, selectedTargetDensity };
         f->rng[pix] = rng.state;
     }
+    else if (useEnvLight(s, p)) { // optix_restir_di_rearch_kernels.cu:648-656
+        const float2 texCoord = decodeTexCoords(gb3.qTexCoord);
+        contribution = p->envLightPowerCoeff * s->env.fetch(texCoord.x, texCoord.y);
+    }
 
     float3 prevColorResult(0.0f);
     if (p->numAccumFrames > 0)
@@ -517,7 +534,7 @@ static uint64_t restirRearch(orc_frame* f, const GfxFrameParams* p, int pass, in
     const uint32_t W = f->W, H = f->H;
     const bool T = p->enableTemporalReuse != 0, S = p->enableSpatialReuse != 0, U = p->useUnbiasedEstimator != 0;
     if (pass == GFX_RESTIR_PRESAMPLE_LIGHTS) {
-        performLightPreSampling(f, numThreads);
+        performLightPreSampling(f, p, numThreads);
         return 0;
     }
     rearchState(f);

@@ -91,6 +91,8 @@ def lib() -> C.CDLL:
         L.orc_svgf_buffer_ptr.restype = vp
         L.orc_svgf_buffer_ptr.argtypes = [vp, C.c_int, C.c_uint32, C.POINTER(C.c_size_t)]
         L.orc_svgf_pass.argtypes = [vp, C.POINTER(abi.GfxFrameParams), C.c_int, C.c_uint32, C.c_int]
+        L.orc_env_query.restype = C.c_int
+        L.orc_env_query.argtypes = [vp, C.c_int, vp, C.c_uint32, vp]
         L.orc_rays_traced.restype = C.c_ulonglong
         L.orc_rays_traced.argtypes = [C.c_int]
         L.orc_nrc_create.restype = vp
@@ -140,6 +142,14 @@ class OracleScene:
 
     def __del__(self):
         self.close()
+
+    def env_query(self, op: int, pairs: np.ndarray) -> np.ndarray:
+        """environment light hooks: op 0 sample(u0, u1) -> (u, v, uvPDF), 1 evaluatePDF(u, v), 2 fetch(u, v) -> rgb"""
+        a = np.ascontiguousarray(pairs, dtype=np.float32).reshape(-1, 2)
+        out = np.zeros((a.shape[0], 3), dtype=np.float32)
+        rc = lib().orc_env_query(self.h, op, a.ctypes.data_as(C.c_void_p), a.shape[0], out.ctypes.data_as(C.c_void_p))
+        assert rc == 0, "scene has no environment map"
+        return out
 
     def update_instances(self, instance_descs):
         """new instance transforms: rebuilds the world-space SBVH and the light distributions"""

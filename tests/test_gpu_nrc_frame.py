@@ -50,7 +50,8 @@ def _compare_pathtrace(ctx, oframe, p, tag):
     return ntrain, has_query, suffix_query
 
 
-@pytest.mark.parametrize("max_path_length,scene_name", [(5, "small_city_scene"), (0, "small_city_scene"), (5, "small_interior_scene")])
+@pytest.mark.parametrize("max_path_length,scene_name", [(5, "small_city_scene"), (0, "small_city_scene"), (5, "small_interior_scene"),
+                                                        (5, "small_city_scene_env")])
 def test_nrc_frames_bit_exact(gfx_ctx, oracle, max_path_length, scene_name):
     scene = getattr(scenes, scene_name)()
     w, h = 192, 108

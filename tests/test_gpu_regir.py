@@ -18,9 +18,11 @@ def _same(got, want, tag):
                              f"{got[tuple(bad[0])]} vs {want[tuple(bad[0])]}")
 
 
-@pytest.mark.parametrize("grid,randomize", [((8, 4, 8), True), ((5, 3, 6), False)])
-def test_regir_frames_bit_exact(gfx_ctx, oracle, grid, randomize):
-    scene = scenes.small_city_scene()
+@pytest.mark.parametrize("grid,randomize,scene_name", [((8, 4, 8), True, "small_city_scene"), ((5, 3, 6), False, "small_city_scene"),
+                                                       ((8, 4, 8), True, "small_city_scene_env")])
+def test_regir_frames_bit_exact(gfx_ctx, oracle, grid, randomize, scene_name):
+    # small_city_scene_env: the cell reservoirs also stream environment-light candidates (build_cell_reservoirs.cu:120-139)
+    scene = getattr(scenes, scene_name)()
     w, h = 160, 90
     gfx_ctx.upload_scene(scene)
     gfx_ctx.build_bvh()

@@ -49,7 +49,11 @@ def test_light_distributions(gfx_ctx, oracle):
 
 
 @pytest.mark.parametrize("unbiased,scene_name", [(False, "small_city_scene"), (True, "small_city_scene"),
-                                                 (False, "small_interior_scene")])
+                                                 (False, "small_interior_scene"),
+                                                 # environment light: importance-map candidates, atInfinity samples through
+                                                 # temporal / spatial reuse, the environment behind miss pixels
+                                                 (False, "small_city_scene_env"), (True, "small_city_scene_env"),
+                                                 (False, "env_only_scene")])
 def test_restir_three_frames_bit_exact(gfx_ctx, oracle, unbiased, scene_name):
     # small_interior_scene: config 3's ingredients - a closed room, 96 two-triangle emitters, SimplePBR materials
     # (common/common_device.cuh:767-776, 806-826)

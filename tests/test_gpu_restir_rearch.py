@@ -67,6 +67,13 @@ def test_rearch_biased_spatiotemporal(gfx_ctx, oracle):
     assert rays < 3.0
 
 
+@pytest.mark.parametrize("unbiased", [False, True])
+def test_rearch_with_environment_light(gfx_ctx, oracle, unbiased):
+    """the first quarter of every presampled light subset comes from the environment's importance map (per_pixel_ris.cu:12-28);
+    miss pixels show the environment"""
+    _run(gfx_ctx, oracle, scenes.small_city_scene_env(), 160, 96, 3, lambda p: dict(temporal=True, spatial=True, unbiased=unbiased))
+
+
 def test_rearch_unbiased_moving_camera_random_neighbors(gfx_ctx, oracle):
     def configure(p):
         p.useLowDiscrepancyNeighbors = 0
