@@ -269,6 +269,7 @@ GFX_D void neeRegir(const DevScene &s, const DevRegir &rg, const f3 &positionInW
     float sumWeights = 0.0f;
     uint32_t combinedStreamLength = 0;
     f3 selectedContribution(0.0f), selectedPosition(0.0f);
+    uint32_t selectedAtInfinity = 0;
     float selectedTargetPDensity = 0.0f;
     const float4* slots = rg.slots[rg.bufferIndex];
     for (uint32_t i = 0; i < numResampling; ++i) {
@@ -295,6 +296,7 @@ GFX_D void neeRegir(const DevScene &s, const DevRegir &rg, const f3 &positionInW
         if (rng.getFloat0cTo1o() < weight / sumWeights) {
             selectedContribution = cont;
             selectedPosition = ls.position;
+            selectedAtInfinity = ls.atInfinity;
             selectedTargetPDensity = targetPDensity;
         }
     }
@@ -313,9 +315,12 @@ GFX_D void neeRegir(const DevScene &s, const DevRegir &rg, const f3 &positionInW
             out->directContNEE = nee;
         }
         else {
-            f3 shadowRayDir = selectedPosition - positionInWorld; // evaluateVisibility (regir_shared.h:544-566)
-            const float dist = sqrtf(sqLength(shadowRayDir));
+            // evaluateVisibility (regir_shared.h:544-566); an environment sample is a direction, 1e+10 away
+            f3 shadowRayDir = selectedAtInfinity ? selectedPosition : (selectedPosition - positionInWorld);
+            float dist = sqrtf(sqLength(shadowRayDir));
             shadowRayDir /= dist;
+            if (selectedAtInfinity)
+                dist = 1e+10f;
             out->directContNEE = cont * (0.0f * recProbDensityEstimate);
             out->wantShadow = true;
             out->shadowDir = shadowRayDir;
