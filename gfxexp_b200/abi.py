@@ -35,12 +35,17 @@ class GfxInstanceDesc(C.Structure):
                 ("uniformScale", c_f), ("firstMeshSlot", c_u32), ("numMeshSlots", c_u32)]
 
 
+class GfxTextureDesc(C.Structure):
+    _fields_ = [("texels", C.POINTER(c_f)), ("width", c_u32), ("height", c_u32)]
+
+
 class GfxSceneDesc(C.Structure):
     _fields_ = [("meshes", C.POINTER(GfxMeshDesc)), ("materials", C.POINTER(GfxMaterialDesc)),
                 ("instances", C.POINTER(GfxInstanceDesc)), ("instanceMeshSlots", C.POINTER(c_u32)),
                 ("numMeshes", c_u32), ("numMaterials", c_u32), ("numInstances", c_u32),
                 ("numInstanceMeshSlots", c_u32),
-                ("envTexels", C.POINTER(c_f)), ("envWidth", c_u32), ("envHeight", c_u32)]
+                ("envTexels", C.POINTER(c_f)), ("envWidth", c_u32), ("envHeight", c_u32),
+                ("textures", C.POINTER(GfxTextureDesc)), ("materialTextures", C.POINTER(c_u32)), ("numTextures", c_u32)]
 
 
 class GfxBvhInfo(C.Structure):
@@ -184,6 +189,19 @@ class SceneArrays:
             assert self.env.ndim == 3 and self.env.shape[2] == 4
             self.desc.envTexels = self.env.ctypes.data_as(C.POINTER(c_f))
             self.desc.envHeight, self.desc.envWidth = self.env.shape[0], self.env.shape[1]
+        textures = getattr(scene, "textures", None)  # list of float32 [H, W, 4] images, already decoded to linear floats
+        if textures:
+            self.textures = [np.ascontiguousarray(t, dtype=np.float32) for t in textures]
+            self.texture_descs = (GfxTextureDesc * len(self.textures))()
+            for d, t in zip(self.texture_descs, self.textures):
+                assert t.ndim == 3 and t.shape[2] == 4
+                d.texels = t.ctypes.data_as(C.POINTER(c_f))
+                d.height, d.width = t.shape[0], t.shape[1]
+            self.material_textures = np.ascontiguousarray(scene.material_textures, dtype=np.uint32).reshape(-1, 4)
+            assert self.material_textures.shape[0] == mats.shape[0]
+            self.desc.textures = C.cast(self.texture_descs, C.POINTER(GfxTextureDesc))
+            self.desc.materialTextures = self.material_textures.ctypes.data_as(C.POINTER(c_u32))
+            self.desc.numTextures = len(self.textures)
 
 
 def make_instance_descs(instances):

@@ -15,6 +15,7 @@ void SceneState::release() {
     cudaFree(primWeights); cudaFree(primCdf); cudaFree(geomWeights); cudaFree(geomCdf);
     cudaFree(instWeights); cudaFree(instCdf); cudaFree(instIntegral);
     cudaFree(primProb); cudaFree(geomProb); cudaFree(instProb); cudaFree(lightTris); cudaFree(lightTriBase); cudaFree(emissiveGeoms); cudaFree(instGuide); cudaFree(primGuide);
+    cudaFree(texPool); cudaFree(texTable); cudaFree(materialTextures);
     cudaFree(envTexels); cudaFree(envPdf); cudaFree(envCdf); cudaFree(envTopPdf); cudaFree(envTopCdf);
     cudaFree(pickGuide); cudaFree(normalMats); cudaFree(pickPieces); cudaFree(pickKeyAt); cudaFree(pickBoundaries); cudaFree(pickCounters); cudaFree(pickSortTemp);
     if (pickFlagsHost) cudaFreeHost(pickFlagsHost);
@@ -157,6 +158,9 @@ DevScene gfx_ctx::devScene() const {
     d.bvh.leafTris = bvh.leafTris;
     d.bvh.numNodes = bvh.numNodes;
     d.bvh.overflowFlag = bvh.overflowFlag;
+    d.texPool = scene.texPool;
+    d.texTable = scene.texTable;
+    d.materialTextures = scene.materialTextures;
     d.env.texels = scene.envTexels;
     d.env.pdf = scene.envPdf;
     d.env.cdf = scene.envCdf;
@@ -419,6 +423,9 @@ int gfx_scene_upload(gfx_ctx* ctx, const GfxSceneDesc* sd) {
     const int envRc = uploadEnvLight(ctx, sd->envTexels, sd->envWidth, sd->envHeight);
     if (envRc != GFX_OK)
         return envRc;
+    const int texRc = uploadTextures(ctx, sd);
+    if (texRc != GFX_OK)
+        return texRc;
     S.uploaded = true;
     return GFX_OK;
 }

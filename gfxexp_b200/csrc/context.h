@@ -41,6 +41,10 @@ struct SceneState {
     // flattened light pick (scene.cuh, lights.cu): tables + the scratch its stream-ordered rebuild needs
     float4* pickGuide = nullptr;           // 2 x kPickGuideSize
     float4* normalMats = nullptr;          // kNormalMatStride x numInstances
+    // image textures of the materials (lights.cu uploadTextures)
+    float4* texPool = nullptr;
+    uint4* texTable = nullptr;
+    uint4* materialTextures = nullptr;
     // environment light (lights.cu uploadEnvLight): texels + the importance map's distributions
     float4* envTexels = nullptr;
     float* envPdf = nullptr;
@@ -264,6 +268,7 @@ int resetVisibilityQueue(gfx_ctx* ctx, cudaStream_t stream);
 int traceVisibilityQueue(gfx_ctx* ctx, cudaStream_t stream);
 int buildLightDistributions(gfx_ctx* ctx, cudaStream_t stream, uint32_t bufferIndex);
 int uploadEnvLight(gfx_ctx* ctx, const float* rgba, uint32_t width, uint32_t height);
+int uploadTextures(gfx_ctx* ctx, const GfxSceneDesc* sd);
 int debugEnvLight(gfx_ctx* ctx, cudaStream_t stream, int op, const float* dIn, uint32_t n, float* dOut);
 int debugLightPick(gfx_ctx* ctx, cudaStream_t stream, const float* dUl, uint32_t n, uint32_t* dFlat, uint32_t* dChain);
 size_t lightPickSortTempBytes(uint32_t capacity);

@@ -11,6 +11,7 @@
 // 128-byte row segments.
 #include "traverse.cuh"
 #include "shading.cuh"
+#include "lighting.cuh"
 #include "context.h"
 
 namespace gfx {
@@ -104,9 +105,7 @@ GFX_D uint32_t gbufferPixel(const DevScene &scene, const DevFrame &frame, const 
         qGeometricNormalInWorld = encodeVector(geometricNormalInWorld);
         qTexCoord = encodeTexCoords(texCoord);
 
-        const GfxMaterialDesc* mat = scene.materials + matSlot;
-        BSDF bsdf;
-        bsdf.setup(mat->bsdfType, mat->p0, mat->p1, mat->p2);
+        const BSDF bsdf = setupBsdf(scene, matSlot, texCoord);
         const ReferenceFrame shadingFrame(shadingNormalInWorld, texCoord0DirInWorld);
         const f3 vOut = -direction;
         const f3 vOutLocal = shadingFrame.toLocal(normalize(vOut));

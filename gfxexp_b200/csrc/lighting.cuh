@@ -548,7 +548,52 @@ GFX_D f3 performDirectLighting(const DevScene &s, const f3 &shadingPoint, const 
     return f3(0.0f);
 }
 
-GFX_D BSDF setupBsdf(const DevScene &s, uint32_t matSlot) {
+// tex2DLod<float4>(materialTexture, u, v, 0) with the reference's material samplers (common_host.cpp:1462-1481: linear filter,
+// repeat addressing) in software: u -> frac(u), xB = frac(u) W - 0.5, i = floor(xB) and i + 1 wrapped modulo W, the fraction kept
+// with 8 fractional bits, the four texels blended in fp32 (the same arithmetic as envFetch, other addressing mode)
+static __device__ __noinline__ float4 textureFetchRepeat(const float4* texels, uint32_t W, uint32_t H, float u, float v) {
+    const float xB = (u - floorf(u)) * W - 0.5f, yB = (v - floorf(v)) * H - 0.5f;
+    const float fx = floorf(xB), fy = floorf(yB);
+    const float a = floorf((xB - fx) * 256.0f + 0.5f) * (1.0f / 256.0f);
+    const float b = floorf((yB - fy) * 256.0f + 0.5f) * (1.0f / 256.0f);
+    const int ix = dm_f2int(fx), iy = dm_f2int(fy); // -1 .. W - 1
+    const uint32_t x0 = ix < 0 ? W - 1 : (uint32_t)ix, x1 = (uint32_t)(ix + 1) >= W ? 0u : (uint32_t)(ix + 1);
+    const uint32_t y0 = iy < 0 ? H - 1 : (uint32_t)iy, y1 = (uint32_t)(iy + 1) >= H ? 0u : (uint32_t)(iy + 1);
+    const float4 t00 = __ldg(texels + (size_t)y0 * W + x0), t10 = __ldg(texels + (size_t)y0 * W + x1);
+    const float4 t01 = __ldg(texels + (size_t)y1 * W + x0), t11 = __ldg(texels + (size_t)y1 * W + x1);
+    const float w00 = (1 - a) * (1 - b), w10 = a * (1 - b), w01 = (1 - a) * b, w11 = a * b;
+    return make_float4(w00 * t00.x + w10 * t10.x + w01 * t01.x + w11 * t11.x, w00 * t00.y + w10 * t10.y + w01 * t01.y + w11 * t11.y,
+                       w00 * t00.z + w10 * t10.z + w01 * t01.z + w11 * t11.z, w00 * t00.w + w10 * t10.w + w01 * t01.w + w11 * t11.w);
+}
+// BSDF::setup(mat, texCoord, 0.0f) (common_device.cuh:376-385, 778-826): the material's constants, or its image textures at
+// texCoord.  The textured form is out of line (and takes the tables as plain pointers): a scene without image textures runs
+// exactly the code it ran before they existed.
+static __device__ __noinline__ BSDF setupBsdfTextured(const GfxMaterialDesc* materials, const uint4* materialTextures, const uint4* texTable,
+                                                      const float4* texPool, uint32_t matSlot, float tu, float tv) {
+    const GfxMaterialDesc* m = materials + matSlot;
+    const uint4 tex = __ldg(materialTextures + matSlot);
+    float p0[3] = { m->p0[0], m->p0[1], m->p0[2] }, p1[3] = { m->p1[0], m->p1[1], m->p1[2] }, p2 = m->p2;
+    if (tex.x != 0xFFFFFFFFu) {
+        const uint4 d = __ldg(texTable + tex.x);
+        const float4 t = textureFetchRepeat(texPool + d.x, d.y, d.z, tu, tv);
+        p0[0] = t.x; p0[1] = t.y; p0[2] = t.z;
+    }
+    if (tex.y != 0xFFFFFFFFu) {
+        const uint4 d = __ldg(texTable + tex.y);
+        const float4 t = textureFetchRepeat(texPool + d.x, d.y, d.z, tu, tv);
+        p1[0] = t.x; p1[1] = t.y; p1[2] = t.z;
+    }
+    if (tex.z != 0xFFFFFFFFu) {
+        const uint4 d = __ldg(texTable + tex.z);
+        p2 = textureFetchRepeat(texPool + d.x, d.y, d.z, tu, tv).x;
+    }
+    BSDF b;
+    b.setup(m->bsdfType, p0, p1, p2);
+    return b;
+}
+GFX_D BSDF setupBsdf(const DevScene &s, uint32_t matSlot, const f2 &texCoord) {
+    if (s.materialTextures)
+        return setupBsdfTextured(s.materials, s.materialTextures, s.texTable, s.texPool, matSlot, texCoord.x, texCoord.y);
     const GfxMaterialDesc* m = s.materials + matSlot;
     BSDF b;
     b.setup(m->bsdfType, m->p0, m->p1, m->p2);

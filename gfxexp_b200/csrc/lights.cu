@@ -571,6 +571,48 @@ int uploadEnvLight(gfx_ctx* ctx, const float* rgba, uint32_t width, uint32_t hei
     return GFX_OK;
 }
 
+// image textures of the materials: one pool of texels, a table of (offset, width, height) and the per-material indices
+int uploadTextures(gfx_ctx* ctx, const GfxSceneDesc* sd) {
+    SceneState &S = ctx->scene;
+    if (!sd->materialTextures || !sd->numTextures)
+        return GFX_OK;
+    if (!sd->textures)
+        return GFX_ERR_INVALID_ARGUMENT;
+    std::vector<uint4> table(sd->numTextures);
+    size_t total = 0;
+    for (uint32_t t = 0; t < sd->numTextures; ++t) {
+        const GfxTextureDesc &d = sd->textures[t];
+        if (!d.texels || !d.width || !d.height || total + (size_t)d.width * d.height > 0xFFFFFFFFull) {
+            ctx->setError("gfx_scene_upload: empty or oversized texture");
+            return GFX_ERR_INVALID_ARGUMENT;
+        }
+        table[t] = make_uint4((uint32_t)total, d.width, d.height, 0u);
+        total += (size_t)d.width * d.height;
+    }
+    std::vector<uint4> perMaterial(sd->numMaterials);
+    for (uint32_t m = 0; m < sd->numMaterials; ++m) {
+        const uint32_t* k = sd->materialTextures + 4 * (size_t)m;
+        for (int c = 0; c < 4; ++c)
+            if (k[c] != 0xFFFFFFFFu && k[c] >= sd->numTextures) {
+                ctx->setError("gfx_scene_upload: material texture index out of range");
+                return GFX_ERR_INVALID_ARGUMENT;
+            }
+        if (k[3] != 0xFFFFFFFFu) {
+            ctx->setError("gfx_scene_upload: textured emittance is not supported (light sampling reads constant emittances)");
+            return GFX_ERR_UNSUPPORTED;
+        }
+        perMaterial[m] = make_uint4(k[0], k[1], k[2], k[3]);
+    }
+    GFX_CUDA(ctx, cudaMalloc((void**)&S.texPool, total * 16));
+    for (uint32_t t = 0; t < sd->numTextures; ++t)
+        GFX_CUDA(ctx, cudaMemcpy(S.texPool + table[t].x, sd->textures[t].texels, (size_t)table[t].y * table[t].z * 16, cudaMemcpyHostToDevice));
+    GFX_CUDA(ctx, cudaMalloc((void**)&S.texTable, table.size() * 16));
+    GFX_CUDA(ctx, cudaMemcpy(S.texTable, table.data(), table.size() * 16, cudaMemcpyHostToDevice));
+    GFX_CUDA(ctx, cudaMalloc((void**)&S.materialTextures, perMaterial.size() * 16));
+    GFX_CUDA(ctx, cudaMemcpy(S.materialTextures, perMaterial.data(), perMaterial.size() * 16, cudaMemcpyHostToDevice));
+    return GFX_OK;
+}
+
 // test hook (gfx_env_light_debug): the device-side importance-map sampler, its density and the software texture fetch
 __global__ void k_envDebug(DevEnvLight env, int op, const float2* in, uint32_t n, float* out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -342,7 +342,7 @@ __global__ void GFX_BOUNCE_BOUNDS k_nrcFirstHit(DevScene s, DevFrame f, DevFrame
             radiance = f3(0.0f);
             if (vOutLocal.z > 0 && mat->hasEmittance)
                 radiance += alpha * f3(mat->emittance[0], mat->emittance[1], mat->emittance[2]) / kPi;
-            const BSDF bsdf = setupBsdf(s, mesh.materialSlot);
+            const BSDF bsdf = setupBsdfAtHit(s, mesh, gb0.z, bcB, bcC);
             shadeVertex(s, positionInWorld, vOutLocal, shadingFrame, bsdf, rng, alpha, &radiance, &v);
             f.rng[pix] = rng.state;
             ps.alphaPdf[pix] = make_float4(v.alpha.x, v.alpha.y, v.alpha.z, v.dirPDensity);
@@ -489,7 +489,7 @@ __global__ void GFX_BOUNCE_BOUNDS k_nrcBounce(DevScene s, DevFrame f, DevFramePa
                     recContinueProb = 1.0f / continueProb;
                 }
 
-                const BSDF bsdf = setupBsdf(s, mesh.materialSlot);
+                const BSDF bsdf = setupBsdfAtHit(s, mesh, hit.y, __uint_as_float(hit.z), __uint_as_float(hit.w));
 
                 // termination into the cache by the spread heuristic (:474-531)
                 bool endsWithCache = pow2f(curSqrtPathSpread) > kPathTerminationFactor * primaryPathSpread;

@@ -96,7 +96,7 @@ __global__ void GFX_BOUNCE_BOUNDS k_ptFirstHit(DevScene s, DevFrame f, DevFrameP
             radiance = f3(0.0f);
             if (vOutLocal.z > 0 && mat->hasEmittance)
                 radiance += alpha * f3(mat->emittance[0], mat->emittance[1], mat->emittance[2]) / kPi;
-            const BSDF bsdf = setupBsdf(s, mesh.materialSlot);
+            const BSDF bsdf = setupBsdfAtHit(s, mesh, gb0.z, bcB, bcC);
             shadeVertexVariant<REGIR>(s, rg, p, positionInWorld, vOutLocal, shadingFrame, bsdf, rng, alpha, 1u, &radiance, &v);
             f.rng[pix] = rng.state;
             ps.alphaPdf[pix] = make_float4(v.alpha.x, v.alpha.y, v.alpha.z, v.dirPDensity);
@@ -174,7 +174,7 @@ __global__ void GFX_BOUNCE_BOUNDS k_ptBounce(DevScene s, DevFrame f, DevFramePar
                 const float continueProb = fminf(sRGB_calcLuminance(alpha) / initImportance, 1.0f);
                 if (!(rng.getFloat0cTo1o() >= continueProb || maxLengthTerminate)) {
                     alpha /= continueProb;
-                    const BSDF bsdf = setupBsdf(s, mesh.materialSlot);
+                    const BSDF bsdf = setupBsdfAtHit(s, mesh, hit.y, __uint_as_float(hit.z), __uint_as_float(hit.w));
                     shadeVertexVariant<REGIR>(s, rg, p, positionInWorld, vOutLocal, shadingFrame, bsdf, rng, alpha, round + 2, &radiance, &v);
                     ps.alphaPdf[pix] = make_float4(v.alpha.x, v.alpha.y, v.alpha.z, v.dirPDensity);
                     alive = true;

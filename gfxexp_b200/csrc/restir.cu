@@ -62,7 +62,7 @@ GFX_D bool risPixel(const DevScene &s, const DevFrame &f, const DevFrameParams &
     const f3 shadingTangentInWorld = decodeVector(gb3.y);
     const ReferenceFrame shadingFrame(shadingNormalInWorld, shadingTangentInWorld);
     const f3 vOutLocal = shadingFrame.toLocal(vOut);
-    const BSDF bsdf = setupBsdf(s, gb3.w);
+    const BSDF bsdf = setupBsdf(s, gb3.w, decodeTexCoords(gb3.z));
 
     const uint32_t curResIndex = p.currentReservoirIndex;
     Reservoir reservoir;
@@ -284,7 +284,7 @@ GFX_D bool risPixel(const DevScene &s, const DevFrame &f, const DevFrameParams &
                 const f3 nbVOut = normalize(p.prevCamera.position - nbPositionInWorld);
                 const float nbFrontHit = dot(nbVOut, nbGeometricNormalInWorld) >= 0.0f ? 1.0f : -1.0f;
                 nbPositionInWorld = offsetRayOrigin(nbPositionInWorld, nbFrontHit * nbGeometricNormalInWorld);
-                const BSDF nbBsdf = setupBsdf(s, nbGb3.w);
+                const BSDF nbBsdf = setupBsdf(s, nbGb3.w, decodeTexCoords(nbGb3.z));
                 const ReferenceFrame nbShadingFrame(decodeVector(nbGb3.x), decodeVector(nbGb3.y));
                 const f3 nbVOutLocal = nbShadingFrame.toLocal(nbVOut);
                 const Reservoir neighbor = loadReservoir(f, prevResIndex, nbPix);
@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(64) k_spatialRIS(DevScene s, DevFrame f, DevFr
 
     const ReferenceFrame shadingFrame(decodeVector(gb3.x), decodeVector(gb3.y));
     const f3 vOutLocal = shadingFrame.toLocal(vOut);
-    const BSDF bsdf = setupBsdf(s, gb3.w);
+    const BSDF bsdf = setupBsdf(s, gb3.w, decodeTexCoords(gb3.z));
 
     const uint32_t srcResIndex = p.currentReservoirIndex;
     const uint32_t dstResIndex = (srcResIndex + 1) % 2;
@@ -459,7 +459,7 @@ __global__ void __launch_bounds__(64) k_spatialRIS(DevScene s, DevFrame f, DevFr
                     const f3 nbVOut = normalize(p.prevCamera.position - nbPositionInWorld);
                     const float nbFrontHit = dot(nbVOut, nbGeometricNormalInWorld) >= 0.0f ? 1.0f : -1.0f;
                     nbPositionInWorld = offsetRayOrigin(nbPositionInWorld, nbFrontHit * nbGeometricNormalInWorld);
-                    const BSDF nbBsdf = setupBsdf(s, nbGb3.w);
+                    const BSDF nbBsdf = setupBsdf(s, nbGb3.w, decodeTexCoords(nbGb3.z));
                     const ReferenceFrame nbShadingFrame(decodeVector(nbGb3.x), decodeVector(nbGb3.y));
                     const f3 nbVOutLocal = nbShadingFrame.toLocal(nbVOut);
                     const Reservoir neighbor = loadReservoir(f, srcResIndex, nbPix);
@@ -549,7 +549,7 @@ __global__ void __launch_bounds__(64) k_shading(DevScene s, DevFrame f, DevFrame
         const ReferenceFrame shadingFrame(decodeVector(gb3.x), decodeVector(gb3.y));
         const f3 vOutLocal = shadingFrame.toLocal(vOut);
         const GfxMaterialDesc* mat = s.materials + gb3.w;
-        const BSDF bsdf = setupBsdf(s, gb3.w);
+        const BSDF bsdf = setupBsdf(s, gb3.w, decodeTexCoords(gb3.z));
 
         const uint32_t curResIndex = p.currentReservoirIndex;
         const Reservoir reservoir = loadReservoir(f, curResIndex, pix);

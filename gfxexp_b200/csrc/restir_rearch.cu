@@ -141,7 +141,7 @@ GFX_D RearchShadingPoint reconstructShadingPoint(const DevScene &s, const DevFra
     sp.positionInWorld = offsetRayOrigin(positionInWorld, frontHit * geometricNormalInWorld);
     sp.shadingFrame = ReferenceFrame(decodeVector(g3.x), decodeVector(g3.y));
     sp.vOutLocal = sp.shadingFrame.toLocal(vOut);
-    sp.bsdf = setupBsdf(s, g3.w);
+    sp.bsdf = setupBsdf(s, g3.w, decodeTexCoords(g3.z));
     return sp;
 }
 

@@ -140,6 +140,11 @@ struct DevScene {
     unsigned long long* rayCounter;  // frame statistics: rays traced (primary + visibility)
     DevBvh bvh;
     DevEnvLight env;
+    // image textures of the materials: texTable[t] = (first texel in texPool, width, height, -); materialTextures[m] = the
+    // textures of p0 / p1 / p2 / emittance or 0xFFFFFFFF; nullptr when no material is textured
+    const float4* texPool;
+    const uint4* texTable;
+    const uint4* materialTextures;
 };
 
 struct DevFrame {

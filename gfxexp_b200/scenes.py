@@ -53,6 +53,8 @@ class Scene:
     fov_y: float
     name: str = "scene"
     env_map: Optional[np.ndarray] = None  # float32 [H, W, 4] equirectangular environment map (GfxSceneDesc::envTexels) or None
+    textures: Optional[List[np.ndarray]] = None       # float32 [H, W, 4] images, linear (after sRGB decode)
+    material_textures: Optional[np.ndarray] = None    # uint32 [numMaterials, 4]: texture of p0, p1, p2, emittance or 0xFFFFFFFF
 
     @property
     def num_triangles(self) -> int:
@@ -479,6 +481,44 @@ def small_city_scene_env() -> Scene:
     scene = small_city_scene()
     scene.env_map = procedural_sky(64, 32)
     scene.name = "small_city_env"
+    return scene
+
+
+def checker_texture(width: int = 32, height: int = 16, cells: int = 4, lo=(0.08, 0.1, 0.3), hi=(0.8, 0.7, 0.5), seed: int = 3) -> np.ndarray:
+    """float32 [H, W, 4] (linear, as GfxTextureDesc wants it): a checker with per-texel noise, no two texels alike"""
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:height, 0:width]
+    mask = (((x * cells) // width + (y * cells) // height) % 2).astype(bool)
+    img = np.where(mask[..., None], np.asarray(hi, dtype=F32), np.asarray(lo, dtype=F32)).astype(F32)
+    img = img * (F32(0.85) + F32(0.15) * rng.random((height, width, 1), dtype=F32))
+    out = np.ones((height, width, 4), dtype=F32)
+    out[..., :3] = img
+    return out
+
+
+def small_city_scene_textured() -> Scene:
+    """small_city_scene with image textures on most materials: albedo / diffuse / baseColor maps (p0), specular or
+    occlusion-roughness-metallic maps (p1) and smoothness maps (p2), non-power-of-two sizes included; texture coordinates run
+    beyond [0, 1) on the tessellated faces, so the repeat addressing is exercised.  Emitters keep constant emittance."""
+    scene = small_city_scene()
+    rng = np.random.default_rng(17)
+    scene.textures = [checker_texture(32, 16, 4), checker_texture(24, 40, 6, (0.02, 0.02, 0.02), (0.3, 0.25, 0.2), 5),
+                      checker_texture(7, 5, 3, (0.1, 0.1, 0.1), (0.6, 0.6, 0.6), 9), checker_texture(64, 64, 8, (0.2, 0.5, 0.2), (0.9, 0.9, 0.8), 11)]
+    n = scene.materials.shape[0]
+    mt = np.full((n, 4), 0xFFFFFFFF, dtype=np.uint32)
+    for m in range(n):
+        if scene.materials[m]["hasEmittance"]:
+            continue
+        pick = rng.integers(0, 5)
+        if pick >= 1:
+            mt[m, 0] = [0, 3, 0, 3][pick - 1]
+        if pick >= 3 and scene.materials[m]["bsdfType"] != BSDF_LAMBERT:
+            mt[m, 1] = 1
+            mt[m, 2] = 2
+    scene.material_textures = mt
+    for mesh in scene.meshes:  # [0, 1] per face in the generator: stretch past the unit square, negative values included
+        mesh.texcoords = (mesh.texcoords * F32(3.7) - F32(1.2)).astype(F32)
+    scene.name = "small_city_textured"
     return scene
 
 

@@ -62,8 +62,9 @@ typedef enum GfxBsdfType {
     GFX_BSDF_SIMPLE_PBR = 2            /* common_device.cuh:767-826   p0 = baseColor, p1 = (occlusion, roughness, metallic) */
 } GfxBsdfType;
 
-/* shared::MaterialData (common/common_shared.h:1131-1170) with every texture a 1x1 texel:
- * the fields are the texel values *after* the texture unit's UNORM8/sRGB decode. */
+/* shared::MaterialData (common/common_shared.h:1131-1170).  The fields are the values of 1x1 textures *after* the texture unit's
+ * UNORM8/sRGB decode; a material whose parameters vary over the surface names image textures instead
+ * (GfxSceneDesc::materialTextures). */
 typedef struct GfxMaterialDesc {
     float p0[3];
     float p2;
@@ -83,6 +84,16 @@ typedef struct GfxInstanceDesc {
     uint32_t numMeshSlots;
 } GfxInstanceDesc;
 
+/* One image texture of a material (Material::texReflectance / texSpecular / ... , common_host.cpp:1462-1533): RGBA fp32 texels,
+ * row-major, as the texture unit would hand them to the filter, i.e. after the UNORM8 -> float and sRGB -> linear decode of the
+ * reference's samplers (NormalizedFloat_sRGB for colour maps).  Sampled like the reference's material samplers - linear filter,
+ * repeat addressing, level 0 (tex2DLod(..., 0.0f)) - restated in software (csrc/lighting.cuh textureFetchRepeat). */
+typedef struct GfxTextureDesc {
+    const float* texels;
+    uint32_t width;
+    uint32_t height;
+} GfxTextureDesc;
+
 typedef struct GfxSceneDesc {
     const GfxMeshDesc* meshes;
     const GfxMaterialDesc* materials;
@@ -100,6 +111,13 @@ typedef struct GfxSceneDesc {
     const float* envTexels;
     uint32_t envWidth;
     uint32_t envHeight;
+    /* image textures: materialTextures[4 * m + k] = index into `textures` of the map that replaces, in material m,
+     * k = 0: p0 (.xyz: reflectance / diffuse / baseColor), 1: p1 (.xyz: specular F0 / occlusion-roughness-metallic),
+     * 2: p2 (.x: smoothness), 3: emittance (must be 0xFFFFFFFF: textured emitters are not supported, gfx_scene_upload refuses
+     * them) - or 0xFFFFFFFF for "use the constant of GfxMaterialDesc".  NULL = no material is textured. */
+    const GfxTextureDesc* textures;
+    const uint32_t* materialTextures;
+    uint32_t numTextures;
 } GfxSceneDesc;
 
 /* ---- BVH formats (bit-identical to the reference structs) ---------------------------- */

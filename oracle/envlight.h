@@ -146,6 +146,29 @@ inline void buildEnvLight(EnvLight* e, const float* rgba, uint32_t width, uint32
     e->topIntegral = buildRegularDistribution1D(e->rowIntegral.data(), height, e->topPdf.data(), e->topCdf.data());
 }
 
+// one image texture of a material and tex2DLod<float4>(tex, u, v, 0) with the reference's material samplers
+// (common_host.cpp:1462-1481: linear filter, repeat addressing): the arithmetic of EnvLight::fetch with wrapped indices
+struct ImageTexture {
+    uint32_t W = 0, H = 0;
+    std::vector<float> texels; // RGBA
+    void fetch(float u, float v, float out[4]) const {
+        const float xB = (u - std::floor(u)) * W - 0.5f, yB = (v - std::floor(v)) * H - 0.5f;
+        const float fx = std::floor(xB), fy = std::floor(yB);
+        const float a = std::floor((xB - fx) * 256.0f + 0.5f) * (1.0f / 256.0f);
+        const float b = std::floor((yB - fy) * 256.0f + 0.5f) * (1.0f / 256.0f);
+        const int ix = (int)fx, iy = (int)fy; // -1 .. W - 1
+        const uint32_t x0 = ix < 0 ? W - 1 : (uint32_t)ix, x1 = (uint32_t)(ix + 1) >= W ? 0u : (uint32_t)(ix + 1);
+        const uint32_t y0 = iy < 0 ? H - 1 : (uint32_t)iy, y1 = (uint32_t)(iy + 1) >= H ? 0u : (uint32_t)(iy + 1);
+        const float* t00 = texels.data() + 4 * ((size_t)y0 * W + x0);
+        const float* t10 = texels.data() + 4 * ((size_t)y0 * W + x1);
+        const float* t01 = texels.data() + 4 * ((size_t)y1 * W + x0);
+        const float* t11 = texels.data() + 4 * ((size_t)y1 * W + x1);
+        const float w00 = (1 - a) * (1 - b), w10 = a * (1 - b), w01 = (1 - a) * b, w11 = a * b;
+        for (int c = 0; c < 4; ++c)
+            out[c] = w00 * t00[c] + w10 * t10[c] + w01 * t01[c] + w11 * t11[c];
+    }
+};
+
 constexpr float kProbToSampleEnvLight = 0.25f; // restir_di_shared.h:6 (and the other apps' *_shared.h:6)
 
 } // namespace orc

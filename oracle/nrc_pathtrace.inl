@@ -264,7 +264,7 @@ static void nrcRayGen(orc_frame* f, orc_nrc_frame* n, const GfxFrameParams* p, c
         const float3 emittance(mat.emittance[0], mat.emittance[1], mat.emittance[2]);
         contribution += alpha * emittance / kPi;
     }
-    const BSDF bsdf = setupBsdf(s, mesh.materialSlot);
+    const BSDF bsdf = setupBsdf(s, mesh.materialSlot, sp.texCoord);
     const float3 directContNEE = performNextEventEstimation(s, p, positionInWorld, vOutLocal, shadingFrame, bsdf, rng, counters);
     contribution += alpha * directContNEE;
 
@@ -371,7 +371,7 @@ static void nrcExtend(orc_frame* f, orc_nrc_frame* n, const GfxFrameParams* p, s
         recContinueProb = 1.0f / continueProb;
     }
 
-    const BSDF bsdf = setupBsdf(s, mesh.materialSlot);
+    const BSDF bsdf = setupBsdf(s, mesh.materialSlot, sp.texCoord);
 
     // path termination by the spread heuristic (:474-531)
     bool endsWithCache = pow2(st.curSqrtPathSpread) > kPathTerminationFactor * st.primaryPathSpread;

@@ -215,7 +215,7 @@ static void pathTracePixel(orc_frame* f, const GfxFrameParams* p, const Camera &
                 const float3 emittance(mat.emittance[0], mat.emittance[1], mat.emittance[2]);
                 contribution += alpha * emittance / kPi;
             }
-            const BSDF bsdf = setupBsdf(s, mesh->materialSlot);
+            const BSDF bsdf = setupBsdf(s, mesh->materialSlot, sp.texCoord);
             contribution += alpha * performNextEventEstimation(s, p, positionInWorld, vOutLocal, shadingFrame, bsdf, rng, counters);
 
             float3 vInLocal;
@@ -271,7 +271,7 @@ static void pathTracePixel(orc_frame* f, const GfxFrameParams* p, const Camera &
                 break;
             alpha /= continueProb;
 
-            const BSDF bsdf = setupBsdf(s, mesh->materialSlot);
+            const BSDF bsdf = setupBsdf(s, mesh->materialSlot, sp.texCoord);
             contribution += alpha * performNextEventEstimation(s, p, positionInWorld, vOutLocal, shadingFrame, bsdf, rng, counters);
 
             float3 vInLocal;

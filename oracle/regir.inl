@@ -352,7 +352,7 @@ static void regirPathTracePixel(orc_frame* f, orc_regir* r, const GfxFrameParams
                 const float3 emittance(mat.emittance[0], mat.emittance[1], mat.emittance[2]);
                 contribution += alpha * emittance / kPi;
             }
-            const BSDF bsdf = setupBsdf(s, mesh->materialSlot);
+            const BSDF bsdf = setupBsdf(s, mesh->materialSlot, sp.texCoord);
             contribution += alpha * regirNextEventEstimation(s, r, p, positionInWorld, vOutLocal, shadingFrame, bsdf, rng, counters);
             float3 vInLocal;
             const float uDir0 = rng.getFloat0cTo1o();
@@ -412,7 +412,7 @@ static void regirPathTracePixel(orc_frame* f, orc_regir* r, const GfxFrameParams
                 break;
             alpha /= continueProb;
 
-            const BSDF bsdf = setupBsdf(s, mesh->materialSlot);
+            const BSDF bsdf = setupBsdf(s, mesh->materialSlot, sp.texCoord);
             contribution += alpha * regirNextEventEstimation(s, r, p, positionInWorld, vOutLocal, shadingFrame, bsdf, rng, counters);
 
             float3 vInLocal;

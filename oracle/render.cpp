@@ -52,6 +52,8 @@ struct orc_scene {
     float sceneMin[3], sceneMax[3];
     OrcBuildConfig buildConfig;
     EnvLight env; // envLightTexture + envLightImportanceMap (restir_di_shared.h:221-222)
+    std::vector<ImageTexture> textures;      // image textures of the materials ...
+    std::vector<uint32_t> materialTextures;  // ... [4 * m + k]: texture of p0 / p1 / p2 / emittance or 0xFFFFFFFF (empty = none)
 };
 
 // plp.s->envLightTexture && plp.f->enableEnvLight
@@ -184,6 +186,15 @@ extern "C" orc_scene* orc_scene_create(const GfxSceneDesc* d, const OrcBuildConf
     s->instanceMeshSlots.assign(d->instanceMeshSlots, d->instanceMeshSlots + d->numInstanceMeshSlots);
 
     buildEnvLight(&s->env, d->envTexels, d->envWidth, d->envHeight);
+    if (d->materialTextures && d->numTextures) {
+        s->textures.resize(d->numTextures);
+        for (uint32_t t = 0; t < d->numTextures; ++t) {
+            s->textures[t].W = d->textures[t].width;
+            s->textures[t].H = d->textures[t].height;
+            s->textures[t].texels.assign(d->textures[t].texels, d->textures[t].texels + 4 * (size_t)d->textures[t].width * d->textures[t].height);
+        }
+        s->materialTextures.assign(d->materialTextures, d->materialTextures + 4 * (size_t)d->numMaterials);
+    }
     s->buildConfig = *cfg;
     rebuildWorld(s, numThreads);
     return s;
@@ -612,10 +623,30 @@ extern "C" void orc_generate_primary_rays(const GfxFrameParams* p, uint32_t W, u
         }
 }
 
-static inline BSDF setupBsdf(const orc_scene* s, uint32_t matSlot) {
+// BSDF::setup(mat, texCoord, 0.0f) (common_device.cuh:376-385, 778-826): constants, or the material's image textures at texCoord
+static inline BSDF setupBsdf(const orc_scene* s, uint32_t matSlot, const float2 &texCoord) {
     const GfxMaterialDesc &m = s->materials[matSlot];
     BSDF b;
-    b.setup(m.bsdfType, m.p0, m.p1, m.p2);
+    if (s->materialTextures.empty()) {
+        b.setup(m.bsdfType, m.p0, m.p1, m.p2);
+        return b;
+    }
+    const uint32_t* tex = &s->materialTextures[4 * (size_t)matSlot];
+    float p0[3] = { m.p0[0], m.p0[1], m.p0[2] }, p1[3] = { m.p1[0], m.p1[1], m.p1[2] }, p2 = m.p2;
+    float t[4];
+    if (tex[0] != 0xFFFFFFFFu) {
+        s->textures[tex[0]].fetch(texCoord.x, texCoord.y, t);
+        p0[0] = t[0]; p0[1] = t[1]; p0[2] = t[2];
+    }
+    if (tex[1] != 0xFFFFFFFFu) {
+        s->textures[tex[1]].fetch(texCoord.x, texCoord.y, t);
+        p1[0] = t[0]; p1[1] = t[1]; p1[2] = t[2];
+    }
+    if (tex[2] != 0xFFFFFFFFu) {
+        s->textures[tex[2]].fetch(texCoord.x, texCoord.y, t);
+        p2 = t[0];
+    }
+    b.setup(m.bsdfType, p0, p1, p2);
     return b;
 }
 
@@ -694,7 +725,7 @@ extern "C" void orc_gbuffer(orc_frame* f, const GfxFrameParams* p, int numThread
                 qGeometricNormalInWorld = encodeVector(geometricNormalInWorld);
                 qTexCoord = encodeTexCoords(texCoord);
 
-                const BSDF bsdf = setupBsdf(s, matSlot);
+                const BSDF bsdf = setupBsdf(s, matSlot, texCoord);
                 const ReferenceFrame shadingFrame(shadingNormalInWorld, texCoord0DirInWorld);
                 const float3 vOut = -direction;
                 const float3 vOutLocal = shadingFrame.toLocal(normalize(vOut));
@@ -972,7 +1003,7 @@ static void performInitialAndTemporalRIS(orc_frame* f, const GfxFrameParams* p, 
     const float3 shadingTangentInWorld = decodeVector(gb3.qShadingTangent);
     const ReferenceFrame shadingFrame(shadingNormalInWorld, shadingTangentInWorld);
     const float3 vOutLocal = shadingFrame.toLocal(vOut);
-    const BSDF bsdf = setupBsdf(s, gb3.matSlot);
+    const BSDF bsdf = setupBsdf(s, gb3.matSlot, decodeTexCoords(gb3.qTexCoord));
 
     const uint32_t curResIndex = p->currentReservoirIndex & 1;
     Reservoir reservoir;
@@ -1089,7 +1120,7 @@ static void performInitialAndTemporalRIS(orc_frame* f, const GfxFrameParams* p, 
                 const float3 nbVOut = normalize(prevCamera.position - nbPositionInWorld);
                 const float nbFrontHit = dot(nbVOut, nbGeometricNormalInWorld) >= 0.0f ? 1.0f : -1.0f;
                 nbPositionInWorld = offsetRayOrigin(nbPositionInWorld, nbFrontHit * nbGeometricNormalInWorld);
-                const BSDF nbBsdf = setupBsdf(s, nbGb3.matSlot);
+                const BSDF nbBsdf = setupBsdf(s, nbGb3.matSlot, decodeTexCoords(nbGb3.qTexCoord));
                 const ReferenceFrame nbShadingFrame(decodeVector(nbGb3.qShadingNormal), decodeVector(nbGb3.qShadingTangent));
                 const float3 nbVOutLocal = nbShadingFrame.toLocal(nbVOut);
                 const Reservoir neighbor = loadReservoir(f, prevResIndex, nbPix);
@@ -1143,7 +1174,7 @@ static void performSpatialRIS(orc_frame* f, const GfxFrameParams* p, const Camer
 
     const ReferenceFrame shadingFrame(decodeVector(gb3.qShadingNormal), decodeVector(gb3.qShadingTangent));
     const float3 vOutLocal = shadingFrame.toLocal(vOut);
-    const BSDF bsdf = setupBsdf(s, gb3.matSlot);
+    const BSDF bsdf = setupBsdf(s, gb3.matSlot, decodeTexCoords(gb3.qTexCoord));
 
     const uint32_t srcResIndex = p->currentReservoirIndex & 1;
     const uint32_t dstResIndex = (srcResIndex + 1) % 2;
@@ -1240,7 +1271,7 @@ static void performSpatialRIS(orc_frame* f, const GfxFrameParams* p, const Camer
                     const float3 nbVOut = normalize(prevCamera.position - nbPositionInWorld);
                     const float nbFrontHit = dot(nbVOut, nbGeometricNormalInWorld) >= 0.0f ? 1.0f : -1.0f;
                     nbPositionInWorld = offsetRayOrigin(nbPositionInWorld, nbFrontHit * nbGeometricNormalInWorld);
-                    const BSDF nbBsdf = setupBsdf(s, nbGb3.matSlot);
+                    const BSDF nbBsdf = setupBsdf(s, nbGb3.matSlot, decodeTexCoords(nbGb3.qTexCoord));
                     const ReferenceFrame nbShadingFrame(decodeVector(nbGb3.qShadingNormal), decodeVector(nbGb3.qShadingTangent));
                     const float3 nbVOutLocal = nbShadingFrame.toLocal(nbVOut);
                     const Reservoir neighbor = loadReservoir(f, srcResIndex, nbPix);
@@ -1296,7 +1327,7 @@ static void shading(orc_frame* f, const GfxFrameParams* p, const Camera &camera,
         const ReferenceFrame shadingFrame(decodeVector(gb3.qShadingNormal), decodeVector(gb3.qShadingTangent));
         const float3 vOutLocal = shadingFrame.toLocal(vOut);
         const GfxMaterialDesc &mat = s->materials[gb3.matSlot];
-        const BSDF bsdf = setupBsdf(s, gb3.matSlot);
+        const BSDF bsdf = setupBsdf(s, gb3.matSlot, decodeTexCoords(gb3.qTexCoord));
 
         const uint32_t curResIndex = p->currentReservoirIndex & 1;
         const Reservoir reservoir = loadReservoir(f, curResIndex, pix);

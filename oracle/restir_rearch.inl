@@ -139,7 +139,7 @@ static inline RearchShadingPoint reconstructShadingPoint(const orc_frame* f, con
     sp.positionInWorld = offsetRayOrigin(positionInWorld, frontHit * geometricNormalInWorld);
     sp.shadingFrame = ReferenceFrame(decodeVector(gb3.qShadingNormal), decodeVector(gb3.qShadingTangent));
     sp.vOutLocal = sp.shadingFrame.toLocal(vOut);
-    sp.bsdf = setupBsdf(s, gb3.matSlot);
+    sp.bsdf = setupBsdf(s, gb3.matSlot, decodeTexCoords(gb3.qTexCoord));
     return sp;
 }
 

@@ -51,7 +51,7 @@ def _compare_pathtrace(ctx, oframe, p, tag):
 
 
 @pytest.mark.parametrize("max_path_length,scene_name", [(5, "small_city_scene"), (0, "small_city_scene"), (5, "small_interior_scene"),
-                                                        (5, "small_city_scene_env")])
+                                                        (5, "small_city_scene_env"), (5, "small_city_scene_textured")])
 def test_nrc_frames_bit_exact(gfx_ctx, oracle, max_path_length, scene_name):
     scene = getattr(scenes, scene_name)()
     w, h = 192, 108

@@ -28,7 +28,8 @@ def _assert_same(got, want, tag):
 
 @pytest.mark.parametrize("max_path_length,scene_name", [(2, "small_city_scene"), (5, "small_city_scene"), (9, "small_city_scene"),
                                                         (5, "small_interior_scene"),
-                                                        (5, "small_city_scene_env"), (4, "env_only_scene")])
+                                                        (5, "small_city_scene_env"), (4, "env_only_scene"),
+                                                        (5, "small_city_scene_textured")])
 def test_pathtrace_accumulation_bit_exact(gfx_ctx, oracle, max_path_length, scene_name):
     """three accumulated samples per pixel in a closed scene with ~100 emitters: every pixel's radiance and RNG
     state equal the oracle's, i.e. the wavefront reordering changes neither the draws nor the summation order

@@ -19,7 +19,8 @@ def _same(got, want, tag):
 
 
 @pytest.mark.parametrize("grid,randomize,scene_name", [((8, 4, 8), True, "small_city_scene"), ((5, 3, 6), False, "small_city_scene"),
-                                                       ((8, 4, 8), True, "small_city_scene_env")])
+                                                       ((8, 4, 8), True, "small_city_scene_env"),
+                                                       ((5, 3, 6), True, "small_city_scene_textured")])
 def test_regir_frames_bit_exact(gfx_ctx, oracle, grid, randomize, scene_name):
     # small_city_scene_env: the cell reservoirs also stream environment-light candidates (build_cell_reservoirs.cu:120-139)
     scene = getattr(scenes, scene_name)()

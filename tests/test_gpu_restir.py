@@ -53,7 +53,9 @@ def test_light_distributions(gfx_ctx, oracle):
                                                  # environment light: importance-map candidates, atInfinity samples through
                                                  # temporal / spatial reuse, the environment behind miss pixels
                                                  (False, "small_city_scene_env"), (True, "small_city_scene_env"),
-                                                 (False, "env_only_scene")])
+                                                 (False, "env_only_scene"),
+                                                 # image textures on the BSDF parameters (software tex2DLod, repeat addressing)
+                                                 (False, "small_city_scene_textured")])
 def test_restir_three_frames_bit_exact(gfx_ctx, oracle, unbiased, scene_name):
     # small_interior_scene: config 3's ingredients - a closed room, 96 two-triangle emitters, SimplePBR materials
     # (common/common_device.cuh:767-776, 806-826)

@@ -74,6 +74,10 @@ def test_rearch_with_environment_light(gfx_ctx, oracle, unbiased):
     _run(gfx_ctx, oracle, scenes.small_city_scene_env(), 160, 96, 3, lambda p: dict(temporal=True, spatial=True, unbiased=unbiased))
 
 
+def test_rearch_with_image_textures(gfx_ctx, oracle):
+    _run(gfx_ctx, oracle, scenes.small_city_scene_textured(), 160, 96, 3, lambda p: dict(temporal=True, spatial=True, unbiased=False))
+
+
 def test_rearch_unbiased_moving_camera_random_neighbors(gfx_ctx, oracle):
     def configure(p):
         p.useLowDiscrepancyNeighbors = 0
