@@ -732,7 +732,7 @@ int launchPathTraceNrc(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* 
         return GFX_ERR_INVALID_ARGUMENT;
     }
     typedef int (*NcclAllGatherFn)(const void*, void*, size_t, int, void*, cudaStream_t);
-    static const NcclAllGatherFn allGather = reinterpret_cast<NcclAllGatherFn>(ncclSymbol("ncclAllGather"));
+    const NcclAllGatherFn allGather = sharded ? reinterpret_cast<NcclAllGatherFn>(ncclSymbol("ncclAllGather")) : nullptr;
     if (sharded && !allGather) {
         ctx->setError("gfx_pathtrace_launch(GFX_PT_NRC): ncclAllGather not found (load NCCL in the host process)");
         return GFX_ERR_UNSUPPORTED;
@@ -976,7 +976,7 @@ int launchNrcPass(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* param
             // every rank trains on all records (the weights stay replicated): each record was written by exactly one rank
             // and is zero elsewhere, so an unsigned integer sum over the ranks reproduces its bits
             typedef int (*NcclAllReduceFn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
-            static const NcclAllReduceFn allReduce = reinterpret_cast<NcclAllReduceFn>(ncclSymbol("ncclAllReduce"));
+            const NcclAllReduceFn allReduce = reinterpret_cast<NcclAllReduceFn>(ncclSymbol("ncclAllReduce"));
             if (!allReduce) {
                 ctx->setError("gfx_nrc_propagate: ncclAllReduce not found (load NCCL in the host process)");
                 return GFX_ERR_UNSUPPORTED;

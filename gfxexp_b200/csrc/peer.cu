@@ -63,12 +63,14 @@ __global__ void k_peerWait(uint32_t* localFlags, uint32_t flagIndex, uint32_t va
     }
 }
 
-// NCCL entry points resolved at run time: from the process image if NCCL is globally visible, else from libnccl.so.2 (which
-// the loader maps to the copy the process has already loaded, e.g. torch's)
+// NCCL entry points resolved at run time, from the NCCL the host process has ALREADY loaded (the ncclComm_t handed to the library
+// comes from it): the global scope first, then the loaded libnccl.so.2 by name with RTLD_NOLOAD (torch loads its bundled copy with
+// local visibility).  Never loads a library: another libnccl of the same soname mapped into the process would shadow the
+// host's own one for everything loaded later.
 void* ncclSymbol(const char* name) {
     void* sym = dlsym(RTLD_DEFAULT, name);
     if (!sym) {
-        static void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
         if (lib)
             sym = dlsym(lib, name);
     }
@@ -208,8 +210,8 @@ typedef int (*NcclCommUserRankFn)(void*, int*);
 int gfx_framebuffer_allgather(gfx_ctx* ctx, void* ncclComm, void* stream, uint32_t rowsPerRank, void* dstFramebuffer) {
     if (!ctx || !ncclComm || !dstFramebuffer || !ctx->frame.created || rowsPerRank == 0)
         return GFX_ERR_INVALID_ARGUMENT;
-    static const NcclAllGatherFn allGather = reinterpret_cast<NcclAllGatherFn>(ncclSymbol("ncclAllGather"));
-    static const NcclCommUserRankFn userRank = reinterpret_cast<NcclCommUserRankFn>(ncclSymbol("ncclCommUserRank"));
+    const NcclAllGatherFn allGather = reinterpret_cast<NcclAllGatherFn>(ncclSymbol("ncclAllGather"));
+    const NcclCommUserRankFn userRank = reinterpret_cast<NcclCommUserRankFn>(ncclSymbol("ncclCommUserRank"));
     if (!allGather || !userRank) {
         ctx->setError("gfx_framebuffer_allgather: ncclAllGather not found (load NCCL in the host process)");
         return GFX_ERR_UNSUPPORTED;
