@@ -387,7 +387,10 @@ def measure_config5(scene, args, rank, world, local_rank):
     ctx.create_frame(W5, H5)
     p = abi.default_frame_params(scene, W5, H5)
     net = engine.NeuralRadianceCache(ctx, 2, 1e-2)
-    driver = multigpu.StripDriver(ctx, p, W5, H5, rank, world)
+    boundaries = None
+    if os.environ.get("GFX_MULTIGPU_EQUAL_STRIPS") != "1":
+        boundaries = multigpu.StripDriver.cost_balanced_boundaries(ctx, p, W5, H5, world)
+    driver = multigpu.StripDriver(ctx, p, W5, H5, rank, world, boundaries=boundaries)
     driver.enable_nrc(net)
     rng = np.random.default_rng(5)
     frame = 0
@@ -442,7 +445,8 @@ def measure_config5(scene, args, rank, world, local_rank):
         dist.all_reduce(r, op=dist.ReduceOp.SUM)
         rays = float(r.item())
     out = {"what": "ReSTIR DI (32 candidates, temporal + 1x4 spatial) + NRC (path tracing with cache termination, inference, "
-                   "4 training steps) in one 3840x2160 frame, strips of %d rows on %d GPU(s), framebuffer all-gathered" % (H5 // world, world),
+                   "4 training steps) in one 3840x2160 frame, %s on %d GPU(s), framebuffer all-gathered" % (
+                       "cost-balanced strips at rows %s" % driver.boundaries if boundaries is not None else "strips of %d rows" % (H5 // world), world),
            "n_gpus": world, "ms": ms / n_frames, "fps": 1e3 * n_frames / ms, "Mrays_per_s": rays / (ms * 1e-3) / 1e6,
            "rays_per_pixel": rays / n_frames / (W5 * H5), "frames_timed": n_frames,
            "training_records_last_frame": int(st[abi.NRC_STATE_NUM_TRAINING_DATA + (frame - 1) % 2]),
@@ -490,7 +494,14 @@ def run_gpu(args):
     if world > 1:
         from gfxexp_b200 import multigpu
         # seam rows travel as one-sided pushes over NVLink peer memory; GFX_MULTIGPU_NCCL=1 selects NCCL send/recv (A/B)
-        driver = multigpu.StripDriver(ctx, params, WIDTH, HEIGHT, rank, world, peer=os.environ.get("GFX_MULTIGPU_NCCL") != "1")
+        # strips of equal work, not of equal height (the sky rows of this view cost next to nothing); GFX_MULTIGPU_EQUAL_STRIPS=1: A/B
+        boundaries = None
+        if os.environ.get("GFX_MULTIGPU_EQUAL_STRIPS") != "1":
+            boundaries = multigpu.StripDriver.cost_balanced_boundaries(ctx, params, WIDTH, HEIGHT, world)
+        driver = multigpu.StripDriver(ctx, params, WIDTH, HEIGHT, rank, world, peer=os.environ.get("GFX_MULTIGPU_NCCL") != "1",
+                                      boundaries=boundaries)
+        if boundaries is not None:
+            driver.use_raw_communicator()  # gfx_framebuffer_allgatherv: one NCCL group launch for the unequal strips
     else:
         driver = None
 
@@ -729,9 +740,10 @@ def run_gpu(args):
                    "emissive_triangles": scene.num_emissive_triangles, "rays_per_pixel": rays_per_px,
                    "l2": "inputs larger than L2 (BVH %.0f MB + %.0f MB of per-pixel state per frame)" % (
                        (info.numTriangles * 52 + info.numNodes * 80) / 1e6, WIDTH * HEIGHT * 400 / 1e6),
-                   "parallelism": ("screen strips x%d (24-row G-buffer halo recomputed per seam, its rays not counted), seam rows by %s, "
+                   "parallelism": ("screen strips x%d %s (24-row G-buffer halo recomputed per seam, its rays not counted), seam rows by %s, "
                                    "beauty strips all-gathered with NCCL" % (
-                       world, "one-sided NVLink peer-memory pushes" if driver.backend.peer_ready else "NCCL send/recv"))
+                       world, ("of equal work, rows %s" % driver.boundaries) if not driver.rows else "of equal height",
+                       "one-sided NVLink peer-memory pushes" if driver.backend.peer_ready else "NCCL send/recv"))
                    if world > 1 else "1 GPU",
                    "bvh_build_ms": bvh_build_ms, "scene_upload_s": upload_s},
         "clocks": clocks,

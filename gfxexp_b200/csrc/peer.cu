@@ -252,4 +252,39 @@ int gfx_peer_close(gfx_ctx* ctx) {
     return GFX_OK;
 }
 
+int gfx_framebuffer_allgatherv(gfx_ctx* ctx, void* ncclComm, void* stream, const uint32_t* rowStarts, uint32_t world, void* dstFramebuffer) {
+    if (!ctx || !ncclComm || !dstFramebuffer || !rowStarts || !ctx->frame.created || world == 0 || world > 64)
+        return GFX_ERR_INVALID_ARGUMENT;
+    typedef int (*NcclBroadcastFn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+    typedef int (*NcclGroupFn)();
+    const NcclBroadcastFn broadcast = reinterpret_cast<NcclBroadcastFn>(ncclSymbol("ncclBroadcast"));
+    const NcclGroupFn groupStart = reinterpret_cast<NcclGroupFn>(ncclSymbol("ncclGroupStart"));
+    const NcclGroupFn groupEnd = reinterpret_cast<NcclGroupFn>(ncclSymbol("ncclGroupEnd"));
+    if (!broadcast || !groupStart || !groupEnd) {
+        ctx->setError("gfx_framebuffer_allgatherv: NCCL not found in the host process");
+        return GFX_ERR_UNSUPPORTED;
+    }
+    const uint32_t H = ctx->frame.H;
+    for (uint32_t r = 0; r < world; ++r)
+        if (rowStarts[r] > rowStarts[r + 1] || rowStarts[r + 1] > H)
+            return GFX_ERR_INVALID_ARGUMENT;
+    // strips of unequal height: one broadcast per strip from its owner, fused into one NCCL launch by the group
+    const size_t rowFloats = (size_t)ctx->frame.W * 4;
+    const float* beauty = reinterpret_cast<const float*>(ctx->frame.beauty);
+    float* dst = reinterpret_cast<float*>(dstFramebuffer);
+    int rc = groupStart();
+    for (uint32_t r = 0; r < world && rc == 0; ++r) {
+        const size_t count = (size_t)(rowStarts[r + 1] - rowStarts[r]) * rowFloats;
+        if (count)
+            rc = broadcast(beauty + rowStarts[r] * rowFloats, dst + rowStarts[r] * rowFloats, count, 7 /* ncclFloat32 */, (int)r, ncclComm,
+                           (cudaStream_t)stream);
+    }
+    const int rcEnd = groupEnd();
+    if (rc != 0 || rcEnd != 0) {
+        ctx->setError("gfx_framebuffer_allgatherv: NCCL returned " + std::to_string(rc ? rc : rcEnd));
+        return GFX_ERR_CUDA;
+    }
+    return GFX_OK;
+}
+
 } // extern "C"

@@ -27,7 +27,7 @@ host-side sharding logic is verified bit-for-bit against a single-process render
 """
 from __future__ import annotations
 
-from typing import List
+from typing import List, Optional
 
 import numpy as np
 import torch
@@ -162,20 +162,53 @@ class GpuBackend:
     peer_seq = 0
 
 
+def balanced_boundaries(row_cost, world: int, min_rows: int, align: int = 8) -> List[int]:
+    """Rows [b[r], b[r + 1]) for rank r such that the strips carry about equal cost: strips of equal height are not strips of equal
+    work (sky rows cost almost nothing; at 8 GPUs the lightest strip of the bistro-class view waits ~15 % of the frame for the
+    heaviest).  Boundaries are multiples of `align` (the 8x8 light-subset tiles of the rearchitected renderer) and every strip
+    keeps at least `min_rows` rows (the halo: a seam exchange only reaches the adjacent rank)."""
+    cost = np.asarray(row_cost, dtype=np.float64)
+    H = cost.shape[0]
+    cum = np.concatenate([[0.0], np.cumsum(cost)])
+    min_rows = max(min_rows, align)
+    b = [0]
+    for r in range(1, world):
+        target = cum[-1] * r / world
+        y = int(np.searchsorted(cum, target))
+        y = int(round(y / align)) * align
+        lo = b[-1] + min_rows
+        hi = H - (world - r) * min_rows
+        lo = (lo + align - 1) // align * align
+        hi = hi // align * align
+        if lo > hi:
+            raise ValueError(f"{H} rows cannot be split into {world} strips of at least {min_rows} rows")
+        b.append(min(max(y, lo), hi))
+    b.append(H)
+    return b
+
+
 class StripDriver:
     def __init__(self, backend_or_ctx, params, width: int, height: int, rank: int, world: int, halo: int = 24,
-                 peer: bool = True, max_motion_rows: int = 0, check_every: int = 0):
+                 peer: bool = True, max_motion_rows: int = 0, check_every: int = 0, boundaries: Optional[List[int]] = None):
         self.backend = GpuBackend(backend_or_ctx) if isinstance(backend_or_ctx, engine.Context) else backend_or_ctx
         self.params = params
         self.W, self.H = width, height
         self.rank, self.world = rank, world
         self.halo = halo
-        rows = (height + world - 1) // world
-        self.y0 = min(height, rank * rows)
-        self.y1 = min(height, self.y0 + rows)
-        self.rows = rows
-        if rows * world != height:
-            raise ValueError(f"height {height} must be divisible by the number of ranks {world} (equal all-gather chunks)")
+        if boundaries is None:
+            rows = (height + world - 1) // world
+            if rows * world != height:
+                raise ValueError(f"height {height} must be divisible by the number of ranks {world} (or pass `boundaries`)")
+            boundaries = [r * rows for r in range(world)] + [height]
+        boundaries = [int(v) for v in boundaries]
+        if len(boundaries) != world + 1 or boundaries[0] != 0 or boundaries[-1] != height or any(
+                boundaries[r + 1] <= boundaries[r] for r in range(world)):
+            raise ValueError(f"boundaries {boundaries}: need {world + 1} increasing rows from 0 to {height}")
+        self.boundaries = boundaries
+        self.y0, self.y1 = boundaries[rank], boundaries[rank + 1]
+        heights = [boundaries[r + 1] - boundaries[r] for r in range(world)]
+        self.rows = heights[0] if len(set(heights)) == 1 else 0  # 0: strips of unequal height (all-gather-v)
+        rows = min(heights)
         if world > 1 and rows < halo:
             raise ValueError(f"{rows} rows per rank < halo {halo}: the seam exchange only reaches the adjacent rank")
         if params.enableJittering:
@@ -266,6 +299,28 @@ class StripDriver:
         return bytes(C.string_at(C.addressof(p.camera), C.sizeof(p.camera))) != bytes(C.string_at(C.addressof(p.prevCamera), C.sizeof(p.prevCamera)))
 
     # -- ReSTIR DI + NRC in one frame (BASELINE config 5) ---------------------------------------------------
+    def use_raw_communicator(self):
+        """collectives through the library on a raw ncclComm_t (gfx_framebuffer_allgather[v]) instead of torch.distributed"""
+        if self.world > 1 and getattr(self, "comm", None) is None:
+            self.comm = NcclComm(self.rank, self.world)
+
+    @staticmethod
+    def cost_balanced_boundaries(ctx: "engine.Context", params, width: int, height: int, world: int, halo: int = 24,
+                                 sky_cost: float = 0.15) -> List[int]:
+        """Strip boundaries from the view itself: one full-frame G-buffer pass on this rank (every rank holds the whole scene and
+        computes the same, deterministic, answer - no communication), cost of a row = its pixels that hit geometry + `sky_cost`
+        per pixel (a miss pixel still costs its primary ray and a write in the shading pass)."""
+        if world == 1:
+            return [0, height]
+        saved = (params.tileOriginY, params.tileRows)
+        params.tileOriginY, params.tileRows = 0, 0
+        ctx.gbuffer(params)
+        params.tileOriginY, params.tileRows = saved
+        ctx.synchronize()
+        gb0 = ctx.download(abi.BUF_GBUFFER0, params.bufferIndex)
+        hits = (gb0[..., 0] != 0xFFFFFFFF).sum(axis=1).astype(np.float64)
+        return balanced_boundaries(hits + sky_cost * width, world, halo)
+
     def enable_nrc(self, net: "engine.NeuralRadianceCache", overlap_training: bool = True):
         """Shard the NRC half of the frame over the ranks (gfx_nrc_shard): every rank path-traces and infers its rows, the
         training vertices are numbered over the whole frame, the records are merged, training runs replicated.
@@ -275,12 +330,12 @@ class StripDriver:
         if (self.y0 * self.W) % 128 or (self.W * self.H) % 128:
             raise ValueError("NRC strips must start on a multiple of 128 pixels (the inference tile)")
         self.net = net
-        self.comm = None
+        self.comm = getattr(self, "comm", None)
         self.train_stream = torch.cuda.Stream(device=f"cuda:{self.backend.ctx.device}") if overlap_training else None
         self.trained = None
         ctx = self.backend.ctx
         if self.world > 1:
-            self.comm = NcclComm(self.rank, self.world)
+            self.use_raw_communicator()
             ctx._check(ctx.lib.gfx_nrc_shard(ctx.h, self.comm.handle, self.rank, self.world), "gfx_nrc_shard")
 
     def render_restir_nrc_frame(self, frame_index: int, offsets, num_spatial_passes: int = 1, unbiased: bool = False,
@@ -377,11 +432,23 @@ class StripDriver:
         if self.world > 1 and getattr(self, "comm", None) is not None:
             # the library's own collective on the host's communicator (the same one the sharded NRC frame uses)
             ctx = self.backend.ctx
-            ctx._check(ctx.lib.gfx_framebuffer_allgather(ctx.h, self.comm.handle, None, self.rows, self.composited.data_ptr()),
-                       "gfx_framebuffer_allgather")
-        elif self.world > 1:
+            if self.rows:
+                ctx._check(ctx.lib.gfx_framebuffer_allgather(ctx.h, self.comm.handle, None, self.rows, self.composited.data_ptr()),
+                           "gfx_framebuffer_allgather")
+            else:
+                import ctypes as C
+                starts = (C.c_uint32 * (self.world + 1))(*self.boundaries)
+                ctx._check(ctx.lib.gfx_framebuffer_allgatherv(ctx.h, self.comm.handle, None, starts, self.world,
+                                                              self.composited.data_ptr()), "gfx_framebuffer_allgatherv")
+        elif self.world > 1 and self.rows:
             strip = self._row_slices(abi.BUF_BEAUTY_ACCUM, 0, self.y0, self.y1)[0]
             dist.all_gather_into_tensor(self.composited, strip.contiguous())
+        elif self.world > 1:  # strips of unequal height without a raw communicator: one broadcast per strip
+            words = self.W * 4
+            mine = self._row_slices(abi.BUF_BEAUTY_ACCUM, 0, self.y0, self.y1)[0]
+            self.composited[self.y0 * words: self.y1 * words].copy_(mine)
+            for r in range(self.world):
+                dist.broadcast(self.composited[self.boundaries[r] * words: self.boundaries[r + 1] * words], src=r)
         elif isinstance(self.backend, GpuBackend):
             self.composited = self.backend.tensor(abi.BUF_BEAUTY_ACCUM, 0)  # one rank: the beauty buffer is the frame
         else:

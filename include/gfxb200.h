@@ -503,6 +503,9 @@ int gfx_restir_strip_frame(gfx_ctx* ctx, void* stream, GfxFrameParams* params, G
  * `ncclComm` is the host's ncclComm_t; the library resolves ncclAllGather from the NCCL the process has loaded (or
  * libnccl.so.2) at first use, so libgfxb200.so has no link-time NCCL dependency.  Stream-ordered on `stream`. */
 int gfx_framebuffer_allgather(gfx_ctx* ctx, void* ncclComm, void* stream, uint32_t rowsPerRank, void* dstFramebuffer);
+/* the same for strips of unequal height (cost-balanced strips): rank r owns rows [rowStarts[r], rowStarts[r + 1]), rowStarts has
+ * world + 1 entries; one ncclBroadcast per strip inside an NCCL group (= one launch) */
+int gfx_framebuffer_allgatherv(gfx_ctx* ctx, void* ncclComm, void* stream, const uint32_t* rowStarts, uint32_t world, void* dstFramebuffer);
 
 /* ---- ReGIR cell reservoirs (regir_main.cpp:2033-2068) --------------------------------- */
 /* replaces kernelBuildCellReservoirs / kernelBuildCellReservoirsAndTemporalReuse (build_cell_reservoirs.cu:71-233):

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 W, H, FRAMES = 320, 192, 3
 
 
-def _worker(rank, world, port, result_path, peer):
+def _worker(rank, world, port, result_path, peer, balanced=False):
     import torch
     import torch.distributed as dist
     sys.path.insert(0, ROOT)
@@ -28,7 +28,13 @@ def _worker(rank, world, port, result_path, peer):
     ctx.build_bvh()
     ctx.create_frame(W, H)
     p = abi.default_frame_params(scene, W, H)
-    driver = multigpu.StripDriver(ctx, p, W, H, rank, world, peer=peer)
+    boundaries = None
+    if balanced:  # strips of equal work instead of equal height, composited by gfx_framebuffer_allgatherv on a raw communicator
+        boundaries = multigpu.StripDriver.cost_balanced_boundaries(ctx, p, W, H, world)
+        assert boundaries[1] != H // 2, "the test scene should not happen to be balanced by equal strips"
+    driver = multigpu.StripDriver(ctx, p, W, H, rank, world, peer=peer, boundaries=boundaries)
+    if balanced:
+        driver.use_raw_communicator()
     assert driver.backend.peer_ready == peer
     outs = []
     for f in range(FRAMES):
@@ -95,7 +101,7 @@ def _nrc_offsets(f):
     return [int(rng.integers(0, 2 ** 32)) for _ in range(2)]
 
 
-def _worker_restir_nrc(rank, world, port, result_path):
+def _worker_restir_nrc(rank, world, port, result_path, boundaries=None):
     """config 5 in small: ReSTIR DI + NRC in one frame, sharded by strips; the NRC half numbers its training vertices over
     the whole frame (one word per rank and round all-gathered), merges the records and trains replicated"""
     import torch
@@ -114,7 +120,7 @@ def _worker_restir_nrc(rank, world, port, result_path):
     p = abi.default_frame_params(scene, W, H)
     p.maxPathLength = 5
     net = engine.NeuralRadianceCache(ctx, 2, 1e-2)
-    driver = multigpu.StripDriver(ctx, p, W, H, rank, world)
+    driver = multigpu.StripDriver(ctx, p, W, H, rank, world, boundaries=boundaries)
     driver.enable_nrc(net)
     outs, states = [], []
     for f in range(NRC_FRAMES):
@@ -135,7 +141,8 @@ def _worker_restir_nrc(rank, world, port, result_path):
     ctx.close()
 
 
-def test_restir_nrc_strips_equal_single_gpu(tmp_path, gfx_ctx):
+@pytest.mark.parametrize("boundaries", [None, [0, 72, 192]])
+def test_restir_nrc_strips_equal_single_gpu(tmp_path, gfx_ctx, boundaries):
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
@@ -146,7 +153,7 @@ def test_restir_nrc_strips_equal_single_gpu(tmp_path, gfx_ctx):
     port = s.getsockname()[1]
     s.close()
     result = str(tmp_path / "restir_nrc")
-    mp.spawn(_worker_restir_nrc, args=(2, port, result), nprocs=2, join=True)
+    mp.spawn(_worker_restir_nrc, args=(2, port, result, boundaries), nprocs=2, join=True)
     got = np.load(result + ".frames.npy")
 
     scene = scenes.small_city_scene()
@@ -204,8 +211,8 @@ def test_framebuffer_allgather_through_the_c_abi(tmp_path):
         assert np.all(got[:rows] == 1.0) and np.all(got[rows:] == 2.0), f"rank {rank}: gathered frame is wrong"
 
 
-@pytest.mark.parametrize("peer", [True, False])
-def test_two_gpu_strips_equal_single_gpu(tmp_path, gfx_ctx, peer):
+@pytest.mark.parametrize("peer,balanced", [(True, False), (False, False), (True, True)])
+def test_two_gpu_strips_equal_single_gpu(tmp_path, gfx_ctx, peer, balanced):
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
@@ -216,7 +223,7 @@ def test_two_gpu_strips_equal_single_gpu(tmp_path, gfx_ctx, peer):
     port = s.getsockname()[1]
     s.close()
     result = str(tmp_path / "composited.npy")
-    mp.spawn(_worker, args=(2, port, result, peer), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, result, peer, balanced), nprocs=2, join=True)
     got = np.load(result)
 
     scene = scenes.small_city_scene()

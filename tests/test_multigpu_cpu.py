@@ -46,7 +46,7 @@ class OracleBackend:
         return torch.empty(numel, dtype=torch.float32)
 
 
-def _worker(rank, world, port, result_path, H=H):
+def _worker(rank, world, port, result_path, H=H, boundaries=None):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -57,7 +57,7 @@ def _worker(rank, world, port, result_path, H=H):
     oscene = O.OracleScene(scene)
     oframe = O.OracleFrame(oscene, W, H)
     p = abi.default_frame_params(scene, W, H)
-    driver = multigpu.StripDriver(OracleBackend(oframe), p, W, H, rank, world, halo=24)
+    driver = multigpu.StripDriver(OracleBackend(oframe), p, W, H, rank, world, halo=24, boundaries=boundaries)
     outs = []
     for f in range(FRAMES):
         driver.render_frame(f, num_spatial_passes=2)
@@ -150,11 +150,12 @@ def _free_port():
     return port
 
 
-@pytest.mark.parametrize("world,H", [(2, 64), (4, 128)])  # 4 ranks: the two middle ranks exchange seams on both sides
-def test_strips_equal_single_process(tmp_path, oracle, world, H):
+# 4 ranks: the two middle ranks exchange seams on both sides; boundaries: cost-balanced strips of unequal height (all-gather-v)
+@pytest.mark.parametrize("world,H,boundaries", [(2, 64, None), (4, 128, None), (2, 64, [0, 40, 64]), (3, 128, [0, 56, 88, 128])])
+def test_strips_equal_single_process(tmp_path, oracle, world, H, boundaries):
     from gfxexp_b200 import abi, engine, scenes
     result = str(tmp_path / "composited.npy")
-    mp.spawn(_worker, args=(world, _free_port(), result, H), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), result, H, boundaries), nprocs=world, join=True)
     got = np.load(result)
 
     scene = scenes.tiny_city_scene()
@@ -169,6 +170,21 @@ def test_strips_equal_single_process(tmp_path, oracle, world, H):
                 oframe.restir(p, pass_id)
         want = oframe.buffer(abi.BUF_BEAUTY_ACCUM).reshape(-1)
         assert np.array_equal(got[f].view(np.uint32), want.view(np.uint32)), f"frame {f}: sharded frame differs"
+
+
+def test_balanced_boundaries():
+    from gfxexp_b200 import multigpu
+    cost = np.r_[np.full(300, 0.15), np.full(780, 1.0)]           # a sky above the geometry
+    b = multigpu.balanced_boundaries(cost, 8, 24)
+    assert b[0] == 0 and b[-1] == 1080 and all(v % 8 == 0 for v in b) and all(b[i + 1] - b[i] >= 24 for i in range(8))
+    per = [cost[b[i]:b[i + 1]].sum() for i in range(8)]
+    assert max(per) / (sum(per) / 8) < 1.05, per                  # within 5 % of equal work ...
+    equal = [cost[i * 135:(i + 1) * 135].sum() for i in range(8)]
+    assert max(equal) / (sum(equal) / 8) > 1.25                   # ... where equal heights are 25 % off
+    assert multigpu.balanced_boundaries(np.ones(192), 2, 24) == [0, 96, 192]
+    assert multigpu.balanced_boundaries(np.r_[np.zeros(150), np.ones(42)], 4, 24) == [0, 120, 144, 168, 192]  # the halo floor
+    with pytest.raises(ValueError):
+        multigpu.balanced_boundaries(np.ones(64), 4, 24)
 
 
 def test_strip_partition_rejects_ragged_heights():
