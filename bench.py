@@ -388,7 +388,7 @@ def measure_config5(scene, args, rank, world, local_rank):
     p = abi.default_frame_params(scene, W5, H5)
     net = engine.NeuralRadianceCache(ctx, 2, 1e-2)
     boundaries = None
-    if os.environ.get("GFX_MULTIGPU_EQUAL_STRIPS") != "1":
+    if os.environ.get("GFX_MULTIGPU_BALANCED_STRIPS") == "1":
         boundaries = multigpu.StripDriver.cost_balanced_boundaries(ctx, p, W5, H5, world)
     driver = multigpu.StripDriver(ctx, p, W5, H5, rank, world, boundaries=boundaries)
     driver.enable_nrc(net)
@@ -494,9 +494,11 @@ def run_gpu(args):
     if world > 1:
         from gfxexp_b200 import multigpu
         # seam rows travel as one-sided pushes over NVLink peer memory; GFX_MULTIGPU_NCCL=1 selects NCCL send/recv (A/B)
-        # strips of equal work, not of equal height (the sky rows of this view cost next to nothing); GFX_MULTIGPU_EQUAL_STRIPS=1: A/B
+        # GFX_MULTIGPU_BALANCED_STRIPS=1 (A/B): strip boundaries that equalise the geometry-hit pixels per strip instead of the
+        # rows.  Measured at N = 8 and rejected as the default: 1.298 ms against 1.147 ms with equal rows (config 5: 5.95 against
+        # 5.86 ms) - hit counts do not predict a strip's cost in this view (profiles/r02_summary.md section 7)
         boundaries = None
-        if os.environ.get("GFX_MULTIGPU_EQUAL_STRIPS") != "1":
+        if os.environ.get("GFX_MULTIGPU_BALANCED_STRIPS") == "1":
             boundaries = multigpu.StripDriver.cost_balanced_boundaries(ctx, params, WIDTH, HEIGHT, world)
         driver = multigpu.StripDriver(ctx, params, WIDTH, HEIGHT, rank, world, peer=os.environ.get("GFX_MULTIGPU_NCCL") != "1",
                                       boundaries=boundaries)

@@ -163,9 +163,8 @@ class GpuBackend:
 
 
 def balanced_boundaries(row_cost, world: int, min_rows: int, align: int = 8) -> List[int]:
-    """Rows [b[r], b[r + 1]) for rank r such that the strips carry about equal cost: strips of equal height are not strips of equal
-    work (sky rows cost almost nothing; at 8 GPUs the lightest strip of the bistro-class view waits ~15 % of the frame for the
-    heaviest).  Boundaries are multiples of `align` (the 8x8 light-subset tiles of the rearchitected renderer) and every strip
+    """Rows [b[r], b[r + 1]) for rank r such that the strips carry about equal cost under the given per-row cost estimate.
+    Boundaries are multiples of `align` (the 8x8 light-subset tiles of the rearchitected renderer) and every strip
     keeps at least `min_rows` rows (the halo: a seam exchange only reaches the adjacent rank)."""
     cost = np.asarray(row_cost, dtype=np.float64)
     H = cost.shape[0]
@@ -309,7 +308,9 @@ class StripDriver:
                                  sky_cost: float = 0.15) -> List[int]:
         """Strip boundaries from the view itself: one full-frame G-buffer pass on this rank (every rank holds the whole scene and
         computes the same, deterministic, answer - no communication), cost of a row = its pixels that hit geometry + `sky_cost`
-        per pixel (a miss pixel still costs its primary ray and a write in the shading pass)."""
+        per pixel (a miss pixel still costs its primary ray and a write in the shading pass).  An experiment, not the default:
+        on the bistro-class view at 8 GPUs this estimate made the frame SLOWER than equal rows (1.298 vs 1.147 ms) - the rows near
+        the horizon, with long rays through many buildings, cost more per hit pixel than the foreground."""
         if world == 1:
             return [0, height]
         saved = (params.tileOriginY, params.tileRows)
