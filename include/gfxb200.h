@@ -500,8 +500,8 @@ int gfx_restir_strip_frame(gfx_ctx* ctx, void* stream, GfxFrameParams* params, G
 /* The one mandatory collective of a strip-sharded frame: all-gathers the composited beauty strips.  Rank r of
  * the communicator contributes the rows [r * rowsPerRank, (r + 1) * rowsPerRank) of its GFX_BUF_BEAUTY_ACCUM; `dstFramebuffer`
  * (DEVICE, W * H float4, may be the beauty buffer itself: in-place all-gather) receives the full frame on every rank.
- * `ncclComm` is the host's ncclComm_t; the library resolves ncclAllGather from the NCCL the process has loaded (or
- * libnccl.so.2) at first use, so libgfxb200.so has no link-time NCCL dependency.  Stream-ordered on `stream`. */
+ * `ncclComm` is the host's ncclComm_t; the library resolves the NCCL entry points at the call from the NCCL the process has
+ * loaded (it never loads one itself), so libgfxb200.so has no link-time NCCL dependency.  Stream-ordered on `stream`. */
 int gfx_framebuffer_allgather(gfx_ctx* ctx, void* ncclComm, void* stream, uint32_t rowsPerRank, void* dstFramebuffer);
 /* the same for strips of unequal height (cost-balanced strips): rank r owns rows [rowStarts[r], rowStarts[r + 1]), rowStarts has
  * world + 1 entries; one ncclBroadcast per strip inside an NCCL group (= one launch) */
