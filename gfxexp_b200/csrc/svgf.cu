@@ -15,6 +15,7 @@
 // exp() is detmath's and pow(x,128) is seven squarings, exactly as in the oracle; compiled with
 // -fmad=false, so outputs are bit-identical to oracle/denoise.cpp.
 #include "shading.cuh"
+#include "lighting.cuh"
 #include "context.h"
 
 namespace gfx {
@@ -321,16 +322,26 @@ __global__ void __launch_bounds__(256) k_svgfATrous(DevSvgf s, DevFrameParams p,
         s.prevLighting[pix] = out;
 }
 
-// ---- fillBackground (svgf.cu:378-461), no environment texture ---------------------------
-__global__ void __launch_bounds__(256) k_svgfBackground(DevSvgf s, DevFrameParams p, uint32_t numFilteringStages) {
+// ---- fillBackground (svgf.cu:378-461) -----------------------------------------------------
+__global__ void __launch_bounds__(256) k_svgfBackground(DevSvgf s, DevFrameParams p, uint32_t numFilteringStages, DevEnvLight env) {
     SVGF_PIXEL();
     const uint32_t curBufIdx = p.bufferIndex;
     if (s.gb0[curBufIdx][pix].x != 0xFFFFFFFFu)
         return;
-    const f3 finalLighting(0.001f, 0.001f, 0.001f);
+    f3 finalLighting(0.001f, 0.001f, 0.001f);
     const float fx = (x + 0.5f) / W;
     const float fy = (y + 0.5f) / H;
     f3 direction = normalize(mul3x3(p.camera.orientation, f3(p.camera.vw * (0.5f - fx), p.camera.vh * (0.5f - fy), 1)));
+    if (env.enabled) { // :431-437; the camera's sub-pixel offset is the pixel centre here (no TAA jitter in this host)
+        float posPhi, posTheta;
+        toPolarYUp(direction, &posPhi, &posTheta);
+        float phi = posPhi + env.rotation;
+        phi += env.rotation; // as written in the reference (:418-420): the rotation is added twice when the environment light is on
+        float u = phi / (2 * kPi);
+        u -= floorf(u);
+        const float v = posTheta / kPi;
+        finalLighting = env.powerCoeff * envFetch(env, u, v);
+    }
     const float* o = p.prevCamera.orientation;
     direction = f3(o[0] * direction.x + o[3] * direction.y + o[6] * direction.z,
                    o[1] * direction.x + o[4] * direction.y + o[7] * direction.z,
@@ -472,7 +483,7 @@ int launchSVGF(gfx_ctx* ctx, cudaStream_t stream, const GfxFrameParams* params, 
         }
         { GFX_TIMED(ctx, stream, "svgf_atrous"); k_svgfATrous<<<grid, block, 0, stream>>>(s, p, stage); }
         break;
-    case GFX_SVGF_FILL_BACKGROUND: { GFX_TIMED(ctx, stream, "svgf_background"); k_svgfBackground<<<grid, block, 0, stream>>>(s, p, stage); } break;
+    case GFX_SVGF_FILL_BACKGROUND: { GFX_TIMED(ctx, stream, "svgf_background"); k_svgfBackground<<<grid, block, 0, stream>>>(s, p, stage, ctx->devScene(params).env); } break;
     case GFX_SVGF_MODULATE_TAA: { GFX_TIMED(ctx, stream, "svgf_modulate_taa"); k_svgfModulateTAA<<<grid, block, 0, stream>>>(s, p, stage); } break;
     default:
         ctx->setError("gfx_svgf_launch: unknown pass");

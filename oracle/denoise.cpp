@@ -399,7 +399,11 @@ void applyATrous(orc_svgf* s, const View &v, const GfxFrameParams* p, uint32_t f
         s->prevLighting[pix] = out;
 }
 
-// ---- fillBackground (svgf.cu:378-461), no environment texture ---------------------------
+extern "C" orc_scene* orc_frame_scene(orc_frame* f);
+extern "C" int orc_env_enabled(orc_scene* s, const GfxFrameParams* p);
+extern "C" int orc_env_query(orc_scene* s, int op, const float* in, uint32_t n, float* out);
+
+// ---- fillBackground (svgf.cu:378-461) -----------------------------------------------------
 void fillBackground(orc_svgf* s, const View &v, const GfxFrameParams* p, const Cam &cam, const Cam &prevCam,
                     uint32_t numFilteringStages, int x, int y) {
     const int W = (int)s->W, H = (int)s->H;
@@ -407,10 +411,23 @@ void fillBackground(orc_svgf* s, const View &v, const GfxFrameParams* p, const C
     const uint32_t curBufIdx = p->bufferIndex & 1;
     if (v.gb0[curBufIdx][pix].x != 0xFFFFFFFFu)
         return;
-    const float3 finalLighting(0.001f, 0.001f, 0.001f);
+    float3 finalLighting(0.001f, 0.001f, 0.001f);
     const float fx = (x + 0.5f) / W;
     const float fy = (y + 0.5f) / H;
     float3 direction = normalize(cam.orientation.mul(float3(cam.vw * (0.5f - fx), cam.vh * (0.5f - fy), 1)));
+    orc_scene* scene = orc_frame_scene(s->frame);
+    if (orc_env_enabled(scene, p)) { // :431-437; the sub-pixel offset is the pixel centre (no TAA jitter in this host)
+        float posPhi, posTheta;
+        toPolarYUp(direction, &posPhi, &posTheta);
+        float phi = posPhi + p->envLightRotation;
+        phi += p->envLightRotation; // as written in the reference (:418-420): added twice when the environment light is on
+        float u = phi / (2 * kPi);
+        u -= std::floor(u);
+        const float uv[2] = { u, posTheta / kPi };
+        float rgb[3];
+        orc_env_query(scene, 2, uv, 1, rgb);
+        finalLighting = p->envLightPowerCoeff * float3(rgb[0], rgb[1], rgb[2]);
+    }
     // transpose(prevCamera.orientation) * direction
     const float* o = prevCam.orientation.m;
     direction = float3(o[0] * direction.x + o[3] * direction.y + o[6] * direction.z,

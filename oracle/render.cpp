@@ -216,6 +216,7 @@ extern "C" int orc_scene_update_instances(orc_scene* s, const GfxInstanceDesc* i
     return 0;
 }
 extern "C" void orc_scene_destroy(orc_scene* s) { delete s; }
+extern "C" int orc_env_enabled(orc_scene* s, const GfxFrameParams* p) { return useEnvLight(s, p) ? 1 : 0; }
 // test hooks of the environment light: op 0 = importance-map sample (u0, u1) -> (u, v, uvPDF), 1 = evaluatePDF(u, v) -> pdf,
 // 2 = texture fetch (u, v) -> rgb; `in` holds n pairs, `out` n triples
 extern "C" int orc_env_query(orc_scene* s, int op, const float* in, uint32_t n, float* out) {
@@ -449,6 +450,8 @@ struct orc_frame {
     struct orc_rearch* rearch = nullptr; // rearchitected ReSTIR state (restir_rearch.inl)
 };
 
+// the SVGF restatement (denoise.cpp, another translation unit) shows the environment behind miss pixels
+extern "C" orc_scene* orc_frame_scene(orc_frame* f) { return f->scene; }
 extern "C" orc_frame* orc_frame_create(orc_scene* s, uint32_t W, uint32_t H) {
     orc_frame* f = new orc_frame();
     f->scene = s;
