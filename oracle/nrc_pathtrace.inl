@@ -74,6 +74,15 @@ struct orc_nrc_frame {
     uint32_t state[NRC_STATE_WORDS];
     std::vector<NrcPathState> paths;
     std::vector<NrcStagedVertex> staged;
+    // strip sharding over ranks, the restatement of gfx_nrc_shard for the gloo tests of the host logic (tests/test_multigpu_cpu.py):
+    // every rank traces its rows; per commit round the ranks exchange (vertex count, any path still active), which makes the
+    // record numbering - tile order = rank order, then local tile order - that of the unsharded frame; after the propagation
+    // the records are merged by an unsigned integer sum over zero-initialised arrays.  The collectives are the caller's.
+    int shardRank = 0, shardWorld = 1;
+    void (*shardExchange)(void* user, const uint32_t* mine, uint32_t numWords, uint32_t* all) = nullptr;
+    void (*shardSum)(void* user, uint32_t* words, uint64_t numWords) = nullptr;
+    void* shardUser = nullptr;
+    bool sharded() const { return shardWorld > 1 && shardExchange && shardSum; }
 };
 
 static orc_nrc_frame* nrcFrame(orc_frame* f) {
@@ -173,9 +182,24 @@ static inline uint32_t packSuffixTerminal(uint32_t prev, bool hasQuery, uint32_t
 }
 
 // nrc_setup_kernels.cu:6-49
+extern "C" void orc_nrc_set_shard(orc_frame* f, int rank, int world,
+                                  void (*exchange)(void*, const uint32_t*, uint32_t, uint32_t*),
+                                  void (*sum)(void*, uint32_t*, uint64_t), void* user) {
+    orc_nrc_frame* n = nrcFrame(f);
+    n->shardRank = rank;
+    n->shardWorld = world;
+    n->shardExchange = exchange;
+    n->shardSum = sum;
+    n->shardUser = user;
+}
+
 extern "C" void orc_nrc_preprocess(orc_frame* f, const GfxFrameParams* p, uint32_t offsetToSelectUnbiasedTile,
                                    uint32_t offsetToSelectTrainingPath, int isNewSequence) {
     orc_nrc_frame* n = nrcFrame(f);
+    if (n->sharded()) { // the ranks' records are merged by an integer sum after the propagation: start from zero
+        std::fill(n->trainQuery[0].begin(), n->trainQuery[0].end(), 0.0f);
+        std::fill(n->trainTarget[0].begin(), n->trainTarget[0].end(), 0.0f);
+    }
     const uint32_t bufIdx = p->bufferIndex & 1, prevBufIdx = (bufIdx + 1) % 2;
     uint32_t newTileSize[2];
     if (isNewSequence) {
@@ -435,17 +459,38 @@ static void nrcExtend(orc_frame* f, orc_nrc_frame* n, const GfxFrameParams* p, s
     }
 }
 
-// numbers the training vertices staged in this round in tile order (:213-248, :568-617)
-static void nrcCommitStagedVertices(orc_frame* f, orc_nrc_frame* n, const GfxFrameParams* p, const std::vector<uint32_t> &tileToPixel) {
+// numbers the training vertices staged in this round in tile order (:213-248, :568-617); returns whether any path of any rank
+// is still active (`localActive` is this rank's answer)
+static bool nrcCommitStagedVertices(orc_frame* f, orc_nrc_frame* n, const GfxFrameParams* p, const std::vector<uint32_t> &tileToPixel,
+                                    bool localActive = false) {
     const uint32_t bufIdx = p->bufferIndex & 1;
     const size_t offset = (size_t)f->W * f->H;
+    uint32_t next = n->state[NRC_NUM_TRAINING_DATA + bufIdx];
+    uint32_t counterAfter = 0;
+    bool anyActive = localActive;
+    if (n->sharded()) {
+        uint32_t mine[2] = { 0u, localActive ? 1u : 0u };
+        for (uint32_t tile = 0; tile < (uint32_t)tileToPixel.size(); ++tile)
+            mine[0] += n->staged[tile].want ? 1u : 0u;
+        std::vector<uint32_t> all(2 * (size_t)n->shardWorld);
+        n->shardExchange(n->shardUser, mine, 2, all.data());
+        uint32_t total = 0;
+        anyActive = false;
+        for (int r = 0; r < n->shardWorld; ++r) {
+            if (r < n->shardRank)
+                next += all[2 * r];
+            total += all[2 * r];
+            anyActive = anyActive || all[2 * r + 1] != 0;
+        }
+        counterAfter = n->state[NRC_NUM_TRAINING_DATA + bufIdx] + total;
+    }
     for (uint32_t tile = 0; tile < (uint32_t)tileToPixel.size(); ++tile) {
         NrcStagedVertex &sv = n->staged[tile];
         if (!sv.want)
             continue;
         sv.want = false;
         NrcPathState &st = n->paths[tileToPixel[tile]];
-        const uint32_t trainDataIndex = n->state[NRC_NUM_TRAINING_DATA + bufIdx]++;
+        const uint32_t trainDataIndex = next++;
         if (trainDataIndex < kTrainBufferSize) {
             std::memcpy(&n->trainQuery[0][14 * (size_t)trainDataIndex], sv.query, sizeof(sv.query));
             uint32_t* vi = &n->trainVertexInfo[4 * (size_t)trainDataIndex];
@@ -464,6 +509,8 @@ static void nrcCommitStagedVertices(orc_frame* f, orc_nrc_frame* n, const GfxFra
             st.trainingSuffixEndsWithCache = true;
         }
     }
+    n->state[NRC_NUM_TRAINING_DATA + bufIdx] = n->sharded() ? counterAfter : next;
+    return anyActive;
 }
 
 static uint64_t nrcPathTrace(orc_frame* f, const GfxFrameParams* p, int numThreads) {
@@ -477,9 +524,14 @@ static uint64_t nrcPathTrace(orc_frame* f, const GfxFrameParams* p, int numThrea
     for (auto &sv : n->staged)
         sv.want = false;
 
+    // a strip of rows (tileOriginY / tileRows) is one rank's share of a sharded frame
+    const uint32_t y0 = p->tileOriginY, y1 = p->tileRows ? std::min(H, p->tileOriginY + p->tileRows) : H;
+    for (size_t pix = 0; pix < (size_t)W * H; ++pix)
+        if (pix < (size_t)y0 * W || pix >= (size_t)y1 * W)
+            n->paths[pix].active = false;
     uint64_t rays = 0;
 #pragma omp parallel for schedule(dynamic, 2) num_threads(numThreads) reduction(+ : rays)
-    for (int64_t y = 0; y < (int64_t)H; ++y) {
+    for (int64_t y = y0; y < (int64_t)y1; ++y) {
         PathTraceCounters counters;
         for (uint32_t x = 0; x < W; ++x) {
             nrcRayGen(f, n, p, camera, x, (uint32_t)y, &counters);
@@ -494,7 +546,7 @@ static uint64_t nrcPathTrace(orc_frame* f, const GfxFrameParams* p, int numThrea
     for (uint32_t round = 0; round < kMaxNrcRounds; ++round) {
         uint64_t numActive = 0;
 #pragma omp parallel for schedule(dynamic, 2) num_threads(numThreads) reduction(+ : rays, numActive)
-        for (int64_t y = 0; y < (int64_t)H; ++y) {
+        for (int64_t y = y0; y < (int64_t)y1; ++y) {
             PathTraceCounters counters;
             for (uint32_t x = 0; x < W; ++x) {
                 const size_t pix = (size_t)y * W + x;
@@ -505,13 +557,12 @@ static uint64_t nrcPathTrace(orc_frame* f, const GfxFrameParams* p, int numThrea
             }
             rays += counters.closestRays + counters.visibilityRays;
         }
-        nrcCommitStagedVertices(f, n, p, tileToPixel);
-        if (numActive == 0)
+        if (!nrcCommitStagedVertices(f, n, p, tileToPixel, numActive != 0))
             break;
     }
 
     // ray-gen epilogue (:312-360)
-    for (size_t pix = 0; pix < (size_t)W * H; ++pix) {
+    for (size_t pix = (size_t)y0 * W; pix < (size_t)y1 * W; ++pix) {
         const NrcPathState &st = n->paths[pix];
         if (f->gb0[bufIdx][pix].instSlot != 0xFFFFFFFFu) {
             f->rng[pix] = st.rng.state;
@@ -530,8 +581,8 @@ static uint64_t nrcPathTrace(orc_frame* f, const GfxFrameParams* p, int numThrea
 // nrc_setup_kernels.cu:51-92
 extern "C" void orc_nrc_accumulate(orc_frame* f, const GfxFrameParams* p) {
     orc_nrc_frame* n = nrcFrame(f);
-    const size_t numPixels = (size_t)f->W * f->H;
-    for (size_t i = 0; i < numPixels; ++i) {
+    const uint32_t y0 = p->tileOriginY, y1 = p->tileRows ? std::min(f->H, p->tileOriginY + p->tileRows) : f->H;
+    for (size_t i = (size_t)y0 * f->W; i < (size_t)y1 * f->W; ++i) {
         const uint32_t* t = &n->terminalInfo[4 * i];
         const float3 alpha(u2f(t[0]), u2f(t[1]), u2f(t[2]));
         const bool hasQuery = t[3] & 1u;
@@ -587,6 +638,10 @@ extern "C" void orc_nrc_propagate(orc_frame* f, const GfxFrameParams* p) {
             tgt[2] = refFactor.z != 0 ? contribution.z / refFactor.z : 0.0f;
             last = vi[3] & 0x7FFFFFu;
         }
+    }
+    if (n->sharded()) { // all records on all ranks: every record is non-zero on one rank only, the integer sum keeps its bits
+        n->shardSum(n->shardUser, reinterpret_cast<uint32_t*>(n->trainQuery[0].data()), n->trainQuery[0].size());
+        n->shardSum(n->shardUser, reinterpret_cast<uint32_t*>(n->trainTarget[0].data()), n->trainTarget[0].size());
     }
 }
 

@@ -87,6 +87,10 @@ void orc_regir_update_access(orc_frame* f, const GfxFrameParams* p, uint32_t fra
  * propagateRadianceValues, shuffleTrainingData; buffers via orc_buffer_ptr(GFX_BUF_NRC_*) */
 void orc_nrc_preprocess(orc_frame* f, const GfxFrameParams* p, uint32_t offsetToSelectUnbiasedTile,
                         uint32_t offsetToSelectTrainingPath, int isNewSequence);
+/* strip sharding of the NRC frame over ranks (the oracle's restatement of gfx_nrc_shard, for the gloo tests of the host logic):
+ * `exchange` all-gathers numWords words per rank, `sum` all-reduces an unsigned 32-bit array in place; world <= 1 switches it off */
+void orc_nrc_set_shard(orc_frame* f, int rank, int world, void (*exchange)(void* user, const uint32_t* mine, uint32_t numWords, uint32_t* all),
+                       void (*sum)(void* user, uint32_t* words, uint64_t numWords), void* user);
 void orc_nrc_accumulate(orc_frame* f, const GfxFrameParams* p);
 void orc_nrc_propagate(orc_frame* f, const GfxFrameParams* p);
 void orc_nrc_shuffle(orc_frame* f, const GfxFrameParams* p);

@@ -45,6 +45,10 @@ def build_oracle(force: bool = False) -> str:
 _lib = None
 
 
+NRC_EXCHANGE_FN = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(C.c_uint32))
+NRC_SUM_FN = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_uint32), C.c_uint64)
+
+
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
@@ -82,6 +86,7 @@ def lib() -> C.CDLL:
         L.orc_regir_build_cells.argtypes = [vp, C.POINTER(abi.GfxFrameParams), C.c_uint32, C.c_int, C.c_int]
         L.orc_regir_update_access.argtypes = [vp, C.POINTER(abi.GfxFrameParams), C.c_uint32]
         L.orc_nrc_preprocess.argtypes = [vp, C.POINTER(abi.GfxFrameParams), C.c_uint32, C.c_uint32, C.c_int]
+        L.orc_nrc_set_shard.argtypes = [vp, C.c_int, C.c_int, NRC_EXCHANGE_FN, NRC_SUM_FN, vp]
         for name in ("orc_nrc_accumulate", "orc_nrc_propagate", "orc_nrc_shuffle"):
             getattr(L, name).argtypes = [vp, C.POINTER(abi.GfxFrameParams)]
         L.orc_generate_primary_rays.argtypes = [C.POINTER(abi.GfxFrameParams), C.c_uint32, C.c_uint32, vp]
@@ -261,6 +266,27 @@ class OracleFrame:
 
     def regir_update_access(self, params, frame_index: int):
         lib().orc_regir_update_access(self.h, C.byref(params), frame_index & 0xFFFFFFFF)
+
+    def nrc_shard(self, rank: int, world: int):
+        """the oracle's gfx_nrc_shard: the two collectives go through the default torch.distributed group (gloo in the CPU tests)"""
+        import torch
+        import torch.distributed as dist
+
+        def exchange(_user, mine, num_words, out):
+            t = torch.tensor([mine[i] for i in range(num_words)], dtype=torch.int64)
+            gathered = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(gathered, t)
+            for r in range(world):
+                for i in range(num_words):
+                    out[r * num_words + i] = int(gathered[r][i])
+
+        def total(_user, words, num_words):
+            a = np.ctypeslib.as_array(words, shape=(num_words,))
+            t = torch.from_numpy(a.astype(np.int64))  # every word is non-zero on one rank only: the sum fits 32 bits again
+            dist.all_reduce(t)
+            a[:] = t.numpy().astype(np.uint32)
+        self._shard_callbacks = (NRC_EXCHANGE_FN(exchange), NRC_SUM_FN(total))  # keep the thunks alive
+        lib().orc_nrc_set_shard(self.h, rank, world, self._shard_callbacks[0], self._shard_callbacks[1], None)
 
     def nrc_preprocess(self, params, offset_unbiased_tile: int, offset_training_path: int, new_sequence: bool):
         lib().orc_nrc_preprocess(self.h, C.byref(params), offset_unbiased_tile, offset_training_path, 1 if new_sequence else 0)

@@ -200,3 +200,104 @@ def test_strip_partition_rejects_ragged_heights():
     p = abi.default_frame_params(scene, 64, 64)
     with pytest.raises(ValueError):     # 16 rows per rank < 24 halo rows: a seam would have to cross two ranks
         multigpu.StripDriver(Dummy(), p, 64, 64, 0, 4)
+
+
+# ---- the NRC frame sharded by strips (the oracle's restatement of gfx_nrc_shard), world_size 2 over gloo ---------------------
+NRC_W, NRC_H, NRC_FRAMES = 64, 48, 3
+
+
+def _nrc_frame(O, oframe, onet, p, frame, rows=None):
+    """one NRC frame on the oracle (network included), on `rows` = (y0, y1) or the whole frame; the perFrameRng() draws are a
+    function of the frame index"""
+    from gfxexp_b200 import abi
+    rng = np.random.default_rng(500 + frame)
+    offsets = [int(rng.integers(0, 2 ** 32)) for _ in range(2)]
+    n = NRC_W * NRC_H
+    p.frameIndex, p.bufferIndex, p.numAccumFrames = frame, frame % 2, frame
+    p.tileOriginY, p.tileRows = 0, 0
+    oframe.gbuffer(p)
+    if rows is not None:
+        p.tileOriginY, p.tileRows = rows[0], rows[1] - rows[0]
+    oframe.nrc_preprocess(p, offsets[0], offsets[1], frame == 0)
+    oframe.pathtrace(p, abi.PT_NRC)
+    q = oframe.linear_buffer(abi.BUF_NRC_INFERENCE_QUERY)
+    ti = oframe.linear_buffer(abi.BUF_NRC_TERMINAL_INFO)
+    suffix = oframe.linear_buffer(abi.BUF_NRC_TRAIN_SUFFIX_TERMINAL)[:, 0]
+    lo, hi = (rows[0] * NRC_W, rows[1] * NRC_W) if rows is not None else (0, n)
+    pix = lo + np.flatnonzero((ti[lo:hi, 3] & 1).astype(bool))
+    sfx = n + np.flatnonzero(((suffix >> 23) & 1).astype(bool))
+    idx = np.concatenate([pix, sfx])
+    pred = oframe.linear_buffer(abi.BUF_NRC_INFERRED_RADIANCE, copy=False)
+    if len(idx):
+        pred[idx] = onet.infer(q[idx])
+    oframe.nrc_accumulate(p)
+    oframe.nrc_propagate(p)
+    oframe.nrc_shuffle(p)
+    tq, tt = oframe.linear_buffer(abi.BUF_NRC_TRAIN_QUERY, 1), oframe.linear_buffer(abi.BUF_NRC_TRAIN_TARGET, 1)
+    for step in range(4):
+        sl = slice(step * 16384, (step + 1) * 16384)
+        onet.train(tq[sl], tt[sl])
+    p.tileOriginY, p.tileRows = 0, 0
+
+
+def _nrc_setup():
+    from gfxexp_b200 import abi, engine, scenes
+    from tests import oracle_lib as O
+    scene = scenes.tiny_city_scene()
+    oframe = O.OracleFrame(O.OracleScene(scene), NRC_W, NRC_H)
+    onet = O.OracleNrc(2, 1e-2)
+    onet.set_params(engine.random_nrc_params(onet.num_params, onet.num_matrix_weights, grid_amplitude=0.1))
+    p = abi.default_frame_params(scene, NRC_W, NRC_H)
+    p.maxPathLength = 4
+    p.radianceScale = 2.0
+    return O, oframe, onet, p
+
+
+def _worker_nrc(rank, world, port, result_path):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from gfxexp_b200 import abi
+    O, oframe, onet, p = _nrc_setup()
+    oframe.nrc_shard(rank, world)
+    rows = (rank * NRC_H // world, (rank + 1) * NRC_H // world)
+    out = {}
+    for f in range(NRC_FRAMES):
+        _nrc_frame(O, oframe, onet, p, f, rows)
+        out[f"beauty{f}"] = oframe.buffer(abi.BUF_BEAUTY_ACCUM)[rows[0]:rows[1]].copy()
+        out[f"state{f}"] = oframe.linear_buffer(abi.BUF_NRC_STATE)[:8, 0].copy()
+        out[f"records{f}"] = oframe.linear_buffer(abi.BUF_NRC_TRAIN_QUERY, 0).copy()
+        out[f"targets{f}"] = oframe.linear_buffer(abi.BUF_NRC_TRAIN_TARGET, 0).copy()
+    out["weights"] = onet.get_master()
+    np.savez(result_path + f".{rank}.npz", **out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_nrc_strips_equal_single_process(tmp_path):
+    """the numbering of the training vertices over the ranks (one count per rank and commit round exchanged), the merge of the
+    records and the replicated training reproduce the unsharded frame bit for bit: images, counters and tile sizes, all
+    records, the trained weights of both ranks"""
+    from gfxexp_b200 import abi
+    result = str(tmp_path / "nrc")
+    mp.spawn(_worker_nrc, args=(2, _free_port(), result), nprocs=2, join=True)
+    O, oframe, onet, p = _nrc_setup()
+    got = [np.load(result + f".{r}.npz") for r in range(2)]
+    for f in range(NRC_FRAMES):
+        _nrc_frame(O, oframe, onet, p, f)
+        st = oframe.linear_buffer(abi.BUF_NRC_STATE)[:8, 0]
+        ntrain = min(int(st[f % 2]), abi.NRC_TRAIN_BUFFER_SIZE)
+        assert ntrain > 30, "vacuous: no training vertices"
+        beauty = oframe.buffer(abi.BUF_BEAUTY_ACCUM)
+        for r in range(2):
+            rows = slice(r * NRC_H // 2, (r + 1) * NRC_H // 2)
+            assert np.array_equal(got[r][f"beauty{f}"].view(np.uint32), beauty[rows].view(np.uint32)), f"frame {f} rank {r}: image"
+            assert np.array_equal(got[r][f"state{f}"], st), f"frame {f} rank {r}: counters / tile sizes"
+            assert np.array_equal(got[r][f"records{f}"][:ntrain].view(np.uint32),
+                                  oframe.linear_buffer(abi.BUF_NRC_TRAIN_QUERY, 0)[:ntrain].view(np.uint32)), f"frame {f} rank {r}: records"
+            assert np.array_equal(got[r][f"targets{f}"][:ntrain].view(np.uint32),
+                                  oframe.linear_buffer(abi.BUF_NRC_TRAIN_TARGET, 0)[:ntrain].view(np.uint32)), f"frame {f} rank {r}: targets"
+    want = onet.get_master()
+    for r in range(2):
+        assert np.array_equal(got[r]["weights"].view(np.uint32), want.view(np.uint32)), f"rank {r}: trained weights"
