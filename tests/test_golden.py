@@ -51,6 +51,20 @@ def test_oracle_reproduces_extra_golden(oracle):
         assert GX.digest(arr) == want[name], f"{name} differs from its golden digest"
 
 
+def test_oracle_reproduces_r02_golden(oracle):
+    """environment light, image textures, ingestion (round 2): CPU-only digests, see make_golden_r02.py"""
+    from tests.golden import make_golden_r02 as G2
+    want = {}
+    with open(os.path.join(GOLDEN_DIR, "golden_r02.sha256")) as f:
+        for line in f:
+            h, name = line.split()[:2]
+            want[name] = h
+    got = G2.run_all()
+    assert set(got) == set(want)
+    for name, arr in got.items():
+        assert G2.digest(arr) == want[name], f"{name} differs from its golden digest"
+
+
 class _GpuBackend:
     def __init__(self, ctx, scene):
         self.ctx, self.scene = ctx, scene
