@@ -19,7 +19,9 @@ peak; `cpu_baseline` = the oracle on the host cores on a bounded sample of the s
 line also carries the rest of BASELINE.json's metric, measured in the same process on the same scene:
 `nrc` (inference / training ms, TFLOP/s, fraction of the measured sustained bf16 tensor peak),
 `north_star_frame` (ReSTIR DI + NRC in one 1080p frame: ms, fps) and `svgf` (config 4: ms per frame,
-algorithmic GB/s, fraction of the measured HBM peak).
+algorithmic GB/s, fraction of the measured HBM peak).  At every N the line carries `config5`: BASELINE.json's fifth
+config - ReSTIR DI + NRC in one 3840x2160 frame, strips over the N ranks, the NRC half sharded with its training
+data kept identical to one GPU (gfx_nrc_shard) - with ms, fps, Mrays/s and rank 0's per-kernel times.
 """
 from __future__ import annotations
 
